@@ -1,0 +1,391 @@
+"""ctypes binding of include/ipx.h and include/ipx_io.h.  No computation happens here."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "csrc", "build")
+LIBIPX = os.path.join(BUILD, "libipx.so")
+LIBIPX_IO = os.path.join(BUILD, "libipx_io.so")
+CLI_EXTRACT = os.path.join(BUILD, "intronProspector")
+CLI_MERGE = os.path.join(BUILD, "intronProspectorMerge")
+
+IPX_OK = 0
+FILTER_NULL, FILTER_ALL, FILTER_CANON = 0, 1, 2
+STRAND_UN, STRAND_RF, STRAND_FR = 0, 1, 2
+FMT_JUNCTION_BED, FMT_INTRON_BED9, FMT_INTRON_BED6, FMT_INTRON_TSV = 0, 1, 2, 3
+
+
+class IpxError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("min_anchor_length", C.c_uint32),
+        ("max_anchor_indel_size", C.c_uint32),
+        ("min_intron_length", C.c_uint32),
+        ("max_intron_length", C.c_uint32),
+        ("junction_filter", C.c_int32),
+        ("strandness", C.c_int32),
+        ("excludes", C.c_uint32),
+        ("skip_missing_targets", C.c_int32),
+        ("device", C.c_int32),
+        ("profile", C.c_int32),
+        ("stream", C.c_void_p),
+        ("table_capacity", C.c_uint64),
+        ("hist_capacity", C.c_uint64),
+    ]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("n_records", C.c_uint64),
+        ("n_cigar", C.c_uint64),
+        ("seq_base", C.c_uint64),
+        ("tid", C.c_void_p),
+        ("pos", C.c_void_p),
+        ("flag", C.c_void_p),
+        ("nh_class", C.c_void_p),
+        ("xs", C.c_void_p),
+        ("cigar_off", C.c_void_p),
+        ("cigar", C.c_void_p),
+    ]
+
+
+class TableStruct(C.Structure):
+    _fields_ = [
+        ("n_junctions", C.c_uint64),
+        ("chrom", C.POINTER(C.c_int32)),
+        ("intron_start", C.POINTER(C.c_uint32)),
+        ("intron_end", C.POINTER(C.c_uint32)),
+        ("anchor_start", C.POINTER(C.c_uint32)),
+        ("anchor_end", C.POINTER(C.c_uint32)),
+        ("strand", C.POINTER(C.c_char)),
+        ("splice_sites", C.POINTER(C.c_char)),
+        ("read_counts", C.POINTER(C.c_uint64)),
+        ("ijunc", C.POINTER(C.c_uint32)),
+        ("confidence", C.POINTER(C.c_float)),
+        ("hist_off", C.POINTER(C.c_uint64)),
+        ("hist_cnt", C.POINTER(C.c_uint32)),
+        ("n_hist", C.c_uint64),
+        ("first_error_seq", C.c_uint64),
+        ("status", C.c_int32),
+        ("error_tid", C.c_int32),
+        ("error_text", C.c_char * 256),
+        ("missing_targets", C.POINTER(C.c_int32)),
+        ("n_missing_targets", C.c_uint64),
+    ]
+
+
+class Timings(C.Structure):
+    _fields_ = [
+        ("extract_ms", C.c_double),
+        ("aggregate_ms", C.c_double),
+        ("motif_ms", C.c_double),
+        ("finalize_ms", C.c_double),
+        ("merge_ms", C.c_double),
+        ("extract_launches", C.c_uint64),
+        ("aggregate_launches", C.c_uint64),
+        ("motif_launches", C.c_uint64),
+        ("finalize_launches", C.c_uint64),
+        ("merge_launches", C.c_uint64),
+        ("records", C.c_uint64),
+        ("cigar_live", C.c_uint64),
+        ("events", C.c_uint64),
+        ("junctions", C.c_uint64),
+        ("hist_runs", C.c_uint64),
+        ("motif_keys", C.c_uint64),
+        ("merge_rows", C.c_uint64),
+    ]
+
+
+class Text(C.Structure):
+    _fields_ = [("data", C.POINTER(C.c_char)), ("len", C.c_size_t)]
+
+
+class MergeRows(C.Structure):
+    _fields_ = [
+        ("n_rows", C.c_uint64),
+        ("chrom", C.c_void_p),
+        ("intron_start", C.c_void_p),
+        ("intron_end", C.c_void_p),
+        ("anchor_start", C.c_void_p),
+        ("anchor_end", C.c_void_p),
+        ("strand", C.c_void_p),
+        ("sites", C.c_void_p),
+        ("counts", C.c_void_p),
+        ("confidence", C.c_void_p),
+        ("site_strings", C.POINTER(C.c_char_p)),
+        ("n_site_strings", C.c_uint32),
+    ]
+
+
+ABI_SYMBOLS = [
+    "ipx_version", "ipx_abi_version", "ipx_device_count", "ipx_create", "ipx_destroy", "ipx_last_error",
+    "ipx_set_targets", "ipx_set_genome", "ipx_push_batch", "ipx_push_batch_device", "ipx_finalize_device",
+    "ipx_flush", "ipx_table_free", "ipx_merge_rows_fold", "ipx_partial_row_bytes", "ipx_partial_sizes",
+    "ipx_partial_export", "ipx_partial_import", "ipx_format", "ipx_format_tsv_header", "ipx_text_free",
+    "ipx_get_timings", "ipx_reset_timings", "ipx_stream",
+]
+IO_SYMBOLS = [
+    "ipxio_last_error", "ipxio_open", "ipxio_close", "ipxio_n_targets", "ipxio_target_name", "ipxio_read_batch",
+    "ipxio_genome_load", "ipxio_genome_free", "ipxio_genome_n_seqs", "ipxio_genome_names", "ipxio_genome_lengths",
+    "ipxio_genome_seqs", "ipxio_faidx_build", "ipxio_calls_load", "ipxio_calls_free", "ipxio_calls_rows",
+    "ipxio_calls_n_chroms", "ipxio_calls_chroms",
+]
+
+_lib = None
+_io = None
+
+
+def _bind(lib):
+    lib.ipx_version.restype = C.c_char_p
+    lib.ipx_last_error.restype = C.c_char_p
+    lib.ipx_last_error.argtypes = [C.c_void_p]
+    lib.ipx_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
+    lib.ipx_destroy.argtypes = [C.c_void_p]
+    lib.ipx_destroy.restype = None
+    lib.ipx_set_targets.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p)]
+    lib.ipx_set_genome.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.POINTER(C.c_char_p)]
+    lib.ipx_push_batch.argtypes = [C.c_void_p, C.POINTER(Batch)]
+    lib.ipx_push_batch_device.argtypes = [C.c_void_p, C.POINTER(Batch)]
+    lib.ipx_finalize_device.argtypes = [C.c_void_p]
+    lib.ipx_flush.argtypes = [C.c_void_p, C.POINTER(C.POINTER(TableStruct))]
+    lib.ipx_table_free.argtypes = [C.POINTER(TableStruct)]
+    lib.ipx_table_free.restype = None
+    lib.ipx_merge_rows_fold.argtypes = [C.c_void_p, C.POINTER(MergeRows), C.POINTER(C.POINTER(TableStruct)), C.POINTER(Text)]
+    lib.ipx_format.argtypes = [C.POINTER(TableStruct), C.POINTER(C.c_char_p), C.c_int, C.c_float, C.c_uint64, C.c_uint64, C.POINTER(Text)]
+    lib.ipx_format_tsv_header.argtypes = [C.POINTER(Text)]
+    lib.ipx_text_free.argtypes = [C.POINTER(Text)]
+    lib.ipx_text_free.restype = None
+    lib.ipx_get_timings.argtypes = [C.c_void_p, C.POINTER(Timings)]
+    lib.ipx_reset_timings.argtypes = [C.c_void_p]
+    lib.ipx_stream.argtypes = [C.c_void_p]
+    lib.ipx_stream.restype = C.c_void_p
+    if not hasattr(lib, "ipx_partial_row_bytes"):
+        return  # the CPU oracle's facade (tests only) has no multi-GPU exchange
+    lib.ipx_partial_row_bytes.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.ipx_partial_sizes.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.ipx_partial_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ipx_partial_import.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+
+
+def load_library(path=None):
+    """Load the CUDA library.  Raises when it has not been built: there is no fallback implementation."""
+    global _lib
+    if _lib is None or path is not None:
+        p = path or LIBIPX
+        if not os.path.exists(p):
+            raise IpxError("%s not found: build it with `make -C intronprospector_b200/csrc` (needs nvcc, sm_100a)" % p)
+        lib = C.CDLL(p)
+        _bind(lib)
+        if path is not None:
+            return lib
+        _lib = lib
+    return _lib
+
+
+def load_io_library():
+    global _io
+    if _io is None:
+        if not os.path.exists(LIBIPX_IO):
+            raise IpxError("%s not found: build it with `make -C intronprospector_b200/csrc`" % LIBIPX_IO)
+        io = C.CDLL(LIBIPX_IO)
+        io.ipxio_last_error.restype = C.c_char_p
+        io.ipxio_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        io.ipxio_close.argtypes = [C.c_void_p]
+        io.ipxio_close.restype = None
+        io.ipxio_n_targets.argtypes = [C.c_void_p]
+        io.ipxio_target_name.argtypes = [C.c_void_p, C.c_int32]
+        io.ipxio_target_name.restype = C.c_char_p
+        io.ipxio_read_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64] + [C.c_void_p] * 7 + [C.POINTER(C.c_uint64)]
+        io.ipxio_read_batch.restype = C.c_int64
+        io.ipxio_genome_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        io.ipxio_genome_free.argtypes = [C.c_void_p]
+        io.ipxio_genome_free.restype = None
+        io.ipxio_genome_n_seqs.argtypes = [C.c_void_p]
+        io.ipxio_genome_names.argtypes = [C.c_void_p]
+        io.ipxio_genome_names.restype = C.POINTER(C.c_char_p)
+        io.ipxio_genome_lengths.argtypes = [C.c_void_p]
+        io.ipxio_genome_lengths.restype = C.POINTER(C.c_uint64)
+        io.ipxio_genome_seqs.argtypes = [C.c_void_p]
+        io.ipxio_genome_seqs.restype = C.POINTER(C.c_char_p)
+        io.ipxio_faidx_build.argtypes = [C.c_char_p]
+        io.ipxio_calls_load.argtypes = [C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        io.ipxio_calls_free.argtypes = [C.c_void_p]
+        io.ipxio_calls_free.restype = None
+        io.ipxio_calls_rows.argtypes = [C.c_void_p]
+        io.ipxio_calls_rows.restype = C.POINTER(MergeRows)
+        io.ipxio_calls_n_chroms.argtypes = [C.c_void_p]
+        io.ipxio_calls_chroms.argtypes = [C.c_void_p]
+        io.ipxio_calls_chroms.restype = C.POINTER(C.c_char_p)
+        _io = io
+    return _io
+
+
+def _arr(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).copy()
+
+
+class Table:
+    """Host copy of an ipx_table (numpy arrays), detached from the library's buffers."""
+
+    def __init__(self, lib, tp, names, free):
+        t = tp.contents
+        n = int(t.n_junctions)
+        self.n = n
+        self.names = list(names)
+        self.chrom = _arr(t.chrom, n, np.int32)
+        self.intron_start = _arr(t.intron_start, n, np.uint32)
+        self.intron_end = _arr(t.intron_end, n, np.uint32)
+        self.anchor_start = _arr(t.anchor_start, n, np.uint32)
+        self.anchor_end = _arr(t.anchor_end, n, np.uint32)
+        self.strand = _arr(C.cast(t.strand, C.POINTER(C.c_uint8)), n, np.uint8)
+        self.splice_sites = _arr(C.cast(t.splice_sites, C.POINTER(C.c_uint8)), n * 8, np.uint8).reshape(n, 8)
+        self.read_counts = _arr(t.read_counts, n * 3, np.uint64).reshape(n, 3)
+        self.ijunc = _arr(t.ijunc, n, np.uint32)
+        self.confidence = _arr(t.confidence, n, np.float32)
+        self.hist_off = _arr(t.hist_off, n + 1, np.uint64)
+        self.hist_cnt = _arr(t.hist_cnt, int(t.n_hist), np.uint32)
+        self.status = int(t.status)
+        self.first_error_seq = int(t.first_error_seq)
+        self.error_tid = int(t.error_tid)
+        self.error_text = t.error_text.decode(errors="replace")
+        self.missing_targets = _arr(t.missing_targets, int(t.n_missing_targets), np.int32)
+        # text through the library's own formatter, while the native table is still alive
+        cnames = (C.c_char_p * max(1, len(names)))(*[s.encode() for s in names])
+        self._text = {}
+        for fmt in (FMT_JUNCTION_BED, FMT_INTRON_BED9, FMT_INTRON_BED6, FMT_INTRON_TSV):
+            for minc in (0.0, 1.0):
+                txt = Text()
+                rc = lib.ipx_format(tp, cnames, fmt, minc, 0, n, C.byref(txt))
+                if rc != IPX_OK:
+                    raise IpxError("ipx_format failed: %d" % rc)
+                self._text[(fmt, minc)] = C.string_at(txt.data, txt.len) if txt.len else b""
+                lib.ipx_text_free(C.byref(txt))
+        free(tp)
+
+    def text(self, fmt, min_confidence=0.0):
+        return self._text[(fmt, float(min_confidence))]
+
+    def columns(self):
+        return dict(chrom=self.chrom, intron_start=self.intron_start, intron_end=self.intron_end,
+                    anchor_start=self.anchor_start, anchor_end=self.anchor_end, strand=self.strand,
+                    splice_sites=self.splice_sites, read_counts=self.read_counts, ijunc=self.ijunc,
+                    confidence=self.confidence, hist_off=self.hist_off, hist_cnt=self.hist_cnt)
+
+
+class Engine:
+    """One ipx_handle.  `lib` lets tests drive the CPU oracle's ABI facade through the same code."""
+
+    def __init__(self, lib=None, device=0, stream=None, profile=False, **kw):
+        self.lib = lib or load_library()
+        p = Params()
+        p.min_anchor_length = kw.pop("min_anchor_length", 8)
+        p.max_anchor_indel_size = kw.pop("max_anchor_indel_size", 0)
+        p.min_intron_length = kw.pop("min_intron_length", 70)
+        p.max_intron_length = kw.pop("max_intron_length", 500000)
+        p.junction_filter = kw.pop("junction_filter", FILTER_NULL)
+        p.strandness = kw.pop("strandness", STRAND_UN)
+        p.excludes = kw.pop("excludes", 0)
+        p.skip_missing_targets = int(kw.pop("skip_missing_targets", False))
+        p.device = device
+        p.profile = int(profile)
+        p.stream = stream
+        p.table_capacity = kw.pop("table_capacity", 0)
+        p.hist_capacity = kw.pop("hist_capacity", 0)
+        if kw:
+            raise TypeError("unknown parameters: %s" % sorted(kw))
+        self.params = p
+        self.h = C.c_void_p()
+        rc = self.lib.ipx_create(C.byref(p), C.byref(self.h))
+        if rc != IPX_OK:
+            raise IpxError("ipx_create failed (%d): no usable CUDA device; there is no CPU fallback" % rc)
+        self.names = []
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.lib.ipx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != IPX_OK:
+            raise IpxError("%s (code %d)" % (self.lib.ipx_last_error(self.h).decode(errors="replace"), rc))
+
+    def set_targets(self, names):
+        self.names = list(names)
+        arr = (C.c_char_p * max(1, len(names)))(*[s.encode() for s in names])
+        self._check(self.lib.ipx_set_targets(self.h, len(names), arr))
+
+    def set_genome(self, names, seqs):
+        n = len(names)
+        cn = (C.c_char_p * max(1, n))(*[s.encode() for s in names])
+        bufs = [s if isinstance(s, bytes) else s.encode() for s in seqs]
+        cs = (C.c_char_p * max(1, n))(*bufs)
+        lens = (C.c_uint64 * max(1, n))(*[len(b) for b in bufs])
+        self._check(self.lib.ipx_set_genome(self.h, n, cn, lens, cs))
+
+    @staticmethod
+    def _ptr(a):
+        if hasattr(a, "data_ptr"):
+            return a.data_ptr()
+        return a.ctypes.data
+
+    def make_batch(self, cols, seq_base=0):
+        b = Batch()
+        b.n_records = int(cols["tid"].shape[0])
+        b.n_cigar = int(cols["cigar"].shape[0])
+        b.seq_base = seq_base
+        for k in ("tid", "pos", "flag", "nh_class", "xs", "cigar_off", "cigar"):
+            setattr(b, k, self._ptr(cols[k]))
+        return b
+
+    def push(self, cols, seq_base=0):
+        """cols: dict of numpy arrays (host) with the ipx_batch columns."""
+        b = self.make_batch(cols, seq_base)
+        self._keep = [cols]
+        self._check(self.lib.ipx_push_batch(self.h, C.byref(b)))
+
+    def push_device(self, cols, seq_base=0):
+        """cols: dict of torch CUDA tensors."""
+        b = self.make_batch(cols, seq_base)
+        self._check(self.lib.ipx_push_batch_device(self.h, C.byref(b)))
+
+    def finalize_device(self):
+        self._check(self.lib.ipx_finalize_device(self.h))
+
+    def flush(self):
+        tp = C.POINTER(TableStruct)()
+        self._check(self.lib.ipx_flush(self.h, C.byref(tp)))
+        return Table(self.lib, tp, self.names, self.lib.ipx_table_free)
+
+    def merge_rows(self, rows_ptr):
+        tp = C.POINTER(TableStruct)()
+        log = Text()
+        rc = self.lib.ipx_merge_rows_fold(self.h, rows_ptr, C.byref(tp), C.byref(log))
+        text = C.string_at(log.data, log.len) if log.len else b""
+        self.lib.ipx_text_free(C.byref(log))
+        self._check(rc)
+        return Table(self.lib, tp, self.names, self.lib.ipx_table_free), text
+
+    def timings(self):
+        t = Timings()
+        self._check(self.lib.ipx_get_timings(self.h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in Timings._fields_}
+
+    def reset_timings(self):
+        self._check(self.lib.ipx_reset_timings(self.h))
+
+    def stream(self):
+        return self.lib.ipx_stream(self.h)

@@ -1,0 +1,468 @@
+/* intronProspector.cc -- drop-in command line tool: same options, defaults, run modes, outputs and error
+ * text as the reference's intronProspector (src/intronProspector.cc), with junction extraction and
+ * aggregation running on a B200 behind the C ABI of include/ipx.h.
+ *
+ * This file is the host side of the boundary: option parsing (intronProspector.cc:131-300), the three run
+ * modes and their record-selection rules (intronProspector.cc:356-401, junctions_extractor.cc:620-683), and
+ * writing the formatted text.  It contains no junction arithmetic.
+ */
+#include <getopt.h>
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "cli_common.h"
+#include "genome_loader.h"
+#include "htslib/sam.h"
+#include "ipx.h"
+#include "record_source.h"
+
+using namespace std;
+
+static const char *usage_msg =
+    "intronProspector [options] [readaligns ...]\n"
+    "\n"
+    "Find putative intron junctions in RNA-Seq alignments (SAM/BAM).  With no input file, or '/dev/stdin',\n"
+    "reads standard input.  Junction extraction runs on an NVIDIA B200 GPU.\n"
+    "\n"
+    "Options:\n"
+    "  -h, --help                        print this message\n"
+    "  -v, --version                     print version\n"
+    "  -u, --unsorted                    input is not coordinate sorted (uses more memory)\n"
+    "  -a, --min-anchor-length=N         minimum anchor length on each side of an intron [8]\n"
+    "  -i, --min-intron-length=N         minimum intron length [70]\n"
+    "  -I, --max-intron-length=N         maximum intron length [500000]\n"
+    "      --allow-anchor-indels         allow indels in anchors\n"
+    "      --max-anchor-indel-size=N     maximum indel size in anchors, with --allow-anchor-indels [36]\n"
+    "  -C, --min-confidence-score=X      minimum Shannon-Wiener confidence score to report [1.0]\n"
+    "  -s, --strandness=UN|RF|FR         library strandness [UN]\n"
+    "  -X, --excludes=multi              exclude a category of reads\n"
+    "  -g, --genome-fasta=FASTA          genome (with .fai) to get splice sites; defaults --sj-filter to canon\n"
+    "  -f, --sj-filter=all|canon         splice junction filter\n"
+    "      --skip-missing-targets        warn rather than fail for targets missing from the genome\n"
+    "  -j, --junction-bed=FILE           junction BED12 output\n"
+    "  -n, --intron-bed=FILE             intron BED9 output\n"
+    "  -b, --intron-bed6=FILE            intron BED6 output\n"
+    "  -c, --intron-calls=FILE           intron calls TSV output\n"
+    "  -p, --pass-through=FILE           copy alignments to this file\n"
+    "  -D, --debug-trace=FILE            per-read trace TSV\n"
+    "      --set-XS-strand-tag           set XS:A on pass-through records from the observed introns\n"
+    "      --set-TS-strand-tag           set TS:A on pass-through records from the observed introns\n"
+    "Output files ending in .gz are gzip compressed.\n";
+
+static void usage() {
+    cerr << usage_msg;
+    exit(0);
+}
+
+/* CmdParser (intronProspector.cc:104-300) */
+struct Options {
+    vector<string> bam_files;
+    uint32_t min_anchor_length = 8;
+    uint32_t min_intron_length = 70;
+    uint32_t max_intron_length = 500000;
+    bool allow_anchor_indels = false;
+    bool unsorted = false; /* uninitialised in the reference (intronProspector.cc:131-143); false is what its tests assume */
+    uint32_t max_anchor_indel_size = 36;
+    float min_confidence_score = 1.0;
+    int junction_filter = IPX_FILTER_NULL;
+    int strandness = IPX_STRAND_UN;
+    unsigned excludes = 0;
+    string genome_fa;
+    bool skip_missing_targets = false;
+    string junction_bed, intron_bed, intron_bed6, intron_call_tsv, bam_pass_through, debug_trace_tsv;
+    bool set_XS_strand_tag = false, set_TS_strand_tag = false;
+};
+
+static int parse_strandness(const string &s) {
+    string su(s);
+    transform(su.begin(), su.end(), su.begin(), ::toupper);
+    if (su == "UN") return IPX_STRAND_UN;
+    if (su == "RF") return IPX_STRAND_RF;
+    if (su == "FR") return IPX_STRAND_FR;
+    cerr << "Error: invalid strandness value '" + s + "', expected one of 'UN', 'RF', or 'FR' (case insensitive)" << endl;
+    exit(1);
+}
+
+static unsigned parse_exclude_cat(const string &cat) {
+    if (cat == "multi") return IPX_EXCLUDE_MULTI;
+    cerr << "Error: invalid exclude category '" << cat << "', expected one of: 'multi'" << endl;
+    exit(1);
+}
+
+static int parse_filter(const string &spec) {
+    if (spec == "all") return IPX_FILTER_ALL;
+    if (spec == "canon") return IPX_FILTER_CANON;
+    throw invalid_argument("invalid splice junction filter '" + spec + "', expected 'all' or 'canon'");
+}
+
+static void parse_options(int argc, char *argv[], Options &o) {
+    static const int OPT_SET_XS_STRAND_TAG = 256;
+    static const int OPT_SET_TS_STRAND_TAG = 257;
+    /* same tables as the reference (intronProspector.cc:159-185), including its quirks: -S takes an argument,
+     * --allow-anchor-indels / --max-anchor-indel-size have no short form, long options may be abbreviated */
+    struct option long_options[] = {{"help", no_argument, NULL, 'h'},
+                                    {"version", no_argument, NULL, 'v'},
+                                    {"unsorted", no_argument, NULL, 'u'},
+                                    {"min-anchor-length", required_argument, NULL, 'a'},
+                                    {"min-intron-length", required_argument, NULL, 'i'},
+                                    {"max-intron-length", required_argument, NULL, 'I'},
+                                    {"allow-anchor-indels", no_argument, NULL, 'd'},
+                                    {"max-anchor-indel-size", required_argument, NULL, 'm'},
+                                    {"min-confidence-score", required_argument, NULL, 'C'},
+                                    {"strandness", required_argument, NULL, 's'},
+                                    {"excludes", required_argument, NULL, 'X'},
+                                    {"genome-fasta", required_argument, NULL, 'g'},
+                                    {"sj-filter", required_argument, NULL, 'f'},
+                                    {"skip-missing-targets", no_argument, NULL, 'S'},
+                                    {"junction-bed", required_argument, NULL, 'j'},
+                                    {"intron-bed", required_argument, NULL, 'n'},
+                                    {"intron-bed6", required_argument, NULL, 'b'},
+                                    {"intron-calls", required_argument, NULL, 'c'},
+                                    {"pass-through", required_argument, NULL, 'p'},
+                                    {"debug-trace", required_argument, NULL, 'D'},
+                                    {"set-XS-strand-tag", no_argument, NULL, OPT_SET_XS_STRAND_TAG},
+                                    {"set-TS-strand-tag", no_argument, NULL, OPT_SET_TS_STRAND_TAG},
+                                    {NULL, 0, NULL, 0}};
+    const char *short_options = "hvua:i:I:C:s:X:g:S:j:n:b:c:p:D:f:";
+    int c;
+    while ((c = getopt_long(argc, argv, short_options, long_options, NULL)) != -1) {
+        switch (c) {
+            case 'a': o.min_anchor_length = atoi(optarg); break;
+            case 'u': o.unsorted = true; break;
+            case 'd': o.allow_anchor_indels = true; break;
+            case 'm': o.max_anchor_indel_size = cli_to_unsigned(optarg); break;
+            case 'i': o.min_intron_length = cli_to_unsigned(optarg); break;
+            case 'I': o.max_intron_length = cli_to_unsigned(optarg); break;
+            case 'C': o.min_confidence_score = cli_to_float(optarg); break;
+            case 's': o.strandness = parse_strandness(optarg); break;
+            case 'X': o.excludes |= parse_exclude_cat(optarg); break;
+            case 'g': o.genome_fa = string(optarg); break;
+            case 'f': o.junction_filter = parse_filter(string(optarg)); break;
+            case 'S': o.skip_missing_targets = true; break;
+            case 'j': o.junction_bed = optarg; break;
+            case 'n': o.intron_bed = optarg; break;
+            case 'b': o.intron_bed6 = optarg; break;
+            case 'c': o.intron_call_tsv = optarg; break;
+            case 'p': o.bam_pass_through = optarg; break;
+            case 'D': o.debug_trace_tsv = optarg; break;
+            case OPT_SET_XS_STRAND_TAG: o.set_XS_strand_tag = true; break;
+            case OPT_SET_TS_STRAND_TAG: o.set_TS_strand_tag = true; break;
+            case 'h': usage();
+            case 'v':
+                cerr << IPX_PACKAGE_NAME << " " << IPX_PACKAGE_VERSION << " " << IPX_PACKAGE_URL << endl;
+                exit(0);
+            case '?':
+            default: cmd_error("bug: option not handled");
+        }
+    }
+    while (optind < argc) o.bam_files.push_back(string(argv[optind++]));
+    if (o.bam_files.size() == 0) o.bam_files.push_back("/dev/stdin");
+    if ((o.bam_files.size() > 1) and (o.bam_pass_through != "")) cmd_error("can only have one input BAM with --bam-pass-through");
+    if ((o.junction_filter == IPX_FILTER_CANON) and (o.genome_fa == "")) cmd_error("--sj-filter=canon requires --genome_fa");
+    if ((o.junction_filter == IPX_FILTER_NULL) and (o.genome_fa != "")) o.junction_filter = IPX_FILTER_CANON;
+    if (not o.allow_anchor_indels) o.max_anchor_indel_size = 0;
+    if ((o.set_XS_strand_tag or o.set_TS_strand_tag) and ((o.bam_pass_through.size() == 0) or (o.genome_fa.size() == 0)))
+        cmd_error("--set-XS-strand-tag and --set-TS-strand-tag require --pass-through and --genome-fasta");
+}
+
+/* OutputFiles (intronProspector.cc:303-328): the TSV header is written when the file is opened */
+struct Outputs {
+    unique_ptr<OutFile> junction_bed, intron_bed, intron_bed6, intron_call;
+    explicit Outputs(const Options &o) {
+        if (o.junction_bed != "") junction_bed.reset(new OutFile(o.junction_bed));
+        if (o.intron_bed != "") intron_bed.reset(new OutFile(o.intron_bed));
+        if (o.intron_bed6 != "") intron_bed6.reset(new OutFile(o.intron_bed6));
+        if (o.intron_call_tsv != "") {
+            intron_call.reset(new OutFile(o.intron_call_tsv));
+            ipx_text t;
+            ipx_format_tsv_header(&t);
+            intron_call->write(t);
+            ipx_text_free(&t);
+        }
+    }
+};
+
+/* one input file being read (JunctionsExtractor::open / close, junctions_extractor.cc:571-617) */
+struct Input {
+    samFile *in = nullptr;
+    sam_hdr_t *hdr = nullptr;
+    samFile *out = nullptr;
+    bam1_t *rec = nullptr;
+    string name;
+    explicit Input(const string &bam) : name(bam) {
+        in = sam_open(bam.c_str(), "r");
+        if (in == NULL) throw runtime_error("Error opening BAM/SAM/CRAM file: " + bam);
+        hdr = sam_hdr_read(in);
+        if (hdr == NULL) throw runtime_error("Error opening BAM/SAM/CRAM file: " + bam);
+        rec = bam_init1();
+    }
+    void open_pass_through(const string &path) {
+        const htsFormat *fmt = hts_get_format(in);
+        if (!((fmt->format == sam) || (fmt->format == bam)))
+            throw invalid_argument("Error: pass-through is only implemented for SAM or BAM files: " + path);
+        out = hts_open_format(path.c_str(), "w", fmt);
+        if (out == NULL) throw runtime_error("Error opening BAM/SAM/CRAM file: " + path);
+        if (sam_hdr_write(out, hdr) < 0) throw runtime_error("Error writing SAM header: " + path);
+    }
+    /* read_align (junctions_extractor.cc:620-634) without the one-record read-ahead, which the caller keeps */
+    bool read() {
+        int stat = sam_read1(in, hdr, rec);
+        if (stat < -1) throw runtime_error("Error reader BAM record: " + name);
+        return stat >= 0;
+    }
+    void pass(const bam1_t *b) {
+        if (out != NULL && sam_write1(out, hdr, b) < 0) throw runtime_error("Error writing BAM record to pass-through file");
+    }
+    ~Input() {
+        if (out) sam_close(out);
+        if (rec) bam_destroy1(rec);
+        if (hdr) sam_hdr_destroy(hdr);
+        if (in) sam_close(in);
+    }
+};
+
+class Driver {
+    const Options &opts_;
+    ipx_handle *h_ = nullptr;
+    vector<string> targets_;            /* targets_, appended per file (save_targets, junctions_extractor.cc:564-568) */
+    vector<int32_t> canon_tid_;         /* first index carrying the same name: the reference keys junctions by name */
+    map<string, int32_t> name_first_;
+    ipx::ColumnarBatch batch_;
+    uint64_t next_seq_ = 0;
+    /* stream segments (first record index, target) of processed records, for attributing deferred errors */
+    vector<pair<uint64_t, int32_t>> segments_;
+    static const size_t BATCH_RECORDS = 1u << 22;
+    static const size_t BATCH_CIGAR = 1u << 26;
+
+    public:
+    explicit Driver(const Options &o) : opts_(o) {
+        ipx_params p;
+        memset(&p, 0, sizeof(p));
+        p.min_anchor_length = o.min_anchor_length;
+        p.max_anchor_indel_size = o.max_anchor_indel_size;
+        p.min_intron_length = o.min_intron_length;
+        p.max_intron_length = o.max_intron_length;
+        p.junction_filter = o.junction_filter;
+        p.strandness = o.strandness;
+        p.excludes = o.excludes;
+        p.skip_missing_targets = o.skip_missing_targets ? 1 : 0;
+        p.device = 0;
+        if (const char *d = getenv("IPX_DEVICE")) p.device = atoi(d);
+        int rc = ipx_create(&p, &h_);
+        if (rc != IPX_OK) throw runtime_error("no usable CUDA device: junction extraction needs an NVIDIA B200 (sm_100a) GPU");
+        batch_.clear(0);
+    }
+    ~Driver() { ipx_destroy(h_); }
+
+    void set_genome(const ipx::LoadedGenome &g) {
+        check_ipx(h_, ipx_set_genome(h_, (int32_t)g.names.size(), g.name_ptrs.data(), g.lengths.data(), g.seq_ptrs.data()));
+    }
+
+    void add_targets(const sam_hdr_t *hdr) {
+        for (int i = 0; i < hdr->n_targets; i++) {
+            string nm(hdr->target_name[i]);
+            auto it = name_first_.find(nm);
+            int32_t idx = (int32_t)targets_.size();
+            if (it == name_first_.end()) {
+                name_first_.emplace(nm, idx);
+                canon_tid_.push_back(idx);
+            } else {
+                canon_tid_.push_back(it->second);
+                /* keep names unique for the engine: this index is never used as a key */
+                nm += string("\x01") + to_string(idx);
+            }
+            targets_.push_back(nm);
+        }
+        vector<const char *> ptrs(targets_.size());
+        for (size_t i = 0; i < targets_.size(); i++) ptrs[i] = targets_[i].c_str();
+        check_ipx(h_, ipx_set_targets(h_, (int32_t)ptrs.size(), ptrs.data()));
+    }
+    size_t n_targets() const { return targets_.size(); }
+    const vector<string> &targets() const { return targets_; }
+
+    /* process_alignment (junctions_extractor.cc:533-549): hand the record to the engine */
+    void process(const bam1_t *b) {
+        int32_t tid = b->core.tid;
+        if (tid >= 0 && (size_t)tid < canon_tid_.size()) tid = canon_tid_[tid];
+        if (segments_.empty() || segments_.back().second != tid) segments_.emplace_back(next_seq_, tid);
+        batch_.add(b, tid);
+        next_seq_++;
+        if (batch_.size() >= BATCH_RECORDS || batch_.cigar.size() >= BATCH_CIGAR) push();
+    }
+    void push() {
+        if (batch_.size() == 0) return;
+        ipx_batch v = batch_.view();
+        check_ipx(h_, ipx_push_batch(h_, &v));
+        batch_.clear(next_seq_);
+    }
+    ipx_table *flush() {
+        push();
+        ipx_table *t = nullptr;
+        check_ipx(h_, ipx_flush(h_, &t));
+        /* get_splice_sites' warning (junctions_extractor.cc:411-415) */
+        for (uint64_t i = 0; i < t->n_missing_targets; i++)
+            cerr << "Warning: genomic sequence not found for " << targets_[t->missing_targets[i]]
+                 << " splice junctions not available" << endl;
+        return t;
+    }
+    int32_t target_of_seq(uint64_t seq) const {
+        int32_t tid = -1;
+        for (auto &s : segments_) {
+            if (s.first > seq) break;
+            tid = s.second;
+        }
+        return tid;
+    }
+    ipx_handle *handle() { return h_; }
+};
+
+/* output_junctions (intronProspector.cc:330-351) for table rows [begin, end) */
+static void output_junctions(const ipx_table *t, const vector<string> &targets, uint64_t begin, uint64_t end,
+                             float min_confidence, Outputs &out) {
+    vector<const char *> names(targets.size());
+    for (size_t i = 0; i < targets.size(); i++) names[i] = targets[i].c_str();
+    auto emit = [&](unique_ptr<OutFile> &f, int fmt) {
+        if (!f) return;
+        ipx_text txt;
+        int rc = ipx_format(t, names.data(), fmt, min_confidence, begin, end, &txt);
+        if (rc != IPX_OK) throw runtime_error("formatting failed");
+        f->write(txt);
+        ipx_text_free(&txt);
+    };
+    emit(out.junction_bed, IPX_FMT_JUNCTION_BED);
+    emit(out.intron_bed, IPX_FMT_INTRON_BED9);
+    emit(out.intron_bed6, IPX_FMT_INTRON_BED6);
+    emit(out.intron_call, IPX_FMT_INTRON_TSV);
+}
+
+/* rows of one target are contiguous in the key-ordered table */
+static void target_rows(const ipx_table *t, int32_t tid, uint64_t *begin, uint64_t *end) {
+    uint64_t b = 0;
+    while (b < t->n_junctions && t->chrom[b] != tid) b++;
+    uint64_t e = b;
+    while (e < t->n_junctions && t->chrom[e] == tid) e++;
+    *begin = b;
+    *end = e;
+}
+
+/* extract_junctions_by_target (intronProspector.cc:356-371) with identify_junctions_for_target /
+ * process_target_alignment (junctions_extractor.cc:637-664) */
+static void extract_by_target(Driver &drv, const Options &opts, Outputs &out) {
+    Input in(opts.bam_files[0]);
+    drv.add_targets(in.hdr);
+    if (opts.bam_pass_through != "") in.open_pass_through(opts.bam_pass_through);
+    const int n_targets = (int)drv.n_targets();
+    int previous_target = -1;
+    bool pending = false, eof = false;
+    int stop_target = n_targets; /* targets [0, stop_target) get their output */
+    string fatal;
+    for (int target = 0; target < n_targets && fatal.empty(); target++) {
+        for (;;) {
+            if (!pending) {
+                if (eof || !in.read()) {
+                    eof = true;
+                    break;
+                }
+            }
+            pending = false;
+            const bam1_t *aln = in.rec;
+            if (aln->core.tid != target) {
+                if ((aln->core.tid >= 0) and (aln->core.tid < previous_target)) {
+                    fatal = "BAM appears to not be coordinate sorted";
+                    stop_target = target;
+                    break;
+                }
+                pending = true;
+                break;
+            }
+            drv.process(aln);
+            in.pass(aln);
+        }
+        previous_target = target;
+    }
+    ipx_table *t = drv.flush();
+    if (t->status != IPX_OK) {
+        /* the reference throws while processing the failing record: earlier targets are already written */
+        int32_t err_tid = t->error_tid >= 0 ? t->error_tid : drv.target_of_seq(t->first_error_seq);
+        if (fatal.empty() || err_tid < stop_target) {
+            fatal = t->error_text;
+            stop_target = err_tid < 0 ? 0 : err_tid;
+        }
+    }
+    /* per target, in header order (intronProspector.cc:365-369) */
+    vector<pair<uint64_t, uint64_t>> ranges(n_targets, make_pair((uint64_t)0, (uint64_t)0));
+    {
+        uint64_t i = 0;
+        while (i < t->n_junctions) {
+            uint64_t e = i;
+            while (e < t->n_junctions && t->chrom[e] == t->chrom[i]) e++;
+            if (t->chrom[i] >= 0 && t->chrom[i] < n_targets) ranges[t->chrom[i]] = make_pair(i, e);
+            i = e;
+        }
+    }
+    for (int target = 0; target < stop_target && target < n_targets; target++)
+        if (ranges[target].second > ranges[target].first)
+            output_junctions(t, drv.targets(), ranges[target].first, ranges[target].second, opts.min_confidence_score, out);
+    ipx_table_free(t);
+    if (!fatal.empty()) throw runtime_error(fatal);
+    /* copy_unaligned_reads (junctions_extractor.cc:667-674) */
+    if (in.out != NULL) {
+        if (pending) in.pass(in.rec);
+        while (!eof && in.read()) in.pass(in.rec);
+    }
+    (void)target_rows;
+}
+
+/* extract_junctions_unsorted / extract_junctions_multiple (intronProspector.cc:375-401) */
+static void extract_whole_files(Driver &drv, const Options &opts, Outputs &out) {
+    for (size_t ibam = 0; ibam < opts.bam_files.size(); ibam++) {
+        Input in(opts.bam_files[ibam]);
+        drv.add_targets(in.hdr);
+        /* in --unsorted mode the reference opens the pass-through file but only copy_unaligned_reads writes to it,
+         * after every record has been consumed: the file gets the header only */
+        if (opts.bam_files.size() == 1 && opts.bam_pass_through != "") in.open_pass_through(opts.bam_pass_through);
+        while (in.read()) drv.process(in.rec);
+    }
+    ipx_table *t = drv.flush();
+    if (t->status != IPX_OK) {
+        string msg = t->error_text;
+        ipx_table_free(t);
+        throw runtime_error(msg);
+    }
+    output_junctions(t, drv.targets(), 0, t->n_junctions, opts.min_confidence_score, out);
+    ipx_table_free(t);
+}
+
+static void extract_junctions(const Options &opts) {
+    ipx::LoadedGenome genome;
+    if (opts.genome_fa.size() > 0) ipx::load_genome(opts.genome_fa, genome);
+    if (opts.debug_trace_tsv != "") throw runtime_error("--debug-trace is not available in the GPU build yet");
+    if (opts.set_XS_strand_tag || opts.set_TS_strand_tag)
+        throw runtime_error("--set-XS-strand-tag / --set-TS-strand-tag are not available in the GPU build yet");
+    Driver drv(opts);
+    if (opts.genome_fa.size() > 0) drv.set_genome(genome);
+    Outputs out(opts);
+    if (opts.bam_files.size() > 1 || opts.unsorted) {
+        extract_whole_files(drv, opts, out);
+    } else {
+        extract_by_target(drv, opts, out);
+    }
+}
+
+int main(int argc, char *argv[]) {
+    Options opts;
+    try {
+        parse_options(argc, argv, opts);
+    } catch (const std::exception &ex) {
+        cerr << "Error parsing command line: " << ex.what() << endl;
+        exit(1);
+    }
+    try {
+        extract_junctions(opts);
+    } catch (const std::exception &e) {
+        cmd_error(e.what());
+    }
+    return 0;
+}

@@ -1,0 +1,185 @@
+/* calls_tsv.cc -- see calls_tsv.h.  Reading goes through zlib's gzread, which also passes plain files through;
+ * the reference picks gzip by the ".gz" suffix (AutoGzip.hh:9-11), which gives the same bytes for both kinds. */
+#include "calls_tsv.h"
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+#include <stdexcept>
+
+namespace ipx {
+
+CallsRows::CallsRows() {
+    memset(&rows, 0, sizeof(rows));
+    site_strings.push_back("");
+    site_index.emplace("", 0u);
+}
+
+void CallsRows::bind() {
+    chrom_ptrs.resize(chrom_names.size());
+    for (size_t i = 0; i < chrom_names.size(); i++) chrom_ptrs[i] = chrom_names[i].c_str();
+    site_ptrs.resize(site_strings.size());
+    for (size_t i = 0; i < site_strings.size(); i++) site_ptrs[i] = site_strings[i].c_str();
+    rows.n_rows = chrom.size();
+    rows.chrom = chrom.data();
+    rows.intron_start = i0.data();
+    rows.intron_end = i1.data();
+    rows.anchor_start = a0.data();
+    rows.anchor_end = a1.data();
+    rows.strand = strand.data();
+    rows.sites = sites.data();
+    rows.counts = counts.data();
+    rows.confidence = conf.data();
+    rows.site_strings = site_ptrs.data();
+    rows.n_site_strings = (uint32_t)site_ptrs.size();
+}
+
+namespace {
+
+struct LineReader {
+    gzFile gz;
+    std::vector<char> buf;
+    size_t beg = 0, end = 0;
+    bool eof = false;
+    explicit LineReader(gzFile g) : gz(g), buf(1 << 20) {}
+    /* std::getline semantics: false only when nothing at all could be read */
+    bool getline(std::string &line) {
+        line.clear();
+        bool any = false;
+        for (;;) {
+            if (beg == end) {
+                if (eof) return any;
+                int got = gzread(gz, buf.data(), (unsigned)buf.size());
+                if (got <= 0) {
+                    eof = true;
+                    return any;
+                }
+                beg = 0;
+                end = (size_t)got;
+            }
+            any = true;
+            const char *p = buf.data() + beg;
+            const char *nl = (const char *)memchr(p, '\n', end - beg);
+            if (nl) {
+                line.append(p, nl - p);
+                beg += (size_t)(nl - p) + 1;
+                return true;
+            }
+            line.append(p, end - beg);
+            beg = end;
+        }
+    }
+};
+
+void split_tabs(const std::string &line, std::vector<std::string> &words) {
+    /* Tsv::split_line (tsv.hh:27-38) */
+    words.clear();
+    size_t prev = 0, cur = line.find('\t');
+    while (cur != std::string::npos) {
+        words.push_back(line.substr(prev, cur - prev));
+        prev = cur + 1;
+        cur = line.find('\t', prev);
+    }
+    words.push_back(line.substr(prev));
+}
+
+uint32_t to_uint(const std::string &s) {
+    /* string_to_uint (type_ops.hh:19-26) */
+    char *end;
+    uint32_t n = (uint32_t)strtoul(s.c_str(), &end, 10);
+    if (end == s.c_str() || *end != '\0') throw std::runtime_error("invalid integer \"" + s + "\"");
+    return n;
+}
+
+float to_float(const std::string &s) {
+    /* string_to_float (type_ops.hh:37-44) */
+    char *end;
+    float n = strtof(s.c_str(), &end);
+    if (end == s.c_str() || *end != '\0') throw std::runtime_error("invalid float \"" + s + "\"");
+    return n;
+}
+
+bool canonical(const std::string &s) {
+    /* is_canonical (splice_juncs.cc:25-38): any letter case */
+    if (s.size() != 5) return false;
+    char u[6];
+    for (int i = 0; i < 5; i++) u[i] = (s[i] >= 'a' && s[i] <= 'z') ? (char)(s[i] - 32) : s[i];
+    u[5] = 0;
+    return !strcmp(u, "GT/AG") || !strcmp(u, "GC/AG") || !strcmp(u, "AT/AC");
+}
+
+}  // namespace
+
+void load_calls_tsv(const std::string &path, int junction_filter, CallsRows &out) {
+    gzFile gz = gzopen(path.c_str(), "rb");
+    if (!gz) throw std::runtime_error(std::string("Failed to open ") + (path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0 ? "gzip file: " : "file: ") + path);
+    gzbuffer(gz, 1 << 20);
+    LineReader rd(gz);
+    std::string line;
+    std::vector<std::string> words;
+    try {
+        if (!rd.getline(line)) throw std::runtime_error("empty TSV file: " + path);
+        split_tabs(line, words);
+        const int ncol = (int)words.size();
+        std::unordered_map<std::string, int> col;
+        for (int i = 0; i < ncol; i++) col[words[i]] = i; /* later duplicates win, as with map::operator[] */
+        auto need = [&](const char *name) -> int {
+            auto it = col.find(name);
+            return it == col.end() ? -1 : it->second;
+        };
+        const int c_chrom = need("chrom"), c_start = need("intron_start"), c_end = need("intron_end"), c_strand = need("strand"),
+                  c_uniq = need("uniq_mapped_count"), c_multi = need("multi_mapped_count"), c_unsure = need("unsure_mapped_count"),
+                  c_left = need("max_left_overhang"), c_right = need("max_right_overhang"), c_conf = need("confidence"),
+                  c_sites = need("splice_sites");
+        auto get = [&](int c, const char *name) -> const std::string & {
+            if (c < 0) throw std::runtime_error(std::string("column '") + name + "' not found: " + path);
+            return words[c];
+        };
+        while (rd.getline(line)) {
+            split_tabs(line, words);
+            if ((int)words.size() != ncol) {
+                const std::string n = std::to_string(ncol);
+                throw std::runtime_error("expected " + n + " columns, got " + n + ":" + path); /* sic, tsv.hh:71 */
+            }
+            const std::string &sites = get(c_sites, "splice_sites");
+            /* junction_filter_check (splice_juncs.cc:52-61) */
+            if (!sites.empty() && junction_filter == IPX_FILTER_CANON && !canonical(sites)) continue;
+            const uint32_t start = to_uint(get(c_start, "intron_start"));
+            const uint32_t end = to_uint(get(c_end, "intron_end"));
+            const std::string &chrom = get(c_chrom, "chrom");
+            const uint32_t a0 = start - to_uint(get(c_left, "max_left_overhang"));
+            const uint32_t a1 = end + to_uint(get(c_right, "max_right_overhang"));
+            const std::string &strand = get(c_strand, "strand");
+            const uint32_t uniq = to_uint(get(c_uniq, "uniq_mapped_count"));
+            const uint32_t multi = to_uint(get(c_multi, "multi_mapped_count"));
+            const uint32_t unsure = to_uint(get(c_unsure, "unsure_mapped_count"));
+            const float conf = to_float(get(c_conf, "confidence"));
+            auto ci = out.chrom_index.find(chrom);
+            if (ci == out.chrom_index.end()) {
+                ci = out.chrom_index.emplace(chrom, (int32_t)out.chrom_names.size()).first;
+                out.chrom_names.push_back(chrom);
+            }
+            auto si = out.site_index.find(sites);
+            if (si == out.site_index.end()) {
+                si = out.site_index.emplace(sites, (uint32_t)out.site_strings.size()).first;
+                out.site_strings.push_back(sites);
+            }
+            out.chrom.push_back(ci->second);
+            out.i0.push_back(start);
+            out.i1.push_back(end);
+            out.a0.push_back(a0);
+            out.a1.push_back(a1);
+            out.strand.push_back(strand.empty() ? '\0' : strand[0]);
+            out.sites.push_back(si->second);
+            out.counts.push_back(uniq);
+            out.counts.push_back(multi);
+            out.counts.push_back(unsure);
+            out.conf.push_back(conf);
+        }
+    } catch (...) {
+        gzclose(gz);
+        throw;
+    }
+    gzclose(gz);
+}
+
+}  // namespace ipx

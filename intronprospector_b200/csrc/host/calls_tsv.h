@@ -1,0 +1,31 @@
+/* calls_tsv.h -- intron-calls TSV files -> merge rows (host side of ipx_merge_rows_fold). */
+#ifndef IPX_CALLS_TSV_H
+#define IPX_CALLS_TSV_H
+#include <stdint.h>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "ipx.h"
+
+namespace ipx {
+
+struct CallsRows {
+    std::vector<int32_t> chrom;
+    std::vector<uint32_t> i0, i1, a0, a1, sites, counts;
+    std::vector<char> strand;
+    std::vector<float> conf;
+    std::vector<std::string> chrom_names, site_strings;
+    std::vector<const char *> chrom_ptrs, site_ptrs;
+    std::unordered_map<std::string, int32_t> chrom_index;
+    std::unordered_map<std::string, uint32_t> site_index;
+    ipx_merge_rows rows;
+    CallsRows();
+    void bind();
+};
+
+/* process_calls_tsv (intronProspectorMerge.cc:190-199) without the fold: appends the rows of one file.
+ * Throws std::runtime_error with the reference's messages (tsv.hh:41,71,88; type_ops.hh:23,32,41). */
+void load_calls_tsv(const std::string &path, int junction_filter, CallsRows &out);
+
+}  // namespace ipx
+#endif

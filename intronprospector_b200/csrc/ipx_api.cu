@@ -1,0 +1,996 @@
+/* ipx_api.cu -- implementation of the C ABI in include/ipx.h on top of the CUDA engine.
+ * CUDA-only: every compute entry point fails with IPX_ERR_CUDA when no device is usable.
+ */
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/ipx.h"
+#include "ipx_engine.h"
+#include "ipx_host.h"
+#include "ipx_merge.h"
+
+using namespace ipx;
+
+namespace {
+
+struct HostTable {
+    ipx_table t;
+    std::vector<int32_t> chrom, missing;
+    std::vector<uint32_t> i0, i1, a0, a1, ijunc, hist_cnt;
+    std::vector<char> strand, sites;
+    std::vector<uint64_t> counts, hist_off;
+    std::vector<float> conf;
+    void bind() {
+        t.n_junctions = chrom.size();
+        t.chrom = chrom.data();
+        t.intron_start = i0.data();
+        t.intron_end = i1.data();
+        t.anchor_start = a0.data();
+        t.anchor_end = a1.data();
+        t.strand = strand.data();
+        t.splice_sites = sites.data();
+        t.read_counts = counts.data();
+        t.ijunc = ijunc.data();
+        t.confidence = conf.data();
+        t.hist_off = hist_off.data();
+        t.hist_cnt = hist_cnt.data();
+        t.n_hist = hist_cnt.size();
+        t.missing_targets = missing.data();
+        t.n_missing_targets = missing.size();
+    }
+};
+
+struct DeviceBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct StageTimer {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+    double ms = 0.0;
+    uint64_t launches = 0;
+};
+
+}  // namespace
+
+struct ipx_handle {
+    ipx_params params;
+    ExtractParams xp;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    /* tables */
+    Tables tab{};
+    bool tables_ready = false;
+    unsigned long long *d_counters = nullptr; /* 8 x 128-byte lines */
+    bool dirty = false;                       /* events folded since the last clear */
+
+    /* targets / genome */
+    std::vector<std::string> targets;
+    uint32_t *d_name_rank = nullptr;
+    size_t d_name_rank_cap = 0;
+    bool have_genome = false;
+    std::vector<std::string> gnames;
+    std::vector<uint64_t> glen;
+    std::vector<char *> d_gseq;
+    const char **d_gseq_ptrs = nullptr;
+    uint64_t *d_glen = nullptr;
+    int32_t *d_target_seq = nullptr;
+    size_t d_target_seq_cap = 0;
+    std::vector<int32_t> target_seq;
+    std::unordered_set<std::string> warned_missing;
+
+    /* staging for host batches */
+    DeviceBuf s_tid, s_pos, s_flag, s_nh, s_xs, s_off, s_cig;
+
+    /* finalize */
+    FinalizeWork fw;
+    DeviceTable dt{};
+    bool finalized = false;
+    bool keep_export = false;
+    uint32_t ijunc_base = 0;
+
+    /* merge */
+    MergeTables mt{};
+    uint64_t mt_cap = 0;
+
+    /* timings */
+    StageTimer tm_extract, tm_motif, tm_finalize, tm_merge;
+    ipx_timings totals{};
+};
+
+namespace {
+
+int fail(ipx_handle *h, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CU(h, call)                                                                              \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return fail((h), IPX_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), \
+                        __FILE__, __LINE__, cudaGetErrorString(e__));                            \
+    } while (0)
+
+struct Span {
+    ipx_handle *h;
+    StageTimer *t;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Span(ipx_handle *h_, StageTimer *t_, uint64_t launches) : h(h_), t(t_) {
+        t->launches += launches;
+        if (h->params.profile) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, h->stream);
+        }
+    }
+    ~Span() {
+        if (a) {
+            cudaEventRecord(b, h->stream);
+            t->spans.emplace_back(a, b);
+        }
+    }
+};
+
+void drain(StageTimer &t) {
+    for (auto &s : t.spans) {
+        float ms = 0.f;
+        cudaEventSynchronize(s.second);
+        if (cudaEventElapsedTime(&ms, s.first, s.second) == cudaSuccess) t.ms += ms;
+        cudaEventDestroy(s.first);
+        cudaEventDestroy(s.second);
+    }
+    t.spans.clear();
+}
+
+int bits_for(uint32_t v) {
+    int b = 1;
+    while (b < 32 && (v >> b) != 0) b++;
+    return b;
+}
+
+uint64_t pow2_at_least(uint64_t v) {
+    uint64_t p = 1024;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+int alloc_tables(ipx_handle *h) {
+    if (h->tables_ready) return IPX_OK;
+    uint64_t cap = pow2_at_least(h->params.table_capacity ? h->params.table_capacity : (1ull << 22));
+    uint64_t hcap = pow2_at_least(h->params.hist_capacity ? h->params.hist_capacity : (1ull << 26));
+    if (cap > (1ull << 31)) return fail(h, IPX_ERR_ARG, "table_capacity too large");
+    Tables &t = h->tab;
+    CU(h, cudaMalloc(&t.keys, cap * sizeof(unsigned long long)));
+    CU(h, cudaMalloc(&t.stat, cap * sizeof(JStat)));
+    CU(h, cudaMalloc(&t.hkeys, hcap * sizeof(unsigned long long)));
+    CU(h, cudaMalloc(&t.hcnt, hcap * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&h->d_counters, 8 * 128));
+    CU(h, cudaMemsetAsync(h->d_counters, 0, 8 * 128, h->stream));
+    t.cap_mask = cap - 1;
+    t.hcap_mask = hcap - 1;
+    t.n_keys = h->d_counters + 0;
+    t.n_hist = h->d_counters + 16;
+    t.n_events = h->d_counters + 32;
+    t.n_live = h->d_counters + 48;
+    t.err_sv = h->d_counters + 64;
+    t.overflow = (uint32_t *)(h->d_counters + 80);
+    const int L = bits_for(h->params.max_intron_length);
+    t.kl.len_bits = L;
+    t.kl.start_shift = L;
+    t.kl.tid_shift = L + 31;
+    t.kl.tid_bits = 63 - t.kl.tid_shift;
+    launch_init_tables(t, h->stream);
+    CU(h, cudaGetLastError());
+    h->tables_ready = true;
+    return IPX_OK;
+}
+
+GenomeView genome_view(const ipx_handle *h) {
+    GenomeView g{};
+    g.seq = h->d_gseq_ptrs;
+    g.len = h->d_glen;
+    g.target_seq = h->d_target_seq;
+    g.n_targets = (int32_t)h->targets.size();
+    g.have_genome = h->have_genome ? 1 : 0;
+    g.skip_missing = h->params.skip_missing_targets ? 1 : 0;
+    g.filter_canon = (h->have_genome && h->params.junction_filter == IPX_FILTER_CANON) ? 1 : 0;
+    return g;
+}
+
+bool two_pass(const ipx_handle *h) {
+    /* events before the first filter-passing event of a junction are dropped (add_junction,
+     * junctions_extractor.cc:494-502); only the canon filter over a genome can reject */
+    return h->have_genome && h->params.junction_filter == IPX_FILTER_CANON;
+}
+
+int upload_target_maps(ipx_handle *h) {
+    const size_t n = h->targets.size();
+    if (n == 0) return IPX_OK;
+    /* rank of every name under std::string::operator< (JunctionKey operator<, junctions.hh:77-100) */
+    std::vector<uint32_t> order(n), rank(n);
+    for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h->targets[a] < h->targets[b]; });
+    for (size_t i = 0; i < n; i++) {
+        if (i > 0 && h->targets[order[i]] == h->targets[order[i - 1]])
+            return fail(h, IPX_ERR_ARG, "duplicate target name '%s'", h->targets[order[i]].c_str());
+        rank[order[i]] = (uint32_t)i;
+    }
+    if (h->d_name_rank_cap < n) {
+        if (h->d_name_rank) cudaFree(h->d_name_rank);
+        CU(h, cudaMalloc(&h->d_name_rank, n * sizeof(uint32_t)));
+        h->d_name_rank_cap = n;
+    }
+    CU(h, cudaMemcpyAsync(h->d_name_rank, rank.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    /* target -> genome sequence (Genome::has_seq, genome.cc:58-60) */
+    h->target_seq.assign(n, -1);
+    if (h->have_genome) {
+        std::unordered_map<std::string, int32_t> by_name;
+        for (size_t g = 0; g < h->gnames.size(); g++) by_name.emplace(h->gnames[g], (int32_t)g);
+        for (size_t i = 0; i < n; i++) {
+            auto it = by_name.find(h->targets[i]);
+            if (it != by_name.end()) h->target_seq[i] = it->second;
+        }
+    }
+    if (h->d_target_seq_cap < n) {
+        if (h->d_target_seq) cudaFree(h->d_target_seq);
+        CU(h, cudaMalloc(&h->d_target_seq, n * sizeof(int32_t)));
+        h->d_target_seq_cap = n;
+    }
+    CU(h, cudaMemcpyAsync(h->d_target_seq, h->target_seq.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return IPX_OK;
+}
+
+void free_genome(ipx_handle *h) {
+    for (char *p : h->d_gseq) cudaFree(p);
+    h->d_gseq.clear();
+    if (h->d_gseq_ptrs) cudaFree((void *)h->d_gseq_ptrs);
+    if (h->d_glen) cudaFree(h->d_glen);
+    h->d_gseq_ptrs = nullptr;
+    h->d_glen = nullptr;
+    h->have_genome = false;
+}
+
+int run_batch(ipx_handle *h, const BatchView &b) {
+    if (h->finalized) return fail(h, IPX_ERR_STATE, "ipx_push_batch after ipx_finalize_device without ipx_flush");
+    if (h->targets.empty()) return fail(h, IPX_ERR_STATE, "ipx_set_targets must be called before ipx_push_batch");
+    int rc = alloc_tables(h);
+    if (rc) return rc;
+    if (b.n >> 36) return fail(h, IPX_ERR_ARG, "batch too large");
+    if (two_pass(h)) {
+        {
+            Span s(h, &h->tm_extract, 1);
+            launch_extract(MODE_PASS1, b, h->xp, h->tab, h->sm_count, h->stream);
+        }
+        {
+            Span s(h, &h->tm_motif, 1);
+            launch_resolve_T(h->tab, genome_view(h), h->stream);
+        }
+        {
+            Span s(h, &h->tm_extract, 1);
+            launch_extract(MODE_PASS2, b, h->xp, h->tab, h->sm_count, h->stream);
+        }
+    } else {
+        Span s(h, &h->tm_extract, 1);
+        launch_extract(MODE_SINGLE, b, h->xp, h->tab, h->sm_count, h->stream);
+    }
+    CU(h, cudaGetLastError());
+    h->totals.records += b.n;
+    h->dirty = true;
+    return IPX_OK;
+}
+
+}  // namespace
+
+/* ------------------------------------------------------------------ basic entry points */
+extern "C" const char *ipx_version(void) { return "intronprospector_b200 0.1 (reference semantics: intronProspector 1.4.0)"; }
+extern "C" int ipx_abi_version(void) { return IPX_ABI_VERSION; }
+
+extern "C" int ipx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int ipx_create(const ipx_params *params, ipx_handle **out) {
+    if (!params || !out) return IPX_ERR_ARG;
+    *out = nullptr;
+    int n = ipx_device_count();
+    if (n <= 0 || params->device < 0 || params->device >= n) return IPX_ERR_CUDA;
+    ipx_handle *h = new ipx_handle();
+    h->params = *params;
+    h->device = params->device;
+    if (cudaSetDevice(h->device) != cudaSuccess) {
+        delete h;
+        return IPX_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    if (params->stream) {
+        h->stream = (cudaStream_t)params->stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete h;
+            return IPX_ERR_CUDA;
+        }
+        h->own_stream = true;
+    }
+    h->xp.min_anchor_length = params->min_anchor_length;
+    h->xp.max_anchor_indel_size = params->max_anchor_indel_size;
+    h->xp.min_intron_length = params->min_intron_length;
+    h->xp.max_intron_length = params->max_intron_length;
+    h->xp.excludes = params->excludes;
+    h->xp.strandness = params->strandness;
+    *out = h;
+    return IPX_OK;
+}
+
+extern "C" void ipx_destroy(ipx_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    drain(h->tm_extract); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
+    if (h->finalized) free_device_table(h->dt);
+    cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.hkeys); cudaFree(h->tab.hcnt);
+    cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq);
+    free_genome(h);
+    h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();
+    h->s_off.release(); h->s_cig.release();
+    cudaFree(h->fw.cub_tmp); cudaFree(h->fw.d_count); cudaFree(h->fw.slot_rank);
+    cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char *ipx_last_error(const ipx_handle *h) { return h ? h->err.c_str() : "invalid handle"; }
+extern "C" void *ipx_stream(ipx_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+extern "C" int ipx_set_targets(ipx_handle *h, int32_t n_targets, const char *const *names) {
+    if (!h || n_targets < 0 || (n_targets && !names)) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    for (size_t i = 0; i < h->targets.size() && i < (size_t)n_targets; i++)
+        if (h->targets[i] != names[i]) return fail(h, IPX_ERR_ARG, "target %zu changed name", i);
+    const int L = bits_for(h->params.max_intron_length);
+    const int tid_bits = 63 - (L + 31);
+    if (tid_bits < 1 || ((uint64_t)n_targets >> tid_bits) != 0)
+        return fail(h, IPX_ERR_CAPACITY, "%d targets with --max-intron-length=%u do not fit the 64-bit junction key "
+                    "(%d bits left for the target index)", n_targets, h->params.max_intron_length, tid_bits < 0 ? 0 : tid_bits);
+    h->targets.assign(names, names + n_targets);
+    return upload_target_maps(h);
+}
+
+extern "C" int ipx_set_genome(ipx_handle *h, int32_t n_seqs, const char *const *names, const uint64_t *lengths,
+                              const char *const *seqs) {
+    if (!h || n_seqs < 0) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    free_genome(h);
+    h->gnames.assign(names, names + n_seqs);
+    h->glen.assign(lengths, lengths + n_seqs);
+    std::vector<const char *> ptrs(n_seqs ? n_seqs : 1, nullptr);
+    for (int32_t i = 0; i < n_seqs; i++) {
+        char *d = nullptr;
+        CU(h, cudaMalloc(&d, lengths[i] ? lengths[i] : 1));
+        h->d_gseq.push_back(d);
+        CU(h, cudaMemcpyAsync(d, seqs[i], lengths[i], cudaMemcpyHostToDevice, h->stream));
+        ptrs[i] = d;
+    }
+    CU(h, cudaMalloc((void **)&h->d_gseq_ptrs, ptrs.size() * sizeof(char *)));
+    CU(h, cudaMalloc(&h->d_glen, ptrs.size() * sizeof(uint64_t)));
+    CU(h, cudaMemcpyAsync((void *)h->d_gseq_ptrs, ptrs.data(), ptrs.size() * sizeof(char *), cudaMemcpyHostToDevice, h->stream));
+    if (n_seqs) CU(h, cudaMemcpyAsync(h->d_glen, lengths, n_seqs * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->have_genome = true;
+    return upload_target_maps(h);
+}
+
+extern "C" int ipx_push_batch_device(ipx_handle *h, const ipx_batch *b) {
+    if (!h || !b) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    BatchView v{b->tid, b->pos, b->flag, b->nh_class, b->xs, b->cigar_off, b->cigar, b->n_records, b->seq_base};
+    return run_batch(h, v);
+}
+
+extern "C" int ipx_push_batch(ipx_handle *h, const ipx_batch *b) {
+    if (!h || !b) return IPX_ERR_ARG;
+    if (b->n_records == 0) return IPX_OK;
+    if (b->n_cigar >> 32) return fail(h, IPX_ERR_ARG, "more than 2^32 CIGAR words in one batch");
+    cudaSetDevice(h->device);
+    const uint64_t n = b->n_records;
+    CU(h, h->s_tid.reserve(n * 4));
+    CU(h, h->s_pos.reserve(n * 4));
+    CU(h, h->s_flag.reserve(n * 2));
+    CU(h, h->s_nh.reserve(n));
+    CU(h, h->s_xs.reserve(n));
+    CU(h, h->s_off.reserve((n + 1) * 4));
+    CU(h, h->s_cig.reserve((b->n_cigar ? b->n_cigar : 1) * 4));
+    /* the staging buffers may still be read by the previous batch's kernels: same stream, so ordered */
+    CU(h, cudaMemcpyAsync(h->s_tid.p, b->tid, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->s_pos.p, b->pos, n * 4, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->s_flag.p, b->flag, n * 2, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->s_nh.p, b->nh_class, n, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->s_xs.p, b->xs, n, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->s_off.p, b->cigar_off, (n + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    if (b->n_cigar) CU(h, cudaMemcpyAsync(h->s_cig.p, b->cigar, b->n_cigar * 4, cudaMemcpyHostToDevice, h->stream));
+    BatchView v{(const int32_t *)h->s_tid.p, (const int32_t *)h->s_pos.p, (const uint16_t *)h->s_flag.p,
+                (const uint8_t *)h->s_nh.p, (const uint8_t *)h->s_xs.p, (const uint32_t *)h->s_off.p,
+                (const uint32_t *)h->s_cig.p, n, b->seq_base};
+    return run_batch(h, v);
+}
+
+extern "C" int ipx_finalize_device(ipx_handle *h) {
+    if (!h) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (h->finalized) return IPX_OK;
+    if (h->targets.empty()) return fail(h, IPX_ERR_STATE, "ipx_set_targets must be called first");
+    int rc = alloc_tables(h);
+    if (rc) return rc;
+    {
+        Span s(h, &h->tm_finalize, 12);
+        cudaError_t e = finalize_tables(h->tab, genome_view(h), h->d_name_rank, (int32_t)h->targets.size(), h->fw, h->dt,
+                                        h->keep_export, h->stream);
+        if (e != cudaSuccess)
+            return fail(h, IPX_ERR_CUDA, "CUDA error %s in finalize: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    }
+    h->finalized = true;
+    return IPX_OK;
+}
+
+namespace {
+
+template <class T>
+cudaError_t d2h(std::vector<T> &dst, const void *src, size_t n, cudaStream_t st) {
+    dst.resize(n);
+    if (n == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, st);
+}
+
+/* text of the exception the reference throws for a deferred device-side error */
+void describe_error(ipx_handle *h, unsigned long long err_sv, HostTable *ht) {
+    const unsigned code = (unsigned)(err_sv & 0xFFull);
+    ht->t.first_error_seq = err_sv >> SV_SEQ_SHIFT;
+    ht->t.error_tid = -1;
+    if (code < 0x80u) {
+        ht->t.status = IPX_ERR_CIGAR;
+        const char *ops = "MIDNSHP=XB";
+        snprintf(ht->t.error_text, sizeof(ht->t.error_text), "Unknown cigar operation '%c'", code < 10 ? ops[code] : '?');
+        return;
+    }
+    ht->t.status = IPX_ERR_GENOME;
+    /* find the junction whose first event raised it: only its key is needed, scan the raw table on the host side
+     * of a small copy (errors are fatal, so this path runs at most once per run) */
+    const uint64_t cap = h->tab.cap_mask + 1;
+    std::vector<unsigned long long> keys(cap);
+    std::vector<JStat> stat(cap);
+    cudaMemcpy(keys.data(), h->tab.keys, cap * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(stat.data(), h->tab.stat, cap * sizeof(JStat), cudaMemcpyDeviceToHost);
+    const int status = (int)(code & 0x7Fu);
+    for (uint64_t i = 0; i < cap; i++) {
+        if (keys[i] == EMPTY64) continue;
+        unsigned long long fm = std::min(stat[i].first[0], std::min(stat[i].first[1], stat[i].first[2]));
+        if (fm == EMPTY64 || (fm & ~0xFFull) != (err_sv & ~0xFFull)) continue;
+        const int32_t tid = key_tid(h->tab.kl, keys[i]);
+        const int64_t i0 = key_start(h->tab.kl, keys[i]), i1 = i0 + key_len(h->tab.kl, keys[i]);
+        ht->t.error_tid = tid;
+        const char *chrom = h->targets[tid].c_str();
+        auto clipped = [&](int64_t s, int64_t e) {
+            const int32_t g = h->target_seq[tid];
+            int64_t len = g >= 0 ? (int64_t)h->glen[g] : 0, b = s, en = e - 1;
+            if (en < b - 1) en = b - 1;
+            if (b < 0) b = 0;
+            if (b >= len) b = len;
+            if (en < 0) en = 0; else if (en >= len) en = len - 1;
+            int64_t got = en - b + 1;
+            return got < 0 ? (int64_t)0 : got;
+        };
+        if (status == 2) /* MOTIF_ERR_MISSING: Genome::fetch, genome.cc:64-67 */
+            snprintf(ht->t.error_text, sizeof(ht->t.error_text), "can't load genome sequence for: %s:%d-%d", chrom, (int)i0, (int)(i0 + 2));
+        else if (status == 3) /* genome.cc:68-70 */
+            snprintf(ht->t.error_text, sizeof(ht->t.error_text), "unexpected length returned for: %s:%d-%d: %d", chrom, (int)i0,
+                     (int)(i0 + 2), (int)clipped(i0, i0 + 2));
+        else
+            snprintf(ht->t.error_text, sizeof(ht->t.error_text), "unexpected length returned for: %s:%d-%d: %d", chrom,
+                     (int)(i1 - 2), (int)i1, (int)clipped(i1 - 2, i1));
+        return;
+    }
+    snprintf(ht->t.error_text, sizeof(ht->t.error_text), "genome sequence error");
+}
+
+}  // namespace
+
+extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
+    if (!h || !out) return IPX_ERR_ARG;
+    *out = nullptr;
+    int rc = ipx_finalize_device(h);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    HostTable *ht = new HostTable();
+    memset(&ht->t, 0, sizeof(ht->t));
+    const DeviceTable &d = h->dt;
+    const uint64_t n = d.n;
+    std::vector<unsigned long long> counts, T, hist_off;
+    cudaError_t e = cudaSuccess;
+    auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    chk(d2h(ht->chrom, d.chrom, n, st));
+    chk(d2h(ht->i0, d.i0, n, st));
+    chk(d2h(ht->i1, d.i1, n, st));
+    chk(d2h(ht->a0, d.a0, n, st));
+    chk(d2h(ht->a1, d.a1, n, st));
+    chk(d2h(ht->ijunc, d.ijunc, n, st));
+    chk(d2h(ht->strand, d.strand, n, st));
+    chk(d2h(ht->sites, d.sites, n * 8, st));
+    chk(d2h(counts, d.counts, n * 3, st));
+    chk(d2h(T, d.T, n, st));
+    chk(d2h(hist_off, d.hist_off, n + 1, st));
+    chk(d2h(ht->hist_cnt, d.hist_cnt, d.n_hist, st));
+    unsigned long long ctr[4] = {0, 0, 0, 0};
+    unsigned long long err_sv = EMPTY64;
+    uint32_t overflow = 0;
+    chk(cudaMemcpyAsync(&ctr[0], h->tab.n_events, 8, cudaMemcpyDeviceToHost, st));
+    chk(cudaMemcpyAsync(&ctr[1], h->tab.n_live, 8, cudaMemcpyDeviceToHost, st));
+    chk(cudaMemcpyAsync(&err_sv, h->tab.err_sv, 8, cudaMemcpyDeviceToHost, st));
+    chk(cudaMemcpyAsync(&overflow, h->tab.overflow, 4, cudaMemcpyDeviceToHost, st));
+    chk(cudaStreamSynchronize(st));
+    if (e != cudaSuccess) {
+        delete ht;
+        return fail(h, IPX_ERR_CUDA, "CUDA error %s in flush: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    }
+    if (overflow) {
+        delete ht;
+        if (overflow == 3) return fail(h, IPX_ERR_CAPACITY, "intron start beyond 2^31 cannot be keyed");
+        return fail(h, IPX_ERR_CAPACITY, "%s hash table is full; raise ipx_params.%s", overflow == 1 ? "junction" : "offset",
+                    overflow == 1 ? "table_capacity" : "hist_capacity");
+    }
+    ht->counts.assign(counts.begin(), counts.end());
+    ht->hist_off.assign(hist_off.begin(), hist_off.end());
+    if (ht->hist_off.empty()) ht->hist_off.push_back(0);
+    /* sjN continues across flushes (ijunc_, junctions_extractor.hh:129) */
+    for (uint64_t i = 0; i < n; i++) ht->ijunc[i] += h->ijunc_base;
+    h->ijunc_base += (uint32_t)n;
+    ht->conf.resize(n);
+    ht->bind();
+    compute_confidences(n, ht->counts.data(), ht->hist_off.data(), ht->hist_cnt.data(), ht->conf.data());
+    /* missing-genome warnings in first-miss order (junctions_extractor.cc:411-417) */
+    if (h->have_genome && h->params.skip_missing_targets) {
+        std::unordered_map<int32_t, unsigned long long> first_miss;
+        for (uint64_t i = 0; i < n; i++) {
+            const int32_t tid = ht->chrom[i];
+            if (h->target_seq[tid] >= 0) continue;
+            auto it = first_miss.find(tid);
+            if (it == first_miss.end() || T[i] < it->second) first_miss[tid] = T[i];
+        }
+        std::vector<std::pair<unsigned long long, int32_t>> v;
+        for (auto &kv : first_miss) v.emplace_back(kv.second, kv.first);
+        std::sort(v.begin(), v.end());
+        for (auto &kv : v)
+            if (h->warned_missing.insert(h->targets[kv.second]).second) ht->missing.push_back(kv.second);
+    }
+    ht->bind();
+    ht->t.status = IPX_OK;
+    if (err_sv != EMPTY64) describe_error(h, err_sv, ht);
+    h->totals.events += ctr[0];
+    h->totals.cigar_live += ctr[1];
+    h->totals.junctions += n;
+    h->totals.hist_runs += d.n_hist;
+    /* clear(), junctions.hh:240-245 */
+    free_device_table(h->dt);
+    h->finalized = false;
+    launch_init_tables(h->tab, st);
+    cudaMemsetAsync(h->tab.n_events, 0, 8, st);
+    cudaMemsetAsync(h->tab.n_live, 0, 8, st);
+    h->dirty = false;
+    *out = &ht->t;
+    return IPX_OK;
+}
+
+extern "C" void ipx_table_free(ipx_table *t) {
+    if (t) delete reinterpret_cast<HostTable *>(t);
+}
+
+/* ------------------------------------------------------------------ formatters */
+static int give_text(const std::string &s, ipx_text *out) {
+    out->data = (char *)malloc(s.size() + 1);
+    if (!out->data) return IPX_ERR_ARG;
+    memcpy(out->data, s.data(), s.size());
+    out->data[s.size()] = 0;
+    out->len = s.size();
+    return IPX_OK;
+}
+
+extern "C" int ipx_format(const ipx_table *t, const char *const *names, int format, float min_confidence, uint64_t begin,
+                          uint64_t end, ipx_text *out) {
+    if (!t || !names || !out) return IPX_ERR_ARG;
+    std::string s;
+    int rc = format_rows(t, names, format, min_confidence, begin, end, s);
+    if (rc) return rc;
+    return give_text(s, out);
+}
+
+extern "C" int ipx_format_tsv_header(ipx_text *out) {
+    if (!out) return IPX_ERR_ARG;
+    return give_text(tsv_header(), out);
+}
+
+extern "C" void ipx_text_free(ipx_text *t) {
+    if (t && t->data) free(t->data);
+    if (t) {
+        t->data = nullptr;
+        t->len = 0;
+    }
+}
+
+/* ------------------------------------------------------------------ timings */
+extern "C" int ipx_get_timings(ipx_handle *h, ipx_timings *out) {
+    if (!h || !out) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    drain(h->tm_extract); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
+    ipx_timings t = h->totals;
+    t.extract_ms = h->tm_extract.ms;
+    t.aggregate_ms = 0.0; /* fused into the extract kernel */
+    t.motif_ms = h->tm_motif.ms;
+    t.finalize_ms = h->tm_finalize.ms;
+    t.merge_ms = h->tm_merge.ms;
+    t.extract_launches = h->tm_extract.launches;
+    t.aggregate_launches = 0;
+    t.motif_launches = h->tm_motif.launches;
+    t.finalize_launches = h->tm_finalize.launches;
+    t.merge_launches = h->tm_merge.launches;
+    if (h->tables_ready && h->dirty) {
+        /* counts of the open (unflushed) table */
+        unsigned long long ev = 0, lw = 0;
+        cudaMemcpy(&ev, h->tab.n_events, 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&lw, h->tab.n_live, 8, cudaMemcpyDeviceToHost);
+        t.events += ev;
+        t.cigar_live += lw;
+    }
+    *out = t;
+    return IPX_OK;
+}
+
+extern "C" int ipx_reset_timings(ipx_handle *h) {
+    if (!h) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    drain(h->tm_extract); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
+    h->tm_extract = StageTimer(); h->tm_motif = StageTimer(); h->tm_finalize = StageTimer(); h->tm_merge = StageTimer();
+    h->totals = ipx_timings{};
+    return IPX_OK;
+}
+
+/* ------------------------------------------------------------------ multi-GPU exchange */
+extern "C" int ipx_partial_row_bytes(uint32_t *jb, uint32_t *hb) {
+    if (jb) *jb = (uint32_t)sizeof(JunctionRow);
+    if (hb) *hb = (uint32_t)sizeof(HistRow);
+    return IPX_OK;
+}
+
+extern "C" int ipx_partial_sizes(ipx_handle *h, int32_t n_parts, const int32_t *split_tid, const uint32_t *split_start,
+                                 uint64_t *junction_rows, uint64_t *hist_rows) {
+    if (!h || n_parts < 1 || !junction_rows || !hist_rows) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (two_pass(h)) return fail(h, IPX_ERR_STATE, "multi-GPU exchange with the canon filter is not implemented yet");
+    if (!h->finalized) {
+        h->keep_export = true;
+        int rc = ipx_finalize_device(h);
+        if (rc) return rc;
+    } else if (!h->dt.slot) {
+        return fail(h, IPX_ERR_STATE, "ipx_partial_sizes must be the call that finalizes the table");
+    }
+    const uint64_t n = h->dt.n;
+    std::vector<int32_t> chrom(n);
+    std::vector<uint32_t> i0(n);
+    std::vector<unsigned long long> hoff(n + 1);
+    if (n) {
+        CU(h, cudaMemcpy(chrom.data(), h->dt.chrom, n * 4, cudaMemcpyDeviceToHost));
+        CU(h, cudaMemcpy(i0.data(), h->dt.i0, n * 4, cudaMemcpyDeviceToHost));
+    }
+    CU(h, cudaMemcpy(hoff.data(), h->dt.hist_off, (n + 1) * 8, cudaMemcpyDeviceToHost));
+    /* rows are in key order (name rank, start, end): binary search each splitter */
+    std::vector<uint32_t> order(h->targets.size()), rank(h->targets.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h->targets[a] < h->targets[b]; });
+    for (size_t i = 0; i < order.size(); i++) rank[order[i]] = (uint32_t)i;
+    uint64_t prev = 0;
+    for (int32_t p = 0; p < n_parts; p++) {
+        uint64_t hi = n;
+        if (p + 1 < n_parts) {
+            const uint32_t sr = rank[split_tid[p]];
+            const uint32_t ss = split_start[p];
+            uint64_t lo = prev, up = n;
+            while (lo < up) {
+                uint64_t mid = (lo + up) >> 1;
+                const uint32_t r = rank[chrom[mid]];
+                if (r < sr || (r == sr && i0[mid] < ss)) lo = mid + 1; else up = mid;
+            }
+            hi = lo;
+        }
+        junction_rows[p] = hi - prev;
+        hist_rows[p] = hoff[hi] - hoff[prev];
+        prev = hi;
+    }
+    return IPX_OK;
+}
+
+extern "C" int ipx_partial_export(ipx_handle *h, void *dev_junction_rows, void *dev_hist_rows) {
+    if (!h) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (!h->finalized || !h->dt.slot) return fail(h, IPX_ERR_STATE, "call ipx_partial_sizes first");
+    launch_export_rows(h->tab, h->dt, (JunctionRow *)dev_junction_rows, (HistRow *)dev_hist_rows, h->stream);
+    CU(h, cudaGetLastError());
+    /* the local table has been handed over: empty it so that imports (own share included) rebuild it */
+    CU(h, cudaStreamSynchronize(h->stream));
+    free_device_table(h->dt);
+    h->finalized = false;
+    h->keep_export = false;
+    launch_init_tables(h->tab, h->stream);
+    CU(h, cudaGetLastError());
+    return IPX_OK;
+}
+
+extern "C" int ipx_partial_import(ipx_handle *h, const void *dev_junction_rows, uint64_t n_junction_rows,
+                                  const void *dev_hist_rows, uint64_t n_hist_rows) {
+    if (!h) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (h->finalized) return fail(h, IPX_ERR_STATE, "table already finalized");
+    int rc = alloc_tables(h);
+    if (rc) return rc;
+    {
+        Span s(h, &h->tm_finalize, 2);
+        launch_import_rows(h->tab, (const JunctionRow *)dev_junction_rows, n_junction_rows, (const HistRow *)dev_hist_rows,
+                           n_hist_rows, h->stream);
+    }
+    CU(h, cudaGetLastError());
+    h->dirty = true;
+    return IPX_OK;
+}
+
+/* ------------------------------------------------------------------ merge */
+namespace {
+
+struct MergeJ {
+    int32_t chrom;
+    uint32_t i0, i1, a0, a1;
+    char strand;
+    uint32_t site;
+    uint64_t cnt[3];
+    float conf;
+};
+
+std::string describe(const ipx_handle *h, const ipx_merge_rows *rows, int32_t chrom, uint32_t s, uint32_t e, char strand,
+                     uint32_t site) {
+    /* Junction::get_description (junctions.cc:72-74); mk_coords_str prints ints */
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s:%d-%d[%c/%s]", h->targets[chrom].c_str(), (int)s, (int)e, strand, rows->site_strings[site]);
+    return buf;
+}
+
+}  // namespace
+
+extern "C" int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ipx_table **out, ipx_text *conflict_log) {
+    if (!h || !rows || !out) return IPX_ERR_ARG;
+    *out = nullptr;
+    if (conflict_log) { conflict_log->data = nullptr; conflict_log->len = 0; }
+    cudaSetDevice(h->device);
+    if (h->targets.empty()) return fail(h, IPX_ERR_STATE, "ipx_set_targets must be called first");
+    cudaStream_t st = h->stream;
+    const uint64_t n = rows->n_rows;
+    /* table sized for the worst case of all rows distinct, load <= 0.5 */
+    uint64_t cap = pow2_at_least(n * 2 + 1024);
+    if (h->mt_cap < cap) {
+        cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
+        h->mt = MergeTables{};
+        CU(h, cudaMalloc(&h->mt.keys, cap * 8));
+        CU(h, cudaMalloc(&h->mt.chrom, cap * 4));
+        CU(h, cudaMalloc(&h->mt.stat, cap * sizeof(MStat)));
+        h->mt_cap = cap;
+    }
+    if (!h->d_counters) {
+        CU(h, cudaMalloc(&h->d_counters, 8 * 128));
+        CU(h, cudaMemsetAsync(h->d_counters, 0, 8 * 128, st));
+    }
+    h->mt.cap_mask = h->mt_cap - 1;
+    h->mt.n_keys = h->d_counters + 96;
+    h->mt.overflow = (uint32_t *)(h->d_counters + 112);
+    /* upload the row columns */
+    DeviceBuf b_chrom, b_i0, b_i1, b_a0, b_a1, b_strand, b_sites, b_counts, b_conf;
+    const uint64_t na = n ? n : 1;
+    CU(h, b_chrom.reserve(na * 4)); CU(h, b_i0.reserve(na * 4)); CU(h, b_i1.reserve(na * 4)); CU(h, b_a0.reserve(na * 4));
+    CU(h, b_a1.reserve(na * 4)); CU(h, b_strand.reserve(na)); CU(h, b_sites.reserve(na * 4)); CU(h, b_counts.reserve(na * 12));
+    CU(h, b_conf.reserve(na * 4));
+    if (n) {
+        CU(h, cudaMemcpyAsync(b_chrom.p, rows->chrom, n * 4, cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(b_i0.p, rows->intron_start, n * 4, cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(b_i1.p, rows->intron_end, n * 4, cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(b_a0.p, rows->anchor_start, n * 4, cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(b_a1.p, rows->anchor_end, n * 4, cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(b_strand.p, rows->strand, n, cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(b_sites.p, rows->sites, n * 4, cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(b_counts.p, rows->counts, n * 12, cudaMemcpyHostToDevice, st));
+        CU(h, cudaMemcpyAsync(b_conf.p, rows->confidence, n * 4, cudaMemcpyHostToDevice, st));
+    }
+    MergeRowsView rv{(const int32_t *)b_chrom.p, (const uint32_t *)b_i0.p, (const uint32_t *)b_i1.p, (const uint32_t *)b_a0.p,
+                     (const uint32_t *)b_a1.p, (const char *)b_strand.p, (const uint32_t *)b_sites.p,
+                     (const uint32_t *)b_counts.p, (const float *)b_conf.p, n, 0};
+    unsigned long long n_keys = 0;
+    {
+        Span s(h, &h->tm_merge, 2);
+        launch_merge_init(h->mt, st);
+        launch_merge_fold(rv, h->mt, h->sm_count, st);
+    }
+    CU(h, cudaGetLastError());
+    uint32_t overflow = 0;
+    CU(h, cudaMemcpyAsync(&n_keys, h->mt.n_keys, 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(&overflow, h->mt.overflow, 4, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    if (overflow) return fail(h, IPX_ERR_CAPACITY, "merge table overflow");
+    const uint64_t J = n_keys, Ja = J ? J : 1;
+    /* key order: (name rank, start, end) via two stable radix passes */
+    DeviceBuf k_hi, k_lo, k_hi2, k_lo2, v_a, v_b, cnt, tmp;
+    CU(h, k_hi.reserve(Ja * 8)); CU(h, k_lo.reserve(Ja * 8)); CU(h, k_hi2.reserve(Ja * 8)); CU(h, k_lo2.reserve(Ja * 8));
+    CU(h, v_a.reserve(Ja * 4)); CU(h, v_b.reserve(Ja * 4)); CU(h, cnt.reserve(8));
+    CU(h, cudaMemsetAsync(cnt.p, 0, 8, st));
+    HostTable *ht = new HostTable();
+    memset(&ht->t, 0, sizeof(ht->t));
+    std::vector<uint32_t> site;
+    std::vector<uint8_t> slow;
+    std::vector<unsigned long long> counts;
+    {
+        Span s(h, &h->tm_merge, 6);
+        launch_merge_compact(h->mt, (unsigned long long *)cnt.p, (unsigned long long *)k_lo.p, (uint32_t *)v_a.p, st);
+        if (J) {
+            /* LSD order: stable sort by (start, end), then stable sort by chromosome-name rank */
+            size_t tb1 = 0, tb2 = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tb1, (unsigned long long *)k_lo.p, (unsigned long long *)k_lo2.p,
+                                            (uint32_t *)v_a.p, (uint32_t *)v_b.p, (int)J, 0, 64, st);
+            cub::DeviceRadixSort::SortPairs(nullptr, tb2, (unsigned long long *)k_hi.p, (unsigned long long *)k_hi2.p,
+                                            (uint32_t *)v_b.p, (uint32_t *)v_a.p, (int)J, 0, 32, st);
+            CU(h, tmp.reserve(std::max(tb1, tb2)));
+            size_t tb = tmp.cap;
+            cub::DeviceRadixSort::SortPairs(tmp.p, tb, (unsigned long long *)k_lo.p, (unsigned long long *)k_lo2.p,
+                                            (uint32_t *)v_a.p, (uint32_t *)v_b.p, (int)J, 0, 64, st);
+            launch_merge_rank_keys(h->mt, h->d_name_rank, (const uint32_t *)v_b.p, J, (unsigned long long *)k_hi.p, st);
+            tb = tmp.cap;
+            cub::DeviceRadixSort::SortPairs(tmp.p, tb, (unsigned long long *)k_hi.p, (unsigned long long *)k_hi2.p,
+                                            (uint32_t *)v_b.p, (uint32_t *)v_a.p, (int)J, 0, 32, st);
+        }
+        DeviceBuf o_chrom, o_i0, o_i1, o_a0, o_a1, o_site, o_counts, o_conf, o_strand, o_slow;
+        CU(h, o_chrom.reserve(Ja * 4)); CU(h, o_i0.reserve(Ja * 4)); CU(h, o_i1.reserve(Ja * 4)); CU(h, o_a0.reserve(Ja * 4));
+        CU(h, o_a1.reserve(Ja * 4)); CU(h, o_site.reserve(Ja * 4)); CU(h, o_counts.reserve(Ja * 24)); CU(h, o_conf.reserve(Ja * 4));
+        CU(h, o_strand.reserve(Ja)); CU(h, o_slow.reserve(Ja));
+        MergeOut mo{(int32_t *)o_chrom.p, (uint32_t *)o_i0.p, (uint32_t *)o_i1.p, (uint32_t *)o_a0.p, (uint32_t *)o_a1.p,
+                    (uint32_t *)o_site.p, (unsigned long long *)o_counts.p, (float *)o_conf.p, (char *)o_strand.p,
+                    (uint8_t *)o_slow.p};
+        launch_merge_gather(h->mt, (const uint32_t *)v_a.p, J, mo, st);
+        cudaError_t e = cudaSuccess;
+        auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+        chk(d2h(ht->chrom, o_chrom.p, J, st)); chk(d2h(ht->i0, o_i0.p, J, st)); chk(d2h(ht->i1, o_i1.p, J, st));
+        chk(d2h(ht->a0, o_a0.p, J, st)); chk(d2h(ht->a1, o_a1.p, J, st)); chk(d2h(site, o_site.p, J, st));
+        chk(d2h(counts, o_counts.p, J * 3, st)); chk(d2h(ht->conf, o_conf.p, J, st)); chk(d2h(ht->strand, o_strand.p, J, st));
+        chk(d2h(slow, o_slow.p, J, st));
+        chk(cudaStreamSynchronize(st));
+        chk(cudaGetLastError());
+        o_chrom.release(); o_i0.release(); o_i1.release(); o_a0.release(); o_a1.release(); o_site.release();
+        o_counts.release(); o_conf.release(); o_strand.release(); o_slow.release();
+        if (e != cudaSuccess) {
+            delete ht;
+            return fail(h, IPX_ERR_CUDA, "CUDA error %s in merge: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+        }
+    }
+    for (DeviceBuf *b : {&b_chrom, &b_i0, &b_i1, &b_a0, &b_a1, &b_strand, &b_sites, &b_counts, &b_conf, &k_hi, &k_lo, &k_hi2,
+                         &k_lo2, &v_a, &v_b, &cnt, &tmp})
+        b->release();
+    ht->counts.assign(counts.begin(), counts.end());
+
+    /* introns whose fold depends on row order: redo them exactly as Junction::merge does (junctions.cc:76-105) */
+    std::string log;
+    std::unordered_map<uint64_t, std::vector<uint64_t>> slow_by_key; /* (start << 32 | end) -> table rows */
+    uint64_t n_slow = 0;
+    for (uint64_t i = 0; i < J; i++)
+        if (slow[i]) {
+            slow_by_key[((uint64_t)ht->i0[i] << 32) | ht->i1[i]].push_back(i);
+            n_slow++;
+        }
+    if (n_slow) {
+        std::vector<char> started(J, 0);
+        for (uint64_t r = 0; r < n; r++) {
+            auto it = slow_by_key.find(((uint64_t)rows->intron_start[r] << 32) | rows->intron_end[r]);
+            if (it == slow_by_key.end()) continue;
+            uint64_t ti = ~0ull;
+            for (uint64_t cand : it->second)
+                if (ht->chrom[cand] == rows->chrom[r]) ti = cand;
+            if (ti == ~0ull) continue;
+            const char rstrand = rows->strand[r];
+            const uint32_t rsite = rows->sites[r];
+            if (!started[ti]) {
+                started[ti] = 1;
+                ht->a0[ti] = rows->anchor_start[r];
+                ht->a1[ti] = rows->anchor_end[r];
+                ht->strand[ti] = rstrand;
+                site[ti] = rsite;
+                for (int c = 0; c < 3; c++) ht->counts[3 * ti + c] = rows->counts[3 * r + c];
+                ht->conf[ti] = rows->confidence[r];
+                continue;
+            }
+            bool update_strand = false;
+            if (rstrand != '.' && ht->strand[ti] == '.') {
+                update_strand = true;
+            } else if (rstrand == '.' && ht->strand[ti] != '.') {
+            } else if (rstrand != ht->strand[ti]) {
+                log += "intron records have different strand:" +
+                       describe(h, rows, rows->chrom[r], rows->intron_start[r], rows->intron_end[r], rstrand, rsite) + " with " +
+                       describe(h, rows, ht->chrom[ti], ht->i0[ti], ht->i1[ti], ht->strand[ti], site[ti]) + "\n";
+                continue;
+            } else if (strcmp(rows->site_strings[rsite], rows->site_strings[site[ti]]) != 0) {
+                std::string msg = "intron records have different splice sites:" +
+                                  describe(h, rows, rows->chrom[r], rows->intron_start[r], rows->intron_end[r], rstrand, rsite) +
+                                  " with " + describe(h, rows, ht->chrom[ti], ht->i0[ti], ht->i1[ti], ht->strand[ti], site[ti]);
+                if (conflict_log) give_text(log, conflict_log);
+                delete ht;
+                return fail(h, IPX_ERR_MERGE, "%s", msg.c_str());
+            }
+            ht->a0[ti] = std::min(rows->anchor_start[r], ht->a0[ti]);
+            ht->a1[ti] = std::max(rows->anchor_end[r], ht->a1[ti]);
+            for (int c = 0; c < 3; c++) ht->counts[3 * ti + c] += rows->counts[3 * r + c];
+            ht->conf[ti] = std::max(rows->confidence[r], ht->conf[ti]);
+            if (update_strand) {
+                ht->strand[ti] = rstrand;
+                site[ti] = rsite;
+            }
+        }
+    }
+    ht->sites.assign(J * 8, 0);
+    for (uint64_t i = 0; i < J; i++) snprintf(ht->sites.data() + 8 * i, 8, "%s", rows->site_strings[site[i]]);
+    ht->ijunc.assign(J, 0);
+    ht->hist_off.assign(J + 1, 0);
+    ht->bind();
+    /* sort_by_anchors + renumber_junctions (intronProspectorMerge.cc:201-223): same std::sort, same start order */
+    std::vector<const char *> names(h->targets.size());
+    for (size_t i = 0; i < names.size(); i++) names[i] = h->targets[i].c_str();
+    std::vector<uint64_t> idx;
+    sort_rows(&ht->t, names.data(), true, 0, J, idx);
+    for (uint64_t k = 0; k < J; k++) ht->ijunc[idx[k]] = (uint32_t)k;
+    h->totals.merge_rows += n;
+    h->totals.junctions += J;
+    if (conflict_log) give_text(log, conflict_log);
+    *out = &ht->t;
+    return IPX_OK;
+}

@@ -1,0 +1,94 @@
+/* ipx_engine.h -- internal interface between the C ABI (ipx_api.cc) and the CUDA side (ipx_kernels.cu). */
+#ifndef IPX_ENGINE_H
+#define IPX_ENGINE_H
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "ipx_table.cuh"
+
+namespace ipx {
+
+/* device pointers of one batch (see ipx_batch in include/ipx.h) */
+struct BatchView {
+    const int32_t *tid;
+    const int32_t *pos;
+    const uint16_t *flag;
+    const uint8_t *nh;
+    const uint8_t *xs;
+    const uint32_t *cigar_off;
+    const uint32_t *cigar;
+    uint64_t n;
+    uint64_t seq_base;
+};
+
+/* HBM-resident genome: raw FASTA characters per sequence */
+struct GenomeView {
+    const char *const *seq;     /* [n_seqs] device pointers */
+    const uint64_t *len;        /* [n_seqs] */
+    const int32_t *target_seq;  /* [n_targets] genome sequence of each target or -1 */
+    int32_t n_targets;
+    int32_t have_genome;
+    int32_t skip_missing;
+    int32_t filter_canon;       /* 1 when the canon filter is active */
+};
+
+/* finished table, device side, key order */
+struct DeviceTable {
+    uint64_t n;        /* junctions */
+    uint64_t n_hist;   /* histogram runs */
+    int32_t *chrom;
+    uint32_t *i0, *i1, *a0, *a1, *ijunc;
+    char *strand;
+    char *sites;       /* [n][8] */
+    unsigned long long *counts; /* [n][3] */
+    unsigned long long *T;      /* [n] creation sequence value (for cross-flush numbering / export) */
+    unsigned long long *hist_off; /* [n+1] */
+    uint32_t *hist_cnt;           /* [n_hist] */
+    uint32_t *hist_offset;        /* [n_hist] the uint16 offsets themselves (export only) */
+    uint32_t *slot;               /* [n] table slot of each junction (export only) */
+};
+
+/* packed rows exchanged between ranks (ipx_partial_export / ipx_partial_import) */
+struct JunctionRow {
+    unsigned long long first[3];
+    unsigned long long cnt[3];
+    int32_t tid;
+    uint32_t i0, i1, a0, a1;
+    uint32_t pad;
+};
+struct HistRow {
+    int32_t tid;
+    uint32_t i0, i1;
+    uint32_t cnt;
+    uint32_t offset;
+    uint32_t pad;
+};
+
+enum ExtractMode { MODE_SINGLE = 0, MODE_PASS1 = 1, MODE_PASS2 = 2 };
+
+/* kernels' launchers; all asynchronous on `st` */
+void launch_init_tables(const Tables &t, cudaStream_t st);
+void launch_extract(int mode, const BatchView &b, const ExtractParams &p, const Tables &t, int sm_count, cudaStream_t st);
+void launch_resolve_T(const Tables &t, const GenomeView &g, cudaStream_t st);
+void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh,
+                        cudaStream_t st);
+
+/* workspace for finalize; grown on demand by the engine */
+struct FinalizeWork {
+    void *cub_tmp = nullptr;
+    size_t cub_tmp_bytes = 0;
+    unsigned long long *d_count = nullptr; /* [4] */
+    uint32_t *slot_rank = nullptr;         /* [cap] key-order rank of each slot, 0xFFFFFFFF = not a junction */
+    uint64_t slot_rank_cap = 0;
+};
+
+/* key-order sort, sjN ranking, histogram ordering, gather; synchronises on the counts it needs.
+ * `name_rank[tid]` orders targets like std::string::operator< on their names. Returns cudaError_t. */
+cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, int32_t n_targets,
+                            FinalizeWork &w, DeviceTable &out, bool keep_export_columns, cudaStream_t st);
+void free_device_table(DeviceTable &t);
+
+/* export rows for destination ranks: rows [0, n) of the finished table are already in key order */
+void launch_export_rows(const Tables &t, const DeviceTable &dt, JunctionRow *jr, HistRow *hr, cudaStream_t st);
+
+}  // namespace ipx
+#endif

@@ -1,0 +1,591 @@
+/* ipx_kernels.cu -- sm_100a kernels of the junction-extraction path.
+ *
+ *  k_extract<MODE>   K1+K2 fused: one thread walks one alignment's CIGAR (ipx_walk.cuh) and folds every
+ *                    junction event straight into the L2-resident junction / offset tables, so events
+ *                    never travel through HBM.  HBM traffic is the record columns and the live CIGAR
+ *                    words, read once, coalesced.
+ *                      MODE_SINGLE  no canon filter: insert + first-seen + counts + anchors + offsets
+ *                      MODE_PASS1   canon filter:    insert + first-seen per strand class only
+ *                      MODE_PASS2   canon filter:    count events at or after the creation threshold T
+ *  k_resolve_T       K3: donor/acceptor gather from the HBM genome, per junction, and the choice of the
+ *                    creating event T = first event whose (key, strand class) passes the filter
+ *  finalize_tables   compaction, key-order sort, sjN ranking, offset-histogram ordering, output gather
+ *  k_import_*        fold partial tables received from other GPUs (multi-GPU exchange)
+ *
+ * Reference semantics: SURVEY.md section 8(a) A1-A8 (junctions_extractor.cc:49-95,124-319,322-530).
+ */
+#include <cub/cub.cuh>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ipx_engine.h"
+
+namespace ipx {
+
+/* ------------------------------------------------------------------ table initialisation */
+__global__ void k_init_tables(Tables t) {
+    const uint64_t cap = t.cap_mask + 1, hcap = t.hcap_mask + 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
+        t.keys[i] = EMPTY64;
+        JStat s;
+        s.first[0] = s.first[1] = s.first[2] = EMPTY64;
+        s.T = EMPTY64;
+        s.cnt[0] = s.cnt[1] = s.cnt[2] = 0ull;
+        s.a0 = 0xFFFFFFFFu;
+        s.a1 = 0u;
+        t.stat[i] = s;
+    }
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hcap; i += stride) {
+        t.hkeys[i] = EMPTY64;
+        t.hcnt[i] = 0u;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *t.n_keys = 0ull;
+        *t.n_hist = 0ull;
+        *t.err_sv = EMPTY64;
+        *t.overflow = 0u;
+    }
+}
+
+void launch_init_tables(const Tables &t, cudaStream_t st) {
+    k_init_tables<<<148 * 8, 256, 0, st>>>(t);
+}
+
+/* ------------------------------------------------------------------ K1+K2: extract and aggregate */
+template <int MODE>
+struct EventSink {
+    const Tables &t;
+    const ExtractParams &p;
+    int32_t tid;
+    int64_t pos;
+    uint64_t record_seq;
+    uint32_t cat;
+    char strand;
+    int cls;
+    bool may_emit;
+    uint32_t n_events;
+
+    __device__ __forceinline__ void operator()(const Candidate &c) {
+        if (!may_emit || !junction_qc(p, c)) return;
+        n_events++;
+        if (c.intron_start < 0 || c.intron_start > 0x7FFFFFFFll) {
+            atomicExch(t.overflow, 3u); /* outside what a BAM position can hold */
+            return;
+        }
+        const uint64_t key = make_key(t.kl, tid, c.intron_start, c.intron_end);
+        const uint64_t sv = make_sv(record_seq, c.ordinal, strand);
+        if (MODE == MODE_PASS2) {
+            const uint64_t slot = junction_find(t, key);
+            if (slot > t.cap_mask) return;
+            JStat *s = &t.stat[slot];
+            const unsigned long long T = *((volatile unsigned long long *)&s->T);
+            if (T == EMPTY64 || sv < T) return; /* before the junction exists: dropped (A6) */
+            stat_accumulate(s, cat, (uint32_t)c.anchor_start, (uint32_t)c.anchor_end);
+            hist_add(t, slot, (uint32_t)(c.intron_start - pos) & 0xFFFFu, 1u);
+        } else {
+            const uint64_t slot = junction_find_or_insert(t, key);
+            if (slot > t.cap_mask) return;
+            JStat *s = &t.stat[slot];
+            stat_first(s, cls, sv);
+            if (MODE == MODE_SINGLE) {
+                stat_accumulate(s, cat, (uint32_t)c.anchor_start, (uint32_t)c.anchor_end);
+                hist_add(t, slot, (uint32_t)(c.intron_start - pos) & 0xFFFFu, 1u);
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+    return v;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_extract(BatchView b, ExtractParams p, Tables t) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long live_words = 0ull, events = 0ull;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < b.n; r += stride) {
+        const uint32_t c0 = __ldg(&b.cigar_off[r]);
+        const uint32_t c1 = __ldg(&b.cigar_off[r + 1]);
+        const int32_t tid = __ldg(&b.tid[r]);
+        const uint32_t flag = __ldg(&b.flag[r]);
+        const uint32_t n_cigar = c1 - c0;
+        if (!record_is_live(n_cigar, tid, flag)) continue;
+        live_words += n_cigar;
+        const int64_t pos = __ldg(&b.pos[r]);
+        const uint32_t nh = __ldg(&b.nh[r]);
+        const uint32_t xs = __ldg(&b.xs[r]);
+        const char strand = read_strand(p.strandness, flag, xs);
+        EventSink<MODE> sink{t, p, tid, pos, b.seq_base + r, read_category(flag, nh), strand, strand_class(strand),
+                             read_may_emit(p, flag, nh), 0u};
+        WalkState w;
+        w.init(pos);
+        uint32_t bad = 0u;
+        const uint32_t *cig = b.cigar + c0;
+        for (uint32_t k = 0; k < n_cigar; ++k) {
+            bad = walk_op(w, __ldg(&cig[k]), p.max_anchor_indel_size, sink);
+            if (bad) break;
+        }
+        if (bad) {
+            /* the reference throws here; keep the first such record in stream order */
+            atomicMin(t.err_sv, make_err_cigar(b.seq_base + r, bad & 15u));
+        } else {
+            walk_finish(w, sink);
+        }
+        events += sink.n_events;
+    }
+    /* one atomic per warp for the unit counters */
+    live_words = warp_sum(live_words);
+    events = warp_sum(events);
+    if ((threadIdx.x & 31) == 0 && MODE != MODE_PASS2) {
+        if (live_words) atomicAdd(t.n_live, live_words);
+        if (events) atomicAdd(t.n_events, events);
+    }
+}
+
+void launch_extract(int mode, const BatchView &b, const ExtractParams &p, const Tables &t, int sm_count,
+                    cudaStream_t st) {
+    if (b.n == 0) return;
+    const int threads = 256;
+    uint64_t want = (b.n + threads - 1) / threads;
+    uint64_t max_blocks = (uint64_t)sm_count * 8;
+    int blocks = (int)(want < max_blocks ? want : max_blocks);
+    switch (mode) {
+        case MODE_SINGLE: k_extract<MODE_SINGLE><<<blocks, threads, 0, st>>>(b, p, t); break;
+        case MODE_PASS1: k_extract<MODE_PASS1><<<blocks, threads, 0, st>>>(b, p, t); break;
+        default: k_extract<MODE_PASS2><<<blocks, threads, 0, st>>>(b, p, t); break;
+    }
+}
+
+/* ------------------------------------------------------------------ K3: motif gather and threshold */
+__device__ __forceinline__ char up(char c) { return (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; }
+__device__ __forceinline__ char low(char c) { return (c >= 'A' && c <= 'Z') ? (char)(c + 32) : c; }
+__device__ __forceinline__ char comp(char c) {
+    /* dna_reverse_complement's table (genome.cc:14-28): only ACGT / acgt are mapped */
+    switch (c) {
+        case 'A': return 'T';
+        case 'T': return 'A';
+        case 'G': return 'C';
+        case 'C': return 'G';
+        case 'a': return 't';
+        case 't': return 'a';
+        case 'g': return 'c';
+        case 'c': return 'g';
+        default: return c;
+    }
+}
+/* is_canonical (splice_juncs.cc:25-38) for an upper-cased donor pair d0 d1 and acceptor pair a0 a1 */
+__device__ __forceinline__ bool canon4(char d0, char d1, char a0, char a1) {
+    return (d0 == 'G' && d1 == 'T' && a0 == 'A' && a1 == 'G') || (d0 == 'G' && d1 == 'C' && a0 == 'A' && a1 == 'G') ||
+           (d0 == 'A' && d1 == 'T' && a0 == 'A' && a1 == 'C');
+}
+
+enum : int { MOTIF_OK = 0, MOTIF_NONE = 1, MOTIF_ERR_MISSING = 2, MOTIF_ERR_LEN_DONOR = 3, MOTIF_ERR_LEN_ACCEPTOR = 4 };
+
+/* Genome::fetch clipping (genome.cc:62-74 over faidx_fetch_seq): number of characters a fetch of [s, e) returns */
+__device__ __forceinline__ int64_t fetch_len(int64_t len, int64_t s, int64_t e) {
+    int64_t b = s, en = e - 1;
+    if (en < b - 1) en = b - 1;
+    if (b < 0) b = 0;
+    if (b >= len) b = len;
+    if (en < 0) en = 0; else if (en >= len) en = len - 1;
+    int64_t got = en - b + 1;
+    return got < 0 ? 0 : got;
+}
+
+/* get_splice_sites' fetches (junctions_extractor.cc:405-420): the four upper-cased characters, forward strand */
+__device__ __forceinline__ int motif_fetch(const GenomeView &g, int32_t tid, uint32_t i0, uint32_t i1, char f[4]) {
+    if (!g.have_genome) return MOTIF_NONE;
+    const int32_t gi = (tid >= 0 && tid < g.n_targets) ? g.target_seq[tid] : -1;
+    if (gi < 0) return g.skip_missing ? MOTIF_NONE : MOTIF_ERR_MISSING;
+    const int64_t len = (int64_t)g.len[gi];
+    if (fetch_len(len, i0, (int64_t)i0 + 2) != 2) return MOTIF_ERR_LEN_DONOR;
+    if (fetch_len(len, (int64_t)i1 - 2, i1) != 2) return MOTIF_ERR_LEN_ACCEPTOR;
+    const char *s = g.seq[gi];
+    f[0] = up(s[i0]);
+    f[1] = up(s[i0 + 1]);
+    f[2] = up(s[i1 - 2]);
+    f[3] = up(s[i1 - 1]);
+    return MOTIF_OK;
+}
+
+/* For every junction slot without a creation threshold yet: T = first event (stream order) whose strand class
+ * passes junction_filter_check (add_junction, junctions_extractor.cc:494-502; SURVEY.md 8a "A6"). */
+__global__ void k_resolve_T(Tables t, GenomeView g) {
+    const uint64_t cap = t.cap_mask + 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
+        const unsigned long long key = t.keys[i];
+        if (key == EMPTY64) continue;
+        JStat *s = &t.stat[i];
+        if (s->T != EMPTY64) continue;
+        const unsigned long long f0 = s->first[CLS_PLUS], f1 = s->first[CLS_MINUS], f2 = s->first[CLS_DOT];
+        bool p0 = true, p1 = true, p2 = true;
+        const int32_t tid = key_tid(t.kl, key);
+        const uint32_t i0 = key_start(t.kl, key), i1 = i0 + key_len(t.kl, key);
+        char f[4];
+        const int rc = motif_fetch(g, tid, i0, i1, f);
+        if (rc >= MOTIF_ERR_MISSING) {
+            /* Genome::fetch throws at the first event that needs the sequence */
+            unsigned long long fm = f0 < f1 ? f0 : f1;
+            fm = fm < f2 ? fm : f2;
+            if (fm != EMPTY64) atomicMin(t.err_sv, make_err_genome(fm, rc));
+            continue;
+        }
+        if (rc == MOTIF_OK && g.filter_canon) {
+            p0 = canon4(f[0], f[1], f[2], f[3]);
+            p1 = canon4(comp(f[3]), comp(f[2]), comp(f[1]), comp(f[0]));
+            p2 = p0 || p1;
+        }
+        unsigned long long T = EMPTY64;
+        if (p0 && f0 < T) T = f0;
+        if (p1 && f1 < T) T = f1;
+        if (p2 && f2 < T) T = f2;
+        s->T = T;
+    }
+}
+
+void launch_resolve_T(const Tables &t, const GenomeView &g, cudaStream_t st) {
+    k_resolve_T<<<148 * 8, 256, 0, st>>>(t, g);
+}
+
+/* ------------------------------------------------------------------ finalize */
+/* gather every created junction: its slot and its key-order sort key */
+__global__ void k_compact_junctions(Tables t, const uint32_t *name_rank, unsigned long long *d_count,
+                                    unsigned long long *sort_key, uint32_t *slot_out) {
+    const uint64_t cap = t.cap_mask + 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < cap; base += stride) {
+        const uint64_t i = base + threadIdx.x;
+        bool take = false;
+        unsigned long long key = EMPTY64;
+        if (i < cap) {
+            key = t.keys[i];
+            take = (key != EMPTY64) && (t.stat[i].T != EMPTY64);
+        }
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, take);
+        if (mask == 0u) continue;
+        const int lane = threadIdx.x & 31;
+        unsigned long long warp_base = 0ull;
+        if (lane == 0) warp_base = atomicAdd(&d_count[0], (unsigned long long)__popc(mask));
+        warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
+        if (take) {
+            const uint64_t o = warp_base + __popc(mask & ((1u << lane) - 1u));
+            const uint64_t tid = (uint64_t)key_tid(t.kl, key);
+            const uint64_t low = key & ((1ull << t.kl.tid_shift) - 1ull);
+            sort_key[o] = ((unsigned long long)name_rank[tid] << t.kl.tid_shift) | low;
+            slot_out[o] = (uint32_t)i;
+        }
+    }
+}
+
+__global__ void k_fill_slot_rank(const uint32_t *sorted_slot, uint64_t n, uint32_t *slot_rank) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slot_rank[sorted_slot[i]] = (uint32_t)i;
+}
+
+__global__ void k_gather_T(Tables t, const uint32_t *sorted_slot, uint64_t n, unsigned long long *T_out,
+                           uint32_t *idx_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        T_out[i] = t.stat[sorted_slot[i]].T;
+        idx_out[i] = (uint32_t)i;
+    }
+}
+
+__global__ void k_scatter_ijunc(const uint32_t *idx_by_T, uint64_t n, uint32_t *ijunc) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ijunc[idx_by_T[i]] = (uint32_t)i;
+}
+
+/* one output row per junction, in key order: attributes of the creating event after motif correction
+ * (get_splice_sites + correct_strand, junctions_extractor.cc:419-444) */
+__global__ void k_gather_rows(Tables t, GenomeView g, const uint32_t *sorted_slot, uint64_t n, DeviceTable out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t slot = sorted_slot[i];
+    const unsigned long long key = t.keys[slot];
+    const JStat s = t.stat[slot];
+    const int32_t tid = key_tid(t.kl, key);
+    const uint32_t i0 = key_start(t.kl, key), i1 = i0 + key_len(t.kl, key);
+    out.chrom[i] = tid;
+    out.i0[i] = i0;
+    out.i1[i] = i1;
+    out.a0[i] = s.a0;
+    out.a1[i] = s.a1;
+    out.counts[3 * i + 0] = s.cnt[0];
+    out.counts[3 * i + 1] = s.cnt[1];
+    out.counts[3 * i + 2] = s.cnt[2];
+    out.T[i] = s.T;
+    if (out.slot) out.slot[i] = slot;
+    char strand = (char)(s.T & 0xFFull);
+    char site[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    char f[4];
+    if (motif_fetch(g, tid, i0, i1, f) == MOTIF_OK) {
+        char d0 = f[0], d1 = f[1], a0 = f[2], a1 = f[3];
+        const char r0 = comp(f[3]), r1 = comp(f[2]), r2 = comp(f[1]), r3 = comp(f[0]);
+        bool canon;
+        if (strand == '-') {
+            d0 = r0; d1 = r1; a0 = r2; a1 = r3;
+            canon = canon4(d0, d1, a0, a1);
+        } else if (strand == '.') {
+            canon = canon4(d0, d1, a0, a1);
+            if (canon) {
+                strand = '+';
+            } else if (canon4(r0, r1, r2, r3)) {
+                strand = '-';
+                d0 = r0; d1 = r1; a0 = r2; a1 = r3;
+                canon = true;
+            }
+        } else {
+            canon = canon4(d0, d1, a0, a1);
+        }
+        if (!canon) { d0 = low(d0); d1 = low(d1); a0 = low(a0); a1 = low(a1); }
+        site[0] = d0; site[1] = d1; site[2] = '/'; site[3] = a0; site[4] = a1;
+    }
+    out.strand[i] = strand;
+    for (int k = 0; k < 8; ++k) out.sites[8 * i + k] = site[k];
+}
+
+/* every (junction, offset) pair of a created junction -> (rank << 16 | offset, count) */
+__global__ void k_compact_hist(Tables t, const uint32_t *slot_rank, unsigned long long *d_count,
+                               unsigned long long *hkey_out, uint32_t *hcnt_out, int count_only) {
+    const uint64_t hcap = t.hcap_mask + 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < hcap; base += stride) {
+        const uint64_t i = base + threadIdx.x;
+        bool take = false;
+        unsigned long long hk = EMPTY64;
+        uint32_t rank = 0xFFFFFFFFu;
+        if (i < hcap) {
+            hk = t.hkeys[i];
+            if (hk != EMPTY64) {
+                rank = slot_rank[hk >> 16];
+                take = rank != 0xFFFFFFFFu;
+            }
+        }
+        const unsigned mask = __ballot_sync(0xFFFFFFFFu, take);
+        if (mask == 0u) continue;
+        const int lane = threadIdx.x & 31;
+        unsigned long long warp_base = 0ull;
+        if (lane == 0) warp_base = atomicAdd(&d_count[1], (unsigned long long)__popc(mask));
+        warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
+        if (take && !count_only) {
+            const uint64_t o = warp_base + __popc(mask & ((1u << lane) - 1u));
+            hkey_out[o] = ((unsigned long long)rank << 16) | (hk & 0xFFFFull);
+            hcnt_out[o] = t.hcnt[i];
+        }
+    }
+}
+
+/* hist_off[r] = index of the first run of junction r in the sorted run list */
+__global__ void k_hist_offsets(const unsigned long long *sorted_hkey, uint64_t n_hist, uint64_t n_junc,
+                               unsigned long long *hist_off, uint32_t *hist_offset_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) hist_off[n_junc] = n_hist;
+    if (i >= n_hist) return;
+    const uint64_t r = sorted_hkey[i] >> 16;
+    if (hist_offset_out) hist_offset_out[i] = (uint32_t)(sorted_hkey[i] & 0xFFFFull);
+    if (i == 0 || (sorted_hkey[i - 1] >> 16) != r) hist_off[r] = i;
+}
+
+#define IPX_CU(x)                          \
+    do {                                   \
+        cudaError_t e__ = (x);             \
+        if (e__ != cudaSuccess) return e__; \
+    } while (0)
+
+static cudaError_t ensure_tmp(FinalizeWork &w, size_t bytes) {
+    if (bytes > w.cub_tmp_bytes) {
+        if (w.cub_tmp) cudaFree(w.cub_tmp);
+        w.cub_tmp = nullptr;
+        w.cub_tmp_bytes = 0;
+        IPX_CU(cudaMalloc(&w.cub_tmp, bytes));
+        w.cub_tmp_bytes = bytes;
+    }
+    return cudaSuccess;
+}
+
+void free_device_table(DeviceTable &t) {
+    cudaFree(t.chrom); cudaFree(t.i0); cudaFree(t.i1); cudaFree(t.a0); cudaFree(t.a1); cudaFree(t.ijunc);
+    cudaFree(t.strand); cudaFree(t.sites); cudaFree(t.counts); cudaFree(t.T); cudaFree(t.hist_off);
+    cudaFree(t.hist_cnt); cudaFree(t.hist_offset); cudaFree(t.slot);
+    t = DeviceTable();
+}
+
+static inline unsigned blocks_for(uint64_t n, unsigned threads) {
+    uint64_t b = (n + threads - 1) / threads;
+    return (unsigned)(b ? b : 1);
+}
+
+cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, int32_t n_targets,
+                            FinalizeWork &w, DeviceTable &out, bool keep_export, cudaStream_t st) {
+    (void)n_targets;
+    const uint64_t cap = t.cap_mask + 1;
+    out = DeviceTable();
+    if (!w.d_count) IPX_CU(cudaMalloc(&w.d_count, 4 * sizeof(unsigned long long)));
+    if (w.slot_rank_cap < cap) {
+        if (w.slot_rank) cudaFree(w.slot_rank);
+        IPX_CU(cudaMalloc(&w.slot_rank, cap * sizeof(uint32_t)));
+        w.slot_rank_cap = cap;
+    }
+    IPX_CU(cudaMemsetAsync(w.d_count, 0, 4 * sizeof(unsigned long long), st));
+    IPX_CU(cudaMemsetAsync(w.slot_rank, 0xFF, cap * sizeof(uint32_t), st));
+
+    /* creation thresholds for anything still unresolved */
+    k_resolve_T<<<148 * 8, 256, 0, st>>>(t, g);
+
+    /* number of keys bounds the number of junctions */
+    unsigned long long n_keys = 0;
+    IPX_CU(cudaMemcpyAsync(&n_keys, t.n_keys, sizeof(n_keys), cudaMemcpyDeviceToHost, st));
+    IPX_CU(cudaStreamSynchronize(st));
+    const uint64_t nk = n_keys ? n_keys : 1;
+
+    unsigned long long *sort_key = nullptr, *sort_key2 = nullptr;
+    uint32_t *slot_a = nullptr, *slot_b = nullptr;
+    IPX_CU(cudaMalloc(&sort_key, nk * 8));
+    IPX_CU(cudaMalloc(&sort_key2, nk * 8));
+    IPX_CU(cudaMalloc(&slot_a, nk * 4));
+    IPX_CU(cudaMalloc(&slot_b, nk * 4));
+    k_compact_junctions<<<148 * 8, 256, 0, st>>>(t, d_name_rank, w.d_count, sort_key, slot_a);
+    unsigned long long n_j = 0;
+    IPX_CU(cudaMemcpyAsync(&n_j, &w.d_count[0], sizeof(n_j), cudaMemcpyDeviceToHost, st));
+    IPX_CU(cudaStreamSynchronize(st));
+    const uint64_t n = n_j, na = n ? n : 1;
+
+    /* key order: chromosome-name rank, intron_start, intron_end */
+    size_t tmp_bytes = 0;
+    IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, sort_key, sort_key2, slot_a, slot_b, (int)n, 0, 64, st));
+    IPX_CU(ensure_tmp(w, tmp_bytes));
+    if (n) IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp_bytes, sort_key, sort_key2, slot_a, slot_b, (int)n, 0, 64, st));
+    const uint32_t *sorted_slot = slot_b;
+    if (n) k_fill_slot_rank<<<blocks_for(n, 256), 256, 0, st>>>(sorted_slot, n, w.slot_rank);
+
+    IPX_CU(cudaMalloc(&out.chrom, na * 4));
+    IPX_CU(cudaMalloc(&out.i0, na * 4));
+    IPX_CU(cudaMalloc(&out.i1, na * 4));
+    IPX_CU(cudaMalloc(&out.a0, na * 4));
+    IPX_CU(cudaMalloc(&out.a1, na * 4));
+    IPX_CU(cudaMalloc(&out.ijunc, na * 4));
+    IPX_CU(cudaMalloc(&out.strand, na));
+    IPX_CU(cudaMalloc(&out.sites, na * 8));
+    IPX_CU(cudaMalloc(&out.counts, na * 24));
+    IPX_CU(cudaMalloc(&out.T, na * 8));
+    IPX_CU(cudaMalloc(&out.hist_off, (na + 1) * 8));
+    if (keep_export) IPX_CU(cudaMalloc(&out.slot, na * 4));
+    out.n = n;
+
+    /* sjN: rank of the creating event in stream order */
+    if (n) {
+        uint32_t *idx_a = slot_a; /* reuse */
+        uint32_t *idx_b = nullptr;
+        IPX_CU(cudaMalloc(&idx_b, na * 4));
+        k_gather_T<<<blocks_for(n, 256), 256, 0, st>>>(t, sorted_slot, n, sort_key, idx_a);
+        size_t tb = 0;
+        IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, sort_key, sort_key2, idx_a, idx_b, (int)n, 0, 64, st));
+        IPX_CU(ensure_tmp(w, tb));
+        IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, sort_key, sort_key2, idx_a, idx_b, (int)n, 0, 64, st));
+        k_scatter_ijunc<<<blocks_for(n, 256), 256, 0, st>>>(idx_b, n, out.ijunc);
+        k_gather_rows<<<blocks_for(n, 256), 256, 0, st>>>(t, g, sorted_slot, n, out);
+        IPX_CU(cudaStreamSynchronize(st));
+        cudaFree(idx_b);
+    }
+
+    /* offset histogram: count, gather, order by (junction rank, offset) */
+    k_compact_hist<<<148 * 8, 256, 0, st>>>(t, w.slot_rank, w.d_count, nullptr, nullptr, 1);
+    unsigned long long n_h = 0;
+    IPX_CU(cudaMemcpyAsync(&n_h, &w.d_count[1], sizeof(n_h), cudaMemcpyDeviceToHost, st));
+    IPX_CU(cudaStreamSynchronize(st));
+    const uint64_t nh = n_h, nha = nh ? nh : 1;
+    unsigned long long *hk_a = nullptr, *hk_b = nullptr;
+    uint32_t *hc_a = nullptr;
+    IPX_CU(cudaMalloc(&hk_a, nha * 8));
+    IPX_CU(cudaMalloc(&hk_b, nha * 8));
+    IPX_CU(cudaMalloc(&hc_a, nha * 4));
+    IPX_CU(cudaMalloc(&out.hist_cnt, nha * 4));
+    if (keep_export) IPX_CU(cudaMalloc(&out.hist_offset, nha * 4));
+    out.n_hist = nh;
+    IPX_CU(cudaMemsetAsync(&w.d_count[1], 0, sizeof(unsigned long long), st));
+    IPX_CU(cudaMemsetAsync(out.hist_off, 0, (na + 1) * 8, st));
+    if (nh) {
+        k_compact_hist<<<148 * 8, 256, 0, st>>>(t, w.slot_rank, w.d_count, hk_a, hc_a, 0);
+        int end_bit = 16;
+        while (end_bit < 64 && (n >> (end_bit - 16)) != 0) end_bit++;
+        size_t tb = 0;
+        IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, hk_a, hk_b, hc_a, out.hist_cnt, (int)nh, 0, end_bit, st));
+        IPX_CU(ensure_tmp(w, tb));
+        IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, hk_a, hk_b, hc_a, out.hist_cnt, (int)nh, 0, end_bit, st));
+    }
+    k_hist_offsets<<<blocks_for(nha, 256), 256, 0, st>>>(hk_b, nh, n, out.hist_off, out.hist_offset);
+    IPX_CU(cudaStreamSynchronize(st));
+    cudaFree(hk_a); cudaFree(hk_b); cudaFree(hc_a);
+    cudaFree(sort_key); cudaFree(sort_key2); cudaFree(slot_a); cudaFree(slot_b);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ multi-GPU exchange */
+__global__ void k_export_rows(Tables t, DeviceTable dt, JunctionRow *jr, HistRow *hr) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < dt.n) {
+        const JStat s = t.stat[dt.slot[i]];
+        JunctionRow r;
+        r.first[0] = s.first[0]; r.first[1] = s.first[1]; r.first[2] = s.first[2];
+        r.cnt[0] = s.cnt[0]; r.cnt[1] = s.cnt[1]; r.cnt[2] = s.cnt[2];
+        r.tid = dt.chrom[i]; r.i0 = dt.i0[i]; r.i1 = dt.i1[i]; r.a0 = s.a0; r.a1 = s.a1; r.pad = 0;
+        jr[i] = r;
+    }
+    if (i < dt.n_hist) {
+        /* owning junction of run i: last r with hist_off[r] <= i */
+        uint64_t lo = 0, hi = dt.n;
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (dt.hist_off[mid] <= i) lo = mid; else hi = mid;
+        }
+        HistRow h;
+        h.tid = dt.chrom[lo]; h.i0 = dt.i0[lo]; h.i1 = dt.i1[lo];
+        h.cnt = dt.hist_cnt[i]; h.offset = dt.hist_offset[i]; h.pad = 0;
+        hr[i] = h;
+    }
+}
+
+void launch_export_rows(const Tables &t, const DeviceTable &dt, JunctionRow *jr, HistRow *hr, cudaStream_t st) {
+    const uint64_t n = dt.n > dt.n_hist ? dt.n : dt.n_hist;
+    if (n == 0) return;
+    k_export_rows<<<blocks_for(n, 256), 256, 0, st>>>(t, dt, jr, hr);
+}
+
+__global__ void k_import_junction_rows(Tables t, const JunctionRow *jr, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const JunctionRow r = jr[i];
+    const uint64_t key = make_key(t.kl, r.tid, r.i0, r.i1);
+    const uint64_t slot = junction_find_or_insert(t, key);
+    if (slot > t.cap_mask) return;
+    JStat *s = &t.stat[slot];
+    for (int c = 0; c < 3; ++c) {
+        if (r.first[c] != EMPTY64) atomicMin(&s->first[c], r.first[c]);
+        if (r.cnt[c]) atomicAdd(&s->cnt[c], r.cnt[c]);
+    }
+    atomicMin(&s->a0, r.a0);
+    atomicMax(&s->a1, r.a1);
+}
+
+__global__ void k_import_hist_rows(Tables t, const HistRow *hr, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const HistRow r = hr[i];
+    const uint64_t key = make_key(t.kl, r.tid, r.i0, r.i1);
+    const uint64_t slot = junction_find_or_insert(t, key);
+    if (slot > t.cap_mask) return;
+    hist_add(t, slot, r.offset & 0xFFFFu, r.cnt);
+}
+
+void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh,
+                        cudaStream_t st) {
+    if (nj) k_import_junction_rows<<<blocks_for(nj, 256), 256, 0, st>>>(t, jr, nj);
+    if (nh) k_import_hist_rows<<<blocks_for(nh, 256), 256, 0, st>>>(t, hr, nh);
+}
+
+}  // namespace ipx

@@ -1,0 +1,194 @@
+/* ipx_walk.cuh -- per-alignment CIGAR automaton and read classification, shared by every kernel.
+ *
+ * The functions are __host__ __device__ so that tests/native can exercise exactly the code the
+ * kernels run against the oracle without a GPU; the product only ever calls them from device code.
+ *
+ * Reference semantics restated here (file:line into the reference's src/):
+ *   ReadJunctionExtractor        junctions_extractor.cc:124-319   walk_cigar()
+ *   get_junction_strand*         junctions_extractor.cc:322-371   read_strand()
+ *   get_read_category            junctions_extractor.cc:59-95     read_category()
+ *   junction_qc                  junctions_extractor.cc:384-401   junction_qc()
+ */
+#ifndef IPX_WALK_CUH
+#define IPX_WALK_CUH
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define IPX_HD __host__ __device__ __forceinline__
+#else
+#define IPX_HD inline
+#endif
+
+namespace ipx {
+
+/* automaton states (junctions_extractor.cc:114-119) */
+enum : int { ST_LIMBO = 0, ST_LEFT = 1, ST_INTRON = 2, ST_RIGHT = 3 };
+
+/* BAM CIGAR op codes, index into "MIDNSHP=XB" */
+enum : uint32_t { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_EQ = 7, OP_X = 8 };
+
+struct ExtractParams {
+    uint32_t min_anchor_length;
+    uint32_t max_anchor_indel_size;
+    uint32_t min_intron_length;
+    uint32_t max_intron_length;
+    uint32_t excludes;
+    int32_t strandness; /* 0 UN, 1 RF, 2 FR */
+};
+
+/* One junction candidate as the automaton hands it to record_junction (junctions_extractor.cc:145-151);
+ * only the sums of mismatch + indel counts are consumed downstream. */
+struct Candidate {
+    int64_t anchor_start, intron_start, intron_end, anchor_end;
+    uint32_t left_bad, right_bad; /* mismatch + indel counts, uint32 wrap-around as in the reference */
+    uint32_t ordinal;             /* position of this candidate among the read's candidates */
+};
+
+/* get_junction_strand (junctions_extractor.cc:362-371): flag rule when stranded, else XS:A, else '.' */
+IPX_HD char read_strand(int32_t strandness, uint32_t flag, uint32_t xs) {
+    if (strandness != 0) {
+        /* get_junction_strand_flag (junctions_extractor.cc:333-359) */
+        uint32_t reversed = (flag >> 4) & 1u, mate_reversed = (flag >> 5) & 1u;
+        uint32_t first_strand = ((flag >> 6) & 1u) ^ reversed;
+        uint32_t second_strand = ((flag >> 7) & 1u) ^ mate_reversed;
+        uint32_t flip = (strandness == 1) ? 1u : 0u; /* "^= !(strandness_ - 1)": RF (1) flips, FR (2) keeps */
+        first_strand ^= flip;
+        second_strand ^= flip;
+        if (first_strand != second_strand) return '.';
+        return first_strand ? '+' : '-';
+    }
+    if (xs == 0u || xs == 0xFFu) return '.'; /* no tag, or a tag that is not a non-NUL 'A' value */
+    return (char)xs;
+}
+
+/* get_read_category (junctions_extractor.cc:71-95); nh_class: 0 none/<=0, 1 ==1, 2 >1 */
+IPX_HD uint32_t read_category(uint32_t flag, uint32_t nh_class) {
+    uint32_t by_tag = (nh_class == 1u) ? 0u : ((nh_class == 2u) ? 1u : 2u);
+    if (flag & (0x100u | 0x800u)) return 1u;
+    if (flag & 0x1u) return ((flag & 0x2u) && !(flag & 0x4u)) ? by_tag : 2u;
+    return by_tag;
+}
+
+/* process_alignment's skip test (junctions_extractor.cc:536) */
+IPX_HD bool record_is_live(uint32_t n_cigar, int32_t tid, uint32_t flag) {
+    return !(n_cigar <= 1u || tid < 0 || (flag & (0x200u | 0x400u)));
+}
+
+/* the per-read half of junction_qc (junctions_extractor.cc:388-391) */
+IPX_HD bool read_may_emit(const ExtractParams &p, uint32_t flag, uint32_t nh_class) {
+    if (flag & 0x100u) return false;
+    if ((p.excludes & 1u) && nh_class == 2u) return false;
+    return true;
+}
+
+/* the per-candidate half of junction_qc (junctions_extractor.cc:392-397), signed 64-bit like hts_pos_t */
+IPX_HD bool junction_qc(const ExtractParams &p, const Candidate &c) {
+    int64_t ilen = c.intron_end - c.intron_start;
+    if (ilen < (int64_t)p.min_intron_length || ilen > (int64_t)p.max_intron_length) return false;
+    int64_t left = (c.intron_start - c.anchor_start) - (int64_t)c.left_bad;
+    int64_t right = (c.anchor_end - c.intron_end) - (int64_t)c.right_bad;
+    return !(left < (int64_t)p.min_anchor_length || right < (int64_t)p.min_anchor_length);
+}
+
+/* Automaton registers; kept in a struct so a kernel can carry it across CIGAR tiles. */
+struct WalkState {
+    int64_t tpos, a0, i0, i1, a1;
+    uint32_t lmm, rmm, lind, rind, cur;
+    uint32_t n_emitted;
+    int state;
+    IPX_HD void init(int64_t pos) {
+        tpos = pos;
+        a0 = i0 = i1 = a1 = -1;
+        lmm = rmm = lind = rind = cur = 0u;
+        n_emitted = 0u;
+        state = ST_LIMBO;
+    }
+};
+
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class Emit>
+IPX_HD void emit_candidate(WalkState &w, Emit &emit) {
+    Candidate c;
+    c.anchor_start = w.a0;
+    c.intron_start = w.i0;
+    c.intron_end = w.i1;
+    c.anchor_end = w.a1;
+    c.left_bad = w.lmm + w.lind;
+    c.right_bad = w.rmm + w.rind;
+    c.ordinal = w.n_emitted++;
+    emit(c);
+}
+
+/* Feed one CIGAR word.  Returns 0, or 0x100 | op for an operation the reference rejects
+ * ("Unknown cigar operation", junctions_extractor.cc:312-313). */
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class Emit>
+IPX_HD uint32_t walk_op(WalkState &w, uint32_t word, uint32_t max_indel, Emit &emit) {
+    const uint32_t op = word & 15u;
+    const uint32_t len = word >> 4;
+    if (op == OP_M || op == OP_EQ || op == OP_X) {
+        /* enter_aligned (junctions_extractor.cc:232-254) */
+        if (w.state == ST_LIMBO) {
+            w.a0 = w.tpos;
+            w.lmm = w.rmm = 0u; /* indel counters are deliberately not reset */
+            w.state = ST_LEFT;
+        } else if (w.state == ST_INTRON) {
+            w.i1 = w.tpos;
+            w.state = ST_RIGHT;
+        }
+        w.a1 = w.tpos + len;
+        if (op == OP_X) {
+            if (w.state == ST_LEFT) w.lmm += len; else w.rmm += len;
+        }
+        w.cur = 0u;
+        w.tpos += len;
+    } else if (op == OP_N) {
+        /* enter_intron (junctions_extractor.cc:208-229) */
+        if (w.state == ST_RIGHT) {
+            emit_candidate(w, emit);
+            w.a0 = w.i1;
+            w.lmm = w.rmm; w.rmm = 0u;
+            w.lind = w.rind; w.rind = 0u;
+            w.state = ST_LEFT;
+        }
+        if (w.state == ST_LEFT) {
+            w.i0 = w.tpos;
+            w.i1 = w.tpos + len;
+            w.state = ST_INTRON;
+        }
+        w.cur = 0u;
+        w.tpos += len;
+    } else if (op == OP_D || op == OP_I) {
+        /* enter_query_delete / enter_query_insert (junctions_extractor.cc:257-275) */
+        if (w.state == ST_LEFT) w.lind += len; else if (w.state == ST_RIGHT) w.rind += len;
+        w.cur += len;
+        if (w.cur > max_indel) {
+            if (w.state == ST_RIGHT) emit_candidate(w, emit);
+            w.state = ST_LIMBO;
+        }
+        if (op == OP_D) w.tpos += len;
+    } else if (op == OP_S || op == OP_H) {
+        /* enter_limbo (junctions_extractor.cc:153-158); cur is not reset */
+        if (w.state == ST_RIGHT) emit_candidate(w, emit);
+        w.state = ST_LIMBO;
+    } else {
+        return 0x100u | op;
+    }
+    return 0u;
+}
+
+/* finish (junctions_extractor.cc:278-282) */
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class Emit>
+IPX_HD void walk_finish(WalkState &w, Emit &emit) {
+    if (w.state == ST_RIGHT) emit_candidate(w, emit);
+}
+
+}  // namespace ipx
+#endif

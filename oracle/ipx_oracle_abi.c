@@ -1,0 +1,67 @@
+/* ipx_oracle_abi.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Presents the CPU oracle (ipx_oracle.c) under the symbol names of the C ABI in include/ipx.h, so that the
+ * product's command line tools can be LINKED, by oracle/Makefile and for tests only, against the oracle
+ * instead of libipx.so.  The resulting binaries (the .oracle files under oracle/_ref) let the host-side logic of the CLIs
+ * (option handling, run modes, record selection, text output) be checked against the reference's goldens on
+ * a machine without a GPU, and give parity tests a second, independent producer of whole output files.
+ * Nothing in intronprospector_b200/ references this file; the product libraries never load it.
+ */
+#define _GNU_SOURCE
+#include <stdlib.h>
+#include <string.h>
+#include "ipx_oracle.h"
+
+struct ipx_handle {
+    ipxo_state *st;
+    size_t log_reported; /* how much of the oracle's stderr text has been handed out as merge conflict log */
+};
+
+const char *ipx_version(void) { return "ipx CPU oracle (test only)"; }
+int ipx_abi_version(void) { return IPX_ABI_VERSION; }
+int ipx_device_count(void) { return 0; }
+
+int ipx_create(const ipx_params *params, ipx_handle **out) {
+    ipx_handle *h = (ipx_handle *)calloc(1, sizeof(*h));
+    h->st = ipxo_create(params);
+    *out = h;
+    return IPX_OK;
+}
+
+void ipx_destroy(ipx_handle *h) {
+    if (!h) return;
+    ipxo_destroy(h->st);
+    free(h);
+}
+
+const char *ipx_last_error(const ipx_handle *h) { return ipxo_last_error(h->st); }
+void *ipx_stream(ipx_handle *h) { (void)h; return NULL; }
+int ipx_set_targets(ipx_handle *h, int32_t n, const char *const *names) { return ipxo_set_targets(h->st, n, names); }
+int ipx_set_genome(ipx_handle *h, int32_t n, const char *const *names, const uint64_t *lengths, const char *const *seqs) {
+    return ipxo_set_genome(h->st, n, names, lengths, seqs);
+}
+int ipx_push_batch(ipx_handle *h, const ipx_batch *b) { return ipxo_push_batch(h->st, b); }
+int ipx_push_batch_device(ipx_handle *h, const ipx_batch *b) { (void)h; (void)b; return IPX_ERR_CUDA; }
+int ipx_finalize_device(ipx_handle *h) { (void)h; return IPX_OK; }
+int ipx_flush(ipx_handle *h, ipx_table **out) { return ipxo_flush(h->st, out); }
+void ipx_table_free(ipx_table *t) { ipxo_table_free(t); }
+
+int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ipx_table **out, ipx_text *conflict_log) {
+    int rc = ipxo_merge_rows_fold(h->st, rows, out);
+    if (conflict_log) {
+        const char *all = ipxo_stderr_text(h->st);
+        conflict_log->data = strdup(all + h->log_reported);
+        conflict_log->len = strlen(conflict_log->data);
+        h->log_reported = strlen(all);
+    }
+    return rc;
+}
+
+int ipx_format(const ipx_table *t, const char *const *names, int format, float min_confidence, uint64_t begin, uint64_t end,
+               ipx_text *out) {
+    return ipxo_format(t, names, format, min_confidence, begin, end, out);
+}
+int ipx_format_tsv_header(ipx_text *out) { return ipxo_format_tsv_header(out); }
+void ipx_text_free(ipx_text *t) { ipxo_text_free(t); }
+int ipx_get_timings(ipx_handle *h, ipx_timings *out) { (void)h; memset(out, 0, sizeof(*out)); return IPX_OK; }
+int ipx_reset_timings(ipx_handle *h) { (void)h; return IPX_OK; }

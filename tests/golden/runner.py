@@ -25,7 +25,7 @@ def ref_binaries():
 def unpack_fixtures(dest):
     """Extract the committed fixture archive (input/ + expected/) under dest and return dest."""
     with tarfile.open(FIXTURE_TAR, "r:gz") as tf:
-        tf.extractall(dest)
+        tf.extractall(dest, filter="data")
     os.makedirs(os.path.join(dest, "output"), exist_ok=True)
     return dest
 

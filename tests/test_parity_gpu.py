@@ -1,0 +1,145 @@
+"""Table-level parity through the C ABI: the CUDA engine against the CPU oracle on the same seeded batches,
+bit-exact on every column (integer work) and on the formatted text (which carries the float32 confidence)."""
+import numpy as np
+import pytest
+
+import helpers  # noqa: F401
+from intronprospector_b200 import _native, selftest
+from intronprospector_b200.synth import LONG, SHORT_STRANDED, SHORT_UNSTRANDED, Synth
+
+pytestmark = pytest.mark.gpu
+
+
+def both(names, cols, n_batches=1, genome=None, **params):
+    gpu = _native.Engine(device=0, **params)
+    got = selftest.run_engine(gpu, names, cols, genome=genome, n_batches=n_batches)
+    gpu.close()
+    ora = selftest.oracle_engine(**{k: v for k, v in params.items() if k not in ("table_capacity", "hist_capacity")})
+    want = selftest.run_engine(ora, names, cols, genome=genome)
+    ora.close()
+    return got, want
+
+
+def genome_of(syn, tmp_path):
+    import ctypes as C
+    fa = str(tmp_path / "g.fa")
+    syn.write_genome(fa)
+    io = _native.load_io_library()
+    g = C.c_void_p()
+    assert io.ipxio_genome_load(fa.encode(), C.byref(g)) == 0
+    n = io.ipxio_genome_n_seqs(g)
+    names = [io.ipxio_genome_names(g)[i].decode() for i in range(n)]
+    lens = [int(io.ipxio_genome_lengths(g)[i]) for i in range(n)]
+    seqs = [C.string_at(io.ipxio_genome_seqs(g)[i], lens[i]) for i in range(n)]
+    io.ipxio_genome_free(g)
+    return names, seqs
+
+
+@pytest.mark.parametrize("n_batches", [1, 7])
+def test_short_unstranded(built, n_batches):
+    syn = Synth(2_000_000, kind=SHORT_UNSTRANDED, genome_len=300_000_000, n_genes=4000)
+    got, want = both(syn.names, syn.columns(), n_batches=n_batches)
+    assert want.n > 5000
+    assert selftest.compare_tables(got, want) == []
+
+
+def test_small_tables_force_collisions(built):
+    syn = Synth(200_000, kind=SHORT_UNSTRANDED, genome_len=100_000_000, n_genes=500)
+    got, want = both(syn.names, syn.columns(), n_batches=2, table_capacity=8192, hist_capacity=1 << 18)
+    assert selftest.compare_tables(got, want) == []
+
+
+def test_table_overflow_is_reported(built):
+    syn = Synth(200_000, kind=SHORT_UNSTRANDED, genome_len=100_000_000, n_genes=500)
+    gpu = _native.Engine(device=0, table_capacity=1024, hist_capacity=1024)
+    with pytest.raises(_native.IpxError):
+        selftest.run_engine(gpu, syn.names, syn.columns())
+    gpu.close()
+
+
+@pytest.mark.parametrize("flt", [_native.FILTER_CANON, _native.FILTER_ALL])
+def test_stranded_with_genome(built, tmp_path, flt):
+    syn = Synth(600_000, kind=SHORT_STRANDED, genome_len=100_000_000, n_genes=1000, n_contigs=5)
+    genome = genome_of(syn, tmp_path)
+    got, want = both(syn.names, syn.columns(), n_batches=4, genome=genome, strandness=_native.STRAND_RF,
+                     min_anchor_length=12, junction_filter=flt)
+    assert want.n > 1000
+    assert selftest.compare_tables(got, want) == []
+
+
+def test_unstranded_with_genome_mixed_strands(built, tmp_path):
+    """XS-derived strands plus '.' reads against the canon filter: exercises strand correction and the rule that
+    events before the first filter-passing event of a junction are dropped."""
+    syn = Synth(400_000, kind=SHORT_UNSTRANDED, genome_len=100_000_000, n_genes=1000, n_contigs=5)
+    cols = syn.columns()
+    rng = np.random.default_rng(5)
+    xs = cols["xs"]
+    spliced = xs != 0
+    r = rng.random(xs.shape[0])
+    xs[spliced & (r < 0.25)] = 0             # no tag -> '.'
+    xs[spliced & (r >= 0.25) & (r < 0.40)] = ord("-")
+    xs[spliced & (r >= 0.40) & (r < 0.55)] = ord("+")
+    xs[spliced & (r >= 0.55) & (r < 0.58)] = 0xFF   # XS present but not a character value
+    xs[spliced & (r >= 0.58) & (r < 0.60)] = ord("?")
+    genome = genome_of(syn, tmp_path)
+    for flt in (_native.FILTER_CANON, _native.FILTER_ALL):
+        got, want = both(syn.names, cols, n_batches=3, genome=genome, junction_filter=flt)
+        assert selftest.compare_tables(got, want) == []
+
+
+def test_missing_genome_targets_are_skipped(built, tmp_path):
+    syn = Synth(200_000, kind=SHORT_UNSTRANDED, genome_len=100_000_000, n_genes=1000, n_contigs=5)
+    names, seqs = genome_of(syn, tmp_path)
+    genome = (names[:2] + names[3:], seqs[:2] + seqs[3:])
+    got, want = both(syn.names, syn.columns(), genome=genome, junction_filter=_native.FILTER_CANON, skip_missing_targets=True)
+    assert selftest.compare_tables(got, want) == []
+    assert list(got.missing_targets) == list(want.missing_targets) == [2]
+
+
+@pytest.mark.parametrize("indel", [0, 36])
+def test_long_reads(built, indel):
+    syn = Synth(30_000, kind=LONG, genome_len=300_000_000, n_genes=2000)
+    got, want = both(syn.names, syn.columns(), n_batches=3, max_anchor_indel_size=indel)
+    assert want.n > 1000
+    assert selftest.compare_tables(got, want) == []
+
+
+def test_empty_and_ragged_batches(built):
+    names = ["c1", "c2"]
+    empty = {k: np.zeros(0, dt) for k, dt in (("tid", np.int32), ("pos", np.int32), ("flag", np.uint16), ("nh_class", np.uint8),
+                                              ("xs", np.uint8), ("cigar", np.uint32))}
+    empty["cigar_off"] = np.zeros(1, np.uint32)
+    got, want = both(names, empty)
+    assert got.n == want.n == 0
+    # records with no CIGAR, unmapped, duplicates, one-op reads and a real junction mixed together
+    def w(length, op):
+        return (length << 4) | "MIDNSHP=XB".index(op)
+    recs = [
+        (0, 100, 0, [w(50, "M"), w(200, "N"), w(50, "M")]),
+        (-1, 0, 4, []),
+        (0, 120, 1024, [w(30, "M"), w(180, "N"), w(70, "M")]),
+        (1, 5, 0, [w(100, "M")]),
+        (1, 7, 16, [w(5, "S"), w(20, "M"), w(100, "N"), w(10, "M"), w(300, "N"), w(40, "M"), w(3, "H")]),
+        (1, 7, 0, [w(20, "M"), w(100, "N"), w(4, "I"), w(300, "N"), w(40, "M")]),
+    ]
+    cols = {"tid": np.array([r[0] for r in recs], np.int32), "pos": np.array([r[1] for r in recs], np.int32),
+            "flag": np.array([r[2] for r in recs], np.uint16), "nh_class": np.array([1, 0, 1, 1, 2, 0], np.uint8),
+            "xs": np.array([ord("+"), 0, 0, 0, ord("-"), 0], np.uint8),
+            "cigar_off": np.cumsum([0] + [len(r[3]) for r in recs]).astype(np.uint32),
+            "cigar": np.array([x for r in recs for x in r[3]], np.uint32)}
+    for indel in (0, 36):
+        got, want = both(names, cols, max_anchor_indel_size=indel)
+        assert want.n >= 2
+        assert selftest.compare_tables(got, want) == []
+
+
+def test_unknown_cigar_op_is_reported(built):
+    def w(length, op):
+        return (length << 4) | op
+    cols = {"tid": np.array([0, 0], np.int32), "pos": np.array([10, 20], np.int32), "flag": np.zeros(2, np.uint16),
+            "nh_class": np.ones(2, np.uint8), "xs": np.zeros(2, np.uint8), "cigar_off": np.array([0, 3, 6], np.uint32),
+            "cigar": np.array([w(50, 0), w(100, 3), w(50, 0), w(50, 0), w(3, 6), w(50, 0)], np.uint32)}
+    got, want = both(["c1"], cols)
+    assert got.status == want.status == -3
+    assert got.error_text == want.error_text == "Unknown cigar operation 'P'"
+    assert got.first_error_seq == want.first_error_seq == 1
