@@ -196,6 +196,8 @@ int ipx_finalize_device(ipx_handle *h);
  * ipx_finalize_device() first if needed.  sjN numbering continues across flushes (ijunc_). */
 int ipx_flush(ipx_handle *h, ipx_table **out);
 void ipx_table_free(ipx_table *t);
+/* clear() alone (junctions_extractor.hh:222-224): drop everything accumulated so far, keep sjN numbering */
+int ipx_clear(ipx_handle *h);
 
 /* Merge fold: process_junction + Junction::merge over all rows (intronProspectorMerge.cc:179-199,
  * junctions.cc:76-105), then sort_by_anchors + renumber_junctions (:201-205, :221-223).

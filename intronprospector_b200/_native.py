@@ -125,7 +125,7 @@ class MergeRows(C.Structure):
 ABI_SYMBOLS = [
     "ipx_version", "ipx_abi_version", "ipx_device_count", "ipx_create", "ipx_destroy", "ipx_last_error",
     "ipx_set_targets", "ipx_set_genome", "ipx_push_batch", "ipx_push_batch_device", "ipx_finalize_device",
-    "ipx_flush", "ipx_table_free", "ipx_merge_rows_fold", "ipx_partial_row_bytes", "ipx_partial_sizes",
+    "ipx_flush", "ipx_table_free", "ipx_clear", "ipx_merge_rows_fold", "ipx_partial_row_bytes", "ipx_partial_sizes",
     "ipx_partial_export", "ipx_partial_import", "ipx_format", "ipx_format_tsv_header", "ipx_text_free",
     "ipx_get_timings", "ipx_reset_timings", "ipx_stream",
 ]
@@ -155,6 +155,7 @@ def _bind(lib):
     lib.ipx_flush.argtypes = [C.c_void_p, C.POINTER(C.POINTER(TableStruct))]
     lib.ipx_table_free.argtypes = [C.POINTER(TableStruct)]
     lib.ipx_table_free.restype = None
+    lib.ipx_clear.argtypes = [C.c_void_p]
     lib.ipx_merge_rows_fold.argtypes = [C.c_void_p, C.POINTER(MergeRows), C.POINTER(C.POINTER(TableStruct)), C.POINTER(Text)]
     lib.ipx_format.argtypes = [C.POINTER(TableStruct), C.POINTER(C.c_char_p), C.c_int, C.c_float, C.c_uint64, C.c_uint64, C.POINTER(Text)]
     lib.ipx_format_tsv_header.argtypes = [C.POINTER(Text)]
@@ -369,6 +370,9 @@ class Engine:
         tp = C.POINTER(TableStruct)()
         self._check(self.lib.ipx_flush(self.h, C.byref(tp)))
         return Table(self.lib, tp, self.names, self.lib.ipx_table_free)
+
+    def clear(self):
+        self._check(self.lib.ipx_clear(self.h))
 
     def merge_rows(self, rows_ptr):
         tp = C.POINTER(TableStruct)()

@@ -464,9 +464,11 @@ extern "C" int ipx_finalize_device(ipx_handle *h) {
     int rc = alloc_tables(h);
     if (rc) return rc;
     {
-        Span s(h, &h->tm_finalize, 12);
+        Span s(h, &h->tm_finalize, 0);
+        int own = 0;
         cudaError_t e = finalize_tables(h->tab, genome_view(h), h->d_name_rank, (int32_t)h->targets.size(), h->fw, h->dt,
-                                        h->keep_export, h->stream);
+                                        h->keep_export, h->stream, &own);
+        h->tm_finalize.launches += (uint64_t)own;
         if (e != cudaSuccess)
             return fail(h, IPX_ERR_CUDA, "CUDA error %s in finalize: %s", cudaGetErrorName(e), cudaGetErrorString(e));
     }
@@ -618,6 +620,25 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     cudaMemsetAsync(h->tab.n_live, 0, 8, st);
     h->dirty = false;
     *out = &ht->t;
+    return IPX_OK;
+}
+
+/* JunctionsExtractor::clear (junctions_extractor.hh:222-224) without reading the table back */
+extern "C" int ipx_clear(ipx_handle *h) {
+    if (!h) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (h->finalized) {
+        free_device_table(h->dt);
+        h->finalized = false;
+    }
+    if (h->tables_ready) {
+        Span s(h, &h->tm_finalize, 1);
+        launch_init_tables(h->tab, h->stream);
+        cudaMemsetAsync(h->tab.n_events, 0, 8, h->stream);
+        cudaMemsetAsync(h->tab.n_live, 0, 8, h->stream);
+        CU(h, cudaGetLastError());
+    }
+    h->dirty = false;
     return IPX_OK;
 }
 

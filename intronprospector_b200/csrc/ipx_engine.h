@@ -84,7 +84,8 @@ struct FinalizeWork {
 /* key-order sort, sjN ranking, histogram ordering, gather; synchronises on the counts it needs.
  * `name_rank[tid]` orders targets like std::string::operator< on their names. Returns cudaError_t. */
 cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, int32_t n_targets,
-                            FinalizeWork &w, DeviceTable &out, bool keep_export_columns, cudaStream_t st);
+                            FinalizeWork &w, DeviceTable &out, bool keep_export_columns, cudaStream_t st,
+                            int *own_launches);
 void free_device_table(DeviceTable &t);
 
 /* export rows for destination ranks: rows [0, n) of the finished table are already in key order */

@@ -421,8 +421,9 @@ static inline unsigned blocks_for(uint64_t n, unsigned threads) {
 }
 
 cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, int32_t n_targets,
-                            FinalizeWork &w, DeviceTable &out, bool keep_export, cudaStream_t st) {
+                            FinalizeWork &w, DeviceTable &out, bool keep_export, cudaStream_t st, int *own_launches) {
     (void)n_targets;
+    int launches = 0;
     const uint64_t cap = t.cap_mask + 1;
     out = DeviceTable();
     if (!w.d_count) IPX_CU(cudaMalloc(&w.d_count, 4 * sizeof(unsigned long long)));
@@ -436,6 +437,7 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
 
     /* creation thresholds for anything still unresolved */
     k_resolve_T<<<148 * 8, 256, 0, st>>>(t, g);
+    launches++;
 
     /* number of keys bounds the number of junctions */
     unsigned long long n_keys = 0;
@@ -450,6 +452,7 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
     IPX_CU(cudaMalloc(&slot_a, nk * 4));
     IPX_CU(cudaMalloc(&slot_b, nk * 4));
     k_compact_junctions<<<148 * 8, 256, 0, st>>>(t, d_name_rank, w.d_count, sort_key, slot_a);
+    launches++;
     unsigned long long n_j = 0;
     IPX_CU(cudaMemcpyAsync(&n_j, &w.d_count[0], sizeof(n_j), cudaMemcpyDeviceToHost, st));
     IPX_CU(cudaStreamSynchronize(st));
@@ -461,7 +464,10 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
     IPX_CU(ensure_tmp(w, tmp_bytes));
     if (n) IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp_bytes, sort_key, sort_key2, slot_a, slot_b, (int)n, 0, 64, st));
     const uint32_t *sorted_slot = slot_b;
-    if (n) k_fill_slot_rank<<<blocks_for(n, 256), 256, 0, st>>>(sorted_slot, n, w.slot_rank);
+    if (n) {
+        k_fill_slot_rank<<<blocks_for(n, 256), 256, 0, st>>>(sorted_slot, n, w.slot_rank);
+        launches++;
+    }
 
     IPX_CU(cudaMalloc(&out.chrom, na * 4));
     IPX_CU(cudaMalloc(&out.i0, na * 4));
@@ -489,12 +495,14 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
         IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, sort_key, sort_key2, idx_a, idx_b, (int)n, 0, 64, st));
         k_scatter_ijunc<<<blocks_for(n, 256), 256, 0, st>>>(idx_b, n, out.ijunc);
         k_gather_rows<<<blocks_for(n, 256), 256, 0, st>>>(t, g, sorted_slot, n, out);
+        launches += 3; /* gather_T, scatter_ijunc, gather_rows */
         IPX_CU(cudaStreamSynchronize(st));
         cudaFree(idx_b);
     }
 
     /* offset histogram: count, gather, order by (junction rank, offset) */
     k_compact_hist<<<148 * 8, 256, 0, st>>>(t, w.slot_rank, w.d_count, nullptr, nullptr, 1);
+    launches++;
     unsigned long long n_h = 0;
     IPX_CU(cudaMemcpyAsync(&n_h, &w.d_count[1], sizeof(n_h), cudaMemcpyDeviceToHost, st));
     IPX_CU(cudaStreamSynchronize(st));
@@ -511,6 +519,7 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
     IPX_CU(cudaMemsetAsync(out.hist_off, 0, (na + 1) * 8, st));
     if (nh) {
         k_compact_hist<<<148 * 8, 256, 0, st>>>(t, w.slot_rank, w.d_count, hk_a, hc_a, 0);
+        launches++;
         int end_bit = 16;
         while (end_bit < 64 && (n >> (end_bit - 16)) != 0) end_bit++;
         size_t tb = 0;
@@ -519,6 +528,8 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
         IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, hk_a, hk_b, hc_a, out.hist_cnt, (int)nh, 0, end_bit, st));
     }
     k_hist_offsets<<<blocks_for(nha, 256), 256, 0, st>>>(hk_b, nh, n, out.hist_off, out.hist_offset);
+    launches++;
+    if (own_launches) *own_launches = launches;
     IPX_CU(cudaStreamSynchronize(st));
     cudaFree(hk_a); cudaFree(hk_b); cudaFree(hc_a);
     cudaFree(sort_key); cudaFree(sort_key2); cudaFree(slot_a); cudaFree(slot_b);

@@ -45,6 +45,7 @@ int ipx_push_batch_device(ipx_handle *h, const ipx_batch *b) { (void)h; (void)b;
 int ipx_finalize_device(ipx_handle *h) { (void)h; return IPX_OK; }
 int ipx_flush(ipx_handle *h, ipx_table **out) { return ipxo_flush(h->st, out); }
 void ipx_table_free(ipx_table *t) { ipxo_table_free(t); }
+int ipx_clear(ipx_handle *h) { ipx_table *t = NULL; ipxo_flush(h->st, &t); ipxo_table_free(t); return IPX_OK; }
 
 int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ipx_table **out, ipx_text *conflict_log) {
     int rc = ipxo_merge_rows_fold(h->st, rows, out);
