@@ -257,21 +257,34 @@ class Table:
         self.error_tid = int(t.error_tid)
         self.error_text = t.error_text.decode(errors="replace")
         self.missing_targets = _arr(t.missing_targets, int(t.n_missing_targets), np.int32)
-        # text through the library's own formatter, while the native table is still alive
-        cnames = (C.c_char_p * max(1, len(names)))(*[s.encode() for s in names])
+        # text is produced on demand by the library's own formatter, so the native table stays alive until close()
+        self._lib, self._tp, self._free = lib, tp, free
+        self._cnames = (C.c_char_p * max(1, len(names)))(*[s.encode() for s in names])
         self._text = {}
-        for fmt in (FMT_JUNCTION_BED, FMT_INTRON_BED9, FMT_INTRON_BED6, FMT_INTRON_TSV):
-            for minc in (0.0, 1.0):
-                txt = Text()
-                rc = lib.ipx_format(tp, cnames, fmt, minc, 0, n, C.byref(txt))
-                if rc != IPX_OK:
-                    raise IpxError("ipx_format failed: %d" % rc)
-                self._text[(fmt, minc)] = C.string_at(txt.data, txt.len) if txt.len else b""
-                lib.ipx_text_free(C.byref(txt))
-        free(tp)
 
     def text(self, fmt, min_confidence=0.0):
-        return self._text[(fmt, float(min_confidence))]
+        key = (fmt, float(min_confidence))
+        if key not in self._text:
+            if self._tp is None:
+                raise IpxError("table already closed")
+            txt = Text()
+            rc = self._lib.ipx_format(self._tp, self._cnames, fmt, key[1], 0, self.n, C.byref(txt))
+            if rc != IPX_OK:
+                raise IpxError("ipx_format failed: %d" % rc)
+            self._text[key] = C.string_at(txt.data, txt.len) if txt.len else b""
+            self._lib.ipx_text_free(C.byref(txt))
+        return self._text[key]
+
+    def close(self):
+        if self._tp is not None:
+            self._free(self._tp)
+            self._tp = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def columns(self):
         return dict(chrom=self.chrom, intron_start=self.intron_start, intron_end=self.intron_end,

@@ -53,18 +53,20 @@ struct HostTable {
 struct DeviceBuf {
     void *p = nullptr;
     size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
+    cudaStream_t st = nullptr;
+    cudaError_t reserve(size_t bytes, cudaStream_t stream) {
+        st = stream;
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, st);
         p = nullptr;
         cap = 0;
         size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
+        cudaError_t e = cudaMallocAsync(&p, want, st);
         if (e == cudaSuccess) cap = want;
         return e;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, st);
         p = nullptr;
         cap = 0;
     }
@@ -125,6 +127,7 @@ struct ipx_handle {
     /* timings */
     StageTimer tm_extract, tm_motif, tm_finalize, tm_merge;
     ipx_timings totals{};
+    unsigned long long events_base = 0, live_base = 0;
 };
 
 namespace {
@@ -354,6 +357,14 @@ extern "C" int ipx_create(const ipx_params *params, ipx_handle **out) {
         }
         h->own_stream = true;
     }
+    {
+        /* keep freed stream-ordered allocations in the pool instead of returning them to the driver */
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     h->xp.min_anchor_length = params->min_anchor_length;
     h->xp.max_anchor_indel_size = params->max_anchor_indel_size;
     h->xp.min_intron_length = params->min_intron_length;
@@ -369,7 +380,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     drain(h->tm_extract); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
-    if (h->finalized) free_device_table(h->dt);
+    if (h->finalized) free_device_table(h->dt, h->stream);
     cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.hkeys); cudaFree(h->tab.hcnt);
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq);
     free_genome(h);
@@ -435,13 +446,13 @@ extern "C" int ipx_push_batch(ipx_handle *h, const ipx_batch *b) {
     if (b->n_cigar >> 32) return fail(h, IPX_ERR_ARG, "more than 2^32 CIGAR words in one batch");
     cudaSetDevice(h->device);
     const uint64_t n = b->n_records;
-    CU(h, h->s_tid.reserve(n * 4));
-    CU(h, h->s_pos.reserve(n * 4));
-    CU(h, h->s_flag.reserve(n * 2));
-    CU(h, h->s_nh.reserve(n));
-    CU(h, h->s_xs.reserve(n));
-    CU(h, h->s_off.reserve((n + 1) * 4));
-    CU(h, h->s_cig.reserve((b->n_cigar ? b->n_cigar : 1) * 4));
+    CU(h, h->s_tid.reserve(n * 4, h->stream));
+    CU(h, h->s_pos.reserve(n * 4, h->stream));
+    CU(h, h->s_flag.reserve(n * 2, h->stream));
+    CU(h, h->s_nh.reserve(n, h->stream));
+    CU(h, h->s_xs.reserve(n, h->stream));
+    CU(h, h->s_off.reserve((n + 1) * 4, h->stream));
+    CU(h, h->s_cig.reserve((b->n_cigar ? b->n_cigar : 1) * 4, h->stream));
     /* the staging buffers may still be read by the previous batch's kernels: same stream, so ordered */
     CU(h, cudaMemcpyAsync(h->s_tid.p, b->tid, n * 4, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->s_pos.p, b->pos, n * 4, cudaMemcpyHostToDevice, h->stream));
@@ -608,16 +619,12 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     ht->bind();
     ht->t.status = IPX_OK;
     if (err_sv != EMPTY64) describe_error(h, err_sv, ht);
-    h->totals.events += ctr[0];
-    h->totals.cigar_live += ctr[1];
     h->totals.junctions += n;
     h->totals.hist_runs += d.n_hist;
     /* clear(), junctions.hh:240-245 */
-    free_device_table(h->dt);
+    free_device_table(h->dt, h->stream);
     h->finalized = false;
     launch_init_tables(h->tab, st);
-    cudaMemsetAsync(h->tab.n_events, 0, 8, st);
-    cudaMemsetAsync(h->tab.n_live, 0, 8, st);
     h->dirty = false;
     *out = &ht->t;
     return IPX_OK;
@@ -628,14 +635,12 @@ extern "C" int ipx_clear(ipx_handle *h) {
     if (!h) return IPX_ERR_ARG;
     cudaSetDevice(h->device);
     if (h->finalized) {
-        free_device_table(h->dt);
+        free_device_table(h->dt, h->stream);
         h->finalized = false;
     }
     if (h->tables_ready) {
         Span s(h, &h->tm_finalize, 1);
         launch_init_tables(h->tab, h->stream);
-        cudaMemsetAsync(h->tab.n_events, 0, 8, h->stream);
-        cudaMemsetAsync(h->tab.n_live, 0, 8, h->stream);
         CU(h, cudaGetLastError());
     }
     h->dirty = false;
@@ -695,13 +700,13 @@ extern "C" int ipx_get_timings(ipx_handle *h, ipx_timings *out) {
     t.motif_launches = h->tm_motif.launches;
     t.finalize_launches = h->tm_finalize.launches;
     t.merge_launches = h->tm_merge.launches;
-    if (h->tables_ready && h->dirty) {
-        /* counts of the open (unflushed) table */
+    if (h->tables_ready) {
+        /* the device counters are cumulative over the life of the handle */
         unsigned long long ev = 0, lw = 0;
         cudaMemcpy(&ev, h->tab.n_events, 8, cudaMemcpyDeviceToHost);
         cudaMemcpy(&lw, h->tab.n_live, 8, cudaMemcpyDeviceToHost);
-        t.events += ev;
-        t.cigar_live += lw;
+        t.events = ev - h->events_base;
+        t.cigar_live = lw - h->live_base;
     }
     *out = t;
     return IPX_OK;
@@ -714,6 +719,10 @@ extern "C" int ipx_reset_timings(ipx_handle *h) {
     drain(h->tm_extract); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
     h->tm_extract = StageTimer(); h->tm_motif = StageTimer(); h->tm_finalize = StageTimer(); h->tm_merge = StageTimer();
     h->totals = ipx_timings{};
+    if (h->tables_ready) {
+        cudaMemcpy(&h->events_base, h->tab.n_events, 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&h->live_base, h->tab.n_live, 8, cudaMemcpyDeviceToHost);
+    }
     return IPX_OK;
 }
 
@@ -779,7 +788,7 @@ extern "C" int ipx_partial_export(ipx_handle *h, void *dev_junction_rows, void *
     CU(h, cudaGetLastError());
     /* the local table has been handed over: empty it so that imports (own share included) rebuild it */
     CU(h, cudaStreamSynchronize(h->stream));
-    free_device_table(h->dt);
+    free_device_table(h->dt, h->stream);
     h->finalized = false;
     h->keep_export = false;
     launch_init_tables(h->tab, h->stream);
@@ -854,9 +863,9 @@ extern "C" int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ip
     /* upload the row columns */
     DeviceBuf b_chrom, b_i0, b_i1, b_a0, b_a1, b_strand, b_sites, b_counts, b_conf;
     const uint64_t na = n ? n : 1;
-    CU(h, b_chrom.reserve(na * 4)); CU(h, b_i0.reserve(na * 4)); CU(h, b_i1.reserve(na * 4)); CU(h, b_a0.reserve(na * 4));
-    CU(h, b_a1.reserve(na * 4)); CU(h, b_strand.reserve(na)); CU(h, b_sites.reserve(na * 4)); CU(h, b_counts.reserve(na * 12));
-    CU(h, b_conf.reserve(na * 4));
+    CU(h, b_chrom.reserve(na * 4, h->stream)); CU(h, b_i0.reserve(na * 4, h->stream)); CU(h, b_i1.reserve(na * 4, h->stream)); CU(h, b_a0.reserve(na * 4, h->stream));
+    CU(h, b_a1.reserve(na * 4, h->stream)); CU(h, b_strand.reserve(na, h->stream)); CU(h, b_sites.reserve(na * 4, h->stream)); CU(h, b_counts.reserve(na * 12, h->stream));
+    CU(h, b_conf.reserve(na * 4, h->stream));
     if (n) {
         CU(h, cudaMemcpyAsync(b_chrom.p, rows->chrom, n * 4, cudaMemcpyHostToDevice, st));
         CU(h, cudaMemcpyAsync(b_i0.p, rows->intron_start, n * 4, cudaMemcpyHostToDevice, st));
@@ -886,8 +895,8 @@ extern "C" int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ip
     const uint64_t J = n_keys, Ja = J ? J : 1;
     /* key order: (name rank, start, end) via two stable radix passes */
     DeviceBuf k_hi, k_lo, k_hi2, k_lo2, v_a, v_b, cnt, tmp;
-    CU(h, k_hi.reserve(Ja * 8)); CU(h, k_lo.reserve(Ja * 8)); CU(h, k_hi2.reserve(Ja * 8)); CU(h, k_lo2.reserve(Ja * 8));
-    CU(h, v_a.reserve(Ja * 4)); CU(h, v_b.reserve(Ja * 4)); CU(h, cnt.reserve(8));
+    CU(h, k_hi.reserve(Ja * 8, h->stream)); CU(h, k_lo.reserve(Ja * 8, h->stream)); CU(h, k_hi2.reserve(Ja * 8, h->stream)); CU(h, k_lo2.reserve(Ja * 8, h->stream));
+    CU(h, v_a.reserve(Ja * 4, h->stream)); CU(h, v_b.reserve(Ja * 4, h->stream)); CU(h, cnt.reserve(8, h->stream));
     CU(h, cudaMemsetAsync(cnt.p, 0, 8, st));
     HostTable *ht = new HostTable();
     memset(&ht->t, 0, sizeof(ht->t));
@@ -904,7 +913,7 @@ extern "C" int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ip
                                             (uint32_t *)v_a.p, (uint32_t *)v_b.p, (int)J, 0, 64, st);
             cub::DeviceRadixSort::SortPairs(nullptr, tb2, (unsigned long long *)k_hi.p, (unsigned long long *)k_hi2.p,
                                             (uint32_t *)v_b.p, (uint32_t *)v_a.p, (int)J, 0, 32, st);
-            CU(h, tmp.reserve(std::max(tb1, tb2)));
+            CU(h, tmp.reserve(std::max(tb1, tb2), h->stream));
             size_t tb = tmp.cap;
             cub::DeviceRadixSort::SortPairs(tmp.p, tb, (unsigned long long *)k_lo.p, (unsigned long long *)k_lo2.p,
                                             (uint32_t *)v_a.p, (uint32_t *)v_b.p, (int)J, 0, 64, st);
@@ -914,9 +923,9 @@ extern "C" int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ip
                                             (uint32_t *)v_b.p, (uint32_t *)v_a.p, (int)J, 0, 32, st);
         }
         DeviceBuf o_chrom, o_i0, o_i1, o_a0, o_a1, o_site, o_counts, o_conf, o_strand, o_slow;
-        CU(h, o_chrom.reserve(Ja * 4)); CU(h, o_i0.reserve(Ja * 4)); CU(h, o_i1.reserve(Ja * 4)); CU(h, o_a0.reserve(Ja * 4));
-        CU(h, o_a1.reserve(Ja * 4)); CU(h, o_site.reserve(Ja * 4)); CU(h, o_counts.reserve(Ja * 24)); CU(h, o_conf.reserve(Ja * 4));
-        CU(h, o_strand.reserve(Ja)); CU(h, o_slow.reserve(Ja));
+        CU(h, o_chrom.reserve(Ja * 4, h->stream)); CU(h, o_i0.reserve(Ja * 4, h->stream)); CU(h, o_i1.reserve(Ja * 4, h->stream)); CU(h, o_a0.reserve(Ja * 4, h->stream));
+        CU(h, o_a1.reserve(Ja * 4, h->stream)); CU(h, o_site.reserve(Ja * 4, h->stream)); CU(h, o_counts.reserve(Ja * 24, h->stream)); CU(h, o_conf.reserve(Ja * 4, h->stream));
+        CU(h, o_strand.reserve(Ja, h->stream)); CU(h, o_slow.reserve(Ja, h->stream));
         MergeOut mo{(int32_t *)o_chrom.p, (uint32_t *)o_i0.p, (uint32_t *)o_i1.p, (uint32_t *)o_a0.p, (uint32_t *)o_a1.p,
                     (uint32_t *)o_site.p, (unsigned long long *)o_counts.p, (float *)o_conf.p, (char *)o_strand.p,
                     (uint8_t *)o_slow.p};

@@ -86,7 +86,18 @@ struct FinalizeWork {
 cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, int32_t n_targets,
                             FinalizeWork &w, DeviceTable &out, bool keep_export_columns, cudaStream_t st,
                             int *own_launches);
-void free_device_table(DeviceTable &t);
+void free_device_table(DeviceTable &t, cudaStream_t st);
+
+/* stream-ordered allocation from the device's default pool (kept resident, see ipx_create): no implicit
+ * device synchronisation and no driver round trip once the pool is warm */
+template <class T>
+inline cudaError_t dmalloc(cudaStream_t st, T **p, size_t bytes) {
+    return cudaMallocAsync((void **)p, bytes ? bytes : 1, st);
+}
+template <class T>
+inline void dfree(cudaStream_t st, T *p) {
+    if (p) cudaFreeAsync((void *)p, st);
+}
 
 /* export rows for destination ranks: rows [0, n) of the finished table are already in key order */
 void launch_export_rows(const Tables &t, const DeviceTable &dt, JunctionRow *jr, HistRow *hr, cudaStream_t st);

@@ -397,21 +397,21 @@ __global__ void k_hist_offsets(const unsigned long long *sorted_hkey, uint64_t n
         if (e__ != cudaSuccess) return e__; \
     } while (0)
 
-static cudaError_t ensure_tmp(FinalizeWork &w, size_t bytes) {
+static cudaError_t ensure_tmp(FinalizeWork &w, size_t bytes, cudaStream_t st) {
     if (bytes > w.cub_tmp_bytes) {
-        if (w.cub_tmp) cudaFree(w.cub_tmp);
+        if (w.cub_tmp) dfree(st, w.cub_tmp);
         w.cub_tmp = nullptr;
         w.cub_tmp_bytes = 0;
-        IPX_CU(cudaMalloc(&w.cub_tmp, bytes));
+        IPX_CU(dmalloc(st, &w.cub_tmp, bytes));
         w.cub_tmp_bytes = bytes;
     }
     return cudaSuccess;
 }
 
-void free_device_table(DeviceTable &t) {
-    cudaFree(t.chrom); cudaFree(t.i0); cudaFree(t.i1); cudaFree(t.a0); cudaFree(t.a1); cudaFree(t.ijunc);
-    cudaFree(t.strand); cudaFree(t.sites); cudaFree(t.counts); cudaFree(t.T); cudaFree(t.hist_off);
-    cudaFree(t.hist_cnt); cudaFree(t.hist_offset); cudaFree(t.slot);
+void free_device_table(DeviceTable &t, cudaStream_t st) {
+    dfree(st, t.chrom); dfree(st, t.i0); dfree(st, t.i1); dfree(st, t.a0); dfree(st, t.a1); dfree(st, t.ijunc);
+    dfree(st, t.strand); dfree(st, t.sites); dfree(st, t.counts); dfree(st, t.T); dfree(st, t.hist_off);
+    dfree(st, t.hist_cnt); dfree(st, t.hist_offset); dfree(st, t.slot);
     t = DeviceTable();
 }
 
@@ -426,10 +426,10 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
     int launches = 0;
     const uint64_t cap = t.cap_mask + 1;
     out = DeviceTable();
-    if (!w.d_count) IPX_CU(cudaMalloc(&w.d_count, 4 * sizeof(unsigned long long)));
+    if (!w.d_count) IPX_CU(dmalloc(st, &w.d_count, 4 * sizeof(unsigned long long)));
     if (w.slot_rank_cap < cap) {
-        if (w.slot_rank) cudaFree(w.slot_rank);
-        IPX_CU(cudaMalloc(&w.slot_rank, cap * sizeof(uint32_t)));
+        if (w.slot_rank) dfree(st, w.slot_rank);
+        IPX_CU(dmalloc(st, &w.slot_rank, cap * sizeof(uint32_t)));
         w.slot_rank_cap = cap;
     }
     IPX_CU(cudaMemsetAsync(w.d_count, 0, 4 * sizeof(unsigned long long), st));
@@ -447,10 +447,10 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
 
     unsigned long long *sort_key = nullptr, *sort_key2 = nullptr;
     uint32_t *slot_a = nullptr, *slot_b = nullptr;
-    IPX_CU(cudaMalloc(&sort_key, nk * 8));
-    IPX_CU(cudaMalloc(&sort_key2, nk * 8));
-    IPX_CU(cudaMalloc(&slot_a, nk * 4));
-    IPX_CU(cudaMalloc(&slot_b, nk * 4));
+    IPX_CU(dmalloc(st, &sort_key, nk * 8));
+    IPX_CU(dmalloc(st, &sort_key2, nk * 8));
+    IPX_CU(dmalloc(st, &slot_a, nk * 4));
+    IPX_CU(dmalloc(st, &slot_b, nk * 4));
     k_compact_junctions<<<148 * 8, 256, 0, st>>>(t, d_name_rank, w.d_count, sort_key, slot_a);
     launches++;
     unsigned long long n_j = 0;
@@ -461,7 +461,7 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
     /* key order: chromosome-name rank, intron_start, intron_end */
     size_t tmp_bytes = 0;
     IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, sort_key, sort_key2, slot_a, slot_b, (int)n, 0, 64, st));
-    IPX_CU(ensure_tmp(w, tmp_bytes));
+    IPX_CU(ensure_tmp(w, tmp_bytes, st));
     if (n) IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp_bytes, sort_key, sort_key2, slot_a, slot_b, (int)n, 0, 64, st));
     const uint32_t *sorted_slot = slot_b;
     if (n) {
@@ -469,35 +469,35 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
         launches++;
     }
 
-    IPX_CU(cudaMalloc(&out.chrom, na * 4));
-    IPX_CU(cudaMalloc(&out.i0, na * 4));
-    IPX_CU(cudaMalloc(&out.i1, na * 4));
-    IPX_CU(cudaMalloc(&out.a0, na * 4));
-    IPX_CU(cudaMalloc(&out.a1, na * 4));
-    IPX_CU(cudaMalloc(&out.ijunc, na * 4));
-    IPX_CU(cudaMalloc(&out.strand, na));
-    IPX_CU(cudaMalloc(&out.sites, na * 8));
-    IPX_CU(cudaMalloc(&out.counts, na * 24));
-    IPX_CU(cudaMalloc(&out.T, na * 8));
-    IPX_CU(cudaMalloc(&out.hist_off, (na + 1) * 8));
-    if (keep_export) IPX_CU(cudaMalloc(&out.slot, na * 4));
+    IPX_CU(dmalloc(st, &out.chrom, na * 4));
+    IPX_CU(dmalloc(st, &out.i0, na * 4));
+    IPX_CU(dmalloc(st, &out.i1, na * 4));
+    IPX_CU(dmalloc(st, &out.a0, na * 4));
+    IPX_CU(dmalloc(st, &out.a1, na * 4));
+    IPX_CU(dmalloc(st, &out.ijunc, na * 4));
+    IPX_CU(dmalloc(st, &out.strand, na));
+    IPX_CU(dmalloc(st, &out.sites, na * 8));
+    IPX_CU(dmalloc(st, &out.counts, na * 24));
+    IPX_CU(dmalloc(st, &out.T, na * 8));
+    IPX_CU(dmalloc(st, &out.hist_off, (na + 1) * 8));
+    if (keep_export) IPX_CU(dmalloc(st, &out.slot, na * 4));
     out.n = n;
 
     /* sjN: rank of the creating event in stream order */
     if (n) {
         uint32_t *idx_a = slot_a; /* reuse */
         uint32_t *idx_b = nullptr;
-        IPX_CU(cudaMalloc(&idx_b, na * 4));
+        IPX_CU(dmalloc(st, &idx_b, na * 4));
         k_gather_T<<<blocks_for(n, 256), 256, 0, st>>>(t, sorted_slot, n, sort_key, idx_a);
         size_t tb = 0;
         IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, sort_key, sort_key2, idx_a, idx_b, (int)n, 0, 64, st));
-        IPX_CU(ensure_tmp(w, tb));
+        IPX_CU(ensure_tmp(w, tb, st));
         IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, sort_key, sort_key2, idx_a, idx_b, (int)n, 0, 64, st));
         k_scatter_ijunc<<<blocks_for(n, 256), 256, 0, st>>>(idx_b, n, out.ijunc);
         k_gather_rows<<<blocks_for(n, 256), 256, 0, st>>>(t, g, sorted_slot, n, out);
         launches += 3; /* gather_T, scatter_ijunc, gather_rows */
         IPX_CU(cudaStreamSynchronize(st));
-        cudaFree(idx_b);
+        dfree(st, idx_b);
     }
 
     /* offset histogram: count, gather, order by (junction rank, offset) */
@@ -509,11 +509,11 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
     const uint64_t nh = n_h, nha = nh ? nh : 1;
     unsigned long long *hk_a = nullptr, *hk_b = nullptr;
     uint32_t *hc_a = nullptr;
-    IPX_CU(cudaMalloc(&hk_a, nha * 8));
-    IPX_CU(cudaMalloc(&hk_b, nha * 8));
-    IPX_CU(cudaMalloc(&hc_a, nha * 4));
-    IPX_CU(cudaMalloc(&out.hist_cnt, nha * 4));
-    if (keep_export) IPX_CU(cudaMalloc(&out.hist_offset, nha * 4));
+    IPX_CU(dmalloc(st, &hk_a, nha * 8));
+    IPX_CU(dmalloc(st, &hk_b, nha * 8));
+    IPX_CU(dmalloc(st, &hc_a, nha * 4));
+    IPX_CU(dmalloc(st, &out.hist_cnt, nha * 4));
+    if (keep_export) IPX_CU(dmalloc(st, &out.hist_offset, nha * 4));
     out.n_hist = nh;
     IPX_CU(cudaMemsetAsync(&w.d_count[1], 0, sizeof(unsigned long long), st));
     IPX_CU(cudaMemsetAsync(out.hist_off, 0, (na + 1) * 8, st));
@@ -524,15 +524,15 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
         while (end_bit < 64 && (n >> (end_bit - 16)) != 0) end_bit++;
         size_t tb = 0;
         IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, hk_a, hk_b, hc_a, out.hist_cnt, (int)nh, 0, end_bit, st));
-        IPX_CU(ensure_tmp(w, tb));
+        IPX_CU(ensure_tmp(w, tb, st));
         IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, hk_a, hk_b, hc_a, out.hist_cnt, (int)nh, 0, end_bit, st));
     }
     k_hist_offsets<<<blocks_for(nha, 256), 256, 0, st>>>(hk_b, nh, n, out.hist_off, out.hist_offset);
     launches++;
     if (own_launches) *own_launches = launches;
     IPX_CU(cudaStreamSynchronize(st));
-    cudaFree(hk_a); cudaFree(hk_b); cudaFree(hc_a);
-    cudaFree(sort_key); cudaFree(sort_key2); cudaFree(slot_a); cudaFree(slot_b);
+    dfree(st, hk_a); dfree(st, hk_b); dfree(st, hc_a);
+    dfree(st, sort_key); dfree(st, sort_key2); dfree(st, slot_a); dfree(st, slot_b);
     return cudaGetLastError();
 }
 
