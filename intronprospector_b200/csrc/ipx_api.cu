@@ -196,13 +196,12 @@ uint64_t pow2_at_least(uint64_t v) {
 int alloc_tables(ipx_handle *h) {
     if (h->tables_ready) return IPX_OK;
     uint64_t cap = pow2_at_least(h->params.table_capacity ? h->params.table_capacity : (1ull << 22));
-    uint64_t hcap = pow2_at_least(h->params.hist_capacity ? h->params.hist_capacity : (1ull << 26));
+    uint64_t hcap = pow2_at_least(h->params.hist_capacity ? h->params.hist_capacity : (1ull << 25));
     if (cap > (1ull << 31)) return fail(h, IPX_ERR_ARG, "table_capacity too large");
     Tables &t = h->tab;
     CU(h, cudaMalloc(&t.keys, cap * sizeof(unsigned long long)));
     CU(h, cudaMalloc(&t.stat, cap * sizeof(JStat)));
-    CU(h, cudaMalloc(&t.hkeys, hcap * sizeof(unsigned long long)));
-    CU(h, cudaMalloc(&t.hcnt, hcap * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&t.hist, hcap * sizeof(HEntry)));
     CU(h, cudaMalloc(&h->d_counters, 8 * 128));
     CU(h, cudaMemsetAsync(h->d_counters, 0, 8 * 128, h->stream));
     t.cap_mask = cap - 1;
@@ -381,7 +380,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     cudaStreamSynchronize(h->stream);
     drain(h->tm_extract); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
     if (h->finalized) free_device_table(h->dt, h->stream);
-    cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.hkeys); cudaFree(h->tab.hcnt);
+    cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.hist);
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq);
     free_genome(h);
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();

@@ -36,10 +36,11 @@ __global__ void k_init_tables(Tables t) {
         s.a1 = 0u;
         t.stat[i] = s;
     }
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hcap; i += stride) {
-        t.hkeys[i] = EMPTY64;
-        t.hcnt[i] = 0u;
-    }
+    HEntry e;
+    e.key = EMPTY64;
+    e.cnt = 0u;
+    e.pad = 0u;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hcap; i += stride) t.hist[i] = e;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         *t.n_keys = 0ull;
         *t.n_hist = 0ull;
@@ -53,10 +54,52 @@ void launch_init_tables(const Tables &t, cudaStream_t st) {
 }
 
 /* ------------------------------------------------------------------ K1+K2: extract and aggregate */
+/* One junction event staged in shared memory between the two phases of a tile. */
+struct __align__(16) Event {
+    unsigned long long key;
+    unsigned long long sv;
+    uint32_t a0, a1;
+    uint32_t off_cat; /* uint16 read offset | category << 16 | strand class << 18 */
+    uint32_t pad;
+};
+
+static const int EX_THREADS = 256;
+static const int EX_RPT = 4;                       /* records per thread per tile */
+static const int EX_TILE = EX_THREADS * EX_RPT;    /* records per tile */
+static const int EX_EVCAP = 1024;                  /* staged events per tile (32 KB) */
+
+/* fold one event directly into the global tables (slow path when the staging buffer is full, and the body of the
+ * import kernels) */
+template <int MODE>
+__device__ __forceinline__ void fold_event_direct(const Tables &t, unsigned long long key, unsigned long long sv, uint32_t a0,
+                                                  uint32_t a1, uint32_t off, uint32_t cat, int cls) {
+    if (MODE == MODE_PASS2) {
+        const uint64_t slot = junction_find(t, key);
+        if (slot > t.cap_mask) return;
+        JStat *s = &t.stat[slot];
+        const unsigned long long T = *((volatile unsigned long long *)&s->T);
+        if (T == EMPTY64 || sv < T) return; /* before the junction exists: dropped */
+        stat_accumulate(s, cat, a0, a1);
+        hist_add(t, slot, off, 1u);
+    } else {
+        const uint64_t slot = junction_find_or_insert(t, key);
+        if (slot > t.cap_mask) return;
+        JStat *s = &t.stat[slot];
+        stat_first(s, cls, sv);
+        if (MODE == MODE_SINGLE) {
+            stat_accumulate(s, cat, a0, a1);
+            hist_add(t, slot, off, 1u);
+        }
+    }
+}
+
+/* Phase A sink: junction_qc, then stage the event in shared memory */
 template <int MODE>
 struct EventSink {
     const Tables &t;
     const ExtractParams &p;
+    Event *ev;
+    uint32_t *ev_count;
     int32_t tid;
     int64_t pos;
     uint64_t record_seq;
@@ -73,25 +116,21 @@ struct EventSink {
             atomicExch(t.overflow, 3u); /* outside what a BAM position can hold */
             return;
         }
-        const uint64_t key = make_key(t.kl, tid, c.intron_start, c.intron_end);
-        const uint64_t sv = make_sv(record_seq, c.ordinal, strand);
-        if (MODE == MODE_PASS2) {
-            const uint64_t slot = junction_find(t, key);
-            if (slot > t.cap_mask) return;
-            JStat *s = &t.stat[slot];
-            const unsigned long long T = *((volatile unsigned long long *)&s->T);
-            if (T == EMPTY64 || sv < T) return; /* before the junction exists: dropped (A6) */
-            stat_accumulate(s, cat, (uint32_t)c.anchor_start, (uint32_t)c.anchor_end);
-            hist_add(t, slot, (uint32_t)(c.intron_start - pos) & 0xFFFFu, 1u);
+        const unsigned long long key = make_key(t.kl, tid, c.intron_start, c.intron_end);
+        const unsigned long long sv = make_sv(record_seq, c.ordinal, strand);
+        const uint32_t off = (uint32_t)(c.intron_start - pos) & 0xFFFFu;
+        const uint32_t idx = atomicAdd(ev_count, 1u);
+        if (idx < (uint32_t)EX_EVCAP) {
+            Event e;
+            e.key = key;
+            e.sv = sv;
+            e.a0 = (uint32_t)c.anchor_start;
+            e.a1 = (uint32_t)c.anchor_end;
+            e.off_cat = off | (cat << 16) | ((uint32_t)cls << 18);
+            e.pad = 0u;
+            ev[idx] = e;
         } else {
-            const uint64_t slot = junction_find_or_insert(t, key);
-            if (slot > t.cap_mask) return;
-            JStat *s = &t.stat[slot];
-            stat_first(s, cls, sv);
-            if (MODE == MODE_SINGLE) {
-                stat_accumulate(s, cat, (uint32_t)c.anchor_start, (uint32_t)c.anchor_end);
-                hist_add(t, slot, (uint32_t)(c.intron_start - pos) & 0xFFFFu, 1u);
-            }
+            fold_event_direct<MODE>(t, key, sv, (uint32_t)c.anchor_start, (uint32_t)c.anchor_end, off, cat, cls);
         }
     }
 };
@@ -102,39 +141,119 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     return v;
 }
 
+/* Phase B: the 32 staged events held by one warp are grouped by key (match.any); the lowest lane of each group
+ * probes the junction table once and applies the group's combined counts and anchor extremes, so a junction that
+ * many neighbouring reads support costs one probe and a few atomics per warp instead of per read. */
 template <int MODE>
-__global__ void __launch_bounds__(256) k_extract(BatchView b, ExtractParams p, Tables t) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+__device__ __forceinline__ void fold_events_warp(const Tables &t, const Event *ev, uint32_t n_ev) {
+    const int lane = threadIdx.x & 31;
+    for (uint32_t base = (threadIdx.x & ~31u); base < n_ev; base += EX_THREADS) {
+        const uint32_t i = base + lane;
+        const bool valid = i < n_ev;
+        Event e;
+        if (valid) e = ev[i];
+        else { e.key = EMPTY64 - 1 - (unsigned)lane; e.sv = EMPTY64; e.a0 = 0xFFFFFFFFu; e.a1 = 0u; e.off_cat = 0u; }
+        const uint32_t cat = (e.off_cat >> 16) & 3u;
+        const int cls = (int)((e.off_cat >> 18) & 3u);
+        const unsigned grp = __match_any_sync(0xFFFFFFFFu, e.key);
+        const int leader = __ffs(grp) - 1;
+        uint64_t slot = t.cap_mask + 1;
+        unsigned long long T = 0ull;
+        if (lane == leader && valid) {
+            if (MODE == MODE_PASS2) {
+                slot = junction_find(t, e.key);
+                if (slot <= t.cap_mask) T = *((volatile unsigned long long *)&t.stat[slot].T);
+            } else {
+                slot = junction_find_or_insert(t, e.key);
+            }
+        }
+        slot = __shfl_sync(grp, slot, leader);
+        bool counted = valid && slot <= t.cap_mask;
+        if (MODE == MODE_PASS2) {
+            T = __shfl_sync(grp, T, leader);
+            counted = counted && T != EMPTY64 && e.sv >= T; /* earlier events are dropped */
+        }
+        if (MODE != MODE_PASS2 && counted) stat_first(&t.stat[slot], cls, e.sv);
+        if (MODE != MODE_PASS1) {
+            const unsigned c0 = __ballot_sync(0xFFFFFFFFu, counted && cat == 0u) & grp;
+            const unsigned c1 = __ballot_sync(0xFFFFFFFFu, counted && cat == 1u) & grp;
+            const unsigned c2 = __ballot_sync(0xFFFFFFFFu, counted && cat == 2u) & grp;
+            const uint32_t a0 = __reduce_min_sync(grp, counted ? e.a0 : 0xFFFFFFFFu);
+            const uint32_t a1 = __reduce_max_sync(grp, counted ? e.a1 : 0u);
+            if (lane == leader && (c0 | c1 | c2)) {
+                JStat *s = &t.stat[slot];
+                if (c0) atomicAdd(&s->cnt[0], (unsigned long long)__popc(c0));
+                if (c1) atomicAdd(&s->cnt[1], (unsigned long long)__popc(c1));
+                if (c2) atomicAdd(&s->cnt[2], (unsigned long long)__popc(c2));
+                if (a0 < *((volatile uint32_t *)&s->a0)) atomicMin(&s->a0, a0);
+                if (a1 > *((volatile uint32_t *)&s->a1)) atomicMax(&s->a1, a1);
+            }
+            if (counted) hist_add(t, slot, e.off_cat & 0xFFFFu, 1u);
+        }
+    }
+}
+
+/* One block works through tiles of EX_TILE consecutive records.
+ * Phase A: every thread loads the fixed-width columns of its EX_RPT records up front (coalesced, all loads in
+ *          flight together), walks the CIGAR of the live ones and stages their junction events in shared memory.
+ * Phase B: all threads fold the staged events into the tables (fold_events_warp). */
+template <int MODE>
+__global__ void __launch_bounds__(EX_THREADS) k_extract(BatchView b, ExtractParams p, Tables t) {
+    __shared__ Event ev[EX_EVCAP];
+    __shared__ uint32_t ev_count;
     unsigned long long live_words = 0ull, events = 0ull;
-    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < b.n; r += stride) {
-        const uint32_t c0 = __ldg(&b.cigar_off[r]);
-        const uint32_t c1 = __ldg(&b.cigar_off[r + 1]);
-        const int32_t tid = __ldg(&b.tid[r]);
-        const uint32_t flag = __ldg(&b.flag[r]);
-        const uint32_t n_cigar = c1 - c0;
-        if (!record_is_live(n_cigar, tid, flag)) continue;
-        live_words += n_cigar;
-        const int64_t pos = __ldg(&b.pos[r]);
-        const uint32_t nh = __ldg(&b.nh[r]);
-        const uint32_t xs = __ldg(&b.xs[r]);
-        const char strand = read_strand(p.strandness, flag, xs);
-        EventSink<MODE> sink{t, p, tid, pos, b.seq_base + r, read_category(flag, nh), strand, strand_class(strand),
-                             read_may_emit(p, flag, nh), 0u};
-        WalkState w;
-        w.init(pos);
-        uint32_t bad = 0u;
-        const uint32_t *cig = b.cigar + c0;
-        for (uint32_t k = 0; k < n_cigar; ++k) {
-            bad = walk_op(w, __ldg(&cig[k]), p.max_anchor_indel_size, sink);
-            if (bad) break;
+    const uint64_t n_tiles = (b.n + EX_TILE - 1) / EX_TILE;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (threadIdx.x == 0) ev_count = 0u;
+        __syncthreads();
+        const uint64_t base = tile * EX_TILE + threadIdx.x;
+        uint32_t c0[EX_RPT], c1[EX_RPT], flag[EX_RPT];
+        int32_t tid[EX_RPT];
+#pragma unroll
+        for (int j = 0; j < EX_RPT; ++j) {
+            const uint64_t r = base + (uint64_t)j * EX_THREADS;
+            c0[j] = c1[j] = 0u;
+            flag[j] = 0u;
+            tid[j] = -1;
+            if (r < b.n) {
+                c0[j] = __ldg(&b.cigar_off[r]);
+                c1[j] = __ldg(&b.cigar_off[r + 1]);
+                tid[j] = __ldg(&b.tid[r]);
+                flag[j] = __ldg(&b.flag[r]);
+            }
         }
-        if (bad) {
-            /* the reference throws here; keep the first such record in stream order */
-            atomicMin(t.err_sv, make_err_cigar(b.seq_base + r, bad & 15u));
-        } else {
-            walk_finish(w, sink);
+#pragma unroll
+        for (int j = 0; j < EX_RPT; ++j) {
+            const uint32_t n_cigar = c1[j] - c0[j];
+            if (!record_is_live(n_cigar, tid[j], flag[j])) continue;
+            const uint64_t r = base + (uint64_t)j * EX_THREADS;
+            live_words += n_cigar;
+            const int64_t pos = __ldg(&b.pos[r]);
+            const uint32_t nh = __ldg(&b.nh[r]);
+            const uint32_t xs = __ldg(&b.xs[r]);
+            const char strand = read_strand(p.strandness, flag[j], xs);
+            EventSink<MODE> sink{t, p, ev, &ev_count, tid[j], pos, b.seq_base + r, read_category(flag[j], nh), strand,
+                                 strand_class(strand), read_may_emit(p, flag[j], nh), 0u};
+            WalkState w;
+            w.init(pos);
+            uint32_t bad = 0u;
+            const uint32_t *cig = b.cigar + c0[j];
+            for (uint32_t k = 0; k < n_cigar; ++k) {
+                bad = walk_op(w, __ldg(&cig[k]), p.max_anchor_indel_size, sink);
+                if (bad) break;
+            }
+            if (bad) {
+                /* the reference throws here; keep the first such record in stream order */
+                atomicMin(t.err_sv, make_err_cigar(b.seq_base + r, bad & 15u));
+            } else {
+                walk_finish(w, sink);
+            }
+            events += sink.n_events;
         }
-        events += sink.n_events;
+        __syncthreads();
+        const uint32_t n_ev = ev_count < (uint32_t)EX_EVCAP ? ev_count : (uint32_t)EX_EVCAP;
+        fold_events_warp<MODE>(t, ev, n_ev);
+        __syncthreads();
     }
     /* one atomic per warp for the unit counters */
     live_words = warp_sum(live_words);
@@ -148,14 +267,13 @@ __global__ void __launch_bounds__(256) k_extract(BatchView b, ExtractParams p, T
 void launch_extract(int mode, const BatchView &b, const ExtractParams &p, const Tables &t, int sm_count,
                     cudaStream_t st) {
     if (b.n == 0) return;
-    const int threads = 256;
-    uint64_t want = (b.n + threads - 1) / threads;
-    uint64_t max_blocks = (uint64_t)sm_count * 8;
-    int blocks = (int)(want < max_blocks ? want : max_blocks);
+    const uint64_t n_tiles = (b.n + EX_TILE - 1) / EX_TILE;
+    const uint64_t max_blocks = (uint64_t)sm_count * 6; /* 33 KB of shared memory per block: 6 resident per SM */
+    const int blocks = (int)(n_tiles < max_blocks ? n_tiles : max_blocks);
     switch (mode) {
-        case MODE_SINGLE: k_extract<MODE_SINGLE><<<blocks, threads, 0, st>>>(b, p, t); break;
-        case MODE_PASS1: k_extract<MODE_PASS1><<<blocks, threads, 0, st>>>(b, p, t); break;
-        default: k_extract<MODE_PASS2><<<blocks, threads, 0, st>>>(b, p, t); break;
+        case MODE_SINGLE: k_extract<MODE_SINGLE><<<blocks, EX_THREADS, 0, st>>>(b, p, t); break;
+        case MODE_PASS1: k_extract<MODE_PASS1><<<blocks, EX_THREADS, 0, st>>>(b, p, t); break;
+        default: k_extract<MODE_PASS2><<<blocks, EX_THREADS, 0, st>>>(b, p, t); break;
     }
 }
 
@@ -349,34 +467,52 @@ __global__ void k_gather_rows(Tables t, GenomeView g, const uint32_t *sorted_slo
     for (int k = 0; k < 8; ++k) out.sites[8 * i + k] = site[k];
 }
 
-/* every (junction, offset) pair of a created junction -> (rank << 16 | offset, count) */
-__global__ void k_compact_hist(Tables t, const uint32_t *slot_rank, unsigned long long *d_count,
-                               unsigned long long *hkey_out, uint32_t *hcnt_out, int count_only) {
+/* every (junction, offset) pair of a created junction -> (rank << 16 | offset, count); one atomic per block step */
+static const int CH_PER_THREAD = 8;
+__global__ void __launch_bounds__(256) k_compact_hist(Tables t, const uint32_t *slot_rank, unsigned long long *d_count,
+                                                      unsigned long long *hkey_out, uint32_t *hcnt_out, int count_only) {
+    typedef cub::BlockScan<uint32_t, 256> Scan;
+    __shared__ typename Scan::TempStorage scan_tmp;
+    __shared__ unsigned long long block_base;
     const uint64_t hcap = t.hcap_mask + 1;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < hcap; base += stride) {
-        const uint64_t i = base + threadIdx.x;
-        bool take = false;
-        unsigned long long hk = EMPTY64;
-        uint32_t rank = 0xFFFFFFFFu;
-        if (i < hcap) {
-            hk = t.hkeys[i];
-            if (hk != EMPTY64) {
-                rank = slot_rank[hk >> 16];
-                take = rank != 0xFFFFFFFFu;
+    const uint64_t step = 256ull * CH_PER_THREAD;
+    for (uint64_t base = (uint64_t)blockIdx.x * step; base < hcap; base += (uint64_t)gridDim.x * step) {
+        unsigned long long hk[CH_PER_THREAD];
+        uint32_t cnt[CH_PER_THREAD], rank[CH_PER_THREAD];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int j = 0; j < CH_PER_THREAD; ++j) {
+            const uint64_t i = base + (uint64_t)j * 256 + threadIdx.x;
+            hk[j] = EMPTY64;
+            cnt[j] = 0u;
+            if (i < hcap) {
+                const HEntry e = t.hist[i];
+                hk[j] = e.key;
+                cnt[j] = e.cnt;
             }
         }
-        const unsigned mask = __ballot_sync(0xFFFFFFFFu, take);
-        if (mask == 0u) continue;
-        const int lane = threadIdx.x & 31;
-        unsigned long long warp_base = 0ull;
-        if (lane == 0) warp_base = atomicAdd(&d_count[1], (unsigned long long)__popc(mask));
-        warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
-        if (take && !count_only) {
-            const uint64_t o = warp_base + __popc(mask & ((1u << lane) - 1u));
-            hkey_out[o] = ((unsigned long long)rank << 16) | (hk & 0xFFFFull);
-            hcnt_out[o] = t.hcnt[i];
+#pragma unroll
+        for (int j = 0; j < CH_PER_THREAD; ++j) {
+            rank[j] = 0xFFFFFFFFu;
+            if (hk[j] != EMPTY64) rank[j] = slot_rank[hk[j] >> 16];
+            if (rank[j] != 0xFFFFFFFFu) mine++;
         }
+        uint32_t offset, total;
+        Scan(scan_tmp).ExclusiveSum(mine, offset, total);
+        if (threadIdx.x == 0 && total) block_base = atomicAdd(&d_count[1], (unsigned long long)total);
+        __syncthreads();
+        if (!count_only && total) {
+            uint64_t o = block_base + offset;
+#pragma unroll
+            for (int j = 0; j < CH_PER_THREAD; ++j) {
+                if (rank[j] != 0xFFFFFFFFu) {
+                    hkey_out[o] = ((unsigned long long)rank[j] << 16) | (hk[j] & 0xFFFFull);
+                    hcnt_out[o] = cnt[j];
+                    o++;
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 

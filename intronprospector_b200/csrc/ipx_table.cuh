@@ -62,6 +62,17 @@ struct alignas(64) JStat {
     uint32_t a1;                 /* max anchor_end */
 };
 
+/* offset-table entry: key and count share one 16-byte slot so that a probe and its count touch one sector */
+#if defined(__CUDACC__)
+struct __align__(16) HEntry {
+#else
+struct alignas(16) HEntry {
+#endif
+    unsigned long long key; /* junction slot << 16 | uint16 read offset, EMPTY64 = free */
+    uint32_t cnt;
+    uint32_t pad;
+};
+
 struct KeyLayout {
     int len_bits;   /* L */
     int start_shift; /* = L */
@@ -89,8 +100,7 @@ IPX_HD uint64_t mix64(uint64_t x) {
 struct Tables {
     unsigned long long *keys; /* [cap] */
     JStat *stat;              /* [cap] */
-    unsigned long long *hkeys; /* [hcap]  slot << 16 | offset */
-    uint32_t *hcnt;           /* [hcap] */
+    HEntry *hist;             /* [hcap] */
     uint64_t cap_mask, hcap_mask;
     /* counters / flags, one cache line each to avoid false sharing */
     unsigned long long *n_keys;    /* distinct keys inserted */
@@ -137,22 +147,18 @@ __device__ __forceinline__ uint64_t junction_find(const Tables &t, uint64_t key)
     return t.cap_mask + 1;
 }
 
-/* count one read at (slot, offset): Junction::count_read's push_back (junctions.hh:163-167) */
+/* count n reads at (slot, offset): Junction::count_read's push_back (junctions.hh:163-167), run-length form */
 __device__ __forceinline__ void hist_add(const Tables &t, uint64_t slot, uint32_t offset16, uint32_t n) {
     const unsigned long long hk = ((unsigned long long)slot << 16) | offset16;
     uint64_t h = mix64(hk) & t.hcap_mask;
     for (uint32_t probe = 0; probe < MAX_PROBE; ++probe) {
-        unsigned long long k = *((volatile unsigned long long *)&t.hkeys[h]);
+        unsigned long long k = *((volatile unsigned long long *)&t.hist[h].key);
         if (k == EMPTY64) {
-            unsigned long long old = atomicCAS(&t.hkeys[h], EMPTY64, hk);
-            if (old == EMPTY64) {
-                k = hk; /* no global counter here: R inserts on one address would serialise */
-            } else {
-                k = old;
-            }
+            const unsigned long long old = atomicCAS(&t.hist[h].key, EMPTY64, hk);
+            k = (old == EMPTY64) ? hk : old; /* no global insert counter: R inserts on one address would serialise */
         }
         if (k == hk) {
-            atomicAdd(&t.hcnt[h], n);
+            atomicAdd(&t.hist[h].cnt, n);
             return;
         }
         h = (h + 1) & t.hcap_mask;
