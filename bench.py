@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -299,13 +299,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # samples cover the warm-up steps and the timed region (both run the same load)
+        time.sleep(0.3)
     for _ in range(args.warmup):
         device_step()
     barrier()
     eng.reset_timings()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for a, b in ev:

@@ -202,6 +202,11 @@ int alloc_tables(ipx_handle *h) {
     CU(h, cudaMalloc(&t.keys, cap * sizeof(unsigned long long)));
     CU(h, cudaMalloc(&t.stat, cap * sizeof(JStat)));
     CU(h, cudaMalloc(&t.hist, hcap * sizeof(HEntry)));
+    /* dense offset rows: one per junction up to a quarter of the slots (the table is kept at most half full) */
+    t.dense_rows = std::min<uint64_t>(cap / 4, 1ull << 21);
+    CU(h, cudaMalloc(&t.dense_idx, cap * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&t.dense, t.dense_rows * DENSE_W * sizeof(uint32_t)));
+    CU(h, cudaMemsetAsync(t.dense, 0, t.dense_rows * DENSE_W * sizeof(uint32_t), h->stream));
     CU(h, cudaMalloc(&h->d_counters, 8 * 128));
     CU(h, cudaMemsetAsync(h->d_counters, 0, 8 * 128, h->stream));
     t.cap_mask = cap - 1;
@@ -380,7 +385,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     cudaStreamSynchronize(h->stream);
     drain(h->tm_extract); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
     if (h->finalized) free_device_table(h->dt, h->stream);
-    cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.hist);
+    cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.hist); cudaFree(h->tab.dense_idx); cudaFree(h->tab.dense);
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq);
     free_genome(h);
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();

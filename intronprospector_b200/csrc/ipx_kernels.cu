@@ -23,11 +23,22 @@
 namespace ipx {
 
 /* ------------------------------------------------------------------ table initialisation */
+/* zero the dense rows in use; runs before k_init_tables resets n_keys */
+__global__ void k_clear_dense(Tables t) {
+    unsigned long long rows = *t.n_keys;
+    if (rows > t.dense_rows) rows = t.dense_rows;
+    const uint64_t n4 = rows * (DENSE_W / 4);
+    uint4 *p = reinterpret_cast<uint4 *>(t.dense);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 __global__ void k_init_tables(Tables t) {
     const uint64_t cap = t.cap_mask + 1, hcap = t.hcap_mask + 1;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
         t.keys[i] = EMPTY64;
+        t.dense_idx[i] = DENSE_NONE;
         JStat s;
         s.first[0] = s.first[1] = s.first[2] = EMPTY64;
         s.T = EMPTY64;
@@ -50,6 +61,7 @@ __global__ void k_init_tables(Tables t) {
 }
 
 void launch_init_tables(const Tables &t, cudaStream_t st) {
+    k_clear_dense<<<148 * 8, 256, 0, st>>>(t);
     k_init_tables<<<148 * 8, 256, 0, st>>>(t);
 }
 
@@ -71,25 +83,26 @@ static const int EX_EVCAP = 1024;                  /* staged events per tile (32
 /* fold one event directly into the global tables (slow path when the staging buffer is full, and the body of the
  * import kernels) */
 template <int MODE>
-__device__ __forceinline__ void fold_event_direct(const Tables &t, unsigned long long key, unsigned long long sv, uint32_t a0,
-                                                  uint32_t a1, uint32_t off, uint32_t cat, int cls) {
+__device__ __forceinline__ uint32_t fold_event_direct(const Tables &t, unsigned long long key, unsigned long long sv,
+                                                      uint32_t a0, uint32_t a1, uint32_t off, uint32_t cat, int cls) {
     if (MODE == MODE_PASS2) {
         const uint64_t slot = junction_find(t, key);
-        if (slot > t.cap_mask) return;
+        if (slot > t.cap_mask) return 0u;
         JStat *s = &t.stat[slot];
         const unsigned long long T = *((volatile unsigned long long *)&s->T);
-        if (T == EMPTY64 || sv < T) return; /* before the junction exists: dropped */
+        if (T == EMPTY64 || sv < T) return 0u; /* before the junction exists: dropped */
         stat_accumulate(s, cat, a0, a1);
-        hist_add(t, slot, off, 1u);
+        return hist_count(t, slot, off, 1u);
     } else {
         const uint64_t slot = junction_find_or_insert(t, key);
-        if (slot > t.cap_mask) return;
+        if (slot > t.cap_mask) return 0u;
         JStat *s = &t.stat[slot];
         stat_first(s, cls, sv);
         if (MODE == MODE_SINGLE) {
             stat_accumulate(s, cat, a0, a1);
-            hist_add(t, slot, off, 1u);
+            return hist_count(t, slot, off, 1u);
         }
+        return 0u;
     }
 }
 
@@ -108,6 +121,7 @@ struct EventSink {
     int cls;
     bool may_emit;
     uint32_t n_events;
+    uint32_t n_hash_inserts;
 
     __device__ __forceinline__ void operator()(const Candidate &c) {
         if (!may_emit || !junction_qc(p, c)) return;
@@ -130,7 +144,7 @@ struct EventSink {
             e.pad = 0u;
             ev[idx] = e;
         } else {
-            fold_event_direct<MODE>(t, key, sv, (uint32_t)c.anchor_start, (uint32_t)c.anchor_end, off, cat, cls);
+            n_hash_inserts += fold_event_direct<MODE>(t, key, sv, (uint32_t)c.anchor_start, (uint32_t)c.anchor_end, off, cat, cls);
         }
     }
 };
@@ -145,8 +159,9 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
  * probes the junction table once and applies the group's combined counts and anchor extremes, so a junction that
  * many neighbouring reads support costs one probe and a few atomics per warp instead of per read. */
 template <int MODE>
-__device__ __forceinline__ void fold_events_warp(const Tables &t, const Event *ev, uint32_t n_ev) {
+__device__ __forceinline__ uint32_t fold_events_warp(const Tables &t, const Event *ev, uint32_t n_ev) {
     const int lane = threadIdx.x & 31;
+    uint32_t inserts = 0u;
     for (uint32_t base = (threadIdx.x & ~31u); base < n_ev; base += EX_THREADS) {
         const uint32_t i = base + lane;
         const bool valid = i < n_ev;
@@ -188,9 +203,10 @@ __device__ __forceinline__ void fold_events_warp(const Tables &t, const Event *e
                 if (a0 < *((volatile uint32_t *)&s->a0)) atomicMin(&s->a0, a0);
                 if (a1 > *((volatile uint32_t *)&s->a1)) atomicMax(&s->a1, a1);
             }
-            if (counted) hist_add(t, slot, e.off_cat & 0xFFFFu, 1u);
+            if (counted) inserts += hist_count(t, slot, e.off_cat & 0xFFFFu, 1u);
         }
     }
+    return inserts;
 }
 
 /* One block works through tiles of EX_TILE consecutive records.
@@ -201,7 +217,7 @@ template <int MODE>
 __global__ void __launch_bounds__(EX_THREADS) k_extract(BatchView b, ExtractParams p, Tables t) {
     __shared__ Event ev[EX_EVCAP];
     __shared__ uint32_t ev_count;
-    unsigned long long live_words = 0ull, events = 0ull;
+    unsigned long long live_words = 0ull, events = 0ull, hash_inserts = 0ull;
     const uint64_t n_tiles = (b.n + EX_TILE - 1) / EX_TILE;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (threadIdx.x == 0) ev_count = 0u;
@@ -233,7 +249,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(BatchView b, ExtractPara
             const uint32_t xs = __ldg(&b.xs[r]);
             const char strand = read_strand(p.strandness, flag[j], xs);
             EventSink<MODE> sink{t, p, ev, &ev_count, tid[j], pos, b.seq_base + r, read_category(flag[j], nh), strand,
-                                 strand_class(strand), read_may_emit(p, flag[j], nh), 0u};
+                                 strand_class(strand), read_may_emit(p, flag[j], nh), 0u, 0u};
             WalkState w;
             w.init(pos);
             uint32_t bad = 0u;
@@ -249,18 +265,21 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(BatchView b, ExtractPara
                 walk_finish(w, sink);
             }
             events += sink.n_events;
+            hash_inserts += sink.n_hash_inserts;
         }
         __syncthreads();
         const uint32_t n_ev = ev_count < (uint32_t)EX_EVCAP ? ev_count : (uint32_t)EX_EVCAP;
-        fold_events_warp<MODE>(t, ev, n_ev);
+        hash_inserts += fold_events_warp<MODE>(t, ev, n_ev);
         __syncthreads();
     }
     /* one atomic per warp for the unit counters */
     live_words = warp_sum(live_words);
     events = warp_sum(events);
-    if ((threadIdx.x & 31) == 0 && MODE != MODE_PASS2) {
-        if (live_words) atomicAdd(t.n_live, live_words);
-        if (events) atomicAdd(t.n_events, events);
+    hash_inserts = warp_sum(hash_inserts);
+    if ((threadIdx.x & 31) == 0) {
+        if (MODE != MODE_PASS2 && live_words) atomicAdd(t.n_live, live_words);
+        if (MODE != MODE_PASS2 && events) atomicAdd(t.n_events, events);
+        if (hash_inserts) atomicAdd(t.n_hist, hash_inserts);
     }
 }
 
@@ -494,7 +513,7 @@ __global__ void __launch_bounds__(256) k_compact_hist(Tables t, const uint32_t *
 #pragma unroll
         for (int j = 0; j < CH_PER_THREAD; ++j) {
             rank[j] = 0xFFFFFFFFu;
-            if (hk[j] != EMPTY64) rank[j] = slot_rank[hk[j] >> 16];
+            if (hk[j] != EMPTY64 && hk[j] != TOMB64) rank[j] = slot_rank[hk[j] >> 16];
             if (rank[j] != 0xFFFFFFFFu) mine++;
         }
         uint32_t offset, total;
@@ -516,15 +535,96 @@ __global__ void __launch_bounds__(256) k_compact_hist(Tables t, const uint32_t *
     }
 }
 
-/* hist_off[r] = index of the first run of junction r in the sorted run list */
-__global__ void k_hist_offsets(const unsigned long long *sorted_hkey, uint64_t n_hist, uint64_t n_junc,
-                               unsigned long long *hist_off, uint32_t *hist_offset_out) {
+/* entries with a small offset that raced ahead of their junction's dense row: move them into the row */
+__global__ void k_drain_small(Tables t) {
+    const uint64_t hcap = t.hcap_mask + 1;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hcap; i += stride) {
+        const HEntry e = t.hist[i];
+        if (e.key == EMPTY64 || e.key == TOMB64) continue;
+        const uint32_t off = (uint32_t)(e.key & 0xFFFFull);
+        if (off >= DENSE_W) continue;
+        const uint32_t d = t.dense_idx[e.key >> 16];
+        if (d == DENSE_NONE) continue;
+        atomicAdd(&t.dense[(uint64_t)d * DENSE_W + off], e.cnt);
+        t.hist[i].key = TOMB64;
+    }
+}
+
+/* per junction (key order): first index and number of its entries in the sorted hash-run list */
+__global__ void k_hash_runs(const unsigned long long *sorted_hkey, uint64_t n_hash, unsigned long long *hash_lo,
+                            unsigned long long *total) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) hist_off[n_junc] = n_hist;
-    if (i >= n_hist) return;
+    if (i >= n_hash) return;
     const uint64_t r = sorted_hkey[i] >> 16;
-    if (hist_offset_out) hist_offset_out[i] = (uint32_t)(sorted_hkey[i] & 0xFFFFull);
-    if (i == 0 || (sorted_hkey[i - 1] >> 16) != r) hist_off[r] = i;
+    if (i == 0 || (sorted_hkey[i - 1] >> 16) != r) hash_lo[r] = i;
+    atomicAdd(&total[r], 1ull);
+}
+
+/* warp per junction: number of non-zero counters of its dense row, added to total[r] */
+__global__ void k_dense_count(Tables t, const uint32_t *sorted_slot, uint64_t n, unsigned long long *total,
+                              uint32_t *dense_nz) {
+    const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const uint32_t d = t.dense_idx[sorted_slot[r]];
+    uint32_t nz = 0;
+    if (d != DENSE_NONE) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)d * DENSE_W);
+        const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
+        nz = (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0) + (b.x != 0) + (b.y != 0) + (b.z != 0) + (b.w != 0);
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, k);
+    if (lane == 0) {
+        dense_nz[r] = nz;
+        total[r] += nz;
+    }
+}
+
+/* warp per junction: write its runs in ascending offset order -- dense row first (offsets < DENSE_W), then its
+ * slice of the sorted hash runs (all >= DENSE_W once k_drain_small has run, or everything when it has no row) */
+__global__ void k_write_runs(Tables t, const uint32_t *sorted_slot, uint64_t n, const unsigned long long *hist_off,
+                             const uint32_t *dense_nz, const unsigned long long *hash_lo,
+                             const unsigned long long *sorted_hkey, const uint32_t *sorted_hcnt, uint32_t *hist_cnt,
+                             uint32_t *hist_offset) {
+    const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const unsigned long long o0 = hist_off[r];
+    const uint32_t nz = dense_nz[r];
+    const uint32_t d = t.dense_idx[sorted_slot[r]];
+    if (d != DENSE_NONE && nz) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)d * DENSE_W);
+        const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
+        const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mine += (v[k] != 0);
+        uint32_t pre = mine;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, pre, k);
+            if (lane >= k) pre += y;
+        }
+        uint64_t o = o0 + (pre - mine);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (v[k] != 0) {
+                hist_cnt[o] = v[k];
+                if (hist_offset) hist_offset[o] = (uint32_t)(lane * 8 + k);
+                o++;
+            }
+        }
+    }
+    const unsigned long long n_hash = (hist_off[r + 1] - o0) - nz;
+    if (n_hash) {
+        const unsigned long long lo = hash_lo[r];
+        for (unsigned long long j = lane; j < n_hash; j += 32) {
+            hist_cnt[o0 + nz + j] = sorted_hcnt[lo + j];
+            if (hist_offset) hist_offset[o0 + nz + j] = (uint32_t)(sorted_hkey[lo + j] & 0xFFFFull);
+        }
+    }
 }
 
 #define IPX_CU(x)                          \
@@ -576,8 +676,9 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
     launches++;
 
     /* number of keys bounds the number of junctions */
-    unsigned long long n_keys = 0;
+    unsigned long long n_keys = 0, n_hash_entries = 0;
     IPX_CU(cudaMemcpyAsync(&n_keys, t.n_keys, sizeof(n_keys), cudaMemcpyDeviceToHost, st));
+    IPX_CU(cudaMemcpyAsync(&n_hash_entries, t.n_hist, sizeof(n_hash_entries), cudaMemcpyDeviceToHost, st));
     IPX_CU(cudaStreamSynchronize(st));
     const uint64_t nk = n_keys ? n_keys : 1;
 
@@ -615,7 +716,7 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
     IPX_CU(dmalloc(st, &out.sites, na * 8));
     IPX_CU(dmalloc(st, &out.counts, na * 24));
     IPX_CU(dmalloc(st, &out.T, na * 8));
-    IPX_CU(dmalloc(st, &out.hist_off, (na + 1) * 8));
+    IPX_CU(dmalloc(st, &out.hist_off, (na + 2) * 8));
     if (keep_export) IPX_CU(dmalloc(st, &out.slot, na * 4));
     out.n = n;
 
@@ -636,38 +737,66 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
         dfree(st, idx_b);
     }
 
-    /* offset histogram: count, gather, order by (junction rank, offset) */
-    k_compact_hist<<<148 * 8, 256, 0, st>>>(t, w.slot_rank, w.d_count, nullptr, nullptr, 1);
-    launches++;
-    unsigned long long n_h = 0;
-    IPX_CU(cudaMemcpyAsync(&n_h, &w.d_count[1], sizeof(n_h), cudaMemcpyDeviceToHost, st));
-    IPX_CU(cudaStreamSynchronize(st));
-    const uint64_t nh = n_h, nha = nh ? nh : 1;
-    unsigned long long *hk_a = nullptr, *hk_b = nullptr;
-    uint32_t *hc_a = nullptr;
-    IPX_CU(dmalloc(st, &hk_a, nha * 8));
-    IPX_CU(dmalloc(st, &hk_b, nha * 8));
-    IPX_CU(dmalloc(st, &hc_a, nha * 4));
-    IPX_CU(dmalloc(st, &out.hist_cnt, nha * 4));
-    if (keep_export) IPX_CU(dmalloc(st, &out.hist_offset, nha * 4));
-    out.n_hist = nh;
-    IPX_CU(cudaMemsetAsync(&w.d_count[1], 0, sizeof(unsigned long long), st));
-    IPX_CU(cudaMemsetAsync(out.hist_off, 0, (na + 1) * 8, st));
+    /* offset histogram.  Hash part first (only long reads / pool overflow put anything there): fold raced
+     * small-offset entries into their dense rows, then order the rest by (junction rank, offset). */
+    unsigned long long *hk_a = nullptr, *hk_b = nullptr, *hash_lo = nullptr, *total = nullptr;
+    uint32_t *hc_a = nullptr, *hc_b = nullptr, *dense_nz = nullptr;
+    uint64_t nh = 0;
+    if (n_hash_entries) {
+        k_drain_small<<<148 * 8, 256, 0, st>>>(t);
+        k_compact_hist<<<148 * 8, 256, 0, st>>>(t, w.slot_rank, w.d_count, nullptr, nullptr, 1);
+        launches += 2;
+        unsigned long long n_h = 0;
+        IPX_CU(cudaMemcpyAsync(&n_h, &w.d_count[1], sizeof(n_h), cudaMemcpyDeviceToHost, st));
+        IPX_CU(cudaStreamSynchronize(st));
+        nh = n_h;
+    }
+    const uint64_t nha = nh ? nh : 1;
+    IPX_CU(dmalloc(st, &hash_lo, na * 8));
+    IPX_CU(dmalloc(st, &total, (na + 1) * 8));
+    IPX_CU(dmalloc(st, &dense_nz, na * 4));
+    IPX_CU(cudaMemsetAsync(total, 0, (na + 1) * 8, st));
     if (nh) {
+        IPX_CU(dmalloc(st, &hk_a, nha * 8));
+        IPX_CU(dmalloc(st, &hk_b, nha * 8));
+        IPX_CU(dmalloc(st, &hc_a, nha * 4));
+        IPX_CU(dmalloc(st, &hc_b, nha * 4));
+        IPX_CU(cudaMemsetAsync(&w.d_count[1], 0, sizeof(unsigned long long), st));
         k_compact_hist<<<148 * 8, 256, 0, st>>>(t, w.slot_rank, w.d_count, hk_a, hc_a, 0);
-        launches++;
         int end_bit = 16;
         while (end_bit < 64 && (n >> (end_bit - 16)) != 0) end_bit++;
         size_t tb = 0;
-        IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, hk_a, hk_b, hc_a, out.hist_cnt, (int)nh, 0, end_bit, st));
+        IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, hk_a, hk_b, hc_a, hc_b, (int)nh, 0, end_bit, st));
         IPX_CU(ensure_tmp(w, tb, st));
-        IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, hk_a, hk_b, hc_a, out.hist_cnt, (int)nh, 0, end_bit, st));
+        IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, hk_a, hk_b, hc_a, hc_b, (int)nh, 0, end_bit, st));
+        k_hash_runs<<<blocks_for(nh, 256), 256, 0, st>>>(hk_b, nh, hash_lo, total);
+        launches += 2;
     }
-    k_hist_offsets<<<blocks_for(nha, 256), 256, 0, st>>>(hk_b, nh, n, out.hist_off, out.hist_offset);
-    launches++;
+    unsigned long long n_runs = 0;
+    if (n) {
+        k_dense_count<<<blocks_for(n * 32, 256), 256, 0, st>>>(t, sorted_slot, n, total, dense_nz);
+        launches++;
+    }
+    {
+        size_t tb = 0;
+        IPX_CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, total, out.hist_off, (int)(n + 1), st));
+        IPX_CU(ensure_tmp(w, tb, st));
+        IPX_CU(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, total, out.hist_off, (int)(n + 1), st));
+    }
+    IPX_CU(cudaMemcpyAsync(&n_runs, out.hist_off + n, sizeof(n_runs), cudaMemcpyDeviceToHost, st));
+    IPX_CU(cudaStreamSynchronize(st));
+    out.n_hist = n_runs;
+    IPX_CU(dmalloc(st, &out.hist_cnt, (n_runs ? n_runs : 1) * 4));
+    if (keep_export) IPX_CU(dmalloc(st, &out.hist_offset, (n_runs ? n_runs : 1) * 4));
+    if (n) {
+        k_write_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(t, sorted_slot, n, out.hist_off, dense_nz, hash_lo, hk_b, hc_b,
+                                                            out.hist_cnt, out.hist_offset);
+        launches++;
+    }
     if (own_launches) *own_launches = launches;
     IPX_CU(cudaStreamSynchronize(st));
-    dfree(st, hk_a); dfree(st, hk_b); dfree(st, hc_a);
+    dfree(st, hk_a); dfree(st, hk_b); dfree(st, hc_a); dfree(st, hc_b);
+    dfree(st, hash_lo); dfree(st, total); dfree(st, dense_nz);
     dfree(st, sort_key); dfree(st, sort_key2); dfree(st, slot_a); dfree(st, slot_b);
     return cudaGetLastError();
 }
@@ -726,7 +855,8 @@ __global__ void k_import_hist_rows(Tables t, const HistRow *hr, uint64_t n) {
     const uint64_t key = make_key(t.kl, r.tid, r.i0, r.i1);
     const uint64_t slot = junction_find_or_insert(t, key);
     if (slot > t.cap_mask) return;
-    hist_add(t, slot, r.offset & 0xFFFFu, r.cnt);
+    const uint32_t ins = hist_count(t, slot, r.offset & 0xFFFFu, r.cnt);
+    if (ins) atomicAdd(t.n_hist, (unsigned long long)ins);
 }
 
 void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh,

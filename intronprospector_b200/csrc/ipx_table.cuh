@@ -25,6 +25,13 @@
 namespace ipx {
 
 static const uint64_t EMPTY64 = ~0ull;
+static const uint64_t TOMB64 = ~0ull - 1; /* offset-table entry folded into a dense row during finalize */
+/* Read offsets (intron_start - read start) of short reads are < read length; counts for offsets below DENSE_W
+ * live in a per-junction dense row (one 1 KB row per junction, allocated in insertion order), where counting a
+ * read is a single fire-and-forget atomic and the ordered run-length output needs no sort.  Larger offsets
+ * (long reads) and junctions beyond the pool go to the (junction, offset) hash table. */
+static const uint32_t DENSE_W = 256;
+static const uint32_t DENSE_NONE = 0xFFFFFFFFu;
 static const int SV_ORD_BITS = 20;
 static const int SV_SEQ_SHIFT = 28;
 
@@ -101,6 +108,9 @@ struct Tables {
     unsigned long long *keys; /* [cap] */
     JStat *stat;              /* [cap] */
     HEntry *hist;             /* [hcap] */
+    uint32_t *dense_idx;      /* [cap] row of the junction in `dense`, DENSE_NONE = none */
+    uint32_t *dense;          /* [dense_rows][DENSE_W] read counts for offsets < DENSE_W */
+    uint64_t dense_rows;
     uint64_t cap_mask, hcap_mask;
     /* counters / flags, one cache line each to avoid false sharing */
     unsigned long long *n_keys;    /* distinct keys inserted */
@@ -124,7 +134,8 @@ __device__ __forceinline__ uint64_t junction_find_or_insert(const Tables &t, uin
         if (k == EMPTY64) {
             unsigned long long old = atomicCAS(&t.keys[h], EMPTY64, (unsigned long long)key);
             if (old == EMPTY64) {
-                atomicAdd(t.n_keys, 1ull);
+                const unsigned long long id = atomicAdd(t.n_keys, 1ull);
+                if (id < t.dense_rows) atomicExch(&t.dense_idx[h], (uint32_t)id);
                 return h;
             }
             if (old == key) return h;
@@ -147,23 +158,40 @@ __device__ __forceinline__ uint64_t junction_find(const Tables &t, uint64_t key)
     return t.cap_mask + 1;
 }
 
-/* count n reads at (slot, offset): Junction::count_read's push_back (junctions.hh:163-167), run-length form */
-__device__ __forceinline__ void hist_add(const Tables &t, uint64_t slot, uint32_t offset16, uint32_t n) {
+/* hash path of hist_count; returns 1 when a new (slot, offset) entry was created */
+__device__ __forceinline__ uint32_t hist_add_hash(const Tables &t, uint64_t slot, uint32_t offset16, uint32_t n) {
     const unsigned long long hk = ((unsigned long long)slot << 16) | offset16;
     uint64_t h = mix64(hk) & t.hcap_mask;
     for (uint32_t probe = 0; probe < MAX_PROBE; ++probe) {
         unsigned long long k = *((volatile unsigned long long *)&t.hist[h].key);
+        uint32_t inserted = 0u;
         if (k == EMPTY64) {
             const unsigned long long old = atomicCAS(&t.hist[h].key, EMPTY64, hk);
-            k = (old == EMPTY64) ? hk : old; /* no global insert counter: R inserts on one address would serialise */
+            inserted = (old == EMPTY64) ? 1u : 0u;
+            k = inserted ? hk : old;
         }
         if (k == hk) {
             atomicAdd(&t.hist[h].cnt, n);
-            return;
+            return inserted;
         }
         h = (h + 1) & t.hcap_mask;
     }
     atomicExch(t.overflow, 2u);
+    return 0u;
+}
+
+/* count n reads at (slot, offset): Junction::count_read's push_back (junctions.hh:163-167), run-length form.
+ * Returns the number of hash entries created (callers sum it per block into n_hist). */
+__device__ __forceinline__ uint32_t hist_count(const Tables &t, uint64_t slot, uint32_t offset16, uint32_t n) {
+    if (offset16 < DENSE_W) {
+        /* the row index is published right after the key; a reader that races ahead of it uses the hash instead */
+        const uint32_t d = *((volatile uint32_t *)&t.dense_idx[slot]);
+        if (d != DENSE_NONE) {
+            atomicAdd(&t.dense[(uint64_t)d * DENSE_W + offset16], n);
+            return 0u;
+        }
+    }
+    return hist_add_hash(t, slot, offset16, n);
 }
 
 /* fold one counted read into a junction's statistics */
