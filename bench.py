@@ -12,8 +12,8 @@ table on the device (key order, sjN ranking, ordered offset histograms).
                launching stream (max over ranks), whole job (all ranks' records / slowest rank's time)
   e2e          the same pass through the public C ABI with HOST (pinned) columns: ipx_push_batch (H2D copies inside
                the timed region) + ipx_flush (table D2H + float32 confidences on the host)
-  roofline     the fused extract+aggregate kernel: algorithmic bytes (16 B per record + 4 B per live CIGAR word, see
-               DESIGN.md) / its CUDA-event time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  roofline     the extract kernel K1: algorithmic bytes (16 B per record + 4 B per live CIGAR word + 32 B per junction
+               event) / its CUDA-event time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline the unmodified reference binary (oracle/_ref/intronProspector, 1 thread) on a bounded prefix of the
                same stream written as an uncompressed BAM, timed on this box's host cores
 
@@ -345,7 +345,7 @@ def main():
         k_ms = tm["extract_ms"] / max(1, tm["extract_launches"])
         live = tm["cigar_live"] / steps
         events = tm["events"] / steps
-        alg_bytes = 16.0 * n + 4.0 * live
+        alg_bytes = 16.0 * n + 4.0 * live + 32.0 * events
         peak, peak_src = measured_hbm_peak()
         achieved = alg_bytes / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0
         traffic = ncu_traffic()
@@ -361,12 +361,15 @@ def main():
                        "generate_s": gen_s},
             "e2e": {"value": total_records / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms},
-            "gpu_launches": int(tm["extract_launches"] + tm["finalize_launches"] + tm["motif_launches"]),
-            "roofline": {"bound": "hbm", "kernel": "k_extract<MODE_SINGLE> (fused CIGAR walk + keyed aggregation)",
+            "gpu_launches": int(tm["extract_launches"] + tm["aggregate_launches"] + tm["finalize_launches"] + tm["motif_launches"]),
+            "roofline": {"bound": "hbm", "kernel": "k_extract (K1: CIGAR walk -> junction events)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": (traffic * n) if traffic else None, "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": k_ms, "peak_source": peak_src,
-                         "stage_ms_per_step": {"extract_aggregate": tm["extract_ms"] / steps, "finalize": tm["finalize_ms"] / steps}},
+                         "stage_ms_per_step": {"extract": tm["extract_ms"] / steps, "aggregate": tm["aggregate_ms"] / steps,
+                                               "finalize_and_clear": tm["finalize_ms"] / steps},
+                         "aggregate_kernel": {"kernel": "k_fold<MODE_SINGLE> (K2)", "algorithmic_bytes_per_launch": 32.0 * events,
+                                              "kernel_ms": tm["aggregate_ms"] / max(1, tm["aggregate_launches"])}},
             "cpu_baseline": cpu_line,
             "clocks": clocks,
         }

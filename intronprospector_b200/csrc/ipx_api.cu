@@ -112,6 +112,7 @@ struct ipx_handle {
 
     /* staging for host batches */
     DeviceBuf s_tid, s_pos, s_flag, s_nh, s_xs, s_off, s_cig;
+    DeviceBuf ev_buf; /* junction events of the batch in flight (K1 -> K2) */
 
     /* finalize */
     FinalizeWork fw;
@@ -125,7 +126,7 @@ struct ipx_handle {
     uint64_t mt_cap = 0;
 
     /* timings */
-    StageTimer tm_extract, tm_motif, tm_finalize, tm_merge;
+    StageTimer tm_extract, tm_aggregate, tm_motif, tm_finalize, tm_merge;
     ipx_timings totals{};
     unsigned long long events_base = 0, live_base = 0;
 };
@@ -294,28 +295,37 @@ void free_genome(ipx_handle *h) {
     h->have_genome = false;
 }
 
-int run_batch(ipx_handle *h, const BatchView &b) {
+int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
     if (h->finalized) return fail(h, IPX_ERR_STATE, "ipx_push_batch after ipx_finalize_device without ipx_flush");
     if (h->targets.empty()) return fail(h, IPX_ERR_STATE, "ipx_set_targets must be called before ipx_push_batch");
     int rc = alloc_tables(h);
     if (rc) return rc;
     if (b.n >> 36) return fail(h, IPX_ERR_ARG, "batch too large");
+    /* event buffer for the worst case: every emitted candidate consumes one N op and a following aligned op */
+    const uint64_t ev_bound = n_cigar / 2 + 1;
+    CU(h, h->ev_buf.reserve(ev_bound * sizeof(Event), h->stream));
+    unsigned long long *ev_count = h->d_counters + 96;
+    CU(h, cudaMemsetAsync(ev_count, 0, sizeof(unsigned long long), h->stream));
+    {
+        Span s(h, &h->tm_extract, 1);
+        launch_extract(b, h->xp, h->tab, (Event *)h->ev_buf.p, ev_count, h->sm_count, h->stream);
+    }
     if (two_pass(h)) {
         {
-            Span s(h, &h->tm_extract, 1);
-            launch_extract(MODE_PASS1, b, h->xp, h->tab, h->sm_count, h->stream);
+            Span s(h, &h->tm_aggregate, 1);
+            launch_fold(MODE_PASS1, h->tab, (const Event *)h->ev_buf.p, ev_count, h->sm_count, h->stream);
         }
         {
             Span s(h, &h->tm_motif, 1);
             launch_resolve_T(h->tab, genome_view(h), h->stream);
         }
         {
-            Span s(h, &h->tm_extract, 1);
-            launch_extract(MODE_PASS2, b, h->xp, h->tab, h->sm_count, h->stream);
+            Span s(h, &h->tm_aggregate, 1);
+            launch_fold(MODE_PASS2, h->tab, (const Event *)h->ev_buf.p, ev_count, h->sm_count, h->stream);
         }
     } else {
-        Span s(h, &h->tm_extract, 1);
-        launch_extract(MODE_SINGLE, b, h->xp, h->tab, h->sm_count, h->stream);
+        Span s(h, &h->tm_aggregate, 1);
+        launch_fold(MODE_SINGLE, h->tab, (const Event *)h->ev_buf.p, ev_count, h->sm_count, h->stream);
     }
     CU(h, cudaGetLastError());
     h->totals.records += b.n;
@@ -383,13 +393,13 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    drain(h->tm_extract); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
+    drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
     if (h->finalized) free_device_table(h->dt, h->stream);
     cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.hist); cudaFree(h->tab.dense_idx); cudaFree(h->tab.dense);
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq);
     free_genome(h);
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();
-    h->s_off.release(); h->s_cig.release();
+    h->s_off.release(); h->s_cig.release(); h->ev_buf.release();
     cudaFree(h->fw.cub_tmp); cudaFree(h->fw.d_count); cudaFree(h->fw.slot_rank);
     cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -441,7 +451,7 @@ extern "C" int ipx_push_batch_device(ipx_handle *h, const ipx_batch *b) {
     if (!h || !b) return IPX_ERR_ARG;
     cudaSetDevice(h->device);
     BatchView v{b->tid, b->pos, b->flag, b->nh_class, b->xs, b->cigar_off, b->cigar, b->n_records, b->seq_base};
-    return run_batch(h, v);
+    return run_batch(h, v, b->n_cigar);
 }
 
 extern "C" int ipx_push_batch(ipx_handle *h, const ipx_batch *b) {
@@ -468,7 +478,7 @@ extern "C" int ipx_push_batch(ipx_handle *h, const ipx_batch *b) {
     BatchView v{(const int32_t *)h->s_tid.p, (const int32_t *)h->s_pos.p, (const uint16_t *)h->s_flag.p,
                 (const uint8_t *)h->s_nh.p, (const uint8_t *)h->s_xs.p, (const uint32_t *)h->s_off.p,
                 (const uint32_t *)h->s_cig.p, n, b->seq_base};
-    return run_batch(h, v);
+    return run_batch(h, v, b->n_cigar);
 }
 
 extern "C" int ipx_finalize_device(ipx_handle *h) {
@@ -692,15 +702,15 @@ extern "C" int ipx_get_timings(ipx_handle *h, ipx_timings *out) {
     if (!h || !out) return IPX_ERR_ARG;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    drain(h->tm_extract); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
+    drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
     ipx_timings t = h->totals;
     t.extract_ms = h->tm_extract.ms;
-    t.aggregate_ms = 0.0; /* fused into the extract kernel */
+    t.aggregate_ms = h->tm_aggregate.ms;
     t.motif_ms = h->tm_motif.ms;
     t.finalize_ms = h->tm_finalize.ms;
     t.merge_ms = h->tm_merge.ms;
     t.extract_launches = h->tm_extract.launches;
-    t.aggregate_launches = 0;
+    t.aggregate_launches = h->tm_aggregate.launches;
     t.motif_launches = h->tm_motif.launches;
     t.finalize_launches = h->tm_finalize.launches;
     t.merge_launches = h->tm_merge.launches;
@@ -720,8 +730,8 @@ extern "C" int ipx_reset_timings(ipx_handle *h) {
     if (!h) return IPX_ERR_ARG;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    drain(h->tm_extract); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
-    h->tm_extract = StageTimer(); h->tm_motif = StageTimer(); h->tm_finalize = StageTimer(); h->tm_merge = StageTimer();
+    drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
+    h->tm_extract = StageTimer(); h->tm_aggregate = StageTimer(); h->tm_motif = StageTimer(); h->tm_finalize = StageTimer(); h->tm_merge = StageTimer();
     h->totals = ipx_timings{};
     if (h->tables_ready) {
         cudaMemcpy(&h->events_base, h->tab.n_events, 8, cudaMemcpyDeviceToHost);
@@ -862,8 +872,8 @@ extern "C" int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ip
         CU(h, cudaMemsetAsync(h->d_counters, 0, 8 * 128, st));
     }
     h->mt.cap_mask = h->mt_cap - 1;
-    h->mt.n_keys = h->d_counters + 96;
-    h->mt.overflow = (uint32_t *)(h->d_counters + 112);
+    h->mt.n_keys = h->d_counters + 112;
+    h->mt.overflow = (uint32_t *)(h->d_counters + 120);
     /* upload the row columns */
     DeviceBuf b_chrom, b_i0, b_i1, b_a0, b_a1, b_strand, b_sites, b_counts, b_conf;
     const uint64_t na = n ? n : 1;

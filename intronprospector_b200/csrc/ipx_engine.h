@@ -67,7 +67,10 @@ enum ExtractMode { MODE_SINGLE = 0, MODE_PASS1 = 1, MODE_PASS2 = 2 };
 
 /* kernels' launchers; all asynchronous on `st` */
 void launch_init_tables(const Tables &t, cudaStream_t st);
-void launch_extract(int mode, const BatchView &b, const ExtractParams &p, const Tables &t, int sm_count, cudaStream_t st);
+void launch_extract(const BatchView &b, const ExtractParams &p, const Tables &t, Event *out, unsigned long long *out_count,
+                    int sm_count, cudaStream_t st);
+void launch_fold(int mode, const Tables &t, const Event *ev, const unsigned long long *n_events_ptr, int sm_count,
+                 cudaStream_t st);
 void launch_resolve_T(const Tables &t, const GenomeView &g, cudaStream_t st);
 void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh,
                         cudaStream_t st);

@@ -65,54 +65,21 @@ void launch_init_tables(const Tables &t, cudaStream_t st) {
     k_init_tables<<<148 * 8, 256, 0, st>>>(t);
 }
 
-/* ------------------------------------------------------------------ K1+K2: extract and aggregate */
-/* One junction event staged in shared memory between the two phases of a tile. */
-struct __align__(16) Event {
-    unsigned long long key;
-    unsigned long long sv;
-    uint32_t a0, a1;
-    uint32_t off_cat; /* uint16 read offset | category << 16 | strand class << 18 */
-    uint32_t pad;
-};
-
+/* ------------------------------------------------------------------ K1: extract */
 static const int EX_THREADS = 256;
 static const int EX_RPT = 4;                       /* records per thread per tile */
 static const int EX_TILE = EX_THREADS * EX_RPT;    /* records per tile */
-static const int EX_EVCAP = 1024;                  /* staged events per tile (32 KB) */
+static const int EX_EVCAP = 1024;                  /* staged events per tile (32 KB); more go out one by one */
 
-/* fold one event directly into the global tables (slow path when the staging buffer is full, and the body of the
- * import kernels) */
-template <int MODE>
-__device__ __forceinline__ uint32_t fold_event_direct(const Tables &t, unsigned long long key, unsigned long long sv,
-                                                      uint32_t a0, uint32_t a1, uint32_t off, uint32_t cat, int cls) {
-    if (MODE == MODE_PASS2) {
-        const uint64_t slot = junction_find(t, key);
-        if (slot > t.cap_mask) return 0u;
-        JStat *s = &t.stat[slot];
-        const unsigned long long T = *((volatile unsigned long long *)&s->T);
-        if (T == EMPTY64 || sv < T) return 0u; /* before the junction exists: dropped (SURVEY.md 8a A6) */
-        stat_accumulate(s, cat, a0, a1);
-        return hist_count(t, slot, off, 1u);
-    } else {
-        const uint64_t slot = junction_find_or_insert(t, key);
-        if (slot > t.cap_mask) return 0u;
-        JStat *s = &t.stat[slot];
-        stat_first(s, cls, sv);
-        if (MODE == MODE_SINGLE) {
-            stat_accumulate(s, cat, a0, a1);
-            return hist_count(t, slot, off, 1u);
-        }
-        return 0u;
-    }
-}
-
-/* Phase A sink: junction_qc, then stage the event in shared memory */
-template <int MODE>
+/* K1 sink: junction_qc, then stage the event in shared memory (or, past the staging capacity, write it out
+ * through a per-event reservation) */
 struct EventSink {
     const Tables &t;
     const ExtractParams &p;
-    Event *ev;
-    uint32_t *ev_count;
+    Event *stage;
+    uint32_t *stage_count;
+    Event *out;
+    unsigned long long *out_count;
     int32_t tid;
     int64_t pos;
     uint64_t record_seq;
@@ -121,7 +88,6 @@ struct EventSink {
     int cls;
     bool may_emit;
     uint32_t n_events;
-    uint32_t n_hash_inserts;
 
     __device__ __forceinline__ void operator()(const Candidate &c) {
         if (!may_emit || !junction_qc(p, c)) return;
@@ -130,22 +96,16 @@ struct EventSink {
             atomicExch(t.overflow, 3u); /* outside what a BAM position can hold */
             return;
         }
-        const unsigned long long key = make_key(t.kl, tid, c.intron_start, c.intron_end);
-        const unsigned long long sv = make_sv(record_seq, c.ordinal, strand);
-        const uint32_t off = (uint32_t)(c.intron_start - pos) & 0xFFFFu;
-        const uint32_t idx = atomicAdd(ev_count, 1u);
-        if (idx < (uint32_t)EX_EVCAP) {
-            Event e;
-            e.key = key;
-            e.sv = sv;
-            e.a0 = (uint32_t)c.anchor_start;
-            e.a1 = (uint32_t)c.anchor_end;
-            e.off_cat = off | (cat << 16) | ((uint32_t)cls << 18);
-            e.pad = 0u;
-            ev[idx] = e;
-        } else {
-            n_hash_inserts += fold_event_direct<MODE>(t, key, sv, (uint32_t)c.anchor_start, (uint32_t)c.anchor_end, off, cat, cls);
-        }
+        Event e;
+        e.key = make_key(t.kl, tid, c.intron_start, c.intron_end);
+        e.sv = make_sv(record_seq, c.ordinal, strand);
+        e.a0 = (uint32_t)c.anchor_start;
+        e.a1 = (uint32_t)c.anchor_end;
+        e.off_cat = ((uint32_t)(c.intron_start - pos) & 0xFFFFu) | (cat << 16) | ((uint32_t)cls << 18);
+        e.pad = 0u;
+        const uint32_t idx = atomicAdd(stage_count, 1u);
+        if (idx < (uint32_t)EX_EVCAP) stage[idx] = e;
+        else out[atomicAdd(out_count, 1ull)] = e; /* a tile of very long reads: rare, still exact */
     }
 };
 
@@ -155,72 +115,20 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     return v;
 }
 
-/* Phase B: the 32 staged events held by one warp are grouped by key (match.any); the lowest lane of each group
- * probes the junction table once and applies the group's combined counts and anchor extremes, so a junction that
- * many neighbouring reads support costs one probe and a few atomics per warp instead of per read. */
-template <int MODE>
-__device__ __forceinline__ uint32_t fold_events_warp(const Tables &t, const Event *ev, uint32_t n_ev) {
-    const int lane = threadIdx.x & 31;
-    uint32_t inserts = 0u;
-    for (uint32_t base = (threadIdx.x & ~31u); base < n_ev; base += EX_THREADS) {
-        const uint32_t i = base + lane;
-        const bool valid = i < n_ev;
-        Event e;
-        if (valid) e = ev[i];
-        else { e.key = EMPTY64 - 1 - (unsigned)lane; e.sv = EMPTY64; e.a0 = 0xFFFFFFFFu; e.a1 = 0u; e.off_cat = 0u; }
-        const uint32_t cat = (e.off_cat >> 16) & 3u;
-        const int cls = (int)((e.off_cat >> 18) & 3u);
-        const unsigned grp = __match_any_sync(0xFFFFFFFFu, e.key);
-        const int leader = __ffs(grp) - 1;
-        uint64_t slot = t.cap_mask + 1;
-        unsigned long long T = 0ull;
-        if (lane == leader && valid) {
-            if (MODE == MODE_PASS2) {
-                slot = junction_find(t, e.key);
-                if (slot <= t.cap_mask) T = *((volatile unsigned long long *)&t.stat[slot].T);
-            } else {
-                slot = junction_find_or_insert(t, e.key);
-            }
-        }
-        slot = __shfl_sync(grp, slot, leader);
-        bool counted = valid && slot <= t.cap_mask;
-        if (MODE == MODE_PASS2) {
-            T = __shfl_sync(grp, T, leader);
-            counted = counted && T != EMPTY64 && e.sv >= T; /* earlier events are dropped (SURVEY.md 8a A6) */
-        }
-        if (MODE != MODE_PASS2 && counted) stat_first(&t.stat[slot], cls, e.sv);
-        if (MODE != MODE_PASS1) {
-            const unsigned c0 = __ballot_sync(0xFFFFFFFFu, counted && cat == 0u) & grp;
-            const unsigned c1 = __ballot_sync(0xFFFFFFFFu, counted && cat == 1u) & grp;
-            const unsigned c2 = __ballot_sync(0xFFFFFFFFu, counted && cat == 2u) & grp;
-            const uint32_t a0 = __reduce_min_sync(grp, counted ? e.a0 : 0xFFFFFFFFu);
-            const uint32_t a1 = __reduce_max_sync(grp, counted ? e.a1 : 0u);
-            if (lane == leader && (c0 | c1 | c2)) {
-                JStat *s = &t.stat[slot];
-                if (c0) atomicAdd(&s->cnt[0], (unsigned long long)__popc(c0));
-                if (c1) atomicAdd(&s->cnt[1], (unsigned long long)__popc(c1));
-                if (c2) atomicAdd(&s->cnt[2], (unsigned long long)__popc(c2));
-                if (a0 < *((volatile uint32_t *)&s->a0)) atomicMin(&s->a0, a0);
-                if (a1 > *((volatile uint32_t *)&s->a1)) atomicMax(&s->a1, a1);
-            }
-            if (counted) inserts += hist_count(t, slot, e.off_cat & 0xFFFFu, 1u);
-        }
-    }
-    return inserts;
-}
-
-/* One block works through tiles of EX_TILE consecutive records.
- * Phase A: every thread loads the fixed-width columns of its EX_RPT records up front (coalesced, all loads in
- *          flight together), walks the CIGAR of the live ones and stages their junction events in shared memory.
- * Phase B: all threads fold the staged events into the tables (fold_events_warp). */
-template <int MODE>
-__global__ void __launch_bounds__(EX_THREADS) k_extract(BatchView b, ExtractParams p, Tables t) {
-    __shared__ Event ev[EX_EVCAP];
-    __shared__ uint32_t ev_count;
-    unsigned long long live_words = 0ull, events = 0ull, hash_inserts = 0ull;
+/* K1.  One block works through tiles of EX_TILE consecutive records.  Every thread loads the fixed-width columns of
+ * its EX_RPT records up front (coalesced, all loads in flight together), walks the CIGAR of the live ones
+ * (ipx_walk.cuh) and stages their junction events in shared memory; the tile then reserves a contiguous range of
+ * the event buffer with ONE atomic and copies its events out with coalesced 16-byte stores.  The event buffer is
+ * sized by the host for the worst case (one event per two CIGAR words), so nothing can be lost. */
+__global__ void __launch_bounds__(EX_THREADS) k_extract(BatchView b, ExtractParams p, Tables t, Event *out,
+                                                        unsigned long long *out_count) {
+    __shared__ Event stage[EX_EVCAP];
+    __shared__ uint32_t stage_count;
+    __shared__ unsigned long long tile_base;
+    unsigned long long live_words = 0ull, events = 0ull;
     const uint64_t n_tiles = (b.n + EX_TILE - 1) / EX_TILE;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (threadIdx.x == 0) ev_count = 0u;
+        if (threadIdx.x == 0) stage_count = 0u;
         __syncthreads();
         const uint64_t base = tile * EX_TILE + threadIdx.x;
         uint32_t c0[EX_RPT], c1[EX_RPT], flag[EX_RPT];
@@ -248,8 +156,8 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(BatchView b, ExtractPara
             const uint32_t nh = __ldg(&b.nh[r]);
             const uint32_t xs = __ldg(&b.xs[r]);
             const char strand = read_strand(p.strandness, flag[j], xs);
-            EventSink<MODE> sink{t, p, ev, &ev_count, tid[j], pos, b.seq_base + r, read_category(flag[j], nh), strand,
-                                 strand_class(strand), read_may_emit(p, flag[j], nh), 0u, 0u};
+            EventSink sink{t, p, stage, &stage_count, out, out_count, tid[j], pos, b.seq_base + r,
+                           read_category(flag[j], nh), strand, strand_class(strand), read_may_emit(p, flag[j], nh), 0u};
             WalkState w;
             w.init(pos);
             uint32_t bad = 0u;
@@ -265,34 +173,147 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(BatchView b, ExtractPara
                 walk_finish(w, sink);
             }
             events += sink.n_events;
-            hash_inserts += sink.n_hash_inserts;
         }
         __syncthreads();
-        const uint32_t n_ev = ev_count < (uint32_t)EX_EVCAP ? ev_count : (uint32_t)EX_EVCAP;
-        hash_inserts += fold_events_warp<MODE>(t, ev, n_ev);
+        const uint32_t n_ev = stage_count < (uint32_t)EX_EVCAP ? stage_count : (uint32_t)EX_EVCAP;
+        if (threadIdx.x == 0 && n_ev) tile_base = atomicAdd(out_count, (unsigned long long)n_ev);
+        __syncthreads();
+        if (n_ev) {
+            /* 32-byte events as two 16-byte halves: consecutive threads write consecutive 16-byte words */
+            const uint4 *src = reinterpret_cast<const uint4 *>(stage);
+            uint4 *dst = reinterpret_cast<uint4 *>(out + tile_base);
+            for (uint32_t i = threadIdx.x; i < n_ev * 2u; i += EX_THREADS) dst[i] = src[i];
+        }
         __syncthreads();
     }
     /* one atomic per warp for the unit counters */
     live_words = warp_sum(live_words);
     events = warp_sum(events);
-    hash_inserts = warp_sum(hash_inserts);
     if ((threadIdx.x & 31) == 0) {
-        if (MODE != MODE_PASS2 && live_words) atomicAdd(t.n_live, live_words);
-        if (MODE != MODE_PASS2 && events) atomicAdd(t.n_events, events);
-        if (hash_inserts) atomicAdd(t.n_hist, hash_inserts);
+        if (live_words) atomicAdd(t.n_live, live_words);
+        if (events) atomicAdd(t.n_events, events);
     }
 }
 
-void launch_extract(int mode, const BatchView &b, const ExtractParams &p, const Tables &t, int sm_count,
-                    cudaStream_t st) {
+void launch_extract(const BatchView &b, const ExtractParams &p, const Tables &t, Event *out, unsigned long long *out_count,
+                    int sm_count, cudaStream_t st) {
     if (b.n == 0) return;
     const uint64_t n_tiles = (b.n + EX_TILE - 1) / EX_TILE;
-    const uint64_t max_blocks = (uint64_t)sm_count * 6; /* 33 KB of shared memory per block: 6 resident per SM */
+    const uint64_t max_blocks = (uint64_t)sm_count * 6; /* 33 KB of shared memory per block */
     const int blocks = (int)(n_tiles < max_blocks ? n_tiles : max_blocks);
+    k_extract<<<blocks, EX_THREADS, 0, st>>>(b, p, t, out, out_count);
+}
+
+/* ------------------------------------------------------------------ K2: keyed aggregation */
+/* fold one event into the tables on its own (import kernels and tests of the slow path) */
+template <int MODE>
+__device__ __forceinline__ uint32_t fold_event_direct(const Tables &t, unsigned long long key, unsigned long long sv,
+                                                      uint32_t a0, uint32_t a1, uint32_t off, uint32_t cat, int cls) {
+    if (MODE == MODE_PASS2) {
+        const uint64_t slot = junction_find(t, key);
+        if (slot > t.cap_mask) return 0u;
+        JStat *s = &t.stat[slot];
+        const unsigned long long T = *((volatile unsigned long long *)&s->T);
+        if (T == EMPTY64 || sv < T) return 0u; /* before the junction exists: dropped (SURVEY.md 8a A6) */
+        stat_accumulate(s, cat, a0, a1);
+        return hist_count(t, slot, off, 1u);
+    } else {
+        const uint64_t slot = junction_find_or_insert(t, key);
+        if (slot > t.cap_mask) return 0u;
+        JStat *s = &t.stat[slot];
+        stat_first(s, cls, sv);
+        if (MODE == MODE_SINGLE) {
+            stat_accumulate(s, cat, a0, a1);
+            return hist_count(t, slot, off, 1u);
+        }
+        return 0u;
+    }
+}
+
+/* K2.  Every warp takes 32 consecutive events (neighbouring reads, so mostly the same few junctions), groups them
+ * by key with match.any, and lets the lowest lane of each group probe the junction table once and apply the
+ * group's combined read counts and anchor extremes; each lane then counts its own read offset (one fire-and-forget
+ * atomic into the junction's dense offset row, or the offset hash table for large offsets).
+ *   MODE_SINGLE  no canon filter: insert + first-seen + counts + anchors + offsets
+ *   MODE_PASS1   canon filter:    insert + first-seen per strand class only
+ *   MODE_PASS2   canon filter:    count events at or after the creation threshold T */
+template <int MODE>
+__global__ void __launch_bounds__(256) k_fold(Tables t, const Event *ev, const unsigned long long *n_events_ptr) {
+    const unsigned long long n_ev = *n_events_ptr;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t inserts = 0u;
+    for (uint64_t base = warp0 * 32; base < n_ev; base += n_warps * 32) {
+        const uint64_t i = base + lane;
+        const bool valid = i < n_ev;
+        Event e;
+        if (valid) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(ev + i);
+            const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+            e.key = ((unsigned long long)lo.y << 32) | lo.x;
+            e.sv = ((unsigned long long)lo.w << 32) | lo.z;
+            e.a0 = hi.x; e.a1 = hi.y; e.off_cat = hi.z;
+        } else {
+            e.key = EMPTY64 - 2 - (unsigned)lane; e.sv = EMPTY64; e.a0 = 0xFFFFFFFFu; e.a1 = 0u; e.off_cat = 0u;
+        }
+        const uint32_t cat = (e.off_cat >> 16) & 3u;
+        const int cls = (int)((e.off_cat >> 18) & 3u);
+        const unsigned grp = __match_any_sync(0xFFFFFFFFu, e.key);
+        const int leader = __ffs(grp) - 1;
+        uint64_t slot = t.cap_mask + 1;
+        uint32_t drow = DENSE_NONE;
+        unsigned long long T = 0ull;
+        if (lane == leader && valid) {
+            if (MODE == MODE_PASS2) {
+                slot = junction_find(t, e.key);
+                if (slot <= t.cap_mask) T = *((volatile unsigned long long *)&t.stat[slot].T);
+            } else {
+                slot = junction_find_or_insert(t, e.key, &drow);
+            }
+            if (MODE != MODE_PASS1 && slot <= t.cap_mask && drow == DENSE_NONE)
+                drow = *((volatile uint32_t *)&t.dense_idx[slot]);
+        }
+        slot = __shfl_sync(grp, slot, leader);
+        bool counted = valid && slot <= t.cap_mask;
+        if (MODE == MODE_PASS2) {
+            T = __shfl_sync(grp, T, leader);
+            counted = counted && T != EMPTY64 && e.sv >= T; /* earlier events are dropped (SURVEY.md 8a A6) */
+        }
+        if (MODE != MODE_PASS2 && counted) stat_first(&t.stat[slot], cls, e.sv);
+        if (MODE != MODE_PASS1) {
+            drow = __shfl_sync(grp, drow, leader);
+            const unsigned c0 = __ballot_sync(0xFFFFFFFFu, counted && cat == 0u) & grp;
+            const unsigned c1 = __ballot_sync(0xFFFFFFFFu, counted && cat == 1u) & grp;
+            const unsigned c2 = __ballot_sync(0xFFFFFFFFu, counted && cat == 2u) & grp;
+            const uint32_t a0 = __reduce_min_sync(grp, counted ? e.a0 : 0xFFFFFFFFu);
+            const uint32_t a1 = __reduce_max_sync(grp, counted ? e.a1 : 0u);
+            if (lane == leader && (c0 | c1 | c2)) {
+                JStat *s = &t.stat[slot];
+                if (c0) atomicAdd(&s->cnt[0], (unsigned long long)__popc(c0));
+                if (c1) atomicAdd(&s->cnt[1], (unsigned long long)__popc(c1));
+                if (c2) atomicAdd(&s->cnt[2], (unsigned long long)__popc(c2));
+                if (a0 < *((volatile uint32_t *)&s->a0)) atomicMin(&s->a0, a0);
+                if (a1 > *((volatile uint32_t *)&s->a1)) atomicMax(&s->a1, a1);
+            }
+            if (counted) {
+                const uint32_t off = e.off_cat & 0xFFFFu;
+                if (off < DENSE_W && drow != DENSE_NONE) atomicAdd(&t.dense[(uint64_t)drow * DENSE_W + off], 1u);
+                else inserts += hist_add_hash(t, slot, off, 1u);
+            }
+        }
+    }
+    unsigned long long ins = warp_sum((unsigned long long)inserts);
+    if (lane == 0 && ins) atomicAdd(t.n_hist, ins);
+}
+
+void launch_fold(int mode, const Tables &t, const Event *ev, const unsigned long long *n_events_ptr, int sm_count,
+                 cudaStream_t st) {
+    const int blocks = sm_count * 8;
     switch (mode) {
-        case MODE_SINGLE: k_extract<MODE_SINGLE><<<blocks, EX_THREADS, 0, st>>>(b, p, t); break;
-        case MODE_PASS1: k_extract<MODE_PASS1><<<blocks, EX_THREADS, 0, st>>>(b, p, t); break;
-        default: k_extract<MODE_PASS2><<<blocks, EX_THREADS, 0, st>>>(b, p, t); break;
+        case MODE_SINGLE: k_fold<MODE_SINGLE><<<blocks, 256, 0, st>>>(t, ev, n_events_ptr); break;
+        case MODE_PASS1: k_fold<MODE_PASS1><<<blocks, 256, 0, st>>>(t, ev, n_events_ptr); break;
+        default: k_fold<MODE_PASS2><<<blocks, 256, 0, st>>>(t, ev, n_events_ptr); break;
     }
 }
 

@@ -80,6 +80,19 @@ struct alignas(16) HEntry {
     uint32_t pad;
 };
 
+/* one junction event between K1 (extract) and K2 (fold): 32 bytes */
+#if defined(__CUDACC__)
+struct __align__(16) Event {
+#else
+struct alignas(16) Event {
+#endif
+    unsigned long long key;
+    unsigned long long sv;
+    uint32_t a0, a1;  /* anchor_start, anchor_end */
+    uint32_t off_cat; /* uint16 read offset | read category << 16 | strand class << 18 */
+    uint32_t pad;
+};
+
 struct KeyLayout {
     int len_bits;   /* L */
     int start_shift; /* = L */
@@ -125,8 +138,9 @@ struct Tables {
 #if defined(__CUDACC__)
 static const uint32_t MAX_PROBE = 1u << 16;
 
-/* find the slot of `key`, inserting it if absent; returns cap_mask + 1 on overflow */
-__device__ __forceinline__ uint64_t junction_find_or_insert(const Tables &t, uint64_t key) {
+/* find the slot of `key`, inserting it if absent; returns cap_mask + 1 on overflow.  When this call creates the
+ * junction, *new_row receives its dense offset row (if the pool still had one). */
+__device__ __forceinline__ uint64_t junction_find_or_insert(const Tables &t, uint64_t key, uint32_t *new_row = nullptr) {
     uint64_t h = mix64(key) & t.cap_mask;
     for (uint32_t probe = 0; probe < MAX_PROBE; ++probe) {
         unsigned long long k = *((volatile unsigned long long *)&t.keys[h]);
@@ -135,7 +149,10 @@ __device__ __forceinline__ uint64_t junction_find_or_insert(const Tables &t, uin
             unsigned long long old = atomicCAS(&t.keys[h], EMPTY64, (unsigned long long)key);
             if (old == EMPTY64) {
                 const unsigned long long id = atomicAdd(t.n_keys, 1ull);
-                if (id < t.dense_rows) atomicExch(&t.dense_idx[h], (uint32_t)id);
+                if (id < t.dense_rows) {
+                    atomicExch(&t.dense_idx[h], (uint32_t)id);
+                    if (new_row) *new_row = (uint32_t)id;
+                }
                 return h;
             }
             if (old == key) return h;
