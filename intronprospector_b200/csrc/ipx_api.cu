@@ -112,7 +112,9 @@ struct ipx_handle {
 
     /* staging for host batches */
     DeviceBuf s_tid, s_pos, s_flag, s_nh, s_xs, s_off, s_cig;
-    DeviceBuf ev_buf; /* junction events of the batch in flight (K1 -> K2) */
+    DeviceBuf ev_buf;   /* junction events of the batch in flight (K1 -> K2), one region per tile */
+    DeviceBuf tile_cnt; /* events per tile */
+    uint64_t seq_hi = 0; /* one past the largest record stream index pushed so far */
 
     /* finalize */
     FinalizeWork fw;
@@ -203,11 +205,14 @@ int alloc_tables(ipx_handle *h) {
     CU(h, cudaMalloc(&t.keys, cap * sizeof(unsigned long long)));
     CU(h, cudaMalloc(&t.stat, cap * sizeof(JStat)));
     CU(h, cudaMalloc(&t.hist, hcap * sizeof(HEntry)));
-    /* dense offset rows: one per junction up to a quarter of the slots (the table is kept at most half full) */
-    t.dense_rows = std::min<uint64_t>(cap / 4, 1ull << 21);
-    CU(h, cudaMalloc(&t.dense_idx, cap * sizeof(uint32_t)));
-    CU(h, cudaMalloc(&t.dense, t.dense_rows * DENSE_W * sizeof(uint32_t)));
-    CU(h, cudaMemsetAsync(t.dense, 0, t.dense_rows * DENSE_W * sizeof(uint32_t), h->stream));
+    CU(h, cudaMalloc(&t.slot_list, cap * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&t.hist_list, hcap * sizeof(uint32_t)));
+    /* dense offset rows: 1 KB per slot, so up to 16 GB of the 180 GB; beyond that every offset goes to the hash */
+    t.dense = nullptr;
+    if (cap <= (1ull << 24) && !getenv("IPX_NO_DENSE")) {
+        CU(h, cudaMalloc(&t.dense, cap * DENSE_W * sizeof(uint32_t)));
+        CU(h, cudaMemsetAsync(t.dense, 0, cap * DENSE_W * sizeof(uint32_t), h->stream));
+    }
     CU(h, cudaMalloc(&h->d_counters, 8 * 128));
     CU(h, cudaMemsetAsync(h->d_counters, 0, 8 * 128, h->stream));
     t.cap_mask = cap - 1;
@@ -304,16 +309,20 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
     /* event buffer for the worst case: every emitted candidate consumes one N op and a following aligned op */
     const uint64_t ev_bound = n_cigar / 2 + 1;
     CU(h, h->ev_buf.reserve(ev_bound * sizeof(Event), h->stream));
-    unsigned long long *ev_count = h->d_counters + 96;
-    CU(h, cudaMemsetAsync(ev_count, 0, sizeof(unsigned long long), h->stream));
+    const uint64_t n_tiles = tiles_of(b.n);
+    CU(h, h->tile_cnt.reserve((n_tiles + 1) * sizeof(uint32_t), h->stream));
+    uint32_t *tile_count = (uint32_t *)h->tile_cnt.p;
+    const Event *events = (const Event *)h->ev_buf.p;
     {
-        Span s(h, &h->tm_extract, 1);
-        launch_extract(b, h->xp, h->tab, (Event *)h->ev_buf.p, ev_count, h->sm_count, h->stream);
+        Span s(h, &h->tm_extract, 0);
+        int launched = 0;
+        CU(h, launch_extract(b, n_cigar, h->xp, h->tab, (Event *)h->ev_buf.p, tile_count, h->sm_count, h->stream, &launched));
+        h->tm_extract.launches += (uint64_t)launched;
     }
     if (two_pass(h)) {
         {
             Span s(h, &h->tm_aggregate, 1);
-            launch_fold(MODE_PASS1, h->tab, (const Event *)h->ev_buf.p, ev_count, h->sm_count, h->stream);
+            launch_fold(MODE_PASS1, h->tab, events, b.cigar_off, tile_count, n_tiles, h->sm_count, h->stream);
         }
         {
             Span s(h, &h->tm_motif, 1);
@@ -321,14 +330,15 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
         }
         {
             Span s(h, &h->tm_aggregate, 1);
-            launch_fold(MODE_PASS2, h->tab, (const Event *)h->ev_buf.p, ev_count, h->sm_count, h->stream);
+            launch_fold(MODE_PASS2, h->tab, events, b.cigar_off, tile_count, n_tiles, h->sm_count, h->stream);
         }
     } else {
         Span s(h, &h->tm_aggregate, 1);
-        launch_fold(MODE_SINGLE, h->tab, (const Event *)h->ev_buf.p, ev_count, h->sm_count, h->stream);
+        launch_fold(MODE_SINGLE, h->tab, events, b.cigar_off, tile_count, n_tiles, h->sm_count, h->stream);
     }
     CU(h, cudaGetLastError());
     h->totals.records += b.n;
+    h->seq_hi = std::max<uint64_t>(h->seq_hi, b.seq_base + b.n);
     h->dirty = true;
     return IPX_OK;
 }
@@ -395,11 +405,11 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     cudaStreamSynchronize(h->stream);
     drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
     if (h->finalized) free_device_table(h->dt, h->stream);
-    cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.hist); cudaFree(h->tab.dense_idx); cudaFree(h->tab.dense);
+    cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.hist); cudaFree(h->tab.slot_list); cudaFree(h->tab.hist_list); cudaFree(h->tab.dense);
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq);
     free_genome(h);
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();
-    h->s_off.release(); h->s_cig.release(); h->ev_buf.release();
+    h->s_off.release(); h->s_cig.release(); h->ev_buf.release(); h->tile_cnt.release();
     cudaFree(h->fw.cub_tmp); cudaFree(h->fw.d_count); cudaFree(h->fw.slot_rank);
     cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -491,7 +501,7 @@ extern "C" int ipx_finalize_device(ipx_handle *h) {
     {
         Span s(h, &h->tm_finalize, 0);
         int own = 0;
-        cudaError_t e = finalize_tables(h->tab, genome_view(h), h->d_name_rank, (int32_t)h->targets.size(), h->fw, h->dt,
+        cudaError_t e = finalize_tables(h->tab, genome_view(h), h->d_name_rank, (int32_t)h->targets.size(), h->seq_hi, h->fw, h->dt,
                                         h->keep_export, h->stream, &own);
         h->tm_finalize.launches += (uint64_t)own;
         if (e != cudaSuccess)
@@ -638,7 +648,7 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     /* clear(), junctions.hh:240-245 */
     free_device_table(h->dt, h->stream);
     h->finalized = false;
-    launch_init_tables(h->tab, st);
+    launch_clear_tables(h->tab, st);
     h->dirty = false;
     *out = &ht->t;
     return IPX_OK;
@@ -653,8 +663,8 @@ extern "C" int ipx_clear(ipx_handle *h) {
         h->finalized = false;
     }
     if (h->tables_ready) {
-        Span s(h, &h->tm_finalize, 1);
-        launch_init_tables(h->tab, h->stream);
+        Span s(h, &h->tm_finalize, 2);
+        launch_clear_tables(h->tab, h->stream);
         CU(h, cudaGetLastError());
     }
     h->dirty = false;
@@ -805,7 +815,7 @@ extern "C" int ipx_partial_export(ipx_handle *h, void *dev_junction_rows, void *
     free_device_table(h->dt, h->stream);
     h->finalized = false;
     h->keep_export = false;
-    launch_init_tables(h->tab, h->stream);
+    launch_clear_tables(h->tab, h->stream);
     CU(h, cudaGetLastError());
     return IPX_OK;
 }

@@ -65,12 +65,22 @@ struct HistRow {
 
 enum ExtractMode { MODE_SINGLE = 0, MODE_PASS1 = 1, MODE_PASS2 = 2 };
 
+/* K1 works on tiles of EX_TILE consecutive records.  The events of tile i go to a private region of the event
+ * buffer starting at event index ceil(cigar_off[i * EX_TILE] / 2): a read needs at least one N and one following
+ * aligned operation per emitted junction, so a tile cannot emit more events than half its CIGAR words and the
+ * regions of consecutive tiles never overlap.  tile_count[i] is the number of events tile i wrote.  No global
+ * atomic is involved; the buffer holds n_cigar / 2 + 1 events. */
+static const int EX_TILE = 1024;
+inline uint64_t tiles_of(uint64_t n_records) { return (n_records + EX_TILE - 1) / EX_TILE; }
+
 /* kernels' launchers; all asynchronous on `st` */
-void launch_init_tables(const Tables &t, cudaStream_t st);
-void launch_extract(const BatchView &b, const ExtractParams &p, const Tables &t, Event *out, unsigned long long *out_count,
-                    int sm_count, cudaStream_t st);
-void launch_fold(int mode, const Tables &t, const Event *ev, const unsigned long long *n_events_ptr, int sm_count,
-                 cudaStream_t st);
+void launch_init_tables(const Tables &t, cudaStream_t st);  /* whole tables, once after allocation */
+void launch_clear_tables(const Tables &t, cudaStream_t st); /* only what the lists say is in use */
+/* returns a CUDA error (attribute set-up of the pipelined kernel can fail), launches counted in *launches */
+cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractParams &p, const Tables &t, Event *out,
+                           uint32_t *tile_count, int sm_count, cudaStream_t st, int *launches);
+void launch_fold(int mode, const Tables &t, const Event *ev, const uint32_t *cigar_off, const uint32_t *tile_count,
+                 uint64_t n_tiles, int sm_count, cudaStream_t st);
 void launch_resolve_T(const Tables &t, const GenomeView &g, cudaStream_t st);
 void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh,
                         cudaStream_t st);
@@ -79,15 +89,15 @@ void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, con
 struct FinalizeWork {
     void *cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
-    unsigned long long *d_count = nullptr; /* [4] */
-    uint32_t *slot_rank = nullptr;         /* [cap] key-order rank of each slot, 0xFFFFFFFF = not a junction */
+    unsigned long long *d_count = nullptr; /* [4]: 0 = junctions, 1 = histogram runs */
+    uint32_t *slot_rank = nullptr;         /* [cap] key-order rank of each slot (only filled when the offset hash is in use) */
     uint64_t slot_rank_cap = 0;
 };
 
 /* key-order sort, sjN ranking, histogram ordering, gather; synchronises on the counts it needs.
  * `name_rank[tid]` orders targets like std::string::operator< on their names. Returns cudaError_t. */
 cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, int32_t n_targets,
-                            FinalizeWork &w, DeviceTable &out, bool keep_export_columns, cudaStream_t st,
+                            uint64_t seq_hi, FinalizeWork &w, DeviceTable &out, bool keep_export_columns, cudaStream_t st,
                             int *own_launches);
 void free_device_table(DeviceTable &t, cudaStream_t st);
 

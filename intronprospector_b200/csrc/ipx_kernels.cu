@@ -1,15 +1,22 @@
 /* ipx_kernels.cu -- sm_100a kernels of the junction-extraction path.
  *
- *  k_extract<MODE>   K1+K2 fused: one thread walks one alignment's CIGAR (ipx_walk.cuh) and folds every
- *                    junction event straight into the L2-resident junction / offset tables, so events
- *                    never travel through HBM.  HBM traffic is the record columns and the live CIGAR
- *                    words, read once, coalesced.
+ *  k_extract_tma     K1, the hot kernel: persistent blocks stream tiles of EX_TILE consecutive records through a
+ *                    3-stage shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier, one producer
+ *                    warp), so every record column and CIGAR word is read from HBM exactly once, coalesced, with
+ *                    the latency hidden behind the previous tiles' work.  Eight consumer warps (a) classify the
+ *                    tile's records and compact the live ones (process_alignment's skip test) into two lists --
+ *                    CIGARs of at most three operations, which can only be "aligned, N, aligned", and longer ones
+ *                    -- then (b) walk the listed records with full warps (ipx_walk.cuh) and write each junction
+ *                    event straight into the tile's private region of the event buffer.
+ *  k_extract_simple  K1 for what the pipeline does not take: the last partial tile, unaligned columns, long reads.
+ *  k_fold<MODE>      K2: warp-grouped keyed aggregation of the events into the junction / offset tables
  *                      MODE_SINGLE  no canon filter: insert + first-seen + counts + anchors + offsets
  *                      MODE_PASS1   canon filter:    insert + first-seen per strand class only
  *                      MODE_PASS2   canon filter:    count events at or after the creation threshold T
  *  k_resolve_T       K3: donor/acceptor gather from the HBM genome, per junction, and the choice of the
  *                    creating event T = first event whose (key, strand class) passes the filter
- *  finalize_tables   compaction, key-order sort, sjN ranking, offset-histogram ordering, output gather
+ *  finalize_tables   key-order sort, sjN ranking, offset-histogram ordering, output gather -- all over the
+ *                    list of slots in use, never over the table's capacity
  *  k_import_*        fold partial tables received from other GPUs (multi-GPU exchange)
  *
  * Reference semantics: SURVEY.md section 8(a) A1-A8 (junctions_extractor.cc:49-95,124-319,322-530).
@@ -17,20 +24,19 @@
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ipx_engine.h"
 
 namespace ipx {
 
 /* ------------------------------------------------------------------ table initialisation */
-/* zero the dense rows in use; runs before k_init_tables resets n_keys */
-__global__ void k_clear_dense(Tables t) {
-    unsigned long long rows = *t.n_keys;
-    if (rows > t.dense_rows) rows = t.dense_rows;
-    const uint64_t n4 = rows * (DENSE_W / 4);
-    uint4 *p = reinterpret_cast<uint4 *>(t.dense);
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) p[i] = make_uint4(0u, 0u, 0u, 0u);
+__device__ __forceinline__ void reset_stat(JStat *s) {
+    uint4 *p = reinterpret_cast<uint4 *>(s);
+    p[0] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu); /* first[0], first[1] */
+    p[1] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu); /* first[2], T */
+    p[2] = make_uint4(0u, 0u, 0u, 0u);                                     /* cnt[0], cnt[1] */
+    p[3] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);                            /* cnt[2], a0 = none, a1 = 0 */
 }
 
 __global__ void k_init_tables(Tables t) {
@@ -38,48 +44,77 @@ __global__ void k_init_tables(Tables t) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
         t.keys[i] = EMPTY64;
-        t.dense_idx[i] = DENSE_NONE;
-        JStat s;
-        s.first[0] = s.first[1] = s.first[2] = EMPTY64;
-        s.T = EMPTY64;
-        s.cnt[0] = s.cnt[1] = s.cnt[2] = 0ull;
-        s.a0 = 0xFFFFFFFFu;
-        s.a1 = 0u;
-        t.stat[i] = s;
+        reset_stat(&t.stat[i]);
     }
     HEntry e;
     e.key = EMPTY64;
     e.cnt = 0u;
     e.pad = 0u;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hcap; i += stride) t.hist[i] = e;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        *t.n_keys = 0ull;
-        *t.n_hist = 0ull;
-        *t.err_sv = EMPTY64;
-        *t.overflow = 0u;
+}
+
+__global__ void k_reset_counters(Tables t) {
+    *t.n_keys = 0ull;
+    *t.n_hist = 0ull;
+    *t.err_sv = EMPTY64;
+    *t.overflow = 0u;
+}
+
+/* clear(): undo exactly what the lists say was touched -- a warp per junction slot (key, 64-byte record, 1 KB
+ * offset row), a thread per offset-table entry */
+__global__ void __launch_bounds__(256) k_clear_tables(Tables t) {
+    const unsigned long long nk = *t.n_keys, nh = *t.n_hist;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = warp0; i < nk; i += n_warps) {
+        const uint64_t slot = t.slot_list[i];
+        if (lane == 0) {
+            t.keys[slot] = EMPTY64;
+            reset_stat(&t.stat[slot]);
+        }
+        if (t.dense) {
+            uint4 *row = reinterpret_cast<uint4 *>(t.dense + slot * DENSE_W);
+            row[lane] = make_uint4(0u, 0u, 0u, 0u);
+            row[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
+    HEntry e;
+    e.key = EMPTY64;
+    e.cnt = 0u;
+    e.pad = 0u;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nh; i += stride) t.hist[t.hist_list[i]] = e;
 }
 
 void launch_init_tables(const Tables &t, cudaStream_t st) {
-    k_clear_dense<<<148 * 8, 256, 0, st>>>(t);
     k_init_tables<<<148 * 8, 256, 0, st>>>(t);
+    k_reset_counters<<<1, 1, 0, st>>>(t);
+}
+
+void launch_clear_tables(const Tables &t, cudaStream_t st) {
+    k_clear_tables<<<148 * 4, 256, 0, st>>>(t);
+    k_reset_counters<<<1, 1, 0, st>>>(t);
 }
 
 /* ------------------------------------------------------------------ K1: extract */
-static const int EX_THREADS = 256;
-static const int EX_RPT = 4;                       /* records per thread per tile */
-static const int EX_TILE = EX_THREADS * EX_RPT;    /* records per tile */
-static const int EX_EVCAP = 1024;                  /* staged events per tile (32 KB); more go out one by one */
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+    return v;
+}
 
-/* K1 sink: junction_qc, then stage the event in shared memory (or, past the staging capacity, write it out
- * through a per-event reservation) */
+/* first event index of a tile's region in the event buffer (see ipx_engine.h) */
+__host__ __device__ __forceinline__ uint64_t tile_event_base(uint32_t first_cigar_word) {
+    return ((uint64_t)first_cigar_word + 1ull) >> 1;
+}
+
+/* K1 sink: junction_qc, then write the event into the next free slot of the tile's region */
 struct EventSink {
     const Tables &t;
     const ExtractParams &p;
-    Event *stage;
-    uint32_t *stage_count;
-    Event *out;
-    unsigned long long *out_count;
+    Event *region;         /* the tile's region of the event buffer */
+    uint32_t *region_fill; /* shared-memory counter of the events written to it */
     int32_t tid;
     int64_t pos;
     uint64_t record_seq;
@@ -96,72 +131,48 @@ struct EventSink {
             atomicExch(t.overflow, 3u); /* outside what a BAM position can hold */
             return;
         }
-        Event e;
-        e.key = make_key(t.kl, tid, c.intron_start, c.intron_end);
-        e.sv = make_sv(record_seq, c.ordinal, strand);
-        e.a0 = (uint32_t)c.anchor_start;
-        e.a1 = (uint32_t)c.anchor_end;
-        e.off_cat = ((uint32_t)(c.intron_start - pos) & 0xFFFFu) | (cat << 16) | ((uint32_t)cls << 18);
-        e.pad = 0u;
-        const uint32_t idx = atomicAdd(stage_count, 1u);
-        if (idx < (uint32_t)EX_EVCAP) stage[idx] = e;
-        else out[atomicAdd(out_count, 1ull)] = e; /* a tile of very long reads: rare, still exact */
+        const unsigned long long key = make_key(t.kl, tid, c.intron_start, c.intron_end);
+        const unsigned long long sv = make_sv(record_seq, c.ordinal, strand);
+        const uint32_t off_cat = ((uint32_t)(c.intron_start - pos) & 0xFFFFu) | (cat << 16) | ((uint32_t)cls << 18);
+        const uint32_t idx = atomicAdd(region_fill, 1u);
+        /* one 32-byte event = one DRAM sector: two 16-byte stores from the emitting lane */
+        uint4 *dst = reinterpret_cast<uint4 *>(region + idx);
+        dst[0] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)sv, (uint32_t)(sv >> 32));
+        dst[1] = make_uint4((uint32_t)c.anchor_start, (uint32_t)c.anchor_end, off_cat, 0u);
     }
 };
 
-__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
-    return v;
+__device__ __forceinline__ EventSink make_sink(const Tables &t, const ExtractParams &p, Event *region, uint32_t *region_fill,
+                                               int32_t tid, int64_t pos, uint64_t seq, uint32_t flag, uint32_t nh, uint32_t xs) {
+    const char strand = read_strand(p.strandness, flag, xs);
+    return EventSink{t, p, region, region_fill, tid, pos, seq, read_category(flag, nh), strand, strand_class(strand),
+                     read_may_emit(p, flag, nh), 0u};
 }
 
-/* K1.  One block works through tiles of EX_TILE consecutive records.  Every thread loads the fixed-width columns of
- * its EX_RPT records up front (coalesced, all loads in flight together), walks the CIGAR of the live ones
- * (ipx_walk.cuh) and stages their junction events in shared memory; the tile then reserves a contiguous range of
- * the event buffer with ONE atomic and copies its events out with coalesced 16-byte stores.  The event buffer is
- * sized by the host for the worst case (one event per two CIGAR words), so nothing can be lost. */
-__global__ void __launch_bounds__(EX_THREADS) k_extract(BatchView b, ExtractParams p, Tables t, Event *out,
-                                                        unsigned long long *out_count) {
-    __shared__ Event stage[EX_EVCAP];
-    __shared__ uint32_t stage_count;
-    __shared__ unsigned long long tile_base;
+/* ---- generic K1: one block per tile, records and CIGAR words straight from global memory ---- */
+static const int EXS_THREADS = 256;
+
+__global__ void __launch_bounds__(EXS_THREADS) k_extract_simple(BatchView b, ExtractParams p, Tables t, Event *out,
+                                                                uint32_t *tile_count, uint64_t first_tile, uint64_t n_tiles) {
+    __shared__ uint32_t region_fill;
     unsigned long long live_words = 0ull, events = 0ull;
-    const uint64_t n_tiles = (b.n + EX_TILE - 1) / EX_TILE;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (threadIdx.x == 0) stage_count = 0u;
+    for (uint64_t tile = first_tile + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (threadIdx.x == 0) region_fill = 0u;
         __syncthreads();
-        const uint64_t base = tile * EX_TILE + threadIdx.x;
-        uint32_t c0[EX_RPT], c1[EX_RPT], flag[EX_RPT];
-        int32_t tid[EX_RPT];
-#pragma unroll
-        for (int j = 0; j < EX_RPT; ++j) {
-            const uint64_t r = base + (uint64_t)j * EX_THREADS;
-            c0[j] = c1[j] = 0u;
-            flag[j] = 0u;
-            tid[j] = -1;
-            if (r < b.n) {
-                c0[j] = __ldg(&b.cigar_off[r]);
-                c1[j] = __ldg(&b.cigar_off[r + 1]);
-                tid[j] = __ldg(&b.tid[r]);
-                flag[j] = __ldg(&b.flag[r]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < EX_RPT; ++j) {
-            const uint32_t n_cigar = c1[j] - c0[j];
-            if (!record_is_live(n_cigar, tid[j], flag[j])) continue;
-            const uint64_t r = base + (uint64_t)j * EX_THREADS;
+        const uint64_t r0 = tile * EX_TILE;
+        Event *region = out + tile_event_base(__ldg(&b.cigar_off[r0]));
+        for (uint64_t r = r0 + threadIdx.x; r < r0 + EX_TILE && r < b.n; r += EXS_THREADS) {
+            const uint32_t c0 = __ldg(&b.cigar_off[r]), n_cigar = __ldg(&b.cigar_off[r + 1]) - c0;
+            const int32_t tid = __ldg(&b.tid[r]);
+            const uint32_t flag = __ldg(&b.flag[r]);
+            if (!record_is_live(n_cigar, tid, flag)) continue;
             live_words += n_cigar;
             const int64_t pos = __ldg(&b.pos[r]);
-            const uint32_t nh = __ldg(&b.nh[r]);
-            const uint32_t xs = __ldg(&b.xs[r]);
-            const char strand = read_strand(p.strandness, flag[j], xs);
-            EventSink sink{t, p, stage, &stage_count, out, out_count, tid[j], pos, b.seq_base + r,
-                           read_category(flag[j], nh), strand, strand_class(strand), read_may_emit(p, flag[j], nh), 0u};
+            EventSink sink = make_sink(t, p, region, &region_fill, tid, pos, b.seq_base + r, flag, __ldg(&b.nh[r]), __ldg(&b.xs[r]));
             WalkState w;
             w.init(pos);
             uint32_t bad = 0u;
-            const uint32_t *cig = b.cigar + c0[j];
+            const uint32_t *cig = b.cigar + c0;
             for (uint32_t k = 0; k < n_cigar; ++k) {
                 bad = walk_op(w, __ldg(&cig[k]), p.max_anchor_indel_size, sink);
                 if (bad) break;
@@ -175,18 +186,9 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(BatchView b, ExtractPara
             events += sink.n_events;
         }
         __syncthreads();
-        const uint32_t n_ev = stage_count < (uint32_t)EX_EVCAP ? stage_count : (uint32_t)EX_EVCAP;
-        if (threadIdx.x == 0 && n_ev) tile_base = atomicAdd(out_count, (unsigned long long)n_ev);
-        __syncthreads();
-        if (n_ev) {
-            /* 32-byte events as two 16-byte halves: consecutive threads write consecutive 16-byte words */
-            const uint4 *src = reinterpret_cast<const uint4 *>(stage);
-            uint4 *dst = reinterpret_cast<uint4 *>(out + tile_base);
-            for (uint32_t i = threadIdx.x; i < n_ev * 2u; i += EX_THREADS) dst[i] = src[i];
-        }
+        if (threadIdx.x == 0) tile_count[tile] = region_fill;
         __syncthreads();
     }
-    /* one atomic per warp for the unit counters */
     live_words = warp_sum(live_words);
     events = warp_sum(events);
     if ((threadIdx.x & 31) == 0) {
@@ -195,125 +197,484 @@ __global__ void __launch_bounds__(EX_THREADS) k_extract(BatchView b, ExtractPara
     }
 }
 
-void launch_extract(const BatchView &b, const ExtractParams &p, const Tables &t, Event *out, unsigned long long *out_count,
-                    int sm_count, cudaStream_t st) {
-    if (b.n == 0) return;
-    const uint64_t n_tiles = (b.n + EX_TILE - 1) / EX_TILE;
-    const uint64_t max_blocks = (uint64_t)sm_count * 6; /* 33 KB of shared memory per block */
-    const int blocks = (int)(n_tiles < max_blocks ? n_tiles : max_blocks);
-    k_extract<<<blocks, EX_THREADS, 0, st>>>(b, p, t, out, out_count);
+/* ---- pipelined K1 ---- */
+/* Warp roles of one block (no block-wide barrier after start-up; everything is handed over through mbarriers):
+ *   producer   (1 warp, one lane)  TMA bulk copies of the next tile's columns and CIGAR words into a free stage;
+ *                                  when a stage comes back it publishes the tile's event count and resets the stage
+ *   classifier (2 warps)           process_alignment's skip test for every record of the tile and compaction of the
+ *                                  live ones into the stage's two lists
+ *   walker     (8 warps)           take 32 listed records at a time from the stage's dispensers and walk them; a
+ *                                  walker that finds a tile's dispensers empty moves on to the next tile at once,
+ *                                  so walkers spread over the tiles in flight and never wait for each other */
+static const int EX_STAGES = 4;
+static const int EX_WALKER_WARPS = 8;
+static const int EX_CLASSIFIER_WARPS = 2;
+static const int EX_THREADS = (EX_WALKER_WARPS + EX_CLASSIFIER_WARPS + 1) * 32;
+static const int EX_CIG_CAP = 2048; /* staged CIGAR words per tile (average short-read tile: ~1500); words beyond are
+                                       read from global memory */
+
+struct __align__(128) ExStage {
+    /* filled by the TMA bulk copies */
+    uint32_t off[EX_TILE + 4]; /* cigar_off of the tile's records; [EX_TILE] is stored by the producer */
+    int32_t tid[EX_TILE];
+    int32_t pos[EX_TILE];
+    uint32_t cig[EX_CIG_CAP];
+    uint16_t flag[EX_TILE];
+    uint8_t nh[EX_TILE];
+    uint8_t xs[EX_TILE];
+    /* written by the block itself */
+    uint16_t list[EX_TILE]; /* live records: short CIGARs (<= 3 operations) from the front, longer ones from the back */
+    uint32_t n_lists;       /* number of short | number of long << 16 */
+    uint32_t next_short, next_long; /* chunk dispensers of the walkers */
+    uint32_t region_fill;   /* events written to the tile's region */
+    uint32_t tile;          /* tile index */
+    uint32_t a0, a_end;     /* staged CIGAR words are [a0, a_end) of the batch's CIGAR column */
+    uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+/* wait for the phase with the given parity; the hint lets the hardware park the thread instead of spinning */
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)
+            : "memory");
+    } while (!done);
+}
+/* TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP) */
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+/* a CIGAR word of the batch: from the stage when it was staged, else from global memory */
+__device__ __forceinline__ uint32_t cigar_word(const ExStage &S, const uint32_t *cigar, uint32_t gi) {
+    return gi < S.a_end ? S.cig[gi - S.a0] : __ldg(&cigar[gi]);
+}
+
+/* walk one listed record with the full automaton */
+__device__ __forceinline__ void walk_record(const BatchView &b, const ExtractParams &p, const Tables &t, ExStage &S, Event *region,
+                                            uint32_t rl, unsigned long long &events) {
+    const uint32_t c0 = S.off[rl], n_cigar = S.off[rl + 1] - c0;
+    const int64_t pos = S.pos[rl];
+    const uint64_t seq = b.seq_base + (uint64_t)S.tile * EX_TILE + rl;
+    EventSink sink = make_sink(t, p, region, &S.region_fill, S.tid[rl], pos, seq, S.flag[rl], S.nh[rl], S.xs[rl]);
+    WalkState w;
+    w.init(pos);
+    uint32_t bad = 0u;
+    for (uint32_t k = 0; k < n_cigar; ++k) {
+        bad = walk_op(w, cigar_word(S, b.cigar, c0 + k), p.max_anchor_indel_size, sink);
+        if (bad) break;
+    }
+    if (bad) {
+        atomicMin(t.err_sv, make_err_cigar(seq, bad & 15u));
+    } else {
+        walk_finish(w, sink);
+    }
+    events += sink.n_events;
+}
+
+__global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint32_t n_cigar_words, ExtractParams p, Tables t,
+                                                               Event *out, uint32_t *tile_count, uint32_t n_full_tiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ExStage *stages = reinterpret_cast<ExStage *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + EX_STAGES * sizeof(ExStage)); /* TMA bytes have landed */
+    uint64_t *classified = full + EX_STAGES;                                               /* lists are complete */
+    uint64_t *empty = classified + EX_STAGES;                                              /* every walker has left */
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < EX_STAGES; ++s) {
+            mbar_init(&full[s], 1u);
+            mbar_init(&classified[s], (uint32_t)EX_CLASSIFIER_WARPS);
+            mbar_init(&empty[s], (uint32_t)EX_WALKER_WARPS);
+            stages[s].n_lists = stages[s].next_short = stages[s].next_long = stages[s].region_fill = 0u;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t first = blockIdx.x, stride = gridDim.x;
+    const uint32_t my_tiles = first < n_full_tiles ? (n_full_tiles - first + stride - 1) / stride : 0u;
+
+    if (warp == EX_WALKER_WARPS + EX_CLASSIFIER_WARPS) {
+        /* ---------------- producer: one lane feeds the ring ---------------- */
+        if (lane != 0) return;
+        uint32_t nc0 = 0u, nc1 = 0u;
+        if (my_tiles) {
+            nc0 = __ldg(&b.cigar_off[(uint64_t)first * EX_TILE]);
+            nc1 = __ldg(&b.cigar_off[(uint64_t)first * EX_TILE + EX_TILE]);
+        }
+        for (uint32_t it = 0; it < my_tiles + EX_STAGES; ++it) {
+            const int s = (int)(it % EX_STAGES);
+            ExStage &S = stages[s];
+            if (it >= (uint32_t)EX_STAGES) {
+                /* the tile that occupied this stage has been left by every walker */
+                mbar_wait(&empty[s], ((it / EX_STAGES) & 1u) ^ 1u);
+                tile_count[S.tile] = S.region_fill;
+                S.n_lists = S.next_short = S.next_long = S.region_fill = 0u;
+            }
+            if (it < my_tiles) {
+                const uint32_t tile = first + it * stride;
+                const uint64_t r0 = (uint64_t)tile * EX_TILE;
+                const uint32_t c0 = nc0, c1 = nc1;
+                if (it + 1 < my_tiles) {
+                    /* boundaries of the next tile: in flight while this one is issued and the stage wait above runs */
+                    nc0 = __ldg(&b.cigar_off[r0 + (uint64_t)stride * EX_TILE]);
+                    nc1 = __ldg(&b.cigar_off[r0 + (uint64_t)stride * EX_TILE + EX_TILE]);
+                }
+                const uint32_t a0 = c0 & ~3u;
+                uint32_t a_end = (c1 + 3u) & ~3u;
+                if (a_end - a0 > (uint32_t)EX_CIG_CAP) a_end = a0 + (uint32_t)EX_CIG_CAP;
+                if (a_end > n_cigar_words) a_end = a0 + ((n_cigar_words - a0) & ~3u);
+                const uint32_t cig_bytes = (a_end - a0) * 4u;
+                S.tile = tile;
+                S.a0 = a0;
+                S.a_end = a_end;
+                S.off[EX_TILE] = c1;
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(EX_TILE * (4 + 4 + 4 + 2 + 1 + 1)) + cig_bytes);
+                bulk_g2s(S.off, b.cigar_off + r0, EX_TILE * 4, &full[s]);
+                bulk_g2s(S.tid, b.tid + r0, EX_TILE * 4, &full[s]);
+                bulk_g2s(S.flag, b.flag + r0, EX_TILE * 2, &full[s]);
+                if (cig_bytes) bulk_g2s(S.cig, b.cigar + a0, cig_bytes, &full[s]);
+                bulk_g2s(S.pos, b.pos + r0, EX_TILE * 4, &full[s]);
+                bulk_g2s(S.nh, b.nh + r0, EX_TILE, &full[s]);
+                bulk_g2s(S.xs, b.xs + r0, EX_TILE, &full[s]);
+            }
+        }
+        return;
+    }
+
+    if (warp >= EX_WALKER_WARPS) {
+        /* ---------------- classifiers: process_alignment's skip test (junctions_extractor.cc:536) + compaction ------- */
+        const int cw = warp - EX_WALKER_WARPS;
+        const int per_warp = EX_TILE / EX_CLASSIFIER_WARPS; /* records of the tile this warp classifies */
+        unsigned long long live_words = 0ull;
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const int s = (int)(it % EX_STAGES);
+            ExStage &S = stages[s];
+            mbar_wait(&full[s], (it / EX_STAGES) & 1u);
+#pragma unroll 1
+            for (int r = 0; r < per_warp; r += 128) {
+                const uint32_t q = (uint32_t)(cw * per_warp + r) / 4u + lane; /* records 4q .. 4q+3 */
+                const uint4 o = reinterpret_cast<const uint4 *>(S.off)[q];
+                const uint32_t o4 = S.off[4 * q + 4];
+                const int4 td = reinterpret_cast<const int4 *>(S.tid)[q];
+                const uint2 f2 = reinterpret_cast<const uint2 *>(S.flag)[q];
+                const uint32_t n[4] = {o.y - o.x, o.z - o.y, o.w - o.z, o4 - o.w};
+                const int32_t tdv[4] = {td.x, td.y, td.z, td.w};
+                const uint32_t fl[4] = {f2.x & 0xFFFFu, f2.x >> 16, f2.y & 0xFFFFu, f2.y >> 16};
+                uint32_t kind[4], mine = 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    kind[j] = 0u;
+                    if (record_is_live(n[j], tdv[j], fl[j])) {
+                        live_words += n[j];
+                        kind[j] = n[j] <= 3u ? 1u : 2u;
+                        mine += n[j] <= 3u ? 1u : 0x10000u;
+                    }
+                }
+                uint32_t incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl += y;
+                }
+                uint32_t base = 0u;
+                if (lane == 31 && incl) base = atomicAdd(&S.n_lists, incl);
+                base = __shfl_sync(0xFFFFFFFFu, base, 31);
+                const uint32_t pre = base + incl - mine;
+                uint32_t ps = pre & 0xFFFFu, pl = pre >> 16;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (kind[j] == 1u) S.list[ps++] = (uint16_t)(4 * q + j);
+                    else if (kind[j] == 2u) S.list[EX_TILE - 1 - (pl++)] = (uint16_t)(4 * q + j);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&classified[s]);
+        }
+        live_words = warp_sum(live_words);
+        if (lane == 0 && live_words) atomicAdd(t.n_live, live_words);
+        return;
+    }
+
+    /* ---------------- walkers ---------------- */
+    unsigned long long events = 0ull;
+    for (uint32_t it = 0; it < my_tiles; ++it) {
+        const int s = (int)(it % EX_STAGES);
+        ExStage &S = stages[s];
+        mbar_wait(&full[s], (it / EX_STAGES) & 1u);       /* the TMA-written columns are visible to this thread */
+        mbar_wait(&classified[s], (it / EX_STAGES) & 1u); /* the lists are complete */
+        const uint32_t n_short = S.n_lists & 0xFFFFu, n_long = S.n_lists >> 16;
+        Event *region = out + tile_event_base(S.off[0]);
+        /* 32 listed records at a time, longest CIGARs first */
+        for (;;) {
+            uint32_t c = 0u;
+            if (lane == 0) c = atomicAdd(&S.next_long, 32u);
+            c = __shfl_sync(0xFFFFFFFFu, c, 0);
+            if (c >= n_long) break;
+            if (c + lane < n_long) walk_record(b, p, t, S, region, S.list[EX_TILE - 1 - (c + lane)], events);
+        }
+        for (;;) {
+            uint32_t c = 0u;
+            if (lane == 0) c = atomicAdd(&S.next_short, 32u);
+            c = __shfl_sync(0xFFFFFFFFu, c, 0);
+            if (c >= n_short) break;
+            if (c + lane < n_short) {
+                /* a CIGAR of two or three operations emits a junction only as "aligned, N, aligned"
+                 * (ReadJunctionExtractor, junctions_extractor.cc:208-254,278-282) */
+                const uint32_t rl = S.list[c + lane];
+                const uint32_t c0 = S.off[rl], n_cigar = S.off[rl + 1] - c0;
+                const uint32_t w0 = cigar_word(S, b.cigar, c0), w1 = cigar_word(S, b.cigar, c0 + 1);
+                const uint32_t w2 = n_cigar == 3u ? cigar_word(S, b.cigar, c0 + 2) : 0u;
+                const uint32_t o0 = w0 & 15u, o1 = w1 & 15u, o2 = w2 & 15u;
+                const uint32_t known = 0x1BFu, aligned = 0x181u; /* MIDNSH=X ; M=X */
+                if (!((known >> o0) & (known >> o1) & (known >> o2) & 1u)) {
+                    walk_record(b, p, t, S, region, rl, events); /* reports the unknown operation exactly */
+                } else if (n_cigar == 3u && o1 == OP_N && ((aligned >> o0) & (aligned >> o2) & 1u)) {
+                    const int64_t pos = S.pos[rl];
+                    const uint64_t seq = b.seq_base + (uint64_t)S.tile * EX_TILE + rl;
+                    EventSink sink = make_sink(t, p, region, &S.region_fill, S.tid[rl], pos, seq, S.flag[rl], S.nh[rl], S.xs[rl]);
+                    Candidate cand;
+                    cand.anchor_start = pos;
+                    cand.intron_start = pos + (int64_t)(w0 >> 4);
+                    cand.intron_end = cand.intron_start + (int64_t)(w1 >> 4);
+                    cand.anchor_end = cand.intron_end + (int64_t)(w2 >> 4);
+                    cand.left_bad = o0 == OP_X ? (w0 >> 4) : 0u;
+                    cand.right_bad = o2 == OP_X ? (w2 >> 4) : 0u;
+                    cand.ordinal = 0u;
+                    sink(cand);
+                    events += sink.n_events;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    events = warp_sum(events);
+    if (lane == 0 && events) atomicAdd(t.n_events, events);
+}
+
+static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
+
+cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractParams &p, const Tables &t, Event *out,
+                           uint32_t *tile_count, int sm_count, cudaStream_t st, int *launches) {
+    if (launches) *launches = 0;
+    if (b.n == 0) return cudaSuccess;
+    const uint64_t n_tiles = tiles_of(b.n), n_full = b.n / EX_TILE;
+    /* the pipelined kernel takes whole tiles of batches whose columns can be bulk-copied and whose reads are short
+     * enough for a tile's CIGAR words to fit its stage */
+    static const bool force_simple = getenv("IPX_K1_SIMPLE") != nullptr;
+    const bool pipelined = !force_simple && n_full > 0 && n_cigar <= 8 * b.n && aligned16(b.tid) && aligned16(b.pos) &&
+                           aligned16(b.flag) && aligned16(b.nh) && aligned16(b.xs) && aligned16(b.cigar_off) && aligned16(b.cigar);
+    uint64_t first_simple = 0;
+    if (pipelined) {
+        const size_t smem = EX_STAGES * sizeof(ExStage) + 3 * EX_STAGES * sizeof(uint64_t);
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(k_extract_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        const uint64_t max_blocks = (uint64_t)sm_count * 2;
+        const int blocks = (int)(n_full < max_blocks ? n_full : max_blocks);
+        k_extract_tma<<<blocks, EX_THREADS, smem, st>>>(b, (uint32_t)n_cigar, p, t, out, tile_count, (uint32_t)n_full);
+        if (launches) (*launches)++;
+        first_simple = n_full;
+    }
+    if (first_simple < n_tiles) {
+        const uint64_t todo = n_tiles - first_simple;
+        const uint64_t max_blocks = (uint64_t)sm_count * 8;
+        const int blocks = (int)(todo < max_blocks ? todo : max_blocks);
+        k_extract_simple<<<blocks, EXS_THREADS, 0, st>>>(b, p, t, out, tile_count, first_simple, n_tiles);
+        if (launches) (*launches)++;
+    }
+    return cudaGetLastError();
 }
 
 /* ------------------------------------------------------------------ K2: keyed aggregation */
-/* fold one event into the tables on its own (import kernels and tests of the slow path) */
+/* fold one event into the tables on its own (import kernels); returns like hist_count */
 template <int MODE>
 __device__ __forceinline__ uint32_t fold_event_direct(const Tables &t, unsigned long long key, unsigned long long sv,
                                                       uint32_t a0, uint32_t a1, uint32_t off, uint32_t cat, int cls) {
     if (MODE == MODE_PASS2) {
         const uint64_t slot = junction_find(t, key);
-        if (slot > t.cap_mask) return 0u;
+        if (slot > t.cap_mask) return HIST_NONE;
         JStat *s = &t.stat[slot];
         const unsigned long long T = *((volatile unsigned long long *)&s->T);
-        if (T == EMPTY64 || sv < T) return 0u; /* before the junction exists: dropped */
+        if (T == EMPTY64 || sv < T) return HIST_NONE; /* before the junction exists: dropped */
         stat_accumulate(s, cat, a0, a1);
         return hist_count(t, slot, off, 1u);
     } else {
         const uint64_t slot = junction_find_or_insert(t, key);
-        if (slot > t.cap_mask) return 0u;
+        if (slot > t.cap_mask) return HIST_NONE;
         JStat *s = &t.stat[slot];
         stat_first(s, cls, sv);
         if (MODE == MODE_SINGLE) {
             stat_accumulate(s, cat, a0, a1);
             return hist_count(t, slot, off, 1u);
         }
-        return 0u;
+        return HIST_NONE;
     }
 }
 
-/* K2.  Every warp takes 32 consecutive events (neighbouring reads, so mostly the same few junctions), groups them
- * by key with match.any, and lets the lowest lane of each group probe the junction table once and apply the
- * group's combined read counts and anchor extremes; each lane then counts its own read offset (one fire-and-forget
- * atomic into the junction's dense offset row, or the offset hash table for large offsets).
- *   MODE_SINGLE  no canon filter: insert + first-seen + counts + anchors + offsets
- *   MODE_PASS1   canon filter:    insert + first-seen per strand class only
- *   MODE_PASS2   canon filter:    count events at or after the creation threshold T */
+__device__ __forceinline__ Event load_event(const Event *ev, uint64_t i, bool valid, int lane) {
+    Event e;
+    if (valid) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(ev + i);
+        const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+        e.key = ((unsigned long long)lo.y << 32) | lo.x;
+        e.sv = ((unsigned long long)lo.w << 32) | lo.z;
+        e.a0 = hi.x; e.a1 = hi.y; e.off_cat = hi.z;
+    } else {
+        /* distinct keys that no real event has (bit 63 is never set in a key), so idle lanes group with nobody */
+        e.key = EMPTY64 - 2 - (unsigned)lane; e.sv = EMPTY64; e.a0 = 0xFFFFFFFFu; e.a1 = 0u; e.off_cat = 0u;
+    }
+    e.pad = 0u;
+    return e;
+}
+
+/* probe for `key` and, in the same round trip, read what the fold wants to know about its junction: the anchor
+ * extremes, the first-seen value of strand class `cls` and the creation threshold.  The values may be stale by the
+ * time they are used; they only ever tighten, so a stale value can cause a redundant atomic, never a missed one. */
+struct Probe {
+    uint64_t slot; /* cap_mask + 1 = absent (lookup) or table full (insert) */
+    uint32_t a0, a1;
+    unsigned long long first, T;
+};
+
+template <bool INSERT>
+__device__ __forceinline__ Probe probe_junction(const Tables &t, unsigned long long key, int cls) {
+    Probe r;
+    uint64_t h = mix64(key) & t.cap_mask;
+    for (uint32_t probe = 0; probe < MAX_PROBE; ++probe) {
+        const JStat *s = &t.stat[h];
+        unsigned long long k = *((volatile unsigned long long *)&t.keys[h]);
+        uint2 a;
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "l"(&s->a0));
+        r.first = *((volatile unsigned long long *)&s->first[cls]);
+        r.T = *((volatile unsigned long long *)&s->T);
+        r.a0 = a.x;
+        r.a1 = a.y;
+        r.slot = h;
+        if (k == key) return r;
+        if (k == EMPTY64) {
+            if (!INSERT) break;
+            const unsigned long long old = atomicCAS(&t.keys[h], EMPTY64, key);
+            if (old == EMPTY64) {
+                t.slot_list[atomicAdd(t.n_keys, 1ull)] = (uint32_t)h;
+                return r; /* the record of a free slot holds the reset values */
+            }
+            if (old == key) {
+                r.a0 = 0xFFFFFFFFu; r.a1 = 0u; r.first = EMPTY64; r.T = EMPTY64; /* not re-read: treat as unknown */
+                return r;
+            }
+        }
+        h = (h + 1) & t.cap_mask;
+    }
+    if (INSERT) atomicExch(t.overflow, 1u);
+    r.slot = t.cap_mask + 1;
+    return r;
+}
+
+/* K2.  A warp takes the event regions of whole tiles; 32 events at a time (neighbouring reads, so mostly the same
+ * few junctions) are grouped by key with match.any and the lowest lane of each group probes the junction table once
+ * for the whole group.  Read counts are added once per group; anchor extremes and first-seen values are compared
+ * against what the probe saw and only improvements are sent as atomics (almost none once a junction is warm); each
+ * lane counts its own read offset with one fire-and-forget atomic into the junction's dense offset row (or the
+ * offset hash table for large offsets).  The next 32 events are already in flight while a chunk is folded. */
 template <int MODE>
-__global__ void __launch_bounds__(256) k_fold(Tables t, const Event *ev, const unsigned long long *n_events_ptr) {
-    const unsigned long long n_ev = *n_events_ptr;
+__global__ void __launch_bounds__(256, 5) k_fold(Tables t, const Event *ev, const uint32_t *cigar_off, const uint32_t *tile_count,
+                                              uint64_t n_tiles) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    uint32_t inserts = 0u;
-    for (uint64_t base = warp0 * 32; base < n_ev; base += n_warps * 32) {
-        const uint64_t i = base + lane;
-        const bool valid = i < n_ev;
-        Event e;
-        if (valid) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(ev + i);
-            const uint4 lo = __ldg(src), hi = __ldg(src + 1);
-            e.key = ((unsigned long long)lo.y << 32) | lo.x;
-            e.sv = ((unsigned long long)lo.w << 32) | lo.z;
-            e.a0 = hi.x; e.a1 = hi.y; e.off_cat = hi.z;
-        } else {
-            e.key = EMPTY64 - 2 - (unsigned)lane; e.sv = EMPTY64; e.a0 = 0xFFFFFFFFu; e.a1 = 0u; e.off_cat = 0u;
+    uint32_t next_cnt = 0u, next_c0 = 0u;
+    if (warp0 < n_tiles) {
+        next_cnt = __ldg(&tile_count[warp0]);
+        next_c0 = __ldg(&cigar_off[warp0 * EX_TILE]);
+    }
+    for (uint64_t tile = warp0; tile < n_tiles; tile += n_warps) {
+        const uint32_t cnt = next_cnt;
+        const uint64_t base = tile_event_base(next_c0);
+        if (tile + n_warps < n_tiles) {
+            next_cnt = __ldg(&tile_count[tile + n_warps]);
+            next_c0 = __ldg(&cigar_off[(tile + n_warps) * EX_TILE]);
         }
-        const uint32_t cat = (e.off_cat >> 16) & 3u;
-        const int cls = (int)((e.off_cat >> 18) & 3u);
-        const unsigned grp = __match_any_sync(0xFFFFFFFFu, e.key);
-        const int leader = __ffs(grp) - 1;
-        uint64_t slot = t.cap_mask + 1;
-        uint32_t drow = DENSE_NONE;
-        unsigned long long T = 0ull;
-        if (lane == leader && valid) {
+        if (cnt == 0u) continue;
+        Event nxt = load_event(ev, base + lane, (uint32_t)lane < cnt, lane);
+        for (uint32_t k0 = 0; k0 < cnt; k0 += 32u) {
+            const Event e = nxt;
+            const bool valid = k0 + lane < cnt;
+            if (k0 + 32u < cnt) nxt = load_event(ev, base + k0 + 32u + lane, k0 + 32u + lane < cnt, lane);
+            const uint32_t cat = (e.off_cat >> 16) & 3u;
+            const int cls = (int)((e.off_cat >> 18) & 3u);
+            const unsigned grp = __match_any_sync(0xFFFFFFFFu, e.key);
+            const int leader = __ffs(grp) - 1;
+            Probe pr;
+            pr.slot = t.cap_mask + 1;
+            pr.a0 = 0xFFFFFFFFu; pr.a1 = 0u; pr.first = EMPTY64; pr.T = EMPTY64;
+            if (lane == leader && valid) pr = probe_junction<MODE != MODE_PASS2>(t, e.key, cls);
+            const uint64_t slot = __shfl_sync(0xFFFFFFFFu, pr.slot, leader);
+            bool counted = valid && slot <= t.cap_mask;
+            JStat *s = &t.stat[counted ? slot : 0];
             if (MODE == MODE_PASS2) {
-                slot = junction_find(t, e.key);
-                if (slot <= t.cap_mask) T = *((volatile unsigned long long *)&t.stat[slot].T);
+                const unsigned long long T = __shfl_sync(0xFFFFFFFFu, pr.T, leader);
+                counted = counted && T != EMPTY64 && e.sv >= T; /* earlier events are dropped */
             } else {
-                slot = junction_find_or_insert(t, e.key, &drow);
+                /* first-seen sequence value of this lane's strand class */
+                const int leader_cls = __shfl_sync(0xFFFFFFFFu, cls, leader);
+                const unsigned long long seen = __shfl_sync(0xFFFFFFFFu, pr.first, leader);
+                if (counted && (cls != leader_cls || e.sv < seen)) atomicMin(&s->first[cls], e.sv);
             }
-            if (MODE != MODE_PASS1 && slot <= t.cap_mask && drow == DENSE_NONE)
-                drow = *((volatile uint32_t *)&t.dense_idx[slot]);
-        }
-        slot = __shfl_sync(grp, slot, leader);
-        bool counted = valid && slot <= t.cap_mask;
-        if (MODE == MODE_PASS2) {
-            T = __shfl_sync(grp, T, leader);
-            counted = counted && T != EMPTY64 && e.sv >= T; /* earlier events are dropped */
-        }
-        if (MODE != MODE_PASS2 && counted) stat_first(&t.stat[slot], cls, e.sv);
-        if (MODE != MODE_PASS1) {
-            drow = __shfl_sync(grp, drow, leader);
-            const unsigned c0 = __ballot_sync(0xFFFFFFFFu, counted && cat == 0u) & grp;
-            const unsigned c1 = __ballot_sync(0xFFFFFFFFu, counted && cat == 1u) & grp;
-            const unsigned c2 = __ballot_sync(0xFFFFFFFFu, counted && cat == 2u) & grp;
-            const uint32_t a0 = __reduce_min_sync(grp, counted ? e.a0 : 0xFFFFFFFFu);
-            const uint32_t a1 = __reduce_max_sync(grp, counted ? e.a1 : 0u);
-            if (lane == leader && (c0 | c1 | c2)) {
-                JStat *s = &t.stat[slot];
-                if (c0) atomicAdd(&s->cnt[0], (unsigned long long)__popc(c0));
-                if (c1) atomicAdd(&s->cnt[1], (unsigned long long)__popc(c1));
-                if (c2) atomicAdd(&s->cnt[2], (unsigned long long)__popc(c2));
-                if (a0 < *((volatile uint32_t *)&s->a0)) atomicMin(&s->a0, a0);
-                if (a1 > *((volatile uint32_t *)&s->a1)) atomicMax(&s->a1, a1);
-            }
-            if (counted) {
-                const uint32_t off = e.off_cat & 0xFFFFu;
-                if (off < DENSE_W && drow != DENSE_NONE) atomicAdd(&t.dense[(uint64_t)drow * DENSE_W + off], 1u);
-                else inserts += hist_add_hash(t, slot, off, 1u);
+            if (MODE != MODE_PASS1) {
+                const unsigned c0 = __ballot_sync(0xFFFFFFFFu, counted && cat == 0u) & grp;
+                const unsigned c1 = __ballot_sync(0xFFFFFFFFu, counted && cat == 1u) & grp;
+                const unsigned c2 = __ballot_sync(0xFFFFFFFFu, counted && cat == 2u) & grp;
+                if (lane == leader) {
+                    if (c0) atomicAdd(&s->cnt[0], (unsigned long long)__popc(c0));
+                    if (c1) atomicAdd(&s->cnt[1], (unsigned long long)__popc(c1));
+                    if (c2) atomicAdd(&s->cnt[2], (unsigned long long)__popc(c2));
+                }
+                const uint32_t seen_a0 = __shfl_sync(0xFFFFFFFFu, pr.a0, leader);
+                const uint32_t seen_a1 = __shfl_sync(0xFFFFFFFFu, pr.a1, leader);
+                uint32_t new_entry = HIST_NONE;
+                if (counted) {
+                    if (e.a0 < seen_a0) atomicMin(&s->a0, e.a0);
+                    if (e.a1 > seen_a1) atomicMax(&s->a1, e.a1);
+                    new_entry = hist_count(t, slot, e.off_cat & 0xFFFFu, 1u);
+                }
+                hist_list_append(t, new_entry, 0xFFFFFFFFu);
             }
         }
     }
-    unsigned long long ins = warp_sum((unsigned long long)inserts);
-    if (lane == 0 && ins) atomicAdd(t.n_hist, ins);
 }
 
-void launch_fold(int mode, const Tables &t, const Event *ev, const unsigned long long *n_events_ptr, int sm_count,
-                 cudaStream_t st) {
-    const int blocks = sm_count * 8;
+void launch_fold(int mode, const Tables &t, const Event *ev, const uint32_t *cigar_off, const uint32_t *tile_count,
+                 uint64_t n_tiles, int sm_count, cudaStream_t st) {
+    if (n_tiles == 0) return;
+    const uint64_t want = (n_tiles + 7) / 8; /* 8 warps per block, one tile per warp at a time */
+    const uint64_t max_blocks = (uint64_t)sm_count * 5; /* what is resident at once (__launch_bounds__(256, 5)) */
+    const int blocks = (int)(want < max_blocks ? want : max_blocks);
     switch (mode) {
-        case MODE_SINGLE: k_fold<MODE_SINGLE><<<blocks, 256, 0, st>>>(t, ev, n_events_ptr); break;
-        case MODE_PASS1: k_fold<MODE_PASS1><<<blocks, 256, 0, st>>>(t, ev, n_events_ptr); break;
-        default: k_fold<MODE_PASS2><<<blocks, 256, 0, st>>>(t, ev, n_events_ptr); break;
+        case MODE_SINGLE: k_fold<MODE_SINGLE><<<blocks, 256, 0, st>>>(t, ev, cigar_off, tile_count, n_tiles); break;
+        case MODE_PASS1: k_fold<MODE_PASS1><<<blocks, 256, 0, st>>>(t, ev, cigar_off, tile_count, n_tiles); break;
+        default: k_fold<MODE_PASS2><<<blocks, 256, 0, st>>>(t, ev, cigar_off, tile_count, n_tiles); break;
     }
 }
 
@@ -372,11 +733,11 @@ __device__ __forceinline__ int motif_fetch(const GenomeView &g, int32_t tid, uin
 /* For every junction slot without a creation threshold yet: T = first event (stream order) whose strand class
  * passes junction_filter_check (add_junction, junctions_extractor.cc:494-502; SURVEY.md 8a "A6"). */
 __global__ void k_resolve_T(Tables t, GenomeView g) {
-    const uint64_t cap = t.cap_mask + 1;
+    const unsigned long long nk = *t.n_keys;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nk; j += stride) {
+        const uint64_t i = t.slot_list[j];
         const unsigned long long key = t.keys[i];
-        if (key == EMPTY64) continue;
         JStat *s = &t.stat[i];
         if (s->T != EMPTY64) continue;
         const unsigned long long f0 = s->first[CLS_PLUS], f1 = s->first[CLS_MINUS], f2 = s->first[CLS_DOT];
@@ -406,63 +767,60 @@ __global__ void k_resolve_T(Tables t, GenomeView g) {
 }
 
 void launch_resolve_T(const Tables &t, const GenomeView &g, cudaStream_t st) {
-    k_resolve_T<<<148 * 8, 256, 0, st>>>(t, g);
+    k_resolve_T<<<148 * 4, 256, 0, st>>>(t, g);
 }
+
 
 /* ------------------------------------------------------------------ finalize */
-/* gather every created junction: its slot and its key-order sort key */
-__global__ void k_compact_junctions(Tables t, const uint32_t *name_rank, unsigned long long *d_count,
-                                    unsigned long long *sort_key, uint32_t *slot_out) {
-    const uint64_t cap = t.cap_mask + 1;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < cap; base += stride) {
-        const uint64_t i = base + threadIdx.x;
-        bool take = false;
-        unsigned long long key = EMPTY64;
-        if (i < cap) {
-            key = t.keys[i];
-            take = (key != EMPTY64) && (t.stat[i].T != EMPTY64);
-        }
-        const unsigned mask = __ballot_sync(0xFFFFFFFFu, take);
-        if (mask == 0u) continue;
-        const int lane = threadIdx.x & 31;
-        unsigned long long warp_base = 0ull;
-        if (lane == 0) warp_base = atomicAdd(&d_count[0], (unsigned long long)__popc(mask));
-        warp_base = __shfl_sync(0xFFFFFFFFu, warp_base, 0);
-        if (take) {
-            const uint64_t o = warp_base + __popc(mask & ((1u << lane) - 1u));
-            const uint64_t tid = (uint64_t)key_tid(t.kl, key);
-            const uint64_t low = key & ((1ull << t.kl.tid_shift) - 1ull);
-            sort_key[o] = ((unsigned long long)name_rank[tid] << t.kl.tid_shift) | low;
-            slot_out[o] = (uint32_t)i;
-        }
-    }
-}
-
-__global__ void k_fill_slot_rank(const uint32_t *sorted_slot, uint64_t n, uint32_t *slot_rank) {
+/* Everything here walks slot_list (the n_keys slots in use), never the table's capacity.  The number of junctions
+ * n_j <= n_keys (keys whose every event was rejected by the canon filter are not junctions) stays on the device:
+ * rejected keys get a sort key above every real one, so they sort to the end, and the kernels read n_j from
+ * d_count[0]. */
+__global__ void k_list_keys(Tables t, const uint32_t *name_rank, unsigned long long nk, int key_bits,
+                            unsigned long long *d_count, unsigned long long *sort_key, uint32_t *slot_out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) slot_rank[sorted_slot[i]] = (uint32_t)i;
+    bool take = false;
+    if (i < nk) {
+        const uint32_t slot = t.slot_list[i];
+        const unsigned long long key = t.keys[slot];
+        take = t.stat[slot].T != EMPTY64;
+        const uint64_t tid = (uint64_t)key_tid(t.kl, key);
+        const uint64_t low = key & ((1ull << t.kl.tid_shift) - 1ull);
+        /* key order: chromosome-name rank, intron_start, intron_end */
+        sort_key[i] = take ? (((unsigned long long)name_rank[tid] << t.kl.tid_shift) | low) : (1ull << key_bits);
+        slot_out[i] = slot;
+    }
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, take);
+    if (mask && (threadIdx.x & 31) == 0) atomicAdd(&d_count[0], (unsigned long long)__popc(mask));
 }
 
-__global__ void k_gather_T(Tables t, const uint32_t *sorted_slot, uint64_t n, unsigned long long *T_out,
+__global__ void k_fill_slot_rank(const uint32_t *sorted_slot, const unsigned long long *d_count, uint32_t *slot_rank) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d_count[0]) slot_rank[sorted_slot[i]] = (uint32_t)i;
+}
+
+/* sort key of the sjN ranking: the creating event's position in the stream (sv without its strand byte) */
+__global__ void k_gather_T(Tables t, const uint32_t *sorted_slot, unsigned long long nk, int t_bits, unsigned long long *T_out,
                            uint32_t *idx_out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        T_out[i] = t.stat[sorted_slot[i]].T;
+    if (i < nk) {
+        const unsigned long long T = t.stat[sorted_slot[i]].T;
+        T_out[i] = T == EMPTY64 ? (1ull << t_bits) : (T >> 8);
         idx_out[i] = (uint32_t)i;
     }
 }
 
-__global__ void k_scatter_ijunc(const uint32_t *idx_by_T, uint64_t n, uint32_t *ijunc) {
+__global__ void k_scatter_ijunc(const uint32_t *idx_by_T, const unsigned long long *d_count, uint32_t *ijunc) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) ijunc[idx_by_T[i]] = (uint32_t)i;
+    if (i < d_count[0]) ijunc[idx_by_T[i]] = (uint32_t)i;
 }
 
 /* one output row per junction, in key order: attributes of the creating event after motif correction
  * (get_splice_sites + correct_strand, junctions_extractor.cc:419-444) */
-__global__ void k_gather_rows(Tables t, GenomeView g, const uint32_t *sorted_slot, uint64_t n, DeviceTable out) {
+__global__ void k_gather_rows(Tables t, GenomeView g, const uint32_t *sorted_slot, const unsigned long long *d_count,
+                              DeviceTable out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= d_count[0]) return;
     const uint32_t slot = sorted_slot[i];
     const unsigned long long key = t.keys[slot];
     const JStat s = t.stat[slot];
@@ -507,91 +865,38 @@ __global__ void k_gather_rows(Tables t, GenomeView g, const uint32_t *sorted_slo
     for (int k = 0; k < 8; ++k) out.sites[8 * i + k] = site[k];
 }
 
-/* every (junction, offset) pair of a created junction -> (rank << 16 | offset, count); one atomic per block step */
-static const int CH_PER_THREAD = 8;
-__global__ void __launch_bounds__(256) k_compact_hist(Tables t, const uint32_t *slot_rank, unsigned long long *d_count,
-                                                      unsigned long long *hkey_out, uint32_t *hcnt_out, int count_only) {
-    typedef cub::BlockScan<uint32_t, 256> Scan;
-    __shared__ typename Scan::TempStorage scan_tmp;
-    __shared__ unsigned long long block_base;
-    const uint64_t hcap = t.hcap_mask + 1;
-    const uint64_t step = 256ull * CH_PER_THREAD;
-    for (uint64_t base = (uint64_t)blockIdx.x * step; base < hcap; base += (uint64_t)gridDim.x * step) {
-        unsigned long long hk[CH_PER_THREAD];
-        uint32_t cnt[CH_PER_THREAD], rank[CH_PER_THREAD];
-        uint32_t mine = 0;
-#pragma unroll
-        for (int j = 0; j < CH_PER_THREAD; ++j) {
-            const uint64_t i = base + (uint64_t)j * 256 + threadIdx.x;
-            hk[j] = EMPTY64;
-            cnt[j] = 0u;
-            if (i < hcap) {
-                const HEntry e = t.hist[i];
-                hk[j] = e.key;
-                cnt[j] = e.cnt;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < CH_PER_THREAD; ++j) {
-            rank[j] = 0xFFFFFFFFu;
-            if (hk[j] != EMPTY64 && hk[j] != TOMB64) rank[j] = slot_rank[hk[j] >> 16];
-            if (rank[j] != 0xFFFFFFFFu) mine++;
-        }
-        uint32_t offset, total;
-        Scan(scan_tmp).ExclusiveSum(mine, offset, total);
-        if (threadIdx.x == 0 && total) block_base = atomicAdd(&d_count[1], (unsigned long long)total);
-        __syncthreads();
-        if (!count_only && total) {
-            uint64_t o = block_base + offset;
-#pragma unroll
-            for (int j = 0; j < CH_PER_THREAD; ++j) {
-                if (rank[j] != 0xFFFFFFFFu) {
-                    hkey_out[o] = ((unsigned long long)rank[j] << 16) | (hk[j] & 0xFFFFull);
-                    hcnt_out[o] = cnt[j];
-                    o++;
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
-/* entries with a small offset that raced ahead of their junction's dense row: move them into the row */
-__global__ void k_drain_small(Tables t) {
-    const uint64_t hcap = t.hcap_mask + 1;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hcap; i += stride) {
-        const HEntry e = t.hist[i];
-        if (e.key == EMPTY64 || e.key == TOMB64) continue;
-        const uint32_t off = (uint32_t)(e.key & 0xFFFFull);
-        if (off >= DENSE_W) continue;
-        const uint32_t d = t.dense_idx[e.key >> 16];
-        if (d == DENSE_NONE) continue;
-        atomicAdd(&t.dense[(uint64_t)d * DENSE_W + off], e.cnt);
-        t.hist[i].key = TOMB64;
-    }
+/* every offset-table entry -> (junction rank << 16 | offset, count); entries of slots that are not junctions (none
+ * are expected) get a key above every real one */
+__global__ void k_hist_pairs(Tables t, const uint32_t *slot_rank, unsigned long long nh, int h_bits,
+                             unsigned long long *hkey_out, uint32_t *hcnt_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nh) return;
+    const HEntry e = t.hist[t.hist_list[i]];
+    const uint32_t r = slot_rank[e.key >> 16];
+    hkey_out[i] = r == 0xFFFFFFFFu ? (1ull << h_bits) : (((unsigned long long)r << 16) | (e.key & 0xFFFFull));
+    hcnt_out[i] = e.cnt;
 }
 
 /* per junction (key order): first index and number of its entries in the sorted hash-run list */
-__global__ void k_hash_runs(const unsigned long long *sorted_hkey, uint64_t n_hash, unsigned long long *hash_lo,
+__global__ void k_hash_runs(const unsigned long long *sorted_hkey, uint64_t n_hash, int h_bits, unsigned long long *hash_lo,
                             unsigned long long *total) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_hash) return;
+    if (sorted_hkey[i] >> h_bits) return;
     const uint64_t r = sorted_hkey[i] >> 16;
     if (i == 0 || (sorted_hkey[i - 1] >> 16) != r) hash_lo[r] = i;
     atomicAdd(&total[r], 1ull);
 }
 
 /* warp per junction: number of non-zero counters of its dense row, added to total[r] */
-__global__ void k_dense_count(Tables t, const uint32_t *sorted_slot, uint64_t n, unsigned long long *total,
+__global__ void k_dense_count(Tables t, const uint32_t *sorted_slot, const unsigned long long *d_count, unsigned long long *total,
                               uint32_t *dense_nz) {
     const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (r >= n) return;
-    const uint32_t d = t.dense_idx[sorted_slot[r]];
+    if (r >= d_count[0]) return;
     uint32_t nz = 0;
-    if (d != DENSE_NONE) {
-        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)d * DENSE_W);
+    if (t.dense) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)sorted_slot[r] * DENSE_W);
         const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
         nz = (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0) + (b.x != 0) + (b.y != 0) + (b.z != 0) + (b.w != 0);
     }
@@ -604,7 +909,7 @@ __global__ void k_dense_count(Tables t, const uint32_t *sorted_slot, uint64_t n,
 }
 
 /* warp per junction: write its runs in ascending offset order -- dense row first (offsets < DENSE_W), then its
- * slice of the sorted hash runs (all >= DENSE_W once k_drain_small has run, or everything when it has no row) */
+ * slice of the sorted hash runs (offsets >= DENSE_W, or every offset when the table has no dense rows) */
 __global__ void k_write_runs(Tables t, const uint32_t *sorted_slot, uint64_t n, const unsigned long long *hist_off,
                              const uint32_t *dense_nz, const unsigned long long *hash_lo,
                              const unsigned long long *sorted_hkey, const uint32_t *sorted_hcnt, uint32_t *hist_cnt,
@@ -614,9 +919,8 @@ __global__ void k_write_runs(Tables t, const uint32_t *sorted_slot, uint64_t n, 
     if (r >= n) return;
     const unsigned long long o0 = hist_off[r];
     const uint32_t nz = dense_nz[r];
-    const uint32_t d = t.dense_idx[sorted_slot[r]];
-    if (d != DENSE_NONE && nz) {
-        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)d * DENSE_W);
+    if (t.dense && nz) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)sorted_slot[r] * DENSE_W);
         const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
         const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         uint32_t mine = 0;
@@ -677,55 +981,40 @@ static inline unsigned blocks_for(uint64_t n, unsigned threads) {
     return (unsigned)(b ? b : 1);
 }
 
+static inline int bits_for64(uint64_t v) {
+    int b = 1;
+    while (b < 64 && (v >> b) != 0) b++;
+    return b;
+}
+
+template <class K, class V>
+static cudaError_t sort_pairs(FinalizeWork &w, const K *k_in, K *k_out, const V *v_in, V *v_out, uint64_t n, int end_bit,
+                              cudaStream_t st) {
+    size_t tb = 0;
+    IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, st));
+    IPX_CU(ensure_tmp(w, tb, st));
+    return cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, st);
+}
+
 cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, int32_t n_targets,
-                            FinalizeWork &w, DeviceTable &out, bool keep_export, cudaStream_t st, int *own_launches) {
-    (void)n_targets;
+                            uint64_t seq_hi, FinalizeWork &w, DeviceTable &out, bool keep_export, cudaStream_t st,
+                            int *own_launches) {
     int launches = 0;
     const uint64_t cap = t.cap_mask + 1;
     out = DeviceTable();
     if (!w.d_count) IPX_CU(dmalloc(st, &w.d_count, 4 * sizeof(unsigned long long)));
-    if (w.slot_rank_cap < cap) {
-        if (w.slot_rank) dfree(st, w.slot_rank);
-        IPX_CU(dmalloc(st, &w.slot_rank, cap * sizeof(uint32_t)));
-        w.slot_rank_cap = cap;
-    }
     IPX_CU(cudaMemsetAsync(w.d_count, 0, 4 * sizeof(unsigned long long), st));
-    IPX_CU(cudaMemsetAsync(w.slot_rank, 0xFF, cap * sizeof(uint32_t), st));
 
     /* creation thresholds for anything still unresolved */
-    k_resolve_T<<<148 * 8, 256, 0, st>>>(t, g);
+    k_resolve_T<<<148 * 4, 256, 0, st>>>(t, g);
     launches++;
 
-    /* number of keys bounds the number of junctions */
-    unsigned long long n_keys = 0, n_hash_entries = 0;
-    IPX_CU(cudaMemcpyAsync(&n_keys, t.n_keys, sizeof(n_keys), cudaMemcpyDeviceToHost, st));
-    IPX_CU(cudaMemcpyAsync(&n_hash_entries, t.n_hist, sizeof(n_hash_entries), cudaMemcpyDeviceToHost, st));
+    /* first of two host round trips: how many slots and offset-table entries are in use */
+    unsigned long long nk = 0, nh = 0;
+    IPX_CU(cudaMemcpyAsync(&nk, t.n_keys, sizeof(nk), cudaMemcpyDeviceToHost, st));
+    IPX_CU(cudaMemcpyAsync(&nh, t.n_hist, sizeof(nh), cudaMemcpyDeviceToHost, st));
     IPX_CU(cudaStreamSynchronize(st));
-    const uint64_t nk = n_keys ? n_keys : 1;
-
-    unsigned long long *sort_key = nullptr, *sort_key2 = nullptr;
-    uint32_t *slot_a = nullptr, *slot_b = nullptr;
-    IPX_CU(dmalloc(st, &sort_key, nk * 8));
-    IPX_CU(dmalloc(st, &sort_key2, nk * 8));
-    IPX_CU(dmalloc(st, &slot_a, nk * 4));
-    IPX_CU(dmalloc(st, &slot_b, nk * 4));
-    k_compact_junctions<<<148 * 8, 256, 0, st>>>(t, d_name_rank, w.d_count, sort_key, slot_a);
-    launches++;
-    unsigned long long n_j = 0;
-    IPX_CU(cudaMemcpyAsync(&n_j, &w.d_count[0], sizeof(n_j), cudaMemcpyDeviceToHost, st));
-    IPX_CU(cudaStreamSynchronize(st));
-    const uint64_t n = n_j, na = n ? n : 1;
-
-    /* key order: chromosome-name rank, intron_start, intron_end */
-    size_t tmp_bytes = 0;
-    IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, sort_key, sort_key2, slot_a, slot_b, (int)n, 0, 64, st));
-    IPX_CU(ensure_tmp(w, tmp_bytes, st));
-    if (n) IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp_bytes, sort_key, sort_key2, slot_a, slot_b, (int)n, 0, 64, st));
-    const uint32_t *sorted_slot = slot_b;
-    if (n) {
-        k_fill_slot_rank<<<blocks_for(n, 256), 256, 0, st>>>(sorted_slot, n, w.slot_rank);
-        launches++;
-    }
+    const uint64_t na = nk ? nk : 1;
 
     IPX_CU(dmalloc(st, &out.chrom, na * 4));
     IPX_CU(dmalloc(st, &out.i0, na * 4));
@@ -739,85 +1028,93 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
     IPX_CU(dmalloc(st, &out.T, na * 8));
     IPX_CU(dmalloc(st, &out.hist_off, (na + 2) * 8));
     if (keep_export) IPX_CU(dmalloc(st, &out.slot, na * 4));
-    out.n = n;
+    if (nk == 0) {
+        IPX_CU(cudaMemsetAsync(out.hist_off, 0, (na + 2) * 8, st));
+        IPX_CU(dmalloc(st, &out.hist_cnt, 4));
+        if (keep_export) IPX_CU(dmalloc(st, &out.hist_offset, 4));
+        if (own_launches) *own_launches = launches;
+        IPX_CU(cudaStreamSynchronize(st));
+        return cudaGetLastError();
+    }
+
+    unsigned long long *sort_key = nullptr, *sort_key2 = nullptr, *hash_lo = nullptr, *total = nullptr;
+    uint32_t *slot_a = nullptr, *slot_b = nullptr, *idx_b = nullptr, *dense_nz = nullptr;
+    IPX_CU(dmalloc(st, &sort_key, nk * 8));
+    IPX_CU(dmalloc(st, &sort_key2, nk * 8));
+    IPX_CU(dmalloc(st, &slot_a, nk * 4));
+    IPX_CU(dmalloc(st, &slot_b, nk * 4));
+    IPX_CU(dmalloc(st, &idx_b, nk * 4));
+    IPX_CU(dmalloc(st, &hash_lo, nk * 8));
+    IPX_CU(dmalloc(st, &total, (nk + 1) * 8));
+    IPX_CU(dmalloc(st, &dense_nz, nk * 4));
+    IPX_CU(cudaMemsetAsync(total, 0, (nk + 1) * 8, st));
+
+    /* key order */
+    const int key_bits = t.kl.tid_shift + bits_for64((uint64_t)(n_targets > 0 ? n_targets : 1));
+    k_list_keys<<<blocks_for(nk, 256), 256, 0, st>>>(t, d_name_rank, nk, key_bits, w.d_count, sort_key, slot_a);
+    IPX_CU(sort_pairs(w, sort_key, sort_key2, slot_a, slot_b, nk, key_bits + 1 > 64 ? 64 : key_bits + 1, st));
+    const uint32_t *sorted_slot = slot_b;
+    launches++;
 
     /* sjN: rank of the creating event in stream order */
-    if (n) {
+    {
+        const int t_bits = (SV_SEQ_SHIFT - 8) + bits_for64(seq_hi ? seq_hi : 1);
         uint32_t *idx_a = slot_a; /* reuse */
-        uint32_t *idx_b = nullptr;
-        IPX_CU(dmalloc(st, &idx_b, na * 4));
-        k_gather_T<<<blocks_for(n, 256), 256, 0, st>>>(t, sorted_slot, n, sort_key, idx_a);
-        size_t tb = 0;
-        IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, sort_key, sort_key2, idx_a, idx_b, (int)n, 0, 64, st));
-        IPX_CU(ensure_tmp(w, tb, st));
-        IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, sort_key, sort_key2, idx_a, idx_b, (int)n, 0, 64, st));
-        k_scatter_ijunc<<<blocks_for(n, 256), 256, 0, st>>>(idx_b, n, out.ijunc);
-        k_gather_rows<<<blocks_for(n, 256), 256, 0, st>>>(t, g, sorted_slot, n, out);
-        launches += 3; /* gather_T, scatter_ijunc, gather_rows */
-        IPX_CU(cudaStreamSynchronize(st));
-        dfree(st, idx_b);
+        k_gather_T<<<blocks_for(nk, 256), 256, 0, st>>>(t, sorted_slot, nk, t_bits, sort_key, idx_a);
+        IPX_CU(sort_pairs(w, sort_key, sort_key2, idx_a, idx_b, nk, t_bits + 1, st));
+        k_scatter_ijunc<<<blocks_for(nk, 256), 256, 0, st>>>(idx_b, w.d_count, out.ijunc);
+        k_gather_rows<<<blocks_for(nk, 256), 256, 0, st>>>(t, g, sorted_slot, w.d_count, out);
+        launches += 3;
     }
 
-    /* offset histogram.  Hash part first (only long reads / pool overflow put anything there): fold raced
-     * small-offset entries into their dense rows, then order the rest by (junction rank, offset). */
-    unsigned long long *hk_a = nullptr, *hk_b = nullptr, *hash_lo = nullptr, *total = nullptr;
-    uint32_t *hc_a = nullptr, *hc_b = nullptr, *dense_nz = nullptr;
-    uint64_t nh = 0;
-    if (n_hash_entries) {
-        k_drain_small<<<148 * 8, 256, 0, st>>>(t);
-        k_compact_hist<<<148 * 8, 256, 0, st>>>(t, w.slot_rank, w.d_count, nullptr, nullptr, 1);
-        launches += 2;
-        unsigned long long n_h = 0;
-        IPX_CU(cudaMemcpyAsync(&n_h, &w.d_count[1], sizeof(n_h), cudaMemcpyDeviceToHost, st));
-        IPX_CU(cudaStreamSynchronize(st));
-        nh = n_h;
-    }
-    const uint64_t nha = nh ? nh : 1;
-    IPX_CU(dmalloc(st, &hash_lo, na * 8));
-    IPX_CU(dmalloc(st, &total, (na + 1) * 8));
-    IPX_CU(dmalloc(st, &dense_nz, na * 4));
-    IPX_CU(cudaMemsetAsync(total, 0, (na + 1) * 8, st));
+    /* offset histograms: the hash part (long reads) is ordered by (junction rank, offset) with a sort; the dense
+     * rows are already in offset order */
+    unsigned long long *hk_a = nullptr, *hk_b = nullptr;
+    uint32_t *hc_a = nullptr, *hc_b = nullptr;
     if (nh) {
-        IPX_CU(dmalloc(st, &hk_a, nha * 8));
-        IPX_CU(dmalloc(st, &hk_b, nha * 8));
-        IPX_CU(dmalloc(st, &hc_a, nha * 4));
-        IPX_CU(dmalloc(st, &hc_b, nha * 4));
-        IPX_CU(cudaMemsetAsync(&w.d_count[1], 0, sizeof(unsigned long long), st));
-        k_compact_hist<<<148 * 8, 256, 0, st>>>(t, w.slot_rank, w.d_count, hk_a, hc_a, 0);
-        int end_bit = 16;
-        while (end_bit < 64 && (n >> (end_bit - 16)) != 0) end_bit++;
-        size_t tb = 0;
-        IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, hk_a, hk_b, hc_a, hc_b, (int)nh, 0, end_bit, st));
-        IPX_CU(ensure_tmp(w, tb, st));
-        IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, hk_a, hk_b, hc_a, hc_b, (int)nh, 0, end_bit, st));
-        k_hash_runs<<<blocks_for(nh, 256), 256, 0, st>>>(hk_b, nh, hash_lo, total);
-        launches += 2;
+        if (w.slot_rank_cap < cap) {
+            if (w.slot_rank) dfree(st, w.slot_rank);
+            w.slot_rank = nullptr;
+            IPX_CU(dmalloc(st, &w.slot_rank, cap * sizeof(uint32_t)));
+            w.slot_rank_cap = cap;
+        }
+        IPX_CU(cudaMemsetAsync(w.slot_rank, 0xFF, cap * sizeof(uint32_t), st));
+        k_fill_slot_rank<<<blocks_for(nk, 256), 256, 0, st>>>(sorted_slot, w.d_count, w.slot_rank);
+        IPX_CU(dmalloc(st, &hk_a, nh * 8));
+        IPX_CU(dmalloc(st, &hk_b, nh * 8));
+        IPX_CU(dmalloc(st, &hc_a, nh * 4));
+        IPX_CU(dmalloc(st, &hc_b, nh * 4));
+        const int h_bits = 16 + bits_for64(nk);
+        k_hist_pairs<<<blocks_for(nh, 256), 256, 0, st>>>(t, w.slot_rank, nh, h_bits, hk_a, hc_a);
+        IPX_CU(sort_pairs(w, hk_a, hk_b, hc_a, hc_b, nh, h_bits + 1, st));
+        k_hash_runs<<<blocks_for(nh, 256), 256, 0, st>>>(hk_b, nh, h_bits, hash_lo, total);
+        launches += 3;
     }
-    unsigned long long n_runs = 0;
-    if (n) {
-        k_dense_count<<<blocks_for(n * 32, 256), 256, 0, st>>>(t, sorted_slot, n, total, dense_nz);
-        launches++;
-    }
+    k_dense_count<<<blocks_for(nk * 32, 256), 256, 0, st>>>(t, sorted_slot, w.d_count, total, dense_nz);
+    launches++;
     {
         size_t tb = 0;
-        IPX_CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, total, out.hist_off, (int)(n + 1), st));
+        IPX_CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, total, out.hist_off, (int)(nk + 1), st));
         IPX_CU(ensure_tmp(w, tb, st));
-        IPX_CU(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, total, out.hist_off, (int)(n + 1), st));
+        IPX_CU(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, total, out.hist_off, (int)(nk + 1), st));
     }
-    IPX_CU(cudaMemcpyAsync(&n_runs, out.hist_off + n, sizeof(n_runs), cudaMemcpyDeviceToHost, st));
+    /* second host round trip: the number of junctions and of histogram runs */
+    unsigned long long n_j = 0, n_runs = 0;
+    IPX_CU(cudaMemcpyAsync(&n_j, &w.d_count[0], sizeof(n_j), cudaMemcpyDeviceToHost, st));
+    IPX_CU(cudaMemcpyAsync(&n_runs, out.hist_off + nk, sizeof(n_runs), cudaMemcpyDeviceToHost, st));
     IPX_CU(cudaStreamSynchronize(st));
+    out.n = n_j;
     out.n_hist = n_runs;
     IPX_CU(dmalloc(st, &out.hist_cnt, (n_runs ? n_runs : 1) * 4));
     if (keep_export) IPX_CU(dmalloc(st, &out.hist_offset, (n_runs ? n_runs : 1) * 4));
-    if (n) {
-        k_write_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(t, sorted_slot, n, out.hist_off, dense_nz, hash_lo, hk_b, hc_b,
-                                                            out.hist_cnt, out.hist_offset);
+    if (n_j) {
+        k_write_runs<<<blocks_for(n_j * 32, 256), 256, 0, st>>>(t, sorted_slot, n_j, out.hist_off, dense_nz, hash_lo, hk_b, hc_b,
+                                                              out.hist_cnt, out.hist_offset);
         launches++;
     }
     if (own_launches) *own_launches = launches;
-    IPX_CU(cudaStreamSynchronize(st));
     dfree(st, hk_a); dfree(st, hk_b); dfree(st, hc_a); dfree(st, hc_b);
-    dfree(st, hash_lo); dfree(st, total); dfree(st, dense_nz);
+    dfree(st, hash_lo); dfree(st, total); dfree(st, dense_nz); dfree(st, idx_b);
     dfree(st, sort_key); dfree(st, sort_key2); dfree(st, slot_a); dfree(st, slot_b);
     return cudaGetLastError();
 }
@@ -871,13 +1168,14 @@ __global__ void k_import_junction_rows(Tables t, const JunctionRow *jr, uint64_t
 
 __global__ void k_import_hist_rows(Tables t, const HistRow *hr, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const HistRow r = hr[i];
-    const uint64_t key = make_key(t.kl, r.tid, r.i0, r.i1);
-    const uint64_t slot = junction_find_or_insert(t, key);
-    if (slot > t.cap_mask) return;
-    const uint32_t ins = hist_count(t, slot, r.offset & 0xFFFFu, r.cnt);
-    if (ins) atomicAdd(t.n_hist, (unsigned long long)ins);
+    uint32_t new_entry = HIST_NONE;
+    if (i < n) {
+        const HistRow r = hr[i];
+        const uint64_t key = make_key(t.kl, r.tid, r.i0, r.i1);
+        const uint64_t slot = junction_find_or_insert(t, key);
+        if (slot <= t.cap_mask) new_entry = hist_count(t, slot, r.offset & 0xFFFFu, r.cnt);
+    }
+    hist_list_append(t, new_entry, 0xFFFFFFFFu);
 }
 
 void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh,

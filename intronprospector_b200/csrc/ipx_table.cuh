@@ -25,13 +25,13 @@
 namespace ipx {
 
 static const uint64_t EMPTY64 = ~0ull;
-static const uint64_t TOMB64 = ~0ull - 1; /* offset-table entry folded into a dense row during finalize */
 /* Read offsets (intron_start - read start) of short reads are < read length; counts for offsets below DENSE_W
- * live in a per-junction dense row (one 1 KB row per junction, allocated in insertion order), where counting a
- * read is a single fire-and-forget atomic and the ordered run-length output needs no sort.  Larger offsets
- * (long reads) and junctions beyond the pool go to the (junction, offset) hash table. */
+ * live in a dense row of DENSE_W counters per table slot (1 KB per slot: 4 GB of HBM for the default 4 M slots,
+ * touched only where a junction lives), where counting a read is a single fire-and-forget atomic and the ordered
+ * run-length output needs no sort.  Larger offsets (long reads) go to the (junction, offset) hash table, as does
+ * everything when the table is too large to give every slot a row. */
 static const uint32_t DENSE_W = 256;
-static const uint32_t DENSE_NONE = 0xFFFFFFFFu;
+static const uint32_t HIST_NONE = 0xFFFFFFFFu;
 static const int SV_ORD_BITS = 20;
 static const int SV_SEQ_SHIFT = 28;
 
@@ -120,14 +120,14 @@ IPX_HD uint64_t mix64(uint64_t x) {
 struct Tables {
     unsigned long long *keys; /* [cap] */
     JStat *stat;              /* [cap] */
+    uint32_t *slot_list;      /* [cap] slots in use, in insertion order: clear and finalize walk this, never the table */
     HEntry *hist;             /* [hcap] */
-    uint32_t *dense_idx;      /* [cap] row of the junction in `dense`, DENSE_NONE = none */
-    uint32_t *dense;          /* [dense_rows][DENSE_W] read counts for offsets < DENSE_W */
-    uint64_t dense_rows;
+    uint32_t *hist_list;      /* [hcap] offset-table entries in use */
+    uint32_t *dense;          /* [cap][DENSE_W] read counts for offsets < DENSE_W, or NULL when disabled */
     uint64_t cap_mask, hcap_mask;
     /* counters / flags, one cache line each to avoid false sharing */
-    unsigned long long *n_keys;    /* distinct keys inserted */
-    unsigned long long *n_hist;    /* distinct (slot, offset) pairs inserted */
+    unsigned long long *n_keys;    /* distinct keys inserted = entries of slot_list */
+    unsigned long long *n_hist;    /* distinct (slot, offset) pairs inserted = entries of hist_list */
     unsigned long long *n_events;  /* events that passed junction_qc */
     unsigned long long *n_live;    /* CIGAR words of live records */
     unsigned long long *err_sv;    /* min over failing records of (record seq << 28 | code); EMPTY64 = none */
@@ -138,9 +138,8 @@ struct Tables {
 #if defined(__CUDACC__)
 static const uint32_t MAX_PROBE = 1u << 16;
 
-/* find the slot of `key`, inserting it if absent; returns cap_mask + 1 on overflow.  When this call creates the
- * junction, *new_row receives its dense offset row (if the pool still had one). */
-__device__ __forceinline__ uint64_t junction_find_or_insert(const Tables &t, uint64_t key, uint32_t *new_row = nullptr) {
+/* find the slot of `key`, inserting it if absent; returns cap_mask + 1 on overflow */
+__device__ __forceinline__ uint64_t junction_find_or_insert(const Tables &t, uint64_t key) {
     uint64_t h = mix64(key) & t.cap_mask;
     for (uint32_t probe = 0; probe < MAX_PROBE; ++probe) {
         unsigned long long k = *((volatile unsigned long long *)&t.keys[h]);
@@ -148,11 +147,8 @@ __device__ __forceinline__ uint64_t junction_find_or_insert(const Tables &t, uin
         if (k == EMPTY64) {
             unsigned long long old = atomicCAS(&t.keys[h], EMPTY64, (unsigned long long)key);
             if (old == EMPTY64) {
-                const unsigned long long id = atomicAdd(t.n_keys, 1ull);
-                if (id < t.dense_rows) {
-                    atomicExch(&t.dense_idx[h], (uint32_t)id);
-                    if (new_row) *new_row = (uint32_t)id;
-                }
+                /* every slot is claimed at most once between clears, so the list cannot overflow */
+                t.slot_list[atomicAdd(t.n_keys, 1ull)] = (uint32_t)h;
                 return h;
             }
             if (old == key) return h;
@@ -175,40 +171,50 @@ __device__ __forceinline__ uint64_t junction_find(const Tables &t, uint64_t key)
     return t.cap_mask + 1;
 }
 
-/* hash path of hist_count; returns 1 when a new (slot, offset) entry was created */
+/* hash path of hist_count; returns the index of the entry when this call created it (the caller appends it to
+ * hist_list, warp-aggregated: hist_list_append), HIST_NONE otherwise */
 __device__ __forceinline__ uint32_t hist_add_hash(const Tables &t, uint64_t slot, uint32_t offset16, uint32_t n) {
     const unsigned long long hk = ((unsigned long long)slot << 16) | offset16;
     uint64_t h = mix64(hk) & t.hcap_mask;
     for (uint32_t probe = 0; probe < MAX_PROBE; ++probe) {
         unsigned long long k = *((volatile unsigned long long *)&t.hist[h].key);
-        uint32_t inserted = 0u;
+        bool inserted = false;
         if (k == EMPTY64) {
             const unsigned long long old = atomicCAS(&t.hist[h].key, EMPTY64, hk);
-            inserted = (old == EMPTY64) ? 1u : 0u;
+            inserted = (old == EMPTY64);
             k = inserted ? hk : old;
         }
         if (k == hk) {
             atomicAdd(&t.hist[h].cnt, n);
-            return inserted;
+            return inserted ? (uint32_t)h : HIST_NONE;
         }
         h = (h + 1) & t.hcap_mask;
     }
     atomicExch(t.overflow, 2u);
-    return 0u;
+    return HIST_NONE;
 }
 
 /* count n reads at (slot, offset): Junction::count_read's push_back (junctions.hh:163-167), run-length form.
- * Returns the number of hash entries created (callers sum it per block into n_hist). */
+ * Returns like hist_add_hash. */
 __device__ __forceinline__ uint32_t hist_count(const Tables &t, uint64_t slot, uint32_t offset16, uint32_t n) {
-    if (offset16 < DENSE_W) {
-        /* the row index is published right after the key; a reader that races ahead of it uses the hash instead */
-        const uint32_t d = *((volatile uint32_t *)&t.dense_idx[slot]);
-        if (d != DENSE_NONE) {
-            atomicAdd(&t.dense[(uint64_t)d * DENSE_W + offset16], n);
-            return 0u;
-        }
+    if (offset16 < DENSE_W && t.dense != nullptr) {
+        atomicAdd(&t.dense[slot * DENSE_W + offset16], n);
+        return HIST_NONE;
     }
     return hist_add_hash(t, slot, offset16, n);
+}
+
+/* record newly created offset-table entries in hist_list: one atomic per warp.  Every lane named in `active`
+ * must call this together (lanes without a new entry pass HIST_NONE). */
+__device__ __forceinline__ void hist_list_append(const Tables &t, uint32_t new_entry, unsigned active) {
+    const unsigned mask = __ballot_sync(active, new_entry != HIST_NONE);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0ull;
+    if (lane == leader) base = atomicAdd(t.n_hist, (unsigned long long)__popc(mask));
+    base = __shfl_sync(active, base, leader);
+    if (new_entry != HIST_NONE) t.hist_list[base + __popc(mask & ((1u << lane) - 1u))] = new_entry;
 }
 
 /* fold one counted read into a junction's statistics */
