@@ -73,8 +73,9 @@ typedef struct ipx_params {
     int32_t device;                 /* CUDA device ordinal */
     int32_t profile;                /* non-zero: record CUDA events around every stage (ipx_get_timings) */
     void *stream;                   /* cudaStream_t to launch on; NULL = library-owned stream */
-    uint64_t table_capacity;        /* junction hash slots, 0 = default (grows on demand) */
-    uint64_t hist_capacity;         /* offset-histogram hash slots, 0 = default (grows on demand) */
+    uint64_t table_capacity;        /* junction hash slots (power of two; at most half may be used), 0 = default 4 M */
+    uint64_t hist_capacity;         /* entries of the read-offset log (8 bytes each; one per read whose offset the
+                                       256-wide dense rows do not take), 0 = default 64 M */
 } ipx_params;
 
 /* One batch of decoded alignment records in stream order, structure-of-arrays.

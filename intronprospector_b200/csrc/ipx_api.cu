@@ -199,14 +199,14 @@ uint64_t pow2_at_least(uint64_t v) {
 int alloc_tables(ipx_handle *h) {
     if (h->tables_ready) return IPX_OK;
     uint64_t cap = pow2_at_least(h->params.table_capacity ? h->params.table_capacity : (1ull << 22));
-    uint64_t hcap = pow2_at_least(h->params.hist_capacity ? h->params.hist_capacity : (1ull << 25));
+    uint64_t hcap = h->params.hist_capacity ? std::max<uint64_t>(h->params.hist_capacity, 1024) : (1ull << 26);
     if (cap > (1ull << 31)) return fail(h, IPX_ERR_ARG, "table_capacity too large");
     Tables &t = h->tab;
     CU(h, cudaMalloc(&t.keys, cap * sizeof(unsigned long long)));
     CU(h, cudaMalloc(&t.stat, cap * sizeof(JStat)));
-    CU(h, cudaMalloc(&t.hist, hcap * sizeof(HEntry)));
+    CU(h, cudaMalloc(&t.olog, hcap * sizeof(unsigned long long)));
+    t.olog_cap = hcap;
     CU(h, cudaMalloc(&t.slot_list, cap * sizeof(uint32_t)));
-    CU(h, cudaMalloc(&t.hist_list, hcap * sizeof(uint32_t)));
     /* dense offset rows: 1 KB per slot, so up to 16 GB of the 180 GB; beyond that every offset goes to the hash */
     t.dense = nullptr;
     if (cap <= (1ull << 24) && !getenv("IPX_NO_DENSE")) {
@@ -216,9 +216,8 @@ int alloc_tables(ipx_handle *h) {
     CU(h, cudaMalloc(&h->d_counters, 8 * 128));
     CU(h, cudaMemsetAsync(h->d_counters, 0, 8 * 128, h->stream));
     t.cap_mask = cap - 1;
-    t.hcap_mask = hcap - 1;
     t.n_keys = h->d_counters + 0;
-    t.n_hist = h->d_counters + 16;
+    t.n_olog = h->d_counters + 16;
     t.n_events = h->d_counters + 32;
     t.n_live = h->d_counters + 48;
     t.err_sv = h->d_counters + 64;
@@ -405,7 +404,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     cudaStreamSynchronize(h->stream);
     drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
     if (h->finalized) free_device_table(h->dt, h->stream);
-    cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.hist); cudaFree(h->tab.slot_list); cudaFree(h->tab.hist_list); cudaFree(h->tab.dense);
+    cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.olog); cudaFree(h->tab.slot_list); cudaFree(h->tab.dense);
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq);
     free_genome(h);
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();
@@ -613,7 +612,7 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     if (overflow) {
         delete ht;
         if (overflow == 3) return fail(h, IPX_ERR_CAPACITY, "intron start beyond 2^31 cannot be keyed");
-        return fail(h, IPX_ERR_CAPACITY, "%s hash table is full; raise ipx_params.%s", overflow == 1 ? "junction" : "offset",
+        return fail(h, IPX_ERR_CAPACITY, "%s is full; raise ipx_params.%s", overflow == 1 ? "junction hash table" : "read-offset log",
                     overflow == 1 ? "table_capacity" : "hist_capacity");
     }
     ht->counts.assign(counts.begin(), counts.end());

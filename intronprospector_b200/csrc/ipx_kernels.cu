@@ -40,30 +40,25 @@ __device__ __forceinline__ void reset_stat(JStat *s) {
 }
 
 __global__ void k_init_tables(Tables t) {
-    const uint64_t cap = t.cap_mask + 1, hcap = t.hcap_mask + 1;
+    const uint64_t cap = t.cap_mask + 1;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
         t.keys[i] = EMPTY64;
         reset_stat(&t.stat[i]);
     }
-    HEntry e;
-    e.key = EMPTY64;
-    e.cnt = 0u;
-    e.pad = 0u;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hcap; i += stride) t.hist[i] = e;
 }
 
 __global__ void k_reset_counters(Tables t) {
     *t.n_keys = 0ull;
-    *t.n_hist = 0ull;
+    *t.n_olog = 0ull;
     *t.err_sv = EMPTY64;
     *t.overflow = 0u;
 }
 
-/* clear(): undo exactly what the lists say was touched -- a warp per junction slot (key, 64-byte record, 1 KB
- * offset row), a thread per offset-table entry */
+/* clear(): undo exactly what the slot list says was touched -- a warp per junction slot (key, 64-byte record, 1 KB
+ * offset row); the offset log is emptied by resetting its counter */
 __global__ void __launch_bounds__(256) k_clear_tables(Tables t) {
-    const unsigned long long nk = *t.n_keys, nh = *t.n_hist;
+    const unsigned long long nk = *t.n_keys;
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -79,12 +74,6 @@ __global__ void __launch_bounds__(256) k_clear_tables(Tables t) {
             row[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
         }
     }
-    HEntry e;
-    e.key = EMPTY64;
-    e.cnt = 0u;
-    e.pad = 0u;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nh; i += stride) t.hist[t.hist_list[i]] = e;
 }
 
 void launch_init_tables(const Tables &t, cudaStream_t st) {
@@ -201,15 +190,17 @@ __global__ void __launch_bounds__(EXS_THREADS) k_extract_simple(BatchView b, Ext
 /* Warp roles of one block (no block-wide barrier after start-up; everything is handed over through mbarriers):
  *   producer   (1 warp, one lane)  TMA bulk copies of the next tile's columns and CIGAR words into a free stage;
  *                                  when a stage comes back it publishes the tile's event count and resets the stage
- *   classifier (2 warps)           process_alignment's skip test for every record of the tile and compaction of the
+ *   classifier (3 warps)           process_alignment's skip test for every record of the tile and compaction of the
  *                                  live ones into the stage's two lists
- *   walker     (8 warps)           take 32 listed records at a time from the stage's dispensers and walk them; a
+ *   walker     (12 warps)          take 32 listed records at a time from the stage's dispensers and walk them; a
  *                                  walker that finds a tile's dispensers empty moves on to the next tile at once,
  *                                  so walkers spread over the tiles in flight and never wait for each other */
 static const int EX_STAGES = 4;
-static const int EX_WALKER_WARPS = 8;
-static const int EX_CLASSIFIER_WARPS = 2;
+static const int EX_WALKER_WARPS = 12;
+static const int EX_CLASSIFIER_WARPS = 3;
 static const int EX_THREADS = (EX_WALKER_WARPS + EX_CLASSIFIER_WARPS + 1) * 32;
+static const int EX_AHEAD = 6;      /* the producer asks L2 for a tile this many of its tiles before it stages it, so the
+                                       copy into a freed stage is an L2 hit and the ring need not cover the DRAM latency */
 static const int EX_CIG_CAP = 2048; /* staged CIGAR words per tile (average short-read tile: ~1500); words beyond are
                                        read from global memory */
 
@@ -253,6 +244,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)
             : "memory");
+        if (!done) __nanosleep(128);
     } while (!done);
 }
 /* TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP) */
@@ -260,6 +252,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+/* TMA prefetch of a global range into L2 (no shared memory involved) */
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 /* a CIGAR word of the batch: from the stage when it was staged, else from global memory */
@@ -319,9 +316,36 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
             nc0 = __ldg(&b.cigar_off[(uint64_t)first * EX_TILE]);
             nc1 = __ldg(&b.cigar_off[(uint64_t)first * EX_TILE + EX_TILE]);
         }
+        auto prefetch_tile = [&](uint32_t j) {
+            const uint64_t r0 = (uint64_t)(first + j * stride) * EX_TILE;
+            bulk_prefetch_l2(b.cigar_off + r0, EX_TILE * 4);
+            bulk_prefetch_l2(b.tid + r0, EX_TILE * 4);
+            bulk_prefetch_l2(b.pos + r0, EX_TILE * 4);
+            bulk_prefetch_l2(b.flag + r0, EX_TILE * 2);
+            bulk_prefetch_l2(b.nh + r0, EX_TILE);
+            bulk_prefetch_l2(b.xs + r0, EX_TILE);
+        };
+        for (uint32_t j = 0; j < (uint32_t)EX_AHEAD && j < my_tiles; ++j) prefetch_tile(j);
+        /* CIGAR range of the tile EX_AHEAD ahead: its boundaries are loaded one iteration before they are used */
+        uint32_t pf0 = 0u, pf1 = 0u;
+        auto load_bounds = [&](uint32_t j) {
+            const uint64_t r0 = (uint64_t)(first + j * stride) * EX_TILE;
+            pf0 = __ldg(&b.cigar_off[r0]);
+            pf1 = __ldg(&b.cigar_off[r0 + EX_TILE]);
+        };
+        if ((uint32_t)EX_AHEAD < my_tiles) load_bounds(EX_AHEAD);
         for (uint32_t it = 0; it < my_tiles + EX_STAGES; ++it) {
             const int s = (int)(it % EX_STAGES);
             ExStage &S = stages[s];
+            if (it + EX_AHEAD < my_tiles) {
+                prefetch_tile(it + EX_AHEAD);
+                const uint32_t lo = pf0 & ~3u;
+                uint32_t hi = (pf1 + 3u) & ~3u;
+                if (hi - lo > (uint32_t)EX_CIG_CAP) hi = lo + (uint32_t)EX_CIG_CAP;
+                if (hi > n_cigar_words) hi = lo + ((n_cigar_words - lo) & ~3u);
+                if (hi > lo) bulk_prefetch_l2(b.cigar + lo, (hi - lo) * 4u);
+                if (it + EX_AHEAD + 1 < my_tiles) load_bounds(it + EX_AHEAD + 1);
+            }
             if (it >= (uint32_t)EX_STAGES) {
                 /* the tile that occupied this stage has been left by every walker */
                 mbar_wait(&empty[s], ((it / EX_STAGES) & 1u) ^ 1u);
@@ -362,15 +386,15 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
     if (warp >= EX_WALKER_WARPS) {
         /* ---------------- classifiers: process_alignment's skip test (junctions_extractor.cc:536) + compaction ------- */
         const int cw = warp - EX_WALKER_WARPS;
-        const int per_warp = EX_TILE / EX_CLASSIFIER_WARPS; /* records of the tile this warp classifies */
         unsigned long long live_words = 0ull;
         for (uint32_t it = 0; it < my_tiles; ++it) {
             const int s = (int)(it % EX_STAGES);
             ExStage &S = stages[s];
             mbar_wait(&full[s], (it / EX_STAGES) & 1u);
+            /* 128 records per warp and round (four consecutive records per lane), rounds dealt out to the warps */
 #pragma unroll 1
-            for (int r = 0; r < per_warp; r += 128) {
-                const uint32_t q = (uint32_t)(cw * per_warp + r) / 4u + lane; /* records 4q .. 4q+3 */
+            for (int r = cw * 128; r < EX_TILE; r += EX_CLASSIFIER_WARPS * 128) {
+                const uint32_t q = (uint32_t)r / 4u + lane; /* records 4q .. 4q+3 */
                 const uint4 o = reinterpret_cast<const uint4 *>(S.off)[q];
                 const uint32_t o4 = S.off[4 * q + 4];
                 const int4 td = reinterpret_cast<const int4 *>(S.tid)[q];
@@ -508,31 +532,6 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
 }
 
 /* ------------------------------------------------------------------ K2: keyed aggregation */
-/* fold one event into the tables on its own (import kernels); returns like hist_count */
-template <int MODE>
-__device__ __forceinline__ uint32_t fold_event_direct(const Tables &t, unsigned long long key, unsigned long long sv,
-                                                      uint32_t a0, uint32_t a1, uint32_t off, uint32_t cat, int cls) {
-    if (MODE == MODE_PASS2) {
-        const uint64_t slot = junction_find(t, key);
-        if (slot > t.cap_mask) return HIST_NONE;
-        JStat *s = &t.stat[slot];
-        const unsigned long long T = *((volatile unsigned long long *)&s->T);
-        if (T == EMPTY64 || sv < T) return HIST_NONE; /* before the junction exists: dropped */
-        stat_accumulate(s, cat, a0, a1);
-        return hist_count(t, slot, off, 1u);
-    } else {
-        const uint64_t slot = junction_find_or_insert(t, key);
-        if (slot > t.cap_mask) return HIST_NONE;
-        JStat *s = &t.stat[slot];
-        stat_first(s, cls, sv);
-        if (MODE == MODE_SINGLE) {
-            stat_accumulate(s, cat, a0, a1);
-            return hist_count(t, slot, off, 1u);
-        }
-        return HIST_NONE;
-    }
-}
-
 __device__ __forceinline__ Event load_event(const Event *ev, uint64_t i, bool valid, int lane) {
     Event e;
     if (valid) {
@@ -604,6 +603,7 @@ __global__ void __launch_bounds__(256, 5) k_fold(Tables t, const Event *ev, cons
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    OlogWriter olog{0ull, 0u};
     uint32_t next_cnt = 0u, next_c0 = 0u;
     if (warp0 < n_tiles) {
         next_cnt = __ldg(&tile_count[warp0]);
@@ -653,16 +653,19 @@ __global__ void __launch_bounds__(256, 5) k_fold(Tables t, const Event *ev, cons
                 }
                 const uint32_t seen_a0 = __shfl_sync(0xFFFFFFFFu, pr.a0, leader);
                 const uint32_t seen_a1 = __shfl_sync(0xFFFFFFFFu, pr.a1, leader);
-                uint32_t new_entry = HIST_NONE;
+                const uint32_t off = e.off_cat & 0xFFFFu;
+                const bool in_row = t.dense != nullptr && off < DENSE_W;
                 if (counted) {
                     if (e.a0 < seen_a0) atomicMin(&s->a0, e.a0);
                     if (e.a1 > seen_a1) atomicMax(&s->a1, e.a1);
-                    new_entry = hist_count(t, slot, e.off_cat & 0xFFFFu, 1u);
+                    /* Junction::count_read's push_back (junctions.hh:163-167), run-length form */
+                    if (in_row) atomicAdd(&t.dense[slot * DENSE_W + off], 1u);
                 }
-                hist_list_append(t, new_entry, 0xFFFFFFFFu);
+                olog_append(t, olog, counted && !in_row, olog_entry(slot, off, 1u));
             }
         }
     }
+    if (MODE != MODE_PASS1) olog_finish(t, olog);
 }
 
 void launch_fold(int mode, const Tables &t, const Event *ev, const uint32_t *cigar_off, const uint32_t *tile_count,
@@ -865,23 +868,23 @@ __global__ void k_gather_rows(Tables t, GenomeView g, const uint32_t *sorted_slo
     for (int k = 0; k < 8; ++k) out.sites[8 * i + k] = site[k];
 }
 
-/* every offset-table entry -> (junction rank << 16 | offset, count); entries of slots that are not junctions (none
- * are expected) get a key above every real one */
-__global__ void k_hist_pairs(Tables t, const uint32_t *slot_rank, unsigned long long nh, int h_bits,
+/* every offset-log entry -> (junction rank << 16 | offset, count); invalid entries and entries of slots that are not
+ * junctions (none are expected) get a key above every real one */
+__global__ void k_olog_pairs(Tables t, const uint32_t *slot_rank, unsigned long long nh, int h_bits,
                              unsigned long long *hkey_out, uint32_t *hcnt_out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nh) return;
-    const HEntry e = t.hist[t.hist_list[i]];
-    const uint32_t r = slot_rank[e.key >> 16];
-    hkey_out[i] = r == 0xFFFFFFFFu ? (1ull << h_bits) : (((unsigned long long)r << 16) | (e.key & 0xFFFFull));
-    hcnt_out[i] = e.cnt;
+    const unsigned long long e = t.olog[i];
+    const uint32_t r = e == OLOG_INVALID ? 0xFFFFFFFFu : slot_rank[e >> 32];
+    hkey_out[i] = r == 0xFFFFFFFFu ? (1ull << h_bits) : (((unsigned long long)r << 16) | ((e >> 16) & 0xFFFFull));
+    hcnt_out[i] = (uint32_t)(e & 0xFFFFull);
 }
 
-/* per junction (key order): first index and number of its entries in the sorted hash-run list */
-__global__ void k_hash_runs(const unsigned long long *sorted_hkey, uint64_t n_hash, int h_bits, unsigned long long *hash_lo,
+/* per junction (key order): first index and number of its runs in the sorted, run-length reduced log */
+__global__ void k_hash_runs(const unsigned long long *sorted_hkey, const uint32_t *n_runs, int h_bits, unsigned long long *hash_lo,
                             unsigned long long *total) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_hash) return;
+    if (i >= *n_runs) return;
     if (sorted_hkey[i] >> h_bits) return;
     const uint64_t r = sorted_hkey[i] >> 16;
     if (i == 0 || (sorted_hkey[i - 1] >> 16) != r) hash_lo[r] = i;
@@ -1011,9 +1014,12 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
 
     /* first of two host round trips: how many slots and offset-table entries are in use */
     unsigned long long nk = 0, nh = 0;
+    uint32_t overflow = 0;
     IPX_CU(cudaMemcpyAsync(&nk, t.n_keys, sizeof(nk), cudaMemcpyDeviceToHost, st));
-    IPX_CU(cudaMemcpyAsync(&nh, t.n_hist, sizeof(nh), cudaMemcpyDeviceToHost, st));
+    IPX_CU(cudaMemcpyAsync(&nh, t.n_olog, sizeof(nh), cudaMemcpyDeviceToHost, st));
+    IPX_CU(cudaMemcpyAsync(&overflow, t.overflow, sizeof(overflow), cudaMemcpyDeviceToHost, st));
     IPX_CU(cudaStreamSynchronize(st));
+    if (overflow) nk = nh = 0; /* a table or the log ran out of room: ipx_flush reports it, there is no result */
     const uint64_t na = nk ? nk : 1;
 
     IPX_CU(dmalloc(st, &out.chrom, na * 4));
@@ -1085,9 +1091,15 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
         IPX_CU(dmalloc(st, &hc_a, nh * 4));
         IPX_CU(dmalloc(st, &hc_b, nh * 4));
         const int h_bits = 16 + bits_for64(nk);
-        k_hist_pairs<<<blocks_for(nh, 256), 256, 0, st>>>(t, w.slot_rank, nh, h_bits, hk_a, hc_a);
+        k_olog_pairs<<<blocks_for(nh, 256), 256, 0, st>>>(t, w.slot_rank, nh, h_bits, hk_a, hc_a);
         IPX_CU(sort_pairs(w, hk_a, hk_b, hc_a, hc_b, nh, h_bits + 1, st));
-        k_hash_runs<<<blocks_for(nh, 256), 256, 0, st>>>(hk_b, nh, h_bits, hash_lo, total);
+        /* equal (junction, offset) pairs -> one run with the summed count; the runs end up in hk_a / hc_a */
+        uint32_t *n_unique = reinterpret_cast<uint32_t *>(w.d_count + 2);
+        size_t tb = 0;
+        IPX_CU(cub::DeviceReduce::ReduceByKey(nullptr, tb, hk_b, hk_a, hc_b, hc_a, n_unique, cub::Sum(), (int)nh, st));
+        IPX_CU(ensure_tmp(w, tb, st));
+        IPX_CU(cub::DeviceReduce::ReduceByKey(w.cub_tmp, tb, hk_b, hk_a, hc_b, hc_a, n_unique, cub::Sum(), (int)nh, st));
+        k_hash_runs<<<blocks_for(nh, 256), 256, 0, st>>>(hk_a, n_unique, h_bits, hash_lo, total);
         launches += 3;
     }
     k_dense_count<<<blocks_for(nk * 32, 256), 256, 0, st>>>(t, sorted_slot, w.d_count, total, dense_nz);
@@ -1108,7 +1120,7 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
     IPX_CU(dmalloc(st, &out.hist_cnt, (n_runs ? n_runs : 1) * 4));
     if (keep_export) IPX_CU(dmalloc(st, &out.hist_offset, (n_runs ? n_runs : 1) * 4));
     if (n_j) {
-        k_write_runs<<<blocks_for(n_j * 32, 256), 256, 0, st>>>(t, sorted_slot, n_j, out.hist_off, dense_nz, hash_lo, hk_b, hc_b,
+        k_write_runs<<<blocks_for(n_j * 32, 256), 256, 0, st>>>(t, sorted_slot, n_j, out.hist_off, dense_nz, hash_lo, hk_a, hc_a,
                                                               out.hist_cnt, out.hist_offset);
         launches++;
     }
@@ -1168,14 +1180,25 @@ __global__ void k_import_junction_rows(Tables t, const JunctionRow *jr, uint64_t
 
 __global__ void k_import_hist_rows(Tables t, const HistRow *hr, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t new_entry = HIST_NONE;
+    OlogWriter olog{0ull, 0u};
+    uint64_t slot = 0;
+    uint32_t off = 0u, left = 0u;
     if (i < n) {
         const HistRow r = hr[i];
-        const uint64_t key = make_key(t.kl, r.tid, r.i0, r.i1);
-        const uint64_t slot = junction_find_or_insert(t, key);
-        if (slot <= t.cap_mask) new_entry = hist_count(t, slot, r.offset & 0xFFFFu, r.cnt);
+        slot = junction_find_or_insert(t, make_key(t.kl, r.tid, r.i0, r.i1));
+        off = r.offset & 0xFFFFu;
+        if (slot <= t.cap_mask) {
+            if (t.dense != nullptr && off < DENSE_W) atomicAdd(&t.dense[slot * DENSE_W + off], r.cnt);
+            else left = r.cnt;
+        }
     }
-    hist_list_append(t, new_entry, 0xFFFFFFFFu);
+    /* log entries hold 16-bit counts */
+    while (__any_sync(0xFFFFFFFFu, left != 0u)) {
+        const uint32_t piece = left > 0xFFFFu ? 0xFFFFu : left;
+        olog_append(t, olog, piece != 0u, olog_entry(slot, off, piece));
+        left -= piece;
+    }
+    olog_finish(t, olog);
 }
 
 void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh,

@@ -31,7 +31,9 @@ static const uint64_t EMPTY64 = ~0ull;
  * run-length output needs no sort.  Larger offsets (long reads) go to the (junction, offset) hash table, as does
  * everything when the table is too large to give every slot a row. */
 static const uint32_t DENSE_W = 256;
-static const uint32_t HIST_NONE = 0xFFFFFFFFu;
+/* log of (slot, offset, count) entries for what the dense rows do not take; sorted and run-length reduced at finalize */
+static const uint64_t OLOG_INVALID = ~0ull;
+static const uint32_t OLOG_BLOCK = 32; /* entries a warp reserves at a time */
 static const int SV_ORD_BITS = 20;
 static const int SV_SEQ_SHIFT = 28;
 
@@ -67,17 +69,6 @@ struct alignas(64) JStat {
     unsigned long long cnt[3];   /* read_counts[] (junctions.hh:117) */
     uint32_t a0;                 /* min anchor_start, 0xFFFFFFFF = none */
     uint32_t a1;                 /* max anchor_end */
-};
-
-/* offset-table entry: key and count share one 16-byte slot so that a probe and its count touch one sector */
-#if defined(__CUDACC__)
-struct __align__(16) HEntry {
-#else
-struct alignas(16) HEntry {
-#endif
-    unsigned long long key; /* junction slot << 16 | uint16 read offset, EMPTY64 = free */
-    uint32_t cnt;
-    uint32_t pad;
 };
 
 /* one junction event between K1 (extract) and K2 (fold): 32 bytes */
@@ -121,13 +112,13 @@ struct Tables {
     unsigned long long *keys; /* [cap] */
     JStat *stat;              /* [cap] */
     uint32_t *slot_list;      /* [cap] slots in use, in insertion order: clear and finalize walk this, never the table */
-    HEntry *hist;             /* [hcap] */
-    uint32_t *hist_list;      /* [hcap] offset-table entries in use */
+    unsigned long long *olog; /* [olog_cap] slot << 32 | read offset << 16 | count, or OLOG_INVALID */
+    uint64_t olog_cap;
     uint32_t *dense;          /* [cap][DENSE_W] read counts for offsets < DENSE_W, or NULL when disabled */
-    uint64_t cap_mask, hcap_mask;
+    uint64_t cap_mask;
     /* counters / flags, one cache line each to avoid false sharing */
     unsigned long long *n_keys;    /* distinct keys inserted = entries of slot_list */
-    unsigned long long *n_hist;    /* distinct (slot, offset) pairs inserted = entries of hist_list */
+    unsigned long long *n_olog;    /* entries of olog handed out (whole blocks; unused ones hold OLOG_INVALID) */
     unsigned long long *n_events;  /* events that passed junction_qc */
     unsigned long long *n_live;    /* CIGAR words of live records */
     unsigned long long *err_sv;    /* min over failing records of (record seq << 28 | code); EMPTY64 = none */
@@ -171,50 +162,44 @@ __device__ __forceinline__ uint64_t junction_find(const Tables &t, uint64_t key)
     return t.cap_mask + 1;
 }
 
-/* hash path of hist_count; returns the index of the entry when this call created it (the caller appends it to
- * hist_list, warp-aggregated: hist_list_append), HIST_NONE otherwise */
-__device__ __forceinline__ uint32_t hist_add_hash(const Tables &t, uint64_t slot, uint32_t offset16, uint32_t n) {
-    const unsigned long long hk = ((unsigned long long)slot << 16) | offset16;
-    uint64_t h = mix64(hk) & t.hcap_mask;
-    for (uint32_t probe = 0; probe < MAX_PROBE; ++probe) {
-        unsigned long long k = *((volatile unsigned long long *)&t.hist[h].key);
-        bool inserted = false;
-        if (k == EMPTY64) {
-            const unsigned long long old = atomicCAS(&t.hist[h].key, EMPTY64, hk);
-            inserted = (old == EMPTY64);
-            k = inserted ? hk : old;
-        }
-        if (k == hk) {
-            atomicAdd(&t.hist[h].cnt, n);
-            return inserted ? (uint32_t)h : HIST_NONE;
-        }
-        h = (h + 1) & t.hcap_mask;
-    }
-    atomicExch(t.overflow, 2u);
-    return HIST_NONE;
-}
+/* Per-warp writer of the offset log.  base/left are warp-uniform; every lane of the (converged) warp calls
+ * olog_append together.  A block of OLOG_BLOCK entries is reserved with one atomic and filled chunk by chunk; what is
+ * left of a block when the next one is needed, or when the kernel ends (olog_finish), is marked invalid. */
+struct OlogWriter {
+    unsigned long long base;
+    uint32_t left;
+};
 
-/* count n reads at (slot, offset): Junction::count_read's push_back (junctions.hh:163-167), run-length form.
- * Returns like hist_add_hash. */
-__device__ __forceinline__ uint32_t hist_count(const Tables &t, uint64_t slot, uint32_t offset16, uint32_t n) {
-    if (offset16 < DENSE_W && t.dense != nullptr) {
-        atomicAdd(&t.dense[slot * DENSE_W + offset16], n);
-        return HIST_NONE;
-    }
-    return hist_add_hash(t, slot, offset16, n);
-}
-
-/* record newly created offset-table entries in hist_list: one atomic per warp.  Every lane named in `active`
- * must call this together (lanes without a new entry pass HIST_NONE). */
-__device__ __forceinline__ void hist_list_append(const Tables &t, uint32_t new_entry, unsigned active) {
-    const unsigned mask = __ballot_sync(active, new_entry != HIST_NONE);
+__device__ __forceinline__ void olog_append(const Tables &t, OlogWriter &w, bool want, unsigned long long entry) {
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, want);
     if (mask == 0u) return;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(mask) - 1;
-    unsigned long long base = 0ull;
-    if (lane == leader) base = atomicAdd(t.n_hist, (unsigned long long)__popc(mask));
-    base = __shfl_sync(active, base, leader);
-    if (new_entry != HIST_NONE) t.hist_list[base + __popc(mask & ((1u << lane) - 1u))] = new_entry;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t m = (uint32_t)__popc(mask);
+    if (m > w.left) {
+        if (lane < w.left) t.olog[w.base + lane] = OLOG_INVALID;
+        unsigned long long nb = 0ull;
+        if (lane == 0u) nb = atomicAdd(t.n_olog, (unsigned long long)OLOG_BLOCK);
+        nb = __shfl_sync(0xFFFFFFFFu, nb, 0);
+        w.base = nb;
+        w.left = OLOG_BLOCK;
+        if (nb + OLOG_BLOCK > t.olog_cap) {
+            atomicExch(t.overflow, 2u); /* the run is lost: ipx_flush reports it */
+            w.left = 0u;
+            return;
+        }
+    }
+    if (want) t.olog[w.base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = entry;
+    w.base += m;
+    w.left -= m;
+}
+
+__device__ __forceinline__ void olog_finish(const Tables &t, const OlogWriter &w) {
+    const uint32_t lane = threadIdx.x & 31u;
+    if (lane < w.left) t.olog[w.base + lane] = OLOG_INVALID;
+}
+
+__device__ __forceinline__ unsigned long long olog_entry(uint64_t slot, uint32_t offset16, uint32_t n) {
+    return ((unsigned long long)slot << 32) | ((unsigned long long)(offset16 & 0xFFFFu) << 16) | (n & 0xFFFFu);
 }
 
 /* fold one counted read into a junction's statistics */
