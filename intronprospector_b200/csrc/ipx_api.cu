@@ -113,7 +113,8 @@ struct ipx_handle {
     /* staging for host batches */
     DeviceBuf s_tid, s_pos, s_flag, s_nh, s_xs, s_off, s_cig;
     DeviceBuf ev_buf;   /* junction events of the batch in flight (K1 -> K2), one region per tile */
-    DeviceBuf tile_cnt; /* events per tile */
+    DeviceBuf tile_cnt; /* TileInfo per tile */
+    DeviceBuf long_buf; /* LongRec regions (records handed from the pipelined kernel to k_extract_long) */
     uint64_t seq_hi = 0; /* one past the largest record stream index pushed so far */
 
     /* finalize */
@@ -309,19 +310,21 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
     const uint64_t ev_bound = n_cigar / 2 + 1;
     CU(h, h->ev_buf.reserve(ev_bound * sizeof(Event), h->stream));
     const uint64_t n_tiles = tiles_of(b.n);
-    CU(h, h->tile_cnt.reserve((n_tiles + 1) * sizeof(uint32_t), h->stream));
-    uint32_t *tile_count = (uint32_t *)h->tile_cnt.p;
+    CU(h, h->tile_cnt.reserve((n_tiles + 1) * sizeof(TileInfo), h->stream));
+    CU(h, h->long_buf.reserve((n_cigar / 4 + 2) * sizeof(LongRec), h->stream));
+    TileInfo *tile_count = (TileInfo *)h->tile_cnt.p;
     const Event *events = (const Event *)h->ev_buf.p;
     {
         Span s(h, &h->tm_extract, 0);
         int launched = 0;
-        CU(h, launch_extract(b, n_cigar, h->xp, h->tab, (Event *)h->ev_buf.p, tile_count, h->sm_count, h->stream, &launched));
+        CU(h, launch_extract(b, n_cigar, h->xp, h->tab, (Event *)h->ev_buf.p, tile_count, (LongRec *)h->long_buf.p, h->sm_count,
+                             h->stream, &launched));
         h->tm_extract.launches += (uint64_t)launched;
     }
     if (two_pass(h)) {
         {
             Span s(h, &h->tm_aggregate, 1);
-            launch_fold(MODE_PASS1, h->tab, events, b.cigar_off, tile_count, n_tiles, h->sm_count, h->stream);
+            launch_fold(MODE_PASS1, h->tab, events, tile_count, n_tiles, h->sm_count, h->stream);
         }
         {
             Span s(h, &h->tm_motif, 1);
@@ -329,11 +332,11 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
         }
         {
             Span s(h, &h->tm_aggregate, 1);
-            launch_fold(MODE_PASS2, h->tab, events, b.cigar_off, tile_count, n_tiles, h->sm_count, h->stream);
+            launch_fold(MODE_PASS2, h->tab, events, tile_count, n_tiles, h->sm_count, h->stream);
         }
     } else {
         Span s(h, &h->tm_aggregate, 1);
-        launch_fold(MODE_SINGLE, h->tab, events, b.cigar_off, tile_count, n_tiles, h->sm_count, h->stream);
+        launch_fold(MODE_SINGLE, h->tab, events, tile_count, n_tiles, h->sm_count, h->stream);
     }
     CU(h, cudaGetLastError());
     h->totals.records += b.n;
@@ -408,7 +411,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq);
     free_genome(h);
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();
-    h->s_off.release(); h->s_cig.release(); h->ev_buf.release(); h->tile_cnt.release();
+    h->s_off.release(); h->s_cig.release(); h->ev_buf.release(); h->tile_cnt.release(); h->long_buf.release();
     cudaFree(h->fw.cub_tmp); cudaFree(h->fw.d_count); cudaFree(h->fw.slot_rank);
     cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
     if (h->own_stream) cudaStreamDestroy(h->stream);

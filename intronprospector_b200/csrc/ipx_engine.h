@@ -68,9 +68,28 @@ enum ExtractMode { MODE_SINGLE = 0, MODE_PASS1 = 1, MODE_PASS2 = 2 };
 /* K1 works on tiles of EX_TILE consecutive records.  The events of tile i go to a private region of the event
  * buffer starting at event index ceil(cigar_off[i * EX_TILE] / 2): a read needs at least one N and one following
  * aligned operation per emitted junction, so a tile cannot emit more events than half its CIGAR words and the
- * regions of consecutive tiles never overlap.  tile_count[i] is the number of events tile i wrote.  No global
+ * regions of consecutive tiles never overlap.  tile_info[i] says how many events tile i wrote.  No global
  * atomic is involved; the buffer holds n_cigar / 2 + 1 events. */
 static const int EX_TILE = 1024;
+struct __align__(16) TileInfo {
+    uint32_t count;      /* events the tile wrote */
+    uint32_t first_word; /* cigar_off of its first record: the region starts at event (first_word + 1) / 2 */
+    uint32_t n_long;     /* records of the tile handed to k_extract_long (LongRec region starts at (first_word + 3) / 4) */
+    uint32_t pad;
+};
+/* A live record with more than three CIGAR operations, as the pipelined kernel hands it to k_extract_long: everything
+ * the walk needs except the CIGAR words themselves.  A tile's records go to a private region of the LongRec buffer
+ * starting at ceil(first_word / 4) -- such a record has at least four words, so regions cannot overlap; the buffer
+ * holds n_cigar / 4 + 2 records. */
+struct __align__(16) LongRec {
+    int32_t pos;
+    int32_t tid;
+    uint32_t c0, n_cigar; /* its words are cigar[c0 .. c0 + n_cigar) */
+    uint32_t rec;         /* index of the record in the batch */
+    uint16_t flag;
+    uint8_t nh, xs;
+    uint32_t pad[2];
+};
 inline uint64_t tiles_of(uint64_t n_records) { return (n_records + EX_TILE - 1) / EX_TILE; }
 
 /* kernels' launchers; all asynchronous on `st` */
@@ -78,9 +97,9 @@ void launch_init_tables(const Tables &t, cudaStream_t st);  /* whole tables, onc
 void launch_clear_tables(const Tables &t, cudaStream_t st); /* only what the lists say is in use */
 /* returns a CUDA error (attribute set-up of the pipelined kernel can fail), launches counted in *launches */
 cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractParams &p, const Tables &t, Event *out,
-                           uint32_t *tile_count, int sm_count, cudaStream_t st, int *launches);
-void launch_fold(int mode, const Tables &t, const Event *ev, const uint32_t *cigar_off, const uint32_t *tile_count,
-                 uint64_t n_tiles, int sm_count, cudaStream_t st);
+                           TileInfo *tile_info, LongRec *long_recs, int sm_count, cudaStream_t st, int *launches);
+void launch_fold(int mode, const Tables &t, const Event *ev, const TileInfo *tile_info, uint64_t n_tiles, int sm_count,
+                 cudaStream_t st);
 void launch_resolve_T(const Tables &t, const GenomeView &g, cudaStream_t st);
 void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh,
                         cudaStream_t st);

@@ -5,7 +5,7 @@
  *                    warp), so every record column and CIGAR word is read from HBM exactly once, coalesced, with
  *                    the latency hidden behind the previous tiles' work.  Eight consumer warps (a) classify the
  *                    tile's records and compact the live ones (process_alignment's skip test) into two lists --
- *                    CIGARs of at most three operations, which can only be "aligned, N, aligned", and longer ones
+ *                    CIGARs of at most three operations, which can only be aligned
  *                    -- then (b) walk the listed records with full warps (ipx_walk.cuh) and write each junction
  *                    event straight into the tile's private region of the event buffer.
  *  k_extract_simple  K1 for what the pipeline does not take: the last partial tile, unaligned columns, long reads.
@@ -26,7 +26,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
-#include "ipx_engine.h"
+#include ipx_engine.h""
 
 namespace ipx {
 
@@ -142,14 +142,15 @@ __device__ __forceinline__ EventSink make_sink(const Tables &t, const ExtractPar
 static const int EXS_THREADS = 256;
 
 __global__ void __launch_bounds__(EXS_THREADS) k_extract_simple(BatchView b, ExtractParams p, Tables t, Event *out,
-                                                                uint32_t *tile_count, uint64_t first_tile, uint64_t n_tiles) {
+                                                                TileInfo *tile_info, uint64_t first_tile, uint64_t n_tiles) {
     __shared__ uint32_t region_fill;
     unsigned long long live_words = 0ull, events = 0ull;
     for (uint64_t tile = first_tile + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (threadIdx.x == 0) region_fill = 0u;
         __syncthreads();
         const uint64_t r0 = tile * EX_TILE;
-        Event *region = out + tile_event_base(__ldg(&b.cigar_off[r0]));
+        const uint32_t first_word = __ldg(&b.cigar_off[r0]);
+        Event *region = out + tile_event_base(first_word);
         for (uint64_t r = r0 + threadIdx.x; r < r0 + EX_TILE && r < b.n; r += EXS_THREADS) {
             const uint32_t c0 = __ldg(&b.cigar_off[r]), n_cigar = __ldg(&b.cigar_off[r + 1]) - c0;
             const int32_t tid = __ldg(&b.tid[r]);
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(EXS_THREADS) k_extract_simple(BatchView b, Ext
             events += sink.n_events;
         }
         __syncthreads();
-        if (threadIdx.x == 0) tile_count[tile] = region_fill;
+        if (threadIdx.x == 0) tile_info[tile] = TileInfo{region_fill, first_word, 0u, 0u};
         __syncthreads();
     }
     live_words = warp_sum(live_words);
@@ -187,20 +188,20 @@ __global__ void __launch_bounds__(EXS_THREADS) k_extract_simple(BatchView b, Ext
 }
 
 /* ---- pipelined K1 ---- */
-/* Warp roles of one block (no block-wide barrier after start-up; everything is handed over through mbarriers):
- *   producer   (1 warp, one lane)  TMA bulk copies of the next tile's columns and CIGAR words into a free stage;
- *                                  when a stage comes back it publishes the tile's event count and resets the stage
- *   classifier (3 warps)           process_alignment's skip test for every record of the tile and compaction of the
- *                                  live ones into the stage's two lists
- *   walker     (12 warps)          take 32 listed records at a time from the stage's dispensers and walk them; a
- *                                  walker that finds a tile's dispensers empty moves on to the next tile at once,
- *                                  so walkers spread over the tiles in flight and never wait for each other */
+/* One block = a producer warp and a pool of worker warps; nothing is synchronised block-wide after start-up.
+ *   producer (one lane)  TMA bulk copies of the next tile's columns and CIGAR words into a free stage of the ring;
+ *                        when a stage comes back it publishes the tile's event count and resets the stage
+ *   workers              walk the ring in tile order.  A tile offers two kinds of work through dispensers in its stage:
+ *                        rounds" (process_alignment's skip test for 128 records and compaction of the live ones into"
+ *                        the stage's lists) and, once all rounds are done, chunks" (walk 32 listed records).  In"
+ *                        iteration i a worker first takes rounds of tile i+1 if its data has landed, then makes sure
+ *                        tile i is classified (helping with its rounds if any are left), then takes chunks of tile i.
+ *                        Classification of a tile therefore overlaps the walk of the tile before it, and a warp busy
+ *                        with a long walk simply takes fewer units. */
 static const int EX_STAGES = 4;
-static const int EX_WALKER_WARPS = 12;
-static const int EX_CLASSIFIER_WARPS = 3;
-static const int EX_THREADS = (EX_WALKER_WARPS + EX_CLASSIFIER_WARPS + 1) * 32;
-static const int EX_AHEAD = 6;      /* the producer asks L2 for a tile this many of its tiles before it stages it, so the
-                                       copy into a freed stage is an L2 hit and the ring need not cover the DRAM latency */
+static const int EX_WORKER_WARPS = 15;
+static const int EX_THREADS = (EX_WORKER_WARPS + 1) * 32;
+static const int EX_ROUNDS = EX_TILE / 128;
 static const int EX_CIG_CAP = 2048; /* staged CIGAR words per tile (average short-read tile: ~1500); words beyond are
                                        read from global memory */
 
@@ -216,47 +217,54 @@ struct __align__(128) ExStage {
     /* written by the block itself */
     uint16_t list[EX_TILE]; /* live records: short CIGARs (<= 3 operations) from the front, longer ones from the back */
     uint32_t n_lists;       /* number of short | number of long << 16 */
-    uint32_t next_short, next_long; /* chunk dispensers of the walkers */
+    uint32_t next_round, rounds_done; /* classification rounds handed out / finished */
+    uint32_t next_short, next_long;   /* chunk dispensers */
     uint32_t region_fill;   /* events written to the tile's region */
     uint32_t tile;          /* tile index */
     uint32_t a0, a_end;     /* staged CIGAR words are [a0, a_end) of the batch's CIGAR column */
-    uint32_t pad;
+    uint32_t pad[3];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile(mbarrier.init.shared::cta.b64 [%0]
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile(mbarrier.arrive.expect_tx.shared::cta.b64 _
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile(mbarrier.arrive.shared::cta.b64 _
 }
-/* wait for the phase with the given parity; the hint lets the hardware park the thread instead of spinning */
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+/* has the phase with the given parity completed?  (the hint lets the hardware park the thread for a while) */
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity, uint32_t hint_ns) {
     uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(100000u)
-            : "memory");
-        if (!done) __nanosleep(128);
-    } while (!done);
+    asm volatile(
+        {\n\t.reg .pred p;\n\t""
+        mbarrier.try_wait.parity.shared::cta.b64 p
+        selp.u32 %0
+        : =r"(done)"
+        : r"(smem_u32(bar))
+        : memory");"
+    return done != 0u;
+}
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        {\n\t.reg .pred p;\n\t""
+        mbarrier.test_wait.parity.shared::cta.b64 p
+        selp.u32 %0
+        : =r"(done)"
+        : r"(smem_u32(bar))
+        : memory");"
+    return done != 0u;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try(bar, parity, 100000u)) __nanosleep(64);
 }
 /* TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP) */
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-/* TMA prefetch of a global range into L2 (no shared memory involved) */
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+    asm volatile(cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0]
+                 : memory");"
 }
 
 /* a CIGAR word of the batch: from the stage when it was staged, else from global memory */
@@ -286,29 +294,139 @@ __device__ __forceinline__ void walk_record(const BatchView &b, const ExtractPar
     events += sink.n_events;
 }
 
+/* one classification round: process_alignment's skip test (junctions_extractor.cc:536) for records
+ * [128 r, 128 r + 128) of the stage's tile, four consecutive records per lane, and compaction of the live ones */
+__device__ __forceinline__ void classify_round(ExStage &S, uint32_t r, int lane, LongRec *long_recs, int walk_long_here,
+                                               unsigned long long &live_words) {
+    const uint32_t q = r * 32u + lane; /* records 4q .. 4q+3 */
+    const uint4 o = reinterpret_cast<const uint4 *>(S.off)[q];
+    const uint32_t o4 = S.off[4 * q + 4];
+    const int4 td = reinterpret_cast<const int4 *>(S.tid)[q];
+    const uint2 f2 = reinterpret_cast<const uint2 *>(S.flag)[q];
+    const uint32_t n[4] = {o.y - o.x, o.z - o.y, o.w - o.z, o4 - o.w};
+    const int32_t tdv[4] = {td.x, td.y, td.z, td.w};
+    const uint32_t fl[4] = {f2.x & 0xFFFFu, f2.x >> 16, f2.y & 0xFFFFu, f2.y >> 16};
+    uint32_t kind[4], mine = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        kind[j] = 0u;
+        if (record_is_live(n[j], tdv[j], fl[j])) {
+            live_words += n[j];
+            kind[j] = n[j] <= 3u ? 1u : 2u;
+            mine += n[j] <= 3u ? 1u : 0x10000u;
+        }
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    uint32_t base = 0u;
+    if (lane == 31 && incl) base = atomicAdd(&S.n_lists, incl);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31);
+    const uint32_t pre = base + incl - mine;
+    uint32_t ps = pre & 0xFFFFu, pl = pre >> 16;
+    LongRec *long_region = long_recs + (((uint64_t)S.off[0] + 3ull) >> 2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t rl = 4 * q + j;
+        if (kind[j] == 1u) {
+            S.list[ps++] = (uint16_t)rl;
+        } else if (kind[j] == 2u && walk_long_here) {
+            S.list[EX_TILE - 1 - (pl++)] = (uint16_t)rl;
+        } else if (kind[j] == 2u) {
+            /* hand the record to k_extract_long */
+            const uint32_t c0r = j == 0 ? o.x : (j == 1 ? o.y : (j == 2 ? o.z : o.w));
+            uint4 *dst = reinterpret_cast<uint4 *>(long_region + (pl++));
+            dst[0] = make_uint4((uint32_t)S.pos[rl], (uint32_t)tdv[j], c0r, n[j]);
+            dst[1] = make_uint4(S.tile * EX_TILE + rl, fl[j] | ((uint32_t)S.nh[rl] << 16) | ((uint32_t)S.xs[rl] << 24), 0u, 0u);
+        }
+    }
+}
+
+/* take classification rounds of a stage until none is left */
+__device__ __forceinline__ void take_rounds(ExStage &S, int lane, LongRec *long_recs, int walk_long_here,
+                                            unsigned long long &live_words) {
+    for (;;) {
+        uint32_t r = 0u;
+        if (lane == 0) r = atomicAdd(&S.next_round, 1u);
+        r = __shfl_sync(0xFFFFFFFFu, r, 0);
+        if (r >= (uint32_t)EX_ROUNDS) break;
+        classify_round(S, r, lane, long_recs, walk_long_here, live_words);
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block(); /* the lists before the count */
+            atomicAdd(&S.rounds_done, 1u);
+        }
+    }
+}
+
+/* the short-CIGAR chunk: aligned
+ * (ReadJunctionExtractor, junctions_extractor.cc:208-254,278-282) */
+__device__ __forceinline__ void walk_short(const BatchView &b, const ExtractParams &p, const Tables &t, ExStage &S, Event *region,
+                                           uint32_t rl, unsigned long long &events) {
+    const uint32_t c0 = S.off[rl], n_cigar = S.off[rl + 1] - c0;
+    const uint32_t w0 = cigar_word(S, b.cigar, c0), w1 = cigar_word(S, b.cigar, c0 + 1);
+    const uint32_t w2 = n_cigar == 3u ? cigar_word(S, b.cigar, c0 + 2) : 0u;
+    const uint32_t o0 = w0 & 15u, o1 = w1 & 15u, o2 = w2 & 15u;
+    const uint32_t known = 0x1BFu, aligned = 0x181u; /* MIDNSH=X ; M=X */
+    if (!((known >> o0) & (known >> o1) & (known >> o2) & 1u)) {
+        walk_record(b, p, t, S, region, rl, events); /* reports the unknown operation exactly */
+    } else if (n_cigar == 3u && o1 == OP_N && ((aligned >> o0) & (aligned >> o2) & 1u)) {
+        /* the one candidate: anchor_start = pos, intron = [pos + l0, + l1), anchor_end = intron_end + l2, mismatches =
+         * the X lengths, no indels.  Operation lengths are below 2^28 and pos is a BAM int32, so 32-bit arithmetic
+         * gives what the reference's 64-bit arithmetic gives wherever the result is usable (a start outside
+         * [0, 2^31) is reported). */
+        const uint32_t l0 = w0 >> 4, l1 = w1 >> 4, l2 = w2 >> 4;
+        const uint32_t flag = S.flag[rl], nh = S.nh[rl];
+        const uint32_t lbad = o0 == OP_X ? l0 : 0u, rbad = o2 == OP_X ? l2 : 0u;
+        /* junction_qc (junctions_extractor.cc:384-401) */
+        if (read_may_emit(p, flag, nh) && l1 >= p.min_intron_length && l1 <= p.max_intron_length &&
+            l0 - lbad >= p.min_anchor_length && l2 - rbad >= p.min_anchor_length) {
+            events++;
+            const uint32_t pos = (uint32_t)S.pos[rl];
+            const uint32_t i0 = pos + l0;
+            if (i0 > 0x7FFFFFFFu) {
+                atomicExch(t.overflow, 3u);
+            } else {
+                const char strand = read_strand(p.strandness, flag, S.xs[rl]);
+                const unsigned long long key = ((unsigned long long)(uint32_t)S.tid[rl] << t.kl.tid_shift) |
+                                               ((unsigned long long)i0 << t.kl.start_shift) | l1;
+                const unsigned long long sv = make_sv(b.seq_base + (uint64_t)S.tile * EX_TILE + rl, 0u, strand);
+                const uint32_t off_cat = (l0 & 0xFFFFu) | (read_category(flag, nh) << 16) | ((uint32_t)strand_class(strand) << 18);
+                const uint32_t idx = atomicAdd(&S.region_fill, 1u);
+                uint4 *dst = reinterpret_cast<uint4 *>(region + idx);
+                dst[0] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)sv, (uint32_t)(sv >> 32));
+                dst[1] = make_uint4(pos, i0 + l1 + l2, off_cat, 0u);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint32_t n_cigar_words, ExtractParams p, Tables t,
-                                                               Event *out, uint32_t *tile_count, uint32_t n_full_tiles) {
+                                                               Event *out, TileInfo *tile_info, LongRec *long_recs,
+                                                               uint32_t n_full_tiles, int walk_long_here) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ExStage *stages = reinterpret_cast<ExStage *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + EX_STAGES * sizeof(ExStage)); /* TMA bytes have landed */
-    uint64_t *classified = full + EX_STAGES;                                               /* lists are complete */
-    uint64_t *empty = classified + EX_STAGES;                                              /* every walker has left */
+    uint64_t *empty = full + EX_STAGES;                                                    /* every worker has left */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < EX_STAGES; ++s) {
             mbar_init(&full[s], 1u);
-            mbar_init(&classified[s], (uint32_t)EX_CLASSIFIER_WARPS);
-            mbar_init(&empty[s], (uint32_t)EX_WALKER_WARPS);
-            stages[s].n_lists = stages[s].next_short = stages[s].next_long = stages[s].region_fill = 0u;
+            mbar_init(&empty[s], (uint32_t)EX_WORKER_WARPS);
+            stages[s].n_lists = stages[s].next_round = stages[s].rounds_done = 0u;
+            stages[s].next_short = stages[s].next_long = stages[s].region_fill = 0u;
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile(fence.mbarrier_init.release.cluster;" ::: "memory");"
+        asm volatile(fence.proxy.async.shared::cta;" ::: "memory");"
     }
     __syncthreads();
     const uint32_t first = blockIdx.x, stride = gridDim.x;
     const uint32_t my_tiles = first < n_full_tiles ? (n_full_tiles - first + stride - 1) / stride : 0u;
 
-    if (warp == EX_WALKER_WARPS + EX_CLASSIFIER_WARPS) {
+    if (warp == EX_WORKER_WARPS) {
         /* ---------------- producer: one lane feeds the ring ---------------- */
         if (lane != 0) return;
         uint32_t nc0 = 0u, nc1 = 0u;
@@ -316,41 +434,14 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
             nc0 = __ldg(&b.cigar_off[(uint64_t)first * EX_TILE]);
             nc1 = __ldg(&b.cigar_off[(uint64_t)first * EX_TILE + EX_TILE]);
         }
-        auto prefetch_tile = [&](uint32_t j) {
-            const uint64_t r0 = (uint64_t)(first + j * stride) * EX_TILE;
-            bulk_prefetch_l2(b.cigar_off + r0, EX_TILE * 4);
-            bulk_prefetch_l2(b.tid + r0, EX_TILE * 4);
-            bulk_prefetch_l2(b.pos + r0, EX_TILE * 4);
-            bulk_prefetch_l2(b.flag + r0, EX_TILE * 2);
-            bulk_prefetch_l2(b.nh + r0, EX_TILE);
-            bulk_prefetch_l2(b.xs + r0, EX_TILE);
-        };
-        for (uint32_t j = 0; j < (uint32_t)EX_AHEAD && j < my_tiles; ++j) prefetch_tile(j);
-        /* CIGAR range of the tile EX_AHEAD ahead: its boundaries are loaded one iteration before they are used */
-        uint32_t pf0 = 0u, pf1 = 0u;
-        auto load_bounds = [&](uint32_t j) {
-            const uint64_t r0 = (uint64_t)(first + j * stride) * EX_TILE;
-            pf0 = __ldg(&b.cigar_off[r0]);
-            pf1 = __ldg(&b.cigar_off[r0 + EX_TILE]);
-        };
-        if ((uint32_t)EX_AHEAD < my_tiles) load_bounds(EX_AHEAD);
         for (uint32_t it = 0; it < my_tiles + EX_STAGES; ++it) {
             const int s = (int)(it % EX_STAGES);
             ExStage &S = stages[s];
-            if (it + EX_AHEAD < my_tiles) {
-                prefetch_tile(it + EX_AHEAD);
-                const uint32_t lo = pf0 & ~3u;
-                uint32_t hi = (pf1 + 3u) & ~3u;
-                if (hi - lo > (uint32_t)EX_CIG_CAP) hi = lo + (uint32_t)EX_CIG_CAP;
-                if (hi > n_cigar_words) hi = lo + ((n_cigar_words - lo) & ~3u);
-                if (hi > lo) bulk_prefetch_l2(b.cigar + lo, (hi - lo) * 4u);
-                if (it + EX_AHEAD + 1 < my_tiles) load_bounds(it + EX_AHEAD + 1);
-            }
             if (it >= (uint32_t)EX_STAGES) {
-                /* the tile that occupied this stage has been left by every walker */
+                /* the tile that occupied this stage has been left by every worker */
                 mbar_wait(&empty[s], ((it / EX_STAGES) & 1u) ^ 1u);
-                tile_count[S.tile] = S.region_fill;
-                S.n_lists = S.next_short = S.next_long = S.region_fill = 0u;
+                tile_info[S.tile] = TileInfo{S.region_fill, S.off[0], walk_long_here ? 0u : S.n_lists >> 16, 0u};
+                S.n_lists = S.next_round = S.rounds_done = S.next_short = S.next_long = S.region_fill = 0u;
             }
             if (it < my_tiles) {
                 const uint32_t tile = first + it * stride;
@@ -383,71 +474,26 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
         return;
     }
 
-    if (warp >= EX_WALKER_WARPS) {
-        /* ---------------- classifiers: process_alignment's skip test (junctions_extractor.cc:536) + compaction ------- */
-        const int cw = warp - EX_WALKER_WARPS;
-        unsigned long long live_words = 0ull;
-        for (uint32_t it = 0; it < my_tiles; ++it) {
-            const int s = (int)(it % EX_STAGES);
-            ExStage &S = stages[s];
-            mbar_wait(&full[s], (it / EX_STAGES) & 1u);
-            /* 128 records per warp and round (four consecutive records per lane), rounds dealt out to the warps */
-#pragma unroll 1
-            for (int r = cw * 128; r < EX_TILE; r += EX_CLASSIFIER_WARPS * 128) {
-                const uint32_t q = (uint32_t)r / 4u + lane; /* records 4q .. 4q+3 */
-                const uint4 o = reinterpret_cast<const uint4 *>(S.off)[q];
-                const uint32_t o4 = S.off[4 * q + 4];
-                const int4 td = reinterpret_cast<const int4 *>(S.tid)[q];
-                const uint2 f2 = reinterpret_cast<const uint2 *>(S.flag)[q];
-                const uint32_t n[4] = {o.y - o.x, o.z - o.y, o.w - o.z, o4 - o.w};
-                const int32_t tdv[4] = {td.x, td.y, td.z, td.w};
-                const uint32_t fl[4] = {f2.x & 0xFFFFu, f2.x >> 16, f2.y & 0xFFFFu, f2.y >> 16};
-                uint32_t kind[4], mine = 0u;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    kind[j] = 0u;
-                    if (record_is_live(n[j], tdv[j], fl[j])) {
-                        live_words += n[j];
-                        kind[j] = n[j] <= 3u ? 1u : 2u;
-                        mine += n[j] <= 3u ? 1u : 0x10000u;
-                    }
-                }
-                uint32_t incl = mine;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                    if (lane >= d) incl += y;
-                }
-                uint32_t base = 0u;
-                if (lane == 31 && incl) base = atomicAdd(&S.n_lists, incl);
-                base = __shfl_sync(0xFFFFFFFFu, base, 31);
-                const uint32_t pre = base + incl - mine;
-                uint32_t ps = pre & 0xFFFFu, pl = pre >> 16;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (kind[j] == 1u) S.list[ps++] = (uint16_t)(4 * q + j);
-                    else if (kind[j] == 2u) S.list[EX_TILE - 1 - (pl++)] = (uint16_t)(4 * q + j);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&classified[s]);
-        }
-        live_words = warp_sum(live_words);
-        if (lane == 0 && live_words) atomicAdd(t.n_live, live_words);
-        return;
-    }
-
-    /* ---------------- walkers ---------------- */
-    unsigned long long events = 0ull;
+    /* ---------------- workers ---------------- */
+    unsigned long long live_words = 0ull, events = 0ull;
     for (uint32_t it = 0; it < my_tiles; ++it) {
         const int s = (int)(it % EX_STAGES);
         ExStage &S = stages[s];
-        mbar_wait(&full[s], (it / EX_STAGES) & 1u);       /* the TMA-written columns are visible to this thread */
-        mbar_wait(&classified[s], (it / EX_STAGES) & 1u); /* the lists are complete */
-        const uint32_t n_short = S.n_lists & 0xFFFFu, n_long = S.n_lists >> 16;
+        /* (1) rounds of the next tile, if its data is already here */
+        if (it + 1 < my_tiles) {
+            const int s1 = (int)((it + 1) % EX_STAGES);
+            if (mbar_test(&full[s1], ((it + 1) / EX_STAGES) & 1u)) take_rounds(stages[s1], lane, long_recs, walk_long_here, live_words);
+        }
+        /* (2) this tile must be classified before it can be walked: help with what is left, then wait for the rest */
+        mbar_wait(&full[s], (it / EX_STAGES) & 1u);
+        take_rounds(S, lane, long_recs, walk_long_here, live_words);
+        while (*((volatile uint32_t *)&S.rounds_done) < (uint32_t)EX_ROUNDS) __nanosleep(32);
+        __threadfence_block();
+        /* (3) chunks of this tile: 32 listed records at a time, longest CIGARs first */
+        const uint32_t n_lists = *((volatile uint32_t *)&S.n_lists);
+        const uint32_t n_short = n_lists & 0xFFFFu, n_long = walk_long_here ? n_lists >> 16 : 0u;
         Event *region = out + tile_event_base(S.off[0]);
-        /* 32 listed records at a time, longest CIGARs first */
-        for (;;) {
+        while (n_long) {
             uint32_t c = 0u;
             if (lane == 0) c = atomicAdd(&S.next_long, 32u);
             c = __shfl_sync(0xFFFFFFFFu, c, 0);
@@ -459,36 +505,55 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
             if (lane == 0) c = atomicAdd(&S.next_short, 32u);
             c = __shfl_sync(0xFFFFFFFFu, c, 0);
             if (c >= n_short) break;
-            if (c + lane < n_short) {
-                /* a CIGAR of two or three operations emits a junction only as "aligned, N, aligned"
-                 * (ReadJunctionExtractor, junctions_extractor.cc:208-254,278-282) */
-                const uint32_t rl = S.list[c + lane];
-                const uint32_t c0 = S.off[rl], n_cigar = S.off[rl + 1] - c0;
-                const uint32_t w0 = cigar_word(S, b.cigar, c0), w1 = cigar_word(S, b.cigar, c0 + 1);
-                const uint32_t w2 = n_cigar == 3u ? cigar_word(S, b.cigar, c0 + 2) : 0u;
-                const uint32_t o0 = w0 & 15u, o1 = w1 & 15u, o2 = w2 & 15u;
-                const uint32_t known = 0x1BFu, aligned = 0x181u; /* MIDNSH=X ; M=X */
-                if (!((known >> o0) & (known >> o1) & (known >> o2) & 1u)) {
-                    walk_record(b, p, t, S, region, rl, events); /* reports the unknown operation exactly */
-                } else if (n_cigar == 3u && o1 == OP_N && ((aligned >> o0) & (aligned >> o2) & 1u)) {
-                    const int64_t pos = S.pos[rl];
-                    const uint64_t seq = b.seq_base + (uint64_t)S.tile * EX_TILE + rl;
-                    EventSink sink = make_sink(t, p, region, &S.region_fill, S.tid[rl], pos, seq, S.flag[rl], S.nh[rl], S.xs[rl]);
-                    Candidate cand;
-                    cand.anchor_start = pos;
-                    cand.intron_start = pos + (int64_t)(w0 >> 4);
-                    cand.intron_end = cand.intron_start + (int64_t)(w1 >> 4);
-                    cand.anchor_end = cand.intron_end + (int64_t)(w2 >> 4);
-                    cand.left_bad = o0 == OP_X ? (w0 >> 4) : 0u;
-                    cand.right_bad = o2 == OP_X ? (w2 >> 4) : 0u;
-                    cand.ordinal = 0u;
-                    sink(cand);
-                    events += sink.n_events;
-                }
-            }
+            if (c + lane < n_short) walk_short(b, p, t, S, region, S.list[c + lane], events);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    live_words = warp_sum(live_words);
+    events = warp_sum(events);
+    if (lane == 0) {
+        if (live_words) atomicAdd(t.n_live, live_words);
+        if (events) atomicAdd(t.n_events, events);
+    }
+}
+
+/* ---- K1 for the records the pipelined kernel handed over: a thread per record, CIGAR words from global memory ---- */
+__global__ void __launch_bounds__(256) k_extract_long(BatchView b, ExtractParams p, Tables t, Event *out, TileInfo *tile_info,
+                                                      const LongRec *long_recs, uint64_t n_tiles) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long events = 0ull;
+    for (uint64_t tile = warp0; tile < n_tiles; tile += n_warps) {
+        const uint4 info = __ldg(reinterpret_cast<const uint4 *>(tile_info + tile));
+        const uint32_t n_long = info.z;
+        if (n_long == 0u) continue;
+        Event *region = out + tile_event_base(info.y);
+        const LongRec *recs = long_recs + (((uint64_t)info.y + 3ull) >> 2);
+        for (uint32_t i = lane; i < n_long; i += 32u) {
+            const uint4 r0 = __ldg(reinterpret_cast<const uint4 *>(recs + i));
+            const uint4 r1 = __ldg(reinterpret_cast<const uint4 *>(recs + i) + 1);
+            const int64_t pos = (int32_t)r0.x;
+            const uint32_t c0 = r0.z, n_cigar = r0.w;
+            const uint64_t seq = b.seq_base + r1.x;
+            /* the tile's event count doubles as the fill pointer of its region */
+            EventSink sink = make_sink(t, p, region, &tile_info[tile].count, (int32_t)r0.y, pos, seq, r1.y & 0xFFFFu,
+                                       (r1.y >> 16) & 0xFFu, r1.y >> 24);
+            WalkState w;
+            w.init(pos);
+            uint32_t bad = 0u;
+            for (uint32_t k = 0; k < n_cigar; ++k) {
+                bad = walk_op(w, __ldg(&b.cigar[c0 + k]), p.max_anchor_indel_size, sink);
+                if (bad) break;
+            }
+            if (bad) {
+                atomicMin(t.err_sv, make_err_cigar(seq, bad & 15u));
+            } else {
+                walk_finish(w, sink);
+            }
+            events += sink.n_events;
+        }
     }
     events = warp_sum(events);
     if (lane == 0 && events) atomicAdd(t.n_events, events);
@@ -497,18 +562,19 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
 cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractParams &p, const Tables &t, Event *out,
-                           uint32_t *tile_count, int sm_count, cudaStream_t st, int *launches) {
+                           TileInfo *tile_info, LongRec *long_recs, int sm_count, cudaStream_t st, int *launches) {
     if (launches) *launches = 0;
     if (b.n == 0) return cudaSuccess;
     const uint64_t n_tiles = tiles_of(b.n), n_full = b.n / EX_TILE;
     /* the pipelined kernel takes whole tiles of batches whose columns can be bulk-copied and whose reads are short
      * enough for a tile's CIGAR words to fit its stage */
-    static const bool force_simple = getenv("IPX_K1_SIMPLE") != nullptr;
+    static const bool force_simple = getenv(IPX_K1_SIMPLE") != nullptr;"
     const bool pipelined = !force_simple && n_full > 0 && n_cigar <= 8 * b.n && aligned16(b.tid) && aligned16(b.pos) &&
                            aligned16(b.flag) && aligned16(b.nh) && aligned16(b.xs) && aligned16(b.cigar_off) && aligned16(b.cigar);
     uint64_t first_simple = 0;
     if (pipelined) {
-        const size_t smem = EX_STAGES * sizeof(ExStage) + 3 * EX_STAGES * sizeof(uint64_t);
+        const size_t smem = EX_STAGES * sizeof(ExStage) + 2 * EX_STAGES * sizeof(uint64_t);
+        static const int walk_long_here = getenv(IPX_K1_SPLIT_LONG") ? 0 : 1;"
         static bool configured = false;
         if (!configured) {
             cudaError_t e = cudaFuncSetAttribute(k_extract_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -517,15 +583,22 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
         }
         const uint64_t max_blocks = (uint64_t)sm_count * 2;
         const int blocks = (int)(n_full < max_blocks ? n_full : max_blocks);
-        k_extract_tma<<<blocks, EX_THREADS, smem, st>>>(b, (uint32_t)n_cigar, p, t, out, tile_count, (uint32_t)n_full);
+        k_extract_tma<<<blocks, EX_THREADS, smem, st>>>(b, (uint32_t)n_cigar, p, t, out, tile_info, long_recs, (uint32_t)n_full,
+                                                        walk_long_here);
         if (launches) (*launches)++;
+        if (!walk_long_here) {
+            const uint64_t want = (n_full + 7) / 8;
+            const uint64_t max_long = (uint64_t)sm_count * 8;
+            k_extract_long<<<(int)(want < max_long ? want : max_long), 256, 0, st>>>(b, p, t, out, tile_info, long_recs, n_full);
+            if (launches) (*launches)++;
+        }
         first_simple = n_full;
     }
     if (first_simple < n_tiles) {
         const uint64_t todo = n_tiles - first_simple;
         const uint64_t max_blocks = (uint64_t)sm_count * 8;
         const int blocks = (int)(todo < max_blocks ? todo : max_blocks);
-        k_extract_simple<<<blocks, EXS_THREADS, 0, st>>>(b, p, t, out, tile_count, first_simple, n_tiles);
+        k_extract_simple<<<blocks, EXS_THREADS, 0, st>>>(b, p, t, out, tile_info, first_simple, n_tiles);
         if (launches) (*launches)++;
     }
     return cudaGetLastError();
@@ -565,7 +638,7 @@ __device__ __forceinline__ Probe probe_junction(const Tables &t, unsigned long l
         const JStat *s = &t.stat[h];
         unsigned long long k = *((volatile unsigned long long *)&t.keys[h]);
         uint2 a;
-        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "l"(&s->a0));
+        asm volatile(ld.volatile.global.v2.u32 {%0
         r.first = *((volatile unsigned long long *)&s->first[cls]);
         r.T = *((volatile unsigned long long *)&s->T);
         r.a0 = a.x;
@@ -598,24 +671,17 @@ __device__ __forceinline__ Probe probe_junction(const Tables &t, unsigned long l
  * lane counts its own read offset with one fire-and-forget atomic into the junction's dense offset row (or the
  * offset hash table for large offsets).  The next 32 events are already in flight while a chunk is folded. */
 template <int MODE>
-__global__ void __launch_bounds__(256, 5) k_fold(Tables t, const Event *ev, const uint32_t *cigar_off, const uint32_t *tile_count,
-                                              uint64_t n_tiles) {
+__global__ void __launch_bounds__(256, 5) k_fold(Tables t, const Event *ev, const TileInfo *tile_info, uint64_t n_tiles) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     OlogWriter olog{0ull, 0u};
-    uint32_t next_cnt = 0u, next_c0 = 0u;
-    if (warp0 < n_tiles) {
-        next_cnt = __ldg(&tile_count[warp0]);
-        next_c0 = __ldg(&cigar_off[warp0 * EX_TILE]);
-    }
+    uint2 next = make_uint2(0u, 0u);
+    if (warp0 < n_tiles) next = __ldg(reinterpret_cast<const uint2 *>(tile_info + warp0));
     for (uint64_t tile = warp0; tile < n_tiles; tile += n_warps) {
-        const uint32_t cnt = next_cnt;
-        const uint64_t base = tile_event_base(next_c0);
-        if (tile + n_warps < n_tiles) {
-            next_cnt = __ldg(&tile_count[tile + n_warps]);
-            next_c0 = __ldg(&cigar_off[(tile + n_warps) * EX_TILE]);
-        }
+        const uint32_t cnt = next.x;
+        const uint64_t base = tile_event_base(next.y);
+        if (tile + n_warps < n_tiles) next = __ldg(reinterpret_cast<const uint2 *>(tile_info + tile + n_warps));
         if (cnt == 0u) continue;
         Event nxt = load_event(ev, base + lane, (uint32_t)lane < cnt, lane);
         for (uint32_t k0 = 0; k0 < cnt; k0 += 32u) {
@@ -668,16 +734,16 @@ __global__ void __launch_bounds__(256, 5) k_fold(Tables t, const Event *ev, cons
     if (MODE != MODE_PASS1) olog_finish(t, olog);
 }
 
-void launch_fold(int mode, const Tables &t, const Event *ev, const uint32_t *cigar_off, const uint32_t *tile_count,
-                 uint64_t n_tiles, int sm_count, cudaStream_t st) {
+void launch_fold(int mode, const Tables &t, const Event *ev, const TileInfo *tile_info, uint64_t n_tiles, int sm_count,
+                 cudaStream_t st) {
     if (n_tiles == 0) return;
     const uint64_t want = (n_tiles + 7) / 8; /* 8 warps per block, one tile per warp at a time */
     const uint64_t max_blocks = (uint64_t)sm_count * 5; /* what is resident at once (__launch_bounds__(256, 5)) */
     const int blocks = (int)(want < max_blocks ? want : max_blocks);
     switch (mode) {
-        case MODE_SINGLE: k_fold<MODE_SINGLE><<<blocks, 256, 0, st>>>(t, ev, cigar_off, tile_count, n_tiles); break;
-        case MODE_PASS1: k_fold<MODE_PASS1><<<blocks, 256, 0, st>>>(t, ev, cigar_off, tile_count, n_tiles); break;
-        default: k_fold<MODE_PASS2><<<blocks, 256, 0, st>>>(t, ev, cigar_off, tile_count, n_tiles); break;
+        case MODE_SINGLE: k_fold<MODE_SINGLE><<<blocks, 256, 0, st>>>(t, ev, tile_info, n_tiles); break;
+        case MODE_PASS1: k_fold<MODE_PASS1><<<blocks, 256, 0, st>>>(t, ev, tile_info, n_tiles); break;
+        default: k_fold<MODE_PASS2><<<blocks, 256, 0, st>>>(t, ev, tile_info, n_tiles); break;
     }
 }
 
@@ -734,7 +800,7 @@ __device__ __forceinline__ int motif_fetch(const GenomeView &g, int32_t tid, uin
 }
 
 /* For every junction slot without a creation threshold yet: T = first event (stream order) whose strand class
- * passes junction_filter_check (add_junction, junctions_extractor.cc:494-502; SURVEY.md 8a "A6"). */
+ * passes junction_filter_check (add_junction, junctions_extractor.cc:494-502; SURVEY.md 8a A6"). */"
 __global__ void k_resolve_T(Tables t, GenomeView g) {
     const unsigned long long nk = *t.n_keys;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
