@@ -5,7 +5,7 @@
  *                    warp), so every record column and CIGAR word is read from HBM exactly once, coalesced, with
  *                    the latency hidden behind the previous tiles' work.  Eight consumer warps (a) classify the
  *                    tile's records and compact the live ones (process_alignment's skip test) into two lists --
- *                    CIGARs of at most three operations, which can only be aligned
+ *                    CIGARs of at most three operations, which can only be "aligned, N, aligned", and longer ones
  *                    -- then (b) walk the listed records with full warps (ipx_walk.cuh) and write each junction
  *                    event straight into the tile's private region of the event buffer.
  *  k_extract_simple  K1 for what the pipeline does not take: the last partial tile, unaligned columns, long reads.
@@ -26,7 +26,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
-#include ipx_engine.h""
+#include "ipx_engine.h"
 
 namespace ipx {
 
@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(EXS_THREADS) k_extract_simple(BatchView b, Ext
  *   producer (one lane)  TMA bulk copies of the next tile's columns and CIGAR words into a free stage of the ring;
  *                        when a stage comes back it publishes the tile's event count and resets the stage
  *   workers              walk the ring in tile order.  A tile offers two kinds of work through dispensers in its stage:
- *                        rounds" (process_alignment's skip test for 128 records and compaction of the live ones into"
- *                        the stage's lists) and, once all rounds are done, chunks" (walk 32 listed records).  In"
+ *                        "rounds" (process_alignment's skip test for 128 records and compaction of the live ones into
+ *                        the stage's lists) and, once all rounds are done, "chunks" (walk 32 listed records).  In
  *                        iteration i a worker first takes rounds of tile i+1 if its data has landed, then makes sure
  *                        tile i is classified (helping with its rounds if any are left), then takes chunks of tile i.
  *                        Classification of a tile therefore overlaps the walk of the tile before it, and a warp busy
@@ -227,35 +227,35 @@ struct __align__(128) ExStage {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile(mbarrier.init.shared::cta.b64 [%0]
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile(mbarrier.arrive.expect_tx.shared::cta.b64 _
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile(mbarrier.arrive.shared::cta.b64 _
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 /* has the phase with the given parity completed?  (the hint lets the hardware park the thread for a while) */
 __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity, uint32_t hint_ns) {
     uint32_t done;
     asm volatile(
-        {\n\t.reg .pred p;\n\t""
-        mbarrier.try_wait.parity.shared::cta.b64 p
-        selp.u32 %0
-        : =r"(done)"
-        : r"(smem_u32(bar))
-        : memory");"
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
     return done != 0u;
 }
 __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
-        {\n\t.reg .pred p;\n\t""
-        mbarrier.test_wait.parity.shared::cta.b64 p
-        selp.u32 %0
-        : =r"(done)"
-        : r"(smem_u32(bar))
-        : memory");"
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
     return done != 0u;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -263,8 +263,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 /* TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP) */
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile(cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0]
-                 : memory");"
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 /* a CIGAR word of the batch: from the stage when it was staged, else from global memory */
@@ -362,7 +363,7 @@ __device__ __forceinline__ void take_rounds(ExStage &S, int lane, LongRec *long_
     }
 }
 
-/* the short-CIGAR chunk: aligned
+/* the short-CIGAR chunk: "aligned, N, aligned" is the only shape of two or three operations that emits a junction
  * (ReadJunctionExtractor, junctions_extractor.cc:208-254,278-282) */
 __device__ __forceinline__ void walk_short(const BatchView &b, const ExtractParams &p, const Tables &t, ExStage &S, Event *region,
                                            uint32_t rl, unsigned long long &events) {
@@ -419,8 +420,8 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
             stages[s].n_lists = stages[s].next_round = stages[s].rounds_done = 0u;
             stages[s].next_short = stages[s].next_long = stages[s].region_fill = 0u;
         }
-        asm volatile(fence.mbarrier_init.release.cluster;" ::: "memory");"
-        asm volatile(fence.proxy.async.shared::cta;" ::: "memory");"
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
     const uint32_t first = blockIdx.x, stride = gridDim.x;
@@ -568,13 +569,13 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
     const uint64_t n_tiles = tiles_of(b.n), n_full = b.n / EX_TILE;
     /* the pipelined kernel takes whole tiles of batches whose columns can be bulk-copied and whose reads are short
      * enough for a tile's CIGAR words to fit its stage */
-    static const bool force_simple = getenv(IPX_K1_SIMPLE") != nullptr;"
+    static const bool force_simple = getenv("IPX_K1_SIMPLE") != nullptr;
     const bool pipelined = !force_simple && n_full > 0 && n_cigar <= 8 * b.n && aligned16(b.tid) && aligned16(b.pos) &&
                            aligned16(b.flag) && aligned16(b.nh) && aligned16(b.xs) && aligned16(b.cigar_off) && aligned16(b.cigar);
     uint64_t first_simple = 0;
     if (pipelined) {
         const size_t smem = EX_STAGES * sizeof(ExStage) + 2 * EX_STAGES * sizeof(uint64_t);
-        static const int walk_long_here = getenv(IPX_K1_SPLIT_LONG") ? 0 : 1;"
+        static const int walk_long_here = getenv("IPX_K1_SPLIT_LONG") ? 0 : 1;
         static bool configured = false;
         if (!configured) {
             cudaError_t e = cudaFuncSetAttribute(k_extract_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -638,7 +639,7 @@ __device__ __forceinline__ Probe probe_junction(const Tables &t, unsigned long l
         const JStat *s = &t.stat[h];
         unsigned long long k = *((volatile unsigned long long *)&t.keys[h]);
         uint2 a;
-        asm volatile(ld.volatile.global.v2.u32 {%0
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(a.x), "=r"(a.y) : "l"(&s->a0));
         r.first = *((volatile unsigned long long *)&s->first[cls]);
         r.T = *((volatile unsigned long long *)&s->T);
         r.a0 = a.x;
@@ -800,7 +801,7 @@ __device__ __forceinline__ int motif_fetch(const GenomeView &g, int32_t tid, uin
 }
 
 /* For every junction slot without a creation threshold yet: T = first event (stream order) whose strand class
- * passes junction_filter_check (add_junction, junctions_extractor.cc:494-502; SURVEY.md 8a A6"). */"
+ * passes junction_filter_check (add_junction, junctions_extractor.cc:494-502; SURVEY.md 8a "A6"). */
 __global__ void k_resolve_T(Tables t, GenomeView g) {
     const unsigned long long nk = *t.n_keys;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
