@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(EXS_THREADS) k_extract_simple(BatchView b, Ext
 static const int EX_STAGES = 4;
 static const int EX_WORKER_WARPS = 15;
 static const int EX_THREADS = (EX_WORKER_WARPS + 1) * 32;
+static const int EX_LOOKAHEAD = 2; /* workers classify up to this many tiles ahead of the one they walk */
 static const int EX_ROUNDS = EX_TILE / 128;
 static const int EX_CIG_CAP = 2048; /* staged CIGAR words per tile (average short-read tile: ~1500); words beyond are
                                        read from global memory */
@@ -350,6 +351,7 @@ __device__ __forceinline__ void classify_round(ExStage &S, uint32_t r, int lane,
 __device__ __forceinline__ void take_rounds(ExStage &S, int lane, LongRec *long_recs, int walk_long_here,
                                             unsigned long long &live_words) {
     for (;;) {
+        if (*((volatile uint32_t *)&S.next_round) >= (uint32_t)EX_ROUNDS) break; /* nothing left: skip the atomic */
         uint32_t r = 0u;
         if (lane == 0) r = atomicAdd(&S.next_round, 1u);
         r = __shfl_sync(0xFFFFFFFFu, r, 0);
@@ -405,6 +407,7 @@ __device__ __forceinline__ void walk_short(const BatchView &b, const ExtractPara
     }
 }
 
+template <int LOOKAHEAD>
 __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint32_t n_cigar_words, ExtractParams p, Tables t,
                                                                Event *out, TileInfo *tile_info, LongRec *long_recs,
                                                                uint32_t n_full_tiles, int walk_long_here) {
@@ -480,10 +483,13 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
     for (uint32_t it = 0; it < my_tiles; ++it) {
         const int s = (int)(it % EX_STAGES);
         ExStage &S = stages[s];
-        /* (1) rounds of the next tile, if its data is already here */
-        if (it + 1 < my_tiles) {
-            const int s1 = (int)((it + 1) % EX_STAGES);
-            if (mbar_test(&full[s1], ((it + 1) / EX_STAGES) & 1u)) take_rounds(stages[s1], lane, long_recs, walk_long_here, live_words);
+        /* (1) rounds of the tiles ahead whose data is already here, nearest first */
+#pragma unroll
+        for (uint32_t d = 1; d <= (uint32_t)LOOKAHEAD; ++d) {
+            if (it + d < my_tiles) {
+                const int s1 = (int)((it + d) % EX_STAGES);
+                if (mbar_test(&full[s1], ((it + d) / EX_STAGES) & 1u)) take_rounds(stages[s1], lane, long_recs, walk_long_here, live_words);
+            }
         }
         /* (2) this tile must be classified before it can be walked: help with what is left, then wait for the rest */
         mbar_wait(&full[s], (it / EX_STAGES) & 1u);
@@ -495,6 +501,7 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
         const uint32_t n_short = n_lists & 0xFFFFu, n_long = walk_long_here ? n_lists >> 16 : 0u;
         Event *region = out + tile_event_base(S.off[0]);
         while (n_long) {
+            if (*((volatile uint32_t *)&S.next_long) >= n_long) break;
             uint32_t c = 0u;
             if (lane == 0) c = atomicAdd(&S.next_long, 32u);
             c = __shfl_sync(0xFFFFFFFFu, c, 0);
@@ -502,6 +509,7 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
             if (c + lane < n_long) walk_record(b, p, t, S, region, S.list[EX_TILE - 1 - (c + lane)], events);
         }
         for (;;) {
+            if (*((volatile uint32_t *)&S.next_short) >= n_short) break;
             uint32_t c = 0u;
             if (lane == 0) c = atomicAdd(&S.next_short, 32u);
             c = __shfl_sync(0xFFFFFFFFu, c, 0);
@@ -576,15 +584,18 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
     if (pipelined) {
         const size_t smem = EX_STAGES * sizeof(ExStage) + 2 * EX_STAGES * sizeof(uint64_t);
         static const int walk_long_here = getenv("IPX_K1_SPLIT_LONG") ? 0 : 1;
+        static const int variant = getenv("IPX_K1_VARIANT") ? atoi(getenv("IPX_K1_VARIANT")) : EX_LOOKAHEAD;
+        typedef void (*Kernel)(BatchView, uint32_t, ExtractParams, Tables, Event *, TileInfo *, LongRec *, uint32_t, int);
+        const Kernel kernel = variant == 1 ? k_extract_tma<1> : (variant == 3 ? k_extract_tma<3> : k_extract_tma<2>);
         static bool configured = false;
         if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(k_extract_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             configured = true;
         }
         const uint64_t max_blocks = (uint64_t)sm_count * 2;
         const int blocks = (int)(n_full < max_blocks ? n_full : max_blocks);
-        k_extract_tma<<<blocks, EX_THREADS, smem, st>>>(b, (uint32_t)n_cigar, p, t, out, tile_info, long_recs, (uint32_t)n_full,
+        kernel<<<blocks, EX_THREADS, smem, st>>>(b, (uint32_t)n_cigar, p, t, out, tile_info, long_recs, (uint32_t)n_full,
                                                         walk_long_here);
         if (launches) (*launches)++;
         if (!walk_long_here) {
