@@ -351,9 +351,9 @@ __device__ __forceinline__ void classify_round(ExStage &S, uint32_t r, int lane,
 __device__ __forceinline__ void take_rounds(ExStage &S, int lane, LongRec *long_recs, int walk_long_here,
                                             unsigned long long &live_words) {
     for (;;) {
-        if (*((volatile uint32_t *)&S.next_round) >= (uint32_t)EX_ROUNDS) break; /* nothing left: skip the atomic */
         uint32_t r = 0u;
-        if (lane == 0) r = atomicAdd(&S.next_round, 1u);
+        /* (the plain read spares the atomic when nothing is left; the decision stays lane 0's, so it is warp-uniform) */
+        if (lane == 0) r = *((volatile uint32_t *)&S.next_round) >= (uint32_t)EX_ROUNDS ? 0xFFFFFFFFu : atomicAdd(&S.next_round, 1u);
         r = __shfl_sync(0xFFFFFFFFu, r, 0);
         if (r >= (uint32_t)EX_ROUNDS) break;
         classify_round(S, r, lane, long_recs, walk_long_here, live_words);
@@ -501,17 +501,15 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
         const uint32_t n_short = n_lists & 0xFFFFu, n_long = walk_long_here ? n_lists >> 16 : 0u;
         Event *region = out + tile_event_base(S.off[0]);
         while (n_long) {
-            if (*((volatile uint32_t *)&S.next_long) >= n_long) break;
             uint32_t c = 0u;
-            if (lane == 0) c = atomicAdd(&S.next_long, 32u);
+            if (lane == 0) c = *((volatile uint32_t *)&S.next_long) >= n_long ? 0xFFFFFFFFu : atomicAdd(&S.next_long, 32u);
             c = __shfl_sync(0xFFFFFFFFu, c, 0);
             if (c >= n_long) break;
             if (c + lane < n_long) walk_record(b, p, t, S, region, S.list[EX_TILE - 1 - (c + lane)], events);
         }
         for (;;) {
-            if (*((volatile uint32_t *)&S.next_short) >= n_short) break;
             uint32_t c = 0u;
-            if (lane == 0) c = atomicAdd(&S.next_short, 32u);
+            if (lane == 0) c = *((volatile uint32_t *)&S.next_short) >= n_short ? 0xFFFFFFFFu : atomicAdd(&S.next_short, 32u);
             c = __shfl_sync(0xFFFFFFFFu, c, 0);
             if (c >= n_short) break;
             if (c + lane < n_short) walk_short(b, p, t, S, region, S.list[c + lane], events);
