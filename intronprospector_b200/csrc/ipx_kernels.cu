@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(EXS_THREADS) k_extract_simple(BatchView b, Ext
 static const int EX_STAGES = 4;
 static const int EX_WORKER_WARPS = 15;
 static const int EX_THREADS = (EX_WORKER_WARPS + 1) * 32;
-static const int EX_LOOKAHEAD = 2; /* workers classify up to this many tiles ahead of the one they walk */
+static const int EX_LOOKAHEAD = 1; /* workers classify up to this many tiles ahead of the one they walk */
 static const int EX_ROUNDS = EX_TILE / 128;
 static const int EX_CIG_CAP = 2048; /* staged CIGAR words per tile (average short-read tile: ~1500); words beyond are
                                        read from global memory */
@@ -348,7 +348,12 @@ __device__ __forceinline__ void classify_round(ExStage &S, uint32_t r, int lane,
 }
 
 /* take classification rounds of a stage until none is left */
-__device__ __forceinline__ void take_rounds(ExStage &S, int lane, LongRec *long_recs, int walk_long_here,
+/* "all rounds of stage s are done": a named barrier per stage.  Every finished round arrives once (the whole warp),
+ * every worker waits once; waiting warps are parked by the hardware instead of polling. */
+static const uint32_t EX_BAR_THREADS = (EX_ROUNDS + EX_WORKER_WARPS) * 32u;
+
+template <bool NAMED>
+__device__ __forceinline__ void take_rounds(ExStage &S, int stage, int lane, LongRec *long_recs, int walk_long_here,
                                             unsigned long long &live_words) {
     for (;;) {
         uint32_t r = 0u;
@@ -358,7 +363,10 @@ __device__ __forceinline__ void take_rounds(ExStage &S, int lane, LongRec *long_
         if (r >= (uint32_t)EX_ROUNDS) break;
         classify_round(S, r, lane, long_recs, walk_long_here, live_words);
         __syncwarp();
-        if (lane == 0) {
+        if (NAMED) {
+            __threadfence_block(); /* the lists before the arrival */
+            asm volatile("bar.arrive %0, %1;" ::"r"(1u + (uint32_t)stage), "r"(EX_BAR_THREADS) : "memory");
+        } else if (lane == 0) {
             __threadfence_block(); /* the lists before the count */
             atomicAdd(&S.rounds_done, 1u);
         }
@@ -407,7 +415,7 @@ __device__ __forceinline__ void walk_short(const BatchView &b, const ExtractPara
     }
 }
 
-template <int LOOKAHEAD>
+template <int LOOKAHEAD, bool NAMED>
 __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint32_t n_cigar_words, ExtractParams p, Tables t,
                                                                Event *out, TileInfo *tile_info, LongRec *long_recs,
                                                                uint32_t n_full_tiles, int walk_long_here) {
@@ -488,14 +496,19 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
         for (uint32_t d = 1; d <= (uint32_t)LOOKAHEAD; ++d) {
             if (it + d < my_tiles) {
                 const int s1 = (int)((it + d) % EX_STAGES);
-                if (mbar_test(&full[s1], ((it + d) / EX_STAGES) & 1u)) take_rounds(stages[s1], lane, long_recs, walk_long_here, live_words);
+                if (mbar_test(&full[s1], ((it + d) / EX_STAGES) & 1u))
+                    take_rounds<NAMED>(stages[s1], s1, lane, long_recs, walk_long_here, live_words);
             }
         }
         /* (2) this tile must be classified before it can be walked: help with what is left, then wait for the rest */
         mbar_wait(&full[s], (it / EX_STAGES) & 1u);
-        take_rounds(S, lane, long_recs, walk_long_here, live_words);
-        while (*((volatile uint32_t *)&S.rounds_done) < (uint32_t)EX_ROUNDS) __nanosleep(32);
-        __threadfence_block();
+        take_rounds<NAMED>(S, s, lane, long_recs, walk_long_here, live_words);
+        if (NAMED) {
+            asm volatile("bar.sync %0, %1;" ::"r"(1u + (uint32_t)s), "r"(EX_BAR_THREADS) : "memory");
+        } else {
+            while (*((volatile uint32_t *)&S.rounds_done) < (uint32_t)EX_ROUNDS) __nanosleep(32);
+            __threadfence_block();
+        }
         /* (3) chunks of this tile: 32 listed records at a time, longest CIGARs first */
         const uint32_t n_lists = *((volatile uint32_t *)&S.n_lists);
         const uint32_t n_short = n_lists & 0xFFFFu, n_long = walk_long_here ? n_lists >> 16 : 0u;
@@ -584,7 +597,7 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
         static const int walk_long_here = getenv("IPX_K1_SPLIT_LONG") ? 0 : 1;
         static const int variant = getenv("IPX_K1_VARIANT") ? atoi(getenv("IPX_K1_VARIANT")) : EX_LOOKAHEAD;
         typedef void (*Kernel)(BatchView, uint32_t, ExtractParams, Tables, Event *, TileInfo *, LongRec *, uint32_t, int);
-        const Kernel kernel = variant == 1 ? k_extract_tma<1> : (variant == 3 ? k_extract_tma<3> : k_extract_tma<2>);
+        const Kernel kernel = variant == 10 ? k_extract_tma<1, false> : (variant == 2 ? k_extract_tma<2, true> : k_extract_tma<1, true>);
         static bool configured = false;
         if (!configured) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
