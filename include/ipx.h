@@ -76,6 +76,9 @@ typedef struct ipx_params {
     uint64_t table_capacity;        /* junction hash slots (power of two; at most half may be used), 0 = default 4 M */
     uint64_t hist_capacity;         /* entries of the read-offset log (8 bytes each; one per read whose offset the
                                        256-wide dense rows do not take), 0 = default 64 M */
+    int32_t deferred_counting;      /* multi-GPU runs with the canon filter: ipx_push_batch only records which reads could
+                                       create each junction and keeps the batch's junction events on the device; they are
+                                       counted by ipx_count_deferred once the creation thresholds of all ranks are known */
 } ipx_params;
 
 /* One batch of decoded alignment records in stream order, structure-of-arrays.
@@ -120,6 +123,9 @@ typedef struct ipx_table {
     const int32_t *missing_targets; /* [n_missing_targets] targets with no genome sequence that were skipped
                                        under -S, in first-miss stream order (junctions_extractor.cc:411-417) */
     uint64_t n_missing_targets;
+    const uint64_t *creation_seq;  /* [n] stream position of the read that created the junction (record index << 20 |
+                                      ordinal of the junction within the read): sjN numbering is the rank of this value,
+                                      which lets per-GPU tables be renumbered globally.  NULL from ipx_merge_rows_fold. */
 } ipx_table;
 
 /* Device-time breakdown (milliseconds, CUDA events on the library's stream) and unit counts
@@ -197,6 +203,9 @@ int ipx_finalize_device(ipx_handle *h);
  * ipx_finalize_device() first if needed.  sjN numbering continues across flushes (ijunc_). */
 int ipx_flush(ipx_handle *h, ipx_table **out);
 void ipx_table_free(ipx_table *t);
+/* Replace the sjN numbers of a table (multi-GPU: ranks of creation_seq over all GPUs' tables); ijunc has n_junctions
+ * entries. */
+int ipx_table_set_ijunc(ipx_table *t, const uint32_t *ijunc);
 /* clear() alone (junctions_extractor.hh:222-224): drop everything accumulated so far, keep sjN numbering */
 int ipx_clear(ipx_handle *h);
 
@@ -218,6 +227,18 @@ int ipx_partial_sizes(ipx_handle *h, int32_t n_parts, const int32_t *split_tid, 
 int ipx_partial_export(ipx_handle *h, void *dev_junction_rows, void *dev_hist_rows);
 int ipx_partial_import(ipx_handle *h, const void *dev_junction_rows, uint64_t n_junction_rows,
                        const void *dev_hist_rows, uint64_t n_hist_rows);
+
+/* Multi-GPU with the canon filter.  Which event creates a junction (add_junction, junctions_extractor.cc:488-506) depends
+ * on every earlier read of the whole stream, so with ipx_params.deferred_counting the ranks first agree on it:
+ *  ipx_thresholds_rows    settle this rank's local creation thresholds; number and size of the rows to exchange
+ *  ipx_thresholds_export  one row per junction key seen here (key + threshold) into a caller-provided DEVICE buffer
+ *  ipx_thresholds_import  rows of any rank (DEVICE buffer): a key known here takes the earlier threshold
+ *  ipx_count_deferred     count the kept junction events against the agreed thresholds; afterwards the
+ *                         ipx_partial_* exchange and ipx_flush work as without the filter */
+int ipx_thresholds_rows(ipx_handle *h, uint64_t *n_rows, uint32_t *row_bytes);
+int ipx_thresholds_export(ipx_handle *h, void *dev_rows);
+int ipx_thresholds_import(ipx_handle *h, const void *dev_rows, uint64_t n_rows);
+int ipx_count_deferred(ipx_handle *h);
 
 /* Formatters (junctions.cc:162-268).  Rows [begin, end) of the table are taken in key order, sorted as
  * the reference sorts them (sort_by_anchors for IPX_FMT_JUNCTION_BED, sort_by_introns otherwise,

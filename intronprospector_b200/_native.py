@@ -36,6 +36,7 @@ class Params(C.Structure):
         ("stream", C.c_void_p),
         ("table_capacity", C.c_uint64),
         ("hist_capacity", C.c_uint64),
+        ("deferred_counting", C.c_int32),
     ]
 
 
@@ -76,6 +77,7 @@ class TableStruct(C.Structure):
         ("error_text", C.c_char * 256),
         ("missing_targets", C.POINTER(C.c_int32)),
         ("n_missing_targets", C.c_uint64),
+        ("creation_seq", C.POINTER(C.c_uint64)),
     ]
 
 
@@ -127,7 +129,8 @@ ABI_SYMBOLS = [
     "ipx_set_targets", "ipx_set_genome", "ipx_push_batch", "ipx_push_batch_device", "ipx_finalize_device",
     "ipx_flush", "ipx_table_free", "ipx_clear", "ipx_merge_rows_fold", "ipx_partial_row_bytes", "ipx_partial_sizes",
     "ipx_partial_export", "ipx_partial_import", "ipx_format", "ipx_format_tsv_header", "ipx_text_free",
-    "ipx_get_timings", "ipx_reset_timings", "ipx_stream",
+    "ipx_get_timings", "ipx_reset_timings", "ipx_stream", "ipx_thresholds_rows", "ipx_thresholds_export",
+    "ipx_thresholds_import", "ipx_count_deferred", "ipx_table_set_ijunc",
 ]
 IO_SYMBOLS = [
     "ipxio_last_error", "ipxio_open", "ipxio_close", "ipxio_n_targets", "ipxio_target_name", "ipxio_read_batch",
@@ -171,6 +174,11 @@ def _bind(lib):
     lib.ipx_partial_sizes.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.ipx_partial_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ipx_partial_import.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    lib.ipx_thresholds_rows.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+    lib.ipx_thresholds_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ipx_thresholds_import.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.ipx_count_deferred.argtypes = [C.c_void_p]
+    lib.ipx_table_set_ijunc.argtypes = [C.POINTER(TableStruct), C.c_void_p]
 
 
 def load_library(path=None):
@@ -257,6 +265,7 @@ class Table:
         self.error_tid = int(t.error_tid)
         self.error_text = t.error_text.decode(errors="replace")
         self.missing_targets = _arr(t.missing_targets, int(t.n_missing_targets), np.int32)
+        self.creation_seq = _arr(t.creation_seq, n, np.uint64) if t.creation_seq else np.zeros(0, np.uint64)
         # text is produced on demand by the library's own formatter, so the native table stays alive until close()
         self._lib, self._tp, self._free = lib, tp, free
         self._cnames = (C.c_char_p * max(1, len(names)))(*[s.encode() for s in names])
@@ -274,6 +283,16 @@ class Table:
             self._text[key] = C.string_at(txt.data, txt.len) if txt.len else b""
             self._lib.ipx_text_free(C.byref(txt))
         return self._text[key]
+
+    def set_ijunc(self, ijunc):
+        """Renumber the junctions (multi-GPU: global ranks of creation_seq)."""
+        a = np.ascontiguousarray(ijunc, dtype=np.uint32)
+        if a.shape[0] != self.n or self._tp is None:
+            raise IpxError("set_ijunc: wrong length or closed table")
+        if self._lib.ipx_table_set_ijunc(self._tp, a.ctypes.data) != IPX_OK:
+            raise IpxError("ipx_table_set_ijunc failed")
+        self.ijunc = a.copy()
+        self._text = {}
 
     def close(self):
         if self._tp is not None:
@@ -312,6 +331,7 @@ class Engine:
         p.stream = stream
         p.table_capacity = kw.pop("table_capacity", 0)
         p.hist_capacity = kw.pop("hist_capacity", 0)
+        p.deferred_counting = int(kw.pop("deferred_counting", False))
         if kw:
             raise TypeError("unknown parameters: %s" % sorted(kw))
         self.params = p
@@ -395,6 +415,39 @@ class Engine:
         self.lib.ipx_text_free(C.byref(log))
         self._check(rc)
         return Table(self.lib, tp, self.names, self.lib.ipx_table_free), text
+
+    # ---- multi-GPU exchange (see sharded.py) ----
+    def partial_row_bytes(self):
+        jb, hb = C.c_uint32(), C.c_uint32()
+        self._check(self.lib.ipx_partial_row_bytes(C.byref(jb), C.byref(hb)))
+        return jb.value, hb.value
+
+    def partial_sizes(self, n_parts, split_tid, split_start):
+        st = (C.c_int32 * max(1, n_parts - 1))(*split_tid)
+        ss = (C.c_uint32 * max(1, n_parts - 1))(*split_start)
+        jr, hr = (C.c_uint64 * n_parts)(), (C.c_uint64 * n_parts)()
+        self._check(self.lib.ipx_partial_sizes(self.h, n_parts, st, ss, jr, hr))
+        return [int(x) for x in jr], [int(x) for x in hr]
+
+    def partial_export(self, dev_junction_rows, dev_hist_rows):
+        self._check(self.lib.ipx_partial_export(self.h, dev_junction_rows, dev_hist_rows))
+
+    def partial_import(self, dev_junction_rows, n_junction_rows, dev_hist_rows, n_hist_rows):
+        self._check(self.lib.ipx_partial_import(self.h, dev_junction_rows, n_junction_rows, dev_hist_rows, n_hist_rows))
+
+    def thresholds_rows(self):
+        n, b = C.c_uint64(), C.c_uint32()
+        self._check(self.lib.ipx_thresholds_rows(self.h, C.byref(n), C.byref(b)))
+        return int(n.value), int(b.value)
+
+    def thresholds_export(self, dev_rows):
+        self._check(self.lib.ipx_thresholds_export(self.h, dev_rows))
+
+    def thresholds_import(self, dev_rows, n_rows):
+        self._check(self.lib.ipx_thresholds_import(self.h, dev_rows, n_rows))
+
+    def count_deferred(self):
+        self._check(self.lib.ipx_count_deferred(self.h))
 
     def timings(self):
         t = Timings()

@@ -30,6 +30,7 @@ struct HostTable {
     std::vector<char> strand, sites;
     std::vector<uint64_t> counts, hist_off;
     std::vector<float> conf;
+    std::vector<uint64_t> creation;
     void bind() {
         t.n_junctions = chrom.size();
         t.chrom = chrom.data();
@@ -47,6 +48,7 @@ struct HostTable {
         t.n_hist = hist_cnt.size();
         t.missing_targets = missing.data();
         t.n_missing_targets = missing.size();
+        t.creation_seq = creation.empty() ? nullptr : creation.data();
     }
 };
 
@@ -115,6 +117,13 @@ struct ipx_handle {
     DeviceBuf ev_buf;   /* junction events of the batch in flight (K1 -> K2), one region per tile */
     DeviceBuf tile_cnt; /* TileInfo per tile */
     DeviceBuf long_buf; /* LongRec regions (records handed from the pipelined kernel to k_extract_long) */
+    /* deferred counting (multi-GPU with the canon filter): the events of every batch pushed since the last count */
+    struct Deferred {
+        void *events;
+        void *tile_info;
+        uint64_t n_tiles;
+    };
+    std::vector<Deferred> deferred;
     uint64_t seq_hi = 0; /* one past the largest record stream index pushed so far */
 
     /* finalize */
@@ -183,6 +192,14 @@ void drain(StageTimer &t) {
         cudaEventDestroy(s.second);
     }
     t.spans.clear();
+}
+
+void drop_deferred(ipx_handle *h) {
+    for (auto &d : h->deferred) {
+        cudaFreeAsync(d.events, h->stream);
+        cudaFreeAsync(d.tile_info, h->stream);
+    }
+    h->deferred.clear();
 }
 
 int bits_for(uint32_t v) {
@@ -308,10 +325,33 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
     if (b.n >> 36) return fail(h, IPX_ERR_ARG, "batch too large");
     /* event buffer for the worst case: every emitted candidate consumes one N op and a following aligned op */
     const uint64_t ev_bound = n_cigar / 2 + 1;
-    CU(h, h->ev_buf.reserve(ev_bound * sizeof(Event), h->stream));
     const uint64_t n_tiles = tiles_of(b.n);
-    CU(h, h->tile_cnt.reserve((n_tiles + 1) * sizeof(TileInfo), h->stream));
     CU(h, h->long_buf.reserve((n_cigar / 4 + 2) * sizeof(LongRec), h->stream));
+    if (h->params.deferred_counting && two_pass(h)) {
+        /* K1 and the first-seen pass only; the events stay on the device until ipx_count_deferred */
+        ipx_handle::Deferred d{nullptr, nullptr, n_tiles};
+        CU(h, cudaMallocAsync(&d.events, ev_bound * sizeof(Event), h->stream));
+        CU(h, cudaMallocAsync(&d.tile_info, (n_tiles + 1) * sizeof(TileInfo), h->stream));
+        h->deferred.push_back(d);
+        {
+            Span s(h, &h->tm_extract, 0);
+            int launched = 0;
+            CU(h, launch_extract(b, n_cigar, h->xp, h->tab, (Event *)d.events, (TileInfo *)d.tile_info, (LongRec *)h->long_buf.p,
+                                 h->sm_count, h->stream, &launched));
+            h->tm_extract.launches += (uint64_t)launched;
+        }
+        {
+            Span s(h, &h->tm_aggregate, 1);
+            launch_fold(MODE_PASS1, h->tab, (const Event *)d.events, (const TileInfo *)d.tile_info, n_tiles, h->sm_count, h->stream);
+        }
+        CU(h, cudaGetLastError());
+        h->totals.records += b.n;
+        h->seq_hi = std::max<uint64_t>(h->seq_hi, b.seq_base + b.n);
+        h->dirty = true;
+        return IPX_OK;
+    }
+    CU(h, h->ev_buf.reserve(ev_bound * sizeof(Event), h->stream));
+    CU(h, h->tile_cnt.reserve((n_tiles + 1) * sizeof(TileInfo), h->stream));
     TileInfo *tile_count = (TileInfo *)h->tile_cnt.p;
     const Event *events = (const Event *)h->ev_buf.p;
     {
@@ -407,6 +447,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     cudaStreamSynchronize(h->stream);
     drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
     if (h->finalized) free_device_table(h->dt, h->stream);
+    drop_deferred(h);
     cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.olog); cudaFree(h->tab.slot_list); cudaFree(h->tab.dense);
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq);
     free_genome(h);
@@ -497,6 +538,7 @@ extern "C" int ipx_finalize_device(ipx_handle *h) {
     if (!h) return IPX_ERR_ARG;
     cudaSetDevice(h->device);
     if (h->finalized) return IPX_OK;
+    if (!h->deferred.empty()) return fail(h, IPX_ERR_STATE, "junction events are waiting to be counted: call ipx_count_deferred first");
     if (h->targets.empty()) return fail(h, IPX_ERR_STATE, "ipx_set_targets must be called first");
     int rc = alloc_tables(h);
     if (rc) return rc;
@@ -625,6 +667,8 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     for (uint64_t i = 0; i < n; i++) ht->ijunc[i] += h->ijunc_base;
     h->ijunc_base += (uint32_t)n;
     ht->conf.resize(n);
+    ht->creation.resize(n);
+    for (uint64_t i = 0; i < n; i++) ht->creation[i] = T[i] >> 8;
     ht->bind();
     compute_confidences(n, ht->counts.data(), ht->hist_off.data(), ht->hist_cnt.data(), ht->conf.data());
     /* missing-genome warnings in first-miss order (junctions_extractor.cc:411-417) */
@@ -669,7 +713,16 @@ extern "C" int ipx_clear(ipx_handle *h) {
         launch_clear_tables(h->tab, h->stream);
         CU(h, cudaGetLastError());
     }
+    drop_deferred(h);
     h->dirty = false;
+    return IPX_OK;
+}
+
+extern "C" int ipx_table_set_ijunc(ipx_table *t, const uint32_t *ijunc) {
+    if (!t || (t->n_junctions && !ijunc)) return IPX_ERR_ARG;
+    HostTable *ht = reinterpret_cast<HostTable *>(t);
+    ht->ijunc.assign(ijunc, ijunc + t->n_junctions);
+    ht->bind();
     return IPX_OK;
 }
 
@@ -763,7 +816,9 @@ extern "C" int ipx_partial_sizes(ipx_handle *h, int32_t n_parts, const int32_t *
                                  uint64_t *junction_rows, uint64_t *hist_rows) {
     if (!h || n_parts < 1 || !junction_rows || !hist_rows) return IPX_ERR_ARG;
     cudaSetDevice(h->device);
-    if (two_pass(h)) return fail(h, IPX_ERR_STATE, "multi-GPU exchange with the canon filter is not implemented yet");
+    if (two_pass(h) && !h->params.deferred_counting)
+        return fail(h, IPX_ERR_STATE, "multi-GPU exchange with the canon filter needs ipx_params.deferred_counting");
+    if (!h->deferred.empty()) return fail(h, IPX_ERR_STATE, "call ipx_count_deferred before the exchange");
     if (!h->finalized) {
         h->keep_export = true;
         int rc = ipx_finalize_device(h);
@@ -836,6 +891,61 @@ extern "C" int ipx_partial_import(ipx_handle *h, const void *dev_junction_rows, 
     }
     CU(h, cudaGetLastError());
     h->dirty = true;
+    return IPX_OK;
+}
+
+/* ------------------------------------------------------------------ multi-GPU with the canon filter */
+extern "C" int ipx_thresholds_rows(ipx_handle *h, uint64_t *n_rows, uint32_t *row_bytes) {
+    if (!h || !n_rows) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (row_bytes) *row_bytes = (uint32_t)sizeof(ThresholdRow);
+    *n_rows = 0;
+    if (h->targets.empty()) return fail(h, IPX_ERR_STATE, "ipx_set_targets must be called first");
+    int rc = alloc_tables(h);
+    if (rc) return rc;
+    {
+        Span s(h, &h->tm_motif, 1);
+        launch_resolve_T(h->tab, genome_view(h), h->stream);
+    }
+    unsigned long long nk = 0;
+    CU(h, cudaMemcpyAsync(&nk, h->tab.n_keys, sizeof(nk), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    *n_rows = nk;
+    return IPX_OK;
+}
+
+extern "C" int ipx_thresholds_export(ipx_handle *h, void *dev_rows) {
+    if (!h || !dev_rows) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (!h->tables_ready) return fail(h, IPX_ERR_STATE, "call ipx_thresholds_rows first");
+    unsigned long long nk = 0;
+    CU(h, cudaMemcpyAsync(&nk, h->tab.n_keys, sizeof(nk), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    launch_export_thresholds(h->tab, (ThresholdRow *)dev_rows, nk, h->stream);
+    CU(h, cudaGetLastError());
+    return IPX_OK;
+}
+
+extern "C" int ipx_thresholds_import(ipx_handle *h, const void *dev_rows, uint64_t n_rows) {
+    if (!h || (n_rows && !dev_rows)) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    int rc = alloc_tables(h);
+    if (rc) return rc;
+    launch_import_thresholds(h->tab, (const ThresholdRow *)dev_rows, n_rows, h->stream);
+    CU(h, cudaGetLastError());
+    return IPX_OK;
+}
+
+extern "C" int ipx_count_deferred(ipx_handle *h) {
+    if (!h) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (h->finalized) return fail(h, IPX_ERR_STATE, "table already finalized");
+    for (auto &d : h->deferred) {
+        Span s(h, &h->tm_aggregate, 1);
+        launch_fold(MODE_PASS2, h->tab, (const Event *)d.events, (const TileInfo *)d.tile_info, d.n_tiles, h->sm_count, h->stream);
+    }
+    CU(h, cudaGetLastError());
+    drop_deferred(h);
     return IPX_OK;
 }
 

@@ -63,6 +63,14 @@ struct HistRow {
     uint32_t pad;
 };
 
+/* a junction key and its creation threshold, exchanged between ranks (ipx_thresholds_export / _import) */
+struct ThresholdRow {
+    int32_t tid;
+    uint32_t i0, i1;
+    uint32_t pad;
+    unsigned long long T; /* EMPTY64 = no read of this rank may create the junction */
+};
+
 enum ExtractMode { MODE_SINGLE = 0, MODE_PASS1 = 1, MODE_PASS2 = 2 };
 
 /* K1 works on tiles of EX_TILE consecutive records.  The events of tile i go to a private region of the event
@@ -101,6 +109,8 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
 void launch_fold(int mode, const Tables &t, const Event *ev, const TileInfo *tile_info, uint64_t n_tiles, int sm_count,
                  cudaStream_t st);
 void launch_resolve_T(const Tables &t, const GenomeView &g, cudaStream_t st);
+void launch_export_thresholds(const Tables &t, ThresholdRow *rows, uint64_t n, cudaStream_t st);
+void launch_import_thresholds(const Tables &t, const ThresholdRow *rows, uint64_t n, cudaStream_t st);
 void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh,
                         cudaStream_t st);
 

@@ -1291,6 +1291,37 @@ __global__ void k_import_hist_rows(Tables t, const HistRow *hr, uint64_t n) {
     olog_finish(t, olog);
 }
 
+__global__ void k_export_thresholds(Tables t, ThresholdRow *rows, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t slot = t.slot_list[i];
+    const unsigned long long key = t.keys[slot];
+    ThresholdRow r;
+    r.tid = key_tid(t.kl, key);
+    r.i0 = key_start(t.kl, key);
+    r.i1 = r.i0 + key_len(t.kl, key);
+    r.pad = 0u;
+    r.T = t.stat[slot].T;
+    rows[i] = r;
+}
+
+/* a key known here takes the earliest threshold any rank found (its own included) */
+__global__ void k_import_thresholds(Tables t, const ThresholdRow *rows, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ThresholdRow r = rows[i];
+    if (r.T == EMPTY64) return;
+    const uint64_t slot = junction_find(t, make_key(t.kl, r.tid, r.i0, r.i1));
+    if (slot <= t.cap_mask) atomicMin(&t.stat[slot].T, r.T);
+}
+
+void launch_export_thresholds(const Tables &t, ThresholdRow *rows, uint64_t n, cudaStream_t st) {
+    if (n) k_export_thresholds<<<blocks_for(n, 256), 256, 0, st>>>(t, rows, n);
+}
+void launch_import_thresholds(const Tables &t, const ThresholdRow *rows, uint64_t n, cudaStream_t st) {
+    if (n) k_import_thresholds<<<blocks_for(n, 256), 256, 0, st>>>(t, rows, n);
+}
+
 void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh,
                         cudaStream_t st) {
     if (nj) k_import_junction_rows<<<blocks_for(nj, 256), 256, 0, st>>>(t, jr, nj);

@@ -1,0 +1,142 @@
+"""Multi-GPU plumbing of the junction-extraction path: one process (one ipx_handle) per GPU.
+
+The record stream is cut into contiguous, ordered shards (global stream indexes preserved through ipx_batch.seq_base).
+Every rank extracts and reduces its shard locally; partial junction rows and read-offset rows are then exchanged by
+key range with ONE all-to-all and folded by the owning rank.  With the canon filter the ranks first agree
+on each junction's creating event (an all-gather of J-sized threshold rows) and count their kept events against it.
+Payloads are J-sized (MBs), so the exchange is latency-, not bandwidth-bound.
+
+The functions come in two flavours that share everything but the transport:
+  *_dist    torch.distributed (NCCL on GPUs; the byte routing also runs over gloo on CPU tensors in the tests)
+  *_local   several handles in one process (tests that emulate ranks on one GPU)
+This module is plumbing: no junction arithmetic happens here.
+"""
+import numpy as np
+import torch
+
+
+def key_splitters(names, n_parts):
+    """Contig-aligned splitters of the key space, which is ordered by chromosome NAME (std::string::operator<), start,
+    end: part p owns the names ranked [p*n/n_parts, (p+1)*n/n_parts).  Returns (split_tid, split_start): the first key of
+    parts 1 .. n_parts-1."""
+    order = sorted(range(len(names)), key=lambda i: names[i].encode())
+    n = len(names)
+    split_tid = []
+    for p in range(1, n_parts):
+        k = min(n - 1, (n * p) // n_parts) if n else 0
+        split_tid.append(order[k] if n else 0)
+    return split_tid, [0] * (n_parts - 1)
+
+
+def _byte_tensor(n_bytes, device):
+    return torch.empty(max(1, n_bytes), dtype=torch.uint8, device=device)
+
+
+def export_partials(eng, names, n_parts, device):
+    """Finalize the local table and pack its rows destination-major.  Returns ((junction bytes, bytes per part),
+    (offset-row bytes, bytes per part)); the local table is empty afterwards."""
+    split_tid, split_start = key_splitters(names, n_parts)
+    jrows, hrows = eng.partial_sizes(n_parts, split_tid, split_start)
+    jb, hb = eng.partial_row_bytes()
+    send_j = _byte_tensor(sum(jrows) * jb, device)
+    send_h = _byte_tensor(sum(hrows) * hb, device)
+    eng.partial_export(send_j.data_ptr(), send_h.data_ptr())
+    return (send_j, [x * jb for x in jrows]), (send_h, [x * hb for x in hrows])
+
+
+def import_partials(eng, recv_j, recv_h):
+    jb, hb = eng.partial_row_bytes()
+    eng.partial_import(recv_j.data_ptr(), recv_j.numel() // jb if recv_j.numel() >= jb else 0,
+                       recv_h.data_ptr(), recv_h.numel() // hb if recv_h.numel() >= hb else 0)
+
+
+def all_to_all_bytes(send, send_counts, group=None):
+    """Variable-size all-to-all of a uint8 tensor laid out destination-major.  Returns (received bytes in source-rank
+    order, bytes per source)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    counts = torch.tensor(send_counts, dtype=torch.int64, device=send.device)
+    recv_counts = torch.empty_like(counts)
+    dist.all_to_all_single(recv_counts, counts, group=group)
+    rc = [int(x) for x in recv_counts.cpu()]
+    recv = torch.empty(max(1, sum(rc)), dtype=torch.uint8, device=send.device)
+    assert len(send_counts) == world
+    dist.all_to_all_single(recv[:sum(rc)], send[:sum(send_counts)], rc, list(send_counts), group=group)
+    return recv[:sum(rc)], rc
+
+
+def exchange_dist(eng, names, device, group=None):
+    """One key-range exchange over torch.distributed; returns the bytes this rank sent + received."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    (send_j, cj), (send_h, ch) = export_partials(eng, names, world, device)
+    recv_j, rj = all_to_all_bytes(send_j, cj, group)
+    recv_h, rh = all_to_all_bytes(send_h, ch, group)
+    import_partials(eng, recv_j, recv_h)
+    return sum(cj) + sum(ch) + sum(rj) + sum(rh)
+
+
+def exchange_local(engines, names, device):
+    """The same exchange among handles of one process (rank = position in `engines`)."""
+    world = len(engines)
+    exports = [export_partials(e, names, world, device) for e in engines]
+    moved = 0
+    for dst, eng in enumerate(engines):
+        pieces_j, pieces_h = [], []
+        for src in range(world):
+            (sj, cj), (sh, ch) = exports[src]
+            oj, oh = sum(cj[:dst]), sum(ch[:dst])
+            pieces_j.append(sj[oj:oj + cj[dst]])
+            pieces_h.append(sh[oh:oh + ch[dst]])
+        rj, rh = torch.cat(pieces_j), torch.cat(pieces_h)
+        moved += rj.numel() + rh.numel()
+        import_partials(eng, rj, rh)
+    return moved
+
+
+def _export_thresholds(eng, device):
+    n, row_bytes = eng.thresholds_rows()
+    rows = _byte_tensor(n * row_bytes, device)
+    eng.thresholds_export(rows.data_ptr())
+    return rows[:n * row_bytes], row_bytes
+
+
+def agree_thresholds_dist(eng, device, group=None):
+    """Canon filter: every rank learns the earliest creating event of each junction it has seen, then counts the
+    junction events it kept (ipx_params.deferred_counting) against it."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rows, row_bytes = _export_thresholds(eng, device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([rows.numel()], dtype=torch.int64, device=device), group=group)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(1, max(sizes))
+    padded = torch.zeros(cap, dtype=torch.uint8, device=device)
+    padded[:rows.numel()] = rows
+    gathered = [torch.empty(cap, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)
+    for r in range(world):
+        if r != dist.get_rank(group) and sizes[r]:
+            eng.thresholds_import(gathered[r].data_ptr(), sizes[r] // row_bytes)
+    torch.cuda.current_stream(device).synchronize() if device.type == "cuda" else None
+    eng.count_deferred()
+    return sum(sizes)
+
+
+def agree_thresholds_local(engines, device):
+    exported = [_export_thresholds(e, device) for e in engines]
+    for i, eng in enumerate(engines):
+        for j, (rows, row_bytes) in enumerate(exported):
+            if j != i and rows.numel():
+                eng.thresholds_import(rows.data_ptr(), rows.numel() // row_bytes)
+    for eng in engines:
+        eng.count_deferred()
+
+
+def global_numbering(creation_seqs):
+    """sjN over several tables: the rank of every junction's creation_seq among all of them (creation_seq values are
+    global stream positions, so they are distinct).  Takes and returns one array per table."""
+    if not creation_seqs:
+        return []
+    allv = np.sort(np.concatenate([np.asarray(c, dtype=np.uint64) for c in creation_seqs]))
+    return [np.searchsorted(allv, np.asarray(c, dtype=np.uint64)).astype(np.uint32) for c in creation_seqs]
