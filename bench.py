@@ -44,6 +44,16 @@ REF_BIN = os.path.join(REPO, "oracle", "_ref", "intronProspector")
 HTS_TOOL = os.path.join(REPO, "oracle", "_ref", "hts_tool")
 
 
+# Libraries (NCCL, torchrun banners) may print to stdout; the contract is ONE JSON line there.  Everything this process
+# prints goes to stderr from here on, and emit() alone writes to the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -149,7 +159,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     if not os.path.exists(REF_BIN):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/intronProspector has not been built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/intronProspector has not been built"})
         return 0
     from intronprospector_b200.synth import SHORT_UNSTRANDED, Synth
     cores = min(os.cpu_count() or 1, 32)
@@ -185,7 +195,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -207,7 +217,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from intronprospector_b200 import _native
+    from intronprospector_b200 import _native, sharded
     from intronprospector_b200.synth import SHORT_UNSTRANDED, Synth
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -251,33 +261,10 @@ def main():
     devc = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     torch.cuda.synchronize()
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
-    lib = eng.lib
-    jb, hb = C.c_uint32(), C.c_uint32()
-    lib.ipx_partial_row_bytes(C.byref(jb), C.byref(hb))
 
     def exchange():
         """key-range all-to-all of the partial tables (contig-aligned splitters), then fold by the owner"""
-        n_t = len(names)
-        by_name = sorted(range(n_t), key=lambda i: names[i].encode())  # key order is chromosome-name order
-        split_tid = (C.c_int32 * max(1, world - 1))(*[by_name[(n_t * (p + 1)) // world] for p in range(world - 1)])
-        split_start = (C.c_uint32 * max(1, world - 1))(*[0] * (world - 1))
-        jrows, hrows = (C.c_uint64 * world)(), (C.c_uint64 * world)()
-        eng._check(lib.ipx_partial_sizes(eng.h, world, split_tid, split_start, jrows, hrows))
-        js, hs = [int(x) for x in jrows], [int(x) for x in hrows]
-        send_j = torch.empty(max(1, sum(js)) * jb.value, dtype=torch.uint8, device=dev)
-        send_h = torch.empty(max(1, sum(hs)) * hb.value, dtype=torch.uint8, device=dev)
-        eng._check(lib.ipx_partial_export(eng.h, send_j.data_ptr(), send_h.data_ptr()))
-        sizes = torch.tensor([js, hs], dtype=torch.int64, device=dev)
-        recv_sizes = torch.empty_like(sizes)
-        dist.all_to_all_single(recv_sizes.view(-1), sizes.t().contiguous().view(-1))
-        rs = recv_sizes.view(world, 2).cpu()
-        rj, rh = [int(x) for x in rs[:, 0]], [int(x) for x in rs[:, 1]]
-        recv_j = torch.empty(max(1, sum(rj)) * jb.value, dtype=torch.uint8, device=dev)
-        recv_h = torch.empty(max(1, sum(rh)) * hb.value, dtype=torch.uint8, device=dev)
-        dist.all_to_all_single(recv_j[:sum(rj) * jb.value], send_j[:sum(js) * jb.value], [x * jb.value for x in rj], [x * jb.value for x in js])
-        dist.all_to_all_single(recv_h[:sum(rh) * hb.value], send_h[:sum(hs) * hb.value], [x * hb.value for x in rh], [x * hb.value for x in hs])
-        eng._check(lib.ipx_partial_import(eng.h, recv_j.data_ptr(), sum(rj), recv_h.data_ptr(), sum(rh)))
-        return (sum(js) + sum(rj)) * jb.value + (sum(hs) + sum(rh)) * hb.value
+        return sharded.exchange_dist(eng, names, dev)
 
     def device_step():
         eng.clear()
@@ -375,7 +362,7 @@ def main():
             "cpu_baseline": cpu_line,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -124,6 +124,12 @@ struct ipx_handle {
         uint64_t n_tiles;
     };
     std::vector<Deferred> deferred;
+    /* key-range export in flight (ipx_partial_sizes -> ipx_partial_export) */
+    Splitters export_split{};
+    unsigned long long *d_export = nullptr; /* [2 * MAX_PARTS] counts, then cursors */
+    unsigned long long export_counts[2 * MAX_PARTS] = {};
+    uint64_t export_keys = 0, export_olog = 0;
+    bool export_ready = false;
     uint64_t seq_hi = 0; /* one past the largest record stream index pushed so far */
 
     /* finalize */
@@ -449,7 +455,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     if (h->finalized) free_device_table(h->dt, h->stream);
     drop_deferred(h);
     cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.olog); cudaFree(h->tab.slot_list); cudaFree(h->tab.dense);
-    cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq);
+    cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq); cudaFree(h->d_export);
     free_genome(h);
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();
     h->s_off.release(); h->s_cig.release(); h->ev_buf.release(); h->tile_cnt.release(); h->long_buf.release();
@@ -814,66 +820,87 @@ extern "C" int ipx_partial_row_bytes(uint32_t *jb, uint32_t *hb) {
 
 extern "C" int ipx_partial_sizes(ipx_handle *h, int32_t n_parts, const int32_t *split_tid, const uint32_t *split_start,
                                  uint64_t *junction_rows, uint64_t *hist_rows) {
-    if (!h || n_parts < 1 || !junction_rows || !hist_rows) return IPX_ERR_ARG;
+    if (!h || n_parts < 1 || n_parts > MAX_PARTS || !junction_rows || !hist_rows) return IPX_ERR_ARG;
     cudaSetDevice(h->device);
     if (two_pass(h) && !h->params.deferred_counting)
         return fail(h, IPX_ERR_STATE, "multi-GPU exchange with the canon filter needs ipx_params.deferred_counting");
     if (!h->deferred.empty()) return fail(h, IPX_ERR_STATE, "call ipx_count_deferred before the exchange");
-    if (!h->finalized) {
-        h->keep_export = true;
-        int rc = ipx_finalize_device(h);
-        if (rc) return rc;
-    } else if (!h->dt.slot) {
-        return fail(h, IPX_ERR_STATE, "ipx_partial_sizes must be the call that finalizes the table");
-    }
-    const uint64_t n = h->dt.n;
-    std::vector<int32_t> chrom(n);
-    std::vector<uint32_t> i0(n);
-    std::vector<unsigned long long> hoff(n + 1);
-    if (n) {
-        CU(h, cudaMemcpy(chrom.data(), h->dt.chrom, n * 4, cudaMemcpyDeviceToHost));
-        CU(h, cudaMemcpy(i0.data(), h->dt.i0, n * 4, cudaMemcpyDeviceToHost));
-    }
-    CU(h, cudaMemcpy(hoff.data(), h->dt.hist_off, (n + 1) * 8, cudaMemcpyDeviceToHost));
-    /* rows are in key order (name rank, start, end): binary search each splitter */
+    if (h->finalized) return fail(h, IPX_ERR_STATE, "the exchange works on the table before ipx_finalize_device");
+    if (h->targets.empty()) return fail(h, IPX_ERR_STATE, "ipx_set_targets must be called first");
+    int rc = alloc_tables(h);
+    if (rc) return rc;
+    /* splitters in key-order terms: chromosome-name rank and intron_start */
     std::vector<uint32_t> order(h->targets.size()), rank(h->targets.size());
     for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h->targets[a] < h->targets[b]; });
     for (size_t i = 0; i < order.size(); i++) rank[order[i]] = (uint32_t)i;
-    uint64_t prev = 0;
-    for (int32_t p = 0; p < n_parts; p++) {
-        uint64_t hi = n;
-        if (p + 1 < n_parts) {
-            const uint32_t sr = rank[split_tid[p]];
-            const uint32_t ss = split_start[p];
-            uint64_t lo = prev, up = n;
-            while (lo < up) {
-                uint64_t mid = (lo + up) >> 1;
-                const uint32_t r = rank[chrom[mid]];
-                if (r < sr || (r == sr && i0[mid] < ss)) lo = mid + 1; else up = mid;
-            }
-            hi = lo;
-        }
-        junction_rows[p] = hi - prev;
-        hist_rows[p] = hoff[hi] - hoff[prev];
-        prev = hi;
+    Splitters &sp = h->export_split;
+    sp.n_parts = n_parts;
+    for (int32_t p = 0; p + 1 < n_parts; p++) {
+        if (split_tid[p] < 0 || (size_t)split_tid[p] >= rank.size()) return fail(h, IPX_ERR_ARG, "splitter %d names no target", p);
+        sp.rank[p] = rank[split_tid[p]];
+        sp.start[p] = split_start[p];
+        if (p > 0 && (sp.rank[p] < sp.rank[p - 1] || (sp.rank[p] == sp.rank[p - 1] && sp.start[p] < sp.start[p - 1])))
+            return fail(h, IPX_ERR_ARG, "splitters are not in key order");
     }
+    cudaStream_t st = h->stream;
+    if (!h->d_export) CU(h, cudaMalloc(&h->d_export, 2 * MAX_PARTS * sizeof(unsigned long long)));
+    CU(h, cudaMemsetAsync(h->d_export, 0, 2 * MAX_PARTS * sizeof(unsigned long long), st));
+    {
+        /* creation thresholds for anything still unresolved: keys that never got one are not exported */
+        Span s(h, &h->tm_motif, 1);
+        launch_resolve_T(h->tab, genome_view(h), st);
+    }
+    unsigned long long nk = 0, nl = 0;
+    uint32_t overflow = 0;
+    CU(h, cudaMemcpyAsync(&nk, h->tab.n_keys, 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(&nl, h->tab.n_olog, 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(&overflow, h->tab.overflow, 4, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    if (overflow) return fail(h, IPX_ERR_CAPACITY, "a table ran out of room before the exchange (raise table_capacity / hist_capacity)");
+    h->export_keys = nk;
+    h->export_olog = nl;
+    {
+        Span s(h, &h->tm_finalize, 2);
+        launch_export_count(h->tab, h->d_name_rank, sp, nk, nl, h->d_export, st);
+    }
+    CU(h, cudaGetLastError());
+    CU(h, cudaMemcpyAsync(h->export_counts, h->d_export, 2 * n_parts * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    for (int32_t p = 0; p < n_parts; p++) {
+        junction_rows[p] = h->export_counts[p];
+        hist_rows[p] = h->export_counts[n_parts + p];
+    }
+    h->export_ready = true;
     return IPX_OK;
 }
 
 extern "C" int ipx_partial_export(ipx_handle *h, void *dev_junction_rows, void *dev_hist_rows) {
     if (!h) return IPX_ERR_ARG;
     cudaSetDevice(h->device);
-    if (!h->finalized || !h->dt.slot) return fail(h, IPX_ERR_STATE, "call ipx_partial_sizes first");
-    launch_export_rows(h->tab, h->dt, (JunctionRow *)dev_junction_rows, (HistRow *)dev_hist_rows, h->stream);
+    if (!h->export_ready) return fail(h, IPX_ERR_STATE, "call ipx_partial_sizes first");
+    cudaStream_t st = h->stream;
+    const int n_parts = h->export_split.n_parts;
+    /* destination-major: the cursor of a part starts where the parts before it end */
+    unsigned long long cursors[2 * MAX_PARTS];
+    unsigned long long j = 0, hh = 0;
+    for (int p = 0; p < n_parts; p++) {
+        cursors[p] = j;
+        cursors[n_parts + p] = hh;
+        j += h->export_counts[p];
+        hh += h->export_counts[n_parts + p];
+    }
+    CU(h, cudaMemcpyAsync(h->d_export, cursors, 2 * n_parts * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    {
+        Span s(h, &h->tm_finalize, 2);
+        launch_export_scatter(h->tab, h->d_name_rank, h->export_split, h->export_keys, h->export_olog, h->d_export,
+                              (JunctionRow *)dev_junction_rows, (HistRow *)dev_hist_rows, st);
+        /* the local table has been handed over: empty it so that imports (own share included) rebuild it */
+        launch_clear_tables(h->tab, st);
+    }
     CU(h, cudaGetLastError());
-    /* the local table has been handed over: empty it so that imports (own share included) rebuild it */
-    CU(h, cudaStreamSynchronize(h->stream));
-    free_device_table(h->dt, h->stream);
-    h->finalized = false;
-    h->keep_export = false;
-    launch_clear_tables(h->tab, h->stream);
-    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(st)); /* `cursors` lives on this stack frame */
+    h->export_ready = false;
     return IPX_OK;
 }
 

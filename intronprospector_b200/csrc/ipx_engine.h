@@ -141,8 +141,20 @@ inline void dfree(cudaStream_t st, T *p) {
     if (p) cudaFreeAsync((void *)p, st);
 }
 
-/* export rows for destination ranks: rows [0, n) of the finished table are already in key order */
-void launch_export_rows(const Tables &t, const DeviceTable &dt, JunctionRow *jr, HistRow *hr, cudaStream_t st);
+/* Export of the partial table for the key-range exchange, straight from the tables (no finalize, no sort): the
+ * destination of a key is found by comparing (chromosome-name rank, intron_start) with the splitters; pass one counts
+ * rows per destination, pass two scatters them behind per-destination cursors. */
+static const int MAX_PARTS = 64;
+struct Splitters {
+    int32_t n_parts;
+    uint32_t rank[MAX_PARTS - 1];  /* first key of parts 1 .. n_parts-1: chromosome-name rank, */
+    uint32_t start[MAX_PARTS - 1]; /* intron_start */
+};
+/* counts / cursors: [2 * n_parts] unsigned long long on the device: junction rows per part, then offset rows per part */
+void launch_export_count(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t n_keys, uint64_t n_olog,
+                         unsigned long long *counts, cudaStream_t st);
+void launch_export_scatter(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t n_keys, uint64_t n_olog,
+                           unsigned long long *cursors, JunctionRow *jr, HistRow *hr, cudaStream_t st);
 
 }  // namespace ipx
 #endif

@@ -1222,34 +1222,116 @@ cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t
 }
 
 /* ------------------------------------------------------------------ multi-GPU exchange */
-__global__ void k_export_rows(Tables t, DeviceTable dt, JunctionRow *jr, HistRow *hr) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < dt.n) {
-        const JStat s = t.stat[dt.slot[i]];
+__device__ __forceinline__ int part_of(const Splitters &sp, uint32_t name_rank, uint32_t i0) {
+    int p = 0;
+    while (p < sp.n_parts - 1 && (name_rank > sp.rank[p] || (name_rank == sp.rank[p] && i0 >= sp.start[p]))) p++;
+    return p;
+}
+
+/* warp per slot in use: its destination and the number of non-zero counters of its dense offset row.
+ * SCATTER = false: count rows per destination; true: write them behind the destination's cursor. */
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_export_slots(Tables t, const uint32_t *name_rank, Splitters sp, uint64_t n_keys,
+                                                      unsigned long long *counts, JunctionRow *jr, HistRow *hr) {
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n_keys) return;
+    const uint32_t slot = t.slot_list[i];
+    const JStat s = t.stat[slot];
+    if (s.T == EMPTY64) return; /* never created: nothing was counted into it */
+    const unsigned long long key = t.keys[slot];
+    const int32_t tid = key_tid(t.kl, key);
+    const uint32_t i0 = key_start(t.kl, key), i1 = i0 + key_len(t.kl, key);
+    const int dest = part_of(sp, name_rank[tid], i0);
+    uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t mine = 0;
+    if (t.dense) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)slot * DENSE_W);
+        const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mine += (v[k] != 0);
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    const uint32_t nz = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned long long jpos = 0ull, hpos = 0ull;
+    if (lane == 0) {
+        jpos = atomicAdd(&counts[dest], 1ull);
+        if (nz) hpos = atomicAdd(&counts[sp.n_parts + dest], (unsigned long long)nz);
+    }
+    if (!SCATTER) return;
+    jpos = __shfl_sync(0xFFFFFFFFu, jpos, 0);
+    hpos = __shfl_sync(0xFFFFFFFFu, hpos, 0);
+    if (lane == 0) {
         JunctionRow r;
         r.first[0] = s.first[0]; r.first[1] = s.first[1]; r.first[2] = s.first[2];
         r.cnt[0] = s.cnt[0]; r.cnt[1] = s.cnt[1]; r.cnt[2] = s.cnt[2];
-        r.tid = dt.chrom[i]; r.i0 = dt.i0[i]; r.i1 = dt.i1[i]; r.a0 = s.a0; r.a1 = s.a1; r.pad = 0;
-        jr[i] = r;
+        r.tid = tid; r.i0 = i0; r.i1 = i1; r.a0 = s.a0; r.a1 = s.a1; r.pad = 0;
+        jr[jpos] = r;
     }
-    if (i < dt.n_hist) {
-        /* owning junction of run i: last r with hist_off[r] <= i */
-        uint64_t lo = 0, hi = dt.n;
-        while (hi - lo > 1) {
-            const uint64_t mid = (lo + hi) >> 1;
-            if (dt.hist_off[mid] <= i) lo = mid; else hi = mid;
+    uint64_t o = hpos + (incl - mine);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (v[k] != 0) {
+            HistRow h;
+            h.tid = tid; h.i0 = i0; h.i1 = i1; h.cnt = v[k]; h.offset = (uint32_t)(lane * 8 + k); h.pad = 0;
+            hr[o++] = h;
         }
-        HistRow h;
-        h.tid = dt.chrom[lo]; h.i0 = dt.i0[lo]; h.i1 = dt.i1[lo];
-        h.cnt = dt.hist_cnt[i]; h.offset = dt.hist_offset[i]; h.pad = 0;
-        hr[i] = h;
     }
 }
 
-void launch_export_rows(const Tables &t, const DeviceTable &dt, JunctionRow *jr, HistRow *hr, cudaStream_t st) {
-    const uint64_t n = dt.n > dt.n_hist ? dt.n : dt.n_hist;
-    if (n == 0) return;
-    k_export_rows<<<blocks_for(n, 256), 256, 0, st>>>(t, dt, jr, hr);
+/* thread per entry of the read-offset log: one offset row each (equal pairs are summed by the importer) */
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_export_olog(Tables t, const uint32_t *name_rank, Splitters sp, uint64_t n_olog,
+                                                     unsigned long long *counts, HistRow *hr) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int dest = -1 - lane; /* idle lanes group with nobody */
+    unsigned long long e = OLOG_INVALID;
+    int32_t tid = 0;
+    uint32_t i0 = 0, i1 = 0;
+    if (i < n_olog) {
+        e = t.olog[i];
+        if (e != OLOG_INVALID) {
+            const uint32_t slot = (uint32_t)(e >> 32);
+            if (t.stat[slot].T != EMPTY64) {
+                const unsigned long long key = t.keys[slot];
+                tid = key_tid(t.kl, key);
+                i0 = key_start(t.kl, key);
+                i1 = i0 + key_len(t.kl, key);
+                dest = part_of(sp, name_rank[tid], i0);
+            }
+        }
+    }
+    /* one atomic per (warp, destination) */
+    const unsigned grp = __match_any_sync(0xFFFFFFFFu, dest);
+    const int leader = __ffs(grp) - 1;
+    unsigned long long base = 0ull;
+    if (dest >= 0 && lane == leader) base = atomicAdd(&counts[sp.n_parts + dest], (unsigned long long)__popc(grp));
+    if (!SCATTER) return;
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (dest >= 0) {
+        HistRow h;
+        h.tid = tid; h.i0 = i0; h.i1 = i1; h.cnt = (uint32_t)(e & 0xFFFFull); h.offset = (uint32_t)((e >> 16) & 0xFFFFull); h.pad = 0;
+        hr[base + __popc(grp & ((1u << lane) - 1u))] = h;
+    }
+}
+
+void launch_export_count(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t n_keys, uint64_t n_olog,
+                         unsigned long long *counts, cudaStream_t st) {
+    if (n_keys) k_export_slots<false><<<blocks_for(n_keys * 32, 256), 256, 0, st>>>(t, name_rank, sp, n_keys, counts, nullptr, nullptr);
+    if (n_olog) k_export_olog<false><<<blocks_for(n_olog, 256), 256, 0, st>>>(t, name_rank, sp, n_olog, counts, nullptr);
+}
+
+void launch_export_scatter(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t n_keys, uint64_t n_olog,
+                           unsigned long long *cursors, JunctionRow *jr, HistRow *hr, cudaStream_t st) {
+    if (n_keys) k_export_slots<true><<<blocks_for(n_keys * 32, 256), 256, 0, st>>>(t, name_rank, sp, n_keys, cursors, jr, hr);
+    if (n_olog) k_export_olog<true><<<blocks_for(n_olog, 256), 256, 0, st>>>(t, name_rank, sp, n_olog, cursors, hr);
 }
 
 __global__ void k_import_junction_rows(Tables t, const JunctionRow *jr, uint64_t n) {
