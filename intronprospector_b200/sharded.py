@@ -140,3 +140,50 @@ def global_numbering(creation_seqs):
         return []
     allv = np.sort(np.concatenate([np.asarray(c, dtype=np.uint64) for c in creation_seqs]))
     return [np.searchsorted(allv, np.asarray(c, dtype=np.uint64)).astype(np.uint32) for c in creation_seqs]
+
+
+class MergeRowsPart:
+    """The rows of an ipx_merge_rows that fall into one key range, as a new ipx_merge_rows over numpy copies."""
+
+    def __init__(self, rows, keep):
+        import ctypes as C
+        from ._native import MergeRows
+        n = int(rows.n_rows)
+
+        def col(ptr, ctype, width=1):
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n * width,)) if n else np.zeros(0, ctype)
+            return a.reshape(n, width) if width > 1 else a
+
+        self.cols = {
+            "chrom": np.ascontiguousarray(col(rows.chrom, C.c_int32)[keep]),
+            "intron_start": np.ascontiguousarray(col(rows.intron_start, C.c_uint32)[keep]),
+            "intron_end": np.ascontiguousarray(col(rows.intron_end, C.c_uint32)[keep]),
+            "anchor_start": np.ascontiguousarray(col(rows.anchor_start, C.c_uint32)[keep]),
+            "anchor_end": np.ascontiguousarray(col(rows.anchor_end, C.c_uint32)[keep]),
+            "strand": np.ascontiguousarray(col(rows.strand, C.c_uint8)[keep]),
+            "sites": np.ascontiguousarray(col(rows.sites, C.c_uint32)[keep]),
+            "counts": np.ascontiguousarray(col(rows.counts, C.c_uint32, 3)[keep]),
+            "confidence": np.ascontiguousarray(col(rows.confidence, C.c_float)[keep]),
+        }
+        m = MergeRows()
+        m.n_rows = int(self.cols["chrom"].shape[0])
+        for k, a in self.cols.items():
+            setattr(m, k, a.ctypes.data)
+        m.site_strings = rows.site_strings
+        m.n_site_strings = rows.n_site_strings
+        self.struct = m
+
+
+def merge_rows_for_part(rows, names, n_parts, part):
+    """intronProspectorMerge across GPUs: keys are sharded by chromosome range BEFORE the fold, so every row of a
+    junction reaches the same rank in (file, row) order and no exchange is needed.  Returns the rows of `part`."""
+    import ctypes as C
+    n = int(rows.n_rows)
+    chrom = np.ctypeslib.as_array(C.cast(rows.chrom, C.POINTER(C.c_int32)), shape=(n,)) if n else np.zeros(0, np.int32)
+    order = sorted(range(len(names)), key=lambda i: names[i].encode())
+    rank = np.zeros(len(names), np.int64)
+    rank[order] = np.arange(len(names))
+    lo = (len(names) * part) // n_parts
+    hi = (len(names) * (part + 1)) // n_parts
+    r = rank[chrom]
+    return MergeRowsPart(rows, (r >= lo) & (r < hi))
