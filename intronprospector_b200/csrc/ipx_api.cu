@@ -134,9 +134,9 @@ struct ipx_handle {
 
     /* finalize */
     FinalizeWork fw;
-    DeviceTable dt{};
-    bool finalized = false;
-    bool keep_export = false;
+    bool finalized = false;        /* a finalize has been enqueued since the last change of the tables */
+    bool finalize_settled = false; /* ... and its bounds were checked (fw.out.n / n_hist are valid) */
+    bool bounds_proven = false;    /* the last checked finalize fitted its buffers: the next one need not be waited for */
     uint32_t ijunc_base = 0;
 
     /* merge */
@@ -452,14 +452,13 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
-    if (h->finalized) free_device_table(h->dt, h->stream);
     drop_deferred(h);
     cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.olog); cudaFree(h->tab.slot_list); cudaFree(h->tab.dense);
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq); cudaFree(h->d_export);
     free_genome(h);
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();
     h->s_off.release(); h->s_cig.release(); h->ev_buf.release(); h->tile_cnt.release(); h->long_buf.release();
-    cudaFree(h->fw.cub_tmp); cudaFree(h->fw.d_count); cudaFree(h->fw.slot_rank);
+    finalize_release(h->fw);
     cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -540,6 +539,34 @@ extern "C" int ipx_push_batch(ipx_handle *h, const ipx_batch *b) {
     return run_batch(h, v, b->n_cigar);
 }
 
+namespace {
+int enqueue_finalize(ipx_handle *h) {
+    Span s(h, &h->tm_finalize, 0);
+    cudaError_t e = finalize_enqueue(h->tab, genome_view(h), h->d_name_rank, (int32_t)h->targets.size(), h->seq_hi, h->fw, h->stream);
+    h->tm_finalize.launches += (uint64_t)h->fw.launches_per_replay;
+    if (e != cudaSuccess)
+        return fail(h, IPX_ERR_CUDA, "CUDA error %s in finalize: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    return IPX_OK;
+}
+
+/* wait for the enqueued finalize and make sure its buffers were large enough (growing and replaying otherwise) */
+int settle_finalize(ipx_handle *h) {
+    if (h->finalize_settled) return IPX_OK;
+    for (int round = 0; round < 8; round++) {
+        CU(h, cudaStreamSynchronize(h->stream));
+        if (finalize_check(h->fw)) {
+            h->finalize_settled = true;
+            h->bounds_proven = true;
+            return IPX_OK;
+        }
+        h->bounds_proven = false;
+        int rc = enqueue_finalize(h);
+        if (rc) return rc;
+    }
+    return fail(h, IPX_ERR_CUDA, "finalize did not settle");
+}
+}  // namespace
+
 extern "C" int ipx_finalize_device(ipx_handle *h) {
     if (!h) return IPX_ERR_ARG;
     cudaSetDevice(h->device);
@@ -548,16 +575,12 @@ extern "C" int ipx_finalize_device(ipx_handle *h) {
     if (h->targets.empty()) return fail(h, IPX_ERR_STATE, "ipx_set_targets must be called first");
     int rc = alloc_tables(h);
     if (rc) return rc;
-    {
-        Span s(h, &h->tm_finalize, 0);
-        int own = 0;
-        cudaError_t e = finalize_tables(h->tab, genome_view(h), h->d_name_rank, (int32_t)h->targets.size(), h->seq_hi, h->fw, h->dt,
-                                        h->keep_export, h->stream, &own);
-        h->tm_finalize.launches += (uint64_t)own;
-        if (e != cudaSuccess)
-            return fail(h, IPX_ERR_CUDA, "CUDA error %s in finalize: %s", cudaGetErrorName(e), cudaGetErrorString(e));
-    }
+    rc = enqueue_finalize(h);
+    if (rc) return rc;
     h->finalized = true;
+    h->finalize_settled = false;
+    /* asynchronous once the buffers have proven large enough; ipx_flush checks every time */
+    if (!h->bounds_proven) return settle_finalize(h);
     return IPX_OK;
 }
 
@@ -628,10 +651,12 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     *out = nullptr;
     int rc = ipx_finalize_device(h);
     if (rc) return rc;
+    rc = settle_finalize(h);
+    if (rc) return rc;
     cudaStream_t st = h->stream;
     HostTable *ht = new HostTable();
     memset(&ht->t, 0, sizeof(ht->t));
-    const DeviceTable &d = h->dt;
+    const DeviceTable &d = h->fw.out;
     const uint64_t n = d.n;
     std::vector<unsigned long long> counts, T, hist_off;
     cudaError_t e = cudaSuccess;
@@ -698,7 +723,6 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     h->totals.junctions += n;
     h->totals.hist_runs += d.n_hist;
     /* clear(), junctions.hh:240-245 */
-    free_device_table(h->dt, h->stream);
     h->finalized = false;
     launch_clear_tables(h->tab, st);
     h->dirty = false;
@@ -710,10 +734,7 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
 extern "C" int ipx_clear(ipx_handle *h) {
     if (!h) return IPX_ERR_ARG;
     cudaSetDevice(h->device);
-    if (h->finalized) {
-        free_device_table(h->dt, h->stream);
-        h->finalized = false;
-    }
+    h->finalized = false;
     if (h->tables_ready) {
         Span s(h, &h->tm_finalize, 2);
         launch_clear_tables(h->tab, h->stream);

@@ -43,8 +43,6 @@ struct DeviceTable {
     unsigned long long *T;      /* [n] creation sequence value (for cross-flush numbering / export) */
     unsigned long long *hist_off; /* [n+1] */
     uint32_t *hist_cnt;           /* [n_hist] */
-    uint32_t *hist_offset;        /* [n_hist] the uint16 offsets themselves (export only) */
-    uint32_t *slot;               /* [n] table slot of each junction (export only) */
 };
 
 /* packed rows exchanged between ranks (ipx_partial_export / ipx_partial_import) */
@@ -115,20 +113,51 @@ void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, con
                         cudaStream_t st);
 
 /* workspace for finalize; grown on demand by the engine */
+/* Everything finalize needs lives in buffers sized by grow-only bounds (B junction keys, L read-offset log entries,
+ * R histogram runs), so the whole sequence -- two radix sorts, the log's sort + run-length reduction, scans, gathers --
+ * is one CUDA graph that is captured once per set of bounds and replayed with a single launch.  The kernels read the
+ * actual counts from device memory, pad up to the bounds with keys that sort last, and raise a flag when a bound was
+ * too small; the host then grows the bound and replays (the graph only reads the tables, so a replay is harmless). */
 struct FinalizeWork {
+    uint64_t B = 0, L = 0, R = 0;
+    uint64_t wish_B = 0, wish_L = 0, wish_R = 0; /* what finalize_check asked for */
+    unsigned long long *sort_key = nullptr, *sort_key2 = nullptr, *hash_lo = nullptr, *total = nullptr, *hk_a = nullptr,
+                       *hk_b = nullptr;
+    uint32_t *slot_a = nullptr, *slot_b = nullptr, *idx_b = nullptr, *dense_nz = nullptr, *hc_a = nullptr, *hc_b = nullptr;
+    uint32_t *slot_rank = nullptr; /* [cap] key-order rank of each slot, for the read-offset log */
+    uint64_t slot_rank_cap = 0;
     void *cub_tmp = nullptr;
     size_t cub_tmp_bytes = 0;
-    unsigned long long *d_count = nullptr; /* [4]: 0 = junctions, 1 = histogram runs */
-    uint32_t *slot_rank = nullptr;         /* [cap] key-order rank of each slot (only filled when the offset hash is in use) */
-    uint64_t slot_rank_cap = 0;
+    /* [8]: 0 junctions, 1 histogram runs, 2 distinct log runs (uint32), 3 flags (1: B too small, 2: L, 4: R),
+     *      4 keys seen, 5 log entries seen */
+    unsigned long long *d_count = nullptr;
+    unsigned long long *h_count = nullptr; /* pinned mirror, filled by the graph's last node */
+    DeviceTable out{};                     /* arrays of B rows (hist_cnt: R runs) */
+    cudaGraphExec_t exec = nullptr;
+    /* what the captured graph depends on */
+    struct Key {
+        uint64_t B, L, R;
+        int key_bits, t_bits;
+        const void *tab_keys, *name_rank, *gseq, *target_seq, *dense;
+        int32_t n_targets, have_genome, skip_missing, filter_canon;
+        bool operator==(const Key &o) const {
+            return B == o.B && L == o.L && R == o.R && key_bits == o.key_bits && t_bits == o.t_bits && tab_keys == o.tab_keys &&
+                   name_rank == o.name_rank && gseq == o.gseq && target_seq == o.target_seq && dense == o.dense &&
+                   n_targets == o.n_targets && have_genome == o.have_genome && skip_missing == o.skip_missing &&
+                   filter_canon == o.filter_canon;
+        }
+    } key{};
+    int launches_per_replay = 0;
 };
 
-/* key-order sort, sjN ranking, histogram ordering, gather; synchronises on the counts it needs.
- * `name_rank[tid]` orders targets like std::string::operator< on their names. Returns cudaError_t. */
-cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, int32_t n_targets,
-                            uint64_t seq_hi, FinalizeWork &w, DeviceTable &out, bool keep_export_columns, cudaStream_t st,
-                            int *own_launches);
-void free_device_table(DeviceTable &t, cudaStream_t st);
+/* key-order sort, sjN ranking, histogram ordering, gather: enqueues one graph launch on `st` and the copy of the
+ * counters to w.h_count; nothing is synchronised.  finalize_check (after a stream synchronise) says whether a bound
+ * was too small -- it then grows the bounds and the caller enqueues again.  `name_rank[tid]` orders targets like
+ * std::string::operator< on their names. */
+cudaError_t finalize_enqueue(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, int32_t n_targets,
+                             uint64_t seq_hi, FinalizeWork &w, cudaStream_t st);
+bool finalize_check(FinalizeWork &w); /* true = results valid (w.out.n / n_hist set); false = bounds grown, run again */
+void finalize_release(FinalizeWork &w);
 
 /* stream-ordered allocation from the device's default pool (kept resident, see ipx_create): no implicit
  * device synchronisation and no driver round trip once the pool is warm */

@@ -865,22 +865,38 @@ void launch_resolve_T(const Tables &t, const GenomeView &g, cudaStream_t st) {
 
 
 /* ------------------------------------------------------------------ finalize */
-/* Everything here walks slot_list (the n_keys slots in use), never the table's capacity.  The number of junctions
- * n_j <= n_keys (keys whose every event was rejected by the canon filter are not junctions) stays on the device:
- * rejected keys get a sort key above every real one, so they sort to the end, and the kernels read n_j from
- * d_count[0]. */
-__global__ void k_list_keys(Tables t, const uint32_t *name_rank, unsigned long long nk, int key_bits,
-                            unsigned long long *d_count, unsigned long long *sort_key, uint32_t *slot_out) {
+/* Everything here walks slot_list (the slots in use), never the table's capacity, inside buffers of fixed bounds
+ * (see FinalizeWork).  Counts stay on the device: d_count[0] junctions (n_j <= keys in use: keys whose every event was
+ * rejected by the canon filter are not junctions), d_count[1] histogram runs, d_count[2] distinct log runs,
+ * d_count[3] flags for bounds that were too small. */
+enum : unsigned long long { FLAG_B = 1ull, FLAG_L = 2ull, FLAG_R = 4ull };
+
+__global__ void k_finalize_begin(Tables t, unsigned long long *d_count, uint64_t B, uint64_t L) {
+    const unsigned long long nk = *t.n_keys, nl = *t.n_olog;
+    d_count[0] = d_count[1] = d_count[2] = 0ull;
+    d_count[3] = (nk > B ? FLAG_B : 0ull) | (nl > L ? FLAG_L : 0ull);
+    d_count[4] = nk;
+    d_count[5] = nl;
+}
+
+/* sort keys of the slots in use: chromosome-name rank, intron_start, intron_end; rejected keys and padding sort last */
+__global__ void k_list_keys(Tables t, const uint32_t *name_rank, uint64_t B, int key_bits, unsigned long long *d_count,
+                            unsigned long long *sort_key, uint32_t *slot_out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long nk = *t.n_keys < B ? *t.n_keys : B;
     bool take = false;
-    if (i < nk) {
-        const uint32_t slot = t.slot_list[i];
-        const unsigned long long key = t.keys[slot];
-        take = t.stat[slot].T != EMPTY64;
-        const uint64_t tid = (uint64_t)key_tid(t.kl, key);
-        const uint64_t low = key & ((1ull << t.kl.tid_shift) - 1ull);
-        /* key order: chromosome-name rank, intron_start, intron_end */
-        sort_key[i] = take ? (((unsigned long long)name_rank[tid] << t.kl.tid_shift) | low) : (1ull << key_bits);
+    if (i < B) {
+        unsigned long long sk = 1ull << key_bits;
+        uint32_t slot = 0u;
+        if (i < nk) {
+            slot = t.slot_list[i];
+            const unsigned long long key = t.keys[slot];
+            take = t.stat[slot].T != EMPTY64;
+            const uint64_t tid = (uint64_t)key_tid(t.kl, key);
+            const uint64_t low = key & ((1ull << t.kl.tid_shift) - 1ull);
+            if (take) sk = ((unsigned long long)name_rank[tid] << t.kl.tid_shift) | low;
+        }
+        sort_key[i] = sk;
         slot_out[i] = slot;
     }
     const unsigned mask = __ballot_sync(0xFFFFFFFFu, take);
@@ -893,12 +909,11 @@ __global__ void k_fill_slot_rank(const uint32_t *sorted_slot, const unsigned lon
 }
 
 /* sort key of the sjN ranking: the creating event's position in the stream (sv without its strand byte) */
-__global__ void k_gather_T(Tables t, const uint32_t *sorted_slot, unsigned long long nk, int t_bits, unsigned long long *T_out,
-                           uint32_t *idx_out) {
+__global__ void k_gather_T(Tables t, const uint32_t *sorted_slot, const unsigned long long *d_count, uint64_t B, int t_bits,
+                           unsigned long long *T_out, uint32_t *idx_out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nk) {
-        const unsigned long long T = t.stat[sorted_slot[i]].T;
-        T_out[i] = T == EMPTY64 ? (1ull << t_bits) : (T >> 8);
+    if (i < B) {
+        T_out[i] = i < d_count[0] ? (t.stat[sorted_slot[i]].T >> 8) : (1ull << t_bits);
         idx_out[i] = (uint32_t)i;
     }
 }
@@ -928,7 +943,6 @@ __global__ void k_gather_rows(Tables t, GenomeView g, const uint32_t *sorted_slo
     out.counts[3 * i + 1] = s.cnt[1];
     out.counts[3 * i + 2] = s.cnt[2];
     out.T[i] = s.T;
-    if (out.slot) out.slot[i] = slot;
     char strand = (char)(s.T & 0xFFull);
     char site[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     char f[4];
@@ -958,13 +972,14 @@ __global__ void k_gather_rows(Tables t, GenomeView g, const uint32_t *sorted_slo
     for (int k = 0; k < 8; ++k) out.sites[8 * i + k] = site[k];
 }
 
-/* every offset-log entry -> (junction rank << 16 | offset, count); invalid entries and entries of slots that are not
- * junctions (none are expected) get a key above every real one */
-__global__ void k_olog_pairs(Tables t, const uint32_t *slot_rank, unsigned long long nh, int h_bits,
-                             unsigned long long *hkey_out, uint32_t *hcnt_out) {
+/* every offset-log entry -> (junction rank << 16 | offset, count); padding, invalid entries and entries of slots that
+ * are not junctions (none are expected) get a key above every real one */
+__global__ void k_olog_pairs(Tables t, const uint32_t *slot_rank, uint64_t L, int h_bits, unsigned long long *hkey_out,
+                             uint32_t *hcnt_out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nh) return;
-    const unsigned long long e = t.olog[i];
+    if (i >= L) return;
+    const unsigned long long nl = *t.n_olog < L ? *t.n_olog : L;
+    const unsigned long long e = i < nl ? t.olog[i] : OLOG_INVALID;
     const uint32_t r = e == OLOG_INVALID ? 0xFFFFFFFFu : slot_rank[e >> 32];
     hkey_out[i] = r == 0xFFFFFFFFu ? (1ull << h_bits) : (((unsigned long long)r << 16) | ((e >> 16) & 0xFFFFull));
     hcnt_out[i] = (uint32_t)(e & 0xFFFFull);
@@ -1002,15 +1017,20 @@ __global__ void k_dense_count(Tables t, const uint32_t *sorted_slot, const unsig
 }
 
 /* warp per junction: write its runs in ascending offset order -- dense row first (offsets < DENSE_W), then its
- * slice of the sorted hash runs (offsets >= DENSE_W, or every offset when the table has no dense rows) */
-__global__ void k_write_runs(Tables t, const uint32_t *sorted_slot, uint64_t n, const unsigned long long *hist_off,
-                             const uint32_t *dense_nz, const unsigned long long *hash_lo,
-                             const unsigned long long *sorted_hkey, const uint32_t *sorted_hcnt, uint32_t *hist_cnt,
-                             uint32_t *hist_offset) {
+ * slice of the sorted log runs (offsets >= DENSE_W, or every offset when the table has no dense rows) */
+__global__ void k_write_runs(Tables t, const uint32_t *sorted_slot, unsigned long long *d_count, uint64_t B, uint64_t R,
+                             const unsigned long long *hist_off, const uint32_t *dense_nz, const unsigned long long *hash_lo,
+                             const uint32_t *sorted_hcnt, uint32_t *hist_cnt) {
     const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (r >= n) return;
-    const unsigned long long o0 = hist_off[r];
+    if (r == 0 && lane == 0) {
+        const unsigned long long n_runs = hist_off[B]; /* total[] is zero beyond the junctions */
+        d_count[1] = n_runs;
+        if (n_runs > R) atomicOr(&d_count[3], FLAG_R);
+    }
+    if (r >= d_count[0]) return;
+    const unsigned long long o0 = hist_off[r], o1 = hist_off[r + 1];
+    if (o1 > R) return; /* does not fit: the host grows R and replays */
     const uint32_t nz = dense_nz[r];
     if (t.dense && nz) {
         const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)sorted_slot[r] * DENSE_W);
@@ -1028,20 +1048,13 @@ __global__ void k_write_runs(Tables t, const uint32_t *sorted_slot, uint64_t n, 
         uint64_t o = o0 + (pre - mine);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            if (v[k] != 0) {
-                hist_cnt[o] = v[k];
-                if (hist_offset) hist_offset[o] = (uint32_t)(lane * 8 + k);
-                o++;
-            }
+            if (v[k] != 0) hist_cnt[o++] = v[k];
         }
     }
-    const unsigned long long n_hash = (hist_off[r + 1] - o0) - nz;
+    const unsigned long long n_hash = (o1 - o0) - nz;
     if (n_hash) {
         const unsigned long long lo = hash_lo[r];
-        for (unsigned long long j = lane; j < n_hash; j += 32) {
-            hist_cnt[o0 + nz + j] = sorted_hcnt[lo + j];
-            if (hist_offset) hist_offset[o0 + nz + j] = (uint32_t)(sorted_hkey[lo + j] & 0xFFFFull);
-        }
+        for (unsigned long long j = lane; j < n_hash; j += 32) hist_cnt[o0 + nz + j] = sorted_hcnt[lo + j];
     }
 }
 
@@ -1050,24 +1063,6 @@ __global__ void k_write_runs(Tables t, const uint32_t *sorted_slot, uint64_t n, 
         cudaError_t e__ = (x);             \
         if (e__ != cudaSuccess) return e__; \
     } while (0)
-
-static cudaError_t ensure_tmp(FinalizeWork &w, size_t bytes, cudaStream_t st) {
-    if (bytes > w.cub_tmp_bytes) {
-        if (w.cub_tmp) dfree(st, w.cub_tmp);
-        w.cub_tmp = nullptr;
-        w.cub_tmp_bytes = 0;
-        IPX_CU(dmalloc(st, &w.cub_tmp, bytes));
-        w.cub_tmp_bytes = bytes;
-    }
-    return cudaSuccess;
-}
-
-void free_device_table(DeviceTable &t, cudaStream_t st) {
-    dfree(st, t.chrom); dfree(st, t.i0); dfree(st, t.i1); dfree(st, t.a0); dfree(st, t.a1); dfree(st, t.ijunc);
-    dfree(st, t.strand); dfree(st, t.sites); dfree(st, t.counts); dfree(st, t.T); dfree(st, t.hist_off);
-    dfree(st, t.hist_cnt); dfree(st, t.hist_offset); dfree(st, t.slot);
-    t = DeviceTable();
-}
 
 static inline unsigned blocks_for(uint64_t n, unsigned threads) {
     uint64_t b = (n + threads - 1) / threads;
@@ -1080,146 +1075,180 @@ static inline int bits_for64(uint64_t v) {
     return b;
 }
 
-template <class K, class V>
-static cudaError_t sort_pairs(FinalizeWork &w, const K *k_in, K *k_out, const V *v_in, V *v_out, uint64_t n, int end_bit,
-                              cudaStream_t st) {
-    size_t tb = 0;
-    IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, st));
-    IPX_CU(ensure_tmp(w, tb, st));
-    return cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, k_in, k_out, v_in, v_out, (int)n, 0, end_bit, st);
+static inline uint64_t pow2_ge(uint64_t v, uint64_t floor_) {
+    uint64_t p = floor_;
+    while (p < v) p <<= 1;
+    return p;
 }
 
-cudaError_t finalize_tables(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, int32_t n_targets,
-                            uint64_t seq_hi, FinalizeWork &w, DeviceTable &out, bool keep_export, cudaStream_t st,
-                            int *own_launches) {
+template <class T>
+static cudaError_t regrow(T **p, size_t count) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    return cudaMalloc((void **)p, (count ? count : 1) * sizeof(T));
+}
+
+void finalize_release(FinalizeWork &w) {
+    if (w.exec) cudaGraphExecDestroy(w.exec);
+    w.exec = nullptr;
+    cudaFree(w.sort_key); cudaFree(w.sort_key2); cudaFree(w.hash_lo); cudaFree(w.total); cudaFree(w.hk_a); cudaFree(w.hk_b);
+    cudaFree(w.slot_a); cudaFree(w.slot_b); cudaFree(w.idx_b); cudaFree(w.dense_nz); cudaFree(w.hc_a); cudaFree(w.hc_b);
+    cudaFree(w.slot_rank); cudaFree(w.cub_tmp); cudaFree(w.d_count);
+    if (w.h_count) cudaFreeHost(w.h_count);
+    DeviceTable &o = w.out;
+    cudaFree(o.chrom); cudaFree(o.i0); cudaFree(o.i1); cudaFree(o.a0); cudaFree(o.a1); cudaFree(o.ijunc); cudaFree(o.strand);
+    cudaFree(o.sites); cudaFree(o.counts); cudaFree(o.T); cudaFree(o.hist_off); cudaFree(o.hist_cnt);
+    w = FinalizeWork();
+}
+
+/* (re)allocate everything whose size follows the bounds */
+static cudaError_t finalize_allocate(FinalizeWork &w, uint64_t cap, uint64_t B, uint64_t L, uint64_t R) {
+    if (!w.d_count) IPX_CU(cudaMalloc(&w.d_count, 8 * sizeof(unsigned long long)));
+    if (!w.h_count) IPX_CU(cudaMallocHost(&w.h_count, 8 * sizeof(unsigned long long)));
+    if (w.slot_rank_cap < cap) {
+        IPX_CU(regrow(&w.slot_rank, cap));
+        w.slot_rank_cap = cap;
+    }
+    if (B != w.B) {
+        IPX_CU(regrow(&w.sort_key, B)); IPX_CU(regrow(&w.sort_key2, B)); IPX_CU(regrow(&w.slot_a, B)); IPX_CU(regrow(&w.slot_b, B));
+        IPX_CU(regrow(&w.idx_b, B)); IPX_CU(regrow(&w.hash_lo, B)); IPX_CU(regrow(&w.total, B + 1)); IPX_CU(regrow(&w.dense_nz, B));
+        DeviceTable &o = w.out;
+        IPX_CU(regrow(&o.chrom, B)); IPX_CU(regrow(&o.i0, B)); IPX_CU(regrow(&o.i1, B)); IPX_CU(regrow(&o.a0, B));
+        IPX_CU(regrow(&o.a1, B)); IPX_CU(regrow(&o.ijunc, B)); IPX_CU(regrow(&o.strand, B)); IPX_CU(regrow(&o.sites, B * 8));
+        IPX_CU(regrow(&o.counts, B * 3)); IPX_CU(regrow(&o.T, B)); IPX_CU(regrow(&o.hist_off, B + 2));
+        w.B = B;
+    }
+    if (L != w.L) {
+        IPX_CU(regrow(&w.hk_a, L)); IPX_CU(regrow(&w.hk_b, L)); IPX_CU(regrow(&w.hc_a, L)); IPX_CU(regrow(&w.hc_b, L));
+        w.L = L;
+    }
+    if (R != w.R) {
+        IPX_CU(regrow(&w.out.hist_cnt, R));
+        w.R = R;
+    }
+    return cudaSuccess;
+}
+
+/* the sequence itself, issued into `st` (under stream capture, or directly when capture is not possible) */
+static cudaError_t finalize_issue(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, FinalizeWork &w, cudaStream_t st) {
+    const uint64_t B = w.B, L = w.L, R = w.R, cap = t.cap_mask + 1;
+    const int key_bits = w.key.key_bits, t_bits = w.key.t_bits, h_bits = 16 + bits_for64(B);
+    DeviceTable &out = w.out;
     int launches = 0;
-    const uint64_t cap = t.cap_mask + 1;
-    out = DeviceTable();
-    if (!w.d_count) IPX_CU(dmalloc(st, &w.d_count, 4 * sizeof(unsigned long long)));
-    IPX_CU(cudaMemsetAsync(w.d_count, 0, 4 * sizeof(unsigned long long), st));
-
-    /* creation thresholds for anything still unresolved */
-    k_resolve_T<<<148 * 4, 256, 0, st>>>(t, g);
-    launches++;
-
-    /* first of two host round trips: how many slots and offset-table entries are in use */
-    unsigned long long nk = 0, nh = 0;
-    uint32_t overflow = 0;
-    IPX_CU(cudaMemcpyAsync(&nk, t.n_keys, sizeof(nk), cudaMemcpyDeviceToHost, st));
-    IPX_CU(cudaMemcpyAsync(&nh, t.n_olog, sizeof(nh), cudaMemcpyDeviceToHost, st));
-    IPX_CU(cudaMemcpyAsync(&overflow, t.overflow, sizeof(overflow), cudaMemcpyDeviceToHost, st));
-    IPX_CU(cudaStreamSynchronize(st));
-    if (overflow) nk = nh = 0; /* a table or the log ran out of room: ipx_flush reports it, there is no result */
-    const uint64_t na = nk ? nk : 1;
-
-    IPX_CU(dmalloc(st, &out.chrom, na * 4));
-    IPX_CU(dmalloc(st, &out.i0, na * 4));
-    IPX_CU(dmalloc(st, &out.i1, na * 4));
-    IPX_CU(dmalloc(st, &out.a0, na * 4));
-    IPX_CU(dmalloc(st, &out.a1, na * 4));
-    IPX_CU(dmalloc(st, &out.ijunc, na * 4));
-    IPX_CU(dmalloc(st, &out.strand, na));
-    IPX_CU(dmalloc(st, &out.sites, na * 8));
-    IPX_CU(dmalloc(st, &out.counts, na * 24));
-    IPX_CU(dmalloc(st, &out.T, na * 8));
-    IPX_CU(dmalloc(st, &out.hist_off, (na + 2) * 8));
-    if (keep_export) IPX_CU(dmalloc(st, &out.slot, na * 4));
-    if (nk == 0) {
-        IPX_CU(cudaMemsetAsync(out.hist_off, 0, (na + 2) * 8, st));
-        IPX_CU(dmalloc(st, &out.hist_cnt, 4));
-        if (keep_export) IPX_CU(dmalloc(st, &out.hist_offset, 4));
-        if (own_launches) *own_launches = launches;
-        IPX_CU(cudaStreamSynchronize(st));
-        return cudaGetLastError();
-    }
-
-    unsigned long long *sort_key = nullptr, *sort_key2 = nullptr, *hash_lo = nullptr, *total = nullptr;
-    uint32_t *slot_a = nullptr, *slot_b = nullptr, *idx_b = nullptr, *dense_nz = nullptr;
-    IPX_CU(dmalloc(st, &sort_key, nk * 8));
-    IPX_CU(dmalloc(st, &sort_key2, nk * 8));
-    IPX_CU(dmalloc(st, &slot_a, nk * 4));
-    IPX_CU(dmalloc(st, &slot_b, nk * 4));
-    IPX_CU(dmalloc(st, &idx_b, nk * 4));
-    IPX_CU(dmalloc(st, &hash_lo, nk * 8));
-    IPX_CU(dmalloc(st, &total, (nk + 1) * 8));
-    IPX_CU(dmalloc(st, &dense_nz, nk * 4));
-    IPX_CU(cudaMemsetAsync(total, 0, (nk + 1) * 8, st));
-
+    size_t tb = w.cub_tmp_bytes;
+    k_resolve_T<<<148 * 4, 256, 0, st>>>(t, g); /* creation thresholds for anything still unresolved */
+    k_finalize_begin<<<1, 1, 0, st>>>(t, w.d_count, B, L);
+    IPX_CU(cudaMemsetAsync(w.total, 0, (B + 1) * 8, st));
     /* key order */
-    const int key_bits = t.kl.tid_shift + bits_for64((uint64_t)(n_targets > 0 ? n_targets : 1));
-    k_list_keys<<<blocks_for(nk, 256), 256, 0, st>>>(t, d_name_rank, nk, key_bits, w.d_count, sort_key, slot_a);
-    IPX_CU(sort_pairs(w, sort_key, sort_key2, slot_a, slot_b, nk, key_bits + 1 > 64 ? 64 : key_bits + 1, st));
-    const uint32_t *sorted_slot = slot_b;
-    launches++;
-
+    k_list_keys<<<blocks_for(B, 256), 256, 0, st>>>(t, d_name_rank, B, key_bits, w.d_count, w.sort_key, w.slot_a);
+    IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.sort_key, w.sort_key2, w.slot_a, w.slot_b, (int)B, 0,
+                                           key_bits + 1 > 64 ? 64 : key_bits + 1, st));
+    const uint32_t *sorted_slot = w.slot_b;
     /* sjN: rank of the creating event in stream order */
-    {
-        const int t_bits = (SV_SEQ_SHIFT - 8) + bits_for64(seq_hi ? seq_hi : 1);
-        uint32_t *idx_a = slot_a; /* reuse */
-        k_gather_T<<<blocks_for(nk, 256), 256, 0, st>>>(t, sorted_slot, nk, t_bits, sort_key, idx_a);
-        IPX_CU(sort_pairs(w, sort_key, sort_key2, idx_a, idx_b, nk, t_bits + 1, st));
-        k_scatter_ijunc<<<blocks_for(nk, 256), 256, 0, st>>>(idx_b, w.d_count, out.ijunc);
-        k_gather_rows<<<blocks_for(nk, 256), 256, 0, st>>>(t, g, sorted_slot, w.d_count, out);
-        launches += 3;
-    }
-
-    /* offset histograms: the hash part (long reads) is ordered by (junction rank, offset) with a sort; the dense
-     * rows are already in offset order */
-    unsigned long long *hk_a = nullptr, *hk_b = nullptr;
-    uint32_t *hc_a = nullptr, *hc_b = nullptr;
-    if (nh) {
-        if (w.slot_rank_cap < cap) {
-            if (w.slot_rank) dfree(st, w.slot_rank);
-            w.slot_rank = nullptr;
-            IPX_CU(dmalloc(st, &w.slot_rank, cap * sizeof(uint32_t)));
-            w.slot_rank_cap = cap;
-        }
-        IPX_CU(cudaMemsetAsync(w.slot_rank, 0xFF, cap * sizeof(uint32_t), st));
-        k_fill_slot_rank<<<blocks_for(nk, 256), 256, 0, st>>>(sorted_slot, w.d_count, w.slot_rank);
-        IPX_CU(dmalloc(st, &hk_a, nh * 8));
-        IPX_CU(dmalloc(st, &hk_b, nh * 8));
-        IPX_CU(dmalloc(st, &hc_a, nh * 4));
-        IPX_CU(dmalloc(st, &hc_b, nh * 4));
-        const int h_bits = 16 + bits_for64(nk);
-        k_olog_pairs<<<blocks_for(nh, 256), 256, 0, st>>>(t, w.slot_rank, nh, h_bits, hk_a, hc_a);
-        IPX_CU(sort_pairs(w, hk_a, hk_b, hc_a, hc_b, nh, h_bits + 1, st));
-        /* equal (junction, offset) pairs -> one run with the summed count; the runs end up in hk_a / hc_a */
-        uint32_t *n_unique = reinterpret_cast<uint32_t *>(w.d_count + 2);
-        size_t tb = 0;
-        IPX_CU(cub::DeviceReduce::ReduceByKey(nullptr, tb, hk_b, hk_a, hc_b, hc_a, n_unique, cub::Sum(), (int)nh, st));
-        IPX_CU(ensure_tmp(w, tb, st));
-        IPX_CU(cub::DeviceReduce::ReduceByKey(w.cub_tmp, tb, hk_b, hk_a, hc_b, hc_a, n_unique, cub::Sum(), (int)nh, st));
-        k_hash_runs<<<blocks_for(nh, 256), 256, 0, st>>>(hk_a, n_unique, h_bits, hash_lo, total);
-        launches += 3;
-    }
-    k_dense_count<<<blocks_for(nk * 32, 256), 256, 0, st>>>(t, sorted_slot, w.d_count, total, dense_nz);
-    launches++;
-    {
-        size_t tb = 0;
-        IPX_CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, total, out.hist_off, (int)(nk + 1), st));
-        IPX_CU(ensure_tmp(w, tb, st));
-        IPX_CU(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, total, out.hist_off, (int)(nk + 1), st));
-    }
-    /* second host round trip: the number of junctions and of histogram runs */
-    unsigned long long n_j = 0, n_runs = 0;
-    IPX_CU(cudaMemcpyAsync(&n_j, &w.d_count[0], sizeof(n_j), cudaMemcpyDeviceToHost, st));
-    IPX_CU(cudaMemcpyAsync(&n_runs, out.hist_off + nk, sizeof(n_runs), cudaMemcpyDeviceToHost, st));
-    IPX_CU(cudaStreamSynchronize(st));
-    out.n = n_j;
-    out.n_hist = n_runs;
-    IPX_CU(dmalloc(st, &out.hist_cnt, (n_runs ? n_runs : 1) * 4));
-    if (keep_export) IPX_CU(dmalloc(st, &out.hist_offset, (n_runs ? n_runs : 1) * 4));
-    if (n_j) {
-        k_write_runs<<<blocks_for(n_j * 32, 256), 256, 0, st>>>(t, sorted_slot, n_j, out.hist_off, dense_nz, hash_lo, hk_a, hc_a,
-                                                              out.hist_cnt, out.hist_offset);
-        launches++;
-    }
-    if (own_launches) *own_launches = launches;
-    dfree(st, hk_a); dfree(st, hk_b); dfree(st, hc_a); dfree(st, hc_b);
-    dfree(st, hash_lo); dfree(st, total); dfree(st, dense_nz); dfree(st, idx_b);
-    dfree(st, sort_key); dfree(st, sort_key2); dfree(st, slot_a); dfree(st, slot_b);
+    k_gather_T<<<blocks_for(B, 256), 256, 0, st>>>(t, sorted_slot, w.d_count, B, t_bits, w.sort_key, w.slot_a);
+    tb = w.cub_tmp_bytes;
+    IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.sort_key, w.sort_key2, w.slot_a, w.idx_b, (int)B, 0, t_bits + 1, st));
+    k_scatter_ijunc<<<blocks_for(B, 256), 256, 0, st>>>(w.idx_b, w.d_count, out.ijunc);
+    k_gather_rows<<<blocks_for(B, 256), 256, 0, st>>>(t, g, sorted_slot, w.d_count, out);
+    launches += 6;
+    /* read-offset log: ordered by (junction rank, offset) with a sort, equal pairs summed */
+    IPX_CU(cudaMemsetAsync(w.slot_rank, 0xFF, cap * sizeof(uint32_t), st));
+    k_fill_slot_rank<<<blocks_for(B, 256), 256, 0, st>>>(sorted_slot, w.d_count, w.slot_rank);
+    k_olog_pairs<<<blocks_for(L, 256), 256, 0, st>>>(t, w.slot_rank, L, h_bits, w.hk_a, w.hc_a);
+    tb = w.cub_tmp_bytes;
+    IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.hk_a, w.hk_b, w.hc_a, w.hc_b, (int)L, 0, h_bits + 1, st));
+    uint32_t *n_unique = reinterpret_cast<uint32_t *>(w.d_count + 2);
+    tb = w.cub_tmp_bytes;
+    IPX_CU(cub::DeviceReduce::ReduceByKey(w.cub_tmp, tb, w.hk_b, w.hk_a, w.hc_b, w.hc_a, n_unique, cub::Sum(), (int)L, st));
+    k_hash_runs<<<blocks_for(L, 256), 256, 0, st>>>(w.hk_a, n_unique, h_bits, w.hash_lo, w.total);
+    /* dense rows are already in offset order */
+    k_dense_count<<<blocks_for(B * 32, 256), 256, 0, st>>>(t, sorted_slot, w.d_count, w.total, w.dense_nz);
+    tb = w.cub_tmp_bytes;
+    IPX_CU(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.total, out.hist_off, (int)(B + 1), st));
+    k_write_runs<<<blocks_for(B * 32, 256), 256, 0, st>>>(t, sorted_slot, w.d_count, B, R, out.hist_off, w.dense_nz, w.hash_lo, w.hc_a,
+                                                        out.hist_cnt);
+    launches += 5;
+    IPX_CU(cudaMemcpyAsync(w.h_count, w.d_count, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    w.launches_per_replay = launches;
     return cudaGetLastError();
 }
+
+cudaError_t finalize_enqueue(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, int32_t n_targets,
+                             uint64_t seq_hi, FinalizeWork &w, cudaStream_t st) {
+    const uint64_t cap = t.cap_mask + 1;
+    uint64_t B = w.B ? w.B : (1ull << 16), L = w.L ? w.L : (1ull << 16), R = w.R ? w.R : (1ull << 20);
+    if (w.wish_B > B) B = w.wish_B;
+    if (w.wish_L > L) L = w.wish_L;
+    if (w.wish_R > R) R = w.wish_R;
+    FinalizeWork::Key key{};
+    key.B = B; key.L = L; key.R = R;
+    key.key_bits = t.kl.tid_shift + bits_for64((uint64_t)(n_targets > 0 ? n_targets : 1));
+    key.t_bits = (SV_SEQ_SHIFT - 8) + bits_for64(seq_hi ? seq_hi : 1);
+    key.tab_keys = t.keys; key.name_rank = d_name_rank; key.gseq = g.seq; key.target_seq = g.target_seq; key.dense = t.dense;
+    key.n_targets = g.n_targets; key.have_genome = g.have_genome; key.skip_missing = g.skip_missing; key.filter_canon = g.filter_canon;
+    if (!w.exec || !(key == w.key)) {
+        if (w.exec) {
+            IPX_CU(cudaStreamSynchronize(st)); /* a replay may still be running */
+            cudaGraphExecDestroy(w.exec);
+            w.exec = nullptr;
+        }
+        IPX_CU(cudaStreamSynchronize(st));
+        IPX_CU(finalize_allocate(w, cap, B, L, R));
+        w.key = key;
+        /* temporary storage of the library calls, sized for the largest of them */
+        size_t need = 0, tb = 0;
+        IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, w.sort_key, w.sort_key2, w.slot_a, w.slot_b, (int)B, 0, 64, st));
+        need = tb > need ? tb : need;
+        IPX_CU(cub::DeviceRadixSort::SortPairs(nullptr, tb, w.hk_a, w.hk_b, w.hc_a, w.hc_b, (int)L, 0, 64, st));
+        need = tb > need ? tb : need;
+        IPX_CU(cub::DeviceReduce::ReduceByKey(nullptr, tb, w.hk_b, w.hk_a, w.hc_b, w.hc_a, (uint32_t *)nullptr, cub::Sum(), (int)L, st));
+        need = tb > need ? tb : need;
+        IPX_CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, w.total, w.out.hist_off, (int)(B + 1), st));
+        need = tb > need ? tb : need;
+        if (need > w.cub_tmp_bytes) {
+            if (w.cub_tmp) cudaFree(w.cub_tmp);
+            w.cub_tmp = nullptr;
+            IPX_CU(cudaMalloc(&w.cub_tmp, need));
+            w.cub_tmp_bytes = need;
+        }
+        static const bool no_graph = getenv("IPX_NO_GRAPH") != nullptr;
+        if (!no_graph) {
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                cudaError_t ei = finalize_issue(t, g, d_name_rank, w, st);
+                e = cudaStreamEndCapture(st, &graph);
+                if (ei != cudaSuccess) e = ei;
+            }
+            if (e == cudaSuccess && graph) e = cudaGraphInstantiate(&w.exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (e != cudaSuccess) {
+                cudaGetLastError(); /* capture is not available here: issue the sequence directly every time */
+                w.exec = nullptr;
+            }
+        }
+    }
+    if (w.exec) return cudaGraphLaunch(w.exec, st);
+    return finalize_issue(t, g, d_name_rank, w, st);
+}
+
+bool finalize_check(FinalizeWork &w) {
+    const unsigned long long flags = w.h_count[3];
+    if (flags == 0ull) {
+        w.out.n = w.h_count[0];
+        w.out.n_hist = w.h_count[1];
+        return true;
+    }
+    /* grow what was too small; the next finalize_enqueue reallocates and re-captures */
+    if (flags & FLAG_B) w.wish_B = pow2_ge(w.h_count[4], w.B * 2);
+    if (flags & FLAG_L) w.wish_L = pow2_ge(w.h_count[5], w.L * 2);
+    if (flags & FLAG_R) w.wish_R = pow2_ge(w.h_count[1], w.R * 2);
+    w.out.n = 0;
+    w.out.n_hist = 0;
+    return false;
+}
+
+void free_device_table(DeviceTable &, cudaStream_t) {}
 
 /* ------------------------------------------------------------------ multi-GPU exchange */
 __device__ __forceinline__ int part_of(const Splitters &sp, uint32_t name_rank, uint32_t i0) {
