@@ -255,8 +255,10 @@ def main():
             os.rmdir(tmpdir)
     syn.close()
 
-    stream = torch.cuda.current_stream()
-    eng = _native.Engine(device=local, stream=stream.cuda_stream, profile=True)
+    # the library launches on its own stream; events are recorded on that stream (torch.cuda.Event only sees the
+    # stream it is recorded on)
+    eng = _native.Engine(device=local, profile=True)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=dev)
     eng.set_targets(names)
     devc = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     torch.cuda.synchronize()

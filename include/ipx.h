@@ -231,7 +231,8 @@ int ipx_partial_import(ipx_handle *h, const void *dev_junction_rows, uint64_t n_
 /* Multi-GPU with the canon filter.  Which event creates a junction (add_junction, junctions_extractor.cc:488-506) depends
  * on every earlier read of the whole stream, so with ipx_params.deferred_counting the ranks first agree on it:
  *  ipx_thresholds_rows    settle this rank's local creation thresholds; number and size of the rows to exchange
- *  ipx_thresholds_export  one row per junction key seen here (key + threshold) into a caller-provided DEVICE buffer
+ *  ipx_thresholds_export  one row per junction key seen here (key + threshold) into a caller-provided DEVICE buffer;
+ *                         returns when the rows are complete
  *  ipx_thresholds_import  rows of any rank (DEVICE buffer): a key known here takes the earlier threshold
  *  ipx_count_deferred     count the kept junction events against the agreed thresholds; afterwards the
  *                         ipx_partial_* exchange and ipx_flush work as without the filter */

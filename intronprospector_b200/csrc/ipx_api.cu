@@ -971,6 +971,7 @@ extern "C" int ipx_thresholds_export(ipx_handle *h, void *dev_rows) {
     CU(h, cudaStreamSynchronize(h->stream));
     launch_export_thresholds(h->tab, (ThresholdRow *)dev_rows, nk, h->stream);
     CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream)); /* the rows are complete when this returns: callers hand them to another stream */
     return IPX_OK;
 }
 

@@ -28,6 +28,14 @@ def key_splitters(names, n_parts):
     return split_tid, [0] * (n_parts - 1)
 
 
+def _sync(device):
+    """Host-side join of torch's work on `device` (collectives, copies) before the engine, which launches on its own
+    stream, touches the same buffers.  The engine side is joined by the library (ipx_partial_export and
+    ipx_thresholds_export return after their kernels have finished)."""
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
+
+
 def _byte_tensor(n_bytes, device):
     return torch.empty(max(1, n_bytes), dtype=torch.uint8, device=device)
 
@@ -72,6 +80,7 @@ def exchange_dist(eng, names, device, group=None):
     (send_j, cj), (send_h, ch) = export_partials(eng, names, world, device)
     recv_j, rj = all_to_all_bytes(send_j, cj, group)
     recv_h, rh = all_to_all_bytes(send_h, ch, group)
+    _sync(device)  # the collectives run on torch's stream, the engine on its own: the rows must have landed
     import_partials(eng, recv_j, recv_h)
     return sum(cj) + sum(ch) + sum(rj) + sum(rh)
 
@@ -115,10 +124,10 @@ def agree_thresholds_dist(eng, device, group=None):
     padded[:rows.numel()] = rows
     gathered = [torch.empty(cap, dtype=torch.uint8, device=device) for _ in range(world)]
     dist.all_gather(gathered, padded, group=group)
+    _sync(device)
     for r in range(world):
         if r != dist.get_rank(group) and sizes[r]:
             eng.thresholds_import(gathered[r].data_ptr(), sizes[r] // row_bytes)
-    torch.cuda.current_stream(device).synchronize() if device.type == "cuda" else None
     eng.count_deferred()
     return sum(sizes)
 
