@@ -758,11 +758,12 @@ __global__ void __launch_bounds__(256, 5) k_fold(Tables t, const Event *ev, cons
     if (MODE != MODE_PASS1) olog_finish(t, olog);
 }
 
-/* K2, one lane per event.  No grouping: every lane probes for its own key (lanes of a warp mostly ask for the same few
- * table lines, which the memory system merges) and sends its own fire-and-forget atomics.  Far fewer instructions per
- * event than the grouped form; more atomics, which the L2 has room for. */
-template <int MODE>
-__global__ void __launch_bounds__(256, 5) k_fold_lanes(Tables t, const Event *ev, const TileInfo *tile_info, uint64_t n_tiles) {
+/* K2, one lane per event, EPL events per lane and iteration.  No grouping: every lane probes for its own keys (lanes of
+ * a warp mostly ask for the same few table lines, which the memory system merges) and sends its own fire-and-forget
+ * atomics.  The probes of a lane's EPL events are independent, so their latencies overlap. */
+template <int MODE, int EPL>
+__global__ void __launch_bounds__(256, 4) k_fold_lanes(Tables t, const Event *ev, const TileInfo *tile_info, uint64_t n_tiles,
+                                                        int dbg) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -774,37 +775,46 @@ __global__ void __launch_bounds__(256, 5) k_fold_lanes(Tables t, const Event *ev
         const uint64_t base = tile_event_base(next.y);
         if (tile + n_warps < n_tiles) next = __ldg(reinterpret_cast<const uint2 *>(tile_info + tile + n_warps));
         if (cnt == 0u) continue;
-        Event nxt = load_event(ev, base + lane, (uint32_t)lane < cnt, lane);
-        for (uint32_t k0 = 0; k0 < cnt; k0 += 32u) {
-            const Event e = nxt;
-            const bool valid = k0 + lane < cnt;
-            if (k0 + 32u < cnt) nxt = load_event(ev, base + k0 + 32u + lane, k0 + 32u + lane < cnt, lane);
-            const uint32_t cat = (e.off_cat >> 16) & 3u;
-            const int cls = (int)((e.off_cat >> 18) & 3u);
-            const uint32_t off = e.off_cat & 0xFFFFu;
-            bool counted = false;
-            uint64_t slot = 0;
-            if (valid) {
-                const Probe pr = probe_junction<MODE != MODE_PASS2>(t, e.key, cls);
-                slot = pr.slot;
-                counted = slot <= t.cap_mask;
-                if (MODE == MODE_PASS2) counted = counted && pr.T != EMPTY64 && e.sv >= pr.T; /* earlier events are dropped */
-                if (counted) {
-                    JStat *s = &t.stat[slot];
-                    if (MODE != MODE_PASS2 && e.sv < pr.first) atomicMin(&s->first[cls], e.sv);
-                    if (MODE != MODE_PASS1) {
+        for (uint32_t k0 = 0; k0 < cnt; k0 += 32u * EPL) {
+            Event e[EPL];
+            Probe pr[EPL];
+            bool valid[EPL], counted[EPL];
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                valid[j] = k0 + j * 32u + lane < cnt;
+                e[j] = load_event(ev, base + k0 + j * 32u + lane, valid[j], lane);
+            }
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                pr[j].slot = t.cap_mask + 1;
+                if (valid[j] && !(dbg & 4)) pr[j] = probe_junction<MODE != MODE_PASS2>(t, e[j].key, (int)((e[j].off_cat >> 18) & 3u));
+            }
+#pragma unroll
+            for (int j = 0; j < EPL; ++j) {
+                const uint32_t cat = (e[j].off_cat >> 16) & 3u;
+                const int cls = (int)((e[j].off_cat >> 18) & 3u);
+                counted[j] = valid[j] && pr[j].slot <= t.cap_mask;
+                if (MODE == MODE_PASS2) counted[j] = counted[j] && pr[j].T != EMPTY64 && e[j].sv >= pr[j].T; /* earlier: dropped */
+                if (counted[j]) {
+                    JStat *s = &t.stat[pr[j].slot];
+                    if (MODE != MODE_PASS2 && e[j].sv < pr[j].first) atomicMin(&s->first[cls], e[j].sv);
+                    if (MODE != MODE_PASS1 && !(dbg & 2)) {
                         atomicAdd(&s->cnt[cat], 1ull);
-                        if (e.a0 < pr.a0) atomicMin(&s->a0, e.a0);
-                        if (e.a1 > pr.a1) atomicMax(&s->a1, e.a1);
+                        if (e[j].a0 < pr[j].a0) atomicMin(&s->a0, e[j].a0);
+                        if (e[j].a1 > pr[j].a1) atomicMax(&s->a1, e[j].a1);
                     }
                 }
             }
             if (MODE != MODE_PASS1) {
-                const bool in_row = t.dense != nullptr && off < DENSE_W;
-                /* Junction::count_read's push_back (junctions.hh:163-167), run-length form */
-                if (counted && in_row) atomicAdd(&t.dense[slot * DENSE_W + off], 1u);
-                __syncwarp();
-                olog_append(t, olog, counted && !in_row, olog_entry(slot, off, 1u));
+#pragma unroll
+                for (int j = 0; j < EPL; ++j) {
+                    const uint32_t off = e[j].off_cat & 0xFFFFu;
+                    const bool in_row = t.dense != nullptr && off < DENSE_W;
+                    /* Junction::count_read's push_back (junctions.hh:163-167), run-length form */
+                    if (counted[j] && in_row && !(dbg & 1)) atomicAdd(&t.dense[pr[j].slot * DENSE_W + off], 1u);
+                    __syncwarp();
+                    olog_append(t, olog, counted[j] && !in_row, olog_entry(pr[j].slot, off, 1u));
+                }
             }
         }
     }
@@ -817,12 +827,14 @@ void launch_fold(int mode, const Tables &t, const Event *ev, const TileInfo *til
     const uint64_t want = (n_tiles + 7) / 8; /* 8 warps per block, one tile per warp at a time */
     static const bool grouped = getenv("IPX_K2_GROUPED") != nullptr;
     if (!grouped) {
-        const uint64_t max_lane_blocks = (uint64_t)sm_count * 5;
+        static const int dbg = getenv("IPX_K2_DBG") ? atoi(getenv("IPX_K2_DBG")) : 0;
+        const uint64_t max_lane_blocks = (uint64_t)sm_count * 4;
+        static const int epl = getenv("IPX_K2_EPL") ? atoi(getenv("IPX_K2_EPL")) : 2;
         const int lb = (int)(want < max_lane_blocks ? want : max_lane_blocks);
         switch (mode) {
-            case MODE_SINGLE: k_fold_lanes<MODE_SINGLE><<<lb, 256, 0, st>>>(t, ev, tile_info, n_tiles); break;
-            case MODE_PASS1: k_fold_lanes<MODE_PASS1><<<lb, 256, 0, st>>>(t, ev, tile_info, n_tiles); break;
-            default: k_fold_lanes<MODE_PASS2><<<lb, 256, 0, st>>>(t, ev, tile_info, n_tiles); break;
+            case MODE_SINGLE: if (epl == 1) k_fold_lanes<MODE_SINGLE, 1><<<lb, 256, 0, st>>>(t, ev, tile_info, n_tiles, dbg); else if (epl == 4) k_fold_lanes<MODE_SINGLE, 4><<<lb, 256, 0, st>>>(t, ev, tile_info, n_tiles, dbg); else k_fold_lanes<MODE_SINGLE, 2><<<lb, 256, 0, st>>>(t, ev, tile_info, n_tiles, dbg); break;
+            case MODE_PASS1: if (epl == 1) k_fold_lanes<MODE_PASS1, 1><<<lb, 256, 0, st>>>(t, ev, tile_info, n_tiles, dbg); else if (epl == 4) k_fold_lanes<MODE_PASS1, 4><<<lb, 256, 0, st>>>(t, ev, tile_info, n_tiles, dbg); else k_fold_lanes<MODE_PASS1, 2><<<lb, 256, 0, st>>>(t, ev, tile_info, n_tiles, dbg); break;
+            default: if (epl == 1) k_fold_lanes<MODE_PASS2, 1><<<lb, 256, 0, st>>>(t, ev, tile_info, n_tiles, dbg); else if (epl == 4) k_fold_lanes<MODE_PASS2, 4><<<lb, 256, 0, st>>>(t, ev, tile_info, n_tiles, dbg); else k_fold_lanes<MODE_PASS2, 2><<<lb, 256, 0, st>>>(t, ev, tile_info, n_tiles, dbg); break;
         }
         return;
     }
