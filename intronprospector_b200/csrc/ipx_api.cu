@@ -222,7 +222,9 @@ uint64_t pow2_at_least(uint64_t v) {
 
 int alloc_tables(ipx_handle *h) {
     if (h->tables_ready) return IPX_OK;
-    uint64_t cap = pow2_at_least(h->params.table_capacity ? h->params.table_capacity : (1ull << 22));
+    uint64_t want_cap = h->params.table_capacity ? h->params.table_capacity : (1ull << 22);
+    if (const char *e = getenv("IPX_TABLE_CAP")) want_cap = strtoull(e, nullptr, 10); /* experiments */
+    uint64_t cap = pow2_at_least(want_cap);
     uint64_t hcap = h->params.hist_capacity ? std::max<uint64_t>(h->params.hist_capacity, 1024) : (1ull << 26);
     if (cap > (1ull << 31)) return fail(h, IPX_ERR_ARG, "table_capacity too large");
     Tables &t = h->tab;

@@ -126,8 +126,8 @@ struct EventSink {
         const uint32_t idx = atomicAdd(region_fill, 1u);
         /* one 32-byte event = one DRAM sector: two 16-byte stores from the emitting lane */
         uint4 *dst = reinterpret_cast<uint4 *>(region + idx);
-        dst[0] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)sv, (uint32_t)(sv >> 32));
-        dst[1] = make_uint4((uint32_t)c.anchor_start, (uint32_t)c.anchor_end, off_cat, 0u);
+        __stcs(dst, make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)sv, (uint32_t)(sv >> 32)));
+        __stcs(dst + 1, make_uint4((uint32_t)c.anchor_start, (uint32_t)c.anchor_end, off_cat, 0u));
     }
 };
 
@@ -408,8 +408,8 @@ __device__ __forceinline__ void walk_short(const BatchView &b, const ExtractPara
                 const uint32_t off_cat = (l0 & 0xFFFFu) | (read_category(flag, nh) << 16) | ((uint32_t)strand_class(strand) << 18);
                 const uint32_t idx = atomicAdd(&S.region_fill, 1u);
                 uint4 *dst = reinterpret_cast<uint4 *>(region + idx);
-                dst[0] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)sv, (uint32_t)(sv >> 32));
-                dst[1] = make_uint4(pos, i0 + l1 + l2, off_cat, 0u);
+                __stcs(dst, make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)sv, (uint32_t)(sv >> 32)));
+                __stcs(dst + 1, make_uint4(pos, i0 + l1 + l2, off_cat, 0u));
             }
         }
     }
@@ -633,7 +633,7 @@ __device__ __forceinline__ Event load_event(const Event *ev, uint64_t i, bool va
     Event e;
     if (valid) {
         const uint4 *src = reinterpret_cast<const uint4 *>(ev + i);
-        const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+        const uint4 lo = __ldcs(src), hi = __ldcs(src + 1); /* streamed once: do not displace the tables in L2 */
         e.key = ((unsigned long long)lo.y << 32) | lo.x;
         e.sv = ((unsigned long long)lo.w << 32) | lo.z;
         e.a0 = hi.x; e.a1 = hi.y; e.off_cat = hi.z;
