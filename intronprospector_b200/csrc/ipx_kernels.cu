@@ -260,7 +260,8 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
     return done != 0u;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try(bar, parity, 100000u)) __nanosleep(64);
+    while (!mbar_try(bar, parity, 1000000u)) {
+    } /* try_wait parks the thread on the barrier (NANOSLEEP.SYNCS) until the phase flips or the hint runs out */
 }
 /* TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP) */
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -353,8 +354,8 @@ __device__ __forceinline__ void classify_round(ExStage &S, uint32_t r, int lane,
 static const uint32_t EX_BAR_THREADS = (EX_ROUNDS + EX_WORKER_WARPS) * 32u;
 
 template <bool NAMED>
-__device__ __forceinline__ void take_rounds(ExStage &S, int stage, int lane, LongRec *long_recs, int walk_long_here,
-                                            unsigned long long &live_words) {
+__device__ __forceinline__ void take_rounds(ExStage &S, int stage, uint64_t *classified, int lane, LongRec *long_recs,
+                                            int walk_long_here, unsigned long long &live_words) {
     for (;;) {
         uint32_t r = 0u;
         /* (the plain read spares the atomic when nothing is left; the decision stays lane 0's, so it is warp-uniform) */
@@ -367,8 +368,7 @@ __device__ __forceinline__ void take_rounds(ExStage &S, int stage, int lane, Lon
             __threadfence_block(); /* the lists before the arrival */
             asm volatile("bar.arrive %0, %1;" ::"r"(1u + (uint32_t)stage), "r"(EX_BAR_THREADS) : "memory");
         } else if (lane == 0) {
-            __threadfence_block(); /* the lists before the count */
-            atomicAdd(&S.rounds_done, 1u);
+            mbar_arrive(&classified[stage]); /* release: the lists are visible to whoever sees the phase complete */
         }
     }
 }
@@ -423,11 +423,13 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
     ExStage *stages = reinterpret_cast<ExStage *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + EX_STAGES * sizeof(ExStage)); /* TMA bytes have landed */
     uint64_t *empty = full + EX_STAGES;                                                    /* every worker has left */
+    uint64_t *classified = empty + EX_STAGES;                                              /* all rounds are done */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < EX_STAGES; ++s) {
             mbar_init(&full[s], 1u);
             mbar_init(&empty[s], (uint32_t)EX_WORKER_WARPS);
+            mbar_init(&classified[s], (uint32_t)EX_ROUNDS);
             stages[s].n_lists = stages[s].next_round = stages[s].rounds_done = 0u;
             stages[s].next_short = stages[s].next_long = stages[s].region_fill = 0u;
         }
@@ -497,17 +499,16 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
             if (it + d < my_tiles) {
                 const int s1 = (int)((it + d) % EX_STAGES);
                 if (mbar_test(&full[s1], ((it + d) / EX_STAGES) & 1u))
-                    take_rounds<NAMED>(stages[s1], s1, lane, long_recs, walk_long_here, live_words);
+                    take_rounds<NAMED>(stages[s1], s1, classified, lane, long_recs, walk_long_here, live_words);
             }
         }
         /* (2) this tile must be classified before it can be walked: help with what is left, then wait for the rest */
         mbar_wait(&full[s], (it / EX_STAGES) & 1u);
-        take_rounds<NAMED>(S, s, lane, long_recs, walk_long_here, live_words);
+        take_rounds<NAMED>(S, s, classified, lane, long_recs, walk_long_here, live_words);
         if (NAMED) {
             asm volatile("bar.sync %0, %1;" ::"r"(1u + (uint32_t)s), "r"(EX_BAR_THREADS) : "memory");
         } else {
-            while (*((volatile uint32_t *)&S.rounds_done) < (uint32_t)EX_ROUNDS) __nanosleep(32);
-            __threadfence_block();
+            mbar_wait(&classified[s], (it / EX_STAGES) & 1u);
         }
         /* (3) chunks of this tile: 32 listed records at a time, longest CIGARs first */
         const uint32_t n_lists = *((volatile uint32_t *)&S.n_lists);
@@ -593,7 +594,7 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
                            aligned16(b.flag) && aligned16(b.nh) && aligned16(b.xs) && aligned16(b.cigar_off) && aligned16(b.cigar);
     uint64_t first_simple = 0;
     if (pipelined) {
-        const size_t smem = EX_STAGES * sizeof(ExStage) + 2 * EX_STAGES * sizeof(uint64_t);
+        const size_t smem = EX_STAGES * sizeof(ExStage) + 3 * EX_STAGES * sizeof(uint64_t);
         static const int walk_long_here = getenv("IPX_K1_SPLIT_LONG") ? 0 : 1;
         static const int variant = getenv("IPX_K1_VARIANT") ? atoi(getenv("IPX_K1_VARIANT")) : EX_LOOKAHEAD;
         typedef void (*Kernel)(BatchView, uint32_t, ExtractParams, Tables, Event *, TileInfo *, LongRec *, uint32_t, int);
