@@ -199,8 +199,7 @@ __global__ void __launch_bounds__(EXS_THREADS) k_extract_simple(BatchView b, Ext
  *                        Classification of a tile therefore overlaps the walk of the tile before it, and a warp busy
  *                        with a long walk simply takes fewer units. */
 static const int EX_STAGES = 4;
-static const int EX_WORKER_WARPS = 15;
-static const int EX_THREADS = (EX_WORKER_WARPS + 1) * 32;
+static const int EX_WORKER_WARPS = 15; /* default; 9 / 11 / 13 are instantiated for tuning (IPX_K1_WORKERS) */
 static const int EX_LOOKAHEAD = 1; /* workers classify up to this many tiles ahead of the one they walk */
 static const int EX_ROUNDS = EX_TILE / 128;
 static const int EX_CIG_CAP = 2048; /* staged CIGAR words per tile (average short-read tile: ~1500); words beyond are
@@ -349,11 +348,6 @@ __device__ __forceinline__ void classify_round(ExStage &S, uint32_t r, int lane,
 }
 
 /* take classification rounds of a stage until none is left */
-/* "all rounds of stage s are done": a named barrier per stage.  Every finished round arrives once (the whole warp),
- * every worker waits once; waiting warps are parked by the hardware instead of polling. */
-static const uint32_t EX_BAR_THREADS = (EX_ROUNDS + EX_WORKER_WARPS) * 32u;
-
-template <bool NAMED>
 __device__ __forceinline__ void take_rounds(ExStage &S, int stage, uint64_t *classified, int lane, LongRec *long_recs,
                                             int walk_long_here, unsigned long long &live_words) {
     for (;;) {
@@ -364,12 +358,7 @@ __device__ __forceinline__ void take_rounds(ExStage &S, int stage, uint64_t *cla
         if (r >= (uint32_t)EX_ROUNDS) break;
         classify_round(S, r, lane, long_recs, walk_long_here, live_words);
         __syncwarp();
-        if (NAMED) {
-            __threadfence_block(); /* the lists before the arrival */
-            asm volatile("bar.arrive %0, %1;" ::"r"(1u + (uint32_t)stage), "r"(EX_BAR_THREADS) : "memory");
-        } else if (lane == 0) {
-            mbar_arrive(&classified[stage]); /* release: the lists are visible to whoever sees the phase complete */
-        }
+        if (lane == 0) mbar_arrive(&classified[stage]); /* release: the lists are visible to whoever sees the phase complete */
     }
 }
 
@@ -415,8 +404,8 @@ __device__ __forceinline__ void walk_short(const BatchView &b, const ExtractPara
     }
 }
 
-template <int LOOKAHEAD, bool NAMED>
-__global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint32_t n_cigar_words, ExtractParams p, Tables t,
+template <int LOOKAHEAD, int WORKERS>
+__global__ void __launch_bounds__((WORKERS + 1) * 32, 2) k_extract_tma(BatchView b, uint32_t n_cigar_words, ExtractParams p, Tables t,
                                                                Event *out, TileInfo *tile_info, LongRec *long_recs,
                                                                uint32_t n_full_tiles, int walk_long_here) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -428,7 +417,7 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
     if (threadIdx.x == 0) {
         for (int s = 0; s < EX_STAGES; ++s) {
             mbar_init(&full[s], 1u);
-            mbar_init(&empty[s], (uint32_t)EX_WORKER_WARPS);
+            mbar_init(&empty[s], (uint32_t)WORKERS);
             mbar_init(&classified[s], (uint32_t)EX_ROUNDS);
             stages[s].n_lists = stages[s].next_round = stages[s].rounds_done = 0u;
             stages[s].next_short = stages[s].next_long = stages[s].region_fill = 0u;
@@ -440,7 +429,7 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
     const uint32_t first = blockIdx.x, stride = gridDim.x;
     const uint32_t my_tiles = first < n_full_tiles ? (n_full_tiles - first + stride - 1) / stride : 0u;
 
-    if (warp == EX_WORKER_WARPS) {
+    if (warp == WORKERS) {
         /* ---------------- producer: one lane feeds the ring ---------------- */
         if (lane != 0) return;
         uint32_t nc0 = 0u, nc1 = 0u;
@@ -499,17 +488,13 @@ __global__ void __launch_bounds__(EX_THREADS, 2) k_extract_tma(BatchView b, uint
             if (it + d < my_tiles) {
                 const int s1 = (int)((it + d) % EX_STAGES);
                 if (mbar_test(&full[s1], ((it + d) / EX_STAGES) & 1u))
-                    take_rounds<NAMED>(stages[s1], s1, classified, lane, long_recs, walk_long_here, live_words);
+                    take_rounds(stages[s1], s1, classified, lane, long_recs, walk_long_here, live_words);
             }
         }
         /* (2) this tile must be classified before it can be walked: help with what is left, then wait for the rest */
         mbar_wait(&full[s], (it / EX_STAGES) & 1u);
-        take_rounds<NAMED>(S, s, classified, lane, long_recs, walk_long_here, live_words);
-        if (NAMED) {
-            asm volatile("bar.sync %0, %1;" ::"r"(1u + (uint32_t)s), "r"(EX_BAR_THREADS) : "memory");
-        } else {
-            mbar_wait(&classified[s], (it / EX_STAGES) & 1u);
-        }
+        take_rounds(S, s, classified, lane, long_recs, walk_long_here, live_words);
+        mbar_wait(&classified[s], (it / EX_STAGES) & 1u);
         /* (3) chunks of this tile: 32 listed records at a time, longest CIGARs first */
         const uint32_t n_lists = *((volatile uint32_t *)&S.n_lists);
         const uint32_t n_short = n_lists & 0xFFFFu, n_long = walk_long_here ? n_lists >> 16 : 0u;
@@ -596,10 +581,14 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
     if (pipelined) {
         const size_t smem = EX_STAGES * sizeof(ExStage) + 3 * EX_STAGES * sizeof(uint64_t);
         static const int walk_long_here = getenv("IPX_K1_SPLIT_LONG") ? 0 : 1;
-        static const int variant = getenv("IPX_K1_VARIANT") ? atoi(getenv("IPX_K1_VARIANT")) : EX_LOOKAHEAD;
+        static const int workers_env = getenv("IPX_K1_WORKERS") ? atoi(getenv("IPX_K1_WORKERS")) : EX_WORKER_WARPS;
         typedef void (*Kernel)(BatchView, uint32_t, ExtractParams, Tables, Event *, TileInfo *, LongRec *, uint32_t, int);
-        /* measured on B200 (100 M short reads): polling 0.74 ms, named barrier 1.05 ms, look-ahead 2: 0.77 ms */
-        const Kernel kernel = variant == 11 ? k_extract_tma<1, true> : (variant == 2 ? k_extract_tma<2, false> : k_extract_tma<1, false>);
+        /* measured on B200 (100 M short reads): look-ahead 1 / 2 / 3 tiles: 0.74 / 0.77 / 0.81 ms; named barriers 1.05 ms */
+        Kernel kernel = k_extract_tma<EX_LOOKAHEAD, EX_WORKER_WARPS>;
+        int workers = EX_WORKER_WARPS;
+        if (workers_env == 9) { kernel = k_extract_tma<EX_LOOKAHEAD, 9>; workers = 9; }
+        if (workers_env == 11) { kernel = k_extract_tma<EX_LOOKAHEAD, 11>; workers = 11; }
+        if (workers_env == 13) { kernel = k_extract_tma<EX_LOOKAHEAD, 13>; workers = 13; }
         static bool configured = false;
         if (!configured) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -608,7 +597,7 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
         }
         const uint64_t max_blocks = (uint64_t)sm_count * 2;
         const int blocks = (int)(n_full < max_blocks ? n_full : max_blocks);
-        kernel<<<blocks, EX_THREADS, smem, st>>>(b, (uint32_t)n_cigar, p, t, out, tile_info, long_recs, (uint32_t)n_full,
+        kernel<<<blocks, (workers + 1) * 32, smem, st>>>(b, (uint32_t)n_cigar, p, t, out, tile_info, long_recs, (uint32_t)n_full,
                                                         walk_long_here);
         if (launches) (*launches)++;
         if (!walk_long_here) {
