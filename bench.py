@@ -308,6 +308,15 @@ def main():
     tm = eng.timings()
     ms_per_step = sum(step_ms) / len(step_ms)
 
+    # ---- what the host link alone costs: the same pinned columns copied to the device, nothing else ----
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        for k, v in host.items():
+            devc[k].copy_(v, non_blocking=True)
+        torch.cuda.synchronize()
+    h2d_floor_ms = 1000.0 * (time.perf_counter() - t0) / 3
+
     # ---- end to end through the C ABI with host buffers ----
     table = e2e_step()
     barrier()
@@ -351,7 +360,9 @@ def main():
                                  + ("export + NCCL all-to-all + fold + " if world > 1 else "") + "device finalize, max over ranks",
                        "generate_s": gen_s},
             "e2e": {"value": total_records / (e2e_ms / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms,
+                    "h2d_copy_alone_ms": h2d_floor_ms,
+                    "note": "host-link bound: the pinned columns alone take h2d_copy_alone_ms to reach the device"},
             "gpu_launches": int(tm["extract_launches"] + tm["aggregate_launches"] + tm["finalize_launches"] + tm["motif_launches"]),
             "roofline": {"bound": "hbm", "kernel": "k_extract_tma (K1: TMA-staged CIGAR walk -> junction events; + k_extract_simple on the last partial tile)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,

@@ -589,6 +589,8 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
         if (workers_env == 9) { kernel = k_extract_tma<EX_LOOKAHEAD, 9>; workers = 9; }
         if (workers_env == 11) { kernel = k_extract_tma<EX_LOOKAHEAD, 11>; workers = 11; }
         if (workers_env == 13) { kernel = k_extract_tma<EX_LOOKAHEAD, 13>; workers = 13; }
+        if (workers_env == 17) { kernel = k_extract_tma<EX_LOOKAHEAD, 17>; workers = 17; }
+        if (workers_env == 19) { kernel = k_extract_tma<EX_LOOKAHEAD, 19>; workers = 19; }
         static bool configured = false;
         if (!configured) {
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
