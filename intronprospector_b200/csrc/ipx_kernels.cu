@@ -187,6 +187,79 @@ __global__ void __launch_bounds__(EXS_THREADS) k_extract_simple(BatchView b, Ext
     }
 }
 
+/* ---- K1 for long reads: thread per record, CIGAR words staged through shared memory 32 at a time ----
+ * A long read has hundreds to thousands of CIGAR operations.  Walking them straight from global memory makes every
+ * lane of a warp pull its own 32-byte sector per load; here the warp copies the next 32 words of each of its 32
+ * records with one coalesced 128-byte load per record, and every lane then walks its own record's words from shared
+ * memory (row stride 33 words: conflict-free).  The automaton state stays in registers between segments. */
+static const int EXL_THREADS = 256;
+static const int EXL_WARPS = EXL_THREADS / 32;
+
+__global__ void __launch_bounds__(EXL_THREADS) k_extract_staged(BatchView b, ExtractParams p, Tables t, Event *out,
+                                                                TileInfo *tile_info, uint64_t first_tile, uint64_t n_tiles) {
+    __shared__ uint32_t region_fill;
+    __shared__ uint32_t rows[EXL_WARPS][32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t(*row)[33] = rows[warp];
+    unsigned long long live_words = 0ull, events = 0ull;
+    for (uint64_t tile = first_tile + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (threadIdx.x == 0) region_fill = 0u;
+        __syncthreads();
+        const uint64_t r0 = tile * EX_TILE;
+        const uint32_t first_word = __ldg(&b.cigar_off[r0]);
+        Event *region = out + tile_event_base(first_word);
+        /* a warp takes 32 consecutive records at a time */
+        for (uint64_t g = r0 + (uint64_t)warp * 32; g < r0 + EX_TILE && g < b.n; g += EXL_THREADS) {
+            const uint64_t r = g + lane;
+            uint32_t c0 = 0u, n_cigar = 0u, flag = 0u;
+            int32_t tid = -1;
+            if (r < b.n) {
+                c0 = __ldg(&b.cigar_off[r]);
+                n_cigar = __ldg(&b.cigar_off[r + 1]) - c0;
+                tid = __ldg(&b.tid[r]);
+                flag = __ldg(&b.flag[r]);
+            }
+            const bool live = record_is_live(n_cigar, tid, flag);
+            if (!live) n_cigar = 0u;
+            live_words += n_cigar;
+            const int64_t pos = live ? (int64_t)__ldg(&b.pos[r]) : 0;
+            EventSink sink = make_sink(t, p, region, &region_fill, tid, pos, b.seq_base + r, flag, live ? __ldg(&b.nh[r]) : 0u,
+                                       live ? __ldg(&b.xs[r]) : 0u);
+            WalkState w;
+            w.init(pos);
+            uint32_t bad = 0u;
+            const uint32_t max_n = __reduce_max_sync(0xFFFFFFFFu, n_cigar);
+            for (uint32_t k0 = 0; k0 < max_n; k0 += 32u) {
+                /* stage words [k0, k0 + 32) of every record that still has some */
+#pragma unroll 4
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t nj = __shfl_sync(0xFFFFFFFFu, n_cigar, j);
+                    const uint32_t cj = __shfl_sync(0xFFFFFFFFu, c0, j);
+                    if (k0 + lane < nj) row[j][lane] = __ldg(&b.cigar[cj + k0 + lane]);
+                }
+                __syncwarp();
+                const uint32_t stop = n_cigar > k0 ? (n_cigar - k0 < 32u ? n_cigar - k0 : 32u) : 0u;
+                for (uint32_t k = 0; k < stop && !bad; ++k) bad = walk_op(w, row[lane][k], p.max_anchor_indel_size, sink);
+                __syncwarp();
+            }
+            if (live) {
+                if (bad) atomicMin(t.err_sv, make_err_cigar(b.seq_base + r, bad & 15u)); /* first such record in stream order */
+                else walk_finish(w, sink);
+            }
+            events += sink.n_events;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) tile_info[tile] = TileInfo{region_fill, first_word, 0u, 0u};
+        __syncthreads();
+    }
+    live_words = warp_sum(live_words);
+    events = warp_sum(events);
+    if (lane == 0) {
+        if (live_words) atomicAdd(t.n_live, live_words);
+        if (events) atomicAdd(t.n_events, events);
+    }
+}
+
 /* ---- pipelined K1 ---- */
 /* One block = a producer warp and a pool of worker warps; nothing is synchronised block-wide after start-up.
  *   producer (one lane)  TMA bulk copies of the next tile's columns and CIGAR words into a free stage of the ring;
@@ -610,7 +683,15 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
         }
         first_simple = n_full;
     }
-    if (first_simple < n_tiles) {
+    static const bool no_staged = getenv("IPX_K1_NO_STAGED") != nullptr;
+    if (first_simple < n_tiles && n_cigar > 8 * b.n && !no_staged) {
+        /* long reads */
+        const uint64_t todo = n_tiles - first_simple;
+        const uint64_t max_blocks = (uint64_t)sm_count * 6;
+        k_extract_staged<<<(int)(todo < max_blocks ? todo : max_blocks), EXL_THREADS, 0, st>>>(b, p, t, out, tile_info, first_simple,
+                                                                                                n_tiles);
+        if (launches) (*launches)++;
+    } else if (first_simple < n_tiles) {
         const uint64_t todo = n_tiles - first_simple;
         const uint64_t max_blocks = (uint64_t)sm_count * 8;
         const int blocks = (int)(todo < max_blocks ? todo : max_blocks);
