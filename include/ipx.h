@@ -219,8 +219,9 @@ int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ipx_table **o
  *                      each = first key owned by the next rank: target index, intron_start)
  *  ipx_partial_export  packed junction / histogram rows, destination-major, into caller-provided
  *                      DEVICE buffers (ipx_partial_row_bytes gives the row sizes)
- *  ipx_partial_import  fold rows received from the other ranks (DEVICE buffers) into this rank's
- *                      emptied table; call ipx_flush afterwards. */
+ *  ipx_partial_import  fold the rows received from ONE source rank (DEVICE buffers: offset rows name their junction
+ *                      by its index among the junction rows of the same source) into this rank's emptied table;
+ *                      call once per source, own share included, then ipx_flush. */
 int ipx_partial_row_bytes(uint32_t *junction_row_bytes, uint32_t *hist_row_bytes);
 int ipx_partial_sizes(ipx_handle *h, int32_t n_parts, const int32_t *split_tid, const uint32_t *split_start,
                       uint64_t *junction_rows, uint64_t *hist_rows);

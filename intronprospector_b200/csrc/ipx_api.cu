@@ -129,6 +129,8 @@ struct ipx_handle {
     unsigned long long *d_export = nullptr; /* [2 * MAX_PARTS] counts, then cursors */
     unsigned long long export_counts[2 * MAX_PARTS] = {};
     uint64_t export_keys = 0, export_olog = 0;
+    DeviceBuf slot_jrow; /* [cap] export: junction-row index of each slot */
+    DeviceBuf slot_of;   /* import: table slot of each received junction row */
     bool export_ready = false;
     uint64_t seq_hi = 0; /* one past the largest record stream index pushed so far */
 
@@ -459,7 +461,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq); cudaFree(h->d_export);
     free_genome(h);
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();
-    h->s_off.release(); h->s_cig.release(); h->ev_buf.release(); h->tile_cnt.release(); h->long_buf.release();
+    h->s_off.release(); h->s_cig.release(); h->ev_buf.release(); h->tile_cnt.release(); h->long_buf.release(); h->slot_jrow.release(); h->slot_of.release();
     finalize_release(h->fw);
     cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -909,15 +911,17 @@ extern "C" int ipx_partial_export(ipx_handle *h, void *dev_junction_rows, void *
     unsigned long long j = 0, hh = 0;
     for (int p = 0; p < n_parts; p++) {
         cursors[p] = j;
+        h->export_split.jbase[p] = (uint32_t)j;
         cursors[n_parts + p] = hh;
         j += h->export_counts[p];
         hh += h->export_counts[n_parts + p];
     }
+    CU(h, h->slot_jrow.reserve((h->tab.cap_mask + 1) * sizeof(uint32_t), st));
     CU(h, cudaMemcpyAsync(h->d_export, cursors, 2 * n_parts * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
     {
         Span s(h, &h->tm_finalize, 2);
         launch_export_scatter(h->tab, h->d_name_rank, h->export_split, h->export_keys, h->export_olog, h->d_export,
-                              (JunctionRow *)dev_junction_rows, (HistRow *)dev_hist_rows, st);
+                              (uint32_t *)h->slot_jrow.p, (JunctionRow *)dev_junction_rows, (HistRow *)dev_hist_rows, st);
         /* the local table has been handed over: empty it so that imports (own share included) rebuild it */
         launch_clear_tables(h->tab, st);
     }
@@ -934,10 +938,11 @@ extern "C" int ipx_partial_import(ipx_handle *h, const void *dev_junction_rows, 
     if (h->finalized) return fail(h, IPX_ERR_STATE, "table already finalized");
     int rc = alloc_tables(h);
     if (rc) return rc;
+    CU(h, h->slot_of.reserve((n_junction_rows + 1) * sizeof(uint32_t), h->stream));
     {
         Span s(h, &h->tm_finalize, 2);
         launch_import_rows(h->tab, (const JunctionRow *)dev_junction_rows, n_junction_rows, (const HistRow *)dev_hist_rows,
-                           n_hist_rows, h->stream);
+                           n_hist_rows, (uint32_t *)h->slot_of.p, h->stream);
     }
     CU(h, cudaGetLastError());
     h->dirty = true;

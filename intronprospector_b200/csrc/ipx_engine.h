@@ -53,12 +53,12 @@ struct JunctionRow {
     uint32_t i0, i1, a0, a1;
     uint32_t pad;
 };
+/* one run of a junction's read-offset histogram.  `jrow` is the index of the junction's JunctionRow among the rows the
+ * same source sends to the same destination, so the 8-byte row needs no key (there are ~50 of these per junction) */
 struct HistRow {
-    int32_t tid;
-    uint32_t i0, i1;
-    uint32_t cnt;
-    uint32_t offset;
-    uint32_t pad;
+    uint32_t jrow;
+    uint16_t offset;
+    uint16_t cnt; /* larger counts are sent as several rows */
 };
 
 /* a junction key and its creation threshold, exchanged between ranks (ipx_thresholds_export / _import) */
@@ -109,7 +109,8 @@ void launch_fold(int mode, const Tables &t, const Event *ev, const TileInfo *til
 void launch_resolve_T(const Tables &t, const GenomeView &g, cudaStream_t st);
 void launch_export_thresholds(const Tables &t, ThresholdRow *rows, uint64_t n, cudaStream_t st);
 void launch_import_thresholds(const Tables &t, const ThresholdRow *rows, uint64_t n, cudaStream_t st);
-void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh,
+/* rows of ONE source: the offset rows refer to the junction rows of the same call; slot_of: [nj] scratch */
+void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh, uint32_t *slot_of,
                         cudaStream_t st);
 
 /* workspace for finalize; grown on demand by the engine */
@@ -178,12 +179,13 @@ struct Splitters {
     int32_t n_parts;
     uint32_t rank[MAX_PARTS - 1];  /* first key of parts 1 .. n_parts-1: chromosome-name rank, */
     uint32_t start[MAX_PARTS - 1]; /* intron_start */
+    uint32_t jbase[MAX_PARTS];     /* scatter pass: index of each part's first junction row in the send buffer */
 };
 /* counts / cursors: [2 * n_parts] unsigned long long on the device: junction rows per part, then offset rows per part */
 void launch_export_count(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t n_keys, uint64_t n_olog,
                          unsigned long long *counts, cudaStream_t st);
 void launch_export_scatter(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t n_keys, uint64_t n_olog,
-                           unsigned long long *cursors, JunctionRow *jr, HistRow *hr, cudaStream_t st);
+                           unsigned long long *cursors, uint32_t *slot_jrow, JunctionRow *jr, HistRow *hr, cudaStream_t st);
 
 }  // namespace ipx
 #endif

@@ -1410,9 +1410,11 @@ __device__ __forceinline__ int part_of(const Splitters &sp, uint32_t name_rank, 
 
 /* warp per slot in use: its destination and the number of non-zero counters of its dense offset row.
  * SCATTER = false: count rows per destination; true: write them behind the destination's cursor. */
+__device__ __forceinline__ uint32_t hist_rows_of(uint32_t v) { return v ? (v - 1u) / 0xFFFFu + 1u : 0u; }
+
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_export_slots(Tables t, const uint32_t *name_rank, Splitters sp, uint64_t n_keys,
-                                                      unsigned long long *counts, JunctionRow *jr, HistRow *hr) {
+                                                      unsigned long long *counts, uint32_t *slot_jrow, JunctionRow *jr, HistRow *hr) {
     const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= n_keys) return;
@@ -1430,7 +1432,7 @@ __global__ void __launch_bounds__(256) k_export_slots(Tables t, const uint32_t *
         const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) mine += (v[k] != 0);
+        for (int k = 0; k < 8; ++k) mine += hist_rows_of(v[k]);
     }
     uint32_t incl = mine;
 #pragma unroll
@@ -1447,20 +1449,25 @@ __global__ void __launch_bounds__(256) k_export_slots(Tables t, const uint32_t *
     if (!SCATTER) return;
     jpos = __shfl_sync(0xFFFFFFFFu, jpos, 0);
     hpos = __shfl_sync(0xFFFFFFFFu, hpos, 0);
+    const uint32_t jrow = (uint32_t)jpos - sp.jbase[dest];
     if (lane == 0) {
         JunctionRow r;
         r.first[0] = s.first[0]; r.first[1] = s.first[1]; r.first[2] = s.first[2];
         r.cnt[0] = s.cnt[0]; r.cnt[1] = s.cnt[1]; r.cnt[2] = s.cnt[2];
         r.tid = tid; r.i0 = i0; r.i1 = i1; r.a0 = s.a0; r.a1 = s.a1; r.pad = 0;
         jr[jpos] = r;
+        slot_jrow[slot] = jrow; /* for the log entries of this junction */
     }
     uint64_t o = hpos + (incl - mine);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        if (v[k] != 0) {
+        uint32_t left = v[k];
+        while (left) {
+            const uint32_t piece = left > 0xFFFFu ? 0xFFFFu : left;
             HistRow h;
-            h.tid = tid; h.i0 = i0; h.i1 = i1; h.cnt = v[k]; h.offset = (uint32_t)(lane * 8 + k); h.pad = 0;
+            h.jrow = jrow; h.offset = (uint16_t)(lane * 8 + k); h.cnt = (uint16_t)piece;
             hr[o++] = h;
+            left -= piece;
         }
     }
 }
@@ -1468,23 +1475,19 @@ __global__ void __launch_bounds__(256) k_export_slots(Tables t, const uint32_t *
 /* thread per entry of the read-offset log: one offset row each (equal pairs are summed by the importer) */
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_export_olog(Tables t, const uint32_t *name_rank, Splitters sp, uint64_t n_olog,
-                                                     unsigned long long *counts, HistRow *hr) {
+                                                     unsigned long long *counts, const uint32_t *slot_jrow, HistRow *hr) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     int dest = -1 - lane; /* idle lanes group with nobody */
     unsigned long long e = OLOG_INVALID;
-    int32_t tid = 0;
-    uint32_t i0 = 0, i1 = 0;
+    uint32_t slot = 0u;
     if (i < n_olog) {
         e = t.olog[i];
         if (e != OLOG_INVALID) {
-            const uint32_t slot = (uint32_t)(e >> 32);
+            slot = (uint32_t)(e >> 32);
             if (t.stat[slot].T != EMPTY64) {
                 const unsigned long long key = t.keys[slot];
-                tid = key_tid(t.kl, key);
-                i0 = key_start(t.kl, key);
-                i1 = i0 + key_len(t.kl, key);
-                dest = part_of(sp, name_rank[tid], i0);
+                dest = part_of(sp, name_rank[key_tid(t.kl, key)], key_start(t.kl, key));
             }
         }
     }
@@ -1497,29 +1500,30 @@ __global__ void __launch_bounds__(256) k_export_olog(Tables t, const uint32_t *n
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
     if (dest >= 0) {
         HistRow h;
-        h.tid = tid; h.i0 = i0; h.i1 = i1; h.cnt = (uint32_t)(e & 0xFFFFull); h.offset = (uint32_t)((e >> 16) & 0xFFFFull); h.pad = 0;
+        h.jrow = slot_jrow[slot]; h.offset = (uint16_t)((e >> 16) & 0xFFFFull); h.cnt = (uint16_t)(e & 0xFFFFull);
         hr[base + __popc(grp & ((1u << lane) - 1u))] = h;
     }
 }
 
 void launch_export_count(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t n_keys, uint64_t n_olog,
                          unsigned long long *counts, cudaStream_t st) {
-    if (n_keys) k_export_slots<false><<<blocks_for(n_keys * 32, 256), 256, 0, st>>>(t, name_rank, sp, n_keys, counts, nullptr, nullptr);
-    if (n_olog) k_export_olog<false><<<blocks_for(n_olog, 256), 256, 0, st>>>(t, name_rank, sp, n_olog, counts, nullptr);
+    if (n_keys) k_export_slots<false><<<blocks_for(n_keys * 32, 256), 256, 0, st>>>(t, name_rank, sp, n_keys, counts, nullptr, nullptr, nullptr);
+    if (n_olog) k_export_olog<false><<<blocks_for(n_olog, 256), 256, 0, st>>>(t, name_rank, sp, n_olog, counts, nullptr, nullptr);
 }
 
 void launch_export_scatter(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t n_keys, uint64_t n_olog,
-                           unsigned long long *cursors, JunctionRow *jr, HistRow *hr, cudaStream_t st) {
-    if (n_keys) k_export_slots<true><<<blocks_for(n_keys * 32, 256), 256, 0, st>>>(t, name_rank, sp, n_keys, cursors, jr, hr);
-    if (n_olog) k_export_olog<true><<<blocks_for(n_olog, 256), 256, 0, st>>>(t, name_rank, sp, n_olog, cursors, hr);
+                           unsigned long long *cursors, uint32_t *slot_jrow, JunctionRow *jr, HistRow *hr, cudaStream_t st) {
+    if (n_keys) k_export_slots<true><<<blocks_for(n_keys * 32, 256), 256, 0, st>>>(t, name_rank, sp, n_keys, cursors, slot_jrow, jr, hr);
+    if (n_olog) k_export_olog<true><<<blocks_for(n_olog, 256), 256, 0, st>>>(t, name_rank, sp, n_olog, cursors, slot_jrow, hr);
 }
 
-__global__ void k_import_junction_rows(Tables t, const JunctionRow *jr, uint64_t n) {
+__global__ void k_import_junction_rows(Tables t, const JunctionRow *jr, uint64_t n, uint32_t *slot_of) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const JunctionRow r = jr[i];
     const uint64_t key = make_key(t.kl, r.tid, r.i0, r.i1);
     const uint64_t slot = junction_find_or_insert(t, key);
+    slot_of[i] = slot <= t.cap_mask ? (uint32_t)slot : 0xFFFFFFFFu;
     if (slot > t.cap_mask) return;
     JStat *s = &t.stat[slot];
     for (int c = 0; c < 3; ++c) {
@@ -1530,26 +1534,20 @@ __global__ void k_import_junction_rows(Tables t, const JunctionRow *jr, uint64_t
     atomicMax(&s->a1, r.a1);
 }
 
-__global__ void k_import_hist_rows(Tables t, const HistRow *hr, uint64_t n) {
+__global__ void k_import_hist_rows(Tables t, const HistRow *hr, uint64_t n, const uint32_t *slot_of, uint64_t nj) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     OlogWriter olog{0ull, 0u};
-    uint64_t slot = 0;
-    uint32_t off = 0u, left = 0u;
+    uint32_t slot = 0xFFFFFFFFu, off = 0u, cnt = 0u;
     if (i < n) {
         const HistRow r = hr[i];
-        slot = junction_find_or_insert(t, make_key(t.kl, r.tid, r.i0, r.i1));
-        off = r.offset & 0xFFFFu;
-        if (slot <= t.cap_mask) {
-            if (t.dense != nullptr && off < DENSE_W) atomicAdd(&t.dense[slot * DENSE_W + off], r.cnt);
-            else left = r.cnt;
-        }
+        if (r.jrow < nj) slot = slot_of[r.jrow];
+        off = r.offset;
+        cnt = r.cnt;
     }
-    /* log entries hold 16-bit counts */
-    while (__any_sync(0xFFFFFFFFu, left != 0u)) {
-        const uint32_t piece = left > 0xFFFFu ? 0xFFFFu : left;
-        olog_append(t, olog, piece != 0u, olog_entry(slot, off, piece));
-        left -= piece;
-    }
+    const bool ok = slot != 0xFFFFFFFFu && cnt != 0u;
+    const bool in_row = t.dense != nullptr && off < DENSE_W;
+    if (ok && in_row) atomicAdd(&t.dense[(uint64_t)slot * DENSE_W + off], cnt);
+    olog_append(t, olog, ok && !in_row, olog_entry(slot, off, cnt));
     olog_finish(t, olog);
 }
 
@@ -1584,10 +1582,10 @@ void launch_import_thresholds(const Tables &t, const ThresholdRow *rows, uint64_
     if (n) k_import_thresholds<<<blocks_for(n, 256), 256, 0, st>>>(t, rows, n);
 }
 
-void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh,
+void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh, uint32_t *slot_of,
                         cudaStream_t st) {
-    if (nj) k_import_junction_rows<<<blocks_for(nj, 256), 256, 0, st>>>(t, jr, nj);
-    if (nh) k_import_hist_rows<<<blocks_for(nh, 256), 256, 0, st>>>(t, hr, nh);
+    if (nj) k_import_junction_rows<<<blocks_for(nj, 256), 256, 0, st>>>(t, jr, nj, slot_of);
+    if (nh) k_import_hist_rows<<<blocks_for(nh, 256), 256, 0, st>>>(t, hr, nh, slot_of, nj);
 }
 
 }  // namespace ipx

@@ -52,10 +52,16 @@ def export_partials(eng, names, n_parts, device):
     return (send_j, [x * jb for x in jrows]), (send_h, [x * hb for x in hrows])
 
 
-def import_partials(eng, recv_j, recv_h):
+def import_partials(eng, recv_j, bytes_j, recv_h, bytes_h):
+    """Fold what every source sent: recv_* hold the sources' segments back to back (bytes_* per source).  One import
+    per source, because offset rows name their junction by its index within the same source's junction rows."""
     jb, hb = eng.partial_row_bytes()
-    eng.partial_import(recv_j.data_ptr(), recv_j.numel() // jb if recv_j.numel() >= jb else 0,
-                       recv_h.data_ptr(), recv_h.numel() // hb if recv_h.numel() >= hb else 0)
+    oj = oh = 0
+    for nj, nh in zip(bytes_j, bytes_h):
+        if nj or nh:
+            eng.partial_import(recv_j.data_ptr() + oj, nj // jb, recv_h.data_ptr() + oh, nh // hb)
+        oj += nj
+        oh += nh
 
 
 def all_to_all_bytes(send, send_counts, group=None):
@@ -81,7 +87,7 @@ def exchange_dist(eng, names, device, group=None):
     recv_j, rj = all_to_all_bytes(send_j, cj, group)
     recv_h, rh = all_to_all_bytes(send_h, ch, group)
     _sync(device)  # the collectives run on torch's stream, the engine on its own: the rows must have landed
-    import_partials(eng, recv_j, recv_h)
+    import_partials(eng, recv_j, rj, recv_h, rh)
     return sum(cj) + sum(ch) + sum(rj) + sum(rh)
 
 
@@ -99,7 +105,7 @@ def exchange_local(engines, names, device):
             pieces_h.append(sh[oh:oh + ch[dst]])
         rj, rh = torch.cat(pieces_j), torch.cat(pieces_h)
         moved += rj.numel() + rh.numel()
-        import_partials(eng, rj, rh)
+        import_partials(eng, rj, [p.numel() for p in pieces_j], rh, [p.numel() for p in pieces_h])
     return moved
 
 

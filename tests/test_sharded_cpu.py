@@ -15,7 +15,7 @@ from intronprospector_b200 import sharded
 
 JROW = np.dtype([("first", "<u8", 3), ("cnt", "<u8", 3), ("tid", "<i4"), ("i0", "<u4"), ("i1", "<u4"), ("a0", "<u4"),
                  ("a1", "<u4"), ("pad", "<u4")])
-HROW = np.dtype([("tid", "<i4"), ("i0", "<u4"), ("i1", "<u4"), ("cnt", "<u4"), ("offset", "<u4"), ("pad", "<u4")])
+HROW = np.dtype([("jrow", "<u4"), ("offset", "<u2"), ("cnt", "<u2")])
 
 
 def test_wire_layout_matches_the_library(built):
@@ -46,37 +46,45 @@ def test_global_numbering():
 
 
 class StandInEngine:
-    """Speaks the ipx_partial_* protocol with real row layouts; its 'table' is a list of rows in key order."""
+    """Speaks the ipx_partial_* protocol with the real row layouts; its 'table' is a list of junction rows in key order
+    and offset rows that name their junction by position."""
 
     def __init__(self, names, rows_j, rows_h):
         self.names = names
         self.rank_of = {t: r for r, t in enumerate(sorted(range(len(names)), key=lambda i: names[i].encode()))}
-        key = lambda r: (self.rank_of[int(r["tid"])], int(r["i0"]), int(r["i1"]))
-        self.j = np.array(sorted(rows_j, key=key), dtype=JROW)
-        self.h = np.array(sorted(rows_h, key=key), dtype=HROW)
-        self.got_j = self.got_h = None
+        order = sorted(range(len(rows_j)), key=lambda i: (self.rank_of[int(rows_j[i]["tid"])], int(rows_j[i]["i0"]), int(rows_j[i]["i1"])))
+        new_index = {old: new for new, old in enumerate(order)}
+        self.j = np.array([rows_j[i] for i in order], dtype=JROW)
+        h = np.array(rows_h, dtype=HROW)
+        h["jrow"] = [new_index[int(x)] for x in h["jrow"]]
+        self.h = h[np.argsort(h["jrow"], kind="stable")]
+        self.got = []
 
     def partial_row_bytes(self):
         return JROW.itemsize, HROW.itemsize
 
-    def _part(self, rows, n_parts, split_tid):
+    def _part_of_junctions(self, n_parts, split_tid):
         bounds = [self.rank_of[t] for t in split_tid] + [len(self.names)]
-        part = np.zeros(len(rows), np.int64)
-        for i, r in enumerate(rows):
-            part[i] = next(p for p in range(n_parts) if self.rank_of[int(r["tid"])] < bounds[p])
-        return part
+        return np.array([next(p for p in range(n_parts) if self.rank_of[int(r["tid"])] < bounds[p]) for r in self.j], np.int64)
 
     def partial_sizes(self, n_parts, split_tid, split_start):
-        pj, ph = self._part(self.j, n_parts, split_tid), self._part(self.h, n_parts, split_tid)
-        return [int((pj == p).sum()) for p in range(n_parts)], [int((ph == p).sum()) for p in range(n_parts)]
+        self.pj = self._part_of_junctions(n_parts, split_tid)
+        ph = self.pj[self.h["jrow"]]
+        return [int((self.pj == p).sum()) for p in range(n_parts)], [int((ph == p).sum()) for p in range(n_parts)]
 
     def partial_export(self, ptr_j, ptr_h):
+        # junction rows are in key order, so each part is a contiguous run; offset rows follow their junctions
+        first = {int(p): int(np.flatnonzero(self.pj == p)[0]) for p in np.unique(self.pj)}
+        h = self.h.copy()
+        h["jrow"] = [int(x) - first[int(self.pj[int(x)])] for x in self.h["jrow"]]
         C.memmove(ptr_j, self.j.ctypes.data, self.j.nbytes)
-        C.memmove(ptr_h, self.h.ctypes.data, self.h.nbytes)
+        C.memmove(ptr_h, h.ctypes.data, h.nbytes)
 
     def partial_import(self, ptr_j, nj, ptr_h, nh):
-        self.got_j = np.frombuffer(C.string_at(ptr_j, nj * JROW.itemsize), dtype=JROW).copy()
-        self.got_h = np.frombuffer(C.string_at(ptr_h, nh * HROW.itemsize), dtype=HROW).copy()
+        j = np.frombuffer(C.string_at(ptr_j, nj * JROW.itemsize), dtype=JROW).copy()
+        h = np.frombuffer(C.string_at(ptr_h, nh * HROW.itemsize), dtype=HROW).copy()
+        assert (h["jrow"] < max(1, nj)).all()
+        self.got.append((j, h))
 
 
 def make_rows(rank, n_targets, seed):
@@ -89,12 +97,16 @@ def make_rows(rank, n_targets, seed):
     rows_j["cnt"][:, 0] = rank * 1000 + np.arange(nj)
     nh = 900 + 11 * rank
     rows_h = np.zeros(nh, HROW)
-    pick = rng.integers(0, nj, nh)
-    for k in ("tid", "i0", "i1"):
-        rows_h[k] = rows_j[k][pick]
+    rows_h["jrow"] = rng.integers(0, nj, nh)
     rows_h["cnt"] = rank * 7 + 1
     rows_h["offset"] = rng.integers(0, 65536, nh)
     return list(rows_j), list(rows_h)
+
+
+def resolved(rows_j, rows_h):
+    """offset rows with their junction's key instead of its index: what must survive the exchange"""
+    return sorted((int(rows_j[int(h["jrow"])]["tid"]), int(rows_j[int(h["jrow"])]["i0"]), int(rows_j[int(h["jrow"])]["i1"]),
+                   int(h["offset"]), int(h["cnt"])) for h in rows_h)
 
 
 def _worker(rank, world, port, names, out_dir):
@@ -104,9 +116,10 @@ def _worker(rank, world, port, names, out_dir):
     try:
         eng = StandInEngine(names, *make_rows(rank, len(names), 99))
         moved = sharded.exchange_dist(eng, names, torch.device("cpu"))
-        np.save(os.path.join(out_dir, "j%d.npy" % rank), eng.got_j)
-        np.save(os.path.join(out_dir, "h%d.npy" % rank), eng.got_h)
-        assert moved > 0
+        for src, (j, h) in enumerate(eng.got):
+            np.save(os.path.join(out_dir, "j%d_%d.npy" % (rank, src)), j)
+            np.save(os.path.join(out_dir, "h%d_%d.npy" % (rank, src)), h)
+        assert moved > 0 and len(eng.got) == world
     finally:
         dist.destroy_process_group()
 
@@ -122,21 +135,23 @@ def test_key_range_exchange_over_gloo(tmp_path):
     rank_of = {t: r for r, t in enumerate(sorted(range(len(names)), key=lambda i: names[i].encode()))}
     split_tid, _ = sharded.key_splitters(names, world)
     bounds = [rank_of[t] for t in split_tid] + [len(names)]
-    sent_j = np.concatenate([np.array(make_rows(r, len(names), 99)[0], dtype=JROW) for r in range(world)])
-    sent_h = np.concatenate([np.array(make_rows(r, len(names), 99)[1], dtype=HROW) for r in range(world)])
-    got_j = [np.load(str(tmp_path / ("j%d.npy" % r))) for r in range(world)]
-    got_h = [np.load(str(tmp_path / ("h%d.npy" % r))) for r in range(world)]
-    # every row reached exactly the owner of its key range, nothing was lost or duplicated
+    sent_j, sent_h = [], []
     for r in range(world):
-        lo = 0 if r == 0 else bounds[r - 1]
-        for rows in (got_j[r], got_h[r]):
-            ranks = np.array([rank_of[int(t)] for t in rows["tid"]])
-            assert ((ranks >= lo) & (ranks < bounds[r])).all()
-    assert sorted(np.concatenate(got_j).tobytes()[i:i + JROW.itemsize] for i in range(0, sent_j.nbytes, JROW.itemsize)) == \
-        sorted(sent_j.tobytes()[i:i + JROW.itemsize] for i in range(0, sent_j.nbytes, JROW.itemsize))
-    assert sorted(np.concatenate(got_h).tobytes()[i:i + HROW.itemsize] for i in range(0, sent_h.nbytes, HROW.itemsize)) == \
-        sorted(sent_h.tobytes()[i:i + HROW.itemsize] for i in range(0, sent_h.nbytes, HROW.itemsize))
-    # rows of one source arrive contiguously, sources in rank order (the owner folds partials in stream order)
-    for r in range(world):
-        src = got_j[r]["cnt"][:, 0] // 1000
-        assert (np.diff(src.astype(np.int64)) >= 0).all()
+        rj, rh = make_rows(r, len(names), 99)
+        sent_j += [bytes(np.array(x, dtype=JROW).tobytes()) for x in rj]
+        sent_h += resolved(rj, rh)
+    got_j, got_h = [], []
+    for dst in range(world):
+        lo = 0 if dst == 0 else bounds[dst - 1]
+        for src in range(world):
+            j = np.load(str(tmp_path / ("j%d_%d.npy" % (dst, src))))
+            h = np.load(str(tmp_path / ("h%d_%d.npy" % (dst, src))))
+            # every junction row reached the owner of its key range, from the right source
+            ranks = np.array([rank_of[int(t)] for t in j["tid"]])
+            assert ((ranks >= lo) & (ranks < bounds[dst])).all()
+            assert ((j["cnt"][:, 0] // 1000) == src).all()
+            got_j += [bytes(x.tobytes()) for x in j]
+            got_h += resolved(list(j), list(h))
+    # nothing was lost, duplicated or attached to another junction
+    assert sorted(got_j) == sorted(sent_j)
+    assert sorted(got_h) == sorted(sent_h)
