@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(EXS_THREADS) k_extract_simple(BatchView b, Ext
             uint32_t bad = 0u;
             const uint32_t *cig = b.cigar + c0;
             for (uint32_t k = 0; k < n_cigar; ++k) {
-                bad = walk_op(w, __ldg(&cig[k]), p.max_anchor_indel_size, sink);
+                bad = walk_op_flat(w, __ldg(&cig[k]), p.max_anchor_indel_size, sink);
                 if (bad) break;
             }
             if (bad) {
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(EXL_THREADS) k_extract_staged(BatchView b, Ext
                 }
                 __syncwarp();
                 const uint32_t stop = n_cigar > k0 ? (n_cigar - k0 < 32u ? n_cigar - k0 : 32u) : 0u;
-                for (uint32_t k = 0; k < stop && !bad; ++k) bad = walk_op(w, row[lane][k], p.max_anchor_indel_size, sink);
+                for (uint32_t k = 0; k < stop && !bad; ++k) bad = walk_op_flat(w, row[lane][k], p.max_anchor_indel_size, sink);
                 __syncwarp();
             }
             if (live) {
@@ -358,7 +358,7 @@ __device__ __forceinline__ void walk_record(const BatchView &b, const ExtractPar
     w.init(pos);
     uint32_t bad = 0u;
     for (uint32_t k = 0; k < n_cigar; ++k) {
-        bad = walk_op(w, cigar_word(S, b.cigar, c0 + k), p.max_anchor_indel_size, sink);
+        bad = walk_op_flat(w, cigar_word(S, b.cigar, c0 + k), p.max_anchor_indel_size, sink);
         if (bad) break;
     }
     if (bad) {
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(256) k_extract_long(BatchView b, ExtractParams
             w.init(pos);
             uint32_t bad = 0u;
             for (uint32_t k = 0; k < n_cigar; ++k) {
-                bad = walk_op(w, __ldg(&b.cigar[c0 + k]), p.max_anchor_indel_size, sink);
+                bad = walk_op_flat(w, __ldg(&b.cigar[c0 + k]), p.max_anchor_indel_size, sink);
                 if (bad) break;
             }
             if (bad) {

@@ -181,6 +181,59 @@ IPX_HD uint32_t walk_op(WalkState &w, uint32_t word, uint32_t max_indel, Emit &e
     return 0u;
 }
 
+/* The same transition function without data-dependent branches (selects only; the rare emission stays a branch).
+ * In a warp that walks 32 different reads, walk_op executes every branch some lane takes -- with long reads that is
+ * all of them, every step; this form executes one straight-line body.  tests/native/walk_fuzz.cc holds the two
+ * equal on random CIGARs. */
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class Emit>
+IPX_HD uint32_t walk_op_flat(WalkState &w, uint32_t word, uint32_t max_indel, Emit &emit) {
+    const uint32_t op = word & 15u;
+    const uint32_t len = word >> 4;
+    const bool is_al = ((0x181u >> op) & 1u) != 0u; /* M = X */
+    const bool is_x = op == OP_X;
+    const bool is_n = op == OP_N;
+    const bool is_di = op == OP_I || op == OP_D;
+    const bool is_cl = op == OP_S || op == OP_H;
+    if (!(is_al | is_n | is_di | is_cl)) return 0x100u | op;
+    const int st = w.state;
+    /* enter_query_delete / enter_query_insert: the indel is counted before the break test */
+    w.lind += (is_di && st == ST_LEFT) ? len : 0u;
+    w.rind += (is_di && st == ST_RIGHT) ? len : 0u;
+    const uint32_t cur = is_di ? w.cur + len : (is_cl ? w.cur : 0u);
+    const bool brk = is_di && cur > max_indel;
+    if (st == ST_RIGHT && (is_n | is_cl | brk)) emit_candidate(w, emit);
+    /* enter_intron on a right anchor: it becomes the next junction's left anchor */
+    const bool shift = is_n && st == ST_RIGHT;
+    w.a0 = shift ? w.i1 : w.a0;
+    w.lmm = shift ? w.rmm : w.lmm;
+    w.lind = shift ? w.rind : w.lind;
+    w.rmm = shift ? 0u : w.rmm;
+    w.rind = shift ? 0u : w.rind;
+    const bool open_intron = is_n && (st == ST_RIGHT || st == ST_LEFT);
+    w.i0 = open_intron ? w.tpos : w.i0;
+    /* enter_aligned */
+    const bool from_limbo = is_al && st == ST_LIMBO, from_intron = is_al && st == ST_INTRON;
+    w.a0 = from_limbo ? w.tpos : w.a0;
+    w.lmm = from_limbo ? 0u : w.lmm;
+    w.rmm = from_limbo ? 0u : w.rmm;
+    w.i1 = open_intron ? w.tpos + len : (from_intron ? w.tpos : w.i1);
+    w.a1 = is_al ? w.tpos + len : w.a1;
+    int ns = st;
+    ns = (is_cl | brk) ? ST_LIMBO : ns;
+    ns = open_intron ? ST_INTRON : ns;
+    ns = from_limbo ? ST_LEFT : ns;
+    ns = from_intron ? ST_RIGHT : ns;
+    w.lmm += (is_x && ns == ST_LEFT) ? len : 0u;
+    w.rmm += (is_x && ns != ST_LEFT) ? len : 0u;
+    w.state = ns;
+    w.cur = cur;
+    w.tpos += (is_al | is_n | (op == OP_D)) ? (int64_t)len : 0;
+    return 0u;
+}
+
 /* finish (junctions_extractor.cc:278-282) */
 #if defined(__CUDACC__)
 #pragma nv_exec_check_disable
