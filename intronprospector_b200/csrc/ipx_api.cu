@@ -235,6 +235,7 @@ int alloc_tables(ipx_handle *h) {
     CU(h, cudaMalloc(&t.olog, hcap * sizeof(unsigned long long)));
     t.olog_cap = hcap;
     CU(h, cudaMalloc(&t.slot_list, cap * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&t.slot_id, cap * sizeof(uint32_t)));
     /* dense offset rows: 1 KB per slot, so up to 16 GB of the 180 GB; beyond that every offset goes to the hash */
     t.dense = nullptr;
     if (cap <= (1ull << 24) && !getenv("IPX_NO_DENSE")) {
@@ -457,7 +458,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     cudaStreamSynchronize(h->stream);
     drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
     drop_deferred(h);
-    cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.olog); cudaFree(h->tab.slot_list); cudaFree(h->tab.dense);
+    cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.olog); cudaFree(h->tab.slot_list); cudaFree(h->tab.slot_id); cudaFree(h->tab.dense);
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq); cudaFree(h->d_export);
     free_genome(h);
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();

@@ -125,10 +125,14 @@ struct FinalizeWork {
     unsigned long long *sort_key = nullptr, *sort_key2 = nullptr, *hash_lo = nullptr, *total = nullptr, *hk_a = nullptr,
                        *hk_b = nullptr;
     uint32_t *slot_a = nullptr, *slot_b = nullptr, *idx_b = nullptr, *dense_nz = nullptr, *hc_a = nullptr, *hc_b = nullptr;
-    uint32_t *slot_rank = nullptr; /* [cap] key-order rank of each slot, for the read-offset log */
-    uint64_t slot_rank_cap = 0;
-    void *cub_tmp = nullptr;
+    /* the sjN chain and the read-offset-log chain run beside the key-order chain, each on its own stream (inside the
+     * graph: parallel branches) with its own scratch */
+    unsigned long long *tkey = nullptr, *tkey2 = nullptr, *total_j = nullptr; /* [B] */
+    uint32_t *tidx_a = nullptr, *tidx_b = nullptr, *t_rank = nullptr;        /* [B] */
+    void *cub_tmp = nullptr, *cub_tmp2 = nullptr, *cub_tmp3 = nullptr;
     size_t cub_tmp_bytes = 0;
+    cudaStream_t s2 = nullptr, s3 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
     /* [8]: 0 junctions, 1 histogram runs, 2 distinct log runs (uint32), 3 flags (1: B too small, 2: L, 4: R),
      *      4 keys seen, 5 log entries seen */
     unsigned long long *d_count = nullptr;

@@ -748,7 +748,9 @@ __device__ __forceinline__ Probe probe_junction(const Tables &t, unsigned long l
             if (!INSERT) break;
             const unsigned long long old = atomicCAS(&t.keys[h], EMPTY64, key);
             if (old == EMPTY64) {
-                t.slot_list[atomicAdd(t.n_keys, 1ull)] = (uint32_t)h;
+                const unsigned long long id = atomicAdd(t.n_keys, 1ull);
+                t.slot_list[id] = (uint32_t)h;
+                t.slot_id[h] = (uint32_t)id;
                 return r; /* the record of a free slot holds the reset values */
             }
             if (old == key) {
@@ -1055,33 +1057,32 @@ __global__ void k_list_keys(Tables t, const uint32_t *name_rank, uint64_t B, int
     if (mask && (threadIdx.x & 31) == 0) atomicAdd(&d_count[0], (unsigned long long)__popc(mask));
 }
 
-__global__ void k_fill_slot_rank(const uint32_t *sorted_slot, const unsigned long long *d_count, uint32_t *slot_rank) {
+/* sjN chain, keyed by position in slot_list (j): sort key = the creating event's position in the stream (sv without
+ * its strand byte); keys that are not junctions and padding sort last */
+__global__ void k_list_T(Tables t, uint64_t B, int t_bits, unsigned long long *T_out, uint32_t *idx_out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < d_count[0]) slot_rank[sorted_slot[i]] = (uint32_t)i;
+    if (i >= B) return;
+    const unsigned long long nk = *t.n_keys < B ? *t.n_keys : B;
+    unsigned long long T = EMPTY64;
+    if (i < nk) T = t.stat[t.slot_list[i]].T;
+    T_out[i] = T == EMPTY64 ? (1ull << t_bits) : (T >> 8);
+    idx_out[i] = (uint32_t)i;
 }
 
-/* sort key of the sjN ranking: the creating event's position in the stream (sv without its strand byte) */
-__global__ void k_gather_T(Tables t, const uint32_t *sorted_slot, const unsigned long long *d_count, uint64_t B, int t_bits,
-                           unsigned long long *T_out, uint32_t *idx_out) {
+/* t_rank[j] = rank of junction j's creating event = its sjN */
+__global__ void k_scatter_trank(const unsigned long long *sorted_T, const uint32_t *j_by_T, uint64_t B, int t_bits, uint32_t *t_rank) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) {
-        T_out[i] = i < d_count[0] ? (t.stat[sorted_slot[i]].T >> 8) : (1ull << t_bits);
-        idx_out[i] = (uint32_t)i;
-    }
-}
-
-__global__ void k_scatter_ijunc(const uint32_t *idx_by_T, const unsigned long long *d_count, uint32_t *ijunc) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < d_count[0]) ijunc[idx_by_T[i]] = (uint32_t)i;
+    if (i < B && !(sorted_T[i] >> t_bits)) t_rank[j_by_T[i]] = (uint32_t)i;
 }
 
 /* one output row per junction, in key order: attributes of the creating event after motif correction
  * (get_splice_sites + correct_strand, junctions_extractor.cc:419-444) */
 __global__ void k_gather_rows(Tables t, GenomeView g, const uint32_t *sorted_slot, const unsigned long long *d_count,
-                              DeviceTable out) {
+                              const uint32_t *t_rank, DeviceTable out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d_count[0]) return;
     const uint32_t slot = sorted_slot[i];
+    out.ijunc[i] = t_rank[t.slot_id[slot]];
     const unsigned long long key = t.keys[slot];
     const JStat s = t.stat[slot];
     const int32_t tid = key_tid(t.kl, key);
@@ -1124,20 +1125,25 @@ __global__ void k_gather_rows(Tables t, GenomeView g, const uint32_t *sorted_slo
     for (int k = 0; k < 8; ++k) out.sites[8 * i + k] = site[k];
 }
 
-/* every offset-log entry -> (junction rank << 16 | offset, count); padding, invalid entries and entries of slots that
- * are not junctions (none are expected) get a key above every real one */
-__global__ void k_olog_pairs(Tables t, const uint32_t *slot_rank, uint64_t L, int h_bits, unsigned long long *hkey_out,
-                             uint32_t *hcnt_out) {
+/* every offset-log entry -> (junction j << 16 | offset, count), j = the slot's position in slot_list; padding, invalid
+ * entries and entries of slots that are not junctions (none are expected) get a key above every real one */
+__global__ void k_olog_pairs(Tables t, uint64_t L, int h_bits, unsigned long long *hkey_out, uint32_t *hcnt_out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L) return;
     const unsigned long long nl = *t.n_olog < L ? *t.n_olog : L;
     const unsigned long long e = i < nl ? t.olog[i] : OLOG_INVALID;
-    const uint32_t r = e == OLOG_INVALID ? 0xFFFFFFFFu : slot_rank[e >> 32];
-    hkey_out[i] = r == 0xFFFFFFFFu ? (1ull << h_bits) : (((unsigned long long)r << 16) | ((e >> 16) & 0xFFFFull));
+    bool ok = e != OLOG_INVALID;
+    uint32_t j = 0u;
+    if (ok) {
+        const uint32_t slot = (uint32_t)(e >> 32);
+        ok = t.stat[slot].T != EMPTY64;
+        j = t.slot_id[slot];
+    }
+    hkey_out[i] = ok ? (((unsigned long long)j << 16) | ((e >> 16) & 0xFFFFull)) : (1ull << h_bits);
     hcnt_out[i] = (uint32_t)(e & 0xFFFFull);
 }
 
-/* per junction (key order): first index and number of its runs in the sorted, run-length reduced log */
+/* per junction j: first index and number of its runs in the sorted, run-length reduced log */
 __global__ void k_hash_runs(const unsigned long long *sorted_hkey, const uint32_t *n_runs, int h_bits, unsigned long long *hash_lo,
                             unsigned long long *total) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1149,8 +1155,8 @@ __global__ void k_hash_runs(const unsigned long long *sorted_hkey, const uint32_
 }
 
 /* warp per junction: number of non-zero counters of its dense row, added to total[r] */
-__global__ void k_dense_count(Tables t, const uint32_t *sorted_slot, const unsigned long long *d_count, unsigned long long *total,
-                              uint32_t *dense_nz) {
+__global__ void k_dense_count(Tables t, const uint32_t *sorted_slot, const unsigned long long *d_count,
+                              const unsigned long long *total_j, unsigned long long *total, uint32_t *dense_nz) {
     const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= d_count[0]) return;
@@ -1164,7 +1170,7 @@ __global__ void k_dense_count(Tables t, const uint32_t *sorted_slot, const unsig
     for (int k = 16; k > 0; k >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, k);
     if (lane == 0) {
         dense_nz[r] = nz;
-        total[r] += nz;
+        total[r] = nz + total_j[t.slot_id[sorted_slot[r]]]; /* + its runs in the log */
     }
 }
 
@@ -1205,7 +1211,7 @@ __global__ void k_write_runs(Tables t, const uint32_t *sorted_slot, unsigned lon
     }
     const unsigned long long n_hash = (o1 - o0) - nz;
     if (n_hash) {
-        const unsigned long long lo = hash_lo[r];
+        const unsigned long long lo = hash_lo[t.slot_id[sorted_slot[r]]];
         for (unsigned long long j = lane; j < n_hash; j += 32) hist_cnt[o0 + nz + j] = sorted_hcnt[lo + j];
     }
 }
@@ -1246,7 +1252,13 @@ void finalize_release(FinalizeWork &w) {
     w.exec = nullptr;
     cudaFree(w.sort_key); cudaFree(w.sort_key2); cudaFree(w.hash_lo); cudaFree(w.total); cudaFree(w.hk_a); cudaFree(w.hk_b);
     cudaFree(w.slot_a); cudaFree(w.slot_b); cudaFree(w.idx_b); cudaFree(w.dense_nz); cudaFree(w.hc_a); cudaFree(w.hc_b);
-    cudaFree(w.slot_rank); cudaFree(w.cub_tmp); cudaFree(w.d_count);
+    cudaFree(w.tkey); cudaFree(w.tkey2); cudaFree(w.total_j); cudaFree(w.tidx_a); cudaFree(w.tidx_b); cudaFree(w.t_rank);
+    cudaFree(w.cub_tmp); cudaFree(w.cub_tmp2); cudaFree(w.cub_tmp3); cudaFree(w.d_count);
+    if (w.s2) cudaStreamDestroy(w.s2);
+    if (w.s3) cudaStreamDestroy(w.s3);
+    if (w.ev_fork) cudaEventDestroy(w.ev_fork);
+    if (w.ev_join2) cudaEventDestroy(w.ev_join2);
+    if (w.ev_join3) cudaEventDestroy(w.ev_join3);
     if (w.h_count) cudaFreeHost(w.h_count);
     DeviceTable &o = w.out;
     cudaFree(o.chrom); cudaFree(o.i0); cudaFree(o.i1); cudaFree(o.a0); cudaFree(o.a1); cudaFree(o.ijunc); cudaFree(o.strand);
@@ -1258,11 +1270,17 @@ void finalize_release(FinalizeWork &w) {
 static cudaError_t finalize_allocate(FinalizeWork &w, uint64_t cap, uint64_t B, uint64_t L, uint64_t R) {
     if (!w.d_count) IPX_CU(cudaMalloc(&w.d_count, 8 * sizeof(unsigned long long)));
     if (!w.h_count) IPX_CU(cudaMallocHost(&w.h_count, 8 * sizeof(unsigned long long)));
-    if (w.slot_rank_cap < cap) {
-        IPX_CU(regrow(&w.slot_rank, cap));
-        w.slot_rank_cap = cap;
+    (void)cap;
+    if (!w.s2) {
+        IPX_CU(cudaStreamCreateWithFlags(&w.s2, cudaStreamNonBlocking));
+        IPX_CU(cudaStreamCreateWithFlags(&w.s3, cudaStreamNonBlocking));
+        IPX_CU(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming));
+        IPX_CU(cudaEventCreateWithFlags(&w.ev_join2, cudaEventDisableTiming));
+        IPX_CU(cudaEventCreateWithFlags(&w.ev_join3, cudaEventDisableTiming));
     }
     if (B != w.B) {
+        IPX_CU(regrow(&w.tkey, B)); IPX_CU(regrow(&w.tkey2, B)); IPX_CU(regrow(&w.total_j, B)); IPX_CU(regrow(&w.tidx_a, B));
+        IPX_CU(regrow(&w.tidx_b, B)); IPX_CU(regrow(&w.t_rank, B));
         IPX_CU(regrow(&w.sort_key, B)); IPX_CU(regrow(&w.sort_key2, B)); IPX_CU(regrow(&w.slot_a, B)); IPX_CU(regrow(&w.slot_b, B));
         IPX_CU(regrow(&w.idx_b, B)); IPX_CU(regrow(&w.hash_lo, B)); IPX_CU(regrow(&w.total, B + 1)); IPX_CU(regrow(&w.dense_nz, B));
         DeviceTable &o = w.out;
@@ -1284,45 +1302,55 @@ static cudaError_t finalize_allocate(FinalizeWork &w, uint64_t cap, uint64_t B, 
 
 /* the sequence itself, issued into `st` (under stream capture, or directly when capture is not possible) */
 static cudaError_t finalize_issue(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, FinalizeWork &w, cudaStream_t st) {
-    const uint64_t B = w.B, L = w.L, R = w.R, cap = t.cap_mask + 1;
+    const uint64_t B = w.B, L = w.L, R = w.R;
     const int key_bits = w.key.key_bits, t_bits = w.key.t_bits, h_bits = 16 + bits_for64(B);
     DeviceTable &out = w.out;
-    int launches = 0;
-    size_t tb = w.cub_tmp_bytes;
+    size_t tb = 0;
     k_resolve_T<<<148 * 4, 256, 0, st>>>(t, g); /* creation thresholds for anything still unresolved */
     k_finalize_begin<<<1, 1, 0, st>>>(t, w.d_count, B, L);
-    IPX_CU(cudaMemsetAsync(w.total, 0, (B + 1) * 8, st));
-    /* key order */
+    /* three independent chains from here: key order (st), sjN ranking (s2), read-offset log (s3) */
+    IPX_CU(cudaEventRecord(w.ev_fork, st));
+    IPX_CU(cudaStreamWaitEvent(w.s2, w.ev_fork, 0));
+    IPX_CU(cudaStreamWaitEvent(w.s3, w.ev_fork, 0));
+
+    /* st: key order -- chromosome-name rank, intron_start, intron_end */
     k_list_keys<<<blocks_for(B, 256), 256, 0, st>>>(t, d_name_rank, B, key_bits, w.d_count, w.sort_key, w.slot_a);
+    tb = w.cub_tmp_bytes;
     IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.sort_key, w.sort_key2, w.slot_a, w.slot_b, (int)B, 0,
                                            key_bits + 1 > 64 ? 64 : key_bits + 1, st));
     const uint32_t *sorted_slot = w.slot_b;
-    /* sjN: rank of the creating event in stream order */
-    k_gather_T<<<blocks_for(B, 256), 256, 0, st>>>(t, sorted_slot, w.d_count, B, t_bits, w.sort_key, w.slot_a);
+
+    /* s2: sjN = rank of the creating event in stream order */
+    k_list_T<<<blocks_for(B, 256), 256, 0, w.s2>>>(t, B, t_bits, w.tkey, w.tidx_a);
     tb = w.cub_tmp_bytes;
-    IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.sort_key, w.sort_key2, w.slot_a, w.idx_b, (int)B, 0, t_bits + 1, st));
-    k_scatter_ijunc<<<blocks_for(B, 256), 256, 0, st>>>(w.idx_b, w.d_count, out.ijunc);
-    k_gather_rows<<<blocks_for(B, 256), 256, 0, st>>>(t, g, sorted_slot, w.d_count, out);
-    launches += 6;
-    /* read-offset log: ordered by (junction rank, offset) with a sort, equal pairs summed */
-    IPX_CU(cudaMemsetAsync(w.slot_rank, 0xFF, cap * sizeof(uint32_t), st));
-    k_fill_slot_rank<<<blocks_for(B, 256), 256, 0, st>>>(sorted_slot, w.d_count, w.slot_rank);
-    k_olog_pairs<<<blocks_for(L, 256), 256, 0, st>>>(t, w.slot_rank, L, h_bits, w.hk_a, w.hc_a);
+    IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp2, tb, w.tkey, w.tkey2, w.tidx_a, w.tidx_b, (int)B, 0, t_bits + 1, w.s2));
+    k_scatter_trank<<<blocks_for(B, 256), 256, 0, w.s2>>>(w.tkey2, w.tidx_b, B, t_bits, w.t_rank);
+    IPX_CU(cudaEventRecord(w.ev_join2, w.s2));
+
+    /* s3: read-offset log ordered by (junction, offset) with a sort, equal pairs summed */
+    IPX_CU(cudaMemsetAsync(w.total_j, 0, B * 8, w.s3));
+    k_olog_pairs<<<blocks_for(L, 256), 256, 0, w.s3>>>(t, L, h_bits, w.hk_a, w.hc_a);
     tb = w.cub_tmp_bytes;
-    IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.hk_a, w.hk_b, w.hc_a, w.hc_b, (int)L, 0, h_bits + 1, st));
+    IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp3, tb, w.hk_a, w.hk_b, w.hc_a, w.hc_b, (int)L, 0, h_bits + 1, w.s3));
     uint32_t *n_unique = reinterpret_cast<uint32_t *>(w.d_count + 2);
     tb = w.cub_tmp_bytes;
-    IPX_CU(cub::DeviceReduce::ReduceByKey(w.cub_tmp, tb, w.hk_b, w.hk_a, w.hc_b, w.hc_a, n_unique, cub::Sum(), (int)L, st));
-    k_hash_runs<<<blocks_for(L, 256), 256, 0, st>>>(w.hk_a, n_unique, h_bits, w.hash_lo, w.total);
-    /* dense rows are already in offset order */
-    k_dense_count<<<blocks_for(B * 32, 256), 256, 0, st>>>(t, sorted_slot, w.d_count, w.total, w.dense_nz);
+    IPX_CU(cub::DeviceReduce::ReduceByKey(w.cub_tmp3, tb, w.hk_b, w.hk_a, w.hc_b, w.hc_a, n_unique, cub::Sum(), (int)L, w.s3));
+    k_hash_runs<<<blocks_for(L, 256), 256, 0, w.s3>>>(w.hk_a, n_unique, h_bits, w.hash_lo, w.total_j);
+    IPX_CU(cudaEventRecord(w.ev_join3, w.s3));
+
+    /* join: rows in key order (motif, strand correction, sjN), then the histograms -- dense rows are already in
+     * offset order, the log runs follow them */
+    IPX_CU(cudaStreamWaitEvent(st, w.ev_join2, 0));
+    k_gather_rows<<<blocks_for(B, 256), 256, 0, st>>>(t, g, sorted_slot, w.d_count, w.t_rank, out);
+    IPX_CU(cudaStreamWaitEvent(st, w.ev_join3, 0));
+    IPX_CU(cudaMemsetAsync(w.total, 0, (B + 1) * 8, st));
+    k_dense_count<<<blocks_for(B * 32, 256), 256, 0, st>>>(t, sorted_slot, w.d_count, w.total_j, w.total, w.dense_nz);
     tb = w.cub_tmp_bytes;
     IPX_CU(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.total, out.hist_off, (int)(B + 1), st));
     k_write_runs<<<blocks_for(B * 32, 256), 256, 0, st>>>(t, sorted_slot, w.d_count, B, R, out.hist_off, w.dense_nz, w.hash_lo, w.hc_a,
                                                         out.hist_cnt);
-    launches += 5;
     IPX_CU(cudaMemcpyAsync(w.h_count, w.d_count, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    w.launches_per_replay = launches;
+    w.launches_per_replay = 12;
     return cudaGetLastError();
 }
 
@@ -1359,15 +1387,17 @@ cudaError_t finalize_enqueue(const Tables &t, const GenomeView &g, const uint32_
         IPX_CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, w.total, w.out.hist_off, (int)(B + 1), st));
         need = tb > need ? tb : need;
         if (need > w.cub_tmp_bytes) {
-            if (w.cub_tmp) cudaFree(w.cub_tmp);
-            w.cub_tmp = nullptr;
+            cudaFree(w.cub_tmp); cudaFree(w.cub_tmp2); cudaFree(w.cub_tmp3);
+            w.cub_tmp = w.cub_tmp2 = w.cub_tmp3 = nullptr;
             IPX_CU(cudaMalloc(&w.cub_tmp, need));
+            IPX_CU(cudaMalloc(&w.cub_tmp2, need));
+            IPX_CU(cudaMalloc(&w.cub_tmp3, need));
             w.cub_tmp_bytes = need;
         }
         static const bool no_graph = getenv("IPX_NO_GRAPH") != nullptr;
         if (!no_graph) {
             cudaGraph_t graph = nullptr;
-            cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+            cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal); /* s2 / s3 join the capture through the fork event */
             if (e == cudaSuccess) {
                 cudaError_t ei = finalize_issue(t, g, d_name_rank, w, st);
                 e = cudaStreamEndCapture(st, &graph);

@@ -112,6 +112,7 @@ struct Tables {
     unsigned long long *keys; /* [cap] */
     JStat *stat;              /* [cap] */
     uint32_t *slot_list;      /* [cap] slots in use, in insertion order: clear and finalize walk this, never the table */
+    uint32_t *slot_id;        /* [cap] position of a slot in slot_list (valid for slots in use) */
     unsigned long long *olog; /* [olog_cap] slot << 32 | read offset << 16 | count, or OLOG_INVALID */
     uint64_t olog_cap;
     uint32_t *dense;          /* [cap][DENSE_W] read counts for offsets < DENSE_W, or NULL when disabled */
@@ -139,7 +140,9 @@ __device__ __forceinline__ uint64_t junction_find_or_insert(const Tables &t, uin
             unsigned long long old = atomicCAS(&t.keys[h], EMPTY64, (unsigned long long)key);
             if (old == EMPTY64) {
                 /* every slot is claimed at most once between clears, so the list cannot overflow */
-                t.slot_list[atomicAdd(t.n_keys, 1ull)] = (uint32_t)h;
+                const unsigned long long id = atomicAdd(t.n_keys, 1ull);
+                t.slot_list[id] = (uint32_t)h;
+                t.slot_id[h] = (uint32_t)id;
                 return h;
             }
             if (old == key) return h;
