@@ -127,8 +127,9 @@ struct ipx_handle {
     /* key-range export in flight (ipx_partial_sizes -> ipx_partial_export) */
     Splitters export_split{};
     unsigned long long *d_export = nullptr; /* [2 * MAX_PARTS] counts, then cursors */
-    unsigned long long export_counts[2 * MAX_PARTS] = {};
-    uint64_t export_keys = 0, export_olog = 0;
+    unsigned long long export_counts[2 * MAX_PARTS + 4] = {}; /* + keys, log entries, overflow flag */
+    unsigned long long export_cursors[2 * MAX_PARTS] = {};
+    uint64_t export_keys = 1 << 16, export_olog = 1 << 16; /* launch bounds of the export passes (grow-only) */
     DeviceBuf slot_jrow; /* [cap] export: junction-row index of each slot */
     DeviceBuf slot_of;   /* import: table slot of each received junction row */
     bool export_ready = false;
@@ -870,29 +871,34 @@ extern "C" int ipx_partial_sizes(ipx_handle *h, int32_t n_parts, const int32_t *
             return fail(h, IPX_ERR_ARG, "splitters are not in key order");
     }
     cudaStream_t st = h->stream;
-    if (!h->d_export) CU(h, cudaMalloc(&h->d_export, 2 * MAX_PARTS * sizeof(unsigned long long)));
-    CU(h, cudaMemsetAsync(h->d_export, 0, 2 * MAX_PARTS * sizeof(unsigned long long), st));
-    {
-        /* creation thresholds for anything still unresolved: keys that never got one are not exported */
-        Span s(h, &h->tm_motif, 1);
-        launch_resolve_T(h->tab, genome_view(h), st);
+    if (!h->d_export) CU(h, cudaMalloc(&h->d_export, (2 * MAX_PARTS + 4) * sizeof(unsigned long long)));
+    /* The two passes are launched for grow-only bounds on the number of keys and log entries (the kernels read the
+     * real numbers on the device); one host round trip brings back the row counts together with the real numbers, and
+     * only a bound that turned out too small costs a second one. */
+    for (int round = 0; round < 2; round++) {
+        CU(h, cudaMemsetAsync(h->d_export, 0, 2 * MAX_PARTS * sizeof(unsigned long long), st));
+        {
+            /* creation thresholds for anything still unresolved: keys that never got one are not exported */
+            Span s(h, &h->tm_motif, 1);
+            launch_resolve_T(h->tab, genome_view(h), st);
+        }
+        {
+            Span s(h, &h->tm_finalize, 2);
+            launch_export_count(h->tab, h->d_name_rank, sp, h->export_keys, h->export_olog, h->d_export, st);
+        }
+        CU(h, cudaGetLastError());
+        CU(h, cudaMemcpyAsync(h->d_export + 2 * MAX_PARTS, h->tab.n_keys, 8, cudaMemcpyDeviceToDevice, st));
+        CU(h, cudaMemcpyAsync(h->d_export + 2 * MAX_PARTS + 1, h->tab.n_olog, 8, cudaMemcpyDeviceToDevice, st));
+        CU(h, cudaMemcpyAsync(h->d_export + 2 * MAX_PARTS + 2, h->tab.overflow, 4, cudaMemcpyDeviceToDevice, st));
+        CU(h, cudaMemcpyAsync(h->export_counts, h->d_export, (2 * MAX_PARTS + 4) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        const unsigned long long nk = h->export_counts[2 * MAX_PARTS], nl = h->export_counts[2 * MAX_PARTS + 1];
+        if ((uint32_t)h->export_counts[2 * MAX_PARTS + 2])
+            return fail(h, IPX_ERR_CAPACITY, "a table ran out of room before the exchange (raise table_capacity / hist_capacity)");
+        if (nk <= h->export_keys && nl <= h->export_olog) break;
+        h->export_keys = nk + nk / 8 + 4096;
+        h->export_olog = nl + nl / 8 + 4096;
     }
-    unsigned long long nk = 0, nl = 0;
-    uint32_t overflow = 0;
-    CU(h, cudaMemcpyAsync(&nk, h->tab.n_keys, 8, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaMemcpyAsync(&nl, h->tab.n_olog, 8, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaMemcpyAsync(&overflow, h->tab.overflow, 4, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaStreamSynchronize(st));
-    if (overflow) return fail(h, IPX_ERR_CAPACITY, "a table ran out of room before the exchange (raise table_capacity / hist_capacity)");
-    h->export_keys = nk;
-    h->export_olog = nl;
-    {
-        Span s(h, &h->tm_finalize, 2);
-        launch_export_count(h->tab, h->d_name_rank, sp, nk, nl, h->d_export, st);
-    }
-    CU(h, cudaGetLastError());
-    CU(h, cudaMemcpyAsync(h->export_counts, h->d_export, 2 * n_parts * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CU(h, cudaStreamSynchronize(st));
     for (int32_t p = 0; p < n_parts; p++) {
         junction_rows[p] = h->export_counts[p];
         hist_rows[p] = h->export_counts[n_parts + p];
@@ -908,7 +914,7 @@ extern "C" int ipx_partial_export(ipx_handle *h, void *dev_junction_rows, void *
     cudaStream_t st = h->stream;
     const int n_parts = h->export_split.n_parts;
     /* destination-major: the cursor of a part starts where the parts before it end */
-    unsigned long long cursors[2 * MAX_PARTS];
+    unsigned long long *cursors = h->export_cursors;
     unsigned long long j = 0, hh = 0;
     for (int p = 0; p < n_parts; p++) {
         cursors[p] = j;
@@ -927,7 +933,6 @@ extern "C" int ipx_partial_export(ipx_handle *h, void *dev_junction_rows, void *
         launch_clear_tables(h->tab, st);
     }
     CU(h, cudaGetLastError());
-    CU(h, cudaStreamSynchronize(st)); /* `cursors` lives on this stack frame */
     h->export_ready = false;
     return IPX_OK;
 }

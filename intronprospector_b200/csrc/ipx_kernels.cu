@@ -1449,7 +1449,7 @@ __global__ void __launch_bounds__(256) k_export_slots(Tables t, const uint32_t *
                                                       unsigned long long *counts, uint32_t *slot_jrow, JunctionRow *jr, HistRow *hr) {
     const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (i >= n_keys) return;
+    if (i >= n_keys || i >= *t.n_keys) return; /* n_keys is a launch bound; the table knows how many there are */
     const uint32_t slot = t.slot_list[i];
     const JStat s = t.stat[slot];
     if (s.T == EMPTY64) return; /* never created: nothing was counted into it */
@@ -1513,7 +1513,7 @@ __global__ void __launch_bounds__(256) k_export_olog(Tables t, const uint32_t *n
     int dest = -1 - lane; /* idle lanes group with nobody */
     unsigned long long e = OLOG_INVALID;
     uint32_t slot = 0u;
-    if (i < n_olog) {
+    if (i < n_olog && i < *t.n_olog) {
         e = t.olog[i];
         if (e != OLOG_INVALID) {
             slot = (uint32_t)(e >> 32);

@@ -28,12 +28,27 @@ def key_splitters(names, n_parts):
     return split_tid, [0] * (n_parts - 1)
 
 
-def _sync(device):
-    """Host-side join of torch's work on `device` (collectives, copies) before the engine, which launches on its own
-    stream, touches the same buffers.  The engine side is joined by the library (ipx_partial_export and
-    ipx_thresholds_export return after their kernels have finished)."""
-    if device.type == "cuda":
-        torch.cuda.synchronize(device)
+def _engine_stream(eng, device):
+    if device.type != "cuda" or not hasattr(eng, "stream"):
+        return None
+    if getattr(eng, "_torch_stream", None) is None:
+        eng._torch_stream = torch.cuda.ExternalStream(eng.stream(), device=device)
+    return eng._torch_stream
+
+
+def _torch_after_engine(eng, device):
+    """The engine launches on its own stream and its export calls return without waiting for the device: make torch's
+    current stream (collectives, copies) wait for what the engine has enqueued.  Device-side ordering, no host sync."""
+    es = _engine_stream(eng, device)
+    if es is not None:
+        torch.cuda.current_stream(device).wait_stream(es)
+
+
+def _engine_after_torch(eng, device):
+    """... and the other way round before the engine reads buffers torch's stream is still filling."""
+    es = _engine_stream(eng, device)
+    if es is not None:
+        es.wait_stream(torch.cuda.current_stream(device))
 
 
 def _byte_tensor(n_bytes, device):
@@ -48,7 +63,9 @@ def export_partials(eng, names, n_parts, device):
     jb, hb = eng.partial_row_bytes()
     send_j = _byte_tensor(sum(jrows) * jb, device)
     send_h = _byte_tensor(sum(hrows) * hb, device)
+    _engine_after_torch(eng, device)  # the allocator may hand out memory torch's stream was still using
     eng.partial_export(send_j.data_ptr(), send_h.data_ptr())
+    _torch_after_engine(eng, device)
     return (send_j, [x * jb for x in jrows]), (send_h, [x * hb for x in hrows])
 
 
@@ -64,19 +81,25 @@ def import_partials(eng, recv_j, bytes_j, recv_h, bytes_h):
         oh += nh
 
 
-def all_to_all_bytes(send, send_counts, group=None):
-    """Variable-size all-to-all of a uint8 tensor laid out destination-major.  Returns (received bytes in source-rank
-    order, bytes per source)."""
+def exchange_counts(count_lists, device, group=None):
+    """What every source will send here: one small all-to-all for all kinds of rows.  count_lists: per kind, the bytes
+    this rank sends to each destination; returns per kind the bytes it receives from each source."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    counts = torch.tensor(send_counts, dtype=torch.int64, device=send.device)
+    counts = torch.tensor(count_lists, dtype=torch.int64, device=device).t().contiguous()  # [dest][kind]
     recv_counts = torch.empty_like(counts)
-    dist.all_to_all_single(recv_counts, counts, group=group)
-    rc = [int(x) for x in recv_counts.cpu()]
-    recv = torch.empty(max(1, sum(rc)), dtype=torch.uint8, device=send.device)
-    assert len(send_counts) == world
-    dist.all_to_all_single(recv[:sum(rc)], send[:sum(send_counts)], rc, list(send_counts), group=group)
-    return recv[:sum(rc)], rc
+    dist.all_to_all_single(recv_counts.view(-1), counts.view(-1), group=group)
+    rc = recv_counts.cpu().tolist()  # [source][kind]
+    return [[int(rc[s][k]) for s in range(world)] for k in range(len(count_lists))]
+
+
+def all_to_all_bytes(send, send_counts, recv_counts, group=None):
+    """Variable-size all-to-all of a uint8 tensor laid out destination-major; returns the received bytes in
+    source-rank order."""
+    import torch.distributed as dist
+    recv = torch.empty(max(1, sum(recv_counts)), dtype=torch.uint8, device=send.device)
+    dist.all_to_all_single(recv[:sum(recv_counts)], send[:sum(send_counts)], list(recv_counts), list(send_counts), group=group)
+    return recv[:sum(recv_counts)]
 
 
 def exchange_dist(eng, names, device, group=None):
@@ -84,10 +107,12 @@ def exchange_dist(eng, names, device, group=None):
     import torch.distributed as dist
     world = dist.get_world_size(group)
     (send_j, cj), (send_h, ch) = export_partials(eng, names, world, device)
-    recv_j, rj = all_to_all_bytes(send_j, cj, group)
-    recv_h, rh = all_to_all_bytes(send_h, ch, group)
-    _sync(device)  # the collectives run on torch's stream, the engine on its own: the rows must have landed
+    rj, rh = exchange_counts([cj, ch], device, group)
+    recv_j = all_to_all_bytes(send_j, cj, rj, group)
+    recv_h = all_to_all_bytes(send_h, ch, rh, group)
+    _engine_after_torch(eng, device)  # the collectives run on torch's stream: the rows must have landed
     import_partials(eng, recv_j, rj, recv_h, rh)
+    _torch_after_engine(eng, device)  # the receive buffers go back to torch's allocator: not before the import has read them
     return sum(cj) + sum(ch) + sum(rj) + sum(rh)
 
 
@@ -105,7 +130,9 @@ def exchange_local(engines, names, device):
             pieces_h.append(sh[oh:oh + ch[dst]])
         rj, rh = torch.cat(pieces_j), torch.cat(pieces_h)
         moved += rj.numel() + rh.numel()
+        _engine_after_torch(eng, device)
         import_partials(eng, rj, [p.numel() for p in pieces_j], rh, [p.numel() for p in pieces_h])
+        _torch_after_engine(eng, device)
     return moved
 
 
@@ -130,7 +157,7 @@ def agree_thresholds_dist(eng, device, group=None):
     padded[:rows.numel()] = rows
     gathered = [torch.empty(cap, dtype=torch.uint8, device=device) for _ in range(world)]
     dist.all_gather(gathered, padded, group=group)
-    _sync(device)
+    _engine_after_torch(eng, device)
     for r in range(world):
         if r != dist.get_rank(group) and sizes[r]:
             eng.thresholds_import(gathered[r].data_ptr(), sizes[r] // row_bytes)

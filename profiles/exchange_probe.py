@@ -20,7 +20,7 @@ for it in range(8):
     dist.barrier(); t0 = T()
     eng.clear(); eng.push_device(devc); t1 = T()
     (sj, cj), (sh, ch) = sharded.export_partials(eng, names, world, dev); t2 = T()
-    rj, nj = sharded.all_to_all_bytes(sj, cj); rh, nh = sharded.all_to_all_bytes(sh, ch); t3 = T()
+    nj, nh = sharded.exchange_counts([cj, ch], dev); rj = sharded.all_to_all_bytes(sj, cj, nj); rh = sharded.all_to_all_bytes(sh, ch, nh); t3 = T()
     sharded.import_partials(eng, rj, nj, rh, nh); t4 = T()
     eng.finalize_device(); t5 = T()
     if it >= 3:
