@@ -240,36 +240,67 @@ def _arr(ptr, n, dtype):
     return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype).copy()
 
 
+def _view(ptr, n, dtype):
+    """numpy view of a library-owned column (no copy): valid while the native table is alive"""
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    a = np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype)
+    a.flags.writeable = False
+    return a
+
+
 class Table:
-    """Host copy of an ipx_table (numpy arrays), detached from the library's buffers."""
+    """An ipx_table.  The columns are numpy views of the library's own buffers, made on first use (so ipx_flush costs
+    what the C call costs); they stay valid until close(), which frees the native table.  Copy what must outlive it."""
+
+    _COLUMNS = {
+        "chrom": ("chrom", np.int32, 1), "intron_start": ("intron_start", np.uint32, 1), "intron_end": ("intron_end", np.uint32, 1),
+        "anchor_start": ("anchor_start", np.uint32, 1), "anchor_end": ("anchor_end", np.uint32, 1),
+        "strand": ("strand", np.uint8, 1), "splice_sites": ("splice_sites", np.uint8, 8), "read_counts": ("read_counts", np.uint64, 3),
+        "ijunc": ("ijunc", np.uint32, 1), "confidence": ("confidence", np.float32, 1),
+    }
 
     def __init__(self, lib, tp, names, free):
         t = tp.contents
-        n = int(t.n_junctions)
-        self.n = n
+        self.n = int(t.n_junctions)
+        self.n_hist = int(t.n_hist)
         self.names = list(names)
-        self.chrom = _arr(t.chrom, n, np.int32)
-        self.intron_start = _arr(t.intron_start, n, np.uint32)
-        self.intron_end = _arr(t.intron_end, n, np.uint32)
-        self.anchor_start = _arr(t.anchor_start, n, np.uint32)
-        self.anchor_end = _arr(t.anchor_end, n, np.uint32)
-        self.strand = _arr(C.cast(t.strand, C.POINTER(C.c_uint8)), n, np.uint8)
-        self.splice_sites = _arr(C.cast(t.splice_sites, C.POINTER(C.c_uint8)), n * 8, np.uint8).reshape(n, 8)
-        self.read_counts = _arr(t.read_counts, n * 3, np.uint64).reshape(n, 3)
-        self.ijunc = _arr(t.ijunc, n, np.uint32)
-        self.confidence = _arr(t.confidence, n, np.float32)
-        self.hist_off = _arr(t.hist_off, n + 1, np.uint64)
-        self.hist_cnt = _arr(t.hist_cnt, int(t.n_hist), np.uint32)
         self.status = int(t.status)
         self.first_error_seq = int(t.first_error_seq)
         self.error_tid = int(t.error_tid)
         self.error_text = t.error_text.decode(errors="replace")
         self.missing_targets = _arr(t.missing_targets, int(t.n_missing_targets), np.int32)
-        self.creation_seq = _arr(t.creation_seq, n, np.uint64) if t.creation_seq else np.zeros(0, np.uint64)
-        # text is produced on demand by the library's own formatter, so the native table stays alive until close()
         self._lib, self._tp, self._free = lib, tp, free
         self._cnames = (C.c_char_p * max(1, len(names)))(*[s.encode() for s in names])
         self._text = {}
+        self._cols = {}
+
+    def __getattr__(self, name):
+        # columns on demand; only called for attributes not set in __init__
+        if name.startswith("_") or self.__dict__.get("_tp") is None:
+            raise AttributeError(name)
+        cols = self.__dict__["_cols"]
+        if name in cols:
+            return cols[name]
+        t = self._tp.contents
+        n = self.n
+        if name in Table._COLUMNS:
+            field, dtype, width = Table._COLUMNS[name]
+            ptr = getattr(t, field)
+            if dtype == np.uint8:
+                ptr = C.cast(ptr, C.POINTER(C.c_uint8))
+            a = _view(ptr, n * width, dtype)
+            a = a.reshape(n, width) if width > 1 else a
+        elif name == "hist_off":
+            a = _view(t.hist_off, n + 1, np.uint64)
+        elif name == "hist_cnt":
+            a = _view(t.hist_cnt, self.n_hist, np.uint32)
+        elif name == "creation_seq":
+            a = _view(t.creation_seq, n, np.uint64) if t.creation_seq else np.zeros(0, np.uint64)
+        else:
+            raise AttributeError(name)
+        cols[name] = a
+        return a
 
     def text(self, fmt, min_confidence=0.0):
         key = (fmt, float(min_confidence))
@@ -291,11 +322,12 @@ class Table:
             raise IpxError("set_ijunc: wrong length or closed table")
         if self._lib.ipx_table_set_ijunc(self._tp, a.ctypes.data) != IPX_OK:
             raise IpxError("ipx_table_set_ijunc failed")
-        self.ijunc = a.copy()
+        self._cols.pop("ijunc", None)  # the library may have moved the column
         self._text = {}
 
     def close(self):
-        if self._tp is not None:
+        if self.__dict__.get("_tp") is not None:
+            self._cols.clear()
             self._free(self._tp)
             self._tp = None
 
@@ -306,10 +338,9 @@ class Table:
             pass
 
     def columns(self):
-        return dict(chrom=self.chrom, intron_start=self.intron_start, intron_end=self.intron_end,
-                    anchor_start=self.anchor_start, anchor_end=self.anchor_end, strand=self.strand,
-                    splice_sites=self.splice_sites, read_counts=self.read_counts, ijunc=self.ijunc,
-                    confidence=self.confidence, hist_off=self.hist_off, hist_cnt=self.hist_cnt)
+        """Detached copies of every column (safe to keep after close())."""
+        return {k: np.array(getattr(self, k)) for k in ("chrom", "intron_start", "intron_end", "anchor_start", "anchor_end", "strand",
+                                                        "splice_sites", "read_counts", "ijunc", "confidence", "hist_off", "hist_cnt")}
 
 
 class Engine:

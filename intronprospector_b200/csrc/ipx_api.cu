@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <string>
@@ -130,6 +131,8 @@ struct ipx_handle {
     unsigned long long export_counts[2 * MAX_PARTS + 4] = {}; /* + keys, log entries, overflow flag */
     unsigned long long export_cursors[2 * MAX_PARTS] = {};
     uint64_t export_keys = 1 << 16, export_olog = 1 << 16; /* launch bounds of the export passes (grow-only) */
+    void *pinned = nullptr; /* grow-only pinned staging for ipx_flush: the table comes over the host link at full speed */
+    size_t pinned_cap = 0;
     DeviceBuf slot_jrow; /* [cap] export: junction-row index of each slot */
     DeviceBuf slot_of;   /* import: table slot of each received junction row */
     bool export_ready = false;
@@ -465,6 +468,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();
     h->s_off.release(); h->s_cig.release(); h->ev_buf.release(); h->tile_cnt.release(); h->long_buf.release(); h->slot_jrow.release(); h->slot_of.release();
     finalize_release(h->fw);
+    if (h->pinned) cudaFreeHost(h->pinned);
     cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -652,33 +656,61 @@ void describe_error(ipx_handle *h, unsigned long long err_sv, HostTable *ht) {
 
 }  // namespace
 
+namespace {
+struct Trace {
+    bool on = getenv("IPX_TRACE") != nullptr;
+    double t0 = now();
+    static double now() {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    void mark(const char *what) {
+        if (!on) return;
+        const double t = now();
+        fprintf(stderr, "[ipx] %-28s %8.3f ms\n", what, t - t0);
+        t0 = t;
+    }
+};
+}  // namespace
+
 extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     if (!h || !out) return IPX_ERR_ARG;
     *out = nullptr;
+    Trace tr;
     int rc = ipx_finalize_device(h);
     if (rc) return rc;
     rc = settle_finalize(h);
     if (rc) return rc;
+    tr.mark("flush: wait for the device");
     cudaStream_t st = h->stream;
     HostTable *ht = new HostTable();
     memset(&ht->t, 0, sizeof(ht->t));
     const DeviceTable &d = h->fw.out;
     const uint64_t n = d.n;
-    std::vector<unsigned long long> counts, T, hist_off;
+    /* every column goes into one pinned staging block (asynchronous copies at link speed), then into the table */
     cudaError_t e = cudaSuccess;
     auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-    chk(d2h(ht->chrom, d.chrom, n, st));
-    chk(d2h(ht->i0, d.i0, n, st));
-    chk(d2h(ht->i1, d.i1, n, st));
-    chk(d2h(ht->a0, d.a0, n, st));
-    chk(d2h(ht->a1, d.a1, n, st));
-    chk(d2h(ht->ijunc, d.ijunc, n, st));
-    chk(d2h(ht->strand, d.strand, n, st));
-    chk(d2h(ht->sites, d.sites, n * 8, st));
-    chk(d2h(counts, d.counts, n * 3, st));
-    chk(d2h(T, d.T, n, st));
-    chk(d2h(hist_off, d.hist_off, n + 1, st));
-    chk(d2h(ht->hist_cnt, d.hist_cnt, d.n_hist, st));
+    struct Col { const void *src; size_t bytes; size_t at; };
+    Col cols[12] = {{d.chrom, n * 4, 0}, {d.i0, n * 4, 0}, {d.i1, n * 4, 0}, {d.a0, n * 4, 0}, {d.a1, n * 4, 0}, {d.ijunc, n * 4, 0},
+                    {d.strand, n, 0}, {d.sites, n * 8, 0}, {d.counts, n * 24, 0}, {d.T, n * 8, 0}, {d.hist_off, (n + 1) * 8, 0},
+                    {d.hist_cnt, d.n_hist * 4, 0}};
+    size_t need = 0;
+    for (auto &c : cols) {
+        c.at = need;
+        need += (c.bytes + 63) & ~(size_t)63;
+    }
+    if (need > h->pinned_cap) {
+        if (h->pinned) cudaFreeHost(h->pinned);
+        h->pinned = nullptr;
+        h->pinned_cap = 0;
+        const size_t want = need + need / 4 + (1 << 20);
+        CU(h, cudaMallocHost(&h->pinned, want));
+        h->pinned_cap = want;
+    }
+    char *stage = (char *)h->pinned;
+    for (auto &c : cols)
+        if (c.bytes) chk(cudaMemcpyAsync(stage + c.at, c.src, c.bytes, cudaMemcpyDeviceToHost, st));
     unsigned long long ctr[4] = {0, 0, 0, 0};
     unsigned long long err_sv = EMPTY64;
     uint32_t overflow = 0;
@@ -687,6 +719,7 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     chk(cudaMemcpyAsync(&err_sv, h->tab.err_sv, 8, cudaMemcpyDeviceToHost, st));
     chk(cudaMemcpyAsync(&overflow, h->tab.overflow, 4, cudaMemcpyDeviceToHost, st));
     chk(cudaStreamSynchronize(st));
+    tr.mark("flush: table to host");
     if (e != cudaSuccess) {
         delete ht;
         return fail(h, IPX_ERR_CUDA, "CUDA error %s in flush: %s", cudaGetErrorName(e), cudaGetErrorString(e));
@@ -697,9 +730,17 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
         return fail(h, IPX_ERR_CAPACITY, "%s is full; raise ipx_params.%s", overflow == 1 ? "junction hash table" : "read-offset log",
                     overflow == 1 ? "table_capacity" : "hist_capacity");
     }
-    ht->counts.assign(counts.begin(), counts.end());
-    ht->hist_off.assign(hist_off.begin(), hist_off.end());
-    if (ht->hist_off.empty()) ht->hist_off.push_back(0);
+    {
+        auto take = [&](auto &vec, int ci, size_t count) {
+            typedef typename std::remove_reference<decltype(vec)>::type::value_type V;
+            const V *p = reinterpret_cast<const V *>(stage + cols[ci].at);
+            vec.assign(p, p + count);
+        };
+        take(ht->chrom, 0, n); take(ht->i0, 1, n); take(ht->i1, 2, n); take(ht->a0, 3, n); take(ht->a1, 4, n); take(ht->ijunc, 5, n);
+        take(ht->strand, 6, n); take(ht->sites, 7, n * 8); take(ht->counts, 8, n * 3); take(ht->hist_off, 10, n + 1);
+        take(ht->hist_cnt, 11, d.n_hist);
+    }
+    const unsigned long long *T = reinterpret_cast<const unsigned long long *>(stage + cols[9].at);
     /* sjN continues across flushes (ijunc_, junctions_extractor.hh:129) */
     for (uint64_t i = 0; i < n; i++) ht->ijunc[i] += h->ijunc_base;
     h->ijunc_base += (uint32_t)n;
@@ -707,7 +748,9 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     ht->creation.resize(n);
     for (uint64_t i = 0; i < n; i++) ht->creation[i] = T[i] >> 8;
     ht->bind();
+    tr.mark("flush: host columns");
     compute_confidences(n, ht->counts.data(), ht->hist_off.data(), ht->hist_cnt.data(), ht->conf.data());
+    tr.mark("flush: confidences");
     /* missing-genome warnings in first-miss order (junctions_extractor.cc:411-417) */
     if (h->have_genome && h->params.skip_missing_targets) {
         std::unordered_map<int32_t, unsigned long long> first_miss;
