@@ -10,6 +10,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -24,8 +25,57 @@ using namespace ipx;
 
 namespace {
 
+/* Pinned host blocks that back the tables ipx_flush returns: the columns arrive from the device straight into the
+ * block the table then owns (no staging copy), and ipx_table_free hands the block back for the next flush. */
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<std::pair<void *, size_t>> free_blocks;
+    void *take(size_t bytes, size_t *cap) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (size_t i = 0; i < free_blocks.size(); i++)
+                if (free_blocks[i].second >= bytes) {
+                    void *p = free_blocks[i].first;
+                    *cap = free_blocks[i].second;
+                    free_blocks.erase(free_blocks.begin() + i);
+                    return p;
+                }
+        }
+        void *p = nullptr;
+        const size_t want = bytes + bytes / 4 + (1 << 20);
+        if (cudaMallocHost(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        *cap = want;
+        return p;
+    }
+    void give(void *p, size_t cap) {
+        std::lock_guard<std::mutex> g(mu);
+        if (free_blocks.size() < 4) {
+            free_blocks.emplace_back(p, cap);
+            return;
+        }
+        /* keep the larger blocks */
+        size_t smallest = 0;
+        for (size_t i = 1; i < free_blocks.size(); i++)
+            if (free_blocks[i].second < free_blocks[smallest].second) smallest = i;
+        if (free_blocks[smallest].second < cap) {
+            std::swap(free_blocks[smallest].first, p);
+            std::swap(free_blocks[smallest].second, cap);
+        }
+        cudaFreeHost(p);
+    }
+};
+PinnedPool g_pinned_pool;
+
 struct HostTable {
     ipx_table t;
+    void *block = nullptr; /* pinned block holding the columns (tables from ipx_flush); else the vectors do */
+    size_t block_cap = 0;
+    ~HostTable() {
+        if (block) g_pinned_pool.give(block, block_cap);
+    }
     std::vector<int32_t> chrom, missing;
     std::vector<uint32_t> i0, i1, a0, a1, ijunc, hist_cnt;
     std::vector<char> strand, sites;
@@ -33,6 +83,12 @@ struct HostTable {
     std::vector<float> conf;
     std::vector<uint64_t> creation;
     void bind() {
+        if (block) { /* the columns live in the block: only what stays in vectors is rebound */
+            t.missing_targets = missing.data();
+            t.n_missing_targets = missing.size();
+            if (!ijunc.empty()) t.ijunc = ijunc.data(); /* renumbered by ipx_table_set_ijunc */
+            return;
+        }
         t.n_junctions = chrom.size();
         t.chrom = chrom.data();
         t.intron_start = i0.data();
@@ -131,8 +187,6 @@ struct ipx_handle {
     unsigned long long export_counts[2 * MAX_PARTS + 4] = {}; /* + keys, log entries, overflow flag */
     unsigned long long export_cursors[2 * MAX_PARTS] = {};
     uint64_t export_keys = 1 << 16, export_olog = 1 << 16; /* launch bounds of the export passes (grow-only) */
-    void *pinned = nullptr; /* grow-only pinned staging for ipx_flush: the table comes over the host link at full speed */
-    size_t pinned_cap = 0;
     DeviceBuf slot_jrow; /* [cap] export: junction-row index of each slot */
     DeviceBuf slot_of;   /* import: table slot of each received junction row */
     bool export_ready = false;
@@ -468,7 +522,6 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();
     h->s_off.release(); h->s_cig.release(); h->ev_buf.release(); h->tile_cnt.release(); h->long_buf.release(); h->slot_jrow.release(); h->slot_of.release();
     finalize_release(h->fw);
-    if (h->pinned) cudaFreeHost(h->pinned);
     cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -688,29 +741,27 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     memset(&ht->t, 0, sizeof(ht->t));
     const DeviceTable &d = h->fw.out;
     const uint64_t n = d.n;
-    /* every column goes into one pinned staging block (asynchronous copies at link speed), then into the table */
+    /* every column goes into one pinned block at link speed; the table then owns that block */
     cudaError_t e = cudaSuccess;
     auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     struct Col { const void *src; size_t bytes; size_t at; };
-    Col cols[12] = {{d.chrom, n * 4, 0}, {d.i0, n * 4, 0}, {d.i1, n * 4, 0}, {d.a0, n * 4, 0}, {d.a1, n * 4, 0}, {d.ijunc, n * 4, 0},
-                    {d.strand, n, 0}, {d.sites, n * 8, 0}, {d.counts, n * 24, 0}, {d.T, n * 8, 0}, {d.hist_off, (n + 1) * 8, 0},
-                    {d.hist_cnt, d.n_hist * 4, 0}};
-    size_t need = 0;
+    enum { C_CHROM, C_I0, C_I1, C_A0, C_A1, C_IJUNC, C_STRAND, C_SITES, C_COUNTS, C_T, C_HOFF, C_HCNT, C_CONF, N_COLS };
+    Col cols[N_COLS] = {{d.chrom, n * 4, 0}, {d.i0, n * 4, 0}, {d.i1, n * 4, 0}, {d.a0, n * 4, 0}, {d.a1, n * 4, 0}, {d.ijunc, n * 4, 0},
+                        {d.strand, n, 0}, {d.sites, n * 8, 0}, {d.counts, n * 24, 0}, {d.T, n * 8, 0}, {d.hist_off, (n + 1) * 8, 0},
+                        {d.hist_cnt, d.n_hist * 4, 0}, {nullptr, n * 4, 0}};
+    size_t need = 64;
     for (auto &c : cols) {
         c.at = need;
         need += (c.bytes + 63) & ~(size_t)63;
     }
-    if (need > h->pinned_cap) {
-        if (h->pinned) cudaFreeHost(h->pinned);
-        h->pinned = nullptr;
-        h->pinned_cap = 0;
-        const size_t want = need + need / 4 + (1 << 20);
-        CU(h, cudaMallocHost(&h->pinned, want));
-        h->pinned_cap = want;
+    ht->block = g_pinned_pool.take(need, &ht->block_cap);
+    if (!ht->block) {
+        delete ht;
+        return fail(h, IPX_ERR_CUDA, "cannot allocate %zu bytes of pinned host memory for the table", need);
     }
-    char *stage = (char *)h->pinned;
+    char *stage = (char *)ht->block;
     for (auto &c : cols)
-        if (c.bytes) chk(cudaMemcpyAsync(stage + c.at, c.src, c.bytes, cudaMemcpyDeviceToHost, st));
+        if (c.bytes && c.src) chk(cudaMemcpyAsync(stage + c.at, c.src, c.bytes, cudaMemcpyDeviceToHost, st));
     unsigned long long ctr[4] = {0, 0, 0, 0};
     unsigned long long err_sv = EMPTY64;
     uint32_t overflow = 0;
@@ -730,32 +781,36 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
         return fail(h, IPX_ERR_CAPACITY, "%s is full; raise ipx_params.%s", overflow == 1 ? "junction hash table" : "read-offset log",
                     overflow == 1 ? "table_capacity" : "hist_capacity");
     }
-    {
-        auto take = [&](auto &vec, int ci, size_t count) {
-            typedef typename std::remove_reference<decltype(vec)>::type::value_type V;
-            const V *p = reinterpret_cast<const V *>(stage + cols[ci].at);
-            vec.assign(p, p + count);
-        };
-        take(ht->chrom, 0, n); take(ht->i0, 1, n); take(ht->i1, 2, n); take(ht->a0, 3, n); take(ht->a1, 4, n); take(ht->ijunc, 5, n);
-        take(ht->strand, 6, n); take(ht->sites, 7, n * 8); take(ht->counts, 8, n * 3); take(ht->hist_off, 10, n + 1);
-        take(ht->hist_cnt, 11, d.n_hist);
-    }
-    const unsigned long long *T = reinterpret_cast<const unsigned long long *>(stage + cols[9].at);
+    ipx_table &tt = ht->t;
+    tt.n_junctions = n;
+    tt.chrom = (const int32_t *)(stage + cols[C_CHROM].at);
+    tt.intron_start = (const uint32_t *)(stage + cols[C_I0].at);
+    tt.intron_end = (const uint32_t *)(stage + cols[C_I1].at);
+    tt.anchor_start = (const uint32_t *)(stage + cols[C_A0].at);
+    tt.anchor_end = (const uint32_t *)(stage + cols[C_A1].at);
+    tt.ijunc = (const uint32_t *)(stage + cols[C_IJUNC].at);
+    tt.strand = stage + cols[C_STRAND].at;
+    tt.splice_sites = stage + cols[C_SITES].at;
+    tt.read_counts = (const uint64_t *)(stage + cols[C_COUNTS].at);
+    tt.creation_seq = (const uint64_t *)(stage + cols[C_T].at);
+    tt.hist_off = (const uint64_t *)(stage + cols[C_HOFF].at);
+    tt.hist_cnt = (const uint32_t *)(stage + cols[C_HCNT].at);
+    tt.n_hist = d.n_hist;
+    tt.confidence = (const float *)(stage + cols[C_CONF].at);
+    if (n == 0) *(uint64_t *)(stage + cols[C_HOFF].at) = 0;
+    unsigned long long *T = (unsigned long long *)(stage + cols[C_T].at);
+    uint32_t *ijunc = (uint32_t *)(stage + cols[C_IJUNC].at);
     /* sjN continues across flushes (ijunc_, junctions_extractor.hh:129) */
-    for (uint64_t i = 0; i < n; i++) ht->ijunc[i] += h->ijunc_base;
+    for (uint64_t i = 0; i < n; i++) ijunc[i] += h->ijunc_base;
     h->ijunc_base += (uint32_t)n;
-    ht->conf.resize(n);
-    ht->creation.resize(n);
-    for (uint64_t i = 0; i < n; i++) ht->creation[i] = T[i] >> 8;
-    ht->bind();
     tr.mark("flush: host columns");
-    compute_confidences(n, ht->counts.data(), ht->hist_off.data(), ht->hist_cnt.data(), ht->conf.data());
+    compute_confidences(n, tt.read_counts, tt.hist_off, tt.hist_cnt, (float *)(stage + cols[C_CONF].at));
     tr.mark("flush: confidences");
     /* missing-genome warnings in first-miss order (junctions_extractor.cc:411-417) */
     if (h->have_genome && h->params.skip_missing_targets) {
         std::unordered_map<int32_t, unsigned long long> first_miss;
         for (uint64_t i = 0; i < n; i++) {
-            const int32_t tid = ht->chrom[i];
+            const int32_t tid = tt.chrom[i];
             if (h->target_seq[tid] >= 0) continue;
             auto it = first_miss.find(tid);
             if (it == first_miss.end() || T[i] < it->second) first_miss[tid] = T[i];
@@ -766,6 +821,7 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
         for (auto &kv : v)
             if (h->warned_missing.insert(h->targets[kv.second]).second) ht->missing.push_back(kv.second);
     }
+    for (uint64_t i = 0; i < n; i++) T[i] >>= 8; /* sequence value -> creation_seq (drops the strand byte) */
     ht->bind();
     ht->t.status = IPX_OK;
     if (err_sv != EMPTY64) describe_error(h, err_sv, ht);
@@ -799,6 +855,7 @@ extern "C" int ipx_table_set_ijunc(ipx_table *t, const uint32_t *ijunc) {
     HostTable *ht = reinterpret_cast<HostTable *>(t);
     ht->ijunc.assign(ijunc, ijunc + t->n_junctions);
     ht->bind();
+    if (ht->block && t->n_junctions == 0) t->ijunc = ht->ijunc.data();
     return IPX_OK;
 }
 
