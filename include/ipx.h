@@ -98,6 +98,25 @@ typedef struct ipx_batch {
     const uint32_t *cigar;     /* [n_cigar] */
 } ipx_batch;
 
+/* The same batch in the form the host link likes best (the end-to-end path is bound by it): what BAM stores per record
+ * -- the number of CIGAR operations, 16 bits -- instead of 32-bit offsets, and the target index as runs (a coordinate
+ * sorted file has one run per chromosome) instead of a column: 10 bytes per record + 4 per CIGAR word.  The library
+ * expands both on the device. */
+typedef struct ipx_batch_compact {
+    uint64_t n_records;
+    uint64_t n_cigar;            /* total CIGAR words in `cigar` (< 2^32) = sum of n_cigar_ops */
+    uint64_t seq_base;           /* stream index of record 0 */
+    const int32_t *pos;          /* [n_records] */
+    const uint16_t *flag;        /* [n_records] */
+    const uint8_t *nh_class;     /* [n_records] IPX_NH_* */
+    const uint8_t *xs;           /* [n_records] IPX_XS_* or the XS:A character */
+    const uint16_t *n_cigar_ops; /* [n_records] CIGAR words of each record (records with more than 65535 need ipx_batch) */
+    const uint32_t *cigar;       /* [n_cigar] */
+    uint64_t n_tid_runs;         /* runs of consecutive records with the same target index */
+    const int32_t *run_tid;      /* [n_tid_runs] */
+    const uint64_t *run_start;   /* [n_tid_runs] index of the first record of each run; run_start[0] == 0 */
+} ipx_batch_compact;
+
 /* Junction table in key order (chromosome name as std::string::operator<, intron_start,
  * intron_end) = iteration order of the reference's JunctionTable (junctions.hh:77-100,225-246).
  * One row per Junction (junctions.hh:103-202). */
@@ -195,6 +214,8 @@ int ipx_set_genome(ipx_handle *h, int32_t n_seqs, const char *const *names, cons
 int ipx_push_batch(ipx_handle *h, const ipx_batch *batch);
 /* Same, with every pointer in `batch` already resident in device memory (no copy). */
 int ipx_push_batch_device(ipx_handle *h, const ipx_batch *batch);
+/* Same as ipx_push_batch from the compact host form. */
+int ipx_push_batch_compact(ipx_handle *h, const ipx_batch_compact *batch);
 
 /* Finish aggregation on the device (key-order sort, sjN ranking, histogram ordering), asynchronously. */
 int ipx_finalize_device(ipx_handle *h);

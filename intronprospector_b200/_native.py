@@ -55,6 +55,23 @@ class Batch(C.Structure):
     ]
 
 
+class BatchCompact(C.Structure):
+    _fields_ = [
+        ("n_records", C.c_uint64),
+        ("n_cigar", C.c_uint64),
+        ("seq_base", C.c_uint64),
+        ("pos", C.c_void_p),
+        ("flag", C.c_void_p),
+        ("nh_class", C.c_void_p),
+        ("xs", C.c_void_p),
+        ("n_cigar_ops", C.c_void_p),
+        ("cigar", C.c_void_p),
+        ("n_tid_runs", C.c_uint64),
+        ("run_tid", C.c_void_p),
+        ("run_start", C.c_void_p),
+    ]
+
+
 class TableStruct(C.Structure):
     _fields_ = [
         ("n_junctions", C.c_uint64),
@@ -130,7 +147,7 @@ ABI_SYMBOLS = [
     "ipx_flush", "ipx_table_free", "ipx_clear", "ipx_merge_rows_fold", "ipx_partial_row_bytes", "ipx_partial_sizes",
     "ipx_partial_export", "ipx_partial_import", "ipx_format", "ipx_format_tsv_header", "ipx_text_free",
     "ipx_get_timings", "ipx_reset_timings", "ipx_stream", "ipx_thresholds_rows", "ipx_thresholds_export",
-    "ipx_thresholds_import", "ipx_count_deferred", "ipx_table_set_ijunc",
+    "ipx_thresholds_import", "ipx_count_deferred", "ipx_table_set_ijunc", "ipx_push_batch_compact",
 ]
 IO_SYMBOLS = [
     "ipxio_last_error", "ipxio_open", "ipxio_close", "ipxio_n_targets", "ipxio_target_name", "ipxio_read_batch",
@@ -179,6 +196,7 @@ def _bind(lib):
     lib.ipx_thresholds_import.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     lib.ipx_count_deferred.argtypes = [C.c_void_p]
     lib.ipx_table_set_ijunc.argtypes = [C.POINTER(TableStruct), C.c_void_p]
+    lib.ipx_push_batch_compact.argtypes = [C.c_void_p, C.POINTER(BatchCompact)]
 
 
 def load_library(path=None):
@@ -421,6 +439,39 @@ class Engine:
         b = self.make_batch(cols, seq_base)
         self._keep = [cols]
         self._check(self.lib.ipx_push_batch(self.h, C.byref(b)))
+
+    @staticmethod
+    def compact_columns(cols, alloc=None):
+        """ipx_batch columns -> ipx_batch_compact columns (host side; what a record packer would produce directly):
+        operation counts instead of offsets, target runs instead of a target column."""
+        off = np.asarray(cols["cigar_off"]).astype(np.int64)
+        n_ops = np.diff(off)
+        if n_ops.size and n_ops.max() > 0xFFFF:
+            raise IpxError("a record has more than 65535 CIGAR operations: use the plain batch")
+        tid = np.asarray(cols["tid"])
+        starts = np.flatnonzero(np.concatenate(([True], tid[1:] != tid[:-1]))) if tid.size else np.zeros(0, np.int64)
+        out = {k: cols[k] for k in ("pos", "flag", "nh_class", "xs", "cigar")}
+        ops = n_ops.astype(np.uint16)
+        if alloc is not None:
+            buf = alloc(ops.shape, np.uint16)
+            (buf.numpy() if hasattr(buf, "numpy") else buf)[...] = ops
+            ops = buf
+        out["n_cigar_ops"] = ops
+        out["run_start"] = np.ascontiguousarray(starts.astype(np.uint64))
+        out["run_tid"] = np.ascontiguousarray(tid[starts].astype(np.int32)) if tid.size else np.zeros(0, np.int32)
+        return out
+
+    def push_compact(self, ccols, seq_base=0):
+        """ccols: what compact_columns returns (host arrays / pinned tensors)."""
+        b = BatchCompact()
+        b.n_records = int(ccols["pos"].shape[0])
+        b.n_cigar = int(ccols["cigar"].shape[0])
+        b.seq_base = seq_base
+        for k in ("pos", "flag", "nh_class", "xs", "n_cigar_ops", "cigar", "run_tid", "run_start"):
+            setattr(b, k, self._ptr(ccols[k]))
+        b.n_tid_runs = int(ccols["run_tid"].shape[0])
+        self._keep = [ccols]
+        self._check(self.lib.ipx_push_batch_compact(self.h, C.byref(b)))
 
     def push_device(self, cols, seq_base=0):
         """cols: dict of torch CUDA tensors."""

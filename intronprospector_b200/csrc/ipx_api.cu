@@ -171,6 +171,7 @@ struct ipx_handle {
 
     /* staging for host batches */
     DeviceBuf s_tid, s_pos, s_flag, s_nh, s_xs, s_off, s_cig;
+    DeviceBuf s_nops, s_runs, s_tmp; /* compact batches: operation counts, target runs, scan scratch */
     DeviceBuf ev_buf;   /* junction events of the batch in flight (K1 -> K2), one region per tile */
     DeviceBuf tile_cnt; /* TileInfo per tile */
     DeviceBuf long_buf; /* LongRec regions (records handed from the pipelined kernel to k_extract_long) */
@@ -520,7 +521,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq); cudaFree(h->d_export);
     free_genome(h);
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();
-    h->s_off.release(); h->s_cig.release(); h->ev_buf.release(); h->tile_cnt.release(); h->long_buf.release(); h->slot_jrow.release(); h->slot_of.release();
+    h->s_off.release(); h->s_cig.release(); h->s_nops.release(); h->s_runs.release(); h->s_tmp.release(); h->ev_buf.release(); h->tile_cnt.release(); h->long_buf.release(); h->slot_jrow.release(); h->slot_of.release();
     finalize_release(h->fw);
     cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -629,6 +630,47 @@ int settle_finalize(ipx_handle *h) {
     return fail(h, IPX_ERR_CUDA, "finalize did not settle");
 }
 }  // namespace
+
+extern "C" int ipx_push_batch_compact(ipx_handle *h, const ipx_batch_compact *b) {
+    if (!h || !b) return IPX_ERR_ARG;
+    if (b->n_records == 0) return IPX_OK;
+    if (b->n_cigar >> 32) return fail(h, IPX_ERR_ARG, "more than 2^32 CIGAR words in one batch");
+    if (b->n_records >> 31) return fail(h, IPX_ERR_ARG, "more than 2^31 records in one compact batch");
+    if (b->n_tid_runs == 0 || !b->run_tid || !b->run_start || b->run_start[0] != 0)
+        return fail(h, IPX_ERR_ARG, "target runs must cover the batch from record 0");
+    cudaSetDevice(h->device);
+    const uint64_t n = b->n_records, nr = b->n_tid_runs;
+    cudaStream_t st = h->stream;
+    CU(h, h->s_tid.reserve(n * 4, st));
+    CU(h, h->s_pos.reserve(n * 4, st));
+    CU(h, h->s_flag.reserve(n * 2, st));
+    CU(h, h->s_nh.reserve(n, st));
+    CU(h, h->s_xs.reserve(n, st));
+    CU(h, h->s_off.reserve((n + 1) * 4, st));
+    CU(h, h->s_cig.reserve((b->n_cigar ? b->n_cigar : 1) * 4, st));
+    CU(h, h->s_nops.reserve(n * 2, st));
+    CU(h, h->s_runs.reserve(nr * 16, st));
+    size_t tmp_bytes = 0;
+    CU(h, expand_compact(nullptr, n, nullptr, nullptr, nullptr, 0, nullptr, nullptr, &tmp_bytes, st));
+    CU(h, h->s_tmp.reserve(tmp_bytes, st));
+    /* same stream as the previous batch's kernels, so the staging buffers are free again when these copies run */
+    CU(h, cudaMemcpyAsync(h->s_nops.p, b->n_cigar_ops, n * 2, cudaMemcpyHostToDevice, st));
+    unsigned long long *d_run_start = (unsigned long long *)h->s_runs.p;
+    int32_t *d_run_tid = (int32_t *)((char *)h->s_runs.p + nr * 8);
+    CU(h, cudaMemcpyAsync(d_run_start, b->run_start, nr * 8, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(d_run_tid, b->run_tid, nr * 4, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->s_pos.p, b->pos, n * 4, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->s_flag.p, b->flag, n * 2, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->s_nh.p, b->nh_class, n, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->s_xs.p, b->xs, n, cudaMemcpyHostToDevice, st));
+    if (b->n_cigar) CU(h, cudaMemcpyAsync(h->s_cig.p, b->cigar, b->n_cigar * 4, cudaMemcpyHostToDevice, st));
+    CU(h, expand_compact((const uint16_t *)h->s_nops.p, n, (uint32_t *)h->s_off.p, d_run_tid, d_run_start, nr, (int32_t *)h->s_tid.p,
+                         h->s_tmp.p, &tmp_bytes, st));
+    BatchView v{(const int32_t *)h->s_tid.p, (const int32_t *)h->s_pos.p, (const uint16_t *)h->s_flag.p,
+                (const uint8_t *)h->s_nh.p, (const uint8_t *)h->s_xs.p, (const uint32_t *)h->s_off.p,
+                (const uint32_t *)h->s_cig.p, n, b->seq_base};
+    return run_batch(h, v, b->n_cigar);
+}
 
 extern "C" int ipx_finalize_device(ipx_handle *h) {
     if (!h) return IPX_ERR_ARG;

@@ -107,6 +107,11 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
 void launch_fold(int mode, const Tables &t, const Event *ev, const TileInfo *tile_info, uint64_t n_tiles, int sm_count,
                  cudaStream_t st);
 void launch_resolve_T(const Tables &t, const GenomeView &g, cudaStream_t st);
+/* ipx_batch_compact -> ipx_batch columns on the device: cigar_off = exclusive scan of the operation counts (n + 1
+ * entries), tid = the run each record falls into.  tmp: scratch of *tmp_bytes (queried when tmp == NULL). */
+cudaError_t expand_compact(const uint16_t *n_ops, uint64_t n, uint32_t *cigar_off, const int32_t *run_tid,
+                           const unsigned long long *run_start, uint64_t n_runs, int32_t *tid, void *tmp, size_t *tmp_bytes,
+                           cudaStream_t st);
 void launch_export_thresholds(const Tables &t, ThresholdRow *rows, uint64_t n, cudaStream_t st);
 void launch_import_thresholds(const Tables &t, const ThresholdRow *rows, uint64_t n, cudaStream_t st);
 /* rows of ONE source: the offset rows refer to the junction rows of the same call; slot_of: [nj] scratch */

@@ -25,6 +25,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "ipx_engine.h"
 
@@ -84,6 +86,36 @@ void launch_init_tables(const Tables &t, cudaStream_t st) {
 void launch_clear_tables(const Tables &t, cudaStream_t st) {
     k_clear_tables<<<148 * 4, 256, 0, st>>>(t);
     k_reset_counters<<<1, 1, 0, st>>>(t);
+}
+
+/* ------------------------------------------------------------------ compact batch -> columns */
+struct OpsOrZero {
+    const uint16_t *n_ops;
+    uint64_t n;
+    __host__ __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return i < n ? (uint32_t)n_ops[i] : 0u; }
+};
+
+__global__ void k_expand_tid(const int32_t *run_tid, const unsigned long long *run_start, uint64_t n_runs, uint64_t n, int32_t *tid) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    /* last run that starts at or before record i */
+    uint64_t lo = 0, hi = n_runs;
+    while (hi - lo > 1) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (run_start[mid] <= i) lo = mid; else hi = mid;
+    }
+    tid[i] = run_tid[lo];
+}
+
+cudaError_t expand_compact(const uint16_t *n_ops, uint64_t n, uint32_t *cigar_off, const int32_t *run_tid,
+                           const unsigned long long *run_start, uint64_t n_runs, int32_t *tid, void *tmp, size_t *tmp_bytes,
+                           cudaStream_t st) {
+    auto in = thrust::make_transform_iterator(thrust::make_counting_iterator<uint64_t>(0), OpsOrZero{n_ops, n});
+    if (!tmp) return cub::DeviceScan::ExclusiveSum(nullptr, *tmp_bytes, in, cigar_off, (int)(n + 1), st);
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, *tmp_bytes, in, cigar_off, (int)(n + 1), st);
+    if (e != cudaSuccess) return e;
+    if (n && n_runs) k_expand_tid<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(run_tid, run_start, n_runs, n, tid);
+    return cudaGetLastError();
 }
 
 /* ------------------------------------------------------------------ K1: extract */

@@ -143,3 +143,27 @@ def test_unknown_cigar_op_is_reported(built):
     assert got.status == want.status == -3
     assert got.error_text == want.error_text == "Unknown cigar operation 'P'"
     assert got.first_error_seq == want.first_error_seq == 1
+
+
+def test_compact_batches_equal_plain_batches(built):
+    """ipx_push_batch_compact (operation counts + target runs, expanded on the device) against ipx_push_batch."""
+    syn = Synth(700_000, kind=SHORT_UNSTRANDED, genome_len=300_000_000, n_genes=3000, n_contigs=9)
+    cols = syn.columns()
+    cols["tid"][1000:1010] = -1  # a few unmapped records in the middle: more runs, negative targets
+    n = int(cols["tid"].shape[0])
+    plain = _native.Engine(device=0)
+    want = selftest.run_engine(plain, syn.names, cols, n_batches=3)
+    plain.close()
+    eng = _native.Engine(device=0)
+    eng.set_targets(syn.names)
+    bounds = [0, n // 3, n // 3 + 1, n]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        c0, c1 = int(cols["cigar_off"][lo]), int(cols["cigar_off"][hi])
+        part = {k: np.ascontiguousarray(cols[k][lo:hi]) for k in ("tid", "pos", "flag", "nh_class", "xs")}
+        part["cigar_off"] = np.ascontiguousarray(cols["cigar_off"][lo:hi + 1] - np.uint32(c0))
+        part["cigar"] = np.ascontiguousarray(cols["cigar"][c0:c1])
+        eng.push_compact(_native.Engine.compact_columns(part), seq_base=lo)
+    got = eng.flush()
+    eng.close()
+    assert want.n > 5000
+    assert selftest.compare_tables(got, want) == []
