@@ -293,8 +293,13 @@ class Driver {
     }
     void push() {
         if (batch_.size() == 0) return;
-        ipx_batch v = batch_.view();
-        check_ipx(h_, ipx_push_batch(h_, &v));
+        if (batch_.compact_ok) {
+            ipx_batch_compact v = batch_.view_compact();
+            check_ipx(h_, ipx_push_batch_compact(h_, &v));
+        } else {
+            ipx_batch v = batch_.view();
+            check_ipx(h_, ipx_push_batch(h_, &v));
+        }
         batch_.clear(next_seq_);
     }
     ipx_table *flush() {

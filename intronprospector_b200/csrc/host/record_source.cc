@@ -62,6 +62,12 @@ void scan_tags(const bam1_t *b, uint8_t *nh_class, uint8_t *xs) {
 void ColumnarBatch::add(const bam1_t *b, int32_t mapped_tid) {
     uint8_t nh, x;
     scan_tags(b, &nh, &x);
+    if (run_tid.empty() || run_tid.back() != mapped_tid) {
+        run_tid.push_back(mapped_tid);
+        run_start.push_back((uint64_t)tid.size());
+    }
+    if (b->core.n_cigar > 0xFFFFu) compact_ok = false;
+    n_cigar_ops.push_back((uint16_t)b->core.n_cigar);
     tid.push_back(mapped_tid);
     pos.push_back((int32_t)b->core.pos);
     flag.push_back(b->core.flag);
@@ -85,6 +91,24 @@ ipx_batch ColumnarBatch::view() const {
     v.xs = xs.data();
     v.cigar_off = cigar_off.data();
     v.cigar = cigar.data();
+    return v;
+}
+
+ipx_batch_compact ColumnarBatch::view_compact() const {
+    ipx_batch_compact v;
+    memset(&v, 0, sizeof(v));
+    v.n_records = tid.size();
+    v.n_cigar = cigar.size();
+    v.seq_base = seq_base;
+    v.pos = pos.data();
+    v.flag = flag.data();
+    v.nh_class = nh_class.data();
+    v.xs = xs.data();
+    v.n_cigar_ops = n_cigar_ops.data();
+    v.cigar = cigar.data();
+    v.n_tid_runs = run_tid.size();
+    v.run_tid = run_tid.data();
+    v.run_start = run_start.data();
     return v;
 }
 

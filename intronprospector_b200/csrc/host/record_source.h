@@ -20,15 +20,23 @@ struct ColumnarBatch {
     std::vector<uint16_t> flag;
     std::vector<uint8_t> nh_class, xs;
     std::vector<uint32_t> cigar_off, cigar;
+    /* the compact form (ipx_batch_compact), kept alongside: what goes over the host link when every record fits it */
+    std::vector<uint16_t> n_cigar_ops;
+    std::vector<int32_t> run_tid;
+    std::vector<uint64_t> run_start;
+    bool compact_ok = true; /* no record with more than 65535 operations so far */
     uint64_t seq_base = 0;
     void clear(uint64_t next_seq_base) {
         tid.clear(); pos.clear(); flag.clear(); nh_class.clear(); xs.clear(); cigar.clear();
         cigar_off.assign(1, 0u);
+        n_cigar_ops.clear(); run_tid.clear(); run_start.clear();
+        compact_ok = true;
         seq_base = next_seq_base;
     }
     size_t size() const { return tid.size(); }
     void add(const bam1_t *b, int32_t mapped_tid);
     ipx_batch view() const;
+    ipx_batch_compact view_compact() const;
 };
 
 }  // namespace ipx

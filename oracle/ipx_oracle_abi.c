@@ -43,6 +43,29 @@ int ipx_set_genome(ipx_handle *h, int32_t n, const char *const *names, const uin
 int ipx_push_batch(ipx_handle *h, const ipx_batch *b) { return ipxo_push_batch(h->st, b); }
 int ipx_push_batch_device(ipx_handle *h, const ipx_batch *b) { (void)h; (void)b; return IPX_ERR_CUDA; }
 int ipx_finalize_device(ipx_handle *h) { (void)h; return IPX_OK; }
+/* ipx_batch_compact -> ipx_batch on the host (the product expands it on the device) */
+int ipx_push_batch_compact(ipx_handle *h, const ipx_batch_compact *c) {
+    if (!h || !c) return IPX_ERR_ARG;
+    if (c->n_records == 0) return IPX_OK;
+    const uint64_t n = c->n_records;
+    int32_t *tid = (int32_t *)malloc(n * sizeof(int32_t));
+    uint32_t *off = (uint32_t *)malloc((n + 1) * sizeof(uint32_t));
+    uint64_t run = 0;
+    off[0] = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        while (run + 1 < c->n_tid_runs && c->run_start[run + 1] <= i) run++;
+        tid[i] = c->run_tid[run];
+        off[i + 1] = off[i] + c->n_cigar_ops[i];
+    }
+    ipx_batch b;
+    b.n_records = n; b.n_cigar = c->n_cigar; b.seq_base = c->seq_base;
+    b.tid = tid; b.pos = c->pos; b.flag = c->flag; b.nh_class = c->nh_class; b.xs = c->xs; b.cigar_off = off; b.cigar = c->cigar;
+    int rc = ipxo_push_batch(h->st, &b);
+    free(tid);
+    free(off);
+    return rc;
+}
+
 int ipx_flush(ipx_handle *h, ipx_table **out) { return ipxo_flush(h->st, out); }
 void ipx_table_free(ipx_table *t) { ipxo_table_free(t); }
 int ipx_clear(ipx_handle *h) { ipx_table *t = NULL; ipxo_flush(h->st, &t); ipxo_table_free(t); return IPX_OK; }
