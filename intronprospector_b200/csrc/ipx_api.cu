@@ -407,7 +407,7 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
             Span s(h, &h->tm_extract, 0);
             int launched = 0;
             CU(h, launch_extract(b, n_cigar, h->xp, h->tab, (Event *)d.events, (TileInfo *)d.tile_info, (LongRec *)h->long_buf.p,
-                                 h->sm_count, h->stream, &launched));
+                                 h->d_counters + 96, h->sm_count, h->stream, &launched));
             h->tm_extract.launches += (uint64_t)launched;
         }
         {
@@ -427,8 +427,8 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
     {
         Span s(h, &h->tm_extract, 0);
         int launched = 0;
-        CU(h, launch_extract(b, n_cigar, h->xp, h->tab, (Event *)h->ev_buf.p, tile_count, (LongRec *)h->long_buf.p, h->sm_count,
-                             h->stream, &launched));
+        CU(h, launch_extract(b, n_cigar, h->xp, h->tab, (Event *)h->ev_buf.p, tile_count, (LongRec *)h->long_buf.p, h->d_counters + 96,
+                             h->sm_count, h->stream, &launched));
         h->tm_extract.launches += (uint64_t)launched;
     }
     if (two_pass(h)) {

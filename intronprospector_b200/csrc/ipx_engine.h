@@ -103,7 +103,8 @@ void launch_init_tables(const Tables &t, cudaStream_t st);  /* whole tables, onc
 void launch_clear_tables(const Tables &t, cudaStream_t st); /* only what the lists say is in use */
 /* returns a CUDA error (attribute set-up of the pipelined kernel can fail), launches counted in *launches */
 cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractParams &p, const Tables &t, Event *out,
-                           TileInfo *tile_info, LongRec *long_recs, int sm_count, cudaStream_t st, int *launches);
+                           TileInfo *tile_info, LongRec *long_recs, unsigned long long *next_record, int sm_count, cudaStream_t st,
+                           int *launches);
 void launch_fold(int mode, const Tables &t, const Event *ev, const TileInfo *tile_info, uint64_t n_tiles, int sm_count,
                  cudaStream_t st);
 void launch_resolve_T(const Tables &t, const GenomeView &g, cudaStream_t st);

@@ -219,6 +219,95 @@ __global__ void __launch_bounds__(EXS_THREADS) k_extract_simple(BatchView b, Ext
     }
 }
 
+/* ---- K1 for long reads: every lane walks its own record and fetches the next one the moment it is done ----
+ * Read lengths are log-normal, so a warp that takes 32 records and waits for the longest idles two thirds of its lanes.
+ * Here lanes are persistent: a lane that finishes a record takes the next unprocessed one from a global counter
+ * (claims are aggregated per warp), so all lanes stay busy until the batch runs out.  The walk itself is the branch-free
+ * automaton, one operation per iteration for all lanes, the word after next already requested from L2. */
+__global__ void k_tile_info_init(const uint32_t *cigar_off, TileInfo *tile_info, uint64_t n_tiles) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tiles) tile_info[i] = TileInfo{0u, __ldg(&cigar_off[i * EX_TILE]), 0u, 0u};
+}
+
+__global__ void __launch_bounds__(256) k_extract_lanes(BatchView b, ExtractParams p, Tables t, Event *out, TileInfo *tile_info,
+                                                       unsigned long long *next_record) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long live_words = 0ull, events = 0ull;
+    /* per-lane record in flight */
+    uint64_t rec = ~0ull;
+    uint32_t k = 0u, n = 0u, c0 = 0u, bad = 0u;
+    bool out_of_work = false;
+    WalkState w;
+    w.init(0);
+    Candidate dummy;
+    (void)dummy;
+    int32_t s_tid = 0;
+    int64_t s_pos = 0;
+    uint32_t s_cat = 0u;
+    char s_strand = '.';
+    bool s_may_emit = false;
+    Event *region = out;
+    uint32_t *fill = nullptr;
+    for (;;) {
+        const bool need = k >= n && !out_of_work;
+        const unsigned need_mask = __ballot_sync(0xFFFFFFFFu, need);
+        if (need_mask) {
+            /* finish what this lane just walked, then claim the next record */
+            unsigned long long base = 0ull;
+            const int leader = __ffs(need_mask) - 1;
+            if (lane == leader) base = atomicAdd(next_record, (unsigned long long)__popc(need_mask));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (need) {
+                if (rec != ~0ull && n != 0u) {
+                    EventSink sink{t, p, region, fill, s_tid, s_pos, b.seq_base + rec, s_cat, s_strand, strand_class(s_strand), s_may_emit, 0u};
+                    if (bad) atomicMin(t.err_sv, make_err_cigar(b.seq_base + rec, bad & 15u));
+                    else walk_finish(w, sink);
+                    events += sink.n_events;
+                }
+                rec = base + (unsigned)__popc(need_mask & ((1u << lane) - 1u));
+                k = 0u; n = 0u; bad = 0u;
+                if (rec >= b.n) {
+                    out_of_work = true;
+                    rec = ~0ull;
+                } else {
+                    c0 = __ldg(&b.cigar_off[rec]);
+                    const uint32_t n_cigar = __ldg(&b.cigar_off[rec + 1]) - c0;
+                    s_tid = __ldg(&b.tid[rec]);
+                    const uint32_t flag = __ldg(&b.flag[rec]);
+                    if (record_is_live(n_cigar, s_tid, flag)) {
+                        n = n_cigar;
+                        live_words += n_cigar;
+                        s_pos = __ldg(&b.pos[rec]);
+                        const uint32_t nh = __ldg(&b.nh[rec]), xs = __ldg(&b.xs[rec]);
+                        s_strand = read_strand(p.strandness, flag, xs);
+                        s_cat = read_category(flag, nh);
+                        s_may_emit = read_may_emit(p, flag, nh);
+                        const uint64_t tile = rec / EX_TILE;
+                        region = out + tile_event_base(__ldg(&b.cigar_off[tile * EX_TILE]));
+                        fill = &tile_info[tile].count; /* the tile's event count doubles as the fill pointer of its region */
+                        w.init(s_pos);
+                    }
+                }
+            }
+        }
+        if (__all_sync(0xFFFFFFFFu, out_of_work)) break;
+        if (k < n) {
+            const uint32_t word = __ldg(&b.cigar[c0 + k]);
+            if (k + 16u < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(b.cigar + c0 + k + 16u));
+            EventSink sink{t, p, region, fill, s_tid, s_pos, b.seq_base + rec, s_cat, s_strand, strand_class(s_strand), s_may_emit, 0u};
+            bad = walk_op_flat(w, word, p.max_anchor_indel_size, sink);
+            events += sink.n_events;
+            k = bad ? n : k + 1u;
+        }
+    }
+    live_words = warp_sum(live_words);
+    events = warp_sum(events);
+    if (lane == 0) {
+        if (live_words) atomicAdd(t.n_live, live_words);
+        if (events) atomicAdd(t.n_events, events);
+    }
+}
+
 /* ---- K1 for long reads: thread per record, CIGAR words staged through shared memory 32 at a time ----
  * A long read has hundreds to thousands of CIGAR operations.  Walking them straight from global memory makes every
  * lane of a warp pull its own 32-byte sector per load; here the warp copies the next 32 words of each of its 32
@@ -673,7 +762,8 @@ __global__ void __launch_bounds__(256) k_extract_long(BatchView b, ExtractParams
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
 cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractParams &p, const Tables &t, Event *out,
-                           TileInfo *tile_info, LongRec *long_recs, int sm_count, cudaStream_t st, int *launches) {
+                           TileInfo *tile_info, LongRec *long_recs, unsigned long long *next_record, int sm_count, cudaStream_t st,
+                           int *launches) {
     if (launches) *launches = 0;
     if (b.n == 0) return cudaSuccess;
     const uint64_t n_tiles = tiles_of(b.n), n_full = b.n / EX_TILE;
@@ -719,7 +809,15 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
      * memory (9.98 vs 9.65 ms per 1 M reads of ~800 operations: both are bound by instructions per operation and by
      * lanes idling behind the longest read of their warp), so it is opt-in */
     static const bool staged = getenv("IPX_K1_STAGED") != nullptr;
-    if (first_simple < n_tiles && n_cigar > 8 * b.n && staged) {
+    static const bool no_lanes = getenv("IPX_K1_NO_LANES") != nullptr;
+    if (first_simple == 0 && n_cigar > 8 * b.n && !staged && !no_lanes && next_record) {
+        /* long reads: persistent lanes */
+        cudaError_t e = cudaMemsetAsync(next_record, 0, sizeof(unsigned long long), st);
+        if (e != cudaSuccess) return e;
+        k_tile_info_init<<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>(b.cigar_off, tile_info, n_tiles);
+        k_extract_lanes<<<sm_count * 6, 256, 0, st>>>(b, p, t, out, tile_info, next_record);
+        if (launches) (*launches) += 2;
+    } else if (first_simple < n_tiles && n_cigar > 8 * b.n && staged) {
         const uint64_t todo = n_tiles - first_simple;
         const uint64_t max_blocks = (uint64_t)sm_count * 6;
         k_extract_staged<<<(int)(todo < max_blocks ? todo : max_blocks), EXL_THREADS, 0, st>>>(b, p, t, out, tile_info, first_simple,
