@@ -809,9 +809,9 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
      * memory (9.98 vs 9.65 ms per 1 M reads of ~800 operations: both are bound by instructions per operation and by
      * lanes idling behind the longest read of their warp), so it is opt-in */
     static const bool staged = getenv("IPX_K1_STAGED") != nullptr;
-    static const bool no_lanes = getenv("IPX_K1_NO_LANES") != nullptr;
-    if (first_simple == 0 && n_cigar > 8 * b.n && !staged && !no_lanes && next_record) {
-        /* long reads: persistent lanes */
+    /* persistent lanes measured slower still (14.7 ms): the per-iteration bookkeeping costs more than the idle lanes */
+    static const bool lanes = getenv("IPX_K1_LANES") != nullptr;
+    if (first_simple == 0 && n_cigar > 8 * b.n && lanes && next_record) {
         cudaError_t e = cudaMemsetAsync(next_record, 0, sizeof(unsigned long long), st);
         if (e != cudaSuccess) return e;
         k_tile_info_init<<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>(b.cigar_off, tile_info, n_tiles);
