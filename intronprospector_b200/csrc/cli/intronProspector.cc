@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <map>
 #include <memory>
+#include <unordered_map>
 #include <vector>
 
 #include "cli_common.h"
@@ -17,6 +18,7 @@
 #include "htslib/sam.h"
 #include "ipx.h"
 #include "record_source.h"
+#include "../ipx_walk.cuh" /* the automaton, host build: per-read annotations below */
 
 using namespace std;
 
@@ -223,6 +225,133 @@ struct Input {
     }
 };
 
+/* Per-read side outputs: --debug-trace rows and --set-XS/TS-strand-tag (create_junction / update_junction trace lines
+ * junctions_extractor.cc:446-485, orientCnt :526-528, update_strand_tag :98-111).  Both depend on the junction a read's
+ * event lands in -- its creator-fixed strand and motif, and whether the event came before the junction existed -- which
+ * is known once the device table is flushed.  So with either option the records are kept in memory in stream order,
+ * and after the flush every kept read is walked once more on the host with the same automaton the kernels run
+ * (ipx_walk.cuh) and looked up in the table.  The junction tables themselves still come from the device. */
+class Annotator {
+    struct Kept {
+        bam1_t *rec;
+        uint64_t seq;
+        int32_t tid;      /* engine target index */
+        bool processed;   /* went through process_alignment */
+        bool pass;        /* is written to the pass-through file */
+    };
+    vector<Kept> kept_;
+    const Options &opts_;
+    unique_ptr<OutFile> trace_;
+
+    struct Key {
+        int32_t tid;
+        uint32_t i0, i1;
+        bool operator==(const Key &o) const { return tid == o.tid && i0 == o.i0 && i1 == o.i1; }
+    };
+    struct KeyHash {
+        size_t operator()(const Key &k) const {
+            uint64_t x = ((uint64_t)(uint32_t)k.tid << 40) ^ ((uint64_t)k.i0 << 20) ^ k.i1;
+            x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33;
+            return (size_t)x;
+        }
+    };
+
+    public:
+    explicit Annotator(const Options &o) : opts_(o) {
+        if (o.debug_trace_tsv != "") trace_.reset(new OutFile(o.debug_trace_tsv));
+    }
+    ~Annotator() {
+        for (auto &k : kept_) bam_destroy1(k.rec);
+    }
+    bool active() const { return trace_ || opts_.set_XS_strand_tag || opts_.set_TS_strand_tag; }
+    /* JunctionsExtractor::open writes the header every time an input is opened (junctions_extractor.cc:579-584) */
+    void input_opened() {
+        if (!trace_) return;
+        const string h = "chrom\tintron_start\tintron_end\tqname\tflag\tstrand\tsplice_sites\tanchor_start\tanchor_end\n";
+        trace_->write(h.data(), h.size());
+    }
+    void keep(const bam1_t *b, uint64_t seq, int32_t tid, bool processed, bool pass) {
+        Kept k{bam_copy1(bam_init1(), b), seq, tid, processed, pass};
+        kept_.push_back(k);
+    }
+    void mark_pass_last() { if (!kept_.empty()) kept_.back().pass = true; }
+
+    /* after the flush: trace rows, strand tags, and the delayed pass-through writes, in stream order */
+    void finish(const ipx_table *t, const vector<string> &targets, Input *in) {
+        std::unordered_map<Key, uint64_t, KeyHash> rows;
+        rows.reserve(t->n_junctions * 2 + 16);
+        for (uint64_t i = 0; i < t->n_junctions; i++) rows.emplace(Key{t->chrom[i], t->intron_start[i], t->intron_end[i]}, i);
+        ipx::ExtractParams xp;
+        xp.min_anchor_length = opts_.min_anchor_length;
+        xp.max_anchor_indel_size = opts_.max_anchor_indel_size;
+        xp.min_intron_length = opts_.min_intron_length;
+        xp.max_intron_length = opts_.max_intron_length;
+        xp.excludes = opts_.excludes;
+        xp.strandness = opts_.strandness;
+        string line;
+        for (auto &k : kept_) {
+            bam1_t *b = k.rec;
+            int orient = 0;
+            if (k.processed && ipx::record_is_live(b->core.n_cigar, b->core.tid, b->core.flag)) {
+                uint8_t nh, xs;
+                ipx::scan_tags(b, &nh, &xs);
+                const char strand = ipx::read_strand(xp.strandness, b->core.flag, xs);
+                const bool may_emit = ipx::read_may_emit(xp, b->core.flag, nh);
+                auto sink = [&](const ipx::Candidate &c) {
+                    if (!may_emit || !ipx::junction_qc(xp, c)) return;
+                    auto it = rows.find(Key{k.tid, (uint32_t)c.intron_start, (uint32_t)c.intron_end});
+                    if (it == rows.end()) return; /* the junction never came to exist */
+                    const uint64_t r = it->second;
+                    const uint64_t ev = (k.seq << 20) | (c.ordinal & 0xFFFFFu);
+                    if (!t->creation_seq || ev < t->creation_seq[r]) return; /* before it existed: add_junction returned NULL */
+                    const char *sites = t->splice_sites + 8 * r;
+                    if (trace_) {
+                        line.clear();
+                        line += targets[k.tid]; line += '\t';
+                        line += to_string((long long)c.intron_start); line += '\t';
+                        line += to_string((long long)c.intron_end); line += '\t';
+                        line += bam_get_qname(b); line += '\t';
+                        line += to_string((unsigned)b->core.flag); line += '\t';
+                        if (ev == t->creation_seq[r]) { /* create_junction: the corrected strand, then an empty column */
+                            line += t->strand[r]; line += '\t';
+                        } else {                        /* update_junction: the read's strand, then the junction's */
+                            line += strand; line += '\t';
+                            line += t->strand[r];
+                        }
+                        line += '\t';
+                        line += sites; line += '\t';
+                        line += to_string((long long)c.anchor_start); line += '\t';
+                        line += to_string((long long)c.anchor_end); line += '\n';
+                        trace_->write(line.data(), line.size());
+                    }
+                    if (sites[0] >= 'A' && sites[0] <= 'Z') orient += (t->strand[r] == '+') ? 1 : -1; /* Junction::is_canonical */
+                };
+                ipx::WalkState w;
+                w.init(b->core.pos);
+                const uint32_t *cig = bam_get_cigar(b);
+                uint32_t bad = 0;
+                for (uint32_t i = 0; i < b->core.n_cigar && !bad; i++) bad = ipx::walk_op(w, cig[i], xp.max_anchor_indel_size, sink);
+                if (!bad) ipx::walk_finish(w, sink);
+            }
+            if (orient != 0) {
+                if (opts_.set_XS_strand_tag) update_strand_tag("XS", orient, b);
+                if (opts_.set_TS_strand_tag) update_strand_tag("TS", orient, b);
+            }
+            if (k.pass && in) in->pass(b);
+            bam_destroy1(b);
+        }
+        kept_.clear();
+    }
+
+    private:
+    static void update_strand_tag(const char *tag, int orient, bam1_t *b) {
+        const uint8_t strand = (orient > 0) ? '+' : '-';
+        uint8_t *existing = bam_aux_get(b, tag);
+        if (existing != NULL && bam_aux_del(b, existing) != 0) throw runtime_error("Error deleting read tag");
+        if (bam_aux_append(b, tag, 'A', 1, &strand) != 0) throw runtime_error("Error adding read tag");
+    }
+};
+
 class Driver {
     const Options &opts_;
     ipx_handle *h_ = nullptr;
@@ -231,6 +360,8 @@ class Driver {
     map<string, int32_t> name_first_;
     ipx::ColumnarBatch batch_;
     uint64_t next_seq_ = 0;
+    uint64_t last_seq_ = 0; /* stream index and engine target of the record process() saw last */
+    int32_t last_tid_ = -1;
     /* stream segments (first record index, target) of processed records, for attributing deferred errors */
     vector<pair<uint64_t, int32_t>> segments_;
     static const size_t BATCH_RECORDS = 1u << 22;
@@ -280,6 +411,8 @@ class Driver {
         check_ipx(h_, ipx_set_targets(h_, (int32_t)ptrs.size(), ptrs.data()));
     }
     size_t n_targets() const { return targets_.size(); }
+    uint64_t last_seq() const { return last_seq_; }
+    int32_t last_tid() const { return last_tid_; }
     const vector<string> &targets() const { return targets_; }
 
     /* process_alignment (junctions_extractor.cc:533-549): hand the record to the engine */
@@ -288,6 +421,8 @@ class Driver {
         if (tid >= 0 && (size_t)tid < canon_tid_.size()) tid = canon_tid_[tid];
         if (segments_.empty() || segments_.back().second != tid) segments_.emplace_back(next_seq_, tid);
         batch_.add(b, tid);
+        last_seq_ = next_seq_;
+        last_tid_ = tid;
         next_seq_++;
         if (batch_.size() >= BATCH_RECORDS || batch_.cigar.size() >= BATCH_CIGAR) push();
     }
@@ -354,9 +489,10 @@ static void target_rows(const ipx_table *t, int32_t tid, uint64_t *begin, uint64
 
 /* extract_junctions_by_target (intronProspector.cc:356-371) with identify_junctions_for_target /
  * process_target_alignment (junctions_extractor.cc:637-664) */
-static void extract_by_target(Driver &drv, const Options &opts, Outputs &out) {
+static void extract_by_target(Driver &drv, const Options &opts, Outputs &out, Annotator &ann) {
     Input in(opts.bam_files[0]);
     drv.add_targets(in.hdr);
+    ann.input_opened();
     if (opts.bam_pass_through != "") in.open_pass_through(opts.bam_pass_through);
     const int n_targets = (int)drv.n_targets();
     int previous_target = -1;
@@ -383,11 +519,13 @@ static void extract_by_target(Driver &drv, const Options &opts, Outputs &out) {
                 break;
             }
             drv.process(aln);
-            in.pass(aln);
+            if (ann.active()) ann.keep(aln, drv.last_seq(), drv.last_tid(), true, true); /* written after the flush */
+            else in.pass(aln);
         }
         previous_target = target;
     }
     ipx_table *t = drv.flush();
+    if (ann.active()) ann.finish(t, drv.targets(), in.out != NULL ? &in : NULL);
     if (t->status != IPX_OK) {
         /* the reference throws while processing the failing record: earlier targets are already written */
         int32_t err_tid = t->error_tid >= 0 ? t->error_tid : drv.target_of_seq(t->first_error_seq);
@@ -421,16 +559,21 @@ static void extract_by_target(Driver &drv, const Options &opts, Outputs &out) {
 }
 
 /* extract_junctions_unsorted / extract_junctions_multiple (intronProspector.cc:375-401) */
-static void extract_whole_files(Driver &drv, const Options &opts, Outputs &out) {
+static void extract_whole_files(Driver &drv, const Options &opts, Outputs &out, Annotator &ann) {
     for (size_t ibam = 0; ibam < opts.bam_files.size(); ibam++) {
         Input in(opts.bam_files[ibam]);
         drv.add_targets(in.hdr);
+        ann.input_opened();
         /* in --unsorted mode the reference opens the pass-through file but only copy_unaligned_reads writes to it,
          * after every record has been consumed: the file gets the header only */
         if (opts.bam_files.size() == 1 && opts.bam_pass_through != "") in.open_pass_through(opts.bam_pass_through);
-        while (in.read()) drv.process(in.rec);
+        while (in.read()) {
+            drv.process(in.rec);
+            if (ann.active()) ann.keep(in.rec, drv.last_seq(), drv.last_tid(), true, false);
+        }
     }
     ipx_table *t = drv.flush();
+    if (ann.active()) ann.finish(t, drv.targets(), NULL);
     if (t->status != IPX_OK) {
         string msg = t->error_text;
         ipx_table_free(t);
@@ -443,16 +586,14 @@ static void extract_whole_files(Driver &drv, const Options &opts, Outputs &out) 
 static void extract_junctions(const Options &opts) {
     ipx::LoadedGenome genome;
     if (opts.genome_fa.size() > 0) ipx::load_genome(opts.genome_fa, genome);
-    if (opts.debug_trace_tsv != "") throw runtime_error("--debug-trace is not available in the GPU build yet");
-    if (opts.set_XS_strand_tag || opts.set_TS_strand_tag)
-        throw runtime_error("--set-XS-strand-tag / --set-TS-strand-tag are not available in the GPU build yet");
+    Annotator ann(opts);
     Driver drv(opts);
     if (opts.genome_fa.size() > 0) drv.set_genome(genome);
     Outputs out(opts);
     if (opts.bam_files.size() > 1 || opts.unsorted) {
-        extract_whole_files(drv, opts, out);
+        extract_whole_files(drv, opts, out, ann);
     } else {
-        extract_by_target(drv, opts, out);
+        extract_by_target(drv, opts, out, ann);
     }
 }
 

@@ -31,6 +31,9 @@ def compare_tables(a, b):
         if ca[k].shape != cb[k].shape or not np.array_equal(ca[k], cb[k]):
             bad = "shape" if ca[k].shape != cb[k].shape else int(np.argmax(np.any((ca[k] != cb[k]).reshape(len(ca[k]), -1), axis=1)))
             diffs.append("column %s differs (first at %s)" % (k, bad))
+    # the stream position of each junction's creating event (what sjN ranks, what multi-GPU runs agree on)
+    if len(a.creation_seq) == a.n and len(b.creation_seq) == b.n and not np.array_equal(a.creation_seq, b.creation_seq):
+        diffs.append("column creation_seq differs")
     for fmt in (_native.FMT_INTRON_BED9, _native.FMT_INTRON_BED6, _native.FMT_INTRON_TSV):
         for minc in (0.0, 1.0):
             if a.text(fmt, minc) != b.text(fmt, minc):

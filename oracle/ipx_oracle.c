@@ -54,6 +54,7 @@ typedef struct {
     char strand;
     char sites[8];
     uint32_t ijunc;
+    uint64_t creation; /* (record stream index << 20) | candidate ordinal of the creating event */
     uint64_t counts[3];
     uint16_t *offsets; /* read_offsets, junctions.hh:120 */
     size_t n_off, cap_off;
@@ -416,6 +417,8 @@ typedef struct {
     int state;
     int64_t tpos, a0, i0, i1, a1;
     uint32_t lmm, rmm, lind, rind, cur;
+    uint64_t seq;     /* stream index of the record */
+    uint32_t ordinal; /* candidates the automaton has handed to record_junction so far */
 } walker;
 
 /* junction_qc, junctions_extractor.cc:384-401 (signed 64-bit comparisons) */
@@ -434,6 +437,7 @@ static int junction_qc(const walker *w) {
 /* record_junction -> add_junction -> create/update_junction, junctions_extractor.cc:446-530 */
 static int record_junction(walker *w) {
     ipxo_state *st = w->st;
+    const uint32_t ordinal = w->ordinal++;
     if (!junction_qc(w)) return IPX_OK;
     st->n_events++;
     uint32_t ks = (uint32_t)w->i0, ke = (uint32_t)w->i1;
@@ -452,6 +456,7 @@ static int record_junction(walker *w) {
         j->strand = strand;
         strcpy(j->sites, sites);
         j->ijunc = st->ijunc++;
+        j->creation = (w->seq << 20) | (ordinal & 0xFFFFFu); /* ipx_table.creation_seq */
         count_read(j, cat, offset);
     } else {
         if (w->a0 < (int64_t)j->anchor_start) j->anchor_start = (uint32_t)w->a0;
@@ -551,6 +556,7 @@ int ipxo_push_batch(ipxo_state *st, const ipx_batch *b) {
         w.flag = flag;
         w.nh_class = b->nh_class[r];
         w.strand = read_strand(&st->p, flag, b->xs[r]);
+        w.seq = b->seq_base + r;
         w.state = LIMBO;
         w.tpos = w.pos;
         w.a0 = w.i0 = w.i1 = w.a1 = -1;
@@ -604,6 +610,7 @@ typedef struct {
     ipx_table t;
     int32_t *chrom;
     uint32_t *i0, *i1, *a0, *a1, *ijunc, *hist_cnt;
+    uint64_t *creation;
     char *strand, *sites;
     uint64_t *counts, *hist_off;
     float *conf;
@@ -619,6 +626,7 @@ static otable *table_alloc(size_t n, size_t n_hist) {
     o->a0 = (uint32_t *)calloc(m, 4);
     o->a1 = (uint32_t *)calloc(m, 4);
     o->ijunc = (uint32_t *)calloc(m, 4);
+    o->creation = (uint64_t *)calloc(m, 8);
     o->strand = (char *)calloc(m, 1);
     o->sites = (char *)calloc(m, 8);
     o->counts = (uint64_t *)calloc(m * 3, 8);
@@ -635,6 +643,7 @@ static otable *table_alloc(size_t n, size_t n_hist) {
     o->t.splice_sites = o->sites;
     o->t.read_counts = o->counts;
     o->t.ijunc = o->ijunc;
+    o->t.creation_seq = o->creation;
     o->t.confidence = o->conf;
     o->t.hist_off = o->hist_off;
     o->t.hist_cnt = o->hist_cnt;
@@ -645,7 +654,7 @@ static otable *table_alloc(size_t n, size_t n_hist) {
 void ipxo_table_free(ipx_table *t) {
     if (!t) return;
     otable *o = (otable *)t;
-    free(o->chrom); free(o->i0); free(o->i1); free(o->a0); free(o->a1); free(o->ijunc);
+    free(o->chrom); free(o->i0); free(o->i1); free(o->a0); free(o->a1); free(o->ijunc); free(o->creation);
     free(o->strand); free(o->sites); free(o->counts); free(o->conf); free(o->hist_off); free(o->hist_cnt);
     free(o->missing);
     free(o);
@@ -684,6 +693,7 @@ int ipxo_flush(ipxo_state *st, ipx_table **out) {
         o->strand[i] = j->strand;
         memcpy(o->sites + 8 * i, j->sites, 8);
         o->ijunc[i] = j->ijunc;
+        o->creation[i] = j->creation;
         for (int c = 0; c < 3; c++) o->counts[3 * i + c] = j->counts[c];
         /* lazy_get_confidence, junctions.cc:44-51 */
         o->conf[i] = (j->counts[0] + j->counts[1] + j->counts[2] == 0) ? 0.0f : confidence_of(j->offsets, j->n_off);

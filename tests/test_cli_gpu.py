@@ -10,7 +10,7 @@ import runner
 from intronprospector_b200.synth import LONG, SHORT_STRANDED, SHORT_UNSTRANDED, Synth
 
 pytestmark = pytest.mark.gpu
-NOT_YET = ("debug-trace", "strand-tags")
+NOT_YET = ()
 
 
 def gpu_binaries():
@@ -22,8 +22,6 @@ def gpu_binaries():
 
 @pytest.mark.parametrize("case", cases.ALL_CASES, ids=[c["name"] for c in cases.ALL_CASES])
 def test_cuda_cli_reproduces_golden(case, built, fixture_dir):
-    if "strand-tags" in case["needs"]:
-        pytest.skip("strand-tag rewriting is a 'next' row (SURVEY.md 8f.2)")
     problems = runner.run_case(case, fixture_dir, gpu_binaries(), skip_needs=NOT_YET)
     assert not problems, "\n".join(problems)
 

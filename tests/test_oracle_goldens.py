@@ -11,8 +11,8 @@ import pytest
 import cases
 import runner
 
-# side outputs that the CLI does not implement yet
-NOT_YET = ("debug-trace", "strand-tags")
+# every side output of the reference is implemented (debug trace, pass-through, strand tags: SURVEY.md 8f rows 2-3)
+NOT_YET = ()
 
 
 def oracle_binaries():
@@ -24,8 +24,6 @@ def oracle_binaries():
 
 @pytest.mark.parametrize("case", cases.ALL_CASES, ids=[c["name"] for c in cases.ALL_CASES])
 def test_oracle_cli_reproduces_golden(case, built, fixture_dir):
-    if "strand-tags" in case["needs"]:
-        pytest.skip("strand-tag rewriting is a 'next' row (SURVEY.md 8f.2)")
     bins = oracle_binaries()
     for p in bins.values():
         assert os.path.exists(p), "missing %s (run make -C oracle)" % p
