@@ -25,31 +25,201 @@
 #include <cerrno>
 #include <cctype>
 #include <string>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <vector>
 #include <unordered_map>
 
 namespace {
 
 /* ---------- buffered reader over gzread ---------- */
+/* BGZF is a series of independent gzip members of at most 64 KiB each, so a BAM file inflates in parallel: one thread
+ * reads the compressed blocks in file order, a few workers inflate them, and the consumer takes the results back in
+ * order.  (The reference gets the same from htslib's thread pool when asked; here it is the default for BGZF input.) */
+class ParallelBgzf {
+    struct Slot {
+        std::vector<uint8_t> in, out;
+        size_t out_len = 0, out_pos = 0;
+        int state = 0; /* 0 free, 1 filled (compressed), 2 being inflated, 3 inflated */
+        bool bad = false;
+    };
+    FILE *fp_ = nullptr;
+    std::vector<Slot> ring_;
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    uint64_t n_read_ = 0;     /* blocks the reader thread has put into the ring */
+    uint64_t n_claimed_ = 0;  /* blocks handed to inflate workers */
+    uint64_t n_consumed_ = 0; /* blocks the consumer is done with */
+    bool read_done_ = false, stop_ = false, read_error_ = false;
+
+    void reader_main() {
+        for (;;) {
+            uint8_t hdr[18];
+            size_t got = fread(hdr, 1, 18, fp_);
+            bool ok = got == 18 && hdr[0] == 0x1f && hdr[1] == 0x8b && hdr[2] == 8 && (hdr[3] & 4) && hdr[12] == 'B' && hdr[13] == 'C';
+            size_t bsize = ok ? (size_t)(hdr[16] | (hdr[17] << 8)) + 1 : 0;
+            std::unique_lock<std::mutex> lk(mu_);
+            if (got == 0 || !ok || bsize < 26) {
+                if (got != 0) read_error_ = true; /* not a BGZF block where one must start */
+                read_done_ = true;
+                cv_.notify_all();
+                return;
+            }
+            cv_.wait(lk, [&] { return stop_ || n_read_ - n_consumed_ < ring_.size(); });
+            if (stop_) return;
+            Slot &s = ring_[n_read_ % ring_.size()];
+            lk.unlock();
+            s.in.resize(bsize);
+            memcpy(s.in.data(), hdr, 18);
+            if (fread(s.in.data() + 18, 1, bsize - 18, fp_) != bsize - 18) {
+                lk.lock();
+                read_error_ = true;
+                read_done_ = true;
+                cv_.notify_all();
+                return;
+            }
+            lk.lock();
+            s.state = 1;
+            s.bad = false;
+            n_read_++;
+            cv_.notify_all();
+        }
+    }
+
+    void worker_main() {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) return;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return stop_ || n_claimed_ < n_read_ || (read_done_ && n_claimed_ >= n_read_); });
+            if (stop_ || n_claimed_ >= n_read_) break;
+            Slot &s = ring_[n_claimed_ % ring_.size()];
+            n_claimed_++;
+            s.state = 2;
+            lk.unlock();
+            const size_t bsize = s.in.size();
+            uint32_t isize;
+            memcpy(&isize, s.in.data() + bsize - 4, 4);
+            s.out.resize(isize ? isize : 1);
+            inflateReset(&zs);
+            zs.next_in = s.in.data() + 18;
+            zs.avail_in = (uInt)(bsize - 18 - 8);
+            zs.next_out = s.out.data();
+            zs.avail_out = (uInt)isize;
+            int rc = isize ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+            const bool bad = rc != Z_STREAM_END || zs.avail_out != 0;
+            lk.lock();
+            s.bad = bad;
+            s.out_len = isize;
+            s.out_pos = 0;
+            s.state = 3;
+            cv_.notify_all();
+        }
+        inflateEnd(&zs);
+    }
+
+   public:
+    static bool looks_like_bgzf(const char *fn) {
+        FILE *f = fopen(fn, "rb");
+        if (!f) return false;
+        uint8_t h[16];
+        bool ok = fread(h, 1, 16, f) == 16 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C';
+        fclose(f);
+        return ok;
+    }
+    bool open(const char *fn, int n_workers) {
+        fp_ = fopen(fn, "rb");
+        if (!fp_) return false;
+        setvbuf(fp_, nullptr, _IOFBF, 1 << 22);
+        ring_.resize((size_t)n_workers * 8);
+        threads_.emplace_back([this] { reader_main(); });
+        for (int i = 0; i < n_workers; i++) threads_.emplace_back([this] { worker_main(); });
+        return true;
+    }
+    /* up to `want` inflated bytes, in file order; 0 at the end of the file, -1 on a damaged block */
+    int read(uint8_t *dst, int want) {
+        int done = 0;
+        while (done < want) {
+            std::unique_lock<std::mutex> lk(mu_);
+            Slot &s = ring_[n_consumed_ % ring_.size()];
+            cv_.wait(lk, [&] { return (n_consumed_ < n_read_ && s.state == 3) || (read_done_ && n_consumed_ >= n_read_); });
+            if (n_consumed_ >= n_read_) return read_error_ && done == 0 ? -1 : done;
+            if (s.bad) return -1;
+            lk.unlock();
+            const size_t take = std::min<size_t>(s.out_len - s.out_pos, (size_t)(want - done));
+            memcpy(dst + done, s.out.data() + s.out_pos, take);
+            s.out_pos += take;
+            done += (int)take;
+            if (s.out_pos == s.out_len) {
+                lk.lock();
+                s.state = 0;
+                n_consumed_++;
+                cv_.notify_all();
+            } else {
+                break; /* `want` is satisfied */
+            }
+            if (done > 0 && done >= want) break;
+        }
+        return done;
+    }
+    void close() {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+        threads_.clear();
+        if (fp_) fclose(fp_);
+        fp_ = nullptr;
+    }
+    ~ParallelBgzf() { close(); }
+};
+
 struct Reader {
     gzFile gz = nullptr;
+    ParallelBgzf *pbgzf = nullptr; /* BGZF input with more than one decode thread */
+    bool direct = false;           /* the input is not compressed */
     std::vector<uint8_t> buf;
     size_t beg = 0, end = 0;
     bool eof = false;
     bool err = false;
 
+    static int decode_threads() {
+        if (const char *e = getenv("IPX_DECODE_THREADS")) return atoi(e);
+        unsigned hw = std::thread::hardware_concurrency();
+        return (int)std::min<unsigned>(8u, hw > 2 ? hw / 2 : 1u);
+    }
     bool open(const char *fn) {
         if (strcmp(fn, "-") == 0) fn = "/dev/stdin";
+        const int threads = decode_threads();
+        if (threads > 1 && strcmp(fn, "/dev/stdin") != 0 && ParallelBgzf::looks_like_bgzf(fn)) {
+            pbgzf = new ParallelBgzf();
+            if (!pbgzf->open(fn, threads)) {
+                delete pbgzf;
+                pbgzf = nullptr;
+                return false;
+            }
+            buf.resize(1 << 20);
+            return true;
+        }
         gz = gzopen(fn, "rb");
         if (!gz) return false;
         gzbuffer(gz, 1 << 20);
         buf.resize(1 << 20);
+        direct = gzdirect(gz) != 0;
         return true;
     }
     void close() {
         if (gz) gzclose(gz);
         gz = nullptr;
+        delete pbgzf;
+        pbgzf = nullptr;
     }
+    int raw_read(uint8_t *dst, int want) { return pbgzf ? pbgzf->read(dst, want) : gzread(gz, dst, want); }
     /* make at least n bytes available if possible; returns bytes available */
     size_t ensure(size_t n) {
         if (end - beg >= n) return end - beg;
@@ -61,7 +231,7 @@ struct Reader {
         if (buf.size() < n) buf.resize(n + (1 << 16));
         while (end - beg < n && !eof) {
             int want = (int)std::min<size_t>(buf.size() - end, 1u << 30);
-            int got = gzread(gz, buf.data() + end, want);
+            int got = raw_read(buf.data() + end, want);
             if (got < 0) { err = true; eof = true; break; }
             if (got == 0) { eof = true; break; }
             end += got;
@@ -209,11 +379,11 @@ extern "C" htsFile *hts_open_format(const char *fn, const char *mode, const htsF
         fp->format.category = sequence_data;
         if (n >= 4 && memcmp(rd.buf.data() + rd.beg, "BAM\1", 4) == 0) {
             fp->format.format = bam;
-            fp->format.compression = gzdirect(rd.gz) ? no_compression : bgzf;
+            fp->format.compression = rd.direct ? no_compression : bgzf;
             fp->is_bin = 1;
         } else {
             fp->format.format = sam;
-            fp->format.compression = gzdirect(rd.gz) ? no_compression : gzip;
+            fp->format.compression = rd.direct ? no_compression : gzip;
         }
         return fp;
     }
