@@ -95,16 +95,45 @@ struct OpsOrZero {
     __host__ __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return i < n ? (uint32_t)n_ops[i] : 0u; }
 };
 
-__global__ void k_expand_tid(const int32_t *run_tid, const unsigned long long *run_start, uint64_t n_runs, uint64_t n, int32_t *tid) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__device__ __forceinline__ uint64_t run_of(const unsigned long long *run_start, uint64_t n_runs, uint64_t i) {
     /* last run that starts at or before record i */
     uint64_t lo = 0, hi = n_runs;
     while (hi - lo > 1) {
         const uint64_t mid = (lo + hi) >> 1;
         if (run_start[mid] <= i) lo = mid; else hi = mid;
     }
-    tid[i] = run_tid[lo];
+    return lo;
+}
+
+/* a warp fills 128 consecutive records; almost always they lie in one run, found once by lane 0 */
+__global__ void __launch_bounds__(256) k_expand_tid(const int32_t *run_tid, const unsigned long long *run_start, uint64_t n_runs,
+                                                    uint64_t n, int32_t *tid) {
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint64_t first = warp * 128;
+    if (first >= n) return;
+    const uint64_t last = first + 127 < n ? first + 127 : n - 1;
+    uint64_t r = 0, r_end = 0;
+    if (lane == 0) {
+        r = run_of(run_start, n_runs, first);
+        r_end = r + 1 < n_runs ? run_start[r + 1] : ~0ull;
+    }
+    r = __shfl_sync(0xFFFFFFFFu, r, 0);
+    r_end = __shfl_sync(0xFFFFFFFFu, r_end, 0);
+    if (last < r_end) {
+        const int32_t v = run_tid[r];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint64_t i = first + (uint64_t)j * 32 + lane;
+            if (i < n) tid[i] = v;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint64_t i = first + (uint64_t)j * 32 + lane;
+            if (i < n) tid[i] = run_tid[run_of(run_start, n_runs, i)];
+        }
+    }
 }
 
 cudaError_t expand_compact(const uint16_t *n_ops, uint64_t n, uint32_t *cigar_off, const int32_t *run_tid,
@@ -114,7 +143,7 @@ cudaError_t expand_compact(const uint16_t *n_ops, uint64_t n, uint32_t *cigar_of
     if (!tmp) return cub::DeviceScan::ExclusiveSum(nullptr, *tmp_bytes, in, cigar_off, (int)(n + 1), st);
     cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, *tmp_bytes, in, cigar_off, (int)(n + 1), st);
     if (e != cudaSuccess) return e;
-    if (n && n_runs) k_expand_tid<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(run_tid, run_start, n_runs, n, tid);
+    if (n && n_runs) k_expand_tid<<<(unsigned)((n + 1023) / 1024), 256, 0, st>>>(run_tid, run_start, n_runs, n, tid);
     return cudaGetLastError();
 }
 
