@@ -481,9 +481,12 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
         : "memory");
     return done != 0u;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+/* try_wait parks the thread on the barrier for a while (NANOSLEEP.SYNCS) but comes back early often enough that a bare
+ * retry loop burns a seventh of the kernel's issue slots; a short sleep between tries gives them to the working warps */
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t sleep_ns) {
     while (!mbar_try(bar, parity, 1000000u)) {
-    } /* try_wait parks the thread on the barrier (NANOSLEEP.SYNCS) until the phase flips or the hint runs out */
+        if (sleep_ns) __nanosleep(sleep_ns);
+    }
 }
 /* TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP) */
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -630,7 +633,7 @@ __device__ __forceinline__ void walk_short(const BatchView &b, const ExtractPara
 template <int LOOKAHEAD, int WORKERS>
 __global__ void __launch_bounds__((WORKERS + 1) * 32, 2) k_extract_tma(BatchView b, uint32_t n_cigar_words, ExtractParams p, Tables t,
                                                                Event *out, TileInfo *tile_info, LongRec *long_recs,
-                                                               uint32_t n_full_tiles, int walk_long_here) {
+                                                               uint32_t n_full_tiles, int walk_long_here, uint32_t sleep_ns) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ExStage *stages = reinterpret_cast<ExStage *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + EX_STAGES * sizeof(ExStage)); /* TMA bytes have landed */
@@ -665,7 +668,7 @@ __global__ void __launch_bounds__((WORKERS + 1) * 32, 2) k_extract_tma(BatchView
             ExStage &S = stages[s];
             if (it >= (uint32_t)EX_STAGES) {
                 /* the tile that occupied this stage has been left by every worker */
-                mbar_wait(&empty[s], ((it / EX_STAGES) & 1u) ^ 1u);
+                mbar_wait(&empty[s], ((it / EX_STAGES) & 1u) ^ 1u, sleep_ns ? 4 * sleep_ns : 0u);
                 tile_info[S.tile] = TileInfo{S.region_fill, S.off[0], walk_long_here ? 0u : S.n_lists >> 16, 0u};
                 S.n_lists = S.next_round = S.rounds_done = S.next_short = S.next_long = S.region_fill = 0u;
             }
@@ -715,9 +718,9 @@ __global__ void __launch_bounds__((WORKERS + 1) * 32, 2) k_extract_tma(BatchView
             }
         }
         /* (2) this tile must be classified before it can be walked: help with what is left, then wait for the rest */
-        mbar_wait(&full[s], (it / EX_STAGES) & 1u);
+        mbar_wait(&full[s], (it / EX_STAGES) & 1u, sleep_ns);
         take_rounds(S, s, classified, lane, long_recs, walk_long_here, live_words);
-        mbar_wait(&classified[s], (it / EX_STAGES) & 1u);
+        mbar_wait(&classified[s], (it / EX_STAGES) & 1u, sleep_ns);
         /* (3) chunks of this tile: 32 listed records at a time, longest CIGARs first */
         const uint32_t n_lists = *((volatile uint32_t *)&S.n_lists);
         const uint32_t n_short = n_lists & 0xFFFFu, n_long = walk_long_here ? n_lists >> 16 : 0u;
@@ -806,7 +809,8 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
         const size_t smem = EX_STAGES * sizeof(ExStage) + 3 * EX_STAGES * sizeof(uint64_t);
         static const int walk_long_here = getenv("IPX_K1_SPLIT_LONG") ? 0 : 1;
         static const int workers_env = getenv("IPX_K1_WORKERS") ? atoi(getenv("IPX_K1_WORKERS")) : EX_WORKER_WARPS;
-        typedef void (*Kernel)(BatchView, uint32_t, ExtractParams, Tables, Event *, TileInfo *, LongRec *, uint32_t, int);
+        typedef void (*Kernel)(BatchView, uint32_t, ExtractParams, Tables, Event *, TileInfo *, LongRec *, uint32_t, int, uint32_t);
+        static const uint32_t sleep_ns = getenv("IPX_K1_SLEEP") ? (uint32_t)atoi(getenv("IPX_K1_SLEEP")) : 0u;
         /* measured on B200 (100 M short reads): look-ahead 1 / 2 / 3 tiles: 0.74 / 0.77 / 0.81 ms; named barriers 1.05 ms */
         Kernel kernel = k_extract_tma<EX_LOOKAHEAD, EX_WORKER_WARPS>;
         int workers = EX_WORKER_WARPS;
@@ -824,7 +828,7 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
         const uint64_t max_blocks = (uint64_t)sm_count * 2;
         const int blocks = (int)(n_full < max_blocks ? n_full : max_blocks);
         kernel<<<blocks, (workers + 1) * 32, smem, st>>>(b, (uint32_t)n_cigar, p, t, out, tile_info, long_recs, (uint32_t)n_full,
-                                                        walk_long_here);
+                                                        walk_long_here, sleep_ns);
         if (launches) (*launches)++;
         if (!walk_long_here) {
             const uint64_t want = (n_full + 7) / 8;
