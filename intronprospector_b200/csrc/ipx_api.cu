@@ -396,7 +396,9 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
     /* event buffer for the worst case: every emitted candidate consumes one N op and a following aligned op */
     const uint64_t ev_bound = n_cigar / 2 + 1;
     const uint64_t n_tiles = tiles_of(b.n);
-    CU(h, h->long_buf.reserve((n_cigar / 4 + 2) * sizeof(LongRec), h->stream));
+    /* only the optional two-kernel variant of K1 (IPX_K1_SPLIT_LONG) hands records over through this buffer */
+    static const bool split_long = getenv("IPX_K1_SPLIT_LONG") != nullptr;
+    if (split_long) CU(h, h->long_buf.reserve((n_cigar / 4 + 2) * sizeof(LongRec), h->stream));
     if (h->params.deferred_counting && two_pass(h)) {
         /* K1 and the first-seen pass only; the events stay on the device until ipx_count_deferred */
         ipx_handle::Deferred d{nullptr, nullptr, n_tiles};
