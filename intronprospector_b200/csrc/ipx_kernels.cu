@@ -248,159 +248,107 @@ __global__ void __launch_bounds__(EXS_THREADS) k_extract_simple(BatchView b, Ext
     }
 }
 
-/* ---- K1 for long reads: every lane walks its own record and fetches the next one the moment it is done ----
- * Read lengths are log-normal, so a warp that takes 32 records and waits for the longest idles two thirds of its lanes.
- * Here lanes are persistent: a lane that finishes a record takes the next unprocessed one from a global counter
- * (claims are aggregated per warp), so all lanes stay busy until the batch runs out.  The walk itself is the branch-free
- * automaton, one operation per iteration for all lanes, the word after next already requested from L2. */
-__global__ void k_tile_info_init(const uint32_t *cigar_off, TileInfo *tile_info, uint64_t n_tiles) {
+/* ---- K1 for long reads: records taken longest first, two-path 32-bit automaton, 16-byte CIGAR loads ----
+ * A long read has hundreds to thousands of CIGAR operations and read lengths are log-normal.  Thread-per-record in
+ * stream order loses twice: a warp idles behind its longest read (ncu: 17.6 of 32 lanes active), and the general
+ * 64-bit automaton spends ~100 instructions per operation.  Here
+ *   - k_long_keys + a radix sort order the records by operation count, longest first; warps claim 32 consecutive
+ *     records of that order from a counter, so the lanes of a warp run the same number of iterations and the long
+ *     reads do not end up in the tail;
+ *   - lanes walk with lean_op (ipx_walk.cuh): positions relative to the record start in 32 bits and a common path
+ *     of a dozen instructions for aligned runs and short indels inside an anchor;
+ *   - a lane reads its record's words as aligned 16-byte groups, the next group requested before the current one is
+ *     walked (one load instruction per four operations, and the four sectors of a 128-byte line are used while hot).
+ * Events go to the region of the record's tile as everywhere else; the tile's event count in tile_info doubles as
+ * the region's fill pointer (global atomics: a long read emits a handful of events per thousand operations). */
+__global__ void __launch_bounds__(256) k_long_keys(const uint32_t *cigar_off, uint64_t n, uint32_t *n_ops, uint32_t *index,
+                                                   TileInfo *tile_info) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_tiles) tile_info[i] = TileInfo{0u, __ldg(&cigar_off[i * EX_TILE]), 0u, 0u};
+    if (i >= n) return;
+    const uint32_t c0 = __ldg(&cigar_off[i]);
+    n_ops[i] = __ldg(&cigar_off[i + 1]) - c0;
+    index[i] = (uint32_t)i;
+    if (i % EX_TILE == 0) tile_info[i / EX_TILE] = TileInfo{0u, c0, 0u, 0u};
 }
 
-__global__ void __launch_bounds__(256) k_extract_lanes(BatchView b, ExtractParams p, Tables t, Event *out, TileInfo *tile_info,
-                                                       unsigned long long *next_record) {
+/* the rest of a record whose relative positions outgrew 32 bits (a CIGAR spanning > 2.9 Gb: malformed input, kept exact) */
+__device__ __forceinline__ uint32_t walk_wide_rest(const LeanState &lw, int64_t pos, const uint32_t *cig, uint32_t k, uint32_t n,
+                                                uint32_t max_indel, EventSink &sink) {
+    WalkState w;
+    lw.widen(pos, w);
+    uint32_t bad = 0u;
+    for (; k < n && !bad; ++k) bad = walk_op_flat(w, __ldg(&cig[k]), max_indel, sink);
+    if (!bad) walk_finish(w, sink);
+    return bad;
+}
+
+__device__ __forceinline__ uint4 load_cigar_group(const uint32_t *cigar, uint64_t group, uint64_t n_words) {
+    if (group * 4 + 4 <= n_words) return __ldg(reinterpret_cast<const uint4 *>(cigar) + group);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u); /* the last, partial group of the buffer */
+    if (group * 4 + 0 < n_words) v.x = __ldg(&cigar[group * 4 + 0]);
+    if (group * 4 + 1 < n_words) v.y = __ldg(&cigar[group * 4 + 1]);
+    if (group * 4 + 2 < n_words) v.z = __ldg(&cigar[group * 4 + 2]);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_extract_sorted(BatchView b, uint64_t n_words, ExtractParams p, Tables t, Event *out,
+                                                        TileInfo *tile_info, const uint32_t *order,
+                                                        unsigned long long *next_chunk) {
     const int lane = threadIdx.x & 31;
     unsigned long long live_words = 0ull, events = 0ull;
-    /* per-lane record in flight */
-    uint64_t rec = ~0ull;
-    uint32_t k = 0u, n = 0u, c0 = 0u, bad = 0u;
-    bool out_of_work = false;
-    WalkState w;
-    w.init(0);
-    Candidate dummy;
-    (void)dummy;
-    int32_t s_tid = 0;
-    int64_t s_pos = 0;
-    uint32_t s_cat = 0u;
-    char s_strand = '.';
-    bool s_may_emit = false;
-    Event *region = out;
-    uint32_t *fill = nullptr;
     for (;;) {
-        const bool need = k >= n && !out_of_work;
-        const unsigned need_mask = __ballot_sync(0xFFFFFFFFu, need);
-        if (need_mask) {
-            /* finish what this lane just walked, then claim the next record */
-            unsigned long long base = 0ull;
-            const int leader = __ffs(need_mask) - 1;
-            if (lane == leader) base = atomicAdd(next_record, (unsigned long long)__popc(need_mask));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (need) {
-                if (rec != ~0ull && n != 0u) {
-                    EventSink sink{t, p, region, fill, s_tid, s_pos, b.seq_base + rec, s_cat, s_strand, strand_class(s_strand), s_may_emit, 0u};
-                    if (bad) atomicMin(t.err_sv, make_err_cigar(b.seq_base + rec, bad & 15u));
-                    else walk_finish(w, sink);
-                    events += sink.n_events;
-                }
-                rec = base + (unsigned)__popc(need_mask & ((1u << lane) - 1u));
-                k = 0u; n = 0u; bad = 0u;
-                if (rec >= b.n) {
-                    out_of_work = true;
-                    rec = ~0ull;
-                } else {
-                    c0 = __ldg(&b.cigar_off[rec]);
-                    const uint32_t n_cigar = __ldg(&b.cigar_off[rec + 1]) - c0;
-                    s_tid = __ldg(&b.tid[rec]);
-                    const uint32_t flag = __ldg(&b.flag[rec]);
-                    if (record_is_live(n_cigar, s_tid, flag)) {
-                        n = n_cigar;
-                        live_words += n_cigar;
-                        s_pos = __ldg(&b.pos[rec]);
-                        const uint32_t nh = __ldg(&b.nh[rec]), xs = __ldg(&b.xs[rec]);
-                        s_strand = read_strand(p.strandness, flag, xs);
-                        s_cat = read_category(flag, nh);
-                        s_may_emit = read_may_emit(p, flag, nh);
-                        const uint64_t tile = rec / EX_TILE;
-                        region = out + tile_event_base(__ldg(&b.cigar_off[tile * EX_TILE]));
-                        fill = &tile_info[tile].count; /* the tile's event count doubles as the fill pointer of its region */
-                        w.init(s_pos);
-                    }
-                }
+        unsigned long long chunk = 0ull;
+        if (lane == 0) chunk = atomicAdd(next_chunk, 1ull);
+        chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
+        if (chunk * 32ull >= b.n) break;
+        const uint64_t i = chunk * 32ull + (unsigned)lane;
+        if (i >= b.n) continue;
+        const uint64_t r = __ldg(&order[i]);
+        const uint32_t c0 = __ldg(&b.cigar_off[r]), c1 = __ldg(&b.cigar_off[r + 1]), n_cigar = c1 - c0;
+        const int32_t tid = __ldg(&b.tid[r]);
+        const uint32_t flag = __ldg(&b.flag[r]);
+        if (!record_is_live(n_cigar, tid, flag)) continue;
+        live_words += n_cigar;
+        const int64_t pos = __ldg(&b.pos[r]);
+        const uint64_t tile = r / EX_TILE;
+        Event *region = out + tile_event_base(__ldg(&b.cigar_off[tile * EX_TILE]));
+        EventSink sink = make_sink(t, p, region, &tile_info[tile].count, tid, pos, b.seq_base + r, flag, __ldg(&b.nh[r]), __ldg(&b.xs[r]));
+        LeanState w;
+        w.init();
+        uint32_t bad = 0u;
+        uint32_t wide_from = 0xFFFFFFFFu;
+        const uint32_t max_indel = p.max_anchor_indel_size;
+        const uint32_t g_first = c0 >> 2, g_last = (c1 - 1u) >> 2; /* n_cigar >= 2 */
+        uint4 cur = load_cigar_group(b.cigar, g_first, n_words);
+        for (uint32_t g = g_first; g <= g_last; ++g) {
+            uint4 nxt = cur;
+            if (g < g_last) nxt = load_cigar_group(b.cigar, g + 1u, n_words);
+            if (w.tpos >= LEAN_TPOS_LIMIT || bad) {
+                wide_from = g * 4u < c0 ? 0u : g * 4u - c0;
+                break;
             }
+            if (g != g_first && g != g_last) { /* all four words belong to the record */
+                lean_op(w, pos, cur.x, max_indel, sink, bad);
+                lean_op(w, pos, cur.y, max_indel, sink, bad);
+                lean_op(w, pos, cur.z, max_indel, sink, bad);
+                lean_op(w, pos, cur.w, max_indel, sink, bad);
+            } else {
+                const uint32_t k0 = g * 4u - c0; /* index of cur.x in the record; wraps below zero in the first group */
+                if (k0 + 0u < n_cigar && !bad) lean_op(w, pos, cur.x, max_indel, sink, bad);
+                if (k0 + 1u < n_cigar && !bad) lean_op(w, pos, cur.y, max_indel, sink, bad);
+                if (k0 + 2u < n_cigar && !bad) lean_op(w, pos, cur.z, max_indel, sink, bad);
+                if (k0 + 3u < n_cigar && !bad) lean_op(w, pos, cur.w, max_indel, sink, bad);
+            }
+            cur = nxt;
         }
-        if (__all_sync(0xFFFFFFFFu, out_of_work)) break;
-        if (k < n) {
-            const uint32_t word = __ldg(&b.cigar[c0 + k]);
-            if (k + 16u < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(b.cigar + c0 + k + 16u));
-            EventSink sink{t, p, region, fill, s_tid, s_pos, b.seq_base + rec, s_cat, s_strand, strand_class(s_strand), s_may_emit, 0u};
-            bad = walk_op_flat(w, word, p.max_anchor_indel_size, sink);
-            events += sink.n_events;
-            k = bad ? n : k + 1u;
+        if (bad) { /* reported below */
+        } else if (wide_from != 0xFFFFFFFFu) {
+            bad = walk_wide_rest(w, pos, b.cigar + c0, wide_from, n_cigar, max_indel, sink);
+        } else {
+            lean_finish(w, pos, sink);
         }
-    }
-    live_words = warp_sum(live_words);
-    events = warp_sum(events);
-    if (lane == 0) {
-        if (live_words) atomicAdd(t.n_live, live_words);
-        if (events) atomicAdd(t.n_events, events);
-    }
-}
-
-/* ---- K1 for long reads: thread per record, CIGAR words staged through shared memory 32 at a time ----
- * A long read has hundreds to thousands of CIGAR operations.  Walking them straight from global memory makes every
- * lane of a warp pull its own 32-byte sector per load; here the warp copies the next 32 words of each of its 32
- * records with one coalesced 128-byte load per record, and every lane then walks its own record's words from shared
- * memory (row stride 33 words: conflict-free).  The automaton state stays in registers between segments. */
-static const int EXL_THREADS = 256;
-static const int EXL_WARPS = EXL_THREADS / 32;
-
-__global__ void __launch_bounds__(EXL_THREADS) k_extract_staged(BatchView b, ExtractParams p, Tables t, Event *out,
-                                                                TileInfo *tile_info, uint64_t first_tile, uint64_t n_tiles) {
-    __shared__ uint32_t region_fill;
-    __shared__ uint32_t rows[EXL_WARPS][32][33];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t(*row)[33] = rows[warp];
-    unsigned long long live_words = 0ull, events = 0ull;
-    for (uint64_t tile = first_tile + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (threadIdx.x == 0) region_fill = 0u;
-        __syncthreads();
-        const uint64_t r0 = tile * EX_TILE;
-        const uint32_t first_word = __ldg(&b.cigar_off[r0]);
-        Event *region = out + tile_event_base(first_word);
-        /* a warp takes 32 consecutive records at a time */
-        for (uint64_t g = r0 + (uint64_t)warp * 32; g < r0 + EX_TILE && g < b.n; g += EXL_THREADS) {
-            const uint64_t r = g + lane;
-            uint32_t c0 = 0u, n_cigar = 0u, flag = 0u;
-            int32_t tid = -1;
-            if (r < b.n) {
-                c0 = __ldg(&b.cigar_off[r]);
-                n_cigar = __ldg(&b.cigar_off[r + 1]) - c0;
-                tid = __ldg(&b.tid[r]);
-                flag = __ldg(&b.flag[r]);
-            }
-            const bool live = record_is_live(n_cigar, tid, flag);
-            if (!live) n_cigar = 0u;
-            live_words += n_cigar;
-            const int64_t pos = live ? (int64_t)__ldg(&b.pos[r]) : 0;
-            EventSink sink = make_sink(t, p, region, &region_fill, tid, pos, b.seq_base + r, flag, live ? __ldg(&b.nh[r]) : 0u,
-                                       live ? __ldg(&b.xs[r]) : 0u);
-            WalkState w;
-            w.init(pos);
-            uint32_t bad = 0u;
-            const uint32_t max_n = __reduce_max_sync(0xFFFFFFFFu, n_cigar);
-            for (uint32_t k0 = 0; k0 < max_n; k0 += 32u) {
-                /* stage words [k0, k0 + 32) of every record that still has some */
-#pragma unroll 4
-                for (int j = 0; j < 32; ++j) {
-                    const uint32_t nj = __shfl_sync(0xFFFFFFFFu, n_cigar, j);
-                    const uint32_t cj = __shfl_sync(0xFFFFFFFFu, c0, j);
-                    if (k0 + lane < nj) row[j][lane] = __ldg(&b.cigar[cj + k0 + lane]);
-                }
-                __syncwarp();
-                const uint32_t stop = n_cigar > k0 ? (n_cigar - k0 < 32u ? n_cigar - k0 : 32u) : 0u;
-                for (uint32_t k = 0; k < stop && !bad; ++k) bad = walk_op_flat(w, row[lane][k], p.max_anchor_indel_size, sink);
-                __syncwarp();
-            }
-            if (live) {
-                if (bad) atomicMin(t.err_sv, make_err_cigar(b.seq_base + r, bad & 15u)); /* first such record in stream order */
-                else walk_finish(w, sink);
-            }
-            events += sink.n_events;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) tile_info[tile] = TileInfo{region_fill, first_word, 0u, 0u};
-        __syncthreads();
+        if (bad) atomicMin(t.err_sv, make_err_cigar(b.seq_base + r, bad & 15u)); /* the reference throws here */
+        events += sink.n_events;
     }
     live_words = warp_sum(live_words);
     events = warp_sum(events);
@@ -838,24 +786,31 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
         }
         first_simple = n_full;
     }
-    /* long reads: staging the CIGAR words through shared memory measured no faster than walking them from global
-     * memory (9.98 vs 9.65 ms per 1 M reads of ~800 operations: both are bound by instructions per operation and by
-     * lanes idling behind the longest read of their warp), so it is opt-in */
-    static const bool staged = getenv("IPX_K1_STAGED") != nullptr;
-    /* persistent lanes measured slower still (14.7 ms): the per-iteration bookkeeping costs more than the idle lanes */
-    static const bool lanes = getenv("IPX_K1_LANES") != nullptr;
-    if (first_simple == 0 && n_cigar > 8 * b.n && lanes && next_record) {
-        cudaError_t e = cudaMemsetAsync(next_record, 0, sizeof(unsigned long long), st);
+    /* long reads (more than 8 operations per record on average): longest first, lean automaton */
+    if (first_simple == 0 && !force_simple && n_cigar > 8 * b.n && aligned16(b.cigar) && next_record) {
+        const int n = (int)b.n;
+        size_t sort_bytes = 0;
+        cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                                  (const uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, 32, st);
         if (e != cudaSuccess) return e;
-        k_tile_info_init<<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>(b.cigar_off, tile_info, n_tiles);
-        k_extract_lanes<<<sm_count * 6, 256, 0, st>>>(b, p, t, out, tile_info, next_record);
-        if (launches) (*launches) += 2;
-    } else if (first_simple < n_tiles && n_cigar > 8 * b.n && staged) {
-        const uint64_t todo = n_tiles - first_simple;
-        const uint64_t max_blocks = (uint64_t)sm_count * 6;
-        k_extract_staged<<<(int)(todo < max_blocks ? todo : max_blocks), EXL_THREADS, 0, st>>>(b, p, t, out, tile_info, first_simple,
-                                                                                                n_tiles);
-        if (launches) (*launches)++;
+        const size_t col = ((size_t)b.n * sizeof(uint32_t) + 255) & ~(size_t)255;
+        char *scratch = nullptr;
+        e = cudaMallocAsync(&scratch, 4 * col + sort_bytes, st);
+        if (e != cudaSuccess) return e;
+        uint32_t *n_ops = reinterpret_cast<uint32_t *>(scratch), *n_ops_sorted = reinterpret_cast<uint32_t *>(scratch + col);
+        uint32_t *index = reinterpret_cast<uint32_t *>(scratch + 2 * col), *order = reinterpret_cast<uint32_t *>(scratch + 3 * col);
+        k_long_keys<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b.cigar_off, b.n, n_ops, index, tile_info);
+        e = cub::DeviceRadixSort::SortPairsDescending(scratch + 4 * col, sort_bytes, n_ops, n_ops_sorted, index, order, n, 0, 32, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(next_record, 0, sizeof(unsigned long long), st);
+        if (e == cudaSuccess) {
+            const uint64_t chunks = (b.n + 31) / 32, want = (chunks + 7) / 8, max_blocks = (uint64_t)sm_count * 8;
+            k_extract_sorted<<<(int)(want < max_blocks ? want : max_blocks), 256, 0, st>>>(b, n_cigar, p, t, out, tile_info, order,
+                                                                                         next_record);
+            e = cudaGetLastError();
+        }
+        cudaFreeAsync(scratch, st);
+        if (launches) (*launches) += 3; /* keys, extract, and the sort counted as one */
+        return e;
     } else if (first_simple < n_tiles) {
         const uint64_t todo = n_tiles - first_simple;
         const uint64_t max_blocks = (uint64_t)sm_count * 8;

@@ -243,5 +243,130 @@ IPX_HD void walk_finish(WalkState &w, Emit &emit) {
     if (w.state == ST_RIGHT) emit_candidate(w, emit);
 }
 
+/* ---- the same automaton for long CIGARs: two paths, 32-bit registers ----
+ * In a long read nearly every operation is an aligned run or a short indel inside an anchor, which changes no state:
+ * those take a path of a dozen instructions.  What makes it short:
+ *   - positions are kept relative to the record's start (32 bits; the caller checks `tpos` against LEAN_TPOS_LIMIT
+ *     every few operations and converts to a WalkState long before a wrap-around),
+ *   - the mismatch / indel counters are kept as "anchor being extended" (cm, ci) and "the other one" (om, oi), so the
+ *     common path does not ask which anchor it is in.  In ST_RIGHT the extended anchor is the right one; in every
+ *     other state (c*) stands for the left counters, (o*) for the right ones.
+ * Everything else (N, clips, an indel run that breaks the anchor, the first aligned run after limbo or an intron,
+ * unknown operations) takes the general path.  tests/native/walk_fuzz.cc holds it equal to walk_op. */
+struct LeanState {
+    uint32_t tpos, a0, i0, i1, a1; /* relative to the record's pos */
+    uint32_t cm, ci, om, oi, cur, n_emitted;
+    int state;
+    IPX_HD void init() {
+        tpos = a0 = i0 = i1 = a1 = 0u;
+        cm = ci = om = oi = cur = n_emitted = 0u;
+        state = ST_LIMBO;
+    }
+    /* the equivalent WalkState, to continue with walk_op_flat */
+    IPX_HD void widen(int64_t pos, WalkState &w) const {
+        w.tpos = pos + (int64_t)tpos;
+        /* registers the automaton has not set yet are never read before it sets them */
+        w.a0 = pos + (int64_t)a0; w.i0 = pos + (int64_t)i0; w.i1 = pos + (int64_t)i1; w.a1 = pos + (int64_t)a1;
+        const bool right = state == ST_RIGHT;
+        w.lmm = right ? om : cm; w.lind = right ? oi : ci;
+        w.rmm = right ? cm : om; w.rind = right ? ci : oi;
+        w.cur = cur;
+        w.n_emitted = n_emitted;
+        w.state = state;
+    }
+};
+static const uint32_t LEAN_TPOS_LIMIT = 0xB0000000u; /* + four operations of < 2^28 each stays below 2^32 */
+
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class Emit>
+IPX_HD void lean_emit(LeanState &w, int64_t pos, Emit &emit) {
+    Candidate c;
+    c.anchor_start = pos + (int64_t)w.a0;
+    c.intron_start = pos + (int64_t)w.i0;
+    c.intron_end = pos + (int64_t)w.i1;
+    c.anchor_end = pos + (int64_t)w.a1;
+    c.left_bad = w.om + w.oi; /* only called in ST_RIGHT */
+    c.right_bad = w.cm + w.ci;
+    c.ordinal = w.n_emitted++;
+    emit(c);
+}
+
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+/* `bad` receives 0x100 | op of the first operation the reference rejects; the caller may test it as rarely as it likes
+ * (what is emitted after such an operation is moot: the run fails with the reference's error) */
+template <class Emit>
+IPX_HD void lean_op(LeanState &w, int64_t pos, uint32_t word, uint32_t max_indel, Emit &emit, uint32_t &bad) {
+    const uint32_t op = word & 15u;
+    const uint32_t len = word >> 4;
+    const bool is_al = ((0x181u >> op) & 1u) != 0u;
+    const bool is_di = ((0x006u >> op) & 1u) != 0u;
+    const bool in_anchor = (w.state & 1) != 0; /* ST_LEFT or ST_RIGHT */
+    const uint32_t ncur = is_di ? w.cur + len : 0u;
+    /* the common path, written as selects on `fast` so that it shares no register moves with the branch below */
+    const bool fast = (is_al && in_anchor) || (is_di && ncur <= max_indel);
+    const uint32_t flen = fast ? len : 0u;
+    w.ci += (is_di && in_anchor) ? flen : 0u;
+    w.cm += (op == OP_X) ? flen : 0u;
+    w.tpos += (op != OP_I) ? flen : 0u;
+    w.a1 = (fast && is_al) ? w.tpos : w.a1;
+    w.cur = fast ? ncur : w.cur;
+    if (fast) return;
+    const bool was_right = w.state == ST_RIGHT;
+    if (is_al) {
+        if (w.state == ST_LIMBO) {
+            w.a0 = w.tpos;
+            w.cm = 0u; w.om = 0u; /* the indel counters are deliberately not reset */
+            w.state = ST_LEFT;
+        } else { /* ST_INTRON: the right anchor starts; it becomes the one being extended */
+            w.i1 = w.tpos;
+            uint32_t x = w.cm; w.cm = w.om; w.om = x;
+            x = w.ci; w.ci = w.oi; w.oi = x;
+            w.state = ST_RIGHT;
+        }
+        w.tpos += len;
+        w.a1 = w.tpos;
+        w.cm += (op == OP_X) ? len : 0u;
+        w.cur = 0u;
+    } else if (op == OP_N) {
+        if (was_right) {
+            lean_emit(w, pos, emit);
+            w.a0 = w.i1; /* the right anchor is the next junction's left anchor: its counters stay in (c*) */
+            w.om = 0u; w.oi = 0u;
+        }
+        if (in_anchor) {
+            w.i0 = w.tpos;
+            w.i1 = w.tpos + len;
+            w.state = ST_INTRON;
+        }
+        w.cur = 0u;
+        w.tpos += len;
+    } else if (is_di || op == OP_S || op == OP_H) {
+        /* an indel run longer than max_indel, or a clip: the anchor ends here */
+        w.ci += (is_di && in_anchor) ? len : 0u; /* counted before the break test, as in the reference */
+        w.cur = is_di ? ncur : w.cur;            /* a clip leaves the run length alone */
+        if (was_right) {
+            lean_emit(w, pos, emit);
+            uint32_t x = w.cm; w.cm = w.om; w.om = x;
+            x = w.ci; w.ci = w.oi; w.oi = x;
+        }
+        w.state = ST_LIMBO;
+        w.tpos += (op == OP_D) ? len : 0u;
+    } else if (!bad) {
+        bad = 0x100u | op;
+    }
+}
+
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class Emit>
+IPX_HD void lean_finish(LeanState &w, int64_t pos, Emit &emit) {
+    if (w.state == ST_RIGHT) lean_emit(w, pos, emit);
+}
+
 }  // namespace ipx
 #endif

@@ -8,10 +8,17 @@ to_torch = {np.int32: torch.int32, np.uint16: torch.uint16, np.uint8: torch.uint
 host = syn.columns(lambda shape, dtype: torch.empty(shape, dtype=to_torch[dtype], pin_memory=True))
 names = syn.names; syn.close()
 eng = _native.Engine(device=0); eng.set_targets(names)
+compact = _native.Engine.compact_columns({k: v.numpy() for k, v in host.items()},
+                                         alloc=lambda shape, dtype: torch.empty(shape, dtype=to_torch[dtype], pin_memory=True))
+use_compact = os.environ.get("PLAIN") is None
 for it in range(4):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     eng.clear(); t1 = time.perf_counter()
-    eng.push(host); t2 = time.perf_counter()
+    if use_compact:
+        eng.push_compact(compact)
+    else:
+        eng.push(host)
+    t2 = time.perf_counter()
     torch.cuda.synchronize(); t3 = time.perf_counter()
     import ctypes as C
     tp = C.POINTER(_native.TableStruct)()
