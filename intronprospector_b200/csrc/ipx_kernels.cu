@@ -271,31 +271,63 @@ __global__ void __launch_bounds__(256) k_long_keys(const uint32_t *cigar_off, ui
     if (i % EX_TILE == 0) tile_info[i / EX_TILE] = TileInfo{0u, c0, 0u, 0u};
 }
 
-/* the rest of a record whose relative positions outgrew 32 bits (a CIGAR spanning > 2.9 Gb: malformed input, kept exact) */
-__device__ __forceinline__ uint32_t walk_wide_rest(const LeanState &lw, int64_t pos, const uint32_t *cig, uint32_t k, uint32_t n,
-                                                uint32_t max_indel, EventSink &sink) {
+/* K1 sink of the long-read kernel: the walk keeps only the record index; what an event needs of the record (strand,
+ * category, region of its tile) is fetched when a candidate comes up -- a few times per thousand operations -- instead
+ * of living in registers through the walk.  Candidates arrive relative to the record's position. */
+struct LazySink {
+    const BatchView &b;
+    const Tables &t;
+    const ExtractParams &p;
+    Event *out;
+    TileInfo *tile_info;
+    uint64_t r;
+    uint32_t n_events;
+    __device__ __forceinline__ EventSink open() const {
+        const uint64_t tile = r / EX_TILE;
+        Event *region = out + tile_event_base(__ldg(&b.cigar_off[tile * EX_TILE]));
+        /* the tile's event count in tile_info doubles as the fill pointer of its region */
+        return make_sink(t, p, region, &tile_info[tile].count, __ldg(&b.tid[r]), __ldg(&b.pos[r]), b.seq_base + r, __ldg(&b.flag[r]),
+                         __ldg(&b.nh[r]), __ldg(&b.xs[r]));
+    }
+    __device__ __forceinline__ void operator()(const Candidate &rel) {
+        EventSink sink = open();
+        Candidate c = rel;
+        c.anchor_start += sink.pos; c.intron_start += sink.pos; c.intron_end += sink.pos; c.anchor_end += sink.pos;
+        sink(c);
+        n_events += sink.n_events;
+    }
+};
+
+/* the rest of a record whose relative positions outgrew 32 bits (a CIGAR spanning > 1.8 Gb: malformed input, kept exact) */
+__device__ __forceinline__ uint32_t walk_wide_rest(const LeanState &lw, const uint32_t *cig, uint32_t k, uint32_t n, uint32_t max_indel,
+                                                   const LazySink &lazy, uint32_t *n_events) {
+    EventSink sink = lazy.open();
     WalkState w;
-    lw.widen(pos, w);
+    lw.widen(sink.pos, w);
     uint32_t bad = 0u;
     for (; k < n && !bad; ++k) bad = walk_op_flat(w, __ldg(&cig[k]), max_indel, sink);
     if (!bad) walk_finish(w, sink);
+    *n_events = sink.n_events;
     return bad;
 }
 
-__device__ __forceinline__ uint4 load_cigar_group(const uint32_t *cigar, uint64_t group, uint64_t n_words) {
-    if (group * 4 + 4 <= n_words) return __ldg(reinterpret_cast<const uint4 *>(cigar) + group);
-    uint4 v = make_uint4(0u, 0u, 0u, 0u); /* the last, partial group of the buffer */
-    if (group * 4 + 0 < n_words) v.x = __ldg(&cigar[group * 4 + 0]);
-    if (group * 4 + 1 < n_words) v.y = __ldg(&cigar[group * 4 + 1]);
-    if (group * 4 + 2 < n_words) v.z = __ldg(&cigar[group * 4 + 2]);
+struct Words8 {
+    uint4 lo, hi;
+};
+__device__ __forceinline__ Words8 load_words8(const uint32_t *cigar, uint32_t k) { /* k a multiple of 8, k + 8 within the buffer */
+    const uint4 *src = reinterpret_cast<const uint4 *>(cigar + k);
+    Words8 v;
+    v.lo = __ldg(src);
+    v.hi = __ldg(src + 1);
     return v;
 }
 
-__global__ void __launch_bounds__(256) k_extract_sorted(BatchView b, uint64_t n_words, ExtractParams p, Tables t, Event *out,
+__global__ void __launch_bounds__(256, 4) k_extract_sorted(BatchView b, uint64_t n_words, ExtractParams p, Tables t, Event *out,
                                                         TileInfo *tile_info, const uint32_t *order,
                                                         unsigned long long *next_chunk) {
     const int lane = threadIdx.x & 31;
     unsigned long long live_words = 0ull, events = 0ull;
+    const uint32_t max_indel = p.max_anchor_indel_size;
     for (;;) {
         unsigned long long chunk = 0ull;
         if (lane == 0) chunk = atomicAdd(next_chunk, 1ull);
@@ -304,51 +336,57 @@ __global__ void __launch_bounds__(256) k_extract_sorted(BatchView b, uint64_t n_
         const uint64_t i = chunk * 32ull + (unsigned)lane;
         if (i >= b.n) continue;
         const uint64_t r = __ldg(&order[i]);
-        const uint32_t c0 = __ldg(&b.cigar_off[r]), c1 = __ldg(&b.cigar_off[r + 1]), n_cigar = c1 - c0;
-        const int32_t tid = __ldg(&b.tid[r]);
-        const uint32_t flag = __ldg(&b.flag[r]);
-        if (!record_is_live(n_cigar, tid, flag)) continue;
-        live_words += n_cigar;
-        const int64_t pos = __ldg(&b.pos[r]);
-        const uint64_t tile = r / EX_TILE;
-        Event *region = out + tile_event_base(__ldg(&b.cigar_off[tile * EX_TILE]));
-        EventSink sink = make_sink(t, p, region, &tile_info[tile].count, tid, pos, b.seq_base + r, flag, __ldg(&b.nh[r]), __ldg(&b.xs[r]));
+        const uint32_t c0 = __ldg(&b.cigar_off[r]), c1 = __ldg(&b.cigar_off[r + 1]);
+        if (!record_is_live(c1 - c0, __ldg(&b.tid[r]), __ldg(&b.flag[r]))) continue;
+        live_words += c1 - c0;
+        LazySink sink{b, t, p, out, tile_info, r, 0u};
         LeanState w;
         w.init();
         uint32_t bad = 0u;
-        uint32_t wide_from = 0xFFFFFFFFu;
-        const uint32_t max_indel = p.max_anchor_indel_size;
-        const uint32_t g_first = c0 >> 2, g_last = (c1 - 1u) >> 2; /* n_cigar >= 2 */
-        uint4 cur = load_cigar_group(b.cigar, g_first, n_words);
-        for (uint32_t g = g_first; g <= g_last; ++g) {
-            uint4 nxt = cur;
-            if (g < g_last) nxt = load_cigar_group(b.cigar, g + 1u, n_words);
-            if (w.tpos >= LEAN_TPOS_LIMIT || bad) {
-                wide_from = g * 4u < c0 ? 0u : g * 4u - c0;
-                break;
+        bool wide = false;
+        /* the record's words [c0, c1) as: a few up to the first 32-byte boundary, whole groups of 8, a few more */
+        const uint32_t head_end = min(c1, (c0 + 7u) & ~7u);
+        const uint32_t body_end = head_end + ((c1 - head_end) & ~7u);
+        uint32_t k = c0;
+        Words8 cur;
+        if (head_end < body_end) cur = load_words8(b.cigar, head_end);
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+            const uint32_t stop = part == 0 ? head_end : c1;
+            if (part == 1 && w.tpos >= LEAN_TPOS_LIMIT) wide = true;
+#pragma unroll 1
+            for (; k < stop && !wide && !bad; ++k) lean_op(w, 0, __ldg(&b.cigar[k]), max_indel, sink, bad);
+            if (part == 1) break;
+            for (; k < body_end; k += 8u) {
+                Words8 nxt = cur;
+                if (k + 8u < body_end) nxt = load_words8(b.cigar, k + 8u);
+                if (w.tpos >= LEAN_TPOS_LIMIT || bad) {
+                    wide = true;
+                    break;
+                }
+                lean_op(w, 0, cur.lo.x, max_indel, sink, bad);
+                lean_op(w, 0, cur.lo.y, max_indel, sink, bad);
+                lean_op(w, 0, cur.lo.z, max_indel, sink, bad);
+                lean_op(w, 0, cur.lo.w, max_indel, sink, bad);
+                lean_op(w, 0, cur.hi.x, max_indel, sink, bad);
+                lean_op(w, 0, cur.hi.y, max_indel, sink, bad);
+                lean_op(w, 0, cur.hi.z, max_indel, sink, bad);
+                lean_op(w, 0, cur.hi.w, max_indel, sink, bad);
+                cur = nxt;
             }
-            if (g != g_first && g != g_last) { /* all four words belong to the record */
-                lean_op(w, pos, cur.x, max_indel, sink, bad);
-                lean_op(w, pos, cur.y, max_indel, sink, bad);
-                lean_op(w, pos, cur.z, max_indel, sink, bad);
-                lean_op(w, pos, cur.w, max_indel, sink, bad);
-            } else {
-                const uint32_t k0 = g * 4u - c0; /* index of cur.x in the record; wraps below zero in the first group */
-                if (k0 + 0u < n_cigar && !bad) lean_op(w, pos, cur.x, max_indel, sink, bad);
-                if (k0 + 1u < n_cigar && !bad) lean_op(w, pos, cur.y, max_indel, sink, bad);
-                if (k0 + 2u < n_cigar && !bad) lean_op(w, pos, cur.z, max_indel, sink, bad);
-                if (k0 + 3u < n_cigar && !bad) lean_op(w, pos, cur.w, max_indel, sink, bad);
-            }
-            cur = nxt;
         }
+        uint32_t n_events = sink.n_events;
         if (bad) { /* reported below */
-        } else if (wide_from != 0xFFFFFFFFu) {
-            bad = walk_wide_rest(w, pos, b.cigar + c0, wide_from, n_cigar, max_indel, sink);
+        } else if (wide) {
+            uint32_t more = 0u;
+            bad = walk_wide_rest(w, b.cigar + c0, k - c0, c1 - c0, max_indel, sink, &more);
+            n_events += more;
         } else {
-            lean_finish(w, pos, sink);
+            lean_finish(w, 0, sink);
+            n_events = sink.n_events;
         }
         if (bad) atomicMin(t.err_sv, make_err_cigar(b.seq_base + r, bad & 15u)); /* the reference throws here */
-        events += sink.n_events;
+        events += n_events;
     }
     live_words = warp_sum(live_words);
     events = warp_sum(events);

@@ -247,7 +247,7 @@ IPX_HD void walk_finish(WalkState &w, Emit &emit) {
  * In a long read nearly every operation is an aligned run or a short indel inside an anchor, which changes no state:
  * those take a path of a dozen instructions.  What makes it short:
  *   - positions are kept relative to the record's start (32 bits; the caller checks `tpos` against LEAN_TPOS_LIMIT
- *     every few operations and converts to a WalkState long before a wrap-around),
+ *     every eighth operation and converts to a WalkState long before a wrap-around),
  *   - the mismatch / indel counters are kept as "anchor being extended" (cm, ci) and "the other one" (om, oi), so the
  *     common path does not ask which anchor it is in.  In ST_RIGHT the extended anchor is the right one; in every
  *     other state (c*) stands for the left counters, (o*) for the right ones.
@@ -275,7 +275,9 @@ struct LeanState {
         w.state = state;
     }
 };
-static const uint32_t LEAN_TPOS_LIMIT = 0xB0000000u; /* + four operations of < 2^28 each stays below 2^32 */
+/* tested before every operation whose index in the CIGAR buffer is a multiple of 8: from below the limit, the up to
+ * 8 operations of < 2^28 each until the next test stay below 2^32 (a record's first test comes after at most 7) */
+static const uint32_t LEAN_TPOS_LIMIT = 0x70000000u;
 
 #if defined(__CUDACC__)
 #pragma nv_exec_check_disable
@@ -302,16 +304,17 @@ template <class Emit>
 IPX_HD void lean_op(LeanState &w, int64_t pos, uint32_t word, uint32_t max_indel, Emit &emit, uint32_t &bad) {
     const uint32_t op = word & 15u;
     const uint32_t len = word >> 4;
-    const bool is_al = ((0x181u >> op) & 1u) != 0u;
-    const bool is_di = ((0x006u >> op) & 1u) != 0u;
+    const uint32_t bit = 1u << op; /* one shift, then every class test is one AND */
+    const bool is_al = (bit & 0x181u) != 0u; /* M = X */
+    const bool is_di = (bit & 0x006u) != 0u; /* I D */
     const bool in_anchor = (w.state & 1) != 0; /* ST_LEFT or ST_RIGHT */
     const uint32_t ncur = is_di ? w.cur + len : 0u;
     /* the common path, written as selects on `fast` so that it shares no register moves with the branch below */
-    const bool fast = (is_al && in_anchor) || (is_di && ncur <= max_indel);
+    const bool fast = is_al ? in_anchor : (is_di && ncur <= max_indel);
     const uint32_t flen = fast ? len : 0u;
     w.ci += (is_di && in_anchor) ? flen : 0u;
-    w.cm += (op == OP_X) ? flen : 0u;
-    w.tpos += (op != OP_I) ? flen : 0u;
+    w.cm += (bit & 0x100u) ? flen : 0u; /* X */
+    w.tpos += (bit & 0x002u) ? 0u : flen; /* everything on this path but I advances the reference */
     w.a1 = (fast && is_al) ? w.tpos : w.a1;
     w.cur = fast ? ncur : w.cur;
     if (fast) return;

@@ -50,20 +50,20 @@ int main(int argc, char **argv) {
         if (!bad_a) walk_finish(wa, a);
         for (uint32_t k = 0; k < n_ops && !bad_b; ++k) bad_b = walk_op_flat(wb, cig[k], max_indel, b);
         if (!bad_b) walk_finish(wb, b);
-        /* the long-read walker as the kernel drives it: lean_op, the position limit tested every fourth operation
-         * (counted from an arbitrary phase, like a record that starts anywhere in a 16-byte group), then the rest of
+        /* the long-read walker as the kernel drives it: lean_op, the position limit tested every eighth operation
+         * (counted from an arbitrary phase, like a record that starts anywhere in a 32-byte group), then the rest of
          * the record on a widened state; every few cases with a tiny limit so the hand-over happens in every state */
         Collect c;
         uint32_t bad_c = 0;
         {
             const uint32_t limit = (t % 5 == 0) ? rnd() % 3000 : LEAN_TPOS_LIMIT;
-            const uint32_t phase = rnd() & 3u;
+            const uint32_t phase = rnd() & 7u;
             LeanState lw;
             lw.init();
             uint32_t k = 0;
             bool wide = false;
             for (; k < n_ops && !bad_c; ++k) {
-                if (((k + phase) & 3u) == 0u && lw.tpos >= limit) { wide = true; break; }
+                if (((k + phase) & 7u) == 0u && lw.tpos >= limit) { wide = true; break; }
                 lean_op(lw, pos, cig[k], max_indel, c, bad_c);
             }
             if (wide) {

@@ -104,6 +104,70 @@ def test_long_reads(built, indel):
     assert selftest.compare_tables(got, want) == []
 
 
+def _hand_made_long_batch(extra=()):
+    """A batch in the long-read regime (more than 8 operations per record on average) built from random operation
+    soup: every state transition, clips in the middle, dead and one-operation records, records of every length
+    modulo the kernel's 8-word groups."""
+    rng = np.random.default_rng(77)
+    ops = np.array([0, 0, 7, 7, 8, 1, 2, 3, 3, 4, 5], np.uint32)  # M = X I D N S H
+    recs = []
+    pos = 1000
+    for i in range(4000):
+        n = int(rng.integers(0, 3)) if i % 50 == 0 else int(rng.integers(2, 90))
+        if i % 400 == 7:
+            n = int(rng.integers(1500, 4000))
+        op = ops[rng.integers(0, len(ops), n)]
+        ln = np.where(rng.random(n) < 0.3, rng.integers(1, 4, n), rng.integers(1, 120, n)).astype(np.uint32)
+        ln = np.where(op == 3, rng.integers(60, 3000, n), ln).astype(np.uint32)
+        ln[rng.random(n) < 0.01] = 0
+        flag = 0x400 if i % 97 == 0 else (0x100 if i % 89 == 0 else (16 if i % 2 else 0))
+        recs.append((0 if i % 211 else -1, pos, flag, ((ln << 4) | op).tolist()))
+        pos += int(rng.integers(0, 40))
+    recs.extend(extra)
+    cols = {"tid": np.array([r[0] for r in recs], np.int32), "pos": np.array([r[1] for r in recs], np.int32),
+            "flag": np.array([r[2] for r in recs], np.uint16), "nh_class": (np.arange(len(recs)) % 3).astype(np.uint8),
+            "xs": np.where(np.arange(len(recs)) % 4 == 0, ord("+"), np.where(np.arange(len(recs)) % 4 == 1, ord("-"), 0)).astype(np.uint8),
+            "cigar_off": np.cumsum([0] + [len(r[3]) for r in recs]).astype(np.uint32),
+            "cigar": np.array([x for r in recs for x in r[3]], np.uint32)}
+    assert cols["cigar"].shape[0] > 8 * len(recs)
+    return cols
+
+
+@pytest.mark.parametrize("indel", [0, 5, 36])
+def test_long_regime_operation_soup(built, indel):
+    cols = _hand_made_long_batch()
+    for n_batches in (1, 3):
+        got, want = both(["c1"], cols, n_batches=n_batches, max_anchor_indel_size=indel, min_anchor_length=3)
+        assert want.n > 500
+        assert selftest.compare_tables(got, want) == []
+
+
+def test_long_regime_positions_beyond_32_bit_offsets(built):
+    """A CIGAR whose reference span outgrows the long-read walker's 32-bit relative positions: the walk is handed to
+    the 64-bit automaton mid-record and the junction after the hand-over is still found where the oracle finds it."""
+    def w(length, op):
+        return (length << 4) | "MIDNSHP=XB".index(op)
+    big = (1 << 28) - 1
+    giant = [w(30, "M")] + [w(big, "D")] * 7 + [w(5000, "M"), w(40, "M"), w(300, "N"), w(45, "M"), w(2, "I"), w(20, "M"),
+                                                  w(900, "N"), w(33, "M")] + [w(3, "M"), w(1, "X")] * 6
+    cols = _hand_made_long_batch(extra=[(0, 100, 0, giant), (0, 120, 16, giant[:-3])])
+    got, want = both(["c1"], cols, max_anchor_indel_size=36)
+    assert int(np.max(want.intron_start)) > 7 * big
+    assert selftest.compare_tables(got, want) == []
+
+
+def test_long_regime_unknown_cigar_op_is_reported(built):
+    def w(length, op):
+        return (length << 4) | op
+    bad_late = [w(10, 0)] * 40 + [w(3, 9)] + [w(10, 0)] * 5   # 'B' deep inside a whole group of 8
+    bad_early = [w(10, 0), w(4, 6), w(10, 0)] + [w(7, 0)] * 30  # 'P' among the record's first words
+    cols = _hand_made_long_batch(extra=[(0, 500, 0, bad_late), (0, 600, 0, bad_early)])
+    got, want = both(["c1"], cols)
+    assert got.status == want.status == -3
+    assert got.error_text == want.error_text == "Unknown cigar operation 'B'"
+    assert got.first_error_seq == want.first_error_seq == 4000
+
+
 def test_empty_and_ragged_batches(built):
     names = ["c1", "c2"]
     empty = {k: np.zeros(0, dt) for k, dt in (("tid", np.int32), ("pos", np.int32), ("flag", np.uint16), ("nh_class", np.uint8),
