@@ -250,6 +250,30 @@ int ipx_partial_export(ipx_handle *h, void *dev_junction_rows, void *dev_hist_ro
 int ipx_partial_import(ipx_handle *h, const void *dev_junction_rows, uint64_t n_junction_rows,
                        const void *dev_hist_rows, uint64_t n_hist_rows);
 
+/* The same exchange over peer memory (NVLink / NVSwitch), without send buffers, size exchange or data-path collective:
+ * every rank owns a mailbox with one slot per source rank, and the exporting kernels store each row straight into its
+ * owner's slot.  Set-up, once:
+ *  ipx_mailbox_create        allocate this rank's mailbox: `world` sources x 2 (consecutive exchanges alternate),
+ *                            each with room for the given numbers of junction and offset rows
+ *  ipx_mailbox_ipc_handle    64 bytes (cudaIpcMemHandle_t) for the other processes;  ipx_mailbox_ptr: the device
+ *                            pointer itself, for handles that live in the same process
+ *  ipx_mailbox_connect       the mailboxes of all ranks, in rank order: ipc != 0: `peers` = world x 64-byte IPC
+ *                            handles (own entry ignored); ipc == 0: `peers` = world device pointers
+ * Per exchange, after the local batches are pushed (and ipx_count_deferred with the canon filter):
+ *  ipx_partial_export_mail   enqueue the export into the owners' slots (asynchronous, no host round trip) and empty
+ *                            the local table
+ *  -- the caller makes every rank's export complete before any import starts: any collective or barrier ordered
+ *     after ipx_stream(h) on every rank and before it on the importing side (a one-element all-reduce will do) --
+ *  ipx_partial_import_mail   fold all the slots of this rank's mailbox (row counts come from the slots' headers);
+ *                            then ipx_flush.  A slot that was too small is reported by ipx_flush as IPX_ERR_CAPACITY. */
+int ipx_mailbox_create(ipx_handle *h, int32_t world, int32_t rank, uint64_t junction_rows_per_source,
+                       uint64_t hist_rows_per_source);
+int ipx_mailbox_ipc_handle(ipx_handle *h, void *handle_64_bytes);
+void *ipx_mailbox_ptr(ipx_handle *h);
+int ipx_mailbox_connect(ipx_handle *h, int32_t ipc, const void *peers);
+int ipx_partial_export_mail(ipx_handle *h, const int32_t *split_tid, const uint32_t *split_start);
+int ipx_partial_import_mail(ipx_handle *h);
+
 /* Multi-GPU with the canon filter.  Which event creates a junction (add_junction, junctions_extractor.cc:488-506) depends
  * on every earlier read of the whole stream, so with ipx_params.deferred_counting the ranks first agree on it:
  *  ipx_thresholds_rows    settle this rank's local creation thresholds; number and size of the rows to exchange

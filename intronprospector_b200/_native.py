@@ -148,6 +148,8 @@ ABI_SYMBOLS = [
     "ipx_partial_export", "ipx_partial_import", "ipx_format", "ipx_format_tsv_header", "ipx_text_free",
     "ipx_get_timings", "ipx_reset_timings", "ipx_stream", "ipx_thresholds_rows", "ipx_thresholds_export",
     "ipx_thresholds_import", "ipx_count_deferred", "ipx_table_set_ijunc", "ipx_push_batch_compact",
+    "ipx_mailbox_create", "ipx_mailbox_ipc_handle", "ipx_mailbox_ptr", "ipx_mailbox_connect", "ipx_partial_export_mail",
+    "ipx_partial_import_mail",
 ]
 IO_SYMBOLS = [
     "ipxio_last_error", "ipxio_open", "ipxio_close", "ipxio_n_targets", "ipxio_target_name", "ipxio_read_batch",
@@ -197,6 +199,13 @@ def _bind(lib):
     lib.ipx_count_deferred.argtypes = [C.c_void_p]
     lib.ipx_table_set_ijunc.argtypes = [C.POINTER(TableStruct), C.c_void_p]
     lib.ipx_push_batch_compact.argtypes = [C.c_void_p, C.POINTER(BatchCompact)]
+    lib.ipx_mailbox_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64]
+    lib.ipx_mailbox_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]
+    lib.ipx_mailbox_ptr.argtypes = [C.c_void_p]
+    lib.ipx_mailbox_ptr.restype = C.c_void_p
+    lib.ipx_mailbox_connect.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.ipx_partial_export_mail.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]
+    lib.ipx_partial_import_mail.argtypes = [C.c_void_p]
 
 
 def load_library(path=None):
@@ -516,6 +525,41 @@ class Engine:
 
     def partial_import(self, dev_junction_rows, n_junction_rows, dev_hist_rows, n_hist_rows):
         self._check(self.lib.ipx_partial_import(self.h, dev_junction_rows, n_junction_rows, dev_hist_rows, n_hist_rows))
+
+    # exchange over peer memory (ipx.h: ipx_mailbox_*, ipx_partial_*_mail)
+    def mailbox_create(self, world, rank, junction_rows_per_source, hist_rows_per_source):
+        self._check(self.lib.ipx_mailbox_create(self.h, world, rank, junction_rows_per_source, hist_rows_per_source))
+        self.mailbox_world = world
+
+    def mailbox_ipc_handle(self):
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.ipx_mailbox_ipc_handle(self.h, buf))
+        return buf.raw
+
+    def mailbox_ptr(self):
+        return int(self.lib.ipx_mailbox_ptr(self.h) or 0)
+
+    def mailbox_connect_ipc(self, handles):
+        """handles: the 64-byte IPC handles of all ranks in rank order (this rank's own entry is ignored)"""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.mailbox_world
+        self._check(self.lib.ipx_mailbox_connect(self.h, 1, C.c_char_p(blob)))
+        self.mailbox_connected = True
+
+    def mailbox_connect_ptrs(self, ptrs):
+        """ptrs: the mailbox device pointers of all ranks in rank order (handles of the same process)"""
+        arr = (C.c_void_p * self.mailbox_world)(*ptrs)
+        self._check(self.lib.ipx_mailbox_connect(self.h, 0, arr))
+        self.mailbox_connected = True
+
+    def partial_export_mail(self, split_tid, split_start):
+        n = max(1, len(split_tid))
+        st = (C.c_int32 * n)(*split_tid)
+        ss = (C.c_uint32 * n)(*split_start)
+        self._check(self.lib.ipx_partial_export_mail(self.h, st, ss))
+
+    def partial_import_mail(self):
+        self._check(self.lib.ipx_partial_import_mail(self.h))
 
     def thresholds_rows(self):
         n, b = C.c_uint64(), C.c_uint32()

@@ -184,6 +184,11 @@ struct ipx_handle {
     std::vector<Deferred> deferred;
     /* key-range export in flight (ipx_partial_sizes -> ipx_partial_export) */
     Splitters export_split{};
+    /* exchange over peer memory */
+    Mailboxes mail = {};
+    char *mail_own = nullptr;
+    bool mail_opened[MAX_PARTS] = {}; /* peers mapped with cudaIpcOpenMemHandle */
+    bool mail_connected = false;
     unsigned long long *d_export = nullptr; /* [2 * MAX_PARTS] counts, then cursors */
     unsigned long long export_counts[2 * MAX_PARTS + 4] = {}; /* + keys, log entries, overflow flag */
     unsigned long long export_cursors[2 * MAX_PARTS] = {};
@@ -513,6 +518,8 @@ extern "C" int ipx_create(const ipx_params *params, ipx_handle **out) {
     return IPX_OK;
 }
 
+static void mailbox_release(ipx_handle *h);
+
 extern "C" void ipx_destroy(ipx_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
@@ -525,6 +532,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();
     h->s_off.release(); h->s_cig.release(); h->s_nops.release(); h->s_runs.release(); h->s_tmp.release(); h->ev_buf.release(); h->tile_cnt.release(); h->long_buf.release(); h->slot_jrow.release(); h->slot_of.release();
     finalize_release(h->fw);
+    mailbox_release(h);
     cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -822,6 +830,7 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     if (overflow) {
         delete ht;
         if (overflow == 3) return fail(h, IPX_ERR_CAPACITY, "intron start beyond 2^31 cannot be keyed");
+        if (overflow == 4) return fail(h, IPX_ERR_CAPACITY, "a mailbox slot was too small for the rows sent to it (ipx_mailbox_create)");
         return fail(h, IPX_ERR_CAPACITY, "%s is full; raise ipx_params.%s", overflow == 1 ? "junction hash table" : "read-offset log",
                     overflow == 1 ? "table_capacity" : "hist_capacity");
     }
@@ -1093,6 +1102,145 @@ extern "C" int ipx_partial_import(ipx_handle *h, const void *dev_junction_rows, 
         Span s(h, &h->tm_finalize, 2);
         launch_import_rows(h->tab, (const JunctionRow *)dev_junction_rows, n_junction_rows, (const HistRow *)dev_hist_rows,
                            n_hist_rows, (uint32_t *)h->slot_of.p, h->stream);
+    }
+    CU(h, cudaGetLastError());
+    h->dirty = true;
+    return IPX_OK;
+}
+
+/* ------------------------------------------------------------------ multi-GPU exchange over peer memory */
+static int splitters_in_key_order(ipx_handle *h, int32_t n_parts, const int32_t *split_tid, const uint32_t *split_start, Splitters &sp) {
+    std::vector<uint32_t> order(h->targets.size()), rank(h->targets.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h->targets[a] < h->targets[b]; });
+    for (size_t i = 0; i < order.size(); i++) rank[order[i]] = (uint32_t)i;
+    sp.n_parts = n_parts;
+    for (int32_t p = 0; p + 1 < n_parts; p++) {
+        if (split_tid[p] < 0 || (size_t)split_tid[p] >= rank.size()) return fail(h, IPX_ERR_ARG, "splitter %d names no target", p);
+        sp.rank[p] = rank[split_tid[p]];
+        sp.start[p] = split_start[p];
+        if (p > 0 && (sp.rank[p] < sp.rank[p - 1] || (sp.rank[p] == sp.rank[p - 1] && sp.start[p] < sp.start[p - 1])))
+            return fail(h, IPX_ERR_ARG, "splitters are not in key order");
+    }
+    return IPX_OK;
+}
+
+static void mailbox_release(ipx_handle *h) {
+    for (int r = 0; r < MAX_PARTS; r++) {
+        if (h->mail_opened[r]) cudaIpcCloseMemHandle(h->mail.base[r]);
+        h->mail_opened[r] = false;
+        h->mail.base[r] = nullptr;
+    }
+    if (h->mail_own) cudaFree(h->mail_own);
+    h->mail_own = nullptr;
+    h->mail_connected = false;
+}
+
+extern "C" int ipx_mailbox_create(ipx_handle *h, int32_t world, int32_t rank, uint64_t junction_rows, uint64_t hist_rows) {
+    if (!h || world < 1 || world > MAX_PARTS || rank < 0 || rank >= world || !junction_rows || !hist_rows) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    mailbox_release(h);
+    Mailboxes &m = h->mail;
+    m.world = world;
+    m.me = rank;
+    m.parity = 0;
+    m.cap_j = junction_rows;
+    m.cap_h = hist_rows;
+    m.hist_offset = (junction_rows * sizeof(JunctionRow) + 255) & ~(uint64_t)255;
+    m.slot_bytes = MAIL_HEADER_BYTES + m.hist_offset + ((hist_rows * sizeof(HistRow) + 255) & ~(uint64_t)255);
+    m.slot_bytes = (m.slot_bytes + 255) & ~(uint64_t)255;
+    /* a plain cudaMalloc: memory from a stream-ordered pool cannot be shared through cudaIpcGetMemHandle */
+    CU(h, cudaMalloc(&h->mail_own, 2 * (size_t)world * m.slot_bytes));
+    CU(h, cudaMemset(h->mail_own, 0, 2 * (size_t)world * m.slot_bytes));
+    m.base[rank] = h->mail_own;
+    return IPX_OK;
+}
+
+extern "C" int ipx_mailbox_ipc_handle(ipx_handle *h, void *handle_64_bytes) {
+    if (!h || !handle_64_bytes) return IPX_ERR_ARG;
+    if (!h->mail_own) return fail(h, IPX_ERR_STATE, "call ipx_mailbox_create first");
+    cudaSetDevice(h->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t ipc;
+    CU(h, cudaIpcGetMemHandle(&ipc, h->mail_own));
+    memcpy(handle_64_bytes, &ipc, sizeof(ipc));
+    return IPX_OK;
+}
+
+extern "C" void *ipx_mailbox_ptr(ipx_handle *h) { return h ? h->mail_own : nullptr; }
+
+extern "C" int ipx_mailbox_connect(ipx_handle *h, int32_t ipc, const void *peers) {
+    if (!h || !peers) return IPX_ERR_ARG;
+    if (!h->mail_own) return fail(h, IPX_ERR_STATE, "call ipx_mailbox_create first");
+    cudaSetDevice(h->device);
+    Mailboxes &m = h->mail;
+    for (int r = 0; r < m.world; r++) {
+        if (r == m.me) continue;
+        if (ipc) {
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, (const char *)peers + 64 * (size_t)r, sizeof(hd));
+            void *p = nullptr;
+            CU(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+            m.base[r] = (char *)p;
+            h->mail_opened[r] = true;
+        } else {
+            m.base[r] = (char *)((void *const *)peers)[r];
+            if (!m.base[r]) return fail(h, IPX_ERR_ARG, "mailbox pointer of rank %d is null", r);
+        }
+    }
+    h->mail_connected = true;
+    return IPX_OK;
+}
+
+extern "C" int ipx_partial_export_mail(ipx_handle *h, const int32_t *split_tid, const uint32_t *split_start) {
+    if (!h) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (!h->mail_connected) return fail(h, IPX_ERR_STATE, "call ipx_mailbox_connect first");
+    if (two_pass(h) && !h->params.deferred_counting)
+        return fail(h, IPX_ERR_STATE, "multi-GPU exchange with the canon filter needs ipx_params.deferred_counting");
+    if (!h->deferred.empty()) return fail(h, IPX_ERR_STATE, "call ipx_count_deferred before the exchange");
+    if (h->finalized) return fail(h, IPX_ERR_STATE, "the exchange works on the table before ipx_finalize_device");
+    if (h->targets.empty()) return fail(h, IPX_ERR_STATE, "ipx_set_targets must be called first");
+    const int world = h->mail.world;
+    if (world > 1 && (!split_tid || !split_start)) return IPX_ERR_ARG;
+    int rc = alloc_tables(h);
+    if (rc) return rc;
+    Splitters &sp = h->export_split;
+    rc = splitters_in_key_order(h, world, split_tid, split_start, sp);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    if (!h->d_export) CU(h, cudaMalloc(&h->d_export, (2 * MAX_PARTS + 4) * sizeof(unsigned long long)));
+    CU(h, h->slot_jrow.reserve((h->tab.cap_mask + 1) * sizeof(uint32_t), st));
+    CU(h, cudaMemsetAsync(h->d_export, 0, 2 * MAX_PARTS * sizeof(unsigned long long), st));
+    h->mail.parity ^= 1; /* the slots of the exchange before this one may still be read by a slower owner */
+    {
+        /* creation thresholds for anything still unresolved: keys that never got one are not exported */
+        Span s(h, &h->tm_motif, 1);
+        launch_resolve_T(h->tab, genome_view(h), st);
+    }
+    {
+        Span s(h, &h->tm_finalize, 4);
+        launch_mail_export(h->tab, h->d_name_rank, sp, h->mail, h->d_export, (uint32_t *)h->slot_jrow.p, h->sm_count, st);
+        /* the local table has been handed over: empty it so that the import (own share included) rebuilds it */
+        launch_clear_tables(h->tab, st);
+    }
+    CU(h, cudaGetLastError());
+    return IPX_OK;
+}
+
+extern "C" int ipx_partial_import_mail(ipx_handle *h) {
+    if (!h) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (!h->mail_connected) return fail(h, IPX_ERR_STATE, "call ipx_mailbox_connect first");
+    if (h->finalized) return fail(h, IPX_ERR_STATE, "table already finalized");
+    int rc = alloc_tables(h);
+    if (rc) return rc;
+    CU(h, h->slot_of.reserve((h->mail.cap_j + 1) * sizeof(uint32_t), h->stream));
+    {
+        Span s(h, &h->tm_finalize, 2 * (uint64_t)h->mail.world);
+        /* one source after the other: the offset rows of a source name junctions by their index among its junction rows */
+        for (int src = 0; src < h->mail.world; src++)
+            launch_mail_import(h->tab, h->mail, src, (uint32_t *)h->slot_of.p, h->sm_count, h->stream);
     }
     CU(h, cudaGetLastError());
     h->dirty = true;

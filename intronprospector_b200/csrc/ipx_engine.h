@@ -197,5 +197,18 @@ void launch_export_count(const Tables &t, const uint32_t *name_rank, const Split
 void launch_export_scatter(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t n_keys, uint64_t n_olog,
                            unsigned long long *cursors, uint32_t *slot_jrow, JunctionRow *jr, HistRow *hr, cudaStream_t st);
 
+
+/* Exchange over peer memory.  Every rank owns a mailbox of 2 (parity) x world slots, all ranks with the same layout;
+ * slot (parity, source) = [header: junction rows, offset rows (2 x u64)] [cap_j junction rows] [cap_h offset rows]. */
+static const uint64_t MAIL_HEADER_BYTES = 128;
+struct Mailboxes {
+    char *base[MAX_PARTS]; /* mailbox of every rank as mapped into this process (own included) */
+    uint64_t slot_bytes, hist_offset, cap_j, cap_h;
+    int32_t world, me, parity;
+};
+void launch_mail_export(const Tables &t, const uint32_t *name_rank, const Splitters &sp, const Mailboxes &m, unsigned long long *counts,
+                        uint32_t *slot_jrow, int sm_count, cudaStream_t st);
+void launch_mail_import(const Tables &t, const Mailboxes &m, int source, uint32_t *slot_of, int sm_count, cudaStream_t st);
+
 }  // namespace ipx
 #endif

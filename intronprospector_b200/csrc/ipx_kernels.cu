@@ -1739,6 +1739,189 @@ __global__ void k_import_hist_rows(Tables t, const HistRow *hr, uint64_t n, cons
     olog_finish(t, olog);
 }
 
+/* ---- the exchange over peer memory: export kernels that store straight into the owners' mailboxes ----
+ * Every rank owns a mailbox (ipx_engine.h: Mailboxes) with one slot per source rank; the exporter's warps decide the
+ * owner of a junction and write its rows behind a per-owner cursor directly into that owner's slot for this rank --
+ * NVLink stores for the peers, plain stores for its own share.  One pass: a slot has room for the worst case, so
+ * there is no counting pass, no size exchange and no send buffer; the row counts are published into the slot's header
+ * by a last small kernel.  The owners fold their slots after a barrier the caller provides (any collective on the
+ * streams involved: kernel completion makes the stores visible system-wide). */
+__device__ __forceinline__ char *mail_slot(const Mailboxes &m, int owner, int source) {
+    return m.base[owner] + (uint64_t)(m.parity * m.world + source) * m.slot_bytes;
+}
+__device__ __forceinline__ JunctionRow *mail_junction_rows(char *slot) { return reinterpret_cast<JunctionRow *>(slot + MAIL_HEADER_BYTES); }
+__device__ __forceinline__ HistRow *mail_hist_rows(const Mailboxes &m, char *slot) {
+    return reinterpret_cast<HistRow *>(slot + MAIL_HEADER_BYTES + m.hist_offset);
+}
+
+__global__ void __launch_bounds__(256) k_mail_slots(Tables t, const uint32_t *name_rank, Splitters sp, Mailboxes m,
+                                                    unsigned long long *counts, uint32_t *slot_jrow) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t n_keys = *t.n_keys;
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_keys; i += n_warps) {
+        const uint32_t slot = t.slot_list[i];
+        const JStat s = t.stat[slot];
+        if (s.T == EMPTY64) continue; /* never created: nothing was counted into it */
+        const unsigned long long key = t.keys[slot];
+        const int32_t tid = key_tid(t.kl, key);
+        const uint32_t i0 = key_start(t.kl, key), i1 = i0 + key_len(t.kl, key);
+        const int dest = part_of(sp, name_rank[tid], i0);
+        uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        uint32_t mine = 0;
+        if (t.dense) {
+            const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)slot * DENSE_W);
+            const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mine += hist_rows_of(v[k]);
+        }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        const uint32_t nz = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        unsigned long long jpos = 0ull, hpos = 0ull;
+        if (lane == 0) {
+            jpos = atomicAdd(&counts[dest], 1ull);
+            if (nz) hpos = atomicAdd(&counts[sp.n_parts + dest], (unsigned long long)nz);
+        }
+        jpos = __shfl_sync(0xFFFFFFFFu, jpos, 0);
+        hpos = __shfl_sync(0xFFFFFFFFu, hpos, 0);
+        /* a slot that is too small keeps counting: the owner sees counts beyond the capacity and reports it */
+        if (jpos >= m.cap_j || hpos + nz > m.cap_h) continue;
+        char *box = mail_slot(m, dest, m.me);
+        if (lane == 0) {
+            JunctionRow r;
+            r.first[0] = s.first[0]; r.first[1] = s.first[1]; r.first[2] = s.first[2];
+            r.cnt[0] = s.cnt[0]; r.cnt[1] = s.cnt[1]; r.cnt[2] = s.cnt[2];
+            r.tid = tid; r.i0 = i0; r.i1 = i1; r.a0 = s.a0; r.a1 = s.a1; r.pad = 0;
+            mail_junction_rows(box)[jpos] = r;
+            slot_jrow[slot] = (uint32_t)jpos; /* for the log entries of this junction */
+        }
+        HistRow *hr = mail_hist_rows(m, box);
+        uint64_t o = hpos + (incl - mine);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t left = v[k];
+            while (left) {
+                const uint32_t piece = left > 0xFFFFu ? 0xFFFFu : left;
+                HistRow h;
+                h.jrow = (uint32_t)jpos; h.offset = (uint16_t)(lane * 8 + k); h.cnt = (uint16_t)piece;
+                hr[o++] = h;
+                left -= piece;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mail_olog(Tables t, const uint32_t *name_rank, Splitters sp, Mailboxes m,
+                                                   unsigned long long *counts, const uint32_t *slot_jrow) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_threads = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_olog = *t.n_olog, n_round = (n_olog + 31ull) & ~31ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += n_threads) {
+        int dest = -1 - lane; /* idle lanes group with nobody */
+        unsigned long long e = OLOG_INVALID;
+        uint32_t slot = 0u;
+        if (i < n_olog) {
+            e = t.olog[i];
+            if (e != OLOG_INVALID) {
+                slot = (uint32_t)(e >> 32);
+                if (t.stat[slot].T != EMPTY64) {
+                    const unsigned long long key = t.keys[slot];
+                    dest = part_of(sp, name_rank[key_tid(t.kl, key)], key_start(t.kl, key));
+                }
+            }
+        }
+        /* one atomic per (warp, destination) */
+        const unsigned grp = __match_any_sync(0xFFFFFFFFu, dest);
+        const int leader = __ffs(grp) - 1;
+        unsigned long long base = 0ull;
+        if (dest >= 0 && lane == leader) base = atomicAdd(&counts[sp.n_parts + dest], (unsigned long long)__popc(grp));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        const uint64_t at = base + __popc(grp & ((1u << lane) - 1u));
+        if (dest >= 0 && at < m.cap_h) {
+            HistRow h;
+            h.jrow = slot_jrow[slot]; h.offset = (uint16_t)((e >> 16) & 0xFFFFull); h.cnt = (uint16_t)(e & 0xFFFFull);
+            mail_hist_rows(m, mail_slot(m, dest, m.me))[at] = h;
+        }
+    }
+}
+
+__global__ void k_mail_publish(Mailboxes m, const unsigned long long *counts) {
+    const int d = threadIdx.x;
+    if (d >= m.world) return;
+    unsigned long long *hdr = reinterpret_cast<unsigned long long *>(mail_slot(m, d, m.me));
+    hdr[0] = counts[d];
+    hdr[1] = counts[m.world + d];
+}
+
+void launch_mail_export(const Tables &t, const uint32_t *name_rank, const Splitters &sp, const Mailboxes &m, unsigned long long *counts,
+                        uint32_t *slot_jrow, int sm_count, cudaStream_t st) {
+    k_mail_slots<<<sm_count * 8, 256, 0, st>>>(t, name_rank, sp, m, counts, slot_jrow);
+    k_mail_olog<<<sm_count * 8, 256, 0, st>>>(t, name_rank, sp, m, counts, slot_jrow);
+    k_mail_publish<<<1, MAX_PARTS, 0, st>>>(m, counts);
+}
+
+/* fold the slot of one source out of this rank's own mailbox; the row counts come from the slot's header */
+__global__ void __launch_bounds__(256) k_mail_import_junctions(Tables t, Mailboxes m, int source, uint32_t *slot_of) {
+    char *box = mail_slot(m, m.me, source);
+    const unsigned long long n_sent = *reinterpret_cast<const unsigned long long *>(box);
+    if (n_sent > m.cap_j || reinterpret_cast<const unsigned long long *>(box)[1] > m.cap_h) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(t.overflow, 4u);
+        return;
+    }
+    const JunctionRow *jr = mail_junction_rows(box);
+    const uint64_t n_threads = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sent; i += n_threads) {
+        const JunctionRow r = jr[i];
+        const uint64_t key = make_key(t.kl, r.tid, r.i0, r.i1);
+        const uint64_t slot = junction_find_or_insert(t, key);
+        slot_of[i] = slot <= t.cap_mask ? (uint32_t)slot : 0xFFFFFFFFu;
+        if (slot > t.cap_mask) continue;
+        JStat *s = &t.stat[slot];
+        for (int c = 0; c < 3; ++c) {
+            if (r.first[c] != EMPTY64) atomicMin(&s->first[c], r.first[c]);
+            if (r.cnt[c]) atomicAdd(&s->cnt[c], r.cnt[c]);
+        }
+        atomicMin(&s->a0, r.a0);
+        atomicMax(&s->a1, r.a1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mail_import_hist(Tables t, Mailboxes m, int source, const uint32_t *slot_of) {
+    char *box = mail_slot(m, m.me, source);
+    const unsigned long long nj = reinterpret_cast<const unsigned long long *>(box)[0];
+    const unsigned long long n_sent = reinterpret_cast<const unsigned long long *>(box)[1];
+    if (nj > m.cap_j || n_sent > m.cap_h) return; /* reported by k_mail_import_junctions */
+    const HistRow *hr = mail_hist_rows(m, box);
+    const uint64_t n_threads = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n_sent + 31ull) & ~31ull;
+    OlogWriter olog{0ull, 0u};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += n_threads) {
+        uint32_t slot = 0xFFFFFFFFu, off = 0u, cnt = 0u;
+        if (i < n_sent) {
+            const HistRow r = hr[i];
+            if (r.jrow < nj) slot = slot_of[r.jrow];
+            off = r.offset;
+            cnt = r.cnt;
+        }
+        const bool ok = slot != 0xFFFFFFFFu && cnt != 0u;
+        const bool in_row = t.dense != nullptr && off < DENSE_W;
+        if (ok && in_row) atomicAdd(&t.dense[(uint64_t)slot * DENSE_W + off], cnt);
+        olog_append(t, olog, ok && !in_row, olog_entry(slot, off, cnt));
+    }
+    olog_finish(t, olog);
+}
+
+void launch_mail_import(const Tables &t, const Mailboxes &m, int source, uint32_t *slot_of, int sm_count, cudaStream_t st) {
+    k_mail_import_junctions<<<sm_count * 4, 256, 0, st>>>(t, m, source, slot_of);
+    k_mail_import_hist<<<sm_count * 8, 256, 0, st>>>(t, m, source, slot_of);
+}
+
 __global__ void k_export_thresholds(Tables t, ThresholdRow *rows, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -2,7 +2,12 @@
 
 The record stream is cut into contiguous, ordered shards (global stream indexes preserved through ipx_batch.seq_base).
 Every rank extracts and reduces its shard locally; partial junction rows and read-offset rows are then exchanged by
-key range with ONE all-to-all and folded by the owning rank.  With the canon filter the ranks first agree
+key range and folded by the owning rank.  Two transports:
+  mailboxes   (GPUs of one node) the exporting kernels store every row straight into its owner's memory over
+              NVLink (ipx_mailbox_*, ipx_partial_export_mail); the only collective is a one-element all-reduce that
+              orders "all exports done" before "imports start".  No send buffers, no size exchange, no host round trip.
+  all-to-all  packed rows through torch.distributed (NCCL, or gloo on CPU tensors in the tests); used when no
+              mailboxes are connected.  With the canon filter the ranks first agree
 on each junction's creating event (an all-gather of J-sized threshold rows) and count their kept events against it.
 Payloads are J-sized (MBs), so the exchange is latency-, not bandwidth-bound.
 
@@ -102,9 +107,57 @@ def all_to_all_bytes(send, send_counts, recv_counts, group=None):
     return recv[:sum(recv_counts)]
 
 
-def exchange_dist(eng, names, device, group=None):
-    """One key-range exchange over torch.distributed; returns the bytes this rank sent + received."""
+def connect_mailboxes_dist(eng, device, junction_rows_per_source, hist_rows_per_source, group=None):
+    """Create this rank's mailbox and map those of all other ranks of the node (CUDA IPC handles, all-gathered)."""
     import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    eng.mailbox_create(world, rank, junction_rows_per_source, hist_rows_per_source)
+    mine = torch.frombuffer(bytearray(eng.mailbox_ipc_handle()), dtype=torch.uint8).to(device)
+    handles = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(handles, mine, group=group)
+    eng.mailbox_connect_ipc([bytes(h.cpu().numpy().tobytes()) for h in handles])
+    eng._mail_token = torch.zeros(1, dtype=torch.int32, device=device)
+    dist.barrier(group=group)
+
+
+def connect_mailboxes_local(engines, junction_rows_per_source, hist_rows_per_source):
+    """The same for handles of one process (emulated ranks on one GPU): plain device pointers."""
+    world = len(engines)
+    for r, e in enumerate(engines):
+        e.mailbox_create(world, r, junction_rows_per_source, hist_rows_per_source)
+    ptrs = [e.mailbox_ptr() for e in engines]
+    for e in engines:
+        e.mailbox_connect_ptrs(ptrs)
+
+
+def exchange_mail_dist(eng, names, device, group=None):
+    """One key-range exchange through the mailboxes: export into the owners' memory, a one-element all-reduce as the
+    barrier between everybody's export and anybody's import, import.  Everything is enqueued; nothing waits on the host."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    split_tid, split_start = key_splitters(names, world)
+    eng.partial_export_mail(split_tid, split_start)
+    _torch_after_engine(eng, device)
+    dist.all_reduce(eng._mail_token, group=group)
+    _engine_after_torch(eng, device)
+    eng.partial_import_mail()
+
+
+def exchange_mail_local(engines, names, device):
+    split_tid, split_start = key_splitters(names, len(engines))
+    for e in engines:
+        e.partial_export_mail(split_tid, split_start)
+    torch.cuda.synchronize(device)  # stands in for the barrier: the handles have separate streams
+    for e in engines:
+        e.partial_import_mail()
+
+
+def exchange_dist(eng, names, device, group=None):
+    """One key-range exchange over torch.distributed; returns the bytes this rank sent + received (None through
+    mailboxes, where nobody counts them on the host)."""
+    import torch.distributed as dist
+    if getattr(eng, "mailbox_connected", False):
+        return exchange_mail_dist(eng, names, device, group)
     world = dist.get_world_size(group)
     (send_j, cj), (send_h, ch) = export_partials(eng, names, world, device)
     rj, rh = exchange_counts([cj, ch], device, group)
@@ -118,6 +171,8 @@ def exchange_dist(eng, names, device, group=None):
 
 def exchange_local(engines, names, device):
     """The same exchange among handles of one process (rank = position in `engines`)."""
+    if all(getattr(e, "mailbox_connected", False) for e in engines):
+        return exchange_mail_local(engines, names, device)
     world = len(engines)
     exports = [export_partials(e, names, world, device) for e in engines]
     moved = 0
