@@ -491,6 +491,12 @@ extern "C" int ipx_create(const ipx_params *params, ipx_handle **out) {
     }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("IPX_FIN_BOUNDS")) { /* tests: start the grow-only finalize bounds small, "B,L,R" */
+        unsigned long long fb = 0, fl = 0, fr = 0;
+        if (sscanf(e, "%llu,%llu,%llu", &fb, &fl, &fr) == 3 && fb && fl && fr) {
+            h->fw.first_B = fb; h->fw.first_L = fl; h->fw.first_R = fr;
+        }
+    }
     if (params->stream) {
         h->stream = (cudaStream_t)params->stream;
     } else {

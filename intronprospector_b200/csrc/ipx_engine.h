@@ -128,6 +128,7 @@ void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, con
 struct FinalizeWork {
     uint64_t B = 0, L = 0, R = 0;
     uint64_t wish_B = 0, wish_L = 0, wish_R = 0; /* what finalize_check asked for */
+    uint64_t first_B = 1ull << 16, first_L = 1ull << 16, first_R = 1ull << 20; /* bounds of the very first finalize */
     unsigned long long *sort_key = nullptr, *sort_key2 = nullptr, *hash_lo = nullptr, *total = nullptr, *hk_a = nullptr,
                        *hk_b = nullptr;
     uint32_t *slot_a = nullptr, *slot_b = nullptr, *idx_b = nullptr, *dense_nz = nullptr, *hc_a = nullptr, *hc_b = nullptr;

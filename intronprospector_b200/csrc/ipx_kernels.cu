@@ -24,6 +24,7 @@
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
@@ -1283,7 +1284,7 @@ __global__ void k_gather_rows(Tables t, GenomeView g, const uint32_t *sorted_slo
 
 /* every offset-log entry -> (junction j << 16 | offset, count), j = the slot's position in slot_list; padding, invalid
  * entries and entries of slots that are not junctions (none are expected) get a key above every real one */
-__global__ void k_olog_pairs(Tables t, uint64_t L, int h_bits, unsigned long long *hkey_out, uint32_t *hcnt_out) {
+__global__ void k_olog_pairs(Tables t, uint64_t B, uint64_t L, int h_bits, unsigned long long *hkey_out, uint32_t *hcnt_out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= L) return;
     const unsigned long long nl = *t.n_olog < L ? *t.n_olog : L;
@@ -1292,8 +1293,10 @@ __global__ void k_olog_pairs(Tables t, uint64_t L, int h_bits, unsigned long lon
     uint32_t j = 0u;
     if (ok) {
         const uint32_t slot = (uint32_t)(e >> 32);
-        ok = t.stat[slot].T != EMPTY64;
         j = t.slot_id[slot];
+        /* a junction beyond the bound this finalize was sized for has no room in the per-junction arrays: the
+         * bound is reported as too small anyway (k_finalize_begin) and the finalize runs again */
+        ok = t.stat[slot].T != EMPTY64 && j < B;
     }
     hkey_out[i] = ok ? (((unsigned long long)j << 16) | ((e >> 16) & 0xFFFFull)) : (1ull << h_bits);
     hcnt_out[i] = (uint32_t)(e & 0xFFFFull);
@@ -1485,7 +1488,7 @@ static cudaError_t finalize_issue(const Tables &t, const GenomeView &g, const ui
 
     /* s3: read-offset log ordered by (junction, offset) with a sort, equal pairs summed */
     IPX_CU(cudaMemsetAsync(w.total_j, 0, B * 8, w.s3));
-    k_olog_pairs<<<blocks_for(L, 256), 256, 0, w.s3>>>(t, L, h_bits, w.hk_a, w.hc_a);
+    k_olog_pairs<<<blocks_for(L, 256), 256, 0, w.s3>>>(t, B, L, h_bits, w.hk_a, w.hc_a);
     tb = w.cub_tmp_bytes;
     IPX_CU(cub::DeviceRadixSort::SortPairs(w.cub_tmp3, tb, w.hk_a, w.hk_b, w.hc_a, w.hc_b, (int)L, 0, h_bits + 1, w.s3));
     uint32_t *n_unique = reinterpret_cast<uint32_t *>(w.d_count + 2);
@@ -1513,7 +1516,7 @@ static cudaError_t finalize_issue(const Tables &t, const GenomeView &g, const ui
 cudaError_t finalize_enqueue(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, int32_t n_targets,
                              uint64_t seq_hi, FinalizeWork &w, cudaStream_t st) {
     const uint64_t cap = t.cap_mask + 1;
-    uint64_t B = w.B ? w.B : (1ull << 16), L = w.L ? w.L : (1ull << 16), R = w.R ? w.R : (1ull << 20);
+    uint64_t B = w.B ? w.B : w.first_B, L = w.L ? w.L : w.first_L, R = w.R ? w.R : w.first_R;
     if (w.wish_B > B) B = w.wish_B;
     if (w.wish_L > L) L = w.wish_L;
     if (w.wish_R > R) R = w.wish_R;
@@ -1756,64 +1759,108 @@ __device__ __forceinline__ HistRow *mail_hist_rows(const Mailboxes &m, char *slo
 
 __global__ void __launch_bounds__(256) k_mail_slots(Tables t, const uint32_t *name_rank, Splitters sp, Mailboxes m,
                                                     unsigned long long *counts, uint32_t *slot_jrow) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    /* a warp per slot in use, eight slots per block and step; the block reserves room for its (up to) eight junctions
+     * with one atomic per owner instead of one per junction -- the cursors are single addresses all blocks hit */
+    __shared__ int s_dest[8];
+    __shared__ uint32_t s_nz[8];
+    __shared__ unsigned long long s_jpos[8], s_hpos[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t n_keys = *t.n_keys;
-    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_keys; i += n_warps) {
-        const uint32_t slot = t.slot_list[i];
-        const JStat s = t.stat[slot];
-        if (s.T == EMPTY64) continue; /* never created: nothing was counted into it */
-        const unsigned long long key = t.keys[slot];
-        const int32_t tid = key_tid(t.kl, key);
-        const uint32_t i0 = key_start(t.kl, key), i1 = i0 + key_len(t.kl, key);
-        const int dest = part_of(sp, name_rank[tid], i0);
+    for (uint64_t base = (uint64_t)blockIdx.x * 8; base < n_keys; base += (uint64_t)gridDim.x * 8) {
+        const uint64_t i = base + warp;
+        int dest = -1;
+        uint32_t slot = 0u, i0 = 0u, i1 = 0u, mine = 0u, incl = 0u;
+        int32_t tid = 0;
+        JStat s;
         uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        uint32_t mine = 0;
-        if (t.dense) {
-            const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)slot * DENSE_W);
-            const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        if (i < n_keys) {
+            slot = t.slot_list[i];
+            s = t.stat[slot];
+            if (s.T != EMPTY64) { /* else never created: nothing was counted into it */
+                const unsigned long long key = t.keys[slot];
+                tid = key_tid(t.kl, key);
+                i0 = key_start(t.kl, key);
+                i1 = i0 + key_len(t.kl, key);
+                dest = part_of(sp, name_rank[tid], i0);
+                if (t.dense) {
+                    const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)slot * DENSE_W);
+                    const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) mine += hist_rows_of(v[k]);
+                    for (int k = 0; k < 8; ++k) mine += hist_rows_of(v[k]);
+                }
+            }
         }
-        uint32_t incl = mine;
+        incl = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if (lane >= d) incl += y;
         }
         const uint32_t nz = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        unsigned long long jpos = 0ull, hpos = 0ull;
         if (lane == 0) {
-            jpos = atomicAdd(&counts[dest], 1ull);
-            if (nz) hpos = atomicAdd(&counts[sp.n_parts + dest], (unsigned long long)nz);
+            s_dest[warp] = dest;
+            s_nz[warp] = nz;
         }
-        jpos = __shfl_sync(0xFFFFFFFFu, jpos, 0);
-        hpos = __shfl_sync(0xFFFFFFFFu, hpos, 0);
-        /* a slot that is too small keeps counting: the owner sees counts beyond the capacity and reports it */
-        if (jpos >= m.cap_j || hpos + nz > m.cap_h) continue;
-        char *box = mail_slot(m, dest, m.me);
-        if (lane == 0) {
-            JunctionRow r;
-            r.first[0] = s.first[0]; r.first[1] = s.first[1]; r.first[2] = s.first[2];
-            r.cnt[0] = s.cnt[0]; r.cnt[1] = s.cnt[1]; r.cnt[2] = s.cnt[2];
-            r.tid = tid; r.i0 = i0; r.i1 = i1; r.a0 = s.a0; r.a1 = s.a1; r.pad = 0;
-            mail_junction_rows(box)[jpos] = r;
-            slot_jrow[slot] = (uint32_t)jpos; /* for the log entries of this junction */
-        }
-        HistRow *hr = mail_hist_rows(m, box);
-        uint64_t o = hpos + (incl - mine);
+        __syncthreads();
+        if (warp == 0) {
+            /* lanes 0..7 stand for the block's eight junctions; the first of each owner reserves for all of them */
+            const int my_dest = lane < 8 ? s_dest[lane] : -1;
+            const uint32_t my_nz = lane < 8 ? s_nz[lane] : 0u;
+            uint32_t rank = 0u, n_same = 0u;
+            unsigned long long before = 0ull, all_nz = 0ull;
+            int first = lane;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            uint32_t left = v[k];
-            while (left) {
-                const uint32_t piece = left > 0xFFFFu ? 0xFFFFu : left;
-                HistRow h;
-                h.jrow = (uint32_t)jpos; h.offset = (uint16_t)(lane * 8 + k); h.cnt = (uint16_t)piece;
-                hr[o++] = h;
-                left -= piece;
+            for (int j = 7; j >= 0; --j) {
+                const int dj = __shfl_sync(0xFFFFFFFFu, my_dest, j);
+                const uint32_t nj = __shfl_sync(0xFFFFFFFFu, my_nz, j);
+                if (dj == my_dest) {
+                    n_same++;
+                    all_nz += nj;
+                    first = j;
+                    if (j < lane) { rank++; before += nj; }
+                }
+            }
+            unsigned long long jb = 0ull, hb = 0ull;
+            if (my_dest >= 0 && first == lane) {
+                jb = atomicAdd(&counts[my_dest], (unsigned long long)n_same);
+                if (all_nz) hb = atomicAdd(&counts[sp.n_parts + my_dest], all_nz);
+            }
+            jb = __shfl_sync(0xFFFFFFFFu, jb, first);
+            hb = __shfl_sync(0xFFFFFFFFu, hb, first);
+            if (lane < 8) {
+                s_jpos[lane] = jb + rank;
+                s_hpos[lane] = hb + before;
             }
         }
+        __syncthreads();
+        const unsigned long long jpos = s_jpos[warp], hpos = s_hpos[warp];
+        /* a slot that is too small keeps counting: the owner sees counts beyond the capacity and reports it */
+        if (dest >= 0 && jpos < m.cap_j && hpos + nz <= m.cap_h) {
+            char *box = mail_slot(m, dest, m.me);
+            if (lane == 0) {
+                JunctionRow r;
+                r.first[0] = s.first[0]; r.first[1] = s.first[1]; r.first[2] = s.first[2];
+                r.cnt[0] = s.cnt[0]; r.cnt[1] = s.cnt[1]; r.cnt[2] = s.cnt[2];
+                r.tid = tid; r.i0 = i0; r.i1 = i1; r.a0 = s.a0; r.a1 = s.a1; r.pad = 0;
+                mail_junction_rows(box)[jpos] = r;
+                slot_jrow[slot] = (uint32_t)jpos; /* for the log entries of this junction */
+            }
+            HistRow *hr = mail_hist_rows(m, box);
+            uint64_t o = hpos + (incl - mine);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint32_t left = v[k];
+                while (left) {
+                    const uint32_t piece = left > 0xFFFFu ? 0xFFFFu : left;
+                    HistRow h;
+                    h.jrow = (uint32_t)jpos; h.offset = (uint16_t)(lane * 8 + k); h.cnt = (uint16_t)piece;
+                    hr[o++] = h;
+                    left -= piece;
+                }
+            }
+        }
+        /* (the next step's first __syncthreads orders these reads of s_jpos / s_hpos before their next writes) */
     }
 }
 

@@ -168,6 +168,18 @@ def test_long_regime_unknown_cigar_op_is_reported(built):
     assert got.first_error_seq == want.first_error_seq == 4000
 
 
+@pytest.mark.parametrize("bounds", ["64,64,64", "1024,200000,256", "100000,64,100000"])
+def test_finalize_grows_from_bounds_that_are_too_small(built, monkeypatch, bounds):
+    """The device finalize runs inside buffers sized by grow-only bounds (junctions, offset-log entries, histogram
+    runs) and runs again when one was too small.  Long reads put most read offsets into the log, so every combination
+    of a bound that is too small with data that needs it comes up here."""
+    monkeypatch.setenv("IPX_FIN_BOUNDS", bounds)
+    syn = Synth(30_000, kind=LONG, genome_len=300_000_000, n_genes=2000)
+    got, want = both(syn.names, syn.columns(), n_batches=2, max_anchor_indel_size=36)
+    assert want.n > 1000
+    assert selftest.compare_tables(got, want) == []
+
+
 def test_empty_and_ragged_batches(built):
     names = ["c1", "c2"]
     empty = {k: np.zeros(0, dt) for k, dt in (("tid", np.int32), ("pos", np.int32), ("flag", np.uint16), ("nh_class", np.uint8),
