@@ -1757,110 +1757,110 @@ __device__ __forceinline__ HistRow *mail_hist_rows(const Mailboxes &m, char *slo
     return reinterpret_cast<HistRow *>(slot + MAIL_HEADER_BYTES + m.hist_offset);
 }
 
+/* what a warp needs of one slot in use: owner, key fields, its dense offset row (8 counters per lane) */
+struct MailSlot {
+    int dest; /* -1: nothing to export */
+    uint32_t slot, i0, i1, mine, incl, nz;
+    int32_t tid;
+    uint32_t v[8];
+};
+__device__ __forceinline__ MailSlot mail_read_slot(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t i, int lane) {
+    MailSlot r;
+    r.dest = -1;
+    r.slot = t.slot_list[i];
+    r.mine = 0u;
+    /* everything that hangs on the slot index is requested at once: the warp's time is round trips, not bytes */
+    const unsigned long long T = t.stat[r.slot].T;
+    const unsigned long long key = t.keys[r.slot];
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+    if (t.dense) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)r.slot * DENSE_W);
+        a = row[lane * 2];
+        b = row[lane * 2 + 1];
+    }
+    r.tid = key_tid(t.kl, key);
+    r.i0 = key_start(t.kl, key);
+    r.i1 = r.i0 + key_len(t.kl, key);
+    const bool live = T != EMPTY64; /* else never created: nothing was counted into it */
+    if (live) r.dest = part_of(sp, name_rank[r.tid], r.i0);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        r.v[k] = live ? r.v[k] : 0u;
+        r.mine += hist_rows_of(r.v[k]);
+    }
+    r.incl = r.mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, r.incl, d);
+        if (lane >= d) r.incl += y;
+    }
+    r.nz = __shfl_sync(0xFFFFFFFFu, r.incl, 31);
+    return r;
+}
+
+/* A warp per slot in use.  The per-owner cursors are single addresses every block wants: a block first adds up what
+ * its slots need per owner in shared memory, reserves it with one atomic per owner, and then hands the positions out
+ * from shared memory while it writes the rows (the slots are read twice; the second time they come from L2). */
 __global__ void __launch_bounds__(256) k_mail_slots(Tables t, const uint32_t *name_rank, Splitters sp, Mailboxes m,
                                                     unsigned long long *counts, uint32_t *slot_jrow) {
-    /* a warp per slot in use, eight slots per block and step; the block reserves room for its (up to) eight junctions
-     * with one atomic per owner instead of one per junction -- the cursors are single addresses all blocks hit */
-    __shared__ int s_dest[8];
-    __shared__ uint32_t s_nz[8];
-    __shared__ unsigned long long s_jpos[8], s_hpos[8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ unsigned long long s_j[MAX_PARTS], s_h[MAX_PARTS]; /* needed, then next free position */
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t n_keys = *t.n_keys;
-    for (uint64_t base = (uint64_t)blockIdx.x * 8; base < n_keys; base += (uint64_t)gridDim.x * 8) {
-        const uint64_t i = base + warp;
-        int dest = -1;
-        uint32_t slot = 0u, i0 = 0u, i1 = 0u, mine = 0u, incl = 0u;
-        int32_t tid = 0;
-        JStat s;
-        uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (i < n_keys) {
-            slot = t.slot_list[i];
-            s = t.stat[slot];
-            if (s.T != EMPTY64) { /* else never created: nothing was counted into it */
-                const unsigned long long key = t.keys[slot];
-                tid = key_tid(t.kl, key);
-                i0 = key_start(t.kl, key);
-                i1 = i0 + key_len(t.kl, key);
-                dest = part_of(sp, name_rank[tid], i0);
-                if (t.dense) {
-                    const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)slot * DENSE_W);
-                    const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
-                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) mine += hist_rows_of(v[k]);
-                }
-            }
+    if (threadIdx.x < MAX_PARTS) s_j[threadIdx.x] = s_h[threadIdx.x] = 0ull;
+    __syncthreads();
+    for (uint64_t i = warp0; i < n_keys; i += n_warps) {
+        const MailSlot r = mail_read_slot(t, name_rank, sp, i, lane);
+        if (lane == 0 && r.dest >= 0) {
+            atomicAdd(&s_j[r.dest], 1ull);
+            if (r.nz) atomicAdd(&s_h[r.dest], (unsigned long long)r.nz);
         }
-        incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += y;
-        }
-        const uint32_t nz = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    __syncthreads();
+    if (threadIdx.x < sp.n_parts) {
+        const int d = threadIdx.x;
+        const unsigned long long nj = s_j[d], nh = s_h[d];
+        s_j[d] = nj ? atomicAdd(&counts[d], nj) : 0ull;
+        s_h[d] = nh ? atomicAdd(&counts[sp.n_parts + d], nh) : 0ull;
+    }
+    __syncthreads();
+    for (uint64_t i = warp0; i < n_keys; i += n_warps) {
+        const MailSlot r = mail_read_slot(t, name_rank, sp, i, lane);
+        if (r.dest < 0) continue;
+        unsigned long long jpos = 0ull, hpos = 0ull;
         if (lane == 0) {
-            s_dest[warp] = dest;
-            s_nz[warp] = nz;
+            jpos = atomicAdd(&s_j[r.dest], 1ull);
+            if (r.nz) hpos = atomicAdd(&s_h[r.dest], (unsigned long long)r.nz);
         }
-        __syncthreads();
-        if (warp == 0) {
-            /* lanes 0..7 stand for the block's eight junctions; the first of each owner reserves for all of them */
-            const int my_dest = lane < 8 ? s_dest[lane] : -1;
-            const uint32_t my_nz = lane < 8 ? s_nz[lane] : 0u;
-            uint32_t rank = 0u, n_same = 0u;
-            unsigned long long before = 0ull, all_nz = 0ull;
-            int first = lane;
-#pragma unroll
-            for (int j = 7; j >= 0; --j) {
-                const int dj = __shfl_sync(0xFFFFFFFFu, my_dest, j);
-                const uint32_t nj = __shfl_sync(0xFFFFFFFFu, my_nz, j);
-                if (dj == my_dest) {
-                    n_same++;
-                    all_nz += nj;
-                    first = j;
-                    if (j < lane) { rank++; before += nj; }
-                }
-            }
-            unsigned long long jb = 0ull, hb = 0ull;
-            if (my_dest >= 0 && first == lane) {
-                jb = atomicAdd(&counts[my_dest], (unsigned long long)n_same);
-                if (all_nz) hb = atomicAdd(&counts[sp.n_parts + my_dest], all_nz);
-            }
-            jb = __shfl_sync(0xFFFFFFFFu, jb, first);
-            hb = __shfl_sync(0xFFFFFFFFu, hb, first);
-            if (lane < 8) {
-                s_jpos[lane] = jb + rank;
-                s_hpos[lane] = hb + before;
-            }
-        }
-        __syncthreads();
-        const unsigned long long jpos = s_jpos[warp], hpos = s_hpos[warp];
+        jpos = __shfl_sync(0xFFFFFFFFu, jpos, 0);
+        hpos = __shfl_sync(0xFFFFFFFFu, hpos, 0);
         /* a slot that is too small keeps counting: the owner sees counts beyond the capacity and reports it */
-        if (dest >= 0 && jpos < m.cap_j && hpos + nz <= m.cap_h) {
-            char *box = mail_slot(m, dest, m.me);
-            if (lane == 0) {
-                JunctionRow r;
-                r.first[0] = s.first[0]; r.first[1] = s.first[1]; r.first[2] = s.first[2];
-                r.cnt[0] = s.cnt[0]; r.cnt[1] = s.cnt[1]; r.cnt[2] = s.cnt[2];
-                r.tid = tid; r.i0 = i0; r.i1 = i1; r.a0 = s.a0; r.a1 = s.a1; r.pad = 0;
-                mail_junction_rows(box)[jpos] = r;
-                slot_jrow[slot] = (uint32_t)jpos; /* for the log entries of this junction */
-            }
-            HistRow *hr = mail_hist_rows(m, box);
-            uint64_t o = hpos + (incl - mine);
+        if (jpos >= m.cap_j || hpos + r.nz > m.cap_h) continue;
+        char *box = mail_slot(m, r.dest, m.me);
+        if (lane == 0) {
+            const JStat s = t.stat[r.slot];
+            JunctionRow jr;
+            jr.first[0] = s.first[0]; jr.first[1] = s.first[1]; jr.first[2] = s.first[2];
+            jr.cnt[0] = s.cnt[0]; jr.cnt[1] = s.cnt[1]; jr.cnt[2] = s.cnt[2];
+            jr.tid = r.tid; jr.i0 = r.i0; jr.i1 = r.i1; jr.a0 = s.a0; jr.a1 = s.a1; jr.pad = 0;
+            mail_junction_rows(box)[jpos] = jr;
+            slot_jrow[r.slot] = (uint32_t)jpos; /* for the log entries of this junction */
+        }
+        HistRow *hr = mail_hist_rows(m, box);
+        uint64_t o = hpos + (r.incl - r.mine);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                uint32_t left = v[k];
-                while (left) {
-                    const uint32_t piece = left > 0xFFFFu ? 0xFFFFu : left;
-                    HistRow h;
-                    h.jrow = (uint32_t)jpos; h.offset = (uint16_t)(lane * 8 + k); h.cnt = (uint16_t)piece;
-                    hr[o++] = h;
-                    left -= piece;
-                }
+        for (int k = 0; k < 8; ++k) {
+            uint32_t left = r.v[k];
+            while (left) {
+                const uint32_t piece = left > 0xFFFFu ? 0xFFFFu : left;
+                HistRow h;
+                h.jrow = (uint32_t)jpos; h.offset = (uint16_t)(lane * 8 + k); h.cnt = (uint16_t)piece;
+                hr[o++] = h;
+                left -= piece;
             }
         }
-        /* (the next step's first __syncthreads orders these reads of s_jpos / s_hpos before their next writes) */
     }
 }
 
