@@ -928,8 +928,11 @@ __device__ __forceinline__ Probe probe_junction(const Tables &t, unsigned long l
  * against what the probe saw and only improvements are sent as atomics (almost none once a junction is warm); each
  * lane counts its own read offset with one fire-and-forget atomic into the junction's dense offset row (or the
  * offset hash table for large offsets).  The next 32 events are already in flight while a chunk is folded. */
+#ifndef IPX_K2_BLOCKS
+#define IPX_K2_BLOCKS 5 /* resident blocks per SM */
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(256, 5) k_fold(Tables t, const Event *ev, const TileInfo *tile_info, uint64_t n_tiles) {
+__global__ void __launch_bounds__(256, IPX_K2_BLOCKS) k_fold(Tables t, const Event *ev, const TileInfo *tile_info, uint64_t n_tiles) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -1073,7 +1076,7 @@ void launch_fold(int mode, const Tables &t, const Event *ev, const TileInfo *til
         }
         return;
     }
-    const uint64_t max_blocks = (uint64_t)sm_count * 5; /* what is resident at once (__launch_bounds__(256, 5)) */
+    const uint64_t max_blocks = (uint64_t)sm_count * IPX_K2_BLOCKS; /* what is resident at once */
     const int blocks = (int)(want < max_blocks ? want : max_blocks);
     switch (mode) {
         case MODE_SINGLE: k_fold<MODE_SINGLE><<<blocks, 256, 0, st>>>(t, ev, tile_info, n_tiles); break;
