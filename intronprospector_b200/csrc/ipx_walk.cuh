@@ -371,5 +371,202 @@ IPX_HD void lean_finish(LeanState &w, int64_t pos, Emit &emit) {
     if (w.state == ST_RIGHT) lean_emit(w, pos, emit);
 }
 
+/* ---- one long CIGAR walked by many lanes ----
+ * A record is cut into segments that start right after an aligned operation: there the automaton is in ST_LEFT or
+ * ST_RIGHT with an empty indel run, and what it does next depends on nothing else -- only the VALUES of its registers
+ * do, and those are carried along as they are (a register at a segment's end is either a value made inside the
+ * segment, or one of the registers it was entered with, plus what the segment added).  So:
+ *   pass A  a lane per segment walks its operations once and writes that mapping (SegSummary); the two possible entry
+ *           states part ways at the first operation that changes state and run identically afterwards, so one walk
+ *           carries both;
+ *   stitch  a thread per record applies the mappings in order: every segment's entry registers, concrete;
+ *   pass C  a lane per segment walks it again from those registers with lean_op and emits.
+ * Positions are relative to the record's pos as in LeanState; a record whose span comes near 2^32, or with an unknown
+ * operation, is flagged (bad) and walked by one lane as usual.  tests/native/walk_fuzz.cc holds the three passes
+ * equal to walk_op for random segment lengths. */
+enum : uint32_t { SRC_NONE = 0, SRC_CM, SRC_CI, SRC_OM, SRC_OI, SRC_A0, SRC_I0, SRC_I1, SRC_A1 };
+struct SegForm {
+    uint32_t val; /* counters: added to the source; positions: relative to the segment's first operation (no source) */
+    uint32_t src;
+};
+struct SegSummary {
+    uint32_t dtpos, cur, n_cand; /* n_cand: candidates the segment emits whatever state it is entered in */
+    uint8_t synced, state, e0, bad; /* e0: entered in ST_RIGHT it emits one more, at its first state-changing operation */
+    SegForm a1;
+    SegForm a0[2], i0[2], i1[2], cm[2], ci[2], om[2], oi[2]; /* [0] entered in ST_LEFT (or at the record start), [1] in ST_RIGHT */
+};
+
+struct SegWalk {
+    SegSummary s;
+    int state;
+    IPX_HD void init(bool record_start) {
+        s.dtpos = s.cur = s.n_cand = 0u;
+        s.e0 = s.bad = 0;
+        s.a1.val = 0u; s.a1.src = SRC_A1;
+        for (int v = 0; v < 2; ++v) {
+            s.a0[v].val = s.i0[v].val = s.i1[v].val = s.cm[v].val = s.ci[v].val = s.om[v].val = s.oi[v].val = 0u;
+            s.a0[v].src = SRC_A0; s.i0[v].src = SRC_I0; s.i1[v].src = SRC_I1;
+            s.cm[v].src = SRC_CM; s.ci[v].src = SRC_CI; s.om[v].src = SRC_OM; s.oi[v].src = SRC_OI;
+        }
+        /* a record starts in limbo: nothing to leave open */
+        s.synced = record_start ? 1 : 0;
+        state = record_start ? ST_LIMBO : ST_LEFT; /* before the first state change: "in an anchor" */
+    }
+    IPX_HD void finish() { s.state = (uint8_t)state; }
+};
+
+IPX_HD void seg_swap(SegForm &a, SegForm &b) {
+    const SegForm t = a;
+    a = b;
+    b = t;
+}
+IPX_HD SegForm seg_local(uint32_t v) {
+    SegForm f;
+    f.val = v;
+    f.src = SRC_NONE;
+    return f;
+}
+
+IPX_HD void seg_op(SegWalk &w, uint32_t word, uint32_t max_indel) {
+    SegSummary &s = w.s;
+    const uint32_t op = word & 15u;
+    const uint32_t len = word >> 4;
+    const bool is_al = ((0x181u >> op) & 1u) != 0u;
+    const bool is_di = ((0x006u >> op) & 1u) != 0u;
+    const bool is_n = op == OP_N, is_cl = op == OP_S || op == OP_H;
+    if (!(is_al | is_di | is_n | is_cl) || s.dtpos >= LEAN_TPOS_LIMIT) {
+        s.bad = 1;
+        return;
+    }
+    const bool in_anchor = (w.state & 1) != 0;
+    const uint32_t ncur = is_di ? s.cur + len : 0u;
+    if (is_al ? in_anchor : (is_di && ncur <= max_indel)) {
+        if (is_di && in_anchor) { s.ci[0].val += len; s.ci[1].val += len; }
+        if (op == OP_X) { s.cm[0].val += len; s.cm[1].val += len; }
+        if (op != OP_I) s.dtpos += len;
+        if (is_al) s.a1 = seg_local(s.dtpos);
+        s.cur = ncur;
+        return;
+    }
+    if (!s.synced) {
+        /* the first operation that changes state: N, a clip, or an indel run that breaks the anchor.  Entered in
+         * ST_RIGHT the segment emits the junction it was handed, and the two entry states are one from here on */
+        s.synced = 1;
+        s.e0 = 1;
+        if (is_di) { s.ci[0].val += len; s.ci[1].val += len; }
+        if (is_n) {
+            s.a0[1] = s.i1[1];
+            s.om[1] = seg_local(0u); s.oi[1] = seg_local(0u);
+            s.i0[0] = s.i0[1] = seg_local(s.dtpos);
+            s.i1[0] = s.i1[1] = seg_local(s.dtpos + len);
+            w.state = ST_INTRON;
+            s.cur = 0u;
+            s.dtpos += len;
+        } else {
+            seg_swap(s.cm[1], s.om[1]);
+            seg_swap(s.ci[1], s.oi[1]);
+            w.state = ST_LIMBO;
+            s.cur = is_di ? ncur : s.cur;
+            s.dtpos += (op == OP_D) ? len : 0u;
+        }
+        return;
+    }
+    const bool was_right = w.state == ST_RIGHT;
+    if (is_al) {
+        for (int v = 0; v < 2; ++v) {
+            if (w.state == ST_LIMBO) {
+                s.a0[v] = seg_local(s.dtpos);
+                s.cm[v] = seg_local(0u); s.om[v] = seg_local(0u);
+            } else {
+                s.i1[v] = seg_local(s.dtpos);
+                seg_swap(s.cm[v], s.om[v]);
+                seg_swap(s.ci[v], s.oi[v]);
+            }
+            if (op == OP_X) s.cm[v].val += len;
+        }
+        w.state = w.state == ST_LIMBO ? ST_LEFT : ST_RIGHT;
+        s.dtpos += len;
+        s.a1 = seg_local(s.dtpos);
+        s.cur = 0u;
+    } else if (is_n) {
+        if (was_right) {
+            s.n_cand++;
+            for (int v = 0; v < 2; ++v) {
+                s.a0[v] = s.i1[v];
+                s.om[v] = seg_local(0u); s.oi[v] = seg_local(0u);
+            }
+        }
+        if (in_anchor) {
+            s.i0[0] = s.i0[1] = seg_local(s.dtpos);
+            s.i1[0] = s.i1[1] = seg_local(s.dtpos + len);
+            w.state = ST_INTRON;
+        }
+        s.cur = 0u;
+        s.dtpos += len;
+    } else {
+        for (int v = 0; v < 2; ++v) {
+            if (is_di && in_anchor) s.ci[v].val += len;
+            if (was_right) {
+                seg_swap(s.cm[v], s.om[v]);
+                seg_swap(s.ci[v], s.oi[v]);
+            }
+        }
+        if (was_right) s.n_cand++;
+        s.cur = is_di ? ncur : s.cur;
+        w.state = ST_LIMBO;
+        s.dtpos += (op == OP_D) ? len : 0u;
+    }
+}
+
+IPX_HD uint32_t seg_position(const SegForm &f, const LeanState &e) {
+    switch (f.src) {
+        case SRC_A0: return e.a0;
+        case SRC_I0: return e.i0;
+        case SRC_I1: return e.i1;
+        case SRC_A1: return e.a1;
+        default: return e.tpos + f.val;
+    }
+}
+IPX_HD uint32_t seg_counter(const SegForm &f, const LeanState &e) {
+    switch (f.src) {
+        case SRC_CM: return e.cm + f.val;
+        case SRC_CI: return e.ci + f.val;
+        case SRC_OM: return e.om + f.val;
+        case SRC_OI: return e.oi + f.val;
+        default: return f.val;
+    }
+}
+
+/* the registers a segment is left with, from the registers it is entered with; false: walk the record in one piece.
+ * (Not for empty segments: those assume nothing about their entry and change nothing.) */
+IPX_HD bool seg_apply(const SegSummary &s, const LeanState &e, LeanState &x) {
+    if (s.bad || (uint64_t)e.tpos + s.dtpos >= LEAN_TPOS_LIMIT) return false;
+    const int v = e.state == ST_RIGHT ? 1 : 0;
+    x.tpos = e.tpos + s.dtpos;
+    x.a0 = seg_position(s.a0[v], e);
+    x.i0 = seg_position(s.i0[v], e);
+    x.i1 = seg_position(s.i1[v], e);
+    x.a1 = seg_position(s.a1, e);
+    x.cm = seg_counter(s.cm[v], e);
+    x.ci = seg_counter(s.ci[v], e);
+    x.om = seg_counter(s.om[v], e);
+    x.oi = seg_counter(s.oi[v], e);
+    x.cur = s.cur;
+    x.n_emitted = e.n_emitted + s.n_cand + ((v == 1 && s.e0) ? 1u : 0u);
+    x.state = s.synced ? (int)s.state : e.state;
+    return true;
+}
+
+/* first operation of segment j (j >= 1) of a record with operations [0, n): the first index at or after j * stride
+ * whose predecessor is an aligned operation, n when there is none */
+template <class Word>
+IPX_HD uint32_t seg_start(const Word &word_at, uint32_t n, uint32_t j, uint32_t stride) {
+    uint64_t k = (uint64_t)j * stride;
+    if (j == 0u) return 0u;
+    for (; k < n; ++k)
+        if ((0x181u >> (word_at((uint32_t)k - 1u) & 15u)) & 1u) return (uint32_t)k;
+    return n;
+}
+
 }  // namespace ipx
 #endif

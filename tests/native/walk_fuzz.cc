@@ -1,5 +1,6 @@
 /* walk_fuzz.cc -- host-side fuzz of the device automaton in intronprospector_b200/csrc/ipx_walk.cuh: the branch-free
- * walk_op_flat and the two-path 32-bit lean_op (with its hand-over to a WalkState when relative positions grow large)
+ * walk_op_flat, the two-path 32-bit lean_op (with its hand-over to a WalkState when relative positions grow large)
+ * and the segmented walk of long records (seg_op summaries, seg_apply stitch, lean_op per segment)
  * must produce exactly the candidates (and error codes) of the branching walk_op, which the GPU parity tests pin
  * against the oracle.  Test infrastructure; built and run by tests/test_walk_native.py. */
 #include <stdint.h>
@@ -75,7 +76,65 @@ int main(int argc, char **argv) {
                 lean_finish(lw, pos, c);
             }
         }
+        /* the segmented walk (seg_op / seg_apply / lean_op per segment), segment length drawn per case */
+        Collect d;
+        bool seg_fallback = false, seg_consistent = true;
+        {
+            const uint32_t stride = (t % 3 == 0) ? 1 + rnd() % 9 : (t % 3 == 1 ? 1 + rnd() % 3 : 16);
+            const uint32_t m = (n_ops + stride - 1) / stride;
+            auto word_at = [&](uint32_t k) { return cig[k]; };
+            std::vector<uint32_t> start(m + 1);
+            for (uint32_t j = 0; j < m; ++j) start[j] = seg_start(word_at, n_ops, j, stride);
+            start[m] = n_ops;
+            std::vector<SegSummary> sum(m);
+            for (uint32_t j = 0; j < m; ++j) {
+                SegWalk sw;
+                sw.init(j == 0);
+                for (uint32_t k = start[j]; k < start[j + 1]; ++k) seg_op(sw, cig[k], max_indel);
+                sw.finish();
+                sum[j] = sw.s;
+            }
+            std::vector<LeanState> entry(m + 1);
+            entry[0].init();
+            for (uint32_t j = 0; j < m && !seg_fallback; ++j) {
+                if (start[j] == start[j + 1]) entry[j + 1] = entry[j]; /* empty: nothing is walked, nothing assumed */
+                else seg_fallback = !seg_apply(sum[j], entry[j], entry[j + 1]);
+            }
+            if (!seg_fallback) {
+                LeanState w;
+                w.init();
+                uint32_t bad_d = 0;
+                for (uint32_t j = 0; j < m; ++j) {
+                    w = entry[j];
+                    for (uint32_t k = start[j]; k < start[j + 1]; ++k) lean_op(w, pos, cig[k], max_indel, d, bad_d);
+                    const LeanState &x = entry[j + 1];
+                    /* what the stitch predicted is what the walk arrives at (registers the automaton may read again) */
+                    seg_consistent = seg_consistent && w.tpos == x.tpos && w.state == x.state && w.cur == x.cur &&
+                                     w.n_emitted == x.n_emitted && w.cm == x.cm && w.ci == x.ci && w.om == x.om && w.oi == x.oi &&
+                                     w.a1 == x.a1 && (w.state == ST_LIMBO || w.a0 == x.a0) &&
+                                     ((w.state != ST_INTRON && w.state != ST_RIGHT) || (w.i0 == x.i0 && w.i1 == x.i1));
+                }
+                lean_finish(w, pos, d);
+                seg_consistent = seg_consistent && bad_d == 0;
+            }
+        }
         bool same = bad_a == bad_b && a.out.size() == b.out.size() && bad_a == bad_c && a.out.size() == c.out.size();
+        if (same && !seg_fallback) {
+            same = seg_consistent && bad_a == 0 && a.out.size() == d.out.size();
+            for (size_t i = 0; same && i < a.out.size(); ++i) {
+                const Candidate &x = a.out[i], &z = d.out[i];
+                same = x.anchor_start == z.anchor_start && x.intron_start == z.intron_start && x.intron_end == z.intron_end &&
+                       x.anchor_end == z.anchor_end && x.left_bad == z.left_bad && x.right_bad == z.right_bad && x.ordinal == z.ordinal;
+            }
+            if (!same) printf("(segmented walk differs; consistent %d, %zu candidates)\n", (int)seg_consistent, d.out.size());
+        }
+        if (same && seg_fallback && bad_a == 0) {
+            /* only spans near 2^32 may send a well-formed record to the one-piece walk */
+            uint64_t span = 0;
+            for (uint32_t k = 0; k < n_ops; ++k) span += cig[k] >> 4;
+            same = span >= LEAN_TPOS_LIMIT;
+            if (!same) printf("(segmented walk fell back without need)\n");
+        }
         for (size_t i = 0; same && i < a.out.size(); ++i) {
             const Candidate &x = a.out[i], &y = b.out[i], &z = c.out[i];
             same = x.anchor_start == y.anchor_start && x.intron_start == y.intron_start && x.intron_end == y.intron_end &&
