@@ -323,12 +323,66 @@ __device__ __forceinline__ Words8 load_words8(const uint32_t *cigar, uint32_t k)
     return v;
 }
 
+/* one live record, start to end, by the calling lane; returns the number of events written */
+__device__ __forceinline__ uint32_t walk_record_lean(const BatchView &b, const ExtractParams &p, const Tables &t, Event *out,
+                                                     TileInfo *tile_info, uint64_t r, uint32_t c0, uint32_t c1) {
+    const uint32_t max_indel = p.max_anchor_indel_size;
+    LazySink sink{b, t, p, out, tile_info, r, 0u};
+    LeanState w;
+    w.init();
+    uint32_t bad = 0u;
+    bool wide = false;
+    /* the record's words [c0, c1) as: a few up to the first 32-byte boundary, whole groups of 8, a few more */
+    const uint32_t head_end = min(c1, (c0 + 7u) & ~7u);
+    const uint32_t body_end = head_end + ((c1 - head_end) & ~7u);
+    uint32_t k = c0;
+    Words8 cur;
+    if (head_end < body_end) cur = load_words8(b.cigar, head_end);
+#pragma unroll 1
+    for (int part = 0; part < 2; ++part) {
+        const uint32_t stop = part == 0 ? head_end : c1;
+        if (part == 1 && w.tpos >= LEAN_TPOS_LIMIT) wide = true;
+#pragma unroll 1
+        for (; k < stop && !wide && !bad; ++k) lean_op(w, 0, __ldg(&b.cigar[k]), max_indel, sink, bad);
+        if (part == 1) break;
+        for (; k < body_end; k += 8u) {
+            Words8 nxt = cur;
+            if (k + 8u < body_end) nxt = load_words8(b.cigar, k + 8u);
+            if (w.tpos >= LEAN_TPOS_LIMIT || bad) {
+                wide = true;
+                break;
+            }
+            lean_op(w, 0, cur.lo.x, max_indel, sink, bad);
+            lean_op(w, 0, cur.lo.y, max_indel, sink, bad);
+            lean_op(w, 0, cur.lo.z, max_indel, sink, bad);
+            lean_op(w, 0, cur.lo.w, max_indel, sink, bad);
+            lean_op(w, 0, cur.hi.x, max_indel, sink, bad);
+            lean_op(w, 0, cur.hi.y, max_indel, sink, bad);
+            lean_op(w, 0, cur.hi.z, max_indel, sink, bad);
+            lean_op(w, 0, cur.hi.w, max_indel, sink, bad);
+            cur = nxt;
+        }
+    }
+    uint32_t n_events = sink.n_events;
+    if (bad) { /* reported below */
+    } else if (wide) {
+        uint32_t more = 0u;
+        bad = walk_wide_rest(w, b.cigar + c0, k - c0, c1 - c0, max_indel, sink, &more);
+        n_events += more;
+    } else {
+        lean_finish(w, 0, sink);
+        n_events = sink.n_events;
+    }
+    if (bad) atomicMin(t.err_sv, make_err_cigar(b.seq_base + r, bad & 15u)); /* the reference throws here */
+    return n_events;
+}
+
+/* records with more than `max_ops` operations are left to the segmented kernels below */
 __global__ void __launch_bounds__(256, 4) k_extract_sorted(BatchView b, uint64_t n_words, ExtractParams p, Tables t, Event *out,
                                                         TileInfo *tile_info, const uint32_t *order,
-                                                        unsigned long long *next_chunk) {
+                                                        unsigned long long *next_chunk, uint32_t max_ops) {
     const int lane = threadIdx.x & 31;
     unsigned long long live_words = 0ull, events = 0ull;
-    const uint32_t max_indel = p.max_anchor_indel_size;
     for (;;) {
         unsigned long long chunk = 0ull;
         if (lane == 0) chunk = atomicAdd(next_chunk, 1ull);
@@ -338,56 +392,9 @@ __global__ void __launch_bounds__(256, 4) k_extract_sorted(BatchView b, uint64_t
         if (i >= b.n) continue;
         const uint64_t r = __ldg(&order[i]);
         const uint32_t c0 = __ldg(&b.cigar_off[r]), c1 = __ldg(&b.cigar_off[r + 1]);
-        if (!record_is_live(c1 - c0, __ldg(&b.tid[r]), __ldg(&b.flag[r]))) continue;
+        if (c1 - c0 > max_ops || !record_is_live(c1 - c0, __ldg(&b.tid[r]), __ldg(&b.flag[r]))) continue;
         live_words += c1 - c0;
-        LazySink sink{b, t, p, out, tile_info, r, 0u};
-        LeanState w;
-        w.init();
-        uint32_t bad = 0u;
-        bool wide = false;
-        /* the record's words [c0, c1) as: a few up to the first 32-byte boundary, whole groups of 8, a few more */
-        const uint32_t head_end = min(c1, (c0 + 7u) & ~7u);
-        const uint32_t body_end = head_end + ((c1 - head_end) & ~7u);
-        uint32_t k = c0;
-        Words8 cur;
-        if (head_end < body_end) cur = load_words8(b.cigar, head_end);
-#pragma unroll 1
-        for (int part = 0; part < 2; ++part) {
-            const uint32_t stop = part == 0 ? head_end : c1;
-            if (part == 1 && w.tpos >= LEAN_TPOS_LIMIT) wide = true;
-#pragma unroll 1
-            for (; k < stop && !wide && !bad; ++k) lean_op(w, 0, __ldg(&b.cigar[k]), max_indel, sink, bad);
-            if (part == 1) break;
-            for (; k < body_end; k += 8u) {
-                Words8 nxt = cur;
-                if (k + 8u < body_end) nxt = load_words8(b.cigar, k + 8u);
-                if (w.tpos >= LEAN_TPOS_LIMIT || bad) {
-                    wide = true;
-                    break;
-                }
-                lean_op(w, 0, cur.lo.x, max_indel, sink, bad);
-                lean_op(w, 0, cur.lo.y, max_indel, sink, bad);
-                lean_op(w, 0, cur.lo.z, max_indel, sink, bad);
-                lean_op(w, 0, cur.lo.w, max_indel, sink, bad);
-                lean_op(w, 0, cur.hi.x, max_indel, sink, bad);
-                lean_op(w, 0, cur.hi.y, max_indel, sink, bad);
-                lean_op(w, 0, cur.hi.z, max_indel, sink, bad);
-                lean_op(w, 0, cur.hi.w, max_indel, sink, bad);
-                cur = nxt;
-            }
-        }
-        uint32_t n_events = sink.n_events;
-        if (bad) { /* reported below */
-        } else if (wide) {
-            uint32_t more = 0u;
-            bad = walk_wide_rest(w, b.cigar + c0, k - c0, c1 - c0, max_indel, sink, &more);
-            n_events += more;
-        } else {
-            lean_finish(w, 0, sink);
-            n_events = sink.n_events;
-        }
-        if (bad) atomicMin(t.err_sv, make_err_cigar(b.seq_base + r, bad & 15u)); /* the reference throws here */
-        events += n_events;
+        events += walk_record_lean(b, p, t, out, tile_info, r, c0, c1);
     }
     live_words = warp_sum(live_words);
     events = warp_sum(events);
@@ -395,6 +402,126 @@ __global__ void __launch_bounds__(256, 4) k_extract_sorted(BatchView b, uint64_t
         if (live_words) atomicAdd(t.n_live, live_words);
         if (events) atomicAdd(t.n_events, events);
     }
+}
+
+/* ---- the longest records, each by many lanes (ipx_walk.cuh: "one long CIGAR walked by many lanes") ----
+ * In the longest-first order the records with more than `min_ops` operations form a prefix; each is cut into
+ * segments of about SEG_STRIDE operations.  seg_count[i] is the number of segments of the i-th record of that order
+ * (0 for the shorter ones), seg_base its exclusive scan, seg_base[n] the number of segments. */
+static const uint32_t SEG_STRIDE = 256;
+struct SegCount {
+    const uint32_t *n_ops_sorted;
+    uint64_t n;
+    uint32_t min_ops;
+    __host__ __device__ __forceinline__ uint32_t operator()(uint64_t i) const {
+        const uint32_t ops = i < n ? n_ops_sorted[i] : 0u;
+        return ops > min_ops ? (ops + SEG_STRIDE - 1u) / SEG_STRIDE : 0u;
+    }
+};
+
+/* the record (position in the longest-first order) that owns segment g: the last i with seg_base[i] <= g */
+__device__ __forceinline__ uint32_t seg_owner(const uint32_t *seg_base, uint32_t n, uint32_t g) {
+    uint32_t lo = 0u, hi = n; /* seg_base[lo] <= g < seg_base[hi] */
+    while (hi - lo > 1u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (seg_base[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+/* pass A: what each segment does to the automaton's registers */
+__global__ void __launch_bounds__(256) k_seg_summaries(BatchView b, ExtractParams p, const uint32_t *order, const uint32_t *seg_base,
+                                                       uint32_t *seg_first, SegSummary *summary) {
+    const uint32_t n = (uint32_t)b.n, n_seg = seg_base[n];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_seg; g += stride) {
+        const uint32_t i = seg_owner(seg_base, n, g), j = g - seg_base[i];
+        const uint64_t r = __ldg(&order[i]);
+        const uint32_t c0 = __ldg(&b.cigar_off[r]), n_ops = __ldg(&b.cigar_off[r + 1]) - c0;
+        const uint32_t *cig = b.cigar + c0;
+        auto word_at = [&](uint32_t k) { return __ldg(&cig[k]); };
+        const uint32_t first = seg_start(word_at, n_ops, j, SEG_STRIDE);
+        const uint32_t last = (j + 1u) * SEG_STRIDE >= n_ops ? n_ops : seg_start(word_at, n_ops, j + 1u, SEG_STRIDE);
+        SegWalk w;
+        w.init(j == 0u);
+        for (uint32_t k = first; k < last; ++k) seg_op(w, __ldg(&cig[k]), p.max_anchor_indel_size);
+        w.finish();
+        seg_first[g] = first;
+        summary[g] = w.s;
+    }
+}
+
+/* stitch: a thread per long record applies its segments' summaries in order; entry[g] = the registers segment g is
+ * entered with, mode[g] = 0 nothing to do / 1 walk the segment / 3 walk it and finish the record (its last segment
+ * that has operations) / 2 walk the whole record in one piece (first segment only) */
+__global__ void __launch_bounds__(128) k_seg_stitch(BatchView b, Tables t, const uint32_t *order, const uint32_t *n_ops_sorted,
+                                                    const uint32_t *seg_base, const uint32_t *seg_first, const SegSummary *summary,
+                                                    LeanState *entry, uint8_t *mode, uint32_t min_ops) {
+    const uint32_t n = (uint32_t)b.n;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    unsigned long long live_words = 0ull;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t n_ops = n_ops_sorted[i];
+        if (n_ops <= min_ops) break; /* longest first: nothing but shorter records from here on */
+        const uint32_t g0 = seg_base[i], m = seg_base[i + 1] - g0;
+        const uint64_t r = __ldg(&order[i]);
+        const bool live = record_is_live(n_ops, __ldg(&b.tid[r]), __ldg(&b.flag[r]));
+        if (live) live_words += n_ops;
+        LeanState e;
+        e.init();
+        bool whole = false;
+        uint32_t last_walked = 0u;
+        for (uint32_t j = 0; j < m && live && !whole; ++j) {
+            const uint32_t g = g0 + j;
+            const uint32_t last = j + 1u < m ? seg_first[g + 1u] : n_ops;
+            entry[g] = e;
+            mode[g] = seg_first[g] < last ? 1 : 0;
+            if (seg_first[g] < last) {
+                LeanState x;
+                whole = !seg_apply(summary[g], e, x);
+                e = x;
+                last_walked = g;
+            }
+        }
+        if (!live || whole) {
+            for (uint32_t j = 0; j < m; ++j) mode[g0 + j] = (j == 0u && live) ? 2 : 0;
+        } else {
+            mode[last_walked] = 3; /* the first segment always has operations */
+        }
+    }
+    if (live_words) atomicAdd(t.n_live, live_words);
+}
+
+/* pass C: every segment again, now from its concrete entry registers, emitting */
+__global__ void __launch_bounds__(256) k_seg_emit(BatchView b, ExtractParams p, Tables t, Event *out, TileInfo *tile_info,
+                                                  const uint32_t *order, const uint32_t *seg_base, const uint32_t *seg_first,
+                                                  const LeanState *entry, const uint8_t *mode) {
+    const uint32_t n = (uint32_t)b.n, n_seg = seg_base[n];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    unsigned long long events = 0ull;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_seg; g += stride) {
+        const uint32_t md = mode[g];
+        if (md == 0u) continue;
+        const uint32_t i = seg_owner(seg_base, n, g), j = g - seg_base[i];
+        const uint64_t r = __ldg(&order[i]);
+        const uint32_t c0 = __ldg(&b.cigar_off[r]), c1 = __ldg(&b.cigar_off[r + 1]), n_ops = c1 - c0;
+        if (md == 2u) {
+            events += walk_record_lean(b, p, t, out, tile_info, r, c0, c1);
+            continue;
+        }
+        const uint32_t first = seg_first[g], last = g + 1u == seg_base[i + 1] ? n_ops : seg_first[g + 1u];
+        const uint32_t *cig = b.cigar + c0;
+        LazySink sink{b, t, p, out, tile_info, r, 0u};
+        LeanState w = entry[g];
+        uint32_t bad = 0u;
+        for (uint32_t k = first; k < last; ++k) lean_op(w, 0, __ldg(&cig[k]), p.max_anchor_indel_size, sink, bad);
+        if (md == 3u) lean_finish(w, 0, sink);
+        if (bad) atomicMin(t.err_sv, make_err_cigar(b.seq_base + r, bad & 15u)); /* (pass A sends such records to mode 2) */
+        events += sink.n_events;
+        (void)j;
+    }
+    events = warp_sum(events);
+    if ((threadIdx.x & 31) == 0 && events) atomicAdd(t.n_events, events);
 }
 
 /* ---- pipelined K1 ---- */
@@ -825,26 +952,62 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
         }
         first_simple = n_full;
     }
-    /* long reads (more than 8 operations per record on average): longest first, lean automaton */
+    /* long reads (more than 8 operations per record on average): longest first, lean automaton; the longest of them
+     * segment by segment */
     if (first_simple == 0 && !force_simple && n_cigar > 8 * b.n && aligned16(b.cigar) && next_record) {
+        /* Records longer than this are walked segment by segment.  That is twice the work per operation, and on
+         * log-normal read lengths (longest read 12x the mean) it measured slower at every threshold (B200, 1 M reads:
+         * 3.6 / 2.9 / 2.6 / 2.6 / 2.4 ms for 1536 / 2048 / 3072 / 4096 / 6144 against 2.3 ms without): the kernel is
+         * bound by throughput, not by its longest record.  So the default only catches outliers that would be -- a
+         * single lane needs ~0.3 us per operation.  (Read per call: the tests lower it.) */
+        const char *seg_env = getenv("IPX_K1_SEG_MIN");
+        const uint32_t seg_min_ops = seg_env ? (uint32_t)atoi(seg_env) : 16384u;
+        const bool segmented = seg_min_ops != 0u;
         const int n = (int)b.n;
-        size_t sort_bytes = 0;
+        size_t sort_bytes = 0, scan_bytes = 0;
         cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
                                                                   (const uint32_t *)nullptr, (uint32_t *)nullptr, n, 0, 32, st);
         if (e != cudaSuccess) return e;
-        const size_t col = ((size_t)b.n * sizeof(uint32_t) + 255) & ~(size_t)255;
+        auto seg_counts = thrust::make_transform_iterator(thrust::make_counting_iterator<uint64_t>(0), SegCount{nullptr, b.n, seg_min_ops});
+        e = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, seg_counts, (uint32_t *)nullptr, n + 1, st);
+        if (e != cudaSuccess) return e;
+        const size_t tmp_bytes = ((sort_bytes > scan_bytes ? sort_bytes : scan_bytes) + 255) & ~(size_t)255;
+        const size_t col = ((size_t)(b.n + 1) * sizeof(uint32_t) + 255) & ~(size_t)255;
+        /* at most one segment per SEG_STRIDE operations plus one per segmented record */
+        const size_t max_seg = segmented ? (size_t)(n_cigar / SEG_STRIDE + n_cigar / (seg_min_ops ? seg_min_ops : 1u) + 2) : 1;
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        const size_t seg_bytes = up(max_seg * sizeof(uint32_t)) + up(max_seg * sizeof(SegSummary)) + up(max_seg * sizeof(LeanState)) + up(max_seg);
         char *scratch = nullptr;
-        e = cudaMallocAsync(&scratch, 4 * col + sort_bytes, st);
+        e = cudaMallocAsync(&scratch, 5 * col + tmp_bytes + seg_bytes, st);
         if (e != cudaSuccess) return e;
         uint32_t *n_ops = reinterpret_cast<uint32_t *>(scratch), *n_ops_sorted = reinterpret_cast<uint32_t *>(scratch + col);
         uint32_t *index = reinterpret_cast<uint32_t *>(scratch + 2 * col), *order = reinterpret_cast<uint32_t *>(scratch + 3 * col);
+        uint32_t *seg_base = reinterpret_cast<uint32_t *>(scratch + 4 * col);
+        char *tmp = scratch + 5 * col, *q = tmp + tmp_bytes;
+        uint32_t *seg_first = reinterpret_cast<uint32_t *>(q); q += up(max_seg * sizeof(uint32_t));
+        SegSummary *summary = reinterpret_cast<SegSummary *>(q); q += up(max_seg * sizeof(SegSummary));
+        LeanState *entry = reinterpret_cast<LeanState *>(q); q += up(max_seg * sizeof(LeanState));
+        uint8_t *mode = reinterpret_cast<uint8_t *>(q);
         k_long_keys<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b.cigar_off, b.n, n_ops, index, tile_info);
-        e = cub::DeviceRadixSort::SortPairsDescending(scratch + 4 * col, sort_bytes, n_ops, n_ops_sorted, index, order, n, 0, 32, st);
+        size_t sb = sort_bytes;
+        e = cub::DeviceRadixSort::SortPairsDescending(tmp, sb, n_ops, n_ops_sorted, index, order, n, 0, 32, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(next_record, 0, sizeof(unsigned long long), st);
+        if (e == cudaSuccess && segmented) {
+            auto counts = thrust::make_transform_iterator(thrust::make_counting_iterator<uint64_t>(0), SegCount{n_ops_sorted, b.n, seg_min_ops});
+            size_t cb = scan_bytes;
+            e = cub::DeviceScan::ExclusiveSum(tmp, cb, counts, seg_base, n + 1, st);
+            if (e == cudaSuccess) {
+                k_seg_summaries<<<sm_count * 8, 256, 0, st>>>(b, p, order, seg_base, seg_first, summary);
+                k_seg_stitch<<<sm_count * 2, 128, 0, st>>>(b, t, order, n_ops_sorted, seg_base, seg_first, summary, entry, mode, seg_min_ops);
+                k_seg_emit<<<sm_count * 8, 256, 0, st>>>(b, p, t, out, tile_info, order, seg_base, seg_first, entry, mode);
+                if (launches) (*launches) += 4;
+                e = cudaGetLastError();
+            }
+        }
         if (e == cudaSuccess) {
             const uint64_t chunks = (b.n + 31) / 32, want = (chunks + 7) / 8, max_blocks = (uint64_t)sm_count * 8;
             k_extract_sorted<<<(int)(want < max_blocks ? want : max_blocks), 256, 0, st>>>(b, n_cigar, p, t, out, tile_info, order,
-                                                                                         next_record);
+                                                                                         next_record, segmented ? seg_min_ops : 0xFFFFFFFFu);
             e = cudaGetLastError();
         }
         cudaFreeAsync(scratch, st);

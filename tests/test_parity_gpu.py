@@ -96,8 +96,17 @@ def test_missing_genome_targets_are_skipped(built, tmp_path):
     assert list(got.missing_targets) == list(want.missing_targets) == [2]
 
 
+@pytest.fixture(params=[None, "600"], ids=["whole-records", "segmented"])
+def segment_threshold(request, monkeypatch):
+    """IPX_K1_SEG_MIN: records with more operations than this are walked segment by segment (default 16384: only
+    outliers); 600 sends a good part of every long-read test through the segmented kernels."""
+    if request.param is not None:
+        monkeypatch.setenv("IPX_K1_SEG_MIN", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("indel", [0, 36])
-def test_long_reads(built, indel):
+def test_long_reads(built, indel, segment_threshold):
     syn = Synth(30_000, kind=LONG, genome_len=300_000_000, n_genes=2000)
     got, want = both(syn.names, syn.columns(), n_batches=3, max_anchor_indel_size=indel)
     assert want.n > 1000
@@ -134,7 +143,7 @@ def _hand_made_long_batch(extra=()):
 
 
 @pytest.mark.parametrize("indel", [0, 5, 36])
-def test_long_regime_operation_soup(built, indel):
+def test_long_regime_operation_soup(built, indel, segment_threshold):
     cols = _hand_made_long_batch()
     for n_batches in (1, 3):
         got, want = both(["c1"], cols, n_batches=n_batches, max_anchor_indel_size=indel, min_anchor_length=3)
@@ -142,7 +151,7 @@ def test_long_regime_operation_soup(built, indel):
         assert selftest.compare_tables(got, want) == []
 
 
-def test_long_regime_positions_beyond_32_bit_offsets(built):
+def test_long_regime_positions_beyond_32_bit_offsets(built, segment_threshold):
     """A CIGAR whose reference span outgrows the long-read walker's 32-bit relative positions: the walk is handed to
     the 64-bit automaton mid-record and the junction after the hand-over is still found where the oracle finds it."""
     def w(length, op):
@@ -150,13 +159,16 @@ def test_long_regime_positions_beyond_32_bit_offsets(built):
     big = (1 << 28) - 1
     giant = [w(30, "M")] + [w(big, "D")] * 7 + [w(5000, "M"), w(40, "M"), w(300, "N"), w(45, "M"), w(2, "I"), w(20, "M"),
                                                   w(900, "N"), w(33, "M")] + [w(3, "M"), w(1, "X")] * 6
-    cols = _hand_made_long_batch(extra=[(0, 100, 0, giant), (0, 120, 16, giant[:-3])])
+    # the same span inside a record long enough to be walked segment by segment (more than 1024 operations)
+    filler = [w(20, "M"), w(1, "X"), w(2, "I"), w(30, "="), w(1, "D")] * 300
+    very_long = filler[:700] + giant + filler
+    cols = _hand_made_long_batch(extra=[(0, 100, 0, giant), (0, 120, 16, giant[:-3]), (0, 90, 0, very_long)])
     got, want = both(["c1"], cols, max_anchor_indel_size=36)
     assert int(np.max(want.intron_start)) > 7 * big
     assert selftest.compare_tables(got, want) == []
 
 
-def test_long_regime_unknown_cigar_op_is_reported(built):
+def test_long_regime_unknown_cigar_op_is_reported(built, segment_threshold):
     def w(length, op):
         return (length << 4) | op
     bad_late = [w(10, 0)] * 40 + [w(3, 9)] + [w(10, 0)] * 5   # 'B' deep inside a whole group of 8
@@ -165,6 +177,13 @@ def test_long_regime_unknown_cigar_op_is_reported(built):
     got, want = both(["c1"], cols)
     assert got.status == want.status == -3
     assert got.error_text == want.error_text == "Unknown cigar operation 'B'"
+    assert got.first_error_seq == want.first_error_seq == 4000
+    # ... and inside a record that is walked segment by segment
+    segmented = [w(10, 0), w(1, 8)] * 900 + [w(3, 6)] + [w(10, 0)] * 700
+    cols = _hand_made_long_batch(extra=[(0, 500, 0, segmented), (0, 600, 0, bad_early)])
+    got, want = both(["c1"], cols)
+    assert got.status == want.status == -3
+    assert got.error_text == want.error_text == "Unknown cigar operation 'P'"
     assert got.first_error_seq == want.first_error_seq == 4000
 
 
