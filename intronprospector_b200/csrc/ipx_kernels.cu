@@ -1008,7 +1008,7 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
             const uint64_t chunks = (b.n + 31) / 32, want = (chunks + 7) / 8, max_blocks = (uint64_t)sm_count * 8;
             k_extract_sorted<<<(int)(want < max_blocks ? want : max_blocks), 256, 0, st>>>(b, n_cigar, p, t, out, tile_info, order,
                                                                                          next_record, segmented ? seg_min_ops : 0xFFFFFFFFu);
-            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaGetLastError();
         }
         cudaFreeAsync(scratch, st);
         if (launches) (*launches) += 3; /* keys, extract, and the sort counted as one */
