@@ -1,23 +1,26 @@
 /* ipx_kernels.cu -- sm_100a kernels of the junction-extraction path.
  *
- *  k_extract_tma     K1, the hot kernel: persistent blocks stream tiles of EX_TILE consecutive records through a
- *                    3-stage shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier, one producer
- *                    warp), so every record column and CIGAR word is read from HBM exactly once, coalesced, with
- *                    the latency hidden behind the previous tiles' work.  Eight consumer warps (a) classify the
- *                    tile's records and compact the live ones (process_alignment's skip test) into two lists --
- *                    CIGARs of at most three operations, which can only be "aligned, N, aligned", and longer ones
- *                    -- then (b) walk the listed records with full warps (ipx_walk.cuh) and write each junction
- *                    event straight into the tile's private region of the event buffer.
- *  k_extract_simple  K1 for what the pipeline does not take: the last partial tile, unaligned columns, long reads.
+ *  k_extract_tma     K1, the hot kernel: persistent blocks (two per SM: a producer warp + 15 worker warps) stream
+ *                    tiles of EX_TILE consecutive records through a 4-stage shared-memory ring filled by TMA bulk
+ *                    copies (cp.async.bulk + mbarrier), so every record column and CIGAR word is read from HBM
+ *                    exactly once, coalesced, with the latency hidden behind the previous tiles' work.  The workers
+ *                    (a) classify the tile's records and compact the live ones (process_alignment's skip test) into
+ *                    two lists -- CIGARs of at most three operations, which can only be "aligned, N, aligned", and
+ *                    longer ones -- then (b) walk the listed records with full warps (ipx_walk.cuh) and write each
+ *                    junction event straight into the tile's private region of the event buffer.
+ *  k_extract_sorted  K1 for long reads: records taken longest first, lean 32-bit automaton, 32-byte CIGAR groups;
+ *                    k_seg_* walk outliers (tens of thousands of operations) segment by segment.
+ *  k_extract_simple  K1 for what is left: the last partial tile, columns that are not 16-byte aligned.
  *  k_fold<MODE>      K2: warp-grouped keyed aggregation of the events into the junction / offset tables
  *                      MODE_SINGLE  no canon filter: insert + first-seen + counts + anchors + offsets
  *                      MODE_PASS1   canon filter:    insert + first-seen per strand class only
  *                      MODE_PASS2   canon filter:    count events at or after the creation threshold T
  *  k_resolve_T       K3: donor/acceptor gather from the HBM genome, per junction, and the choice of the
  *                    creating event T = first event whose (key, strand class) passes the filter
- *  finalize_tables   key-order sort, sjN ranking, offset-histogram ordering, output gather -- all over the
- *                    list of slots in use, never over the table's capacity
- *  k_import_*        fold partial tables received from other GPUs (multi-GPU exchange)
+ *  finalize_*        key-order sort, sjN ranking, offset-histogram ordering, output gather -- one CUDA graph over
+ *                    the list of slots in use, never over the table's capacity
+ *  k_export_* / k_import_*   partial tables packed for / folded from other GPUs (all-to-all transport)
+ *  k_mail_*          the same exchange over peer memory: rows stored straight into the owners' mailboxes
  *
  * Reference semantics: SURVEY.md section 8(a) A1-A8 (junctions_extractor.cc:49-95,124-319,322-530).
  */
