@@ -101,7 +101,7 @@ static void merge(const Options &opts) {
     ipx::CallsRows rows;
     string parse_error;
     try {
-        for (const string &f : opts.input_calls_tsvs) ipx::load_calls_tsv(f, opts.junction_filter, rows);
+        ipx::load_calls_tsvs(opts.input_calls_tsvs, opts.junction_filter, rows);
     } catch (const std::exception &e) {
         parse_error = e.what(); /* rows read before the bad one are still folded: their stderr lines come first */
     }

@@ -4,7 +4,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
+#include <atomic>
+#include <memory>
 #include <stdexcept>
+#include <thread>
 
 namespace ipx {
 
@@ -180,6 +183,89 @@ void load_calls_tsv(const std::string &path, int junction_filter, CallsRows &out
         throw;
     }
     gzclose(gz);
+}
+
+namespace {
+
+/* append the rows of one file, parsed into dictionaries of its own, translating them into the common dictionaries:
+ * names new to `out` get their numbers in the order the file first used them, as if it had been parsed into `out` */
+void append_part(const CallsRows &part, CallsRows &out) {
+    std::vector<int32_t> chrom_map(part.chrom_names.size());
+    for (size_t i = 0; i < part.chrom_names.size(); i++) {
+        auto it = out.chrom_index.find(part.chrom_names[i]);
+        if (it == out.chrom_index.end()) {
+            it = out.chrom_index.emplace(part.chrom_names[i], (int32_t)out.chrom_names.size()).first;
+            out.chrom_names.push_back(part.chrom_names[i]);
+        }
+        chrom_map[i] = it->second;
+    }
+    std::vector<uint32_t> site_map(part.site_strings.size());
+    for (size_t i = 0; i < part.site_strings.size(); i++) {
+        auto it = out.site_index.find(part.site_strings[i]);
+        if (it == out.site_index.end()) {
+            it = out.site_index.emplace(part.site_strings[i], (uint32_t)out.site_strings.size()).first;
+            out.site_strings.push_back(part.site_strings[i]);
+        }
+        site_map[i] = it->second;
+    }
+    const size_t n0 = out.chrom.size(), n = part.chrom.size();
+    out.chrom.resize(n0 + n);
+    out.sites.resize(n0 + n);
+    for (size_t i = 0; i < n; i++) {
+        out.chrom[n0 + i] = chrom_map[part.chrom[i]];
+        out.sites[n0 + i] = site_map[part.sites[i]];
+    }
+    out.i0.insert(out.i0.end(), part.i0.begin(), part.i0.end());
+    out.i1.insert(out.i1.end(), part.i1.begin(), part.i1.end());
+    out.a0.insert(out.a0.end(), part.a0.begin(), part.a0.end());
+    out.a1.insert(out.a1.end(), part.a1.begin(), part.a1.end());
+    out.strand.insert(out.strand.end(), part.strand.begin(), part.strand.end());
+    out.counts.insert(out.counts.end(), part.counts.begin(), part.counts.end());
+    out.conf.insert(out.conf.end(), part.conf.begin(), part.conf.end());
+}
+
+}  // namespace
+
+void load_calls_tsvs(const std::vector<std::string> &paths, int junction_filter, CallsRows &out) {
+    unsigned threads = std::thread::hardware_concurrency();
+    if (threads > 16u) threads = 16u;
+    if (const char *e = getenv("IPX_PARSE_THREADS")) threads = (unsigned)atoi(e);
+    if (threads > paths.size()) threads = (unsigned)paths.size();
+    if (threads <= 1u) {
+        for (const std::string &f : paths) load_calls_tsv(f, junction_filter, out);
+        return;
+    }
+    struct Part {
+        CallsRows rows;
+        std::string error;
+        bool failed = false;
+    };
+    std::vector<std::unique_ptr<Part>> parts(paths.size());
+    for (auto &p : parts) p.reset(new Part());
+    std::atomic<size_t> next(0), first_bad(paths.size());
+    auto work = [&]() {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= paths.size() || i > first_bad.load()) break; /* nothing after the first bad file is used */
+            try {
+                load_calls_tsv(paths[i], junction_filter, parts[i]->rows);
+            } catch (const std::exception &e) {
+                parts[i]->error = e.what();
+                parts[i]->failed = true;
+                size_t seen = first_bad.load();
+                while (i < seen && !first_bad.compare_exchange_weak(seen, i)) {
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; t++) pool.emplace_back(work);
+    for (auto &t : pool) t.join();
+    for (size_t i = 0; i < paths.size(); i++) {
+        append_part(parts[i]->rows, out);
+        if (parts[i]->failed) throw std::runtime_error(parts[i]->error);
+        parts[i].reset(); /* give the file's rows back before the next one is appended */
+    }
 }
 
 }  // namespace ipx

@@ -27,5 +27,11 @@ struct CallsRows {
  * Throws std::runtime_error with the reference's messages (tsv.hh:41,71,88; type_ops.hh:23,32,41). */
 void load_calls_tsv(const std::string &path, int junction_filter, CallsRows &out);
 
+/* The same for a list of files, in list order, with the files parsed by a pool of threads (IPX_PARSE_THREADS, default:
+ * the host's cores, at most 16).  Rows, chromosome and splice-site dictionaries come out exactly as from calling
+ * load_calls_tsv file by file; so does a failure: the rows up to the first bad line of the first bad file are kept and
+ * its error is thrown. */
+void load_calls_tsvs(const std::vector<std::string> &paths, int junction_filter, CallsRows &out);
+
 }  // namespace ipx
 #endif

@@ -121,7 +121,9 @@ extern "C" int ipxio_calls_load(const char *const *paths, int32_t n_paths, int32
     *out = c;
     int rc = IPX_OK;
     try {
-        for (int32_t i = 0; i < n_paths; i++) ipx::load_calls_tsv(paths[i], junction_filter, c->rows);
+        std::vector<std::string> files;
+        for (int32_t i = 0; i < n_paths; i++) files.push_back(paths[i]);
+        ipx::load_calls_tsvs(files, junction_filter, c->rows);
     } catch (const std::exception &e) {
         g_err = e.what();
         rc = IPX_ERR_ARG;
