@@ -4,7 +4,12 @@
 #include "genome_loader.h"
 #include <ctype.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <algorithm>
+#include <atomic>
 #include <stdexcept>
+#include <thread>
+#include <vector>
 #include "htslib/faidx.h"
 
 namespace ipx {
@@ -16,17 +21,35 @@ void load_genome(const std::string &fasta, LoadedGenome &out) {
     out.names.resize(n);
     out.seqs.resize(n);
     out.lengths.resize(n);
-    for (int i = 0; i < n; i++) {
-        out.names[i] = faidx_iseq(fai, i);
-        int len = faidx_seq_len(fai, out.names[i].c_str());
+    for (int i = 0; i < n; i++) out.names[i] = faidx_iseq(fai, i);
+    auto fetch = [&](faidx_t *f, int i) {
+        int len = faidx_seq_len(f, out.names[i].c_str());
         int got = 0;
-        char *s = len > 0 ? faidx_fetch_seq(fai, out.names[i].c_str(), 0, len - 1, &got) : NULL;
+        char *s = len > 0 ? faidx_fetch_seq(f, out.names[i].c_str(), 0, len - 1, &got) : NULL;
         if (s) {
             out.seqs[i].assign(s, (size_t)got);
             free(s);
         }
         /* a short read (truncated file) leaves the tail unfetchable, as it would be for faidx_fetch_seq */
         out.lengths[i] = out.seqs[i].size();
+    };
+    /* the sequences are independent: a few threads, each with an index handle (and file position) of its own */
+    unsigned threads = std::min<unsigned>(std::min<unsigned>(8u, std::thread::hardware_concurrency()), (unsigned)n);
+    if (const char *e = getenv("IPX_GENOME_THREADS")) threads = (unsigned)atoi(e);
+    if (threads <= 1u) {
+        for (int i = 0; i < n; i++) fetch(fai, i);
+    } else {
+        std::atomic<int> next(0);
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < threads; t++)
+            pool.emplace_back([&]() {
+                faidx_t *mine = fai_load3(fasta.c_str(), NULL, NULL, 0);
+                if (mine == NULL) return; /* the others, or the caller below, take its share */
+                for (int i; (i = next.fetch_add(1)) < n;) fetch(mine, i);
+                fai_destroy(mine);
+            });
+        for (auto &t : pool) t.join();
+        for (int i; (i = next.fetch_add(1)) < n;) fetch(fai, i);
     }
     fai_destroy(fai);
     out.name_ptrs.resize(n);

@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cerrno>
+#include <algorithm>
 #include <cctype>
 #include <string>
 #include <condition_variable>
@@ -650,7 +651,7 @@ static void restore_long_cigar(bam1_t *b) {
 
 static int bam_read_record(ipx_hts_impl *im, bam1_t *b) {
     Reader &rd = im->rd;
-    int32_t block_len;
+    int32_t block_len = 0;
     if (rd.ensure(4) < 4) return rd.err ? -2 : ((rd.end - rd.beg) == 0 ? -1 : -4);
     rd.read_exact(&block_len, 4);
     if (block_len < 32) return -4;
@@ -1285,9 +1286,19 @@ extern "C" char *faidx_fetch_seq(const faidx_t *fai, const char *c_name, int p_b
     if (want > 0 && e.line_blen > 0) {
         int64_t off = e.offset + beg / e.line_blen * e.line_len + beg % e.line_blen;
         if (fseeko(fai->fp, off, SEEK_SET) != 0) { free(s); *len = -1; return nullptr; }
-        int ch;
-        while (got < want && (ch = fgetc(fai->fp)) != EOF)
-            if (isgraph(ch)) s[got++] = (char)ch;
+        /* the bases are what is left of the bytes from `off` on once non-printing characters (line ends) are dropped;
+         * read in blocks -- a getc per base costs tens of nanoseconds, a whole genome minutes */
+        const int64_t with_line_ends = want + (want / e.line_blen + 2) * (e.line_len - e.line_blen) + 16; /* small fetches stay small */
+        std::vector<unsigned char> block((size_t)std::min<int64_t>(1 << 20, with_line_ends));
+        while (got < want) {
+            const size_t n = fread(block.data(), 1, block.size(), fai->fp);
+            if (n == 0) break;
+            for (size_t i = 0; i < n && got < want; i++) {
+                const unsigned char ch = block[i];
+                s[got] = (char)ch; /* one byte of slack past `want` is the terminator's */
+                got += isgraph(ch) ? 1 : 0;
+            }
+        }
     }
     s[got] = 0;
     *len = (int)got;
