@@ -199,6 +199,34 @@ def test_finalize_grows_from_bounds_that_are_too_small(built, monkeypatch, bound
     assert selftest.compare_tables(got, want) == []
 
 
+@pytest.mark.parametrize("bounds", ["64,64,64", "70000,64,4096"])
+def test_finalize_grows_from_small_bounds_short_reads(built, tmp_path, monkeypatch, bounds):
+    """The same for short reads (offsets in the dense rows, a few in the log), with and without the canon filter, and
+    over several flushes of one handle (the bounds only ever grow)."""
+    monkeypatch.setenv("IPX_FIN_BOUNDS", bounds)
+    syn = Synth(400_000, kind=SHORT_UNSTRANDED, genome_len=100_000_000, n_genes=1000, n_contigs=5)
+    cols = syn.columns()
+    got, want = both(syn.names, cols, n_batches=3)
+    assert want.n > 3000
+    assert selftest.compare_tables(got, want) == []
+    genome = genome_of(syn, tmp_path)
+    got, want = both(syn.names, cols, n_batches=2, genome=genome, junction_filter=_native.FILTER_CANON)
+    assert selftest.compare_tables(got, want) == []
+    # one handle, three jobs of different sizes: small, large, small again (sjN keeps counting across the flushes of a
+    # handle, junctions_extractor.hh:129, so the oracle handle lives as long)
+    gpu, ora = _native.Engine(device=0), selftest.oracle_engine()
+    for n_rec in (20_000, 400_000, 50_000):
+        part = {k: (v[:n_rec] if k not in ("cigar", "cigar_off") else v) for k, v in cols.items()}
+        part["cigar_off"] = cols["cigar_off"][:n_rec + 1]
+        part["cigar"] = cols["cigar"][:int(cols["cigar_off"][n_rec])]
+        got = selftest.run_engine(gpu, syn.names, part)
+        want = selftest.run_engine(ora, syn.names, part)
+        assert want.n > 200
+        assert selftest.compare_tables(got, want) == []
+    gpu.close()
+    ora.close()
+
+
 def test_empty_and_ragged_batches(built):
     names = ["c1", "c2"]
     empty = {k: np.zeros(0, dt) for k, dt in (("tid", np.int32), ("pos", np.int32), ("flag", np.uint16), ("nh_class", np.uint8),
