@@ -46,6 +46,8 @@ class ParallelBgzf {
         bool bad = false;
     };
     FILE *fp_ = nullptr;
+    std::vector<uint8_t> prefix_; /* bytes of the stream somebody already took from fp_ (input that cannot seek) */
+    size_t prefix_pos_ = 0;
     std::vector<Slot> ring_;
     std::vector<std::thread> threads_;
     std::mutex mu_;
@@ -55,10 +57,21 @@ class ParallelBgzf {
     uint64_t n_consumed_ = 0; /* blocks the consumer is done with */
     bool read_done_ = false, stop_ = false, read_error_ = false;
 
+    size_t take(void *dst, size_t n) { /* reader thread only */
+        size_t done = 0;
+        if (prefix_pos_ < prefix_.size()) {
+            done = std::min(n, prefix_.size() - prefix_pos_);
+            memcpy(dst, prefix_.data() + prefix_pos_, done);
+            prefix_pos_ += done;
+        }
+        if (done < n) done += fread((uint8_t *)dst + done, 1, n - done, fp_);
+        return done;
+    }
+
     void reader_main() {
         for (;;) {
             uint8_t hdr[18];
-            size_t got = fread(hdr, 1, 18, fp_);
+            size_t got = take(hdr, 18);
             bool ok = got == 18 && hdr[0] == 0x1f && hdr[1] == 0x8b && hdr[2] == 8 && (hdr[3] & 4) && hdr[12] == 'B' && hdr[13] == 'C';
             size_t bsize = ok ? (size_t)(hdr[16] | (hdr[17] << 8)) + 1 : 0;
             std::unique_lock<std::mutex> lk(mu_);
@@ -74,7 +87,7 @@ class ParallelBgzf {
             lk.unlock();
             s.in.resize(bsize);
             memcpy(s.in.data(), hdr, 18);
-            if (fread(s.in.data() + 18, 1, bsize - 18, fp_) != bsize - 18) {
+            if (take(s.in.data() + 18, bsize - 18) != bsize - 18) {
                 lk.lock();
                 read_error_ = true;
                 read_done_ = true;
@@ -131,6 +144,19 @@ class ParallelBgzf {
         fclose(f);
         return ok;
     }
+    static bool is_bgzf_header(const uint8_t *h, size_t n) {
+        return n >= 16 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C';
+    }
+    /* a stream that is already open and of which `prefix` was already read (takes the FILE over) */
+    bool open_stream(FILE *f, const uint8_t *prefix, size_t n_prefix, int n_workers) {
+        fp_ = f;
+        prefix_.assign(prefix, prefix + n_prefix);
+        prefix_pos_ = 0;
+        ring_.resize((size_t)n_workers * 8);
+        threads_.emplace_back([this] { reader_main(); });
+        for (int i = 0; i < n_workers; i++) threads_.emplace_back([this] { worker_main(); });
+        return true;
+    }
     bool open(const char *fn, int n_workers) {
         fp_ = fopen(fn, "rb");
         if (!fp_) return false;
@@ -180,8 +206,83 @@ class ParallelBgzf {
     ~ParallelBgzf() { close(); }
 };
 
+/* Sequential input that cannot be reopened or rewound (a pipe on stdin) and of which a few bytes were already read to
+ * see what it is: those bytes first, then the rest of the FILE -- as they are, or inflated when they are gzip members
+ * (any gzip, BGZF included).  What gzread does, minus the need to hand zlib a descriptor it reads from the start. */
+class StreamSource {
+    FILE *fp_ = nullptr;
+    std::vector<uint8_t> in_;
+    size_t beg_ = 0, end_ = 0;
+    bool gz_ = false, z_ready_ = false, in_eof_ = false, member_done_ = true;
+    z_stream zs_;
+
+    void refill() {
+        if (beg_ < end_ || in_eof_) return;
+        beg_ = 0;
+        end_ = fread(in_.data(), 1, in_.size(), fp_);
+        if (end_ == 0) in_eof_ = true;
+    }
+
+   public:
+    bool gzip() const { return gz_; }
+    bool open(FILE *f, const uint8_t *prefix, size_t n_prefix) {
+        fp_ = f;
+        in_.resize(1 << 20);
+        memcpy(in_.data(), prefix, n_prefix);
+        beg_ = 0;
+        end_ = n_prefix;
+        gz_ = n_prefix >= 2 && prefix[0] == 0x1f && prefix[1] == 0x8b;
+        if (gz_) {
+            memset(&zs_, 0, sizeof(zs_));
+            if (inflateInit2(&zs_, 15 + 16) != Z_OK) return false;
+            z_ready_ = true;
+        }
+        return true;
+    }
+    int read(uint8_t *dst, int want) {
+        int done = 0;
+        if (!gz_) {
+            while (done < want) {
+                refill();
+                if (beg_ == end_) break;
+                const size_t n = std::min<size_t>(end_ - beg_, (size_t)(want - done));
+                memcpy(dst + done, in_.data() + beg_, n);
+                beg_ += n;
+                done += (int)n;
+            }
+            return done;
+        }
+        while (done < want) {
+            refill();
+            if (beg_ == end_) return member_done_ || done > 0 ? done : -1; /* the input ends inside a member: truncated */
+            if (member_done_) {
+                inflateReset(&zs_); /* the next member */
+                member_done_ = false;
+            }
+            zs_.next_in = in_.data() + beg_;
+            zs_.avail_in = (uInt)(end_ - beg_);
+            zs_.next_out = dst + done;
+            zs_.avail_out = (uInt)(want - done);
+            const int rc = inflate(&zs_, Z_NO_FLUSH);
+            beg_ = end_ - zs_.avail_in;
+            done = want - (int)zs_.avail_out;
+            if (rc == Z_STREAM_END) member_done_ = true;
+            else if (rc != Z_OK && rc != Z_BUF_ERROR) return -1;
+        }
+        return done;
+    }
+    void close() {
+        if (z_ready_) inflateEnd(&zs_);
+        z_ready_ = false;
+        if (fp_) fclose(fp_);
+        fp_ = nullptr;
+    }
+    ~StreamSource() { close(); }
+};
+
 struct Reader {
     gzFile gz = nullptr;
+    StreamSource *stream = nullptr; /* input that cannot seek (stdin), not handled by the BGZF decoder pool */
     ParallelBgzf *pbgzf = nullptr; /* BGZF input with more than one decode thread */
     bool direct = false;           /* the input is not compressed */
     std::vector<uint8_t> buf;
@@ -197,7 +298,25 @@ struct Reader {
     bool open(const char *fn) {
         if (strcmp(fn, "-") == 0) fn = "/dev/stdin";
         const int threads = decode_threads();
-        if (threads > 1 && strcmp(fn, "/dev/stdin") != 0 && ParallelBgzf::looks_like_bgzf(fn)) {
+        if (strcmp(fn, "/dev/stdin") == 0) {
+            /* a pipe cannot be looked at and then handed to zlib from the start: read the first bytes here and pass
+             * them on -- to the BGZF decoder pool when that is what they are, else to a plain / gzip stream reader */
+            FILE *f = fopen(fn, "rb");
+            if (!f) return false;
+            setvbuf(f, nullptr, _IOFBF, 1 << 22);
+            uint8_t head[18];
+            const size_t n_head = fread(head, 1, sizeof(head), f);
+            buf.resize(1 << 20);
+            if (threads > 1 && ParallelBgzf::is_bgzf_header(head, n_head)) {
+                pbgzf = new ParallelBgzf();
+                return pbgzf->open_stream(f, head, n_head, threads);
+            }
+            stream = new StreamSource();
+            if (!stream->open(f, head, n_head)) return false;
+            direct = !stream->gzip();
+            return true;
+        }
+        if (threads > 1 && ParallelBgzf::looks_like_bgzf(fn)) {
             pbgzf = new ParallelBgzf();
             if (!pbgzf->open(fn, threads)) {
                 delete pbgzf;
@@ -219,8 +338,12 @@ struct Reader {
         gz = nullptr;
         delete pbgzf;
         pbgzf = nullptr;
+        delete stream;
+        stream = nullptr;
     }
-    int raw_read(uint8_t *dst, int want) { return pbgzf ? pbgzf->read(dst, want) : gzread(gz, dst, want); }
+    int raw_read(uint8_t *dst, int want) {
+        return pbgzf ? pbgzf->read(dst, want) : (stream ? stream->read(dst, want) : gzread(gz, dst, want));
+    }
     /* make at least n bytes available if possible; returns bytes available */
     size_t ensure(size_t n) {
         if (end - beg >= n) return end - beg;

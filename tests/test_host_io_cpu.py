@@ -42,3 +42,51 @@ def test_genome_loader_threads_and_content(built, tmp_path, monkeypatch):
     assert sum(len(s) for _, s in one) > 25_000_000
     for threads in (3, 8):
         assert _load(fa, threads, monkeypatch) == one
+
+
+def _extract(binary, workdir, tag, source, stdin_file=None, env=None):
+    """intron calls of `source` (a path, or None = standard input fed from stdin_file through a pipe)"""
+    import os
+    import subprocess
+    out = os.path.join(workdir, tag + ".tsv")
+    cmd = [binary, "--intron-calls=" + out, "-C", "0.0"] + ([source] if source else [])
+    e = dict(os.environ)
+    e.update(env or {})
+    if stdin_file is None:
+        proc = subprocess.run(cmd, cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+    else:
+        feeder = subprocess.Popen(["cat", stdin_file], stdout=subprocess.PIPE)  # a real pipe: not seekable
+        proc = subprocess.run(cmd, cwd=workdir, stdin=feeder.stdout, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+        feeder.stdout.close()
+        feeder.wait()
+    assert proc.returncode == 0, proc.stderr
+    return open(out, "rb").read()
+
+
+@pytest.mark.parametrize("binary", ["ORACLE_EXTRACT", "REF_EXTRACT"])
+def test_piped_input_of_every_kind(built, tmp_path, binary):
+    """SAM, gzipped SAM, BGZF BAM and uncompressed BAM through a pipe on standard input give what the files give --
+    with the BGZF decoder pool (the default) and with one decoding thread (the gzip stream reader)."""
+    import gzip
+    import subprocess
+    binary = getattr(helpers, binary)
+    tool = helpers.HTS_TOOL if hasattr(helpers, "HTS_TOOL") else helpers.REF_EXTRACT.replace("intronProspector", "hts_tool")
+    syn = Synth(60_000, kind=SHORT_UNSTRANDED, genome_len=50_000_000, n_genes=400, n_contigs=4)
+    raw = str(tmp_path / "raw.bam")
+    syn.write_raw_bam(raw)
+    syn.close()
+    bam, sam, samgz = str(tmp_path / "in.bam"), str(tmp_path / "in.sam"), str(tmp_path / "in.sam.gz")
+    subprocess.run([tool, "view-bam", raw, bam], check=True)
+    subprocess.run([tool, "view-sam", raw, sam], check=True)
+    with open(sam, "rb") as fi, gzip.open(samgz, "wb") as fo:
+        fo.write(fi.read())
+    want = _extract(binary, str(tmp_path), "file", bam)
+    assert want.count(b"\n") > 200
+    n = 0
+    for path in (bam, raw, sam, samgz):
+        for threads in ("4", "1"):
+            n += 1
+            got = _extract(binary, str(tmp_path), "pipe%d" % n, None, stdin_file=path, env={"IPX_DECODE_THREADS": threads})
+            assert got == want, (path, threads)
+            got = _extract(binary, str(tmp_path), "devstdin%d" % n, "/dev/stdin", stdin_file=path, env={"IPX_DECODE_THREADS": threads})
+            assert got == want, (path, threads)
