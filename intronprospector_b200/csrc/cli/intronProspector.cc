@@ -208,6 +208,12 @@ struct Input {
         if (out == NULL) throw runtime_error("Error opening BAM/SAM/CRAM file: " + path);
         if (sam_hdr_write(out, hdr) < 0) throw runtime_error("Error writing SAM header: " + path);
     }
+    /* BAM records can be packed where they lie in the reader's buffer, without building a bam1_t, when nobody needs
+     * the record itself afterwards (no pass-through, no per-read side output).  IPX_NO_RAW_PACK=1 turns that off. */
+    bool raw = false;
+    void enable_raw() { raw = hts_get_format(in)->format == bam && getenv("IPX_NO_RAW_PACK") == NULL; }
+    bool peek_raw(const uint8_t **rec_bytes, uint32_t *len) { return raw && ipx_bam_peek(in, rec_bytes, len) == 1; }
+    void consume_raw() { ipx_bam_consume(in); }
     /* read_align (junctions_extractor.cc:620-634) without the one-record read-ahead, which the caller keeps */
     bool read() {
         int stat = sam_read1(in, hdr, rec);
@@ -426,6 +432,18 @@ class Driver {
         next_seq_++;
         if (batch_.size() >= BATCH_RECORDS || batch_.cigar.size() >= BATCH_CIGAR) push();
     }
+    /* the same for a BAM record in the reader's buffer (Input::peek_raw) */
+    void process_raw(const uint8_t *rec, uint32_t len) {
+        int32_t tid;
+        memcpy(&tid, rec, 4);
+        if (tid >= 0 && (size_t)tid < canon_tid_.size()) tid = canon_tid_[tid];
+        if (segments_.empty() || segments_.back().second != tid) segments_.emplace_back(next_seq_, tid);
+        batch_.add_raw(rec, len, tid);
+        last_seq_ = next_seq_;
+        last_tid_ = tid;
+        next_seq_++;
+        if (batch_.size() >= BATCH_RECORDS || batch_.cigar.size() >= BATCH_CIGAR) push();
+    }
     void push() {
         if (batch_.size() == 0) return;
         if (batch_.compact_ok) {
@@ -494,23 +512,39 @@ static void extract_by_target(Driver &drv, const Options &opts, Outputs &out, An
     drv.add_targets(in.hdr);
     ann.input_opened();
     if (opts.bam_pass_through != "") in.open_pass_through(opts.bam_pass_through);
+    if (!ann.active() && in.out == NULL) in.enable_raw();
     const int n_targets = (int)drv.n_targets();
     int previous_target = -1;
     bool pending = false, eof = false;
     int stop_target = n_targets; /* targets [0, stop_target) get their output */
     string fatal;
+    /* the record in hand: in the reader's buffer (not consumed until it is processed) or in in.rec */
+    bool cur_raw = false;
+    const uint8_t *cur_bytes = NULL;
+    uint32_t cur_len = 0;
+    int32_t cur_tid = -1;
+    auto fetch = [&]() -> bool {
+        if (in.peek_raw(&cur_bytes, &cur_len)) {
+            cur_raw = true;
+            memcpy(&cur_tid, cur_bytes, 4);
+            return true;
+        }
+        if (!in.read()) return false;
+        cur_raw = false;
+        cur_tid = in.rec->core.tid;
+        return true;
+    };
     for (int target = 0; target < n_targets && fatal.empty(); target++) {
         for (;;) {
             if (!pending) {
-                if (eof || !in.read()) {
+                if (eof || !fetch()) {
                     eof = true;
                     break;
                 }
             }
             pending = false;
-            const bam1_t *aln = in.rec;
-            if (aln->core.tid != target) {
-                if ((aln->core.tid >= 0) and (aln->core.tid < previous_target)) {
+            if (cur_tid != target) {
+                if ((cur_tid >= 0) and (cur_tid < previous_target)) {
                     fatal = "BAM appears to not be coordinate sorted";
                     stop_target = target;
                     break;
@@ -518,6 +552,12 @@ static void extract_by_target(Driver &drv, const Options &opts, Outputs &out, An
                 pending = true;
                 break;
             }
+            if (cur_raw) {
+                drv.process_raw(cur_bytes, cur_len);
+                in.consume_raw();
+                continue;
+            }
+            const bam1_t *aln = in.rec;
             drv.process(aln);
             if (ann.active()) ann.keep(aln, drv.last_seq(), drv.last_tid(), true, true); /* written after the flush */
             else in.pass(aln);
@@ -567,7 +607,16 @@ static void extract_whole_files(Driver &drv, const Options &opts, Outputs &out, 
         /* in --unsorted mode the reference opens the pass-through file but only copy_unaligned_reads writes to it,
          * after every record has been consumed: the file gets the header only */
         if (opts.bam_files.size() == 1 && opts.bam_pass_through != "") in.open_pass_through(opts.bam_pass_through);
-        while (in.read()) {
+        if (!ann.active()) in.enable_raw();
+        for (;;) {
+            const uint8_t *bytes;
+            uint32_t len;
+            if (in.peek_raw(&bytes, &len)) {
+                drv.process_raw(bytes, len);
+                in.consume_raw();
+                continue;
+            }
+            if (!in.read()) break;
             drv.process(in.rec);
             if (ann.active()) ann.keep(in.rec, drv.last_seq(), drv.last_tid(), true, false);
         }

@@ -26,12 +26,16 @@ static size_t aux_size(const uint8_t *t, const uint8_t *end) {
     }
 }
 
+static void scan_tag_range(const uint8_t *a, const uint8_t *end, uint8_t *nh_class, uint8_t *xs);
+
 void scan_tags(const bam1_t *b, uint8_t *nh_class, uint8_t *xs) {
+    scan_tag_range(bam_get_aux(b), b->data + b->l_data, nh_class, xs);
+}
+
+static void scan_tag_range(const uint8_t *a, const uint8_t *end, uint8_t *nh_class, uint8_t *xs) {
     *nh_class = IPX_NH_NONE;
     *xs = IPX_XS_ABSENT;
     bool seen_nh = false, seen_xs = false;
-    const uint8_t *a = bam_get_aux(b);
-    const uint8_t *end = b->data + b->l_data;
     while (a + 2 < end && !(seen_nh && seen_xs)) {
         const uint8_t *t = a + 2;
         size_t vs = aux_size(t, end);
@@ -75,6 +79,42 @@ void ColumnarBatch::add(const bam1_t *b, int32_t mapped_tid) {
     xs.push_back(x);
     const uint32_t *c = bam_get_cigar(b);
     cigar.insert(cigar.end(), c, c + b->core.n_cigar);
+    cigar_off.push_back((uint32_t)cigar.size());
+}
+
+void ColumnarBatch::add_raw(const uint8_t *rec, uint32_t len, int32_t mapped_tid) {
+    int32_t p, l_seq;
+    uint16_t n_cigar, fl;
+    memcpy(&p, rec + 4, 4);
+    memcpy(&n_cigar, rec + 12, 2);
+    memcpy(&fl, rec + 14, 2);
+    memcpy(&l_seq, rec + 16, 4);
+    const uint8_t *cig = rec + 32 + rec[8];
+    const uint8_t *aux = cig + 4 * (size_t)n_cigar + (size_t)((l_seq + 1) / 2) + (size_t)l_seq;
+    uint8_t nh, x;
+    scan_tag_range(aux, rec + len, &nh, &x);
+    if (run_tid.empty() || run_tid.back() != mapped_tid) {
+        run_tid.push_back(mapped_tid);
+        run_start.push_back((uint64_t)tid.size());
+    }
+    n_cigar_ops.push_back(n_cigar);
+    tid.push_back(mapped_tid);
+    pos.push_back(p);
+    flag.push_back(fl);
+    nh_class.push_back(nh);
+    xs.push_back(x);
+    /* BAM is little-endian, and so is every host this runs on; the words may sit at any address in the buffer */
+    if (n_cigar <= 16) {
+        for (unsigned k = 0; k < n_cigar; k++) { /* short reads: cheaper than growing and copying */
+            uint32_t w;
+            memcpy(&w, cig + 4 * k, 4);
+            cigar.push_back(w);
+        }
+    } else {
+        const size_t at = cigar.size();
+        cigar.resize(at + n_cigar);
+        memcpy(cigar.data() + at, cig, 4 * (size_t)n_cigar);
+    }
     cigar_off.push_back((uint32_t)cigar.size());
 }
 

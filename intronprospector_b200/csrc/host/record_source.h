@@ -35,6 +35,9 @@ struct ColumnarBatch {
     }
     size_t size() const { return tid.size(); }
     void add(const bam1_t *b, int32_t mapped_tid);
+    /* the same straight from a BAM record in the reader's buffer (ipx_bam_peek: `rec` = the fixed 32-byte part,
+     * `len` = block_size), without building a bam1_t: position, flag, CIGAR words, and a scan of the tags for NH / XS */
+    void add_raw(const uint8_t *rec, uint32_t len, int32_t mapped_tid);
     ipx_batch view() const;
     ipx_batch_compact view_compact() const;
 };

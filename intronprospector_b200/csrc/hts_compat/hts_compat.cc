@@ -819,6 +819,40 @@ static int bam_read_record(ipx_hts_impl *im, bam1_t *b) {
     return 0;
 }
 
+extern "C" int ipx_bam_peek(samFile *fp, const uint8_t **rec, uint32_t *len) {
+    if (!fp || fp->is_write || fp->format.format != bam) return 0;
+    Reader &rd = fp->impl->rd;
+    if (rd.ensure(4) < 4) return 0;
+    int32_t block_len;
+    memcpy(&block_len, rd.buf.data() + rd.beg, 4);
+    if (block_len < 32) return 0;
+    if (rd.ensure(4 + (size_t)block_len) < 4 + (size_t)block_len) return 0;
+    const uint8_t *x = rd.buf.data() + rd.beg + 4;
+    int32_t l_seq;
+    memcpy(&l_seq, x + 16, 4);
+    uint16_t n_cigar;
+    memcpy(&n_cigar, x + 12, 2);
+    const size_t l_qname = x[8], rest = (size_t)block_len - 32;
+    if (l_seq < 0 || rest < l_qname) return 0;
+    if (l_qname + (size_t)n_cigar * 4 + (size_t)((l_seq + 1) / 2) + (size_t)l_seq > rest) return 0;
+    if (n_cigar == 2) {
+        /* "<l_seq>S<ref_len>N": the real CIGAR may sit in a CG:B,I tag (restore_long_cigar) */
+        uint32_t c0;
+        memcpy(&c0, x + 32 + l_qname, 4);
+        if ((c0 & 15u) == BAM_CSOFT_CLIP && (int32_t)(c0 >> 4) == l_seq) return 0;
+    }
+    *rec = x;
+    *len = (uint32_t)block_len;
+    return 1;
+}
+
+extern "C" void ipx_bam_consume(samFile *fp) {
+    Reader &rd = fp->impl->rd;
+    int32_t block_len;
+    memcpy(&block_len, rd.buf.data() + rd.beg, 4);
+    rd.beg += 4 + (size_t)block_len;
+}
+
 static const uint8_t *nt16_table() {
     static uint8_t tab[256];
     static bool init = false;

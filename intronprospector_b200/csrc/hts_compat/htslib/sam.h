@@ -123,6 +123,15 @@ char *bam_aux2Z(const uint8_t *s);
 int bam_aux_append(bam1_t *b, const char tag[2], char type, int len, const uint8_t *data);
 int bam_aux_del(bam1_t *b, uint8_t *s);
 
+/* ---- not htslib: an extension of this subset for the drop-in CLI's record packer ----
+ * The next BAM record where it lies in the reader's buffer.  ipx_bam_peek returns 1 and sets *rec to the record's
+ * fixed 32-byte part (the bytes after block_size) and *len to block_size when the whole record is buffered and
+ * well-formed; 0 when the caller has to use sam_read1 instead (not a BAM file, end of file, a truncated or malformed
+ * record, a CIGAR kept in the CG tag).  Nothing is consumed; the pointer is valid until the next read on fp.
+ * ipx_bam_consume steps over the record the last ipx_bam_peek returned. */
+int ipx_bam_peek(samFile *fp, const uint8_t **rec, uint32_t *len);
+void ipx_bam_consume(samFile *fp);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,3 +90,30 @@ def test_piped_input_of_every_kind(built, tmp_path, binary):
             assert got == want, (path, threads)
             got = _extract(binary, str(tmp_path), "devstdin%d" % n, "/dev/stdin", stdin_file=path, env={"IPX_DECODE_THREADS": threads})
             assert got == want, (path, threads)
+
+
+@pytest.mark.parametrize("kind", ["short", "long"])
+def test_records_packed_in_place_equal_records_through_bam1_t(built, tmp_path, kind):
+    """BAM records are packed where they lie in the reader's buffer (the default when nothing needs the record
+    afterwards); IPX_NO_RAW_PACK=1 goes through sam_read1 and a bam1_t.  Same junction calls either way, sorted mode
+    (with its per-target loop and its read-ahead) and --unsorted."""
+    import subprocess
+    from intronprospector_b200.synth import LONG
+    syn = Synth(5_000 if kind == "long" else 80_000, kind=LONG if kind == "long" else SHORT_UNSTRANDED, genome_len=50_000_000,
+                n_genes=400, n_contigs=4)
+    raw, bam = str(tmp_path / "raw.bam"), str(tmp_path / "in.bam")
+    syn.write_raw_bam(raw)
+    syn.close()
+    subprocess.run([helpers.HTS_TOOL, "view-bam", raw, bam], check=True)
+    for extra in ([], ["--unsorted"]):
+        outs = []
+        for env in ({}, {"IPX_NO_RAW_PACK": "1"}):
+            import os
+            out = str(tmp_path / "o.tsv")
+            e = dict(os.environ)
+            e.update(env)
+            proc = subprocess.run([helpers.ORACLE_EXTRACT, "--intron-calls=" + out, "-C", "0.0", "--allow-anchor-indels"] + extra + [bam],
+                                  stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+            assert proc.returncode == 0, proc.stderr
+            outs.append(open(out, "rb").read())
+        assert outs[0] == outs[1] and outs[0].count(b"\n") > 100
