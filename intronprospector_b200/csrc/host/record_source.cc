@@ -90,9 +90,30 @@ void ColumnarBatch::add_raw(const uint8_t *rec, uint32_t len, int32_t mapped_tid
     memcpy(&fl, rec + 14, 2);
     memcpy(&l_seq, rec + 16, 4);
     const uint8_t *cig = rec + 32 + rec[8];
-    const uint8_t *aux = cig + 4 * (size_t)n_cigar + (size_t)((l_seq + 1) / 2) + (size_t)l_seq;
-    uint8_t nh, x;
-    scan_tag_range(aux, rec + len, &nh, &x);
+    /* BAM is little-endian, and so is every host this runs on; the words may sit at any address in the buffer */
+    bool has_intron = false;
+    if (n_cigar <= 16) {
+        for (unsigned k = 0; k < n_cigar; k++) { /* short reads: cheaper than growing and copying */
+            uint32_t w;
+            memcpy(&w, cig + 4 * k, 4);
+            has_intron |= (w & 15u) == 3u;
+            cigar.push_back(w);
+        }
+    } else {
+        const size_t at = cigar.size();
+        cigar.resize(at + n_cigar);
+        memcpy(cigar.data() + at, cig, 4 * (size_t)n_cigar);
+        has_intron = true; /* not worth a second pass: look at the tags */
+    }
+    cigar_off.push_back((uint32_t)cigar.size());
+    /* NH and XS only ever matter for a read that yields a junction candidate, and that takes an N operation
+     * (ReadJunctionExtractor, junctions_extractor.cc:208-229): most reads of an RNA-Seq file have none, and their
+     * tags -- a dozen per record in aligner output -- need not be walked */
+    uint8_t nh = IPX_NH_NONE, x = IPX_XS_ABSENT;
+    if (has_intron) {
+        const uint8_t *aux = cig + 4 * (size_t)n_cigar + (size_t)((l_seq + 1) / 2) + (size_t)l_seq;
+        scan_tag_range(aux, rec + len, &nh, &x);
+    }
     if (run_tid.empty() || run_tid.back() != mapped_tid) {
         run_tid.push_back(mapped_tid);
         run_start.push_back((uint64_t)tid.size());
@@ -103,19 +124,6 @@ void ColumnarBatch::add_raw(const uint8_t *rec, uint32_t len, int32_t mapped_tid
     flag.push_back(fl);
     nh_class.push_back(nh);
     xs.push_back(x);
-    /* BAM is little-endian, and so is every host this runs on; the words may sit at any address in the buffer */
-    if (n_cigar <= 16) {
-        for (unsigned k = 0; k < n_cigar; k++) { /* short reads: cheaper than growing and copying */
-            uint32_t w;
-            memcpy(&w, cig + 4 * k, 4);
-            cigar.push_back(w);
-        }
-    } else {
-        const size_t at = cigar.size();
-        cigar.resize(at + n_cigar);
-        memcpy(cigar.data() + at, cig, 4 * (size_t)n_cigar);
-    }
-    cigar_off.push_back((uint32_t)cigar.size());
 }
 
 ipx_batch ColumnarBatch::view() const {
