@@ -117,3 +117,46 @@ def test_records_packed_in_place_equal_records_through_bam1_t(built, tmp_path, k
             assert proc.returncode == 0, proc.stderr
             outs.append(open(out, "rb").read())
         assert outs[0] == outs[1] and outs[0].count(b"\n") > 100
+
+
+def test_aligner_style_tags_in_place_and_through_bam1_t(built, tmp_path):
+    """Records that carry a dozen tags the way aligners write them (integers of several widths, strings, arrays, XS on
+    spliced reads only, NH in the middle): the in-place packer, the bam1_t packer and the unmodified reference agree."""
+    import os
+    import subprocess
+    import numpy as np
+    syn = Synth(40_000, kind=SHORT_UNSTRANDED, genome_len=50_000_000, n_genes=300, n_contigs=3)
+    raw, sam, sam2, bam = (str(tmp_path / n) for n in ("raw.bam", "plain.sam", "tagged.sam", "tagged.bam"))
+    syn.write_raw_bam(raw)
+    syn.close()
+    subprocess.run([helpers.HTS_TOOL, "view-sam", raw, sam], check=True)
+    rng = np.random.default_rng(3)
+    with open(sam) as fi, open(sam2, "w") as fo:
+        for line in fi:
+            if line.startswith("@"):
+                fo.write(line)
+                continue
+            f = line.rstrip("\n").split("\t")
+            core, tags = f[:11], [t for t in f[11:] if not t.startswith(("NH:", "XS:"))]
+            spliced = "N" in core[5]
+            nh = int(rng.choice([1, 1, 1, 2, 5, 300, 70000]))
+            new = ["HI:i:1", "AS:i:%d" % rng.integers(0, 300), "nM:i:%d" % rng.integers(0, 5), "NH:i:%d" % nh,
+                   "MD:Z:%d" % rng.integers(1, 150), "jM:B:c,%d" % (-1 if not spliced else 1), "jI:B:i,%d,%d" % (10, 20)]
+            if spliced and rng.random() < 0.8:
+                new.append("XS:A:%s" % rng.choice(["+", "-"]))
+            new.append("RG:Z:sample1")
+            fo.write("\t".join(core + tags + new) + "\n")
+    subprocess.run([helpers.HTS_TOOL, "view-bam", sam2, bam], check=True)
+    outs = {}
+    for tag, binary, env in (("ref", helpers.REF_EXTRACT, {}), ("raw", helpers.ORACLE_EXTRACT, {}),
+                             ("bam1_t", helpers.ORACLE_EXTRACT, {"IPX_NO_RAW_PACK": "1"})):
+        e = dict(os.environ)
+        e.update(env)
+        out = str(tmp_path / (tag + ".tsv"))
+        proc = subprocess.run([binary, "--intron-calls=" + out, "-C", "0.0", "--exclude=multi", bam], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, env=e)
+        assert proc.returncode == 0, proc.stderr
+        outs[tag] = open(out, "rb").read()
+    assert outs["ref"].count(b"\n") > 100
+    assert outs["raw"] == outs["ref"]
+    assert outs["bam1_t"] == outs["ref"]
