@@ -160,3 +160,40 @@ def test_aligner_style_tags_in_place_and_through_bam1_t(built, tmp_path):
     assert outs["ref"].count(b"\n") > 100
     assert outs["raw"] == outs["ref"]
     assert outs["bam1_t"] == outs["ref"]
+
+
+def test_reference_inputs_as_bam_through_both_packers(built, tmp_path):
+    """Every SAM input of the reference's own test suite, converted to BAM: sorted mode (with its per-target loop,
+    out-of-order and skipped targets, the sortedness error) and --unsorted, records packed in place and through bam1_t
+    -- return code, messages and all outputs as the unmodified reference gives them."""
+    import os
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(helpers.REPO, "tests", "golden"))
+    import runner
+    work = runner.unpack_fixtures(str(tmp_path / "fx"))
+    sams = sorted(f for f in os.listdir(os.path.join(work, "input")) if f.endswith(".sam"))
+    assert len(sams) >= 8
+    checked = 0
+    for name in sams:
+        bam = str(tmp_path / (name[:-4] + ".bam"))
+        if subprocess.run([helpers.HTS_TOOL, "view-bam", os.path.join(work, "input", name), bam]).returncode != 0:
+            continue  # an input the writer cannot represent
+        for extra in ([], ["--unsorted"]):
+            runs = {}
+            for tag, binary, env in (("ref", helpers.REF_EXTRACT, {}), ("in_place", helpers.ORACLE_EXTRACT, {}),
+                                     ("bam1_t", helpers.ORACLE_EXTRACT, {"IPX_NO_RAW_PACK": "1"})):
+                e = dict(os.environ)
+                e.update(env)
+                d = tmp_path / ("%s.%s.%d" % (name, tag, len(extra)))
+                d.mkdir()
+                out = {s: str(d / s) for s in ("introns.tsv", "juncs.bed", "introns.bed")}
+                proc = subprocess.run([binary, "--intron-calls=" + out["introns.tsv"], "--junction-bed=" + out["juncs.bed"],
+                                       "--intron-bed=" + out["introns.bed"], "-C", "0.0"] + extra + [bam],
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+                runs[tag] = (proc.returncode, proc.stderr,
+                             {s: (open(p, "rb").read() if os.path.exists(p) else None) for s, p in out.items()})
+            for tag in ("in_place", "bam1_t"):
+                assert runs[tag] == runs["ref"], (name, extra, tag)
+            checked += 1
+    assert checked >= 16
