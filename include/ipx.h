@@ -163,6 +163,9 @@ typedef struct ipx_timings {
     uint64_t hist_runs;  /* R  histogram runs in flushed tables */
     uint64_t motif_keys; /* U  keys evaluated against the genome */
     uint64_t merge_rows; /* rows folded by ipx_merge_rows */
+    double export_ms;    /* multi-GPU exchange: rows of junctions other ranks own stored into their mailboxes */
+    double import_ms;    /* ... wait for every source's export (device-side) + fold of what arrived */
+    uint64_t exchange_launches;
 } ipx_timings;
 
 /* Text produced by the formatters; free with ipx_text_free. */
@@ -273,6 +276,15 @@ void *ipx_mailbox_ptr(ipx_handle *h);
 int ipx_mailbox_connect(ipx_handle *h, int32_t ipc, const void *peers);
 int ipx_partial_export_mail(ipx_handle *h, const int32_t *split_tid, const uint32_t *split_start);
 int ipx_partial_import_mail(ipx_handle *h);
+/* The export is enqueued without a host round trip, i.e. before the host knows whether the fold of the last batch was
+ * complete (a junction table that fills up is grown and the fold repeated, lazily).  ipx_exchange_settle (every rank,
+ * before ipx_flush) waits for this rank's work and reports in *repeat_exchange whether events were folded after its
+ * export: if any rank reports 1, every rank repeats ipx_partial_export_mail / ipx_partial_import_mail (cheap: only
+ * what is still held for other ranks moves).  ipx_flush refuses to return a table that skipped this. */
+int ipx_exchange_settle(ipx_handle *h, int32_t *repeat_exchange);
+/* Every stride-th junction key of the local table (target index, intron start), at most max_keys, into host arrays:
+ * a sample for load-balanced key-range splitters.  Synchronises. */
+int ipx_sample_keys(ipx_handle *h, uint64_t stride, uint64_t max_keys, int32_t *tid, uint32_t *intron_start, uint64_t *n_keys);
 
 /* Multi-GPU with the canon filter.  Which event creates a junction (add_junction, junctions_extractor.cc:488-506) depends
  * on every earlier read of the whole stream, so with ipx_params.deferred_counting the ranks first agree on it:

@@ -117,6 +117,9 @@ class Timings(C.Structure):
         ("hist_runs", C.c_uint64),
         ("motif_keys", C.c_uint64),
         ("merge_rows", C.c_uint64),
+        ("export_ms", C.c_double),
+        ("import_ms", C.c_double),
+        ("exchange_launches", C.c_uint64),
     ]
 
 
@@ -149,7 +152,7 @@ ABI_SYMBOLS = [
     "ipx_get_timings", "ipx_reset_timings", "ipx_stream", "ipx_thresholds_rows", "ipx_thresholds_export",
     "ipx_thresholds_import", "ipx_count_deferred", "ipx_table_set_ijunc", "ipx_push_batch_compact",
     "ipx_mailbox_create", "ipx_mailbox_ipc_handle", "ipx_mailbox_ptr", "ipx_mailbox_connect", "ipx_partial_export_mail",
-    "ipx_partial_import_mail",
+    "ipx_partial_import_mail", "ipx_exchange_settle", "ipx_sample_keys",
 ]
 IO_SYMBOLS = [
     "ipxio_last_error", "ipxio_open", "ipxio_close", "ipxio_n_targets", "ipxio_target_name", "ipxio_read_batch",
@@ -206,6 +209,8 @@ def _bind(lib):
     lib.ipx_mailbox_connect.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.ipx_partial_export_mail.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]
     lib.ipx_partial_import_mail.argtypes = [C.c_void_p]
+    lib.ipx_exchange_settle.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    lib.ipx_sample_keys.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
 
 
 def load_library(path=None):
@@ -560,6 +565,21 @@ class Engine:
 
     def partial_import_mail(self):
         self._check(self.lib.ipx_partial_import_mail(self.h))
+
+    def exchange_settle(self):
+        """Wait for this rank's share of the exchange; True when events were folded after its export (a table had been
+        full): every rank then repeats the exchange before flushing."""
+        r = C.c_int32()
+        self._check(self.lib.ipx_exchange_settle(self.h, C.byref(r)))
+        return bool(r.value)
+
+    def sample_keys(self, stride=1, max_keys=1 << 16):
+        """Every stride-th junction key of the local table as (target index, intron start) arrays."""
+        tid = np.empty(max_keys, np.int32)
+        i0 = np.empty(max_keys, np.uint32)
+        n = C.c_uint64()
+        self._check(self.lib.ipx_sample_keys(self.h, stride, max_keys, tid.ctypes.data, i0.ctypes.data, C.byref(n)))
+        return tid[:n.value], i0[:n.value]
 
     def thresholds_rows(self):
         n, b = C.c_uint64(), C.c_uint32()

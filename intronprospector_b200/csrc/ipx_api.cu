@@ -1,7 +1,7 @@
 /* ipx_api.cu -- implementation of the C ABI in include/ipx.h on top of the CUDA engine.
  * CUDA-only: every compute entry point fails with IPX_ERR_CUDA when no device is usable.
  */
-#include <cub/cub.cuh>
+#include <cub/cub.cuh> /* the merge fold still orders its keys with the library sort */
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -137,6 +137,8 @@ struct StageTimer {
     uint64_t launches = 0;
 };
 
+static const size_t COUNTER_WORDS = 16 * 16; /* 16 cache lines of counters and flags */
+
 }  // namespace
 
 struct ipx_handle {
@@ -151,7 +153,8 @@ struct ipx_handle {
     /* tables */
     Tables tab{};
     bool tables_ready = false;
-    unsigned long long *d_counters = nullptr; /* 8 x 128-byte lines */
+    unsigned long long *d_counters = nullptr; /* COUNTER_WORDS: one 128-byte line per counter */
+    unsigned long long *h_flags = nullptr;    /* pinned: counters / flags read back from the device */
     bool dirty = false;                       /* events folded since the last clear */
 
     /* targets / genome */
@@ -174,7 +177,15 @@ struct ipx_handle {
     DeviceBuf s_nops, s_runs, s_tmp; /* compact batches: operation counts, target runs, scan scratch */
     DeviceBuf ev_buf;   /* junction events of the batch in flight (K1 -> K2), one region per tile */
     DeviceBuf tile_cnt; /* TileInfo per tile */
-    DeviceBuf long_buf; /* LongRec regions (records handed from the pipelined kernel to k_extract_long) */
+    /* The last batch folded with the events still in ev_buf / tile_cnt: when a table turns out to have been full
+     * (overflow flag, read back lazily) the host grows it and repeats the fold, which picks up exactly the events
+     * that were left (see k_fold). */
+    bool unsettled = false;
+    uint64_t unsettled_tiles = 0;
+    bool import_pending = false;         /* ipx_partial_import_mail enqueued, its verdict not read yet */
+    bool exported_unsettled = false;     /* an export went out before the last batch's fold was known to be complete */
+    bool late_fold = false;              /* ... and it was not: events were folded after the export (ipx_exchange_settle) */
+    uint64_t log_bound = 0; /* upper bound of the log entries written since the last clear (sizes the log ahead of a batch) */
     /* deferred counting (multi-GPU with the canon filter): the events of every batch pushed since the last count */
     struct Deferred {
         void *events;
@@ -193,8 +204,10 @@ struct ipx_handle {
     unsigned long long export_counts[2 * MAX_PARTS + 4] = {}; /* + keys, log entries, overflow flag */
     unsigned long long export_cursors[2 * MAX_PARTS] = {};
     uint64_t export_keys = 1 << 16, export_olog = 1 << 16; /* launch bounds of the export passes (grow-only) */
-    DeviceBuf slot_jrow; /* [cap] export: junction-row index of each slot */
-    DeviceBuf slot_of;   /* import: table slot of each received junction row */
+    DeviceBuf jrow_of;  /* [max_j] export: owner << 24 | junction-row index of each junction */
+    DeviceBuf jid_of;   /* import: junction id of each received junction row */
+    unsigned long long mail_timeout_ns = 20ull * 1000 * 1000 * 1000; /* a peer that never publishes: give up */
+    StageTimer tm_export, tm_import;
     bool export_ready = false;
     uint64_t seq_hi = 0; /* one past the largest record stream index pushed so far */
 
@@ -286,43 +299,157 @@ uint64_t pow2_at_least(uint64_t v) {
     return p;
 }
 
-int alloc_tables(ipx_handle *h) {
-    if (h->tables_ready) return IPX_OK;
-    uint64_t want_cap = h->params.table_capacity ? h->params.table_capacity : (1ull << 22);
-    if (const char *e = getenv("IPX_TABLE_CAP")) want_cap = strtoull(e, nullptr, 10); /* experiments */
-    uint64_t cap = pow2_at_least(want_cap);
-    uint64_t hcap = h->params.hist_capacity ? std::max<uint64_t>(h->params.hist_capacity, 1024) : (1ull << 26);
-    if (cap > (1ull << 31)) return fail(h, IPX_ERR_ARG, "table_capacity too large");
+void set_counter_pointers(ipx_handle *h) {
     Tables &t = h->tab;
-    CU(h, cudaMalloc(&t.keys, cap * sizeof(unsigned long long)));
-    CU(h, cudaMalloc(&t.stat, cap * sizeof(JStat)));
-    CU(h, cudaMalloc(&t.olog, hcap * sizeof(unsigned long long)));
-    t.olog_cap = hcap;
-    CU(h, cudaMalloc(&t.slot_list, cap * sizeof(uint32_t)));
-    CU(h, cudaMalloc(&t.slot_id, cap * sizeof(uint32_t)));
-    /* dense offset rows: 1 KB per slot, so up to 16 GB of the 180 GB; beyond that every offset goes to the hash */
-    t.dense = nullptr;
-    if (cap <= (1ull << 24) && !getenv("IPX_NO_DENSE")) {
-        CU(h, cudaMalloc(&t.dense, cap * DENSE_W * sizeof(uint32_t)));
-        CU(h, cudaMemsetAsync(t.dense, 0, cap * DENSE_W * sizeof(uint32_t), h->stream));
-    }
-    CU(h, cudaMalloc(&h->d_counters, 8 * 128));
-    CU(h, cudaMemsetAsync(h->d_counters, 0, 8 * 128, h->stream));
-    t.cap_mask = cap - 1;
     t.n_keys = h->d_counters + 0;
     t.n_olog = h->d_counters + 16;
     t.n_events = h->d_counters + 32;
     t.n_live = h->d_counters + 48;
     t.err_sv = h->d_counters + 64;
     t.overflow = (uint32_t *)(h->d_counters + 80);
-    const int L = bits_for(h->params.max_intron_length);
-    t.kl.len_bits = L;
-    t.kl.start_shift = L;
-    t.kl.tid_shift = L + 31;
-    t.kl.tid_bits = 63 - t.kl.tid_shift;
+    t.n_unfolded = h->d_counters + 128;
+}
+
+int alloc_counters(ipx_handle *h) {
+    if (h->d_counters) return IPX_OK;
+    CU(h, cudaMalloc(&h->d_counters, COUNTER_WORDS * sizeof(unsigned long long)));
+    CU(h, cudaMemsetAsync(h->d_counters, 0, COUNTER_WORDS * sizeof(unsigned long long), h->stream));
+    if (!h->h_flags) CU(h, cudaMallocHost(&h->h_flags, 8 * sizeof(unsigned long long)));
+    return IPX_OK;
+}
+
+/* the junction rows: everything indexed by junction id */
+int alloc_rows(ipx_handle *h, Tables &t, uint64_t max_j, bool dense) {
+    t.max_j = max_j;
+    CU(h, cudaMalloc(&t.jkey, max_j * sizeof(unsigned long long)));
+    CU(h, cudaMalloc(&t.jtid, max_j * sizeof(int32_t)));
+    CU(h, cudaMalloc(&t.jslot, max_j * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&t.stat, max_j * sizeof(JStat)));
+    CU(h, cudaMalloc(&t.olog_cnt, max_j * sizeof(uint32_t)));
+    t.dense = nullptr;
+    /* dense offset rows: 1 KB per junction */
+    if (dense) CU(h, cudaMalloc(&t.dense, max_j * DENSE_W * sizeof(uint32_t)));
+    return IPX_OK;
+}
+
+void free_rows(Tables &t) {
+    cudaFree(t.jkey); cudaFree(t.jtid); cudaFree(t.jslot); cudaFree(t.stat); cudaFree(t.olog_cnt); cudaFree(t.dense);
+    t.jkey = nullptr; t.jtid = nullptr; t.jslot = nullptr; t.stat = nullptr; t.olog_cnt = nullptr; t.dense = nullptr;
+}
+
+int alloc_tables(ipx_handle *h) {
+    if (h->tables_ready) return IPX_OK;
+    /* table_capacity = hash slots; at most half of them are used, so half as many junction rows.  Both grow on demand. */
+    uint64_t want_cap = h->params.table_capacity ? h->params.table_capacity : (1ull << 22);
+    uint64_t cap = pow2_at_least(want_cap);
+    uint64_t hcap = h->params.hist_capacity ? std::max<uint64_t>(h->params.hist_capacity, 1024) : (1ull << 26);
+    if (cap > (1ull << 31)) return fail(h, IPX_ERR_ARG, "table_capacity too large");
+    int rc = alloc_counters(h);
+    if (rc) return rc;
+    Tables &t = h->tab;
+    CU(h, cudaMalloc(&t.keys, cap * sizeof(unsigned long long)));
+    CU(h, cudaMalloc(&t.jid, cap * sizeof(uint32_t)));
+    t.cap_mask = cap - 1;
+    rc = alloc_rows(h, t, cap / 2, !getenv("IPX_NO_DENSE"));
+    if (rc) return rc;
+    CU(h, cudaMalloc(&t.olog, hcap * sizeof(unsigned long long)));
+    t.olog_cap = hcap;
+    set_counter_pointers(h);
+    t.kl = make_key_layout(bits_for(h->params.max_intron_length), h->targets.size());
     launch_init_tables(t, h->stream);
     CU(h, cudaGetLastError());
     h->tables_ready = true;
+    return IPX_OK;
+}
+
+/* ---- growth: nothing here is on the steady-state path ---- */
+/* twice the junction rows (prefix copy of what is in use; the new rows get the reset values) */
+int grow_rows(ipx_handle *h, uint64_t in_use) {
+    Tables old = h->tab, &t = h->tab;
+    const uint64_t max_j = old.max_j * 2;
+    if (max_j >> 31) return fail(h, IPX_ERR_CAPACITY, "more than 2^31 junctions");
+    int rc = alloc_rows(h, t, max_j, old.dense != nullptr);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    CU(h, cudaMemcpyAsync(t.jkey, old.jkey, in_use * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    CU(h, cudaMemcpyAsync(t.jtid, old.jtid, in_use * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    CU(h, cudaMemcpyAsync(t.jslot, old.jslot, in_use * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    CU(h, cudaMemcpyAsync(t.stat, old.stat, in_use * sizeof(JStat), cudaMemcpyDeviceToDevice, st));
+    CU(h, cudaMemcpyAsync(t.olog_cnt, old.olog_cnt, in_use * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    if (t.dense) CU(h, cudaMemcpyAsync(t.dense, old.dense, in_use * DENSE_W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    launch_init_rows(t, in_use, st);
+    CU(h, cudaStreamSynchronize(st));
+    free_rows(old);
+    return IPX_OK;
+}
+
+/* fresh hash slots (twice as many when `twice`), every junction row inserted again */
+int rebuild_slots(ipx_handle *h, bool twice) {
+    Tables &t = h->tab;
+    const uint64_t cap = (t.cap_mask + 1) * (twice ? 2 : 1);
+    if (cap > (1ull << 32)) return fail(h, IPX_ERR_CAPACITY, "junction hash table beyond 2^32 slots");
+    if (twice) {
+        cudaFree(t.keys); cudaFree(t.jid);
+        t.keys = nullptr; t.jid = nullptr;
+        CU(h, cudaMalloc(&t.keys, cap * sizeof(unsigned long long)));
+        CU(h, cudaMalloc(&t.jid, cap * sizeof(uint32_t)));
+        t.cap_mask = cap - 1;
+    }
+    CU(h, cudaMemsetAsync(t.keys, 0xFF, cap * sizeof(unsigned long long), h->stream));
+    CU(h, cudaMemsetAsync(t.jid, 0xFF, cap * sizeof(uint32_t), h->stream));
+    launch_rehash(t, h->stream);
+    CU(h, cudaGetLastError());
+    return IPX_OK;
+}
+
+int grow_log(ipx_handle *h, uint64_t in_use, uint64_t want) {
+    Tables &t = h->tab;
+    uint64_t cap = t.olog_cap;
+    while (cap < want) cap *= 2;
+    if (cap >> 32) return fail(h, IPX_ERR_CAPACITY, "read-offset log beyond 2^32 entries");
+    unsigned long long *fresh = nullptr;
+    CU(h, cudaMalloc(&fresh, cap * sizeof(unsigned long long)));
+    if (in_use) CU(h, cudaMemcpyAsync(fresh, t.olog, in_use * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    cudaFree(t.olog);
+    t.olog = fresh;
+    t.olog_cap = cap;
+    return IPX_OK;
+}
+
+/* counters and flags of the tables, on the host (synchronises the stream) */
+struct TableState {
+    unsigned long long n_keys, n_olog, n_unfolded;
+    uint32_t overflow;
+};
+int read_table_state(ipx_handle *h, TableState *out) {
+    unsigned long long *f = h->h_flags;
+    cudaStream_t st = h->stream;
+    CU(h, cudaMemcpyAsync(&f[0], h->tab.n_keys, 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(&f[1], h->tab.n_olog, 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(&f[2], h->tab.n_unfolded, 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaMemcpyAsync(&f[3], h->tab.overflow, 4, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    out->n_keys = f[0]; out->n_olog = f[1]; out->n_unfolded = f[2]; out->overflow = (uint32_t)f[3];
+    return IPX_OK;
+}
+
+/* make room for `bound` more log entries (an upper bound of what the next launches can write) */
+int ensure_log(ipx_handle *h, uint64_t bound) {
+    if (h->log_bound + bound <= h->tab.olog_cap) {
+        h->log_bound += bound;
+        return IPX_OK;
+    }
+    /* the bound is loose (one entry per two CIGAR words): see what is really there before growing */
+    TableState ts;
+    int rc = read_table_state(h, &ts);
+    if (rc) return rc;
+    const uint64_t in_use = std::min<uint64_t>(ts.n_olog, h->tab.olog_cap);
+    if (in_use + bound > h->tab.olog_cap) {
+        rc = grow_log(h, in_use, in_use + bound);
+        if (rc) return rc;
+    }
+    h->log_bound = in_use + bound;
     return IPX_OK;
 }
 
@@ -392,6 +519,78 @@ void free_genome(ipx_handle *h) {
     h->have_genome = false;
 }
 
+/* K2 (and K3 with the canon filter) over events that are on the device */
+void fold_events(ipx_handle *h, Event *events, TileInfo *tile_info, uint64_t n_tiles) {
+    if (two_pass(h)) {
+        {
+            Span s(h, &h->tm_aggregate, 1);
+            launch_fold(MODE_PASS1, h->tab, events, tile_info, n_tiles, h->sm_count, h->stream);
+        }
+        {
+            Span s(h, &h->tm_motif, 1);
+            launch_resolve_T(h->tab, genome_view(h), h->stream);
+        }
+        {
+            Span s(h, &h->tm_aggregate, 1);
+            launch_fold(MODE_PASS2, h->tab, events, tile_info, n_tiles, h->sm_count, h->stream);
+        }
+    } else {
+        Span s(h, &h->tm_aggregate, 1);
+        launch_fold(MODE_SINGLE, h->tab, events, tile_info, n_tiles, h->sm_count, h->stream);
+    }
+}
+
+/* Give the tables room and repeat `again` (the launches that met the full table) until nothing is left over.
+ * Rows are doubled when the junction ids ran out; the hash slots are rebuilt either way (slots claimed while no row was
+ * left are dropped by that) and doubled when more than half of them would be in use. */
+template <class Again>
+int grow_and_repeat(ipx_handle *h, TableState ts, Again again) {
+    for (int round = 0; round < 40 && (ts.overflow & (OVF_TABLE | OVF_LOG)); round++) {
+        launch_settle_counters(h->tab, h->stream);
+        const uint64_t in_use = std::min<uint64_t>(ts.n_keys, h->tab.max_j);
+        int rc = IPX_OK;
+        if (ts.overflow & OVF_LOG) rc = grow_log(h, std::min<uint64_t>(ts.n_olog, h->tab.olog_cap), h->tab.olog_cap * 2);
+        if (rc) return rc;
+        if (ts.overflow & OVF_TABLE) {
+            if (ts.n_keys >= h->tab.max_j) rc = grow_rows(h, in_use);
+            if (rc) return rc;
+            rc = rebuild_slots(h, 2 * h->tab.max_j > h->tab.cap_mask + 1 || 4 * in_use > h->tab.cap_mask + 1);
+            if (rc) return rc;
+        }
+        rc = again();
+        if (rc) return rc;
+        rc = read_table_state(h, &ts);
+        if (rc) return rc;
+    }
+    if (ts.overflow & (OVF_TABLE | OVF_LOG)) return fail(h, IPX_ERR_CAPACITY, "the junction table could not be grown far enough");
+    return IPX_OK;
+}
+
+/* Was a table full while the last batch was folded?  Then grow it and fold what was left.  Called before the batch's
+ * event buffer is used again and before results are read; costs one host round trip. */
+int settle_batch(ipx_handle *h, bool *repeated = nullptr) {
+    if (repeated) *repeated = false;
+    if (!h->unsettled) return IPX_OK;
+    TableState ts;
+    int rc = read_table_state(h, &ts);
+    if (rc) return rc;
+    h->unsettled = false;
+    if (!(ts.overflow & (OVF_TABLE | OVF_LOG))) {
+        h->exported_unsettled = false;
+        return IPX_OK;
+    }
+    if (repeated) *repeated = true;
+    if (h->exported_unsettled) h->late_fold = true; /* what is folded now may belong to another rank */
+    Event *events = (Event *)h->ev_buf.p;
+    TileInfo *tile_info = (TileInfo *)h->tile_cnt.p;
+    const uint64_t n_tiles = h->unsettled_tiles;
+    return grow_and_repeat(h, ts, [&]() {
+        fold_events(h, events, tile_info, n_tiles);
+        cudaError_t e = cudaGetLastError();
+        return e == cudaSuccess ? IPX_OK : fail(h, IPX_ERR_CUDA, "CUDA error %s while repeating a fold", cudaGetErrorName(e));
+    });
+}
+
 int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
     if (h->finalized) return fail(h, IPX_ERR_STATE, "ipx_push_batch after ipx_finalize_device without ipx_flush");
     if (h->targets.empty()) return fail(h, IPX_ERR_STATE, "ipx_set_targets must be called before ipx_push_batch");
@@ -401,9 +600,10 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
     /* event buffer for the worst case: every emitted candidate consumes one N op and a following aligned op */
     const uint64_t ev_bound = n_cigar / 2 + 1;
     const uint64_t n_tiles = tiles_of(b.n);
-    /* only the optional two-kernel variant of K1 (IPX_K1_SPLIT_LONG) hands records over through this buffer */
-    static const bool split_long = getenv("IPX_K1_SPLIT_LONG") != nullptr;
-    if (split_long) CU(h, h->long_buf.reserve((n_cigar / 4 + 2) * sizeof(LongRec), h->stream));
+    rc = settle_batch(h); /* the previous batch's events are about to be overwritten */
+    if (rc) return rc;
+    rc = ensure_log(h, ev_bound);
+    if (rc) return rc;
     if (h->params.deferred_counting && two_pass(h)) {
         /* K1 and the first-seen pass only; the events stay on the device until ipx_count_deferred */
         ipx_handle::Deferred d{nullptr, nullptr, n_tiles};
@@ -413,13 +613,13 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
         {
             Span s(h, &h->tm_extract, 0);
             int launched = 0;
-            CU(h, launch_extract(b, n_cigar, h->xp, h->tab, (Event *)d.events, (TileInfo *)d.tile_info, (LongRec *)h->long_buf.p,
-                                 h->d_counters + 96, h->sm_count, h->stream, &launched));
+            CU(h, launch_extract(b, n_cigar, h->xp, h->tab, (Event *)d.events, (TileInfo *)d.tile_info, h->d_counters + 96,
+                                 h->sm_count, h->stream, &launched));
             h->tm_extract.launches += (uint64_t)launched;
         }
         {
             Span s(h, &h->tm_aggregate, 1);
-            launch_fold(MODE_PASS1, h->tab, (const Event *)d.events, (const TileInfo *)d.tile_info, n_tiles, h->sm_count, h->stream);
+            launch_fold(MODE_PASS1, h->tab, (Event *)d.events, (TileInfo *)d.tile_info, n_tiles, h->sm_count, h->stream);
         }
         CU(h, cudaGetLastError());
         h->totals.records += b.n;
@@ -429,33 +629,17 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
     }
     CU(h, h->ev_buf.reserve(ev_bound * sizeof(Event), h->stream));
     CU(h, h->tile_cnt.reserve((n_tiles + 1) * sizeof(TileInfo), h->stream));
-    TileInfo *tile_count = (TileInfo *)h->tile_cnt.p;
-    const Event *events = (const Event *)h->ev_buf.p;
     {
         Span s(h, &h->tm_extract, 0);
         int launched = 0;
-        CU(h, launch_extract(b, n_cigar, h->xp, h->tab, (Event *)h->ev_buf.p, tile_count, (LongRec *)h->long_buf.p, h->d_counters + 96,
+        CU(h, launch_extract(b, n_cigar, h->xp, h->tab, (Event *)h->ev_buf.p, (TileInfo *)h->tile_cnt.p, h->d_counters + 96,
                              h->sm_count, h->stream, &launched));
         h->tm_extract.launches += (uint64_t)launched;
     }
-    if (two_pass(h)) {
-        {
-            Span s(h, &h->tm_aggregate, 1);
-            launch_fold(MODE_PASS1, h->tab, events, tile_count, n_tiles, h->sm_count, h->stream);
-        }
-        {
-            Span s(h, &h->tm_motif, 1);
-            launch_resolve_T(h->tab, genome_view(h), h->stream);
-        }
-        {
-            Span s(h, &h->tm_aggregate, 1);
-            launch_fold(MODE_PASS2, h->tab, events, tile_count, n_tiles, h->sm_count, h->stream);
-        }
-    } else {
-        Span s(h, &h->tm_aggregate, 1);
-        launch_fold(MODE_SINGLE, h->tab, events, tile_count, n_tiles, h->sm_count, h->stream);
-    }
+    fold_events(h, (Event *)h->ev_buf.p, (TileInfo *)h->tile_cnt.p, n_tiles);
     CU(h, cudaGetLastError());
+    h->unsettled = true;
+    h->unsettled_tiles = n_tiles;
     h->totals.records += b.n;
     h->seq_hi = std::max<uint64_t>(h->seq_hi, b.seq_base + b.n);
     h->dirty = true;
@@ -530,13 +714,15 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
+    drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge); drain(h->tm_export); drain(h->tm_import);
     drop_deferred(h);
-    cudaFree(h->tab.keys); cudaFree(h->tab.stat); cudaFree(h->tab.olog); cudaFree(h->tab.slot_list); cudaFree(h->tab.slot_id); cudaFree(h->tab.dense);
+    cudaFree(h->tab.keys); cudaFree(h->tab.jid); cudaFree(h->tab.olog);
+    free_rows(h->tab);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq); cudaFree(h->d_export);
     free_genome(h);
     h->s_tid.release(); h->s_pos.release(); h->s_flag.release(); h->s_nh.release(); h->s_xs.release();
-    h->s_off.release(); h->s_cig.release(); h->s_nops.release(); h->s_runs.release(); h->s_tmp.release(); h->ev_buf.release(); h->tile_cnt.release(); h->long_buf.release(); h->slot_jrow.release(); h->slot_of.release();
+    h->s_off.release(); h->s_cig.release(); h->s_nops.release(); h->s_runs.release(); h->s_tmp.release(); h->ev_buf.release(); h->tile_cnt.release(); h->jrow_of.release(); h->jid_of.release();
     finalize_release(h->fw);
     mailbox_release(h);
     cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
@@ -552,11 +738,9 @@ extern "C" int ipx_set_targets(ipx_handle *h, int32_t n_targets, const char *con
     cudaSetDevice(h->device);
     for (size_t i = 0; i < h->targets.size() && i < (size_t)n_targets; i++)
         if (h->targets[i] != names[i]) return fail(h, IPX_ERR_ARG, "target %zu changed name", i);
-    const int L = bits_for(h->params.max_intron_length);
-    const int tid_bits = 63 - (L + 31);
-    if (tid_bits < 1 || ((uint64_t)n_targets >> tid_bits) != 0)
-        return fail(h, IPX_ERR_CAPACITY, "%d targets with --max-intron-length=%u do not fit the 64-bit junction key "
-                    "(%d bits left for the target index)", n_targets, h->params.max_intron_length, tid_bits < 0 ? 0 : tid_bits);
+    /* the key holds as many bits of the target index as the intron length leaves; beyond that the tables compare the
+     * full index stored with every junction (the "wide" layout, ipx_table.cuh) */
+    if (h->tables_ready && make_key_layout(h->tab.kl.len_bits, (uint64_t)n_targets).wide) h->tab.kl.wide = 1;
     h->targets.assign(names, names + n_targets);
     return upload_target_maps(h);
 }
@@ -622,17 +806,32 @@ extern "C" int ipx_push_batch(ipx_handle *h, const ipx_batch *b) {
 namespace {
 int enqueue_finalize(ipx_handle *h) {
     Span s(h, &h->tm_finalize, 0);
-    cudaError_t e = finalize_enqueue(h->tab, genome_view(h), h->d_name_rank, (int32_t)h->targets.size(), h->seq_hi, h->fw, h->stream);
+    cudaError_t e = finalize_enqueue(h->tab, genome_view(h), h->d_name_rank, h->fw, h->stream);
     h->tm_finalize.launches += (uint64_t)h->fw.launches_per_replay;
     if (e != cudaSuccess)
         return fail(h, IPX_ERR_CUDA, "CUDA error %s in finalize: %s", cudaGetErrorName(e), cudaGetErrorString(e));
     return IPX_OK;
 }
 
+int settle_import(ipx_handle *h, bool *repeated);
+
 /* wait for the enqueued finalize and make sure its buffers were large enough (growing and replaying otherwise) */
 int settle_finalize(ipx_handle *h) {
     if (h->finalize_settled) return IPX_OK;
-    for (int round = 0; round < 8; round++) {
+    {
+        /* a table that was full while the last batch was folded, or too small for what other ranks sent: the finalize
+         * that was enqueued saw a partial table */
+        bool repeated = false, repeated_import = false;
+        int rc = settle_batch(h, &repeated);
+        if (rc) return rc;
+        rc = settle_import(h, &repeated_import);
+        if (rc) return rc;
+        if (repeated || repeated_import) {
+            rc = enqueue_finalize(h);
+            if (rc) return rc;
+        }
+    }
+    for (int round = 0; round < 12; round++) {
         CU(h, cudaStreamSynchronize(h->stream));
         if (finalize_check(h->fw)) {
             h->finalize_settled = true;
@@ -726,19 +925,22 @@ void describe_error(ipx_handle *h, unsigned long long err_sv, HostTable *ht) {
         return;
     }
     ht->t.status = IPX_ERR_GENOME;
-    /* find the junction whose first event raised it: only its key is needed, scan the raw table on the host side
-     * of a small copy (errors are fatal, so this path runs at most once per run) */
-    const uint64_t cap = h->tab.cap_mask + 1;
-    std::vector<unsigned long long> keys(cap);
-    std::vector<JStat> stat(cap);
-    cudaMemcpy(keys.data(), h->tab.keys, cap * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    cudaMemcpy(stat.data(), h->tab.stat, cap * sizeof(JStat), cudaMemcpyDeviceToHost);
+    /* find the junction whose first event raised it: only its key is needed, scan the junction rows in use on the host
+     * (errors are fatal, so this path runs at most once per run) */
+    unsigned long long nk = 0;
+    cudaMemcpy(&nk, h->tab.n_keys, sizeof(nk), cudaMemcpyDeviceToHost);
+    const uint64_t n = std::min<uint64_t>(nk, h->tab.max_j);
+    std::vector<unsigned long long> keys(n);
+    std::vector<int32_t> tids(n);
+    std::vector<JStat> stat(n);
+    cudaMemcpy(keys.data(), h->tab.jkey, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemcpy(tids.data(), h->tab.jtid, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    cudaMemcpy(stat.data(), h->tab.stat, n * sizeof(JStat), cudaMemcpyDeviceToHost);
     const int status = (int)(code & 0x7Fu);
-    for (uint64_t i = 0; i < cap; i++) {
-        if (keys[i] == EMPTY64) continue;
+    for (uint64_t i = 0; i < n; i++) {
         unsigned long long fm = std::min(stat[i].first[0], std::min(stat[i].first[1], stat[i].first[2]));
         if (fm == EMPTY64 || (fm & ~0xFFull) != (err_sv & ~0xFFull)) continue;
-        const int32_t tid = key_tid(h->tab.kl, keys[i]);
+        const int32_t tid = tids[i];
         const int64_t i0 = key_start(h->tab.kl, keys[i]), i1 = i0 + key_len(h->tab.kl, keys[i]);
         ht->t.error_tid = tid;
         const char *chrom = h->targets[tid].c_str();
@@ -793,6 +995,9 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     if (rc) return rc;
     rc = settle_finalize(h);
     if (rc) return rc;
+    if (h->late_fold)
+        return fail(h, IPX_ERR_STATE, "a table was full when the partial tables were exchanged: what was folded afterwards may belong "
+                    "to another rank -- call ipx_exchange_settle on every rank and repeat the exchange before ipx_flush");
     tr.mark("flush: wait for the device");
     cudaStream_t st = h->stream;
     HostTable *ht = new HostTable();
@@ -835,10 +1040,11 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     }
     if (overflow) {
         delete ht;
-        if (overflow == 3) return fail(h, IPX_ERR_CAPACITY, "intron start beyond 2^31 cannot be keyed");
-        if (overflow == 4) return fail(h, IPX_ERR_CAPACITY, "a mailbox slot was too small for the rows sent to it (ipx_mailbox_create)");
-        return fail(h, IPX_ERR_CAPACITY, "%s is full; raise ipx_params.%s", overflow == 1 ? "junction hash table" : "read-offset log",
-                    overflow == 1 ? "table_capacity" : "hist_capacity");
+        if (overflow & OVF_START) return fail(h, IPX_ERR_CAPACITY, "intron start beyond 2^31 cannot be keyed");
+        if (overflow & OVF_MAIL) return fail(h, IPX_ERR_CAPACITY, "a mailbox slot was too small for the rows sent to it (ipx_mailbox_create)");
+        if (overflow & OVF_PEER) return fail(h, IPX_ERR_STATE, "a rank never published its share of the exchange (ipx_partial_export_mail)");
+        /* (a full table is grown and the fold repeated before results are read: settle_batch) */
+        return fail(h, IPX_ERR_CAPACITY, "%s is full", (overflow & OVF_TABLE) ? "junction table" : "read-offset log");
     }
     ipx_table &tt = ht->t;
     tt.n_junctions = n;
@@ -889,6 +1095,9 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     /* clear(), junctions.hh:240-245 */
     h->finalized = false;
     launch_clear_tables(h->tab, st);
+    h->log_bound = 0;
+    h->unsettled = false;
+    h->exported_unsettled = false;
     h->dirty = false;
     *out = &ht->t;
     return IPX_OK;
@@ -901,10 +1110,15 @@ extern "C" int ipx_clear(ipx_handle *h) {
     h->finalized = false;
     if (h->tables_ready) {
         Span s(h, &h->tm_finalize, 2);
+        /* (a table that was full while the last batch was folded is not repaired: everything is dropped anyway) */
         launch_clear_tables(h->tab, h->stream);
         CU(h, cudaGetLastError());
     }
     drop_deferred(h);
+    h->log_bound = 0;
+    h->unsettled = false;
+    h->import_pending = false;
+    h->exported_unsettled = h->late_fold = false;
     h->dirty = false;
     return IPX_OK;
 }
@@ -959,7 +1173,7 @@ extern "C" int ipx_get_timings(ipx_handle *h, ipx_timings *out) {
     if (!h || !out) return IPX_ERR_ARG;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
+    drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge); drain(h->tm_export); drain(h->tm_import);
     ipx_timings t = h->totals;
     t.extract_ms = h->tm_extract.ms;
     t.aggregate_ms = h->tm_aggregate.ms;
@@ -971,6 +1185,9 @@ extern "C" int ipx_get_timings(ipx_handle *h, ipx_timings *out) {
     t.motif_launches = h->tm_motif.launches;
     t.finalize_launches = h->tm_finalize.launches;
     t.merge_launches = h->tm_merge.launches;
+    t.export_ms = h->tm_export.ms;
+    t.import_ms = h->tm_import.ms;
+    t.exchange_launches = h->tm_export.launches + h->tm_import.launches;
     if (h->tables_ready) {
         /* the device counters are cumulative over the life of the handle */
         unsigned long long ev = 0, lw = 0;
@@ -987,8 +1204,9 @@ extern "C" int ipx_reset_timings(ipx_handle *h) {
     if (!h) return IPX_ERR_ARG;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge);
+    drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge); drain(h->tm_export); drain(h->tm_import);
     h->tm_extract = StageTimer(); h->tm_aggregate = StageTimer(); h->tm_motif = StageTimer(); h->tm_finalize = StageTimer(); h->tm_merge = StageTimer();
+    h->tm_export = StageTimer(); h->tm_import = StageTimer();
     h->totals = ipx_timings{};
     if (h->tables_ready) {
         cudaMemcpy(&h->events_base, h->tab.n_events, 8, cudaMemcpyDeviceToHost);
@@ -1014,6 +1232,8 @@ extern "C" int ipx_partial_sizes(ipx_handle *h, int32_t n_parts, const int32_t *
     if (h->finalized) return fail(h, IPX_ERR_STATE, "the exchange works on the table before ipx_finalize_device");
     if (h->targets.empty()) return fail(h, IPX_ERR_STATE, "ipx_set_targets must be called first");
     int rc = alloc_tables(h);
+    if (rc) return rc;
+    rc = settle_batch(h);
     if (rc) return rc;
     /* splitters in key-order terms: chromosome-name rank and intron_start */
     std::vector<uint32_t> order(h->targets.size()), rank(h->targets.size());
@@ -1052,8 +1272,8 @@ extern "C" int ipx_partial_sizes(ipx_handle *h, int32_t n_parts, const int32_t *
         CU(h, cudaMemcpyAsync(h->export_counts, h->d_export, (2 * MAX_PARTS + 4) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CU(h, cudaStreamSynchronize(st));
         const unsigned long long nk = h->export_counts[2 * MAX_PARTS], nl = h->export_counts[2 * MAX_PARTS + 1];
-        if ((uint32_t)h->export_counts[2 * MAX_PARTS + 2])
-            return fail(h, IPX_ERR_CAPACITY, "a table ran out of room before the exchange (raise table_capacity / hist_capacity)");
+        if ((uint32_t)h->export_counts[2 * MAX_PARTS + 2] & (OVF_TABLE | OVF_LOG))
+            return fail(h, IPX_ERR_CAPACITY, "a table ran out of room before the exchange");
         if (nk <= h->export_keys && nl <= h->export_olog) break;
         h->export_keys = nk + nk / 8 + 4096;
         h->export_olog = nl + nl / 8 + 4096;
@@ -1082,14 +1302,15 @@ extern "C" int ipx_partial_export(ipx_handle *h, void *dev_junction_rows, void *
         j += h->export_counts[p];
         hh += h->export_counts[n_parts + p];
     }
-    CU(h, h->slot_jrow.reserve((h->tab.cap_mask + 1) * sizeof(uint32_t), st));
+    CU(h, h->jrow_of.reserve(h->tab.max_j * sizeof(uint32_t), st));
     CU(h, cudaMemcpyAsync(h->d_export, cursors, 2 * n_parts * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
     {
-        Span s(h, &h->tm_finalize, 2);
+        Span s(h, &h->tm_export, 2);
         launch_export_scatter(h->tab, h->d_name_rank, h->export_split, h->export_keys, h->export_olog, h->d_export,
-                              (uint32_t *)h->slot_jrow.p, (JunctionRow *)dev_junction_rows, (HistRow *)dev_hist_rows, st);
+                              (uint32_t *)h->jrow_of.p, (JunctionRow *)dev_junction_rows, (HistRow *)dev_hist_rows, st);
         /* the local table has been handed over: empty it so that imports (own share included) rebuild it */
         launch_clear_tables(h->tab, st);
+        h->log_bound = 0;
     }
     CU(h, cudaGetLastError());
     h->export_ready = false;
@@ -1103,11 +1324,32 @@ extern "C" int ipx_partial_import(ipx_handle *h, const void *dev_junction_rows, 
     if (h->finalized) return fail(h, IPX_ERR_STATE, "table already finalized");
     int rc = alloc_tables(h);
     if (rc) return rc;
-    CU(h, h->slot_of.reserve((n_junction_rows + 1) * sizeof(uint32_t), h->stream));
+    /* room for everything that arrives, ahead of the launches (the rows are J-sized: exact growth is cheap) */
     {
-        Span s(h, &h->tm_finalize, 2);
+        TableState ts;
+        rc = read_table_state(h, &ts);
+        if (rc) return rc;
+        uint64_t in_use = std::min<uint64_t>(ts.n_keys, h->tab.max_j);
+        bool rebuilt = false;
+        while (in_use + n_junction_rows > h->tab.max_j) {
+            rc = grow_rows(h, in_use);
+            if (rc) return rc;
+            rebuilt = true;
+        }
+        while (2 * (in_use + n_junction_rows) > h->tab.cap_mask + 1) {
+            rc = rebuild_slots(h, true);
+            if (rc) return rc;
+            rebuilt = false;
+        }
+        if (rebuilt) { /* (the rows moved, the slots did not: nothing to do) */ }
+        rc = ensure_log(h, n_hist_rows);
+        if (rc) return rc;
+    }
+    CU(h, h->jid_of.reserve((n_junction_rows + 1) * sizeof(uint32_t), h->stream));
+    {
+        Span s(h, &h->tm_import, 2);
         launch_import_rows(h->tab, (const JunctionRow *)dev_junction_rows, n_junction_rows, (const HistRow *)dev_hist_rows,
-                           n_hist_rows, (uint32_t *)h->slot_of.p, h->stream);
+                           n_hist_rows, (uint32_t *)h->jid_of.p, h->stream);
     }
     CU(h, cudaGetLastError());
     h->dirty = true;
@@ -1150,6 +1392,8 @@ extern "C" int ipx_mailbox_create(ipx_handle *h, int32_t world, int32_t rank, ui
     m.world = world;
     m.me = rank;
     m.parity = 0;
+    m.epoch = 0;
+    if (junction_rows >= (1ull << 24) - 1) return fail(h, IPX_ERR_ARG, "at most 2^24 - 2 junction rows per mailbox slot");
     m.cap_j = junction_rows;
     m.cap_h = hist_rows;
     m.hist_offset = (junction_rows * sizeof(JunctionRow) + 255) & ~(uint64_t)255;
@@ -1215,24 +1459,94 @@ extern "C" int ipx_partial_export_mail(ipx_handle *h, const int32_t *split_tid, 
     rc = splitters_in_key_order(h, world, split_tid, split_start, sp);
     if (rc) return rc;
     cudaStream_t st = h->stream;
-    if (!h->d_export) CU(h, cudaMalloc(&h->d_export, (2 * MAX_PARTS + 4) * sizeof(unsigned long long)));
-    CU(h, h->slot_jrow.reserve((h->tab.cap_mask + 1) * sizeof(uint32_t), st));
-    CU(h, cudaMemsetAsync(h->d_export, 0, 2 * MAX_PARTS * sizeof(unsigned long long), st));
+    if (!h->d_export) CU(h, cudaMalloc(&h->d_export, (2 * MAX_PARTS + 8) * sizeof(unsigned long long)));
+    CU(h, h->jrow_of.reserve(h->tab.max_j * sizeof(uint32_t), st));
+    CU(h, cudaMemsetAsync(h->d_export, 0, (2 * MAX_PARTS + 8) * sizeof(unsigned long long), st));
     h->mail.parity ^= 1; /* the slots of the exchange before this one may still be read by a slower owner */
+    h->mail.epoch += 1;
+    /* no host round trip here: whether the last batch's fold was complete (no table was full) is checked later, by
+     * ipx_exchange_settle or ipx_flush */
+    h->exported_unsettled = h->unsettled;
     {
         /* creation thresholds for anything still unresolved: keys that never got one are not exported */
         Span s(h, &h->tm_motif, 1);
         launch_resolve_T(h->tab, genome_view(h), st);
     }
     {
-        Span s(h, &h->tm_finalize, 4);
-        launch_mail_export(h->tab, h->d_name_rank, sp, h->mail, h->d_export, (uint32_t *)h->slot_jrow.p, h->sm_count, st);
-        /* the local table has been handed over: empty it so that the import (own share included) rebuilds it */
-        launch_clear_tables(h->tab, st);
+        /* only what other ranks own moves; this rank's own share stays where it is */
+        Span s(h, &h->tm_export, 3);
+        launch_mail_export(h->tab, h->d_name_rank, sp, h->mail, h->d_export, (uint32_t *)h->jrow_of.p, h->sm_count, st);
     }
     CU(h, cudaGetLastError());
     return IPX_OK;
 }
+
+namespace {
+int enqueue_mail_import(ipx_handle *h);
+}
+extern "C" int ipx_exchange_settle(ipx_handle *h, int32_t *repeat_exchange) {
+    if (!h || !repeat_exchange) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    *repeat_exchange = 0;
+    bool repeated = false;
+    int rc = settle_batch(h, &repeated);
+    if (rc) return rc;
+    rc = settle_import(h, &repeated);
+    if (rc) return rc;
+    if (h->late_fold) {
+        *repeat_exchange = 1;
+        h->late_fold = false;
+        h->finalized = false; /* whatever was finalized saw a table that is about to change */
+        h->finalize_settled = false;
+    }
+    return IPX_OK;
+}
+
+namespace {
+int enqueue_mail_import(ipx_handle *h) {
+    Span s(h, &h->tm_import, 3);
+    unsigned long long *verdict = h->d_export + 2 * MAX_PARTS + 4;
+    launch_mail_import(h->tab, h->mail, verdict, (uint32_t *)h->jid_of.p, h->sm_count, h->mail_timeout_ns, h->stream);
+    CU(h, cudaMemcpyAsync(h->h_flags + 4, verdict, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaGetLastError());
+    return IPX_OK;
+}
+
+/* the import checks on the device that everything fits before it folds anything; when it refused, grow and repeat */
+int settle_import(ipx_handle *h, bool *repeated) {
+    if (!h->import_pending) return IPX_OK;
+    for (int round = 0; round < 40; round++) {
+        CU(h, cudaStreamSynchronize(h->stream));
+        if (h->h_flags[4] != 2ull) break;
+        TableState ts;
+        int rc = read_table_state(h, &ts);
+        if (rc) return rc;
+        if (ts.overflow & (OVF_MAIL | OVF_PEER)) break; /* not a matter of room: reported by ipx_flush */
+        *repeated = true;
+        launch_settle_counters(h->tab, h->stream);
+        const uint64_t nj = h->h_flags[5], nh = h->h_flags[6];
+        uint64_t in_use = std::min<uint64_t>(ts.n_keys, h->tab.max_j);
+        while (in_use + nj > h->tab.max_j) {
+            rc = grow_rows(h, in_use);
+            if (rc) return rc;
+        }
+        while (2 * (in_use + nj) > h->tab.cap_mask + 1) {
+            rc = rebuild_slots(h, true);
+            if (rc) return rc;
+        }
+        const uint64_t log_in_use = std::min<uint64_t>(ts.n_olog, h->tab.olog_cap);
+        if (log_in_use + nh > h->tab.olog_cap) {
+            rc = grow_log(h, log_in_use, log_in_use + nh);
+            if (rc) return rc;
+        }
+        h->log_bound = log_in_use + nh;
+        rc = enqueue_mail_import(h);
+        if (rc) return rc;
+    }
+    h->import_pending = false;
+    return IPX_OK;
+}
+}  // namespace
 
 extern "C" int ipx_partial_import_mail(ipx_handle *h) {
     if (!h) return IPX_ERR_ARG;
@@ -1241,15 +1555,39 @@ extern "C" int ipx_partial_import_mail(ipx_handle *h) {
     if (h->finalized) return fail(h, IPX_ERR_STATE, "table already finalized");
     int rc = alloc_tables(h);
     if (rc) return rc;
-    CU(h, h->slot_of.reserve((h->mail.cap_j + 1) * sizeof(uint32_t), h->stream));
-    {
-        Span s(h, &h->tm_finalize, 2 * (uint64_t)h->mail.world);
-        /* one source after the other: the offset rows of a source name junctions by their index among its junction rows */
-        for (int src = 0; src < h->mail.world; src++)
-            launch_mail_import(h->tab, h->mail, src, (uint32_t *)h->slot_of.p, h->sm_count, h->stream);
-    }
-    CU(h, cudaGetLastError());
+    if (!h->d_export) return fail(h, IPX_ERR_STATE, "call ipx_partial_export_mail first");
+    CU(h, h->jid_of.reserve(((uint64_t)h->mail.world * h->mail.cap_j + 1) * sizeof(uint32_t), h->stream));
+    rc = enqueue_mail_import(h);
+    if (rc) return rc;
+    h->import_pending = true;
     h->dirty = true;
+    return IPX_OK;
+}
+
+extern "C" int ipx_sample_keys(ipx_handle *h, uint64_t stride, uint64_t max_keys, int32_t *tid, uint32_t *intron_start, uint64_t *n_keys) {
+    if (!h || !n_keys || (max_keys && (!tid || !intron_start))) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    *n_keys = 0;
+    if (!h->tables_ready || max_keys == 0) return IPX_OK;
+    int rc = settle_batch(h);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    DeviceBuf d_tid, d_i0, d_n;
+    CU(h, d_tid.reserve(max_keys * 4, st));
+    CU(h, d_i0.reserve(max_keys * 4, st));
+    CU(h, d_n.reserve(8, st));
+    launch_sample_keys(h->tab, stride, max_keys, (int32_t *)d_tid.p, (uint32_t *)d_i0.p, (unsigned long long *)d_n.p, st);
+    CU(h, cudaGetLastError());
+    unsigned long long n = 0;
+    CU(h, cudaMemcpyAsync(&n, d_n.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    if (n) {
+        CU(h, cudaMemcpyAsync(tid, d_tid.p, n * 4, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(intron_start, d_i0.p, n * 4, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+    }
+    d_tid.release(); d_i0.release(); d_n.release();
+    *n_keys = n;
     return IPX_OK;
 }
 
@@ -1262,14 +1600,26 @@ extern "C" int ipx_thresholds_rows(ipx_handle *h, uint64_t *n_rows, uint32_t *ro
     if (h->targets.empty()) return fail(h, IPX_ERR_STATE, "ipx_set_targets must be called first");
     int rc = alloc_tables(h);
     if (rc) return rc;
+    TableState ts;
+    rc = read_table_state(h, &ts);
+    if (rc) return rc;
+    if (ts.overflow & OVF_TABLE) {
+        /* the first-seen pass met a full table: grow it and run the pass again over the kept events (it is idempotent) */
+        rc = grow_and_repeat(h, ts, [&]() {
+            for (auto &d : h->deferred)
+                launch_fold(MODE_PASS1, h->tab, (Event *)d.events, (TileInfo *)d.tile_info, d.n_tiles, h->sm_count, h->stream);
+            cudaError_t e = cudaGetLastError();
+            return e == cudaSuccess ? IPX_OK : fail(h, IPX_ERR_CUDA, "CUDA error %s while repeating a fold", cudaGetErrorName(e));
+        });
+        if (rc) return rc;
+        rc = read_table_state(h, &ts);
+        if (rc) return rc;
+    }
     {
         Span s(h, &h->tm_motif, 1);
         launch_resolve_T(h->tab, genome_view(h), h->stream);
     }
-    unsigned long long nk = 0;
-    CU(h, cudaMemcpyAsync(&nk, h->tab.n_keys, sizeof(nk), cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    *n_rows = nk;
+    *n_rows = std::min<uint64_t>(ts.n_keys, h->tab.max_j);
     return IPX_OK;
 }
 
@@ -1280,6 +1630,7 @@ extern "C" int ipx_thresholds_export(ipx_handle *h, void *dev_rows) {
     unsigned long long nk = 0;
     CU(h, cudaMemcpyAsync(&nk, h->tab.n_keys, sizeof(nk), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    nk = std::min<uint64_t>(nk, h->tab.max_j);
     launch_export_thresholds(h->tab, (ThresholdRow *)dev_rows, nk, h->stream);
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(h->stream)); /* the rows are complete when this returns: callers hand them to another stream */
@@ -1302,7 +1653,7 @@ extern "C" int ipx_count_deferred(ipx_handle *h) {
     if (h->finalized) return fail(h, IPX_ERR_STATE, "table already finalized");
     for (auto &d : h->deferred) {
         Span s(h, &h->tm_aggregate, 1);
-        launch_fold(MODE_PASS2, h->tab, (const Event *)d.events, (const TileInfo *)d.tile_info, d.n_tiles, h->sm_count, h->stream);
+        launch_fold(MODE_PASS2, h->tab, (Event *)d.events, (TileInfo *)d.tile_info, d.n_tiles, h->sm_count, h->stream);
     }
     CU(h, cudaGetLastError());
     drop_deferred(h);
@@ -1349,9 +1700,9 @@ extern "C" int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ip
         CU(h, cudaMalloc(&h->mt.stat, cap * sizeof(MStat)));
         h->mt_cap = cap;
     }
-    if (!h->d_counters) {
-        CU(h, cudaMalloc(&h->d_counters, 8 * 128));
-        CU(h, cudaMemsetAsync(h->d_counters, 0, 8 * 128, st));
+    {
+        int rcc = alloc_counters(h);
+        if (rcc) return rcc;
     }
     h->mt.cap_mask = h->mt_cap - 1;
     h->mt.n_keys = h->d_counters + 112;

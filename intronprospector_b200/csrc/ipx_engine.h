@@ -78,35 +78,26 @@ enum ExtractMode { MODE_SINGLE = 0, MODE_PASS1 = 1, MODE_PASS2 = 2 };
  * atomic is involved; the buffer holds n_cigar / 2 + 1 events. */
 static const int EX_TILE = 1024;
 struct __align__(16) TileInfo {
-    uint32_t count;      /* events the tile wrote */
+    uint32_t count;      /* events in the tile's region: written by K1, events K2 could not fold (table full) after K2 */
     uint32_t first_word; /* cigar_off of its first record: the region starts at event (first_word + 1) / 2 */
-    uint32_t n_long;     /* records of the tile handed to k_extract_long (LongRec region starts at (first_word + 3) / 4) */
-    uint32_t pad;
-};
-/* A live record with more than three CIGAR operations, as the pipelined kernel hands it to k_extract_long: everything
- * the walk needs except the CIGAR words themselves.  A tile's records go to a private region of the LongRec buffer
- * starting at ceil(first_word / 4) -- such a record has at least four words, so regions cannot overlap; the buffer
- * holds n_cigar / 4 + 2 records. */
-struct __align__(16) LongRec {
-    int32_t pos;
-    int32_t tid;
-    uint32_t c0, n_cigar; /* its words are cigar[c0 .. c0 + n_cigar) */
-    uint32_t rec;         /* index of the record in the batch */
-    uint16_t flag;
-    uint8_t nh, xs;
     uint32_t pad[2];
 };
+/* first event index of a tile's region in the event buffer */
+__host__ __device__ inline uint64_t tile_event_base(uint32_t first_cigar_word) { return ((uint64_t)first_cigar_word + 1ull) >> 1; }
 inline uint64_t tiles_of(uint64_t n_records) { return (n_records + EX_TILE - 1) / EX_TILE; }
 
 /* kernels' launchers; all asynchronous on `st` */
 void launch_init_tables(const Tables &t, cudaStream_t st);  /* whole tables, once after allocation */
-void launch_clear_tables(const Tables &t, cudaStream_t st); /* only what the lists say is in use */
+void launch_init_rows(const Tables &t, uint64_t first, cudaStream_t st); /* junction rows [first, max_j) after growth */
+/* only what is in use (and, when the overflow flag is up, the slots that were claimed while no junction row was left) */
+void launch_clear_tables(const Tables &t, cudaStream_t st);
+void launch_settle_counters(const Tables &t, cudaStream_t st); /* counters back to what exists, before growth */
+void launch_rehash(const Tables &t, cudaStream_t st);          /* every junction row into the (fresh) hash slots */
 /* returns a CUDA error (attribute set-up of the pipelined kernel can fail), launches counted in *launches */
 cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractParams &p, const Tables &t, Event *out,
-                           TileInfo *tile_info, LongRec *long_recs, unsigned long long *next_record, int sm_count, cudaStream_t st,
-                           int *launches);
-void launch_fold(int mode, const Tables &t, const Event *ev, const TileInfo *tile_info, uint64_t n_tiles, int sm_count,
-                 cudaStream_t st);
+                           TileInfo *tile_info, unsigned long long *next_record, int sm_count, cudaStream_t st, int *launches);
+/* K2 consumes the events: afterwards tile_info[].count is what it could not fold (0 unless a table was full) */
+void launch_fold(int mode, const Tables &t, Event *ev, TileInfo *tile_info, uint64_t n_tiles, int sm_count, cudaStream_t st);
 void launch_resolve_T(const Tables &t, const GenomeView &g, cudaStream_t st);
 /* ipx_batch_compact -> ipx_batch columns on the device: cigar_off = exclusive scan of the operation counts (n + 1
  * entries), tid = the run each record falls into.  tmp: scratch of *tmp_bytes (queried when tmp == NULL). */
@@ -115,59 +106,58 @@ cudaError_t expand_compact(const uint16_t *n_ops, uint64_t n, uint32_t *cigar_of
                            cudaStream_t st);
 void launch_export_thresholds(const Tables &t, ThresholdRow *rows, uint64_t n, cudaStream_t st);
 void launch_import_thresholds(const Tables &t, const ThresholdRow *rows, uint64_t n, cudaStream_t st);
-/* rows of ONE source: the offset rows refer to the junction rows of the same call; slot_of: [nj] scratch */
-void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh, uint32_t *slot_of,
+/* rows of ONE source: the offset rows refer to the junction rows of the same call; jid_of: [nj] scratch */
+void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh, uint32_t *jid_of,
                         cudaStream_t st);
 
-/* workspace for finalize; grown on demand by the engine */
-/* Everything finalize needs lives in buffers sized by grow-only bounds (B junction keys, L read-offset log entries,
- * R histogram runs), so the whole sequence -- two radix sorts, the log's sort + run-length reduction, scans, gathers --
- * is one CUDA graph that is captured once per set of bounds and replayed with a single launch.  The kernels read the
- * actual counts from device memory, pad up to the bounds with keys that sort last, and raise a flag when a bound was
- * too small; the host then grows the bound and replays (the graph only reads the tables, so a replay is harmless). */
+/* Workspace of finalize.  Everything it needs lives in buffers sized by grow-only bounds (B junction ids, L read-offset
+ * log entries, R histogram runs, C keys per sort bucket), so the whole sequence is one CUDA graph that is captured once
+ * per set of bounds and replayed with a single launch.  The kernels read the actual counts from device memory and
+ * raise a flag when a bound was too small; the host then grows the bound and replays (the graph only reads the
+ * tables, so a replay is harmless). */
 struct FinalizeWork {
-    uint64_t B = 0, L = 0, R = 0;
-    uint64_t wish_B = 0, wish_L = 0, wish_R = 0; /* what finalize_check asked for */
+    uint64_t B = 0, L = 0, R = 0, C = 0;
+    uint64_t wish_B = 0, wish_L = 0, wish_R = 0, wish_C = 0; /* what finalize_check asked for */
     uint64_t first_B = 1ull << 16, first_L = 1ull << 16, first_R = 1ull << 20; /* bounds of the very first finalize */
-    unsigned long long *sort_key = nullptr, *sort_key2 = nullptr, *hash_lo = nullptr, *total = nullptr, *hk_a = nullptr,
-                       *hk_b = nullptr;
-    uint32_t *slot_a = nullptr, *slot_b = nullptr, *idx_b = nullptr, *dense_nz = nullptr, *hc_a = nullptr, *hc_b = nullptr;
-    /* the sjN chain and the read-offset-log chain run beside the key-order chain, each on its own stream (inside the
-     * graph: parallel branches) with its own scratch */
-    unsigned long long *tkey = nullptr, *tkey2 = nullptr, *total_j = nullptr; /* [B] */
-    uint32_t *tidx_a = nullptr, *tidx_b = nullptr, *t_rank = nullptr;        /* [B] */
-    void *cub_tmp = nullptr, *cub_tmp2 = nullptr, *cub_tmp3 = nullptr;
-    size_t cub_tmp_bytes = 0;
+    unsigned long long *sort_key = nullptr, *tkey = nullptr;                     /* [B] */
+    uint32_t *sort_sub = nullptr, *order = nullptr, *t_order = nullptr, *t_rank = nullptr; /* [B] */
+    uint32_t *seg_off = nullptr, *seg_fill = nullptr, *runs_j = nullptr, *nz_j = nullptr, *big_list = nullptr; /* [B] */
+    uint32_t *runs_r = nullptr;  /* [B + 1] */
+    uint32_t *seg = nullptr;     /* [L] log entries grouped by junction, then the ordered runs' counts */
+    uint32_t *big_scratch = nullptr;
+    unsigned long long *scan_state = nullptr;
+    /* the two sample sorts (key order, sjN) run side by side */
+    unsigned long long *ss_splitters[2] = {nullptr, nullptr}, *ss_bk[2] = {nullptr, nullptr};
+    uint32_t *ss_bucket_cnt[2] = {nullptr, nullptr}, *ss_bs[2] = {nullptr, nullptr}, *ss_bv[2] = {nullptr, nullptr};
     cudaStream_t s2 = nullptr, s3 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
-    /* [8]: 0 junctions, 1 histogram runs, 2 distinct log runs (uint32), 3 flags (1: B too small, 2: L, 4: R),
-     *      4 keys seen, 5 log entries seen */
+    /* [8]: 0 junctions, 1 histogram runs, 2 log entries in segments, 3 flags (1: B too small, 2: L, 4: R, 8: C),
+     *      4 junction ids in use, 5 log entries in use, 6 junctions ordered by the block pass, 7 largest bucket */
     unsigned long long *d_count = nullptr;
     unsigned long long *h_count = nullptr; /* pinned mirror, filled by the graph's last node */
     DeviceTable out{};                     /* arrays of B rows (hist_cnt: R runs) */
     cudaGraphExec_t exec = nullptr;
     /* what the captured graph depends on */
     struct Key {
-        uint64_t B, L, R;
-        int key_bits, t_bits;
-        const void *tab_keys, *name_rank, *gseq, *target_seq, *dense;
-        int32_t n_targets, have_genome, skip_missing, filter_canon;
+        uint64_t B, L, R, C, max_j, olog_cap;
+        const void *tab_keys, *tab_rows, *tab_log, *name_rank, *gseq, *target_seq, *dense;
+        int32_t n_targets, have_genome, skip_missing, filter_canon, wide, len_bits;
         bool operator==(const Key &o) const {
-            return B == o.B && L == o.L && R == o.R && key_bits == o.key_bits && t_bits == o.t_bits && tab_keys == o.tab_keys &&
-                   name_rank == o.name_rank && gseq == o.gseq && target_seq == o.target_seq && dense == o.dense &&
-                   n_targets == o.n_targets && have_genome == o.have_genome && skip_missing == o.skip_missing &&
-                   filter_canon == o.filter_canon;
+            return B == o.B && L == o.L && R == o.R && C == o.C && max_j == o.max_j && olog_cap == o.olog_cap &&
+                   tab_keys == o.tab_keys && tab_rows == o.tab_rows && tab_log == o.tab_log && name_rank == o.name_rank &&
+                   gseq == o.gseq && target_seq == o.target_seq && dense == o.dense && n_targets == o.n_targets &&
+                   have_genome == o.have_genome && skip_missing == o.skip_missing && filter_canon == o.filter_canon &&
+                   wide == o.wide && len_bits == o.len_bits;
         }
     } key{};
     int launches_per_replay = 0;
 };
 
-/* key-order sort, sjN ranking, histogram ordering, gather: enqueues one graph launch on `st` and the copy of the
+/* key order, sjN ranking, histogram ordering, row gather: enqueues one graph launch on `st` and the copy of the
  * counters to w.h_count; nothing is synchronised.  finalize_check (after a stream synchronise) says whether a bound
  * was too small -- it then grows the bounds and the caller enqueues again.  `name_rank[tid]` orders targets like
  * std::string::operator< on their names. */
-cudaError_t finalize_enqueue(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, int32_t n_targets,
-                             uint64_t seq_hi, FinalizeWork &w, cudaStream_t st);
+cudaError_t finalize_enqueue(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, FinalizeWork &w, cudaStream_t st);
 bool finalize_check(FinalizeWork &w); /* true = results valid (w.out.n / n_hist set); false = bounds grown, run again */
 void finalize_release(FinalizeWork &w);
 
@@ -192,24 +182,31 @@ struct Splitters {
     uint32_t start[MAX_PARTS - 1]; /* intron_start */
     uint32_t jbase[MAX_PARTS];     /* scatter pass: index of each part's first junction row in the send buffer */
 };
-/* counts / cursors: [2 * n_parts] unsigned long long on the device: junction rows per part, then offset rows per part */
+/* counts / cursors: [2 * n_parts] unsigned long long on the device: junction rows per part, then offset rows per part;
+ * jrow_of: [max_j] owner << 24 | index of the junction's row among the rows sent to that owner */
 void launch_export_count(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t n_keys, uint64_t n_olog,
                          unsigned long long *counts, cudaStream_t st);
 void launch_export_scatter(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t n_keys, uint64_t n_olog,
-                           unsigned long long *cursors, uint32_t *slot_jrow, JunctionRow *jr, HistRow *hr, cudaStream_t st);
-
+                           unsigned long long *cursors, uint32_t *jrow_of, JunctionRow *jr, HistRow *hr, cudaStream_t st);
 
 /* Exchange over peer memory.  Every rank owns a mailbox of 2 (parity) x world slots, all ranks with the same layout;
- * slot (parity, source) = [header: junction rows, offset rows (2 x u64)] [cap_j junction rows] [cap_h offset rows]. */
+ * slot (parity, source) = [header: junction rows, offset rows, epoch (3 x u64)] [cap_j junction rows] [cap_h offset rows]. */
 static const uint64_t MAIL_HEADER_BYTES = 128;
 struct Mailboxes {
     char *base[MAX_PARTS]; /* mailbox of every rank as mapped into this process (own included) */
     uint64_t slot_bytes, hist_offset, cap_j, cap_h;
+    unsigned long long epoch; /* number of the exchange in flight (same on every rank) */
     int32_t world, me, parity;
 };
+/* export the junctions other ranks own into their slots, disown them here, publish counts + epoch */
 void launch_mail_export(const Tables &t, const uint32_t *name_rank, const Splitters &sp, const Mailboxes &m, unsigned long long *counts,
-                        uint32_t *slot_jrow, int sm_count, cudaStream_t st);
-void launch_mail_import(const Tables &t, const Mailboxes &m, int source, uint32_t *slot_of, int sm_count, cudaStream_t st);
+                        uint32_t *jrow_of, int sm_count, cudaStream_t st);
+/* wait (on the device) for every source's epoch, then fold all slots; verdict: [3] words on the device, jid_of: [world * cap_j] */
+void launch_mail_import(const Tables &t, const Mailboxes &m, unsigned long long *verdict, uint32_t *jid_of, int sm_count,
+                        unsigned long long timeout_ns, cudaStream_t st);
+/* every stride-th junction key (target index, intron start), at most max_out; *n_out = how many */
+void launch_sample_keys(const Tables &t, uint64_t stride, uint64_t max_out, int32_t *tid, uint32_t *i0, unsigned long long *n_out,
+                        cudaStream_t st);
 
 }  // namespace ipx
 #endif

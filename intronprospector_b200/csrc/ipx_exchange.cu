@@ -1,0 +1,492 @@
+/* ipx_exchange.cu -- multi-GPU exchange of partial junction tables by key range (sm_100a).
+ *
+ *  k_mail_*          the exchange over peer memory (NVLink / NVSwitch): every rank owns a mailbox with one slot per
+ *                    source rank; the exporting kernels store the rows of the junctions another rank owns straight
+ *                    into that rank's slot and disown them locally -- the rank's own share never moves.  A last small
+ *                    kernel publishes the row counts and the exchange's epoch into the slot headers; the importing
+ *                    side starts with a one-warp kernel that waits for the epoch of every source (a device-side
+ *                    barrier: no collective, no host round trip) and then folds all sources' slots in two launches.
+ *  k_export_* / k_import_*   the same rows packed into send buffers for an all-to-all transport (hosts without peer
+ *                    access; what the gloo test drives): everything is exported, the table cleared, every share imported.
+ *  k_*_thresholds    canon filter across ranks: (key, creation threshold) rows
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ipx_engine.h"
+
+namespace ipx {
+
+static inline unsigned blocks_for(uint64_t n, unsigned threads) {
+    uint64_t b = (n + threads - 1) / threads;
+    return (unsigned)(b ? b : 1);
+}
+
+__device__ __forceinline__ int part_of(const Splitters &sp, uint32_t name_rank, uint32_t i0) {
+    int p = 0;
+    while (p < sp.n_parts - 1 && (name_rank > sp.rank[p] || (name_rank == sp.rank[p] && i0 >= sp.start[p]))) p++;
+    return p;
+}
+
+/* offset rows a counter needs: counts above 65535 are sent as several rows */
+__device__ __forceinline__ uint32_t hist_rows_of(uint32_t v) { return v ? (v - 1u) / 0xFFFFu + 1u : 0u; }
+
+/* what a warp needs of one junction row: owner, key fields, its dense offset row (8 counters per lane) */
+struct RowView {
+    int dest; /* -1: nothing to export (never created: nothing was counted into it) */
+    uint32_t i0, i1, mine, incl, nz;
+    int32_t tid;
+    uint32_t v[8];
+};
+__device__ __forceinline__ RowView read_row(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t j, int lane) {
+    RowView r;
+    r.dest = -1;
+    r.mine = 0u;
+    /* everything that hangs on the junction id is requested at once: the warp's time is round trips, not bytes */
+    const unsigned long long T = t.stat[j].T;
+    const unsigned long long key = t.jkey[j];
+    r.tid = t.jtid[j];
+    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+    if (t.dense) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + j * DENSE_W);
+        a = row[lane * 2];
+        b = row[lane * 2 + 1];
+    }
+    r.i0 = key_start(t.kl, key);
+    r.i1 = r.i0 + key_len(t.kl, key);
+    const bool live = T != EMPTY64;
+    if (live) r.dest = part_of(sp, name_rank[r.tid], r.i0);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        r.v[k] = live ? r.v[k] : 0u;
+        r.mine += hist_rows_of(r.v[k]);
+    }
+    r.incl = r.mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, r.incl, d);
+        if (lane >= d) r.incl += y;
+    }
+    r.nz = __shfl_sync(0xFFFFFFFFu, r.incl, 31);
+    return r;
+}
+
+__device__ __forceinline__ JunctionRow make_junction_row(const JStat &s, const RowView &r) {
+    JunctionRow jr;
+    jr.first[0] = s.first[0]; jr.first[1] = s.first[1]; jr.first[2] = s.first[2];
+    jr.cnt[0] = s.cnt[0]; jr.cnt[1] = s.cnt[1]; jr.cnt[2] = s.cnt[2];
+    jr.tid = r.tid; jr.i0 = r.i0; jr.i1 = r.i1; jr.a0 = s.a0; jr.a1 = s.a1; jr.pad = 0;
+    return jr;
+}
+
+/* the lanes' non-zero dense counters as offset rows of junction row `jrow`, starting at hr[o] */
+__device__ __forceinline__ void write_dense_rows(HistRow *hr, uint64_t o, uint32_t jrow, const RowView &r, int lane) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t left = r.v[k];
+        while (left) {
+            const uint32_t piece = left > 0xFFFFu ? 0xFFFFu : left;
+            HistRow h;
+            h.jrow = jrow; h.offset = (uint16_t)(lane * 8 + k); h.cnt = (uint16_t)piece;
+            hr[o++] = h;
+            left -= piece;
+        }
+    }
+}
+
+/* ---- packed rows for an all-to-all transport ---- */
+/* warp per junction row.  SCATTER = false: count rows per destination; true: write them behind the destination's cursor. */
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_export_rows(Tables t, const uint32_t *name_rank, Splitters sp, uint64_t n_keys,
+                                                     unsigned long long *counts, uint32_t *jrow_of, JunctionRow *jr, HistRow *hr) {
+    const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= n_keys || j >= junctions_in_use(t)) return; /* n_keys is a launch bound; the table knows how many there are */
+    const RowView r = read_row(t, name_rank, sp, j, lane);
+    if (r.dest < 0) return;
+    unsigned long long jpos = 0ull, hpos = 0ull;
+    if (lane == 0) {
+        jpos = atomicAdd(&counts[r.dest], 1ull);
+        if (r.nz) hpos = atomicAdd(&counts[sp.n_parts + r.dest], (unsigned long long)r.nz);
+    }
+    if (!SCATTER) return;
+    jpos = __shfl_sync(0xFFFFFFFFu, jpos, 0);
+    hpos = __shfl_sync(0xFFFFFFFFu, hpos, 0);
+    const uint32_t jrow = (uint32_t)jpos - sp.jbase[r.dest];
+    if (lane == 0) {
+        jr[jpos] = make_junction_row(t.stat[j], r);
+        jrow_of[j] = ((uint32_t)r.dest << 24) | jrow; /* for the log entries of this junction */
+    }
+    write_dense_rows(hr, hpos + (r.incl - r.mine), jrow, r, lane);
+}
+
+/* thread per entry of the read-offset log: one offset row each (equal pairs are summed by the importer) */
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_export_olog(Tables t, const uint32_t *name_rank, Splitters sp, uint64_t n_olog,
+                                                     unsigned long long *counts, const uint32_t *jrow_of, HistRow *hr) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int dest = -1 - lane; /* idle lanes group with nobody */
+    unsigned long long e = EMPTY64;
+    uint32_t j = 0u;
+    if (i < n_olog && i < log_entries_in_use(t)) {
+        e = t.olog[i];
+        j = (uint32_t)(e >> 32);
+        if (j < junctions_in_use(t) && t.stat[j].T != EMPTY64)
+            dest = part_of(sp, name_rank[t.jtid[j]], key_start(t.kl, t.jkey[j]));
+    }
+    /* one atomic per (warp, destination) */
+    const unsigned grp = __match_any_sync(0xFFFFFFFFu, dest);
+    const int leader = __ffs(grp) - 1;
+    unsigned long long base = 0ull;
+    if (dest >= 0 && lane == leader) base = atomicAdd(&counts[sp.n_parts + dest], (unsigned long long)__popc(grp));
+    if (!SCATTER) return;
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (dest >= 0) {
+        HistRow h;
+        h.jrow = jrow_of[j] & 0xFFFFFFu; h.offset = (uint16_t)((e >> 16) & 0xFFFFull); h.cnt = (uint16_t)(e & 0xFFFFull);
+        hr[base + __popc(grp & ((1u << lane) - 1u))] = h;
+    }
+}
+
+void launch_export_count(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t n_keys, uint64_t n_olog,
+                         unsigned long long *counts, cudaStream_t st) {
+    if (n_keys) k_export_rows<false><<<blocks_for(n_keys * 32, 256), 256, 0, st>>>(t, name_rank, sp, n_keys, counts, nullptr, nullptr, nullptr);
+    if (n_olog) k_export_olog<false><<<blocks_for(n_olog, 256), 256, 0, st>>>(t, name_rank, sp, n_olog, counts, nullptr, nullptr);
+}
+
+void launch_export_scatter(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t n_keys, uint64_t n_olog,
+                           unsigned long long *cursors, uint32_t *jrow_of, JunctionRow *jr, HistRow *hr, cudaStream_t st) {
+    if (n_keys) k_export_rows<true><<<blocks_for(n_keys * 32, 256), 256, 0, st>>>(t, name_rank, sp, n_keys, cursors, jrow_of, jr, hr);
+    if (n_olog) k_export_olog<true><<<blocks_for(n_olog, 256), 256, 0, st>>>(t, name_rank, sp, n_olog, cursors, jrow_of, hr);
+}
+
+/* fold one received junction row; returns the junction id or JID_NONE */
+__device__ __forceinline__ uint32_t import_junction_row(const Tables &t, const JunctionRow &r) {
+    const uint32_t j = junction_probe<true>(t, make_key(t.kl, r.tid, r.i0, r.i1), r.tid);
+    if (j == JID_NONE) return j;
+    JStat *s = &t.stat[j];
+    for (int c = 0; c < 3; ++c) {
+        if (r.first[c] != EMPTY64) atomicMin(&s->first[c], r.first[c]);
+        if (r.cnt[c]) atomicAdd(&s->cnt[c], r.cnt[c]);
+    }
+    atomicMin(&s->a0, r.a0);
+    atomicMax(&s->a1, r.a1);
+    /* the junction's creating event may now be one of another rank's: resolved again by the next k_resolve_T */
+    *((volatile unsigned long long *)&s->T) = EMPTY64;
+    return j;
+}
+
+__global__ void k_import_junction_rows(Tables t, const JunctionRow *jr, uint64_t n, uint32_t *jid_of) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    jid_of[i] = import_junction_row(t, jr[i]);
+}
+
+__global__ void __launch_bounds__(256) k_import_hist_rows(Tables t, const HistRow *hr, uint64_t n, const uint32_t *jid_of, uint64_t nj) {
+    __shared__ unsigned long long s_stage[8][LOG_STAGE];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    LogStage log{s_stage[threadIdx.x >> 5], 0u};
+    uint32_t j = JID_NONE, off = 0u, cnt = 0u;
+    if (i < n) {
+        const HistRow r = hr[i];
+        if (r.jrow < nj) j = jid_of[r.jrow];
+        off = r.offset;
+        cnt = r.cnt;
+    }
+    const bool ok = j != JID_NONE && cnt != 0u;
+    const bool in_row = t.dense != nullptr && off < DENSE_W;
+    if (ok && in_row) atomicAdd(&t.dense[(uint64_t)j * DENSE_W + off], cnt);
+    log_append(t, log, ok && !in_row, olog_entry(j, off, cnt));
+    log_flush(t, log);
+}
+
+void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh, uint32_t *jid_of,
+                        cudaStream_t st) {
+    if (nj) k_import_junction_rows<<<blocks_for(nj, 256), 256, 0, st>>>(t, jr, nj, jid_of);
+    if (nh) k_import_hist_rows<<<blocks_for(nh, 256), 256, 0, st>>>(t, hr, nh, jid_of, nj);
+}
+
+/* ---- the exchange over peer memory ---- */
+__device__ __forceinline__ char *mail_slot(const Mailboxes &m, int owner, int source) {
+    return m.base[owner] + (uint64_t)(m.parity * m.world + source) * m.slot_bytes;
+}
+__device__ __forceinline__ JunctionRow *mail_junction_rows(char *slot) { return reinterpret_cast<JunctionRow *>(slot + MAIL_HEADER_BYTES); }
+__device__ __forceinline__ HistRow *mail_hist_rows(const Mailboxes &m, char *slot) {
+    return reinterpret_cast<HistRow *>(slot + MAIL_HEADER_BYTES + m.hist_offset);
+}
+
+static const uint32_t NOT_EXPORTED = 0xFFFFFFFFu;
+
+/* A warp per junction row, a block's eight warps in lock step: the block adds up what its eight rows need per owner
+ * in shared memory, reserves it behind the owners' cursors with one atomic per owner that occurs (junction ids follow
+ * the stream, so neighbours mostly share their owner), and the warps write their rows -- still in registers -- into the
+ * owners' slots: NVLink stores.  An exported row is disowned here: its record and offset row go back to the reset
+ * values, so that finalize passes over it and later events would start it afresh. */
+__global__ void __launch_bounds__(256) k_mail_rows(Tables t, const uint32_t *name_rank, Splitters sp, Mailboxes m,
+                                                   unsigned long long *counts, uint32_t *jrow_of) {
+    __shared__ unsigned long long s_j[MAX_PARTS], s_h[MAX_PARTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t n_keys = junctions_in_use(t);
+    const uint64_t rounds = (n_keys + 8ull * gridDim.x - 1ull) / (8ull * gridDim.x);
+    for (uint64_t round = 0; round < rounds; ++round) {
+        const uint64_t j = (round * gridDim.x + blockIdx.x) * 8ull + (uint64_t)warp;
+        if (threadIdx.x < MAX_PARTS) s_j[threadIdx.x] = s_h[threadIdx.x] = 0ull;
+        __syncthreads();
+        RowView r;
+        r.dest = -1;
+        r.nz = 0u;
+        if (j < n_keys) r = read_row(t, name_rank, sp, j, lane);
+        const bool foreign = r.dest >= 0 && r.dest != m.me;
+        unsigned long long jpos = 0ull, hpos = 0ull;
+        if (foreign && lane == 0) {
+            jpos = atomicAdd(&s_j[r.dest], 1ull);
+            if (r.nz) hpos = atomicAdd(&s_h[r.dest], (unsigned long long)r.nz);
+        }
+        __syncthreads();
+        if (threadIdx.x < sp.n_parts) {
+            const int d = threadIdx.x;
+            const unsigned long long nj = s_j[d], nh = s_h[d];
+            s_j[d] = nj ? atomicAdd(&counts[d], nj) : 0ull;
+            s_h[d] = nh ? atomicAdd(&counts[sp.n_parts + d], nh) : 0ull;
+        }
+        __syncthreads();
+        if (j < n_keys && lane == 0 && !foreign) jrow_of[j] = NOT_EXPORTED;
+        if (foreign) {
+            if (lane == 0) {
+                jpos += s_j[r.dest];
+                hpos += s_h[r.dest];
+            }
+            jpos = __shfl_sync(0xFFFFFFFFu, jpos, 0);
+            hpos = __shfl_sync(0xFFFFFFFFu, hpos, 0);
+            /* a slot that is too small keeps counting: the owner sees counts beyond the capacity and reports it */
+            const bool fits = jpos < m.cap_j && hpos + r.nz <= m.cap_h;
+            char *box = mail_slot(m, r.dest, m.me);
+            if (lane == 0) {
+                if (fits) mail_junction_rows(box)[jpos] = make_junction_row(t.stat[j], r);
+                jrow_of[j] = fits ? (((uint32_t)r.dest << 24) | (uint32_t)jpos) : (((uint32_t)r.dest << 24) | 0xFFFFFFu);
+                /* disown */
+                JStat *s = &t.stat[j];
+                uint4 *p = reinterpret_cast<uint4 *>(s);
+                p[0] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                p[1] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                p[2] = make_uint4(0u, 0u, 0u, 0u);
+                p[3] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+                t.olog_cnt[j] = 0u;
+            }
+            if (fits) write_dense_rows(mail_hist_rows(m, box), hpos + (r.incl - r.mine), (uint32_t)jpos, r, lane);
+            if (t.dense && r.nz) {
+                uint4 *row = reinterpret_cast<uint4 *>(t.dense + j * DENSE_W);
+                row[lane * 2] = make_uint4(0u, 0u, 0u, 0u);
+                row[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/* the log entries of the exported junctions follow them; they are struck from the local log */
+__global__ void __launch_bounds__(256) k_mail_olog(Tables t, Splitters sp, Mailboxes m, unsigned long long *counts, const uint32_t *jrow_of) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_threads = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_olog = log_entries_in_use(t), n_round = (n_olog + 31ull) & ~31ull;
+    const uint64_t n_keys = junctions_in_use(t);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += n_threads) {
+        int dest = -1 - lane; /* idle lanes group with nobody */
+        unsigned long long e = EMPTY64;
+        uint32_t jrow = 0u;
+        if (i < n_olog) {
+            e = t.olog[i];
+            const uint32_t j = (uint32_t)(e >> 32);
+            if (j < n_keys) {
+                const uint32_t v = jrow_of[j];
+                if (v != NOT_EXPORTED) {
+                    dest = (int)(v >> 24);
+                    jrow = v & 0xFFFFFFu;
+                    t.olog[i] = EMPTY64; /* names no junction any more */
+                }
+            }
+        }
+        /* one atomic per (warp, destination) */
+        const unsigned grp = __match_any_sync(0xFFFFFFFFu, dest);
+        const int leader = __ffs(grp) - 1;
+        unsigned long long base = 0ull;
+        if (dest >= 0 && lane == leader) base = atomicAdd(&counts[sp.n_parts + dest], (unsigned long long)__popc(grp));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        const uint64_t at = base + __popc(grp & ((1u << lane) - 1u));
+        if (dest >= 0 && at < m.cap_h && jrow != 0xFFFFFFu) {
+            HistRow h;
+            h.jrow = jrow; h.offset = (uint16_t)((e >> 16) & 0xFFFFull); h.cnt = (uint16_t)(e & 0xFFFFull);
+            mail_hist_rows(m, mail_slot(m, dest, m.me))[at] = h;
+        }
+    }
+}
+
+/* header of a slot: [0] junction rows, [1] offset rows, [2] epoch of the exchange they belong to */
+__global__ void k_mail_publish(Mailboxes m, const unsigned long long *counts) {
+    const int d = threadIdx.x;
+    if (d >= m.world || d == m.me) return;
+    volatile unsigned long long *hdr = reinterpret_cast<volatile unsigned long long *>(mail_slot(m, d, m.me));
+    hdr[0] = counts[d];
+    hdr[1] = counts[m.world + d];
+    __threadfence_system(); /* rows (earlier kernels of this stream) and counts before the epoch */
+    hdr[2] = m.epoch;
+}
+
+void launch_mail_export(const Tables &t, const uint32_t *name_rank, const Splitters &sp, const Mailboxes &m, unsigned long long *counts,
+                        uint32_t *jrow_of, int sm_count, cudaStream_t st) {
+    k_mail_rows<<<sm_count * 8, 256, 0, st>>>(t, name_rank, sp, m, counts, jrow_of);
+    k_mail_olog<<<sm_count * 8, 256, 0, st>>>(t, sp, m, counts, jrow_of);
+    k_mail_publish<<<1, MAX_PARTS, 0, st>>>(m, counts);
+}
+
+/* One warp: lane s waits until source s has published this exchange's epoch into its slot here (every rank enqueues
+ * its export before its import, so nobody waits for a kernel that waits for it), then decides whether everything that
+ * was sent fits the slots and this rank's tables.  verdict[0] = 1 go / 2 refused; verdict[1..2] = rows arriving. */
+__global__ void k_mail_wait(Tables t, Mailboxes m, unsigned long long *verdict, unsigned long long timeout_ns) {
+    const int s = threadIdx.x;
+    unsigned long long nj = 0ull, nh = 0ull;
+    bool bad = false;
+    if (s < m.world && s != m.me) {
+        volatile unsigned long long *hdr = reinterpret_cast<volatile unsigned long long *>(mail_slot(m, m.me, s));
+        unsigned long long t0, now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (hdr[2] != m.epoch) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > timeout_ns) {
+                bad = true;
+                atomicOr(t.overflow, OVF_PEER);
+                break;
+            }
+            __nanosleep(200);
+        }
+        __threadfence_system();
+        nj = hdr[0];
+        nh = hdr[1];
+        if (nj > m.cap_j || nh > m.cap_h) {
+            bad = true;
+            atomicOr(t.overflow, OVF_MAIL);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        nj += __shfl_xor_sync(0xFFFFFFFFu, nj, d);
+        nh += __shfl_xor_sync(0xFFFFFFFFu, nh, d);
+    }
+    const bool any_bad = __any_sync(0xFFFFFFFFu, bad);
+    if (threadIdx.x == 0) {
+        bool go = !any_bad;
+        /* all or nothing: a refused import can be repeated after the host has grown the tables */
+        if (go && (junctions_in_use(t) + nj > t.max_j || 2ull * (junctions_in_use(t) + nj) > t.cap_mask + 1ull)) {
+            go = false;
+            atomicOr(t.overflow, OVF_TABLE);
+        }
+        if (go && log_entries_in_use(t) + nh > t.olog_cap) {
+            go = false;
+            atomicOr(t.overflow, OVF_LOG);
+        }
+        verdict[1] = nj;
+        verdict[2] = nh;
+        verdict[0] = go ? 1ull : 2ull;
+    }
+}
+
+/* fold the junction rows of every source (blockIdx.y) out of this rank's own mailbox */
+__global__ void __launch_bounds__(256) k_mail_import_junctions(Tables t, Mailboxes m, const unsigned long long *verdict, uint32_t *jid_of) {
+    const int source = blockIdx.y;
+    if (source == m.me || verdict[0] != 1ull) return;
+    char *box = mail_slot(m, m.me, source);
+    const unsigned long long n_sent = *reinterpret_cast<const unsigned long long *>(box);
+    const JunctionRow *jr = mail_junction_rows(box);
+    uint32_t *ids = jid_of + (uint64_t)source * m.cap_j;
+    const uint64_t n_threads = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sent; i += n_threads) ids[i] = import_junction_row(t, jr[i]);
+}
+
+__global__ void __launch_bounds__(256) k_mail_import_hist(Tables t, Mailboxes m, const unsigned long long *verdict, const uint32_t *jid_of) {
+    __shared__ unsigned long long s_stage[8][LOG_STAGE];
+    const int source = blockIdx.y;
+    if (source == m.me || verdict[0] != 1ull) return;
+    char *box = mail_slot(m, m.me, source);
+    const unsigned long long nj = reinterpret_cast<const unsigned long long *>(box)[0];
+    const unsigned long long n_sent = reinterpret_cast<const unsigned long long *>(box)[1];
+    const HistRow *hr = mail_hist_rows(m, box);
+    const uint32_t *ids = jid_of + (uint64_t)source * m.cap_j;
+    const uint64_t n_threads = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n_sent + 31ull) & ~31ull;
+    LogStage log{s_stage[threadIdx.x >> 5], 0u};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += n_threads) {
+        uint32_t j = JID_NONE, off = 0u, cnt = 0u;
+        if (i < n_sent) {
+            const HistRow r = hr[i];
+            if (r.jrow < nj) j = ids[r.jrow];
+            off = r.offset;
+            cnt = r.cnt;
+        }
+        const bool ok = j != JID_NONE && cnt != 0u;
+        const bool in_row = t.dense != nullptr && off < DENSE_W;
+        if (ok && in_row) atomicAdd(&t.dense[(uint64_t)j * DENSE_W + off], cnt);
+        log_append(t, log, ok && !in_row, olog_entry(j, off, cnt));
+    }
+    log_flush(t, log);
+}
+
+void launch_mail_import(const Tables &t, const Mailboxes &m, unsigned long long *verdict, uint32_t *jid_of, int sm_count,
+                        unsigned long long timeout_ns, cudaStream_t st) {
+    k_mail_wait<<<1, 32, 0, st>>>(t, m, verdict, timeout_ns);
+    if (m.world < 2) return;
+    const unsigned per_source = (unsigned)((sm_count * 4 + m.world - 2) / (m.world - 1));
+    k_mail_import_junctions<<<dim3(per_source ? per_source : 1, m.world), 256, 0, st>>>(t, m, verdict, jid_of);
+    k_mail_import_hist<<<dim3(per_source ? 2 * per_source : 1, m.world), 256, 0, st>>>(t, m, verdict, jid_of);
+}
+
+/* ---- canon filter across ranks ---- */
+__global__ void k_export_thresholds(Tables t, ThresholdRow *rows, uint64_t n) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned long long key = t.jkey[j];
+    ThresholdRow r;
+    r.tid = t.jtid[j];
+    r.i0 = key_start(t.kl, key);
+    r.i1 = r.i0 + key_len(t.kl, key);
+    r.pad = 0u;
+    r.T = t.stat[j].T;
+    rows[j] = r;
+}
+
+/* a key known here takes the earliest threshold any rank found (its own included) */
+__global__ void k_import_thresholds(Tables t, const ThresholdRow *rows, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ThresholdRow r = rows[i];
+    if (r.T == EMPTY64) return;
+    const uint32_t j = junction_probe<false>(t, make_key(t.kl, r.tid, r.i0, r.i1), r.tid);
+    if (j != JID_NONE) atomicMin(&t.stat[j].T, r.T);
+}
+
+void launch_export_thresholds(const Tables &t, ThresholdRow *rows, uint64_t n, cudaStream_t st) {
+    if (n) k_export_thresholds<<<blocks_for(n, 256), 256, 0, st>>>(t, rows, n);
+}
+void launch_import_thresholds(const Tables &t, const ThresholdRow *rows, uint64_t n, cudaStream_t st) {
+    if (n) k_import_thresholds<<<blocks_for(n, 256), 256, 0, st>>>(t, rows, n);
+}
+
+/* ---- a sample of the junction keys, for load-balanced splitters ---- */
+__global__ void k_sample_keys(Tables t, uint64_t stride, uint64_t max_out, int32_t *tid, uint32_t *i0, unsigned long long *n_out) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nk = junctions_in_use(t);
+    const uint64_t n = (nk + stride - 1) / stride;
+    if (q == 0) *n_out = n < max_out ? n : max_out;
+    if (q >= n || q >= max_out) return;
+    const uint64_t j = q * stride;
+    tid[q] = t.jtid[j];
+    i0[q] = key_start(t.kl, t.jkey[j]);
+}
+
+void launch_sample_keys(const Tables &t, uint64_t stride, uint64_t max_out, int32_t *tid, uint32_t *i0, unsigned long long *n_out,
+                        cudaStream_t st) {
+    k_sample_keys<<<blocks_for(max_out, 256), 256, 0, st>>>(t, stride ? stride : 1, max_out, tid, i0, n_out);
+}
+
+}  // namespace ipx

@@ -1,0 +1,701 @@
+/* ipx_finalize.cu -- the finished table on the device (sm_100a): key order, sjN ranking, ordered read-offset
+ * histograms, output rows.  One CUDA graph of hand-written kernels over the junction rows in use, never over the
+ * table's capacity, inside buffers of grow-only bounds (see FinalizeWork); no library sort.
+ *
+ *   key order   (chromosome-name rank, intron_start, intron_end) -- the iteration order of the reference's
+ *               JunctionTable (junctions.hh:77-100,225-246) -- by a sample sort: splitters from a sorted sample (one
+ *               block), one scatter pass into buckets of ~512 keys, one block per bucket sorting in shared memory
+ *   sjN         rank of the creating event's stream position (junctions_extractor.cc:458-460), the same sort on T
+ *   histograms  Junction::read_offsets (junctions.hh:120) in run-length form, ascending offset: the dense row gives the
+ *               offsets < DENSE_W in order; the junction's entries of the read-offset log are gathered into a private
+ *               segment (their number is known per junction: olog_cnt), ordered there -- a warp's bitonic sort in
+ *               shared memory for up to FIN_SMALL entries, a 65536-bin bitmap + counter pass by a block for the
+ *               few junctions with more -- and run-length reduced in place
+ * The three chains run as parallel branches of the graph and join in the row gather; an exclusive scan of the runs per
+ * junction (ipx_scan.cuh) gives hist_off, and a last pass writes the runs.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "ipx_engine.h"
+#include "ipx_motif.cuh"
+#include "ipx_scan.cuh"
+
+namespace ipx {
+
+enum : unsigned long long { FLAG_B = 1ull, FLAG_L = 2ull, FLAG_R = 4ull, FLAG_C = 8ull };
+/* d_count: 0 junctions, 1 histogram runs, 2 log-segment cursor, 3 flags, 4 junction ids in use, 5 log entries in use,
+ *          6 junctions whose log entries need the block pass, 7 largest bucket seen */
+
+__global__ void k_fin_begin(Tables t, unsigned long long *d_count, uint64_t B, uint64_t L) {
+    const unsigned long long nk = junctions_in_use(t), nl = log_entries_in_use(t);
+    d_count[0] = d_count[1] = d_count[2] = 0ull;
+    d_count[3] = (nk > B ? FLAG_B : 0ull) | (nl > L ? FLAG_L : 0ull);
+    d_count[4] = nk;
+    d_count[5] = nl;
+    d_count[6] = d_count[7] = 0ull;
+}
+
+/* per junction id: the two sort keys, and a private segment for its log entries */
+__global__ void __launch_bounds__(256) k_fin_list(Tables t, const uint32_t *name_rank, uint64_t B, unsigned long long *d_count,
+                                                  unsigned long long *sort_key, uint32_t *sort_sub, unsigned long long *tkey,
+                                                  uint32_t *seg_off, uint32_t *seg_fill) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint64_t nk = d_count[4] < B ? d_count[4] : B;
+    bool take = false;
+    uint32_t lc = 0u;
+    unsigned long long sk = EMPTY64, tk = EMPTY64;
+    uint32_t sub = 0u;
+    if (j < nk) {
+        const unsigned long long T = t.stat[j].T;
+        take = T != EMPTY64; /* keys whose every event was rejected by the canon filter are not junctions */
+        if (take) {
+            const unsigned long long key = t.jkey[j];
+            sk = ((unsigned long long)name_rank[t.jtid[j]] << 31) | key_start(t.kl, key);
+            sub = key_len(t.kl, key);
+            tk = T >> 8;
+            lc = t.olog_cnt[j];
+        }
+    }
+    uint32_t incl = lc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    unsigned long long seg0 = 0ull;
+    const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (lane == 31 && warp_total) seg0 = atomicAdd(&d_count[2], (unsigned long long)warp_total);
+    seg0 = __shfl_sync(0xFFFFFFFFu, seg0, 31);
+    if (j < B) {
+        sort_key[j] = sk;
+        sort_sub[j] = sub;
+        tkey[j] = tk;
+        seg_off[j] = (uint32_t)(seg0 + incl - lc);
+        seg_fill[j] = 0u;
+    }
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, take);
+    if (mask && lane == 0) atomicAdd(&d_count[0], (unsigned long long)__popc(mask));
+}
+
+/* ------------------------------------------------------------------ sample sort of (u64 key, u32 sub-key) -> u32 value
+ * Keys equal to EMPTY64 are not part of the input.  (key, sub) pairs are unique. */
+static const int SS_MAX_BUCKETS = 4096;
+static const int SS_MAX_SAMPLE = 8192;
+static const int SS_SMEM_BUCKET = 4096; /* elements a bucket may have to be sorted in shared memory */
+
+struct SampleSort {
+    unsigned long long *splitters; /* [SS_MAX_BUCKETS] */
+    uint32_t *bucket_cnt;          /* [SS_MAX_BUCKETS + 1]: counts, then the number of buckets */
+    unsigned long long *bk;        /* [P_bound * C] */
+    uint32_t *bs, *bv;             /* [P_bound * C] */
+    uint64_t C;                    /* capacity of a bucket in bk / bs / bv */
+};
+
+__device__ __forceinline__ bool pair_less(unsigned long long ka, uint32_t sa, unsigned long long kb, uint32_t sb) {
+    return ka < kb || (ka == kb && sa < sb);
+}
+
+/* bitonic sort of n = 2^k elements in shared memory by the whole block */
+template <bool WITH_PAYLOAD>
+__device__ __forceinline__ void block_bitonic(unsigned long long *k, uint32_t *s, uint32_t *v, uint32_t n) {
+    for (uint32_t size = 2u; size <= n; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0u; stride >>= 1) {
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < (n >> 1); i += blockDim.x) {
+                const uint32_t lo = 2u * i - (i & (stride - 1u)); /* index with bit `stride` clear */
+                const uint32_t hi = lo + stride;
+                const bool up = (lo & size) == 0u;
+                const unsigned long long ka = k[lo], kb = k[hi];
+                uint32_t sa = 0u, sb = 0u;
+                if (WITH_PAYLOAD) { sa = s[lo]; sb = s[hi]; }
+                const bool swap = up ? pair_less(kb, sb, ka, sa) : pair_less(ka, sa, kb, sb);
+                if (swap) {
+                    k[lo] = kb; k[hi] = ka;
+                    if (WITH_PAYLOAD) {
+                        s[lo] = sb; s[hi] = sa;
+                        const uint32_t x = v[lo]; v[lo] = v[hi]; v[hi] = x;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+/* one block: a sorted sample of the keys -> splitters; also resets the bucket counters */
+__global__ void __launch_bounds__(1024) k_ss_sample(const unsigned long long *keys, const unsigned long long *n_ptr, uint64_t bound,
+                                                    SampleSort ss) {
+    extern __shared__ unsigned long long s_sample[];
+    const uint64_t n = *n_ptr < bound ? *n_ptr : bound;
+    uint32_t P = (uint32_t)((n + 511) / 512);
+    if (P < 1u) P = 1u;
+    if (P > (uint32_t)SS_MAX_BUCKETS) P = SS_MAX_BUCKETS;
+    uint64_t S = 4ull * P;
+    if (S > (uint64_t)SS_MAX_SAMPLE) S = SS_MAX_SAMPLE;
+    if (S > n) S = n;
+    uint32_t S2 = 1u;
+    while (S2 < S) S2 <<= 1;
+    if (S2 < 2u) S2 = 2u;
+    for (uint32_t i = threadIdx.x; i < S2; i += blockDim.x) s_sample[i] = i < S ? keys[(uint64_t)i * n / S] : EMPTY64;
+    for (uint32_t i = threadIdx.x; i <= (uint32_t)SS_MAX_BUCKETS; i += blockDim.x) ss.bucket_cnt[i] = i == (uint32_t)SS_MAX_BUCKETS ? P : 0u;
+    block_bitonic<false>(s_sample, nullptr, nullptr, S2);
+    /* splitter p = first key of bucket p + 1; padding and keys that are not part of the input (EMPTY64) sort last and
+     * make empty buckets */
+    for (uint32_t p = threadIdx.x; p + 1u < P; p += blockDim.x) ss.splitters[p] = S ? s_sample[(uint64_t)(p + 1u) * S / P] : EMPTY64;
+}
+
+/* every key into its bucket: the number of splitters <= key */
+__global__ void __launch_bounds__(256) k_ss_scatter(const unsigned long long *keys, const uint32_t *sub, const unsigned long long *n_ptr,
+                                                    uint64_t bound, SampleSort ss, unsigned long long *d_count) {
+    __shared__ unsigned long long s_split[SS_MAX_BUCKETS];
+    const uint32_t P = ss.bucket_cnt[SS_MAX_BUCKETS];
+    for (uint32_t p = threadIdx.x; p + 1u < P; p += blockDim.x) s_split[p] = ss.splitters[p];
+    __syncthreads();
+    const uint64_t n = *n_ptr < bound ? *n_ptr : bound;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = keys[i];
+    if (key == EMPTY64) return;
+    uint32_t lo = 0u, hi = P - 1u; /* number of splitters <= key lies in [lo, hi] */
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_split[mid] <= key) lo = mid + 1u; else hi = mid;
+    }
+    const uint32_t pos = atomicAdd(&ss.bucket_cnt[lo], 1u);
+    if (pos < ss.C) {
+        const uint64_t at = (uint64_t)lo * ss.C + pos;
+        ss.bk[at] = key;
+        ss.bs[at] = sub ? sub[i] : 0u;
+        ss.bv[at] = (uint32_t)i;
+    } else {
+        atomicOr(&d_count[3], FLAG_C);
+        atomicMax(&d_count[7], (unsigned long long)pos + 1ull);
+    }
+}
+
+/* one block per bucket: sort it, write the values at the bucket's place in the global order (and, when asked, the
+ * position of every value).  A bucket that does not fit shared memory is ranked by counting (quadratic: only a
+ * pathological input makes such buckets). */
+__global__ void __launch_bounds__(512) k_ss_local(SampleSort ss, uint32_t *out_vals, uint32_t *out_rank) {
+    extern __shared__ unsigned long long s_mem[];
+    __shared__ uint32_t s_part[16];
+    const uint32_t P = ss.bucket_cnt[SS_MAX_BUCKETS];
+    const uint32_t b = blockIdx.x;
+    if (b >= P) return;
+    const uint32_t cnt = ss.bucket_cnt[b] < ss.C ? ss.bucket_cnt[b] : (uint32_t)ss.C;
+    /* where the bucket starts: the sizes of the buckets before it */
+    uint32_t before = 0u;
+    for (uint32_t p = threadIdx.x; p < b; p += blockDim.x) before += ss.bucket_cnt[p] < ss.C ? ss.bucket_cnt[p] : (uint32_t)ss.C;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, d);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = before;
+    __syncthreads();
+    uint32_t base = 0u;
+    for (uint32_t w = 0; w < blockDim.x / 32; ++w) base += s_part[w];
+    if (cnt == 0u) return;
+    const unsigned long long *gk = ss.bk + (uint64_t)b * ss.C;
+    const uint32_t *gs = ss.bs + (uint64_t)b * ss.C, *gv = ss.bv + (uint64_t)b * ss.C;
+    if (cnt <= (uint32_t)SS_SMEM_BUCKET) {
+        uint32_t n2 = 2u;
+        while (n2 < cnt) n2 <<= 1;
+        unsigned long long *k = s_mem;
+        uint32_t *s = reinterpret_cast<uint32_t *>(s_mem + SS_SMEM_BUCKET);
+        uint32_t *v = s + SS_SMEM_BUCKET;
+        for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
+            k[i] = i < cnt ? gk[i] : EMPTY64;
+            s[i] = i < cnt ? gs[i] : 0xFFFFFFFFu;
+            v[i] = i < cnt ? gv[i] : 0u;
+        }
+        block_bitonic<true>(k, s, v, n2);
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+            out_vals[base + i] = v[i];
+            if (out_rank) out_rank[v[i]] = base + i;
+        }
+    } else {
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const unsigned long long ki = gk[i];
+            const uint32_t si = gs[i];
+            uint32_t rank = 0u;
+            for (uint32_t x = 0; x < cnt; ++x) rank += pair_less(gk[x], gs[x], ki, si) ? 1u : 0u;
+            out_vals[base + rank] = gv[i];
+            if (out_rank) out_rank[gv[i]] = base + rank;
+        }
+    }
+}
+
+static const size_t SS_LOCAL_SMEM = (size_t)SS_SMEM_BUCKET * (8 + 4 + 4);
+
+static cudaError_t sample_sort(const unsigned long long *keys, const uint32_t *sub, const unsigned long long *n_ptr, uint64_t bound,
+                               const SampleSort &ss, uint32_t *out_vals, uint32_t *out_rank, unsigned long long *d_count,
+                               cudaStream_t st) {
+    uint64_t p_bound = (bound + 511) / 512;
+    if (p_bound < 1) p_bound = 1;
+    if (p_bound > (uint64_t)SS_MAX_BUCKETS) p_bound = SS_MAX_BUCKETS;
+    k_ss_sample<<<1, 1024, SS_MAX_SAMPLE * sizeof(unsigned long long), st>>>(keys, n_ptr, bound, ss);
+    k_ss_scatter<<<(unsigned)((bound + 255) / 256), 256, 0, st>>>(keys, sub, n_ptr, bound, ss, d_count);
+    k_ss_local<<<(unsigned)p_bound, 512, SS_LOCAL_SMEM, st>>>(ss, out_vals, out_rank);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ read-offset log -> ordered runs per junction */
+static const uint32_t FIN_SMALL = 256; /* log entries a warp orders in shared memory */
+
+/* every log entry into its junction's segment: offset << 16 | count */
+__global__ void __launch_bounds__(256) k_fin_scatter(Tables t, uint64_t B, uint64_t L, const unsigned long long *d_count,
+                                                     const uint32_t *seg_off, uint32_t *seg_fill, uint32_t *seg) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nl = d_count[5] < L ? d_count[5] : L;
+    if (i >= nl) return;
+    const unsigned long long e = t.olog[i];
+    const uint32_t j = (uint32_t)(e >> 32);
+    /* a junction beyond the bound this finalize was sized for has no segment: the bound is reported as too small
+     * anyway (k_fin_begin) and the finalize runs again */
+    if (j >= B || t.stat[j].T == EMPTY64) return;
+    const uint32_t pos = atomicAdd(&seg_fill[j], 1u);
+    if ((uint64_t)seg_off[j] + pos < L) seg[seg_off[j] + pos] = (uint32_t)e;
+}
+
+__device__ __forceinline__ uint32_t dense_nonzeros(const Tables &t, uint64_t j, int lane) {
+    uint32_t nz = 0u;
+    if (t.dense) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + j * DENSE_W);
+        const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
+        nz = (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0) + (b.x != 0) + (b.y != 0) + (b.z != 0) + (b.w != 0);
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, k);
+    return nz;
+}
+
+/* warp per junction id: non-zero counters of its dense row; its log segment ordered by offset and run-length reduced
+ * in place (the counts of the runs, ascending offset, replace the entries); runs_j = runs of both kinds.  Junctions
+ * with more than FIN_SMALL log entries are left to k_fin_big. */
+__global__ void __launch_bounds__(256) k_fin_small(Tables t, uint64_t B, uint64_t L, unsigned long long *d_count, const uint32_t *seg_off,
+                                                   uint32_t *seg, uint32_t *runs_j, uint32_t *nz_j, uint32_t *big_list) {
+    __shared__ uint32_t s_w[8][FIN_SMALL];
+    __shared__ uint32_t s_c[8][FIN_SMALL];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nk = d_count[4] < B ? d_count[4] : B;
+    if (j >= nk) return;
+    if (t.stat[j].T == EMPTY64) {
+        if (lane == 0) { runs_j[j] = 0u; nz_j[j] = 0u; }
+        return;
+    }
+    const uint32_t nz = dense_nonzeros(t, j, lane);
+    const uint32_t n = t.olog_cnt[j];
+    const uint64_t s0 = seg_off[j];
+    if (n == 0u || s0 + n > L) { /* (beyond L: the bound was too small, the finalize runs again) */
+        if (lane == 0) { runs_j[j] = nz; nz_j[j] = nz; }
+        return;
+    }
+    if (n > FIN_SMALL) {
+        if (lane == 0) {
+            nz_j[j] = nz;
+            big_list[atomicAdd(&d_count[6], 1ull)] = (uint32_t)j;
+        }
+        return;
+    }
+    uint32_t *w = s_w[warp], *c = s_c[warp];
+    uint32_t n2 = 2u;
+    while (n2 < n) n2 <<= 1;
+    for (uint32_t i = lane; i < n2; i += 32u) w[i] = i < n ? seg[s0 + i] : 0xFFFFFFFFu;
+    for (uint32_t size = 2u; size <= n2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0u; stride >>= 1) {
+            __syncwarp();
+            for (uint32_t i = lane; i < (n2 >> 1); i += 32u) {
+                const uint32_t lo = 2u * i - (i & (stride - 1u)), hi = lo + stride;
+                const uint32_t a = w[lo], b = w[hi];
+                if (((lo & size) == 0u) ? (b < a) : (a < b)) { w[lo] = b; w[hi] = a; }
+            }
+        }
+    }
+    __syncwarp();
+    /* runs of equal offsets (the high half of an entry), their counts summed */
+    uint32_t n_runs = 0u;
+    for (uint32_t i0 = 0; i0 < n; i0 += 32u) {
+        const uint32_t i = i0 + lane;
+        const bool valid = i < n;
+        const uint32_t x = valid ? w[i] : 0u;
+        const bool head = valid && (i == 0u || (w[i - 1] >> 16) != (x >> 16));
+        const unsigned hm = __ballot_sync(0xFFFFFFFFu, head);
+        const uint32_t run = n_runs + (uint32_t)__popc(hm & (0xFFFFFFFFu >> (31 - lane))) - 1u;
+        if (head) c[run] = 0u;
+        __syncwarp();
+        if (valid) atomicAdd(&c[run], x & 0xFFFFu);
+        n_runs += (uint32_t)__popc(hm);
+        __syncwarp();
+    }
+    for (uint32_t r = lane; r < n_runs; r += 32u) seg[s0 + r] = c[r];
+    if (lane == 0) { runs_j[j] = nz + n_runs; nz_j[j] = nz; }
+}
+
+/* block per junction with many log entries: the entries' counts are summed per offset in a 65536-counter scratch of the
+ * block (global memory, zero between uses) while a bitmap in shared memory remembers which offsets occur; the runs are
+ * then read off the bitmap in ascending order */
+static const int FIN_BIG_BLOCKS = 148 * 2;
+__global__ void __launch_bounds__(256) k_fin_big(Tables t, uint64_t L, const unsigned long long *d_count, const uint32_t *big_list,
+                                                 const uint32_t *seg_off, uint32_t *seg, uint32_t *runs_j, const uint32_t *nz_j,
+                                                 uint32_t *scratch) {
+    __shared__ uint32_t s_bits[2048];
+    __shared__ uint32_t s_warp[8];
+    uint32_t *cnt = scratch + (uint64_t)blockIdx.x * 65536u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t n_big = d_count[6];
+    for (uint64_t q = blockIdx.x; q < n_big; q += gridDim.x) {
+        const uint32_t j = big_list[q];
+        const uint32_t n = t.olog_cnt[j];
+        const uint64_t s0 = seg_off[j];
+        for (uint32_t i = threadIdx.x; i < 2048u; i += blockDim.x) s_bits[i] = 0u;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t x = seg[s0 + i];
+            const uint32_t off = x >> 16;
+            atomicOr(&s_bits[off >> 5], 1u << (off & 31u));
+            atomicAdd(&cnt[off], x & 0xFFFFu);
+        }
+        __threadfence();
+        __syncthreads();
+        /* thread i owns bitmap words [8 i, 8 i + 8) */
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mine += (uint32_t)__popc(s_bits[threadIdx.x * 8 + k]);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t pre = incl - mine, total = 0u;
+#pragma unroll
+        for (int w2 = 0; w2 < 8; ++w2) {
+            if (w2 < warp) pre += s_warp[w2];
+            total += s_warp[w2];
+        }
+        /* total <= n: the runs fit where the entries were */
+        for (int k = 0; k < 8; ++k) {
+            uint32_t bits = s_bits[threadIdx.x * 8 + k];
+            while (bits) {
+                const uint32_t bit = (uint32_t)__ffs(bits) - 1u;
+                bits &= bits - 1u;
+                const uint32_t off = ((uint32_t)threadIdx.x * 8u + (uint32_t)k) * 32u + bit;
+                seg[s0 + pre++] = __ldcg(&cnt[off]);
+                cnt[off] = 0u;
+            }
+        }
+        if (threadIdx.x == 0) runs_j[j] = nz_j[j] + total;
+        __syncthreads();
+    }
+    (void)L;
+}
+
+/* ------------------------------------------------------------------ output rows */
+/* one output row per junction, in key order: attributes of the creating event after motif correction
+ * (get_splice_sites + correct_strand, junctions_extractor.cc:419-444); rows [n_j, B] get zero runs for the scan */
+__global__ void __launch_bounds__(256) k_fin_rows(Tables t, GenomeView g, uint64_t B, const uint32_t *order, const unsigned long long *d_count,
+                                                  const uint32_t *t_rank, const uint32_t *runs_j, uint32_t *runs_r, DeviceTable out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > B) return;
+    if (i >= d_count[0] || i >= B) {
+        runs_r[i] = 0u;
+        return;
+    }
+    const uint32_t j = order[i];
+    runs_r[i] = runs_j[j];
+    out.ijunc[i] = t_rank[j];
+    const unsigned long long key = t.jkey[j];
+    const JStat s = t.stat[j];
+    const int32_t tid = t.jtid[j];
+    const uint32_t i0 = key_start(t.kl, key), i1 = i0 + key_len(t.kl, key);
+    out.chrom[i] = tid;
+    out.i0[i] = i0;
+    out.i1[i] = i1;
+    out.a0[i] = s.a0;
+    out.a1[i] = s.a1;
+    out.counts[3 * i + 0] = s.cnt[0];
+    out.counts[3 * i + 1] = s.cnt[1];
+    out.counts[3 * i + 2] = s.cnt[2];
+    out.T[i] = s.T;
+    char strand = (char)(s.T & 0xFFull);
+    char site[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    char f[4];
+    if (motif_fetch(g, tid, i0, i1, f) == MOTIF_OK) {
+        char d0 = f[0], d1 = f[1], a0 = f[2], a1 = f[3];
+        const char r0 = comp(f[3]), r1 = comp(f[2]), r2 = comp(f[1]), r3 = comp(f[0]);
+        bool canon;
+        if (strand == '-') {
+            d0 = r0; d1 = r1; a0 = r2; a1 = r3;
+            canon = canon4(d0, d1, a0, a1);
+        } else if (strand == '.') {
+            canon = canon4(d0, d1, a0, a1);
+            if (canon) {
+                strand = '+';
+            } else if (canon4(r0, r1, r2, r3)) {
+                strand = '-';
+                d0 = r0; d1 = r1; a0 = r2; a1 = r3;
+                canon = true;
+            }
+        } else {
+            canon = canon4(d0, d1, a0, a1);
+        }
+        if (!canon) { d0 = low(d0); d1 = low(d1); a0 = low(a0); a1 = low(a1); }
+        site[0] = d0; site[1] = d1; site[2] = '/'; site[3] = a0; site[4] = a1;
+    }
+    out.strand[i] = strand;
+    for (int k = 0; k < 8; ++k) out.sites[8 * i + k] = site[k];
+}
+
+struct RunsIn {
+    const uint32_t *runs_r;
+    __device__ __forceinline__ unsigned long long operator()(uint64_t i) const { return runs_r[i]; }
+};
+
+/* warp per junction, key order: its runs in ascending offset order -- dense row first (offsets < DENSE_W), then the
+ * ordered runs of its log segment (offsets >= DENSE_W, or every offset when the table has no dense rows) */
+__global__ void __launch_bounds__(256) k_fin_write(Tables t, uint64_t B, uint64_t R, const uint32_t *order, unsigned long long *d_count,
+                                                   const unsigned long long *hist_off, const uint32_t *nz_j, const uint32_t *seg_off,
+                                                   const uint32_t *seg, uint32_t *hist_cnt) {
+    const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long n_runs = hist_off[B]; /* rows beyond the junctions count zero runs */
+    if (r == 0 && lane == 0) {
+        d_count[1] = n_runs;
+        if (n_runs > R) atomicOr(&d_count[3], FLAG_R);
+    }
+    if (n_runs > R) return; /* does not fit: the host grows R and replays */
+    if (r >= d_count[0] || r >= B) return;
+    const uint32_t j = order[r];
+    const unsigned long long o0 = hist_off[r], o1 = hist_off[r + 1];
+    const uint32_t nz = nz_j[j];
+    if (t.dense && nz) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)j * DENSE_W);
+        const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
+        const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mine += (v[k] != 0);
+        uint32_t pre = mine;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, pre, k);
+            if (lane >= k) pre += y;
+        }
+        uint64_t o = o0 + (pre - mine);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (v[k] != 0) hist_cnt[o++] = v[k];
+        }
+    }
+    const unsigned long long n_log = (o1 - o0) - nz;
+    const uint64_t s0 = seg_off[j];
+    for (unsigned long long q = lane; q < n_log; q += 32) hist_cnt[o0 + nz + q] = seg[s0 + q];
+}
+
+/* ------------------------------------------------------------------ host side */
+#define IPX_CU(x)                          \
+    do {                                   \
+        cudaError_t e__ = (x);             \
+        if (e__ != cudaSuccess) return e__; \
+    } while (0)
+
+static inline unsigned blocks_for(uint64_t n, unsigned threads) {
+    uint64_t b = (n + threads - 1) / threads;
+    return (unsigned)(b ? b : 1);
+}
+
+/* a bound for v with some headroom: v plus an eighth, rounded up to a multiple of 4096, at least floor_ */
+static inline uint64_t bound_for(uint64_t v, uint64_t floor_) {
+    uint64_t b = ((v + v / 8 + 4095) / 4096) * 4096;
+    return b > floor_ ? b : floor_;
+}
+
+template <class T>
+static cudaError_t regrow(T **p, size_t count) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    return cudaMalloc((void **)p, (count ? count : 1) * sizeof(T));
+}
+
+void finalize_release(FinalizeWork &w) {
+    if (w.exec) cudaGraphExecDestroy(w.exec);
+    w.exec = nullptr;
+    cudaFree(w.sort_key); cudaFree(w.sort_sub); cudaFree(w.tkey); cudaFree(w.order); cudaFree(w.t_order); cudaFree(w.t_rank);
+    cudaFree(w.seg_off); cudaFree(w.seg_fill); cudaFree(w.runs_j); cudaFree(w.nz_j); cudaFree(w.big_list); cudaFree(w.runs_r);
+    cudaFree(w.seg); cudaFree(w.big_scratch); cudaFree(w.scan_state); cudaFree(w.d_count);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(w.ss_splitters[k]); cudaFree(w.ss_bucket_cnt[k]); cudaFree(w.ss_bk[k]); cudaFree(w.ss_bs[k]); cudaFree(w.ss_bv[k]);
+    }
+    if (w.s2) cudaStreamDestroy(w.s2);
+    if (w.s3) cudaStreamDestroy(w.s3);
+    if (w.ev_fork) cudaEventDestroy(w.ev_fork);
+    if (w.ev_join2) cudaEventDestroy(w.ev_join2);
+    if (w.ev_join3) cudaEventDestroy(w.ev_join3);
+    if (w.h_count) cudaFreeHost(w.h_count);
+    DeviceTable &o = w.out;
+    cudaFree(o.chrom); cudaFree(o.i0); cudaFree(o.i1); cudaFree(o.a0); cudaFree(o.a1); cudaFree(o.ijunc); cudaFree(o.strand);
+    cudaFree(o.sites); cudaFree(o.counts); cudaFree(o.T); cudaFree(o.hist_off); cudaFree(o.hist_cnt);
+    w = FinalizeWork();
+}
+
+static uint64_t bucket_bound(uint64_t B) {
+    uint64_t p = (B + 511) / 512;
+    if (p < 1) p = 1;
+    return p > (uint64_t)SS_MAX_BUCKETS ? (uint64_t)SS_MAX_BUCKETS : p;
+}
+
+/* (re)allocate everything whose size follows the bounds */
+static cudaError_t finalize_allocate(FinalizeWork &w, uint64_t B, uint64_t L, uint64_t R, uint64_t C) {
+    if (!w.d_count) IPX_CU(cudaMalloc(&w.d_count, 8 * sizeof(unsigned long long)));
+    if (!w.h_count) IPX_CU(cudaMallocHost(&w.h_count, 8 * sizeof(unsigned long long)));
+    if (!w.s2) {
+        IPX_CU(cudaStreamCreateWithFlags(&w.s2, cudaStreamNonBlocking));
+        IPX_CU(cudaStreamCreateWithFlags(&w.s3, cudaStreamNonBlocking));
+        IPX_CU(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming));
+        IPX_CU(cudaEventCreateWithFlags(&w.ev_join2, cudaEventDisableTiming));
+        IPX_CU(cudaEventCreateWithFlags(&w.ev_join3, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) {
+            IPX_CU(regrow(&w.ss_splitters[k], SS_MAX_BUCKETS));
+            IPX_CU(regrow(&w.ss_bucket_cnt[k], SS_MAX_BUCKETS + 1));
+        }
+        IPX_CU(cudaMalloc(&w.big_scratch, (size_t)FIN_BIG_BLOCKS * 65536 * sizeof(uint32_t)));
+        IPX_CU(cudaMemset(w.big_scratch, 0, (size_t)FIN_BIG_BLOCKS * 65536 * sizeof(uint32_t)));
+        IPX_CU(cudaFuncSetAttribute(k_ss_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SS_MAX_SAMPLE * sizeof(unsigned long long))));
+        IPX_CU(cudaFuncSetAttribute(k_ss_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_LOCAL_SMEM));
+    }
+    if (B != w.B || C != w.C) {
+        const uint64_t cells = bucket_bound(B) * C;
+        for (int k = 0; k < 2; ++k) {
+            IPX_CU(regrow(&w.ss_bk[k], cells)); IPX_CU(regrow(&w.ss_bs[k], cells)); IPX_CU(regrow(&w.ss_bv[k], cells));
+        }
+        w.C = C;
+    }
+    if (B != w.B) {
+        IPX_CU(regrow(&w.sort_key, B)); IPX_CU(regrow(&w.sort_sub, B)); IPX_CU(regrow(&w.tkey, B)); IPX_CU(regrow(&w.order, B));
+        IPX_CU(regrow(&w.t_order, B)); IPX_CU(regrow(&w.t_rank, B)); IPX_CU(regrow(&w.seg_off, B)); IPX_CU(regrow(&w.seg_fill, B));
+        IPX_CU(regrow(&w.runs_j, B)); IPX_CU(regrow(&w.nz_j, B)); IPX_CU(regrow(&w.big_list, B)); IPX_CU(regrow(&w.runs_r, B + 1));
+        IPX_CU(regrow(&w.scan_state, scan_state_words(B + 1)));
+        DeviceTable &o = w.out;
+        IPX_CU(regrow(&o.chrom, B)); IPX_CU(regrow(&o.i0, B)); IPX_CU(regrow(&o.i1, B)); IPX_CU(regrow(&o.a0, B));
+        IPX_CU(regrow(&o.a1, B)); IPX_CU(regrow(&o.ijunc, B)); IPX_CU(regrow(&o.strand, B)); IPX_CU(regrow(&o.sites, B * 8));
+        IPX_CU(regrow(&o.counts, B * 3)); IPX_CU(regrow(&o.T, B)); IPX_CU(regrow(&o.hist_off, B + 2));
+        w.B = B;
+    }
+    if (L != w.L) {
+        IPX_CU(regrow(&w.seg, L));
+        w.L = L;
+    }
+    if (R != w.R) {
+        IPX_CU(regrow(&w.out.hist_cnt, R));
+        w.R = R;
+    }
+    return cudaSuccess;
+}
+
+/* the sequence itself, issued into `st` (under stream capture, or directly when capture is not possible) */
+static cudaError_t finalize_issue(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, FinalizeWork &w, cudaStream_t st) {
+    const uint64_t B = w.B, L = w.L, R = w.R;
+    DeviceTable &out = w.out;
+    launch_resolve_T(t, g, st); /* creation thresholds for anything still unresolved */
+    k_fin_begin<<<1, 1, 0, st>>>(t, w.d_count, B, L);
+    k_fin_list<<<blocks_for(B, 256), 256, 0, st>>>(t, d_name_rank, B, w.d_count, w.sort_key, w.sort_sub, w.tkey, w.seg_off, w.seg_fill);
+    /* three independent chains from here: key order (st), sjN ranking (s2), read-offset log (s3) */
+    IPX_CU(cudaEventRecord(w.ev_fork, st));
+    IPX_CU(cudaStreamWaitEvent(w.s2, w.ev_fork, 0));
+    IPX_CU(cudaStreamWaitEvent(w.s3, w.ev_fork, 0));
+    const unsigned long long *n_ptr = w.d_count + 4;
+
+    /* st: key order -- chromosome-name rank, intron_start, intron_end */
+    SampleSort ssa{w.ss_splitters[0], w.ss_bucket_cnt[0], w.ss_bk[0], w.ss_bs[0], w.ss_bv[0], w.C};
+    IPX_CU(sample_sort(w.sort_key, w.sort_sub, n_ptr, B, ssa, w.order, nullptr, w.d_count, st));
+
+    /* s2: sjN = rank of the creating event in stream order */
+    SampleSort ssb{w.ss_splitters[1], w.ss_bucket_cnt[1], w.ss_bk[1], w.ss_bs[1], w.ss_bv[1], w.C};
+    IPX_CU(sample_sort(w.tkey, nullptr, n_ptr, B, ssb, w.t_order, w.t_rank, w.d_count, w.s2));
+    IPX_CU(cudaEventRecord(w.ev_join2, w.s2));
+
+    /* s3: the log entries gathered per junction, ordered and run-length reduced */
+    k_fin_scatter<<<blocks_for(L, 256), 256, 0, w.s3>>>(t, B, L, w.d_count, w.seg_off, w.seg_fill, w.seg);
+    k_fin_small<<<blocks_for(B * 32, 256), 256, 0, w.s3>>>(t, B, L, w.d_count, w.seg_off, w.seg, w.runs_j, w.nz_j, w.big_list);
+    k_fin_big<<<FIN_BIG_BLOCKS, 256, 0, w.s3>>>(t, L, w.d_count, w.big_list, w.seg_off, w.seg, w.runs_j, w.nz_j, w.big_scratch);
+    IPX_CU(cudaEventRecord(w.ev_join3, w.s3));
+
+    /* join: rows in key order (motif, strand correction, sjN), then the histograms */
+    IPX_CU(cudaStreamWaitEvent(st, w.ev_join2, 0));
+    IPX_CU(cudaStreamWaitEvent(st, w.ev_join3, 0));
+    k_fin_rows<<<blocks_for(B + 1, 256), 256, 0, st>>>(t, g, B, w.order, w.d_count, w.t_rank, w.runs_j, w.runs_r, out);
+    IPX_CU(scan_exclusive(RunsIn{w.runs_r}, out.hist_off, B + 1, w.scan_state, st));
+    k_fin_write<<<blocks_for(B * 32, 256), 256, 0, st>>>(t, B, R, w.order, w.d_count, out.hist_off, w.nz_j, w.seg_off, w.seg, out.hist_cnt);
+    IPX_CU(cudaMemcpyAsync(w.h_count, w.d_count, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    w.launches_per_replay = 16;
+    return cudaGetLastError();
+}
+
+cudaError_t finalize_enqueue(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, FinalizeWork &w, cudaStream_t st) {
+    uint64_t B = w.B ? w.B : w.first_B, L = w.L ? w.L : w.first_L, R = w.R ? w.R : w.first_R, C = w.C ? w.C : 2048;
+    if (w.wish_B > B) B = w.wish_B;
+    if (w.wish_L > L) L = w.wish_L;
+    if (w.wish_R > R) R = w.wish_R;
+    if (w.wish_C > C) C = w.wish_C;
+    FinalizeWork::Key key{};
+    key.B = B; key.L = L; key.R = R; key.C = C;
+    key.tab_keys = t.keys; key.tab_rows = t.stat; key.tab_log = t.olog; key.max_j = t.max_j; key.olog_cap = t.olog_cap;
+    key.name_rank = d_name_rank; key.gseq = g.seq; key.target_seq = g.target_seq; key.dense = t.dense;
+    key.n_targets = g.n_targets; key.have_genome = g.have_genome; key.skip_missing = g.skip_missing; key.filter_canon = g.filter_canon;
+    key.wide = t.kl.wide; key.len_bits = t.kl.len_bits;
+    if (!w.exec || !(key == w.key)) {
+        IPX_CU(cudaStreamSynchronize(st)); /* a replay may still be running */
+        if (w.exec) {
+            cudaGraphExecDestroy(w.exec);
+            w.exec = nullptr;
+        }
+        IPX_CU(finalize_allocate(w, B, L, R, C));
+        w.key = key;
+        static const bool no_graph = getenv("IPX_NO_GRAPH") != nullptr;
+        if (!no_graph) {
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal); /* s2 / s3 join the capture through the fork event */
+            if (e == cudaSuccess) {
+                cudaError_t ei = finalize_issue(t, g, d_name_rank, w, st);
+                e = cudaStreamEndCapture(st, &graph);
+                if (ei != cudaSuccess) e = ei;
+            }
+            if (e == cudaSuccess && graph) e = cudaGraphInstantiate(&w.exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (e != cudaSuccess) {
+                cudaGetLastError(); /* capture is not available here: issue the sequence directly every time */
+                w.exec = nullptr;
+            }
+        }
+    }
+    if (w.exec) return cudaGraphLaunch(w.exec, st);
+    return finalize_issue(t, g, d_name_rank, w, st);
+}
+
+bool finalize_check(FinalizeWork &w) {
+    const unsigned long long flags = w.h_count[3];
+    if (flags == 0ull) {
+        w.out.n = w.h_count[0];
+        w.out.n_hist = w.h_count[1];
+        return true;
+    }
+    /* grow what was too small; the next finalize_enqueue reallocates and re-captures */
+    if (flags & FLAG_B) w.wish_B = bound_for(w.h_count[4], w.B + 4096);
+    if (flags & FLAG_L) w.wish_L = bound_for(w.h_count[5], w.L + 4096);
+    if (flags & FLAG_R) w.wish_R = bound_for(w.h_count[1], w.R + 4096);
+    if (flags & FLAG_C) {
+        uint64_t c = w.C * 2;
+        while (c < w.h_count[7]) c *= 2;
+        w.wish_C = c;
+    }
+    w.out.n = 0;
+    w.out.n_hist = 0;
+    return false;
+}
+
+}  // namespace ipx

@@ -1,15 +1,21 @@
 /* ipx_table.cuh -- device-resident junction table: the replacement for the reference's
  * std::map<JunctionKey, Junction*> (junctions.hh:225-246) and Junction::read_offsets (junctions.hh:120).
  *
- * Two open-addressing hash tables live in HBM for the whole run (and, being a few tens of MB for
- * real data, mostly in the 126 MB L2):
- *   junction table   key64 -> JStat (64-byte record: per-strand-class first sequence numbers, the
- *                    creation threshold T, read counts by category, min anchor start, max anchor end)
- *   offset table     (junction slot, uint16 read offset) -> count, the run-length form of read_offsets
+ * Layout in HBM (for real data a few tens of MB are live, i.e. mostly resident in the 126 MB L2):
+ *   hash slots     keys[cap] (open addressing, linear probing) -> jid[cap], the junction id of the slot's key
+ *   junction rows  indexed by junction id = order of first insertion, so everything a junction owns is COMPACT:
+ *                  jkey / jtid / jslot (identity), JStat (64-byte record: per-strand-class first sequence numbers, the
+ *                  creation threshold T, read counts by category, min anchor start, max anchor end), a dense row of
+ *                  DENSE_W read-offset counters, and the number of its entries in the read-offset log.
+ *                  clear / finalize / export walk [0, n_keys) with coalesced accesses and never touch the hash slots'
+ *                  capacity; growing the hash (rehash) moves no junction data, growing the rows is a prefix copy.
+ *   read-offset log  (junction id, uint16 read offset, count) entries for the offsets the dense rows do not take.
  *
- * key64 = target index | intron_start (31 bits) | intron length (L bits, L = bits(max_intron_length));
- * junction_qc guarantees length <= max_intron_length (junctions_extractor.cc:392-393) and BAM positions
- * are int32, so the key is exact.  The top bit is always 0, so ~0 is free as the empty marker.
+ * key64 = target index (low bits that fit) | intron_start (31 bits) | intron length (L bits, L = bits(max_intron_length));
+ * junction_qc guarantees length <= max_intron_length (junctions_extractor.cc:392-393) and BAM positions are int32, so
+ * start and length are exact.  When the target index does not fit the bits that are left ("wide" layout: many contigs
+ * or a large --max-intron-length) the slot's identity is (key64, full target index): a slot whose key64 matches is
+ * compared by jtid[jid] as well.  The top bit is always 0, so ~0 is free as the empty marker.
  *
  * Order dependence of the reference is carried by "sequence values":
  *   sv = record stream index (36 bits) | candidate ordinal within the read (20 bits) | strand char (8 bits)
@@ -25,15 +31,15 @@
 namespace ipx {
 
 static const uint64_t EMPTY64 = ~0ull;
+static const uint32_t JID_UNSET = 0xFFFFFFFFu; /* slot claimed, junction id not published yet */
+static const uint32_t JID_FULL = 0xFFFFFFFEu;  /* slot claimed when no junction row was left */
+static const uint32_t JID_NONE = 0xFFFFFFFDu;  /* probe result: absent (lookup) or no room (insert) */
 /* Read offsets (intron_start - read start) of short reads are < read length; counts for offsets below DENSE_W
- * live in a dense row of DENSE_W counters per table slot (1 KB per slot: 4 GB of HBM for the default 4 M slots,
- * touched only where a junction lives), where counting a read is a single fire-and-forget atomic and the ordered
- * run-length output needs no sort.  Larger offsets (long reads) go to the (junction, offset) hash table, as does
- * everything when the table is too large to give every slot a row. */
+ * live in a dense row of DENSE_W counters per junction (1 KB), where counting a read is a single fire-and-forget
+ * atomic and the ordered run-length output needs no sort.  Larger offsets (second junction of a read, long reads)
+ * go to the read-offset log, as does everything when the rows are disabled. */
 static const uint32_t DENSE_W = 256;
-/* log of (slot, offset, count) entries for what the dense rows do not take; sorted and run-length reduced at finalize */
-static const uint64_t OLOG_INVALID = ~0ull;
-static const uint32_t OLOG_BLOCK = 32; /* entries a warp reserves at a time */
+static const uint32_t LOG_STAGE = 128; /* log entries a warp stages in shared memory between reservations */
 static const int SV_ORD_BITS = 20;
 static const int SV_SEQ_SHIFT = 28;
 
@@ -81,20 +87,34 @@ struct alignas(16) Event {
     unsigned long long sv;
     uint32_t a0, a1;  /* anchor_start, anchor_end */
     uint32_t off_cat; /* uint16 read offset | read category << 16 | strand class << 18 */
-    uint32_t pad;
+    int32_t tid;      /* target index (the key holds only its low bits in the wide layout) */
 };
 
 struct KeyLayout {
-    int len_bits;   /* L */
+    int len_bits;    /* L */
     int start_shift; /* = L */
-    int tid_shift;  /* = L + 31 */
-    int tid_bits;   /* 63 - tid_shift */
+    int tid_shift;   /* = L + 31 */
+    int tid_bits;    /* 63 - tid_shift: bits of the target index the key holds */
+    uint32_t tid_mask; /* (1 << tid_bits) - 1 */
+    int wide;        /* the target index does not fit tid_bits: compare jtid as well */
 };
 
-IPX_HD uint64_t make_key(const KeyLayout &kl, int32_t tid, int64_t i0, int64_t i1) {
-    return ((uint64_t)(uint32_t)tid << kl.tid_shift) | ((uint64_t)i0 << kl.start_shift) | (uint64_t)(i1 - i0);
+IPX_HD KeyLayout make_key_layout(int len_bits, uint64_t n_targets) {
+    KeyLayout kl;
+    kl.len_bits = len_bits;
+    kl.start_shift = len_bits;
+    kl.tid_shift = len_bits + 31;
+    kl.tid_bits = 63 - kl.tid_shift;
+    if (kl.tid_bits > 31) kl.tid_bits = 31;
+    if (kl.tid_bits < 0) kl.tid_bits = 0;
+    kl.tid_mask = kl.tid_bits ? ((1u << kl.tid_bits) - 1u) : 0u;
+    kl.wide = (n_targets > (uint64_t)kl.tid_mask + 1ull) ? 1 : 0;
+    return kl;
 }
-IPX_HD int32_t key_tid(const KeyLayout &kl, uint64_t k) { return (int32_t)(k >> kl.tid_shift); }
+
+IPX_HD uint64_t make_key(const KeyLayout &kl, int32_t tid, int64_t i0, int64_t i1) {
+    return ((uint64_t)((uint32_t)tid & kl.tid_mask) << kl.tid_shift) | ((uint64_t)i0 << kl.start_shift) | (uint64_t)(i1 - i0);
+}
 IPX_HD uint32_t key_start(const KeyLayout &kl, uint64_t k) { return (uint32_t)((k >> kl.start_shift) & 0x7FFFFFFFu); }
 IPX_HD uint32_t key_len(const KeyLayout &kl, uint64_t k) { return (uint32_t)(k & ((1ull << kl.len_bits) - 1ull)); }
 
@@ -106,113 +126,144 @@ IPX_HD uint64_t mix64(uint64_t x) {
     x ^= x >> 32;
     return x;
 }
+/* hash of a junction's identity; the target index enters separately because the wide layout keeps only its low bits
+ * in the key */
+IPX_HD uint64_t junction_hash(uint64_t key, int32_t tid) { return mix64(key ^ ((uint64_t)(uint32_t)tid * 0x9E3779B97F4A7C15ull)); }
 
 /* device-side view of the tables, passed to kernels by value */
 struct Tables {
-    unsigned long long *keys; /* [cap] */
-    JStat *stat;              /* [cap] */
-    uint32_t *slot_list;      /* [cap] slots in use, in insertion order: clear and finalize walk this, never the table */
-    uint32_t *slot_id;        /* [cap] position of a slot in slot_list (valid for slots in use) */
-    unsigned long long *olog; /* [olog_cap] slot << 32 | read offset << 16 | count, or OLOG_INVALID */
-    uint64_t olog_cap;
-    uint32_t *dense;          /* [cap][DENSE_W] read counts for offsets < DENSE_W, or NULL when disabled */
+    unsigned long long *keys; /* [cap] key64 or EMPTY64 */
+    uint32_t *jid;            /* [cap] junction id of the slot's key (JID_UNSET while its inserter publishes it) */
     uint64_t cap_mask;
+    /* junction rows, [max_j] each, in order of first insertion */
+    unsigned long long *jkey;
+    int32_t *jtid;
+    uint32_t *jslot;          /* hash slot of the junction's key (for clear) */
+    JStat *stat;
+    uint32_t *dense;          /* [max_j][DENSE_W] read counts for offsets < DENSE_W, or NULL when disabled */
+    uint32_t *olog_cnt;       /* entries of the read-offset log that name the junction */
+    uint64_t max_j;
+    unsigned long long *olog; /* [olog_cap] junction id << 32 | read offset << 16 | count */
+    uint64_t olog_cap;
     /* counters / flags, one cache line each to avoid false sharing */
-    unsigned long long *n_keys;    /* distinct keys inserted = entries of slot_list */
-    unsigned long long *n_olog;    /* entries of olog handed out (whole blocks; unused ones hold OLOG_INVALID) */
+    unsigned long long *n_keys;    /* junction ids handed out (may run past max_j when the rows are full) */
+    unsigned long long *n_olog;    /* log entries reserved (may run past olog_cap when the log is full) */
     unsigned long long *n_events;  /* events that passed junction_qc */
     unsigned long long *n_live;    /* CIGAR words of live records */
     unsigned long long *err_sv;    /* min over failing records of (record seq << 28 | code); EMPTY64 = none */
-    uint32_t *overflow;            /* set when a probe sequence ran out of room */
+    unsigned long long *n_unfolded; /* events K2 left in the event buffer because a table was full (see k_fold) */
+    uint32_t *overflow;            /* bit set: 1 hash slots / junction rows full, 2 log full, 4 intron start beyond 2^31,
+                                      8 mailbox slot too small, 16 a peer never published its export */
     KeyLayout kl;
 };
+
+enum : uint32_t { OVF_TABLE = 1u, OVF_LOG = 2u, OVF_START = 4u, OVF_MAIL = 8u, OVF_PEER = 16u };
 
 #if defined(__CUDACC__)
 static const uint32_t MAX_PROBE = 1u << 16;
 
-/* find the slot of `key`, inserting it if absent; returns cap_mask + 1 on overflow */
-__device__ __forceinline__ uint64_t junction_find_or_insert(const Tables &t, uint64_t key) {
-    uint64_t h = mix64(key) & t.cap_mask;
+/* number of junction ids in use (the counter keeps counting when the rows are full) */
+__device__ __forceinline__ uint64_t junctions_in_use(const Tables &t) {
+    const unsigned long long n = *t.n_keys;
+    return n < t.max_j ? n : t.max_j;
+}
+__device__ __forceinline__ uint64_t log_entries_in_use(const Tables &t) {
+    const unsigned long long n = *t.n_olog;
+    return n < t.olog_cap ? n : t.olog_cap;
+}
+
+/* Find the junction id of (key, tid); INSERT: claim a slot and a junction row when absent.  Returns JID_NONE when the
+ * key is absent (lookup) or when no slot / row is left (insert: the overflow flag is raised, the caller keeps the event).
+ * The junction rows of ids never handed out hold the reset values (init / clear), so an inserter has nothing to
+ * initialise but the identity. */
+template <bool INSERT>
+__device__ __forceinline__ uint32_t junction_probe(const Tables &t, unsigned long long key, int32_t tid) {
+    uint64_t h = junction_hash(key, tid) & t.cap_mask;
     for (uint32_t probe = 0; probe < MAX_PROBE; ++probe) {
         unsigned long long k = *((volatile unsigned long long *)&t.keys[h]);
-        if (k == key) return h;
         if (k == EMPTY64) {
-            unsigned long long old = atomicCAS(&t.keys[h], EMPTY64, (unsigned long long)key);
-            if (old == EMPTY64) {
-                /* every slot is claimed at most once between clears, so the list cannot overflow */
-                const unsigned long long id = atomicAdd(t.n_keys, 1ull);
-                t.slot_list[id] = (uint32_t)h;
-                t.slot_id[h] = (uint32_t)id;
-                return h;
+            if (!INSERT) return JID_NONE;
+            k = atomicCAS(&t.keys[h], EMPTY64, key);
+            if (k == EMPTY64) {
+                const unsigned long long j = atomicAdd(t.n_keys, 1ull);
+                if (j >= t.max_j) {
+                    /* no row left: the slot stays claimed (it is re-used by the rehash that follows the growth) */
+                    *((volatile uint32_t *)&t.jid[h]) = JID_FULL;
+                    atomicOr(t.overflow, OVF_TABLE);
+                    return JID_NONE;
+                }
+                t.jkey[j] = key;
+                t.jtid[j] = tid;
+                t.jslot[j] = (uint32_t)h;
+                __threadfence(); /* the identity is visible before the id is */
+                *((volatile uint32_t *)&t.jid[h]) = (uint32_t)j;
+                return (uint32_t)j;
             }
-            if (old == key) return h;
+        }
+        if (k == key) {
+            uint32_t j;
+            do {
+                j = *((volatile uint32_t *)&t.jid[h]);
+            } while (j == JID_UNSET);
+            if (j == JID_FULL) {
+                if (INSERT && !t.kl.wide) return JID_NONE; /* the same key met the full table before (flag already raised) */
+            } else if (!t.kl.wide || *((volatile int32_t *)&t.jtid[j]) == tid) {
+                return j;
+            }
         }
         h = (h + 1) & t.cap_mask;
     }
-    atomicExch(t.overflow, 1u);
-    return t.cap_mask + 1;
+    if (INSERT) atomicOr(t.overflow, OVF_TABLE);
+    return JID_NONE;
 }
 
-/* lookup only; returns cap_mask + 1 when absent */
-__device__ __forceinline__ uint64_t junction_find(const Tables &t, uint64_t key) {
-    uint64_t h = mix64(key) & t.cap_mask;
-    for (uint32_t probe = 0; probe < MAX_PROBE; ++probe) {
-        unsigned long long k = *((volatile unsigned long long *)&t.keys[h]);
-        if (k == key) return h;
-        if (k == EMPTY64) break;
-        h = (h + 1) & t.cap_mask;
-    }
-    return t.cap_mask + 1;
-}
-
-/* Per-warp writer of the offset log.  base/left are warp-uniform; every lane of the (converged) warp calls
- * olog_append together.  A block of OLOG_BLOCK entries is reserved with one atomic and filled chunk by chunk; what is
- * left of a block when the next one is needed, or when the kernel ends (olog_finish), is marked invalid. */
-struct OlogWriter {
-    unsigned long long base;
-    uint32_t left;
+/* Per-warp writer of the read-offset log: entries are staged in shared memory (LOG_STAGE of them) and written out
+ * with one reservation on the log's counter per stage, coalesced.  Every lane of the (converged) warp calls
+ * log_append / log_flush together; `fill` is warp-uniform. */
+struct LogStage {
+    unsigned long long *buf; /* this warp's LOG_STAGE entries of shared memory */
+    uint32_t fill;
 };
 
-__device__ __forceinline__ void olog_append(const Tables &t, OlogWriter &w, bool want, unsigned long long entry) {
+__device__ __forceinline__ unsigned long long olog_entry(uint32_t jid, uint32_t offset16, uint32_t n) {
+    return ((unsigned long long)jid << 32) | ((unsigned long long)(offset16 & 0xFFFFu) << 16) | (n & 0xFFFFu);
+}
+
+__device__ __forceinline__ void log_flush(const Tables &t, LogStage &s) {
+    if (s.fill == 0u) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    __syncwarp();
+    unsigned long long base = 0ull;
+    if (lane == 0u) base = atomicAdd(t.n_olog, (unsigned long long)s.fill);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (base + s.fill > t.olog_cap) {
+        if (lane == 0u) atomicOr(t.overflow, OVF_LOG); /* the host sizes the log before every batch: not expected */
+    } else {
+        for (uint32_t i = lane; i < s.fill; i += 32u) {
+            const unsigned long long e = s.buf[i];
+            t.olog[base + i] = e;
+            atomicAdd(&t.olog_cnt[(uint32_t)(e >> 32)], 1u);
+        }
+    }
+    __syncwarp();
+    s.fill = 0u;
+}
+
+__device__ __forceinline__ void log_append(const Tables &t, LogStage &s, bool want, unsigned long long entry) {
     const unsigned mask = __ballot_sync(0xFFFFFFFFu, want);
     if (mask == 0u) return;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t m = (uint32_t)__popc(mask);
-    if (m > w.left) {
-        if (lane < w.left) t.olog[w.base + lane] = OLOG_INVALID;
-        unsigned long long nb = 0ull;
-        if (lane == 0u) nb = atomicAdd(t.n_olog, (unsigned long long)OLOG_BLOCK);
-        nb = __shfl_sync(0xFFFFFFFFu, nb, 0);
-        w.base = nb;
-        w.left = OLOG_BLOCK;
-        if (nb + OLOG_BLOCK > t.olog_cap) {
-            atomicExch(t.overflow, 2u); /* the run is lost: ipx_flush reports it */
-            w.left = 0u;
-            return;
-        }
-    }
-    if (want) t.olog[w.base + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = entry;
-    w.base += m;
-    w.left -= m;
+    if (s.fill + m > LOG_STAGE) log_flush(t, s);
+    if (want) s.buf[s.fill + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = entry;
+    s.fill += m;
 }
 
-__device__ __forceinline__ void olog_finish(const Tables &t, const OlogWriter &w) {
-    const uint32_t lane = threadIdx.x & 31u;
-    if (lane < w.left) t.olog[w.base + lane] = OLOG_INVALID;
-}
-
-__device__ __forceinline__ unsigned long long olog_entry(uint64_t slot, uint32_t offset16, uint32_t n) {
-    return ((unsigned long long)slot << 32) | ((unsigned long long)(offset16 & 0xFFFFu) << 16) | (n & 0xFFFFu);
-}
-
-/* fold one counted read into a junction's statistics */
-__device__ __forceinline__ void stat_accumulate(JStat *s, uint32_t cat, uint32_t a0, uint32_t a1) {
-    atomicAdd(&s->cnt[cat], 1ull);
-    /* min/max only ever tighten, so a stale read can only cause a redundant atomic, never a missed one */
+/* min/max only ever tighten, so a stale read can only cause a redundant atomic, never a missed one */
+__device__ __forceinline__ void stat_anchor(JStat *s, uint32_t a0, uint32_t a1) {
     if (a0 < *((volatile uint32_t *)&s->a0)) atomicMin(&s->a0, a0);
     if (a1 > *((volatile uint32_t *)&s->a1)) atomicMax(&s->a1, a1);
 }
-
 __device__ __forceinline__ void stat_first(JStat *s, int cls, uint64_t sv) {
     if (sv < *((volatile unsigned long long *)&s->first[cls])) atomicMin(&s->first[cls], (unsigned long long)sv);
 }

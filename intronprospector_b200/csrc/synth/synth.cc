@@ -508,6 +508,169 @@ extern "C" int ipx_synth_write_bam(const ipx_synth_data *d, const char *path, ui
     return fclose(fp) == 0 ? 0 : -1;
 }
 
+/* ---- the same records as an aligner writes them: BGZF-compressed BAM with read names, bases, qualities, mate fields and
+ * a STAR-style tag set (NH HI AS nM, XS:A on spliced reads, jM / jI arrays) -- what the command-line tools read ---- */
+static std::string bam_header_bytes(const ipx_synth_data *d) {
+    std::string hdr_text = "@HD\tVN:1.6\tSO:coordinate\n";
+    for (size_t i = 0; i < d->contig_names.size(); i++)
+        hdr_text += "@SQ\tSN:" + d->contig_names[i] + "\tLN:" + std::to_string(d->contig_len[i]) + "\n";
+    hdr_text += "@PG\tID:synth\tPN:ipx_synth\tVN:1\tCL:seeded generator (SURVEY.md 8d)\n";
+    std::string b;
+    b.append("BAM\1", 4);
+    int32_t l_text = (int32_t)hdr_text.size();
+    b.append((const char *)&l_text, 4);
+    b += hdr_text;
+    int32_t n_ref = (int32_t)d->contig_names.size();
+    b.append((const char *)&n_ref, 4);
+    for (int32_t i = 0; i < n_ref; i++) {
+        int32_t l_name = (int32_t)d->contig_names[i].size() + 1;
+        b.append((const char *)&l_name, 4);
+        b.append(d->contig_names[i].c_str(), l_name);
+        int32_t l_ref = (int32_t)d->contig_len[i];
+        b.append((const char *)&l_ref, 4);
+    }
+    return b;
+}
+
+static void append_full_record(const ipx_synth_data *d, uint64_t r, std::string &b) {
+    const Out &o = d->out;
+    const uint32_t c0 = d->cigar_off[r], nc = d->cigar_off[r + 1] - c0;
+    int64_t rlen = 0, qlen = 0;
+    bool spliced = false;
+    for (uint32_t k = 0; k < nc; k++) {
+        const uint32_t op = o.cigar[c0 + k] & 15, len = o.cigar[c0 + k] >> 4;
+        if (op == M || op == D || op == N || op == EQ || op == X) rlen += len;
+        if (op == M || op == I || op == S || op == EQ || op == X) qlen += len;
+        spliced |= op == N;
+    }
+    if (rlen == 0) rlen = 1;
+    if (qlen > 400) qlen = 400; /* long reads: keep the file a sensible size; nothing on the path reads SEQ */
+    Rng rng(0xA11CEull ^ (r * 0x9E3779B97F4A7C15ull));
+    char qname[40];
+    const int lq = snprintf(qname, sizeof(qname), "SYN%llu.%llu", (unsigned long long)(d->spec.seed % 100000), (unsigned long long)(r >> 1)) + 1;
+    uint8_t aux[96];
+    int la = 0;
+    auto tag_C = [&](char a, char bch, uint8_t v) { aux[la++] = a; aux[la++] = bch; aux[la++] = 'C'; aux[la++] = v; };
+    if (o.nh[r]) tag_C('N', 'H', (o.nh[r] == 1) ? 1 : 3);
+    tag_C('H', 'I', 1);
+    aux[la++] = 'A'; aux[la++] = 'S'; aux[la++] = 'S';
+    const uint16_t as = (uint16_t)(2 * qlen - 2 - rng.below(6));
+    memcpy(aux + la, &as, 2); la += 2;
+    tag_C('n', 'M', (uint8_t)rng.below(3));
+    if (o.xs[r]) { aux[la++] = 'X'; aux[la++] = 'S'; aux[la++] = 'A'; aux[la++] = o.xs[r]; }
+    /* jM:B:c / jI:B:i as STAR writes them with --outSAMattributes All */
+    aux[la++] = 'j'; aux[la++] = 'M'; aux[la++] = 'B'; aux[la++] = 'c';
+    int32_t one = 1;
+    memcpy(aux + la, &one, 4); la += 4;
+    aux[la++] = spliced ? 1 : (uint8_t)-1;
+    aux[la++] = 'j'; aux[la++] = 'I'; aux[la++] = 'B'; aux[la++] = 'i';
+    int32_t two = spliced ? 2 : 1;
+    memcpy(aux + la, &two, 4); la += 4;
+    int32_t ji0 = spliced ? o.pos[r] + 50 : -1, ji1 = o.pos[r] + 150;
+    memcpy(aux + la, &ji0, 4); la += 4;
+    if (spliced) { memcpy(aux + la, &ji1, 4); la += 4; }
+    int32_t x[8];
+    x[0] = o.tid[r];
+    x[1] = o.pos[r];
+    x[2] = (int32_t)(((uint32_t)reg2bin(o.pos[r], o.pos[r] + rlen) << 16) | (255u << 8) | (uint32_t)lq);
+    x[3] = (int32_t)(((uint32_t)o.flag[r] << 16) | nc);
+    x[4] = (int32_t)qlen;
+    x[5] = (o.flag[r] & 1) ? o.tid[r] : -1;
+    x[6] = (o.flag[r] & 1) ? o.pos[r] + (int32_t)rng.below(300) - 150 : -1;
+    if (x[6] < -1) x[6] = 0;
+    x[7] = (o.flag[r] & 1) ? (int32_t)rng.below(500) - 250 : 0;
+    const size_t seq_bytes = (size_t)((qlen + 1) / 2);
+    int32_t block = 32 + lq + (int32_t)nc * 4 + (int32_t)seq_bytes + (int32_t)qlen + la;
+    b.append((const char *)&block, 4);
+    b.append((const char *)x, 32);
+    b.append(qname, lq);
+    b.append((const char *)&o.cigar[c0], (size_t)nc * 4);
+    const size_t at = b.size();
+    b.resize(at + seq_bytes + (size_t)qlen);
+    uint8_t *sq = (uint8_t *)&b[at];
+    static const uint8_t nib[4] = {1, 2, 4, 8};
+    for (size_t k = 0; k < seq_bytes; k += 8) {
+        uint64_t v = rng.next();
+        for (size_t q = k; q < k + 8 && q < seq_bytes; q++, v >>= 4) sq[q] = (uint8_t)((nib[v & 3] << 4) | nib[(v >> 2) & 3]);
+    }
+    uint8_t *ql = sq + seq_bytes;
+    for (int64_t k = 0; k < qlen; k += 8) {
+        uint64_t v = rng.next();
+        for (int64_t q = k; q < k + 8 && q < qlen; q++, v >>= 8) ql[q] = (uint8_t)(((v & 0xFF) < 200) ? 37 : (2 + (v & 0x1F)));
+    }
+    b.append((const char *)aux, la);
+}
+
+#include <zlib.h>
+/* `in` as BGZF blocks appended to `out` */
+static bool bgzf_compress(const std::string &in, std::string &out, int level) {
+    const size_t BLOCK = 0xff00;
+    std::vector<uint8_t> tmp(0x10000 + 1024);
+    for (size_t at = 0; at < in.size() || (at == 0 && in.empty());) {
+        const size_t n = std::min(BLOCK, in.size() - at);
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+        zs.next_in = (Bytef *)(in.data() + at);
+        zs.avail_in = (uInt)n;
+        zs.next_out = tmp.data();
+        zs.avail_out = (uInt)tmp.size();
+        if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { deflateEnd(&zs); return false; }
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        const uint8_t head[12] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0};
+        out.append((const char *)head, 12);
+        const uint8_t sub[4] = {'B', 'C', 2, 0};
+        out.append((const char *)sub, 4);
+        const uint16_t bsize = (uint16_t)(clen + 25);
+        out.append((const char *)&bsize, 2);
+        out.append((const char *)tmp.data(), clen);
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)(in.data() + at), (uInt)n);
+        const uint32_t isize = (uint32_t)n;
+        out.append((const char *)&crc, 4);
+        out.append((const char *)&isize, 4);
+        at += n;
+        if (n == 0) break;
+    }
+    return true;
+}
+
+extern "C" int ipx_synth_write_bam_full(const ipx_synth_data *d, const char *path, uint64_t begin, uint64_t end, int threads, int level) {
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return -1;
+    if (end > d->out.tid.size()) end = d->out.tid.size();
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = 1;
+    if (threads > 64) threads = 64;
+    bool ok = true;
+    {
+        std::string z;
+        ok = bgzf_compress(bam_header_bytes(d), z, level) && fwrite(z.data(), 1, z.size(), fp) == z.size();
+    }
+    const uint64_t SLICE = 1u << 16; /* records a thread turns into BGZF blocks at a time */
+    for (uint64_t r0 = begin; r0 < end && ok; r0 += SLICE * (uint64_t)threads) {
+        std::vector<std::string> zs((size_t)threads);
+        std::vector<char> good((size_t)threads, 1);
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++) {
+            pool.emplace_back([&, t]() {
+                const uint64_t lo = r0 + SLICE * (uint64_t)t, hi = std::min(end, lo + SLICE);
+                if (lo >= hi) return;
+                std::string raw;
+                raw.reserve((size_t)(hi - lo) * 400);
+                for (uint64_t r = lo; r < hi; r++) append_full_record(d, r, raw);
+                good[(size_t)t] = bgzf_compress(raw, zs[(size_t)t], level) ? 1 : 0;
+            });
+        }
+        for (auto &th : pool) th.join();
+        for (int t = 0; t < threads && ok; t++)
+            ok = good[(size_t)t] && (zs[(size_t)t].empty() || fwrite(zs[(size_t)t].data(), 1, zs[(size_t)t].size(), fp) == zs[(size_t)t].size());
+    }
+    static const uint8_t eof_block[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (ok) ok = fwrite(eof_block, 1, 28, fp) == 28;
+    return (fclose(fp) == 0 && ok) ? 0 : -1;
+}
+
 /* deterministic background base for (contig, pos) */
 static inline char bg_base(uint64_t seed, int contig, int64_t p) {
     uint64_t z = seed ^ ((uint64_t)contig << 48) ^ (uint64_t)p;

@@ -38,6 +38,9 @@ const char *ipx_synth_contig_name(const ipx_synth_data *d, int32_t i);
 uint64_t ipx_synth_contig_len(const ipx_synth_data *d, int32_t i);
 /* write records [begin, end) as a BAM stream: raw != 0 -> uncompressed, no BGZF framing (hts_compat reads it) */
 int ipx_synth_write_bam(const ipx_synth_data *d, const char *path, uint64_t begin, uint64_t end, int raw);
+/* the same records as an aligner writes them (read names, bases, qualities, mate fields, STAR-style tags incl. B arrays),
+ * BGZF-compressed at `level` by `threads` threads (0 = all): the input of the command-line tools */
+int ipx_synth_write_bam_full(const ipx_synth_data *d, const char *path, uint64_t begin, uint64_t end, int threads, int level);
 /* synthetic genome consistent with the gene model (planted splice motifs); writes FASTA + .fai */
 int ipx_synth_write_genome(const ipx_synth_data *d, const char *fasta_path);
 

@@ -3,9 +3,10 @@
 The record stream is cut into contiguous, ordered shards (global stream indexes preserved through ipx_batch.seq_base).
 Every rank extracts and reduces its shard locally; partial junction rows and read-offset rows are then exchanged by
 key range and folded by the owning rank.  Two transports:
-  mailboxes   (GPUs of one node) the exporting kernels store every row straight into its owner's memory over
-              NVLink (ipx_mailbox_*, ipx_partial_export_mail); the only collective is a one-element all-reduce that
-              orders "all exports done" before "imports start".  No send buffers, no size exchange, no host round trip.
+  mailboxes   (GPUs of one node) the exporting kernels store the rows of junctions another rank owns straight into
+              that rank's memory over NVLink (ipx_mailbox_*, ipx_partial_export_mail) -- a rank's own share never
+              moves -- and publish an epoch into the slot headers; the importing side waits for the epochs on the
+              device.  No send buffers, no size exchange, no collective, no host round trip.
   all-to-all  packed rows through torch.distributed (NCCL, or gloo on CPU tensors in the tests); used when no
               mailboxes are connected.  With the canon filter the ranks first agree
 on each junction's creating event (an all-gather of J-sized threshold rows) and count their kept events against it.
@@ -31,6 +32,47 @@ def key_splitters(names, n_parts):
         k = min(n - 1, (n * p) // n_parts) if n else 0
         split_tid.append(order[k] if n else 0)
     return split_tid, [0] * (n_parts - 1)
+
+
+def balanced_splitters(names, samples, n_parts):
+    """Splitters that give every part about the same number of junctions: `samples` = (target index, intron start)
+    arrays of junction keys (every rank's ipx_sample_keys, concatenated).  Keys are ordered by chromosome NAME, start."""
+    tid = np.concatenate([np.asarray(t, dtype=np.int64) for t, _ in samples]) if samples else np.zeros(0, np.int64)
+    i0 = np.concatenate([np.asarray(s, dtype=np.int64) for _, s in samples]) if samples else np.zeros(0, np.int64)
+    if tid.size < n_parts:
+        return key_splitters(names, n_parts)
+    order = sorted(range(len(names)), key=lambda i: names[i].encode())
+    rank = np.zeros(len(names), np.int64)
+    rank[order] = np.arange(len(names))
+    key = (rank[tid] << 32) | i0
+    key.sort()
+    split_tid, split_start = [], []
+    for p in range(1, n_parts):
+        k = int(key[(key.size * p) // n_parts])
+        split_tid.append(order[k >> 32])
+        split_start.append(k & 0xFFFFFFFF)
+    return split_tid, split_start
+
+
+def balanced_splitters_dist(eng, names, device, group=None, max_keys=1 << 14):
+    """Every rank samples its junction keys, the samples are all-gathered, every rank derives the same splitters."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    tid, i0 = eng.sample_keys(stride=1, max_keys=1 << 22)
+    if tid.size > max_keys:
+        step = (tid.size + max_keys - 1) // max_keys
+        tid, i0 = tid[::step], i0[::step]
+    mine = torch.full((2, max_keys), -1, dtype=torch.int64, device=device)
+    mine[0, :tid.size] = torch.from_numpy(tid.astype(np.int64)).to(device)
+    mine[1, :i0.size] = torch.from_numpy(i0.astype(np.int64)).to(device)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    samples = []
+    for g in gathered:
+        a = g.cpu().numpy()
+        keep = a[0] >= 0
+        samples.append((a[0][keep], a[1][keep]))
+    return balanced_splitters(names, samples, world)
 
 
 def _engine_stream(eng, device):
@@ -116,7 +158,6 @@ def connect_mailboxes_dist(eng, device, junction_rows_per_source, hist_rows_per_
     handles = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
     dist.all_gather(handles, mine, group=group)
     eng.mailbox_connect_ipc([bytes(h.cpu().numpy().tobytes()) for h in handles])
-    eng._mail_token = torch.zeros(1, dtype=torch.int32, device=device)
     dist.barrier(group=group)
 
 
@@ -130,34 +171,50 @@ def connect_mailboxes_local(engines, junction_rows_per_source, hist_rows_per_sou
         e.mailbox_connect_ptrs(ptrs)
 
 
-def exchange_mail_dist(eng, names, device, group=None):
-    """One key-range exchange through the mailboxes: export into the owners' memory, a one-element all-reduce as the
-    barrier between everybody's export and anybody's import, import.  Everything is enqueued; nothing waits on the host."""
+def exchange_mail_dist(eng, names, device, group=None, splitters=None):
+    """One key-range exchange through the mailboxes: export what other ranks own into their memory, then fold what
+    arrived here -- the importing kernels wait on the device for every source's epoch.  Everything is enqueued on the
+    engine's stream; there is no collective and nothing waits on the host."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    split_tid, split_start = key_splitters(names, world)
+    split_tid, split_start = splitters if splitters is not None else key_splitters(names, world)
     eng.partial_export_mail(split_tid, split_start)
-    _torch_after_engine(eng, device)
-    dist.all_reduce(eng._mail_token, group=group)
-    _engine_after_torch(eng, device)
     eng.partial_import_mail()
 
 
-def exchange_mail_local(engines, names, device):
-    split_tid, split_start = key_splitters(names, len(engines))
-    for e in engines:
-        e.partial_export_mail(split_tid, split_start)
-    torch.cuda.synchronize(device)  # stands in for the barrier: the handles have separate streams
-    for e in engines:
-        e.partial_import_mail()
+def settle_exchange_dist(eng, names, device, group=None, splitters=None):
+    """Before ipx_flush: did any rank fold events after its export (its junction table had been full and was grown)?
+    Then everybody repeats the exchange -- only what is still held for other ranks moves."""
+    import torch.distributed as dist
+    for _ in range(8):
+        flag = torch.tensor([1 if eng.exchange_settle() else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()) == 0:
+            return
+        exchange_mail_dist(eng, names, device, group, splitters)
+    raise RuntimeError("the exchange did not settle")
 
 
-def exchange_dist(eng, names, device, group=None):
+def exchange_mail_local(engines, names, device, splitters=None):
+    split_tid, split_start = splitters if splitters is not None else key_splitters(names, len(engines))
+    for _ in range(8):
+        for e in engines:
+            e.partial_export_mail(split_tid, split_start)
+        # the handles have separate streams and the importers wait on the device for every exporter's epoch: all the
+        # exports must be enqueued before the first import, or an importer could wait for a kernel queued behind it
+        for e in engines:
+            e.partial_import_mail()
+        if not any([e.exchange_settle() for e in engines]):
+            return
+    raise RuntimeError("the exchange did not settle")
+
+
+def exchange_dist(eng, names, device, group=None, splitters=None):
     """One key-range exchange over torch.distributed; returns the bytes this rank sent + received (None through
     mailboxes, where nobody counts them on the host)."""
     import torch.distributed as dist
     if getattr(eng, "mailbox_connected", False):
-        return exchange_mail_dist(eng, names, device, group)
+        return exchange_mail_dist(eng, names, device, group, splitters)
     world = dist.get_world_size(group)
     (send_j, cj), (send_h, ch) = export_partials(eng, names, world, device)
     rj, rh = exchange_counts([cj, ch], device, group)

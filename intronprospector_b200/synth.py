@@ -45,6 +45,7 @@ def lib():
         L.ipx_synth_contig_len.argtypes = [C.c_void_p, C.c_int32]
         L.ipx_synth_contig_len.restype = C.c_uint64
         L.ipx_synth_write_bam.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_int]
+        L.ipx_synth_write_bam_full.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
         L.ipx_synth_write_genome.argtypes = [C.c_void_p, C.c_char_p]
         _lib = L
     return _lib
@@ -82,6 +83,12 @@ class Synth:
 
     def write_raw_bam(self, path, begin=0, end=None):
         rc = lib().ipx_synth_write_bam(self.p, path.encode(), begin, self.n if end is None else end, 1)
+        if rc != 0:
+            raise RuntimeError("writing %s failed" % path)
+
+    def write_full_bam(self, path, begin=0, end=None, threads=0, level=1):
+        """The records as an aligner writes them (names, bases, qualities, a STAR-style tag set), BGZF-compressed."""
+        rc = lib().ipx_synth_write_bam_full(self.p, path.encode(), begin, self.n if end is None else end, threads, level)
         if rc != 0:
             raise RuntimeError("writing %s failed" % path)
 

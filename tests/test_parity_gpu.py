@@ -49,12 +49,56 @@ def test_small_tables_force_collisions(built):
     assert selftest.compare_tables(got, want) == []
 
 
-def test_table_overflow_is_reported(built):
+@pytest.mark.parametrize("n_batches", [1, 5])
+def test_tables_grow_from_tiny_capacities(built, n_batches):
+    """1024 hash slots / 512 junction rows / a 1024-entry offset log against thousands of junctions: the fold leaves the
+    events it has no room for in the event buffer, the host grows the tables (rows doubled, slots rehashed, log sized
+    ahead of each batch) and repeats the fold until nothing is left -- same table as the oracle's."""
     syn = Synth(200_000, kind=SHORT_UNSTRANDED, genome_len=100_000_000, n_genes=500)
-    gpu = _native.Engine(device=0, table_capacity=1024, hist_capacity=1024)
-    with pytest.raises(_native.IpxError):
-        selftest.run_engine(gpu, syn.names, syn.columns())
-    gpu.close()
+    got, want = both(syn.names, syn.columns(), n_batches=n_batches, table_capacity=1024, hist_capacity=1024)
+    assert want.n > 1500
+    assert selftest.compare_tables(got, want) == []
+
+
+def test_tables_grow_with_the_canon_filter_and_long_reads(built, tmp_path):
+    syn = Synth(300_000, kind=SHORT_STRANDED, genome_len=100_000_000, n_genes=1000, n_contigs=5)
+    genome = genome_of(syn, tmp_path)
+    got, want = both(syn.names, syn.columns(), n_batches=3, genome=genome, strandness=_native.STRAND_RF,
+                     junction_filter=_native.FILTER_CANON, table_capacity=1024, hist_capacity=1024)
+    assert want.n > 1000
+    assert selftest.compare_tables(got, want) == []
+    syn = Synth(20_000, kind=LONG, genome_len=300_000_000, n_genes=2000)
+    got, want = both(syn.names, syn.columns(), n_batches=2, max_anchor_indel_size=36, table_capacity=2048, hist_capacity=1024)
+    assert want.n > 1000
+    assert selftest.compare_tables(got, want) == []
+
+
+def test_more_targets_than_the_key_has_bits_for(built):
+    """20 000 contigs at the default --max-intron-length (13 bits of the key are left for the target index), and a few
+    hundred with -I 10000000 (8 bits): the tables compare the full target index kept with every junction."""
+    rng = np.random.default_rng(3)
+    def w(length, op):
+        return (length << 4) | "MIDNSHP=XB".index(op)
+    for n_targets, max_intron in ((20_000, 500_000), (600, 10_000_000)):
+        names = ["scaffold_%d" % i for i in range(n_targets)]
+        n = 60_000
+        tid = np.sort(rng.integers(0, n_targets, n)).astype(np.int32)
+        pos = rng.integers(0, 2000, n).astype(np.int32)
+        order = np.lexsort((pos, tid))
+        tid, pos = tid[order], pos[order]
+        # the same few introns on every target: identical (start, length) under different target indexes
+        starts = rng.integers(40, 60, n)
+        lens = rng.choice([100, 250, 400_000 if max_intron >= 400_000 else 900], n)
+        cigar = np.empty((n, 3), np.uint32)
+        cigar[:, 0] = (starts << 4) | 0
+        cigar[:, 1] = (lens << 4) | 3
+        cigar[:, 2] = (50 << 4) | 0
+        cols = {"tid": tid, "pos": pos, "flag": np.zeros(n, np.uint16), "nh_class": np.ones(n, np.uint8),
+                "xs": np.full(n, ord("+"), np.uint8), "cigar_off": (np.arange(n + 1) * 3).astype(np.uint32),
+                "cigar": cigar.reshape(-1)}
+        got, want = both(names, cols, n_batches=2, max_intron_length=max_intron)
+        assert want.n > 10_000
+        assert selftest.compare_tables(got, want) == []
 
 
 @pytest.mark.parametrize("flt", [_native.FILTER_CANON, _native.FILTER_ALL])
