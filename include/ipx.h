@@ -220,6 +220,14 @@ int ipx_push_batch_device(ipx_handle *h, const ipx_batch *batch);
 /* Same as ipx_push_batch from the compact host form. */
 int ipx_push_batch_compact(ipx_handle *h, const ipx_batch_compact *batch);
 
+/* The host -> device copies of ipx_push_batch / ipx_push_batch_compact are asynchronous when the batch lies in pinned
+ * memory (ipx_host_alloc): the call returns once they are enqueued and the buffers must stay untouched until they have
+ * run.  ipx_sync_uploads waits until at most `keep_in_flight` of the pushes made so far (0 ... 3) still have copies
+ * pending: a caller that packs into two buffers in turn calls it with 1 before it refills a buffer. */
+void *ipx_host_alloc(size_t bytes);
+void ipx_host_free(void *p);
+int ipx_sync_uploads(ipx_handle *h, uint32_t keep_in_flight);
+
 /* Finish aggregation on the device (key-order sort, sjN ranking, histogram ordering), asynchronously. */
 int ipx_finalize_device(ipx_handle *h);
 /* get_junctions() + clear() (junctions_extractor.hh:222-256): copy the finished table to the host,

@@ -32,6 +32,13 @@ const char *ipxio_target_name(const ipxio_reader *r, int32_t i);
 int64_t ipxio_read_batch(ipxio_reader *r, uint64_t max_records, uint64_t max_cigar, int32_t *tid, int32_t *pos,
                          uint16_t *flag, uint8_t *nh_class, uint8_t *xs, uint32_t *cigar_off, uint32_t *cigar,
                          uint64_t *n_cigar_out);
+/* The same columns for a whole BAM file through the multi-threaded BAM pipeline (host/bam_pipeline.h: what the
+ * command-line tool reads BAM files with; `threads` <= 0: one per core).  Returns the number of records, -1 on a damaged
+ * file, -2 when the buffers are too small.  Unlike ipxio_read_batch the NH / XS columns are only filled for reads with
+ * an N operation (the only reads the path looks at them for). */
+int64_t ipxio_pipeline_read(const char *path, int32_t threads, uint64_t max_records, uint64_t max_cigar, int32_t *tid, int32_t *pos,
+                            uint16_t *flag, uint8_t *nh_class, uint8_t *xs, uint32_t *cigar_off, uint32_t *cigar,
+                            uint64_t *n_cigar_out);
 
 /* Genome::Genome (genome.cc:44-50): needs "<fasta>.fai"; sequences are returned whole, newlines removed */
 int ipxio_genome_load(const char *fasta, ipxio_genome **out);

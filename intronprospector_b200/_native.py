@@ -152,13 +152,13 @@ ABI_SYMBOLS = [
     "ipx_get_timings", "ipx_reset_timings", "ipx_stream", "ipx_thresholds_rows", "ipx_thresholds_export",
     "ipx_thresholds_import", "ipx_count_deferred", "ipx_table_set_ijunc", "ipx_push_batch_compact",
     "ipx_mailbox_create", "ipx_mailbox_ipc_handle", "ipx_mailbox_ptr", "ipx_mailbox_connect", "ipx_partial_export_mail",
-    "ipx_partial_import_mail", "ipx_exchange_settle", "ipx_sample_keys",
+    "ipx_partial_import_mail", "ipx_exchange_settle", "ipx_sample_keys", "ipx_host_alloc", "ipx_host_free", "ipx_sync_uploads",
 ]
 IO_SYMBOLS = [
     "ipxio_last_error", "ipxio_open", "ipxio_close", "ipxio_n_targets", "ipxio_target_name", "ipxio_read_batch",
     "ipxio_genome_load", "ipxio_genome_free", "ipxio_genome_n_seqs", "ipxio_genome_names", "ipxio_genome_lengths",
     "ipxio_genome_seqs", "ipxio_faidx_build", "ipxio_calls_load", "ipxio_calls_free", "ipxio_calls_rows",
-    "ipxio_calls_n_chroms", "ipxio_calls_chroms",
+    "ipxio_calls_n_chroms", "ipxio_calls_chroms", "ipxio_pipeline_read",
 ]
 
 _lib = None
@@ -243,6 +243,8 @@ def load_io_library():
         io.ipxio_target_name.restype = C.c_char_p
         io.ipxio_read_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64] + [C.c_void_p] * 7 + [C.POINTER(C.c_uint64)]
         io.ipxio_read_batch.restype = C.c_int64
+        io.ipxio_pipeline_read.argtypes = [C.c_char_p, C.c_int32, C.c_uint64, C.c_uint64] + [C.c_void_p] * 7 + [C.POINTER(C.c_uint64)]
+        io.ipxio_pipeline_read.restype = C.c_int64
         io.ipxio_genome_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         io.ipxio_genome_free.argtypes = [C.c_void_p]
         io.ipxio_genome_free.restype = None
@@ -334,18 +336,38 @@ class Table:
         cols[name] = a
         return a
 
-    def text(self, fmt, min_confidence=0.0):
-        key = (fmt, float(min_confidence))
+    def text(self, fmt, min_confidence=0.0, begin=0, end=None):
+        """Formatted rows [begin, end) of the table (all of it by default), sorted as the reference sorts them."""
+        end = self.n if end is None else end
+        key = (fmt, float(min_confidence), begin, end)
         if key not in self._text:
             if self._tp is None:
                 raise IpxError("table already closed")
             txt = Text()
-            rc = self._lib.ipx_format(self._tp, self._cnames, fmt, key[1], 0, self.n, C.byref(txt))
+            rc = self._lib.ipx_format(self._tp, self._cnames, fmt, key[1], begin, end, C.byref(txt))
             if rc != IPX_OK:
                 raise IpxError("ipx_format failed: %d" % rc)
             self._text[key] = C.string_at(txt.data, txt.len) if txt.len else b""
             self._lib.ipx_text_free(C.byref(txt))
         return self._text[key]
+
+    def text_by_target(self, fmt, min_confidence=0.0):
+        """The text of a coordinate-sorted single-file run: the rows of each target in header order, each target's rows
+        sorted on their own (extract_junctions_by_target, intronProspector.cc:356-371)."""
+        if self.n == 0:
+            return b""
+        chrom = np.asarray(self.chrom)
+        cuts = np.flatnonzero(np.concatenate(([True], chrom[1:] != chrom[:-1], [True])))
+        ranges = sorted((int(chrom[b]), int(b), int(e)) for b, e in zip(cuts[:-1], cuts[1:]))
+        return b"".join(self.text(fmt, min_confidence, b, e) for _, b, e in ranges)
+
+    def tsv_header(self):
+        txt = Text()
+        if self._lib.ipx_format_tsv_header(C.byref(txt)) != IPX_OK:
+            raise IpxError("ipx_format_tsv_header failed")
+        out = C.string_at(txt.data, txt.len)
+        self._lib.ipx_text_free(C.byref(txt))
+        return out
 
     def set_ijunc(self, ijunc):
         """Renumber the junctions (multi-GPU: global ranks of creation_seq)."""

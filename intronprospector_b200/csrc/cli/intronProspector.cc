@@ -17,6 +17,7 @@
 #include "genome_loader.h"
 #include "htslib/sam.h"
 #include "ipx.h"
+#include "bam_pipeline.h"
 #include "record_source.h"
 #include "../ipx_walk.cuh" /* the automaton, host build: per-read annotations below */
 
@@ -358,20 +359,83 @@ class Annotator {
     }
 };
 
+/* One batch of packed records in pinned host memory (ipx_batch_compact: 10 bytes per record + 4 per CIGAR word).
+ * Two of them take turns: while the copy of one to the device is in flight, the other is being filled. */
+struct PinnedBatch {
+    size_t cap_rec = 0, cap_cig = 0, n = 0, n_cig = 0;
+    int32_t *pos = nullptr;
+    uint16_t *flag = nullptr, *n_ops = nullptr;
+    uint8_t *nh = nullptr, *xs = nullptr;
+    uint32_t *cigar = nullptr;
+    vector<int32_t> run_tid;
+    vector<uint64_t> run_start;
+    vector<uint32_t> ops32; /* the operation counts once more, 32 bits wide: only used when one exceeds 65535 */
+    bool compact_ok = true;
+    uint64_t seq_base = 0;
+    void allocate(size_t records, size_t cigar_words) {
+        cap_rec = records;
+        cap_cig = cigar_words;
+        pos = (int32_t *)ipx_host_alloc(records * 4);
+        flag = (uint16_t *)ipx_host_alloc(records * 2);
+        n_ops = (uint16_t *)ipx_host_alloc(records * 2);
+        nh = (uint8_t *)ipx_host_alloc(records);
+        xs = (uint8_t *)ipx_host_alloc(records);
+        cigar = (uint32_t *)ipx_host_alloc(cigar_words * 4);
+        if (!pos || !flag || !n_ops || !nh || !xs || !cigar) throw runtime_error("cannot allocate pinned host memory for the record batches");
+    }
+    void release() {
+        ipx_host_free(pos); ipx_host_free(flag); ipx_host_free(n_ops); ipx_host_free(nh); ipx_host_free(xs); ipx_host_free(cigar);
+        pos = nullptr;
+    }
+    void clear(uint64_t next_seq_base) {
+        n = n_cig = 0;
+        run_tid.clear(); run_start.clear(); ops32.clear();
+        compact_ok = true;
+        seq_base = next_seq_base;
+    }
+    bool room_for(size_t records, size_t cigar_words) const { return n + records <= cap_rec && n_cig + cigar_words <= cap_cig; }
+    void begin_run(int32_t tid) {
+        if (run_tid.empty() || run_tid.back() != tid) {
+            run_tid.push_back(tid);
+            run_start.push_back((uint64_t)n);
+        }
+    }
+    void add_fields(int32_t tid, int32_t p, uint16_t fl, uint8_t nh_class, uint8_t x, const uint32_t *cig, uint32_t n_cigar) {
+        begin_run(tid);
+        pos[n] = p; flag[n] = fl; nh[n] = nh_class; xs[n] = x;
+        n_ops[n] = (uint16_t)n_cigar;
+        ops32.push_back(n_cigar);
+        if (n_cigar > 0xFFFFu) compact_ok = false;
+        memcpy(cigar + n_cig, cig, 4 * (size_t)n_cigar);
+        n_cig += n_cigar;
+        n++;
+    }
+};
+
 class Driver {
     const Options &opts_;
     ipx_handle *h_ = nullptr;
     vector<string> targets_;            /* targets_, appended per file (save_targets, junctions_extractor.cc:564-568) */
     vector<int32_t> canon_tid_;         /* first index carrying the same name: the reference keys junctions by name */
     map<string, int32_t> name_first_;
-    ipx::ColumnarBatch batch_;
+    PinnedBatch batches_[2];
+    int cur_ = 0;
     uint64_t next_seq_ = 0;
     uint64_t last_seq_ = 0; /* stream index and engine target of the record process() saw last */
     int32_t last_tid_ = -1;
     /* stream segments (first record index, target) of processed records, for attributing deferred errors */
     vector<pair<uint64_t, int32_t>> segments_;
     static const size_t BATCH_RECORDS = 1u << 22;
-    static const size_t BATCH_CIGAR = 1u << 26;
+    static const size_t BATCH_CIGAR = 1u << 24;
+
+    PinnedBatch &batch() { return batches_[cur_]; }
+    int32_t map_tid(int32_t tid) const { return (tid >= 0 && (size_t)tid < canon_tid_.size()) ? canon_tid_[tid] : tid; }
+    void note(int32_t tid, uint64_t n_records) {
+        if (segments_.empty() || segments_.back().second != tid) segments_.emplace_back(next_seq_, tid);
+        last_seq_ = next_seq_ + n_records - 1;
+        last_tid_ = tid;
+        next_seq_ += n_records;
+    }
 
     public:
     explicit Driver(const Options &o) : opts_(o) {
@@ -389,9 +453,15 @@ class Driver {
         if (const char *d = getenv("IPX_DEVICE")) p.device = atoi(d);
         int rc = ipx_create(&p, &h_);
         if (rc != IPX_OK) throw runtime_error("no usable CUDA device: junction extraction needs an NVIDIA B200 (sm_100a) GPU");
-        batch_.clear(0);
+        for (auto &b : batches_) {
+            b.allocate(BATCH_RECORDS, BATCH_CIGAR);
+            b.clear(0);
+        }
     }
-    ~Driver() { ipx_destroy(h_); }
+    ~Driver() {
+        ipx_destroy(h_);
+        for (auto &b : batches_) b.release();
+    }
 
     void set_genome(const ipx::LoadedGenome &g) {
         check_ipx(h_, ipx_set_genome(h_, (int32_t)g.names.size(), g.name_ptrs.data(), g.lengths.data(), g.seq_ptrs.data()));
@@ -423,37 +493,117 @@ class Driver {
 
     /* process_alignment (junctions_extractor.cc:533-549): hand the record to the engine */
     void process(const bam1_t *b) {
-        int32_t tid = b->core.tid;
-        if (tid >= 0 && (size_t)tid < canon_tid_.size()) tid = canon_tid_[tid];
-        if (segments_.empty() || segments_.back().second != tid) segments_.emplace_back(next_seq_, tid);
-        batch_.add(b, tid);
-        last_seq_ = next_seq_;
-        last_tid_ = tid;
-        next_seq_++;
-        if (batch_.size() >= BATCH_RECORDS || batch_.cigar.size() >= BATCH_CIGAR) push();
+        const int32_t tid = map_tid(b->core.tid);
+        if (!batch().room_for(1, b->core.n_cigar)) push(b->core.n_cigar);
+        uint8_t nh, x;
+        ipx::scan_tags(b, &nh, &x);
+        batch().add_fields(tid, (int32_t)b->core.pos, b->core.flag, nh, x, bam_get_cigar(b), b->core.n_cigar);
+        note(tid, 1);
     }
     /* the same for a BAM record in the reader's buffer (Input::peek_raw) */
     void process_raw(const uint8_t *rec, uint32_t len) {
-        int32_t tid;
+        int32_t tid, p, l_seq;
+        uint16_t n_cigar, fl;
         memcpy(&tid, rec, 4);
-        if (tid >= 0 && (size_t)tid < canon_tid_.size()) tid = canon_tid_[tid];
-        if (segments_.empty() || segments_.back().second != tid) segments_.emplace_back(next_seq_, tid);
-        batch_.add_raw(rec, len, tid);
-        last_seq_ = next_seq_;
-        last_tid_ = tid;
-        next_seq_++;
-        if (batch_.size() >= BATCH_RECORDS || batch_.cigar.size() >= BATCH_CIGAR) push();
-    }
-    void push() {
-        if (batch_.size() == 0) return;
-        if (batch_.compact_ok) {
-            ipx_batch_compact v = batch_.view_compact();
-            check_ipx(h_, ipx_push_batch_compact(h_, &v));
-        } else {
-            ipx_batch v = batch_.view();
-            check_ipx(h_, ipx_push_batch(h_, &v));
+        memcpy(&p, rec + 4, 4);
+        memcpy(&n_cigar, rec + 12, 2);
+        memcpy(&fl, rec + 14, 2);
+        memcpy(&l_seq, rec + 16, 4);
+        tid = map_tid(tid);
+        const uint8_t *cig = rec + 32 + rec[8];
+        if (!batch().room_for(1, n_cigar)) push(n_cigar);
+        /* NH and XS only ever matter for a read that yields a junction candidate, and that takes an N operation
+         * (ReadJunctionExtractor, junctions_extractor.cc:208-229): most reads of an RNA-Seq file have none, and their
+         * tags -- a dozen per record in aligner output -- need not be walked */
+        bool has_intron = n_cigar > 16;
+        for (unsigned k = 0; k < n_cigar && !has_intron; k++) {
+            uint32_t w;
+            memcpy(&w, cig + 4 * k, 4);
+            has_intron = (w & 15u) == 3u;
         }
-        batch_.clear(next_seq_);
+        uint8_t nh = IPX_NH_NONE, x = IPX_XS_ABSENT;
+        if (has_intron) ipx::scan_tag_range(cig + 4 * (size_t)n_cigar + (size_t)((l_seq + 1) / 2) + (size_t)l_seq, rec + len, &nh, &x);
+        PinnedBatch &b = batch();
+        b.begin_run(tid);
+        b.pos[b.n] = p; b.flag[b.n] = fl; b.nh[b.n] = nh; b.xs[b.n] = x; b.n_ops[b.n] = n_cigar;
+        b.ops32.push_back(n_cigar);
+        memcpy(b.cigar + b.n_cig, cig, 4 * (size_t)n_cigar); /* BAM is little-endian, and so is every host this runs on */
+        b.n_cig += n_cigar;
+        b.n++;
+        note(tid, 1);
+    }
+    /* records [first, first + n) of a chunk the BAM pipeline packed: one run of the same target index */
+    void process_run(const ipx::PackedChunk &c, const ipx::TidRun &run, uint32_t first, uint32_t n, uint64_t cigar_first) {
+        const int32_t tid = map_tid(run.tid);
+        uint32_t done = 0;
+        while (done < n) {
+            PinnedBatch *b = &batch();
+            /* as many records as fit the batch (a single record always fits an empty one: see push) */
+            uint32_t take = 0;
+            uint64_t words = 0;
+            while (done + take < n && b->n + take < b->cap_rec && b->n_cig + words + c.n_ops[first + done + take] <= b->cap_cig) {
+                words += c.n_ops[first + done + take];
+                take++;
+            }
+            if (take == 0) {
+                push(c.n_ops[first + done]);
+                continue;
+            }
+            b->begin_run(tid);
+            memcpy(b->pos + b->n, c.pos.data() + first + done, (size_t)take * 4);
+            memcpy(b->flag + b->n, c.flag.data() + first + done, (size_t)take * 2);
+            memcpy(b->nh + b->n, c.nh_class.data() + first + done, take);
+            memcpy(b->xs + b->n, c.xs.data() + first + done, take);
+            for (uint32_t k = 0; k < take; k++) b->n_ops[b->n + k] = (uint16_t)c.n_ops[first + done + k];
+            b->ops32.insert(b->ops32.end(), c.n_ops.begin() + first + done, c.n_ops.begin() + first + done + take);
+            if (c.max_ops > 0xFFFFu) b->compact_ok = false;
+            memcpy(b->cigar + b->n_cig, c.cigar.data() + cigar_first, (size_t)words * 4);
+            b->n_cig += words;
+            b->n += take;
+            cigar_first += words;
+            done += take;
+            note(tid, take);
+        }
+    }
+    /* hand the batch in hand to the engine (the copy to the device is asynchronous) and continue in the other one;
+     * next_cigar: CIGAR words of the record that comes next (a record with more words than a batch holds gets a batch
+     * of its own size) */
+    void push(size_t next_cigar = 0) {
+        PinnedBatch &b = batch();
+        if (b.n != 0) {
+            if (b.compact_ok) {
+                ipx_batch_compact v;
+                memset(&v, 0, sizeof(v));
+                v.n_records = b.n; v.n_cigar = b.n_cig; v.seq_base = b.seq_base;
+                v.pos = b.pos; v.flag = b.flag; v.nh_class = b.nh; v.xs = b.xs; v.n_cigar_ops = b.n_ops; v.cigar = b.cigar;
+                v.n_tid_runs = b.run_tid.size(); v.run_tid = b.run_tid.data(); v.run_start = b.run_start.data();
+                check_ipx(h_, ipx_push_batch_compact(h_, &v));
+            } else {
+                /* a record with more than 65535 operations: the plain batch with 32-bit offsets */
+                vector<uint32_t> off(b.n + 1, 0u);
+                vector<int32_t> tid(b.n);
+                for (size_t i = 0; i < b.n; i++) off[i + 1] = off[i] + b.ops32[i];
+                for (size_t r = 0; r < b.run_tid.size(); r++) {
+                    const size_t e = r + 1 < b.run_tid.size() ? (size_t)b.run_start[r + 1] : b.n;
+                    for (size_t i = (size_t)b.run_start[r]; i < e; i++) tid[i] = b.run_tid[r];
+                }
+                ipx_batch v;
+                memset(&v, 0, sizeof(v));
+                v.n_records = b.n; v.n_cigar = b.n_cig; v.seq_base = b.seq_base;
+                v.tid = tid.data(); v.pos = b.pos; v.flag = b.flag; v.nh_class = b.nh; v.xs = b.xs; v.cigar_off = off.data(); v.cigar = b.cigar;
+                check_ipx(h_, ipx_push_batch(h_, &v));
+                check_ipx(h_, ipx_sync_uploads(h_, 0)); /* off / tid go out of scope */
+            }
+            cur_ ^= 1;
+            /* the other buffer was handed over two pushes ago: its copy must have run before it is written again */
+            check_ipx(h_, ipx_sync_uploads(h_, 1));
+        }
+        PinnedBatch &nb = batch();
+        nb.clear(next_seq_);
+        if (next_cigar > nb.cap_cig) {
+            nb.release();
+            nb.allocate(nb.cap_rec, next_cigar + next_cigar / 4);
+        }
     }
     ipx_table *flush() {
         push();
@@ -475,6 +625,24 @@ class Driver {
     }
     ipx_handle *handle() { return h_; }
 };
+
+/* The BAM pipeline (host/bam_pipeline.h) takes a regular BAM file whenever nobody needs the records themselves (no
+ * pass-through, no per-read side output).  IPX_NO_PIPELINE=1 keeps the record-at-a-time reader. */
+static bool pipeline_eligible(const Input &in, const string &path) {
+    if (getenv("IPX_NO_PIPELINE") != NULL || getenv("IPX_NO_RAW_PACK") != NULL) return false;
+    if (hts_get_format(in.in)->format != bam) return false;
+    if (path == "-" || path == "/dev/stdin") return false;
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    const bool seekable = fseek(f, 0, SEEK_END) == 0;
+    fclose(f);
+    return seekable;
+}
+
+static int pipeline_threads() {
+    if (const char *e = getenv("IPX_DECODE_THREADS")) return atoi(e) > 0 ? atoi(e) : 1;
+    return 0; /* one per core */
+}
 
 /* output_junctions (intronProspector.cc:330-351) for table rows [begin, end) */
 static void output_junctions(const ipx_table *t, const vector<string> &targets, uint64_t begin, uint64_t end,
@@ -518,6 +686,37 @@ static void extract_by_target(Driver &drv, const Options &opts, Outputs &out, An
     bool pending = false, eof = false;
     int stop_target = n_targets; /* targets [0, stop_target) get their output */
     string fatal;
+    const bool fast = !ann.active() && in.out == NULL && pipeline_eligible(in, opts.bam_files[0]);
+    if (fast) {
+        /* The same selection of records as the loops below, on runs of equal target index: target t takes the records
+         * of index t; a record of another index ends target t (it is "not coordinate sorted" when its index lies below
+         * the target before), and stays in hand for the targets that follow. */
+        ipx::BamPipeline pipe;
+        if (!pipe.open(opts.bam_files[0].c_str(), ipx_bam_header_bytes(in.in), pipeline_threads()))
+            throw runtime_error("Error opening BAM/SAM/CRAM file: " + opts.bam_files[0]);
+        int target = 0;
+        bool stopped = n_targets == 0, damaged = false;
+        ipx::PackedChunk *c;
+        while (!stopped && !damaged && (c = pipe.next()) != NULL) {
+            for (size_t r = 0; r < c->runs.size() && !stopped; r++) {
+                const ipx::TidRun &run = c->runs[r];
+                while (!stopped && run.tid != target) {
+                    if (run.tid >= 0 && run.tid < previous_target) {
+                        fatal = "BAM appears to not be coordinate sorted";
+                        stop_target = target;
+                        stopped = true;
+                        break;
+                    }
+                    previous_target = target;
+                    if (++target >= n_targets) stopped = true;
+                }
+                if (!stopped) drv.process_run(*c, run, run.first, run.n, run.cigar_first);
+            }
+            damaged = c->bad && !stopped;
+            pipe.release(c);
+        }
+        if (damaged) throw runtime_error("Error reader BAM record: " + opts.bam_files[0]);
+    }
     /* the record in hand: in the reader's buffer (not consumed until it is processed) or in in.rec */
     bool cur_raw = false;
     const uint8_t *cur_bytes = NULL;
@@ -534,7 +733,7 @@ static void extract_by_target(Driver &drv, const Options &opts, Outputs &out, An
         cur_tid = in.rec->core.tid;
         return true;
     };
-    for (int target = 0; target < n_targets && fatal.empty(); target++) {
+    for (int target = 0; !fast && target < n_targets && fatal.empty(); target++) {
         for (;;) {
             if (!pending) {
                 if (eof || !fetch()) {
@@ -608,6 +807,20 @@ static void extract_whole_files(Driver &drv, const Options &opts, Outputs &out, 
          * after every record has been consumed: the file gets the header only */
         if (opts.bam_files.size() == 1 && opts.bam_pass_through != "") in.open_pass_through(opts.bam_pass_through);
         if (!ann.active()) in.enable_raw();
+        if (!ann.active() && in.out == NULL && pipeline_eligible(in, opts.bam_files[ibam])) {
+            ipx::BamPipeline pipe;
+            if (!pipe.open(opts.bam_files[ibam].c_str(), ipx_bam_header_bytes(in.in), pipeline_threads()))
+                throw runtime_error("Error opening BAM/SAM/CRAM file: " + opts.bam_files[ibam]);
+            bool damaged = false;
+            ipx::PackedChunk *c;
+            while (!damaged && (c = pipe.next()) != NULL) {
+                for (const ipx::TidRun &run : c->runs) drv.process_run(*c, run, run.first, run.n, run.cigar_first);
+                damaged = c->bad;
+                pipe.release(c);
+            }
+            if (damaged) throw runtime_error("Error reader BAM record: " + opts.bam_files[ibam]);
+            continue;
+        }
         for (;;) {
             const uint8_t *bytes;
             uint32_t len;

@@ -7,6 +7,7 @@
 #include "genome_loader.h"
 #include "htslib/faidx.h"
 #include "htslib/sam.h"
+#include "bam_pipeline.h"
 #include "record_source.h"
 
 static thread_local std::string g_err;
@@ -92,6 +93,68 @@ extern "C" int64_t ipxio_read_batch(ipxio_reader *r, uint64_t max_records, uint6
         cigar_off[n] = (uint32_t)nc;
     }
     if (n_cigar_out) *n_cigar_out = nc;
+    return (int64_t)n;
+}
+
+/* The whole file through the BAM pipeline (what the command-line tool does with a BAM file): the same columns as
+ * ipxio_read_batch over all records, into caller buffers sized max_records / max_cigar.  Returns the number of records,
+ * -1 on a damaged file (after the records before the damage), -2 when the buffers are too small. */
+extern "C" int64_t ipxio_pipeline_read(const char *path, int32_t threads, uint64_t max_records, uint64_t max_cigar, int32_t *tid,
+                                       int32_t *pos, uint16_t *flag, uint8_t *nh_class, uint8_t *xs, uint32_t *cigar_off, uint32_t *cigar,
+                                       uint64_t *n_cigar_out) {
+    samFile *fp = sam_open(path, "r");
+    if (!fp) {
+        g_err = std::string("Error opening BAM/SAM/CRAM file: ") + path;
+        return -1;
+    }
+    sam_hdr_t *hdr = sam_hdr_read(fp);
+    if (!hdr || hts_get_format(fp)->format != bam) {
+        if (hdr) sam_hdr_destroy(hdr);
+        sam_close(fp);
+        g_err = std::string("not a BAM file: ") + path;
+        return -1;
+    }
+    const uint64_t skip = ipx_bam_header_bytes(fp);
+    sam_hdr_destroy(hdr);
+    sam_close(fp);
+    ipx::BamPipeline pipe;
+    if (!pipe.open(path, skip, threads)) {
+        g_err = std::string("Error opening BAM/SAM/CRAM file: ") + path;
+        return -1;
+    }
+    uint64_t n = 0, nc = 0;
+    cigar_off[0] = 0;
+    bool damaged = false, full = false;
+    ipx::PackedChunk *c;
+    while (!damaged && !full && (c = pipe.next()) != nullptr) {
+        if (n + c->size() > max_records || nc + c->cigar.size() > max_cigar) {
+            full = true;
+        } else {
+            for (const ipx::TidRun &run : c->runs)
+                for (uint32_t i = 0; i < run.n; i++) tid[n + run.first + i] = run.tid;
+            for (size_t i = 0; i < c->size(); i++) {
+                pos[n + i] = c->pos[i];
+                flag[n + i] = c->flag[i];
+                nh_class[n + i] = c->nh_class[i];
+                xs[n + i] = c->xs[i];
+                cigar_off[n + i + 1] = cigar_off[n + i] + c->n_ops[i];
+            }
+            memcpy(cigar + nc, c->cigar.data(), c->cigar.size() * 4);
+            n += c->size();
+            nc += c->cigar.size();
+            damaged = c->bad;
+        }
+        pipe.release(c);
+    }
+    if (n_cigar_out) *n_cigar_out = nc;
+    if (full) {
+        g_err = "the buffers are too small for the file";
+        return -2;
+    }
+    if (damaged) {
+        g_err = "Error reader BAM record";
+        return -1;
+    }
     return (int64_t)n;
 }
 

@@ -26,13 +26,23 @@ static size_t aux_size(const uint8_t *t, const uint8_t *end) {
     }
 }
 
-static void scan_tag_range(const uint8_t *a, const uint8_t *end, uint8_t *nh_class, uint8_t *xs);
 
 void scan_tags(const bam1_t *b, uint8_t *nh_class, uint8_t *xs) {
     scan_tag_range(bam_get_aux(b), b->data + b->l_data, nh_class, xs);
 }
 
-static void scan_tag_range(const uint8_t *a, const uint8_t *end, uint8_t *nh_class, uint8_t *xs) {
+const uint8_t *find_aux(const uint8_t *a, const uint8_t *end, char t0, char t1) {
+    while (a + 2 < end) {
+        const uint8_t *t = a + 2;
+        const size_t vs = aux_size(t, end);
+        if (vs == 0 || t + vs > end) return nullptr;
+        if (a[0] == (uint8_t)t0 && a[1] == (uint8_t)t1) return t;
+        a = t + vs;
+    }
+    return nullptr;
+}
+
+void scan_tag_range(const uint8_t *a, const uint8_t *end, uint8_t *nh_class, uint8_t *xs) {
     *nh_class = IPX_NH_NONE;
     *xs = IPX_XS_ABSENT;
     bool seen_nh = false, seen_xs = false;

@@ -13,6 +13,10 @@ namespace ipx {
  *   nh_class: get_num_aligns (junctions_extractor.cc:49-56) -- first NH tag; bam_aux2i yields 0 for non-integer types
  *   xs:       get_junction_strand_XS (junctions_extractor.cc:322-330) -- first XS tag; bam_aux2A yields 0 unless type 'A' */
 void scan_tags(const bam1_t *b, uint8_t *nh_class, uint8_t *xs);
+/* the same over the aux block [a, end) of a BAM record where it lies in a buffer */
+void scan_tag_range(const uint8_t *a, const uint8_t *end, uint8_t *nh_class, uint8_t *xs);
+/* the first tag named t0 t1 in an aux block: pointer to its type byte, or NULL */
+const uint8_t *find_aux(const uint8_t *a, const uint8_t *end, char t0, char t1);
 
 /* growable structure-of-arrays batch */
 struct ColumnarBatch {

@@ -474,6 +474,7 @@ struct ipx_hts_impl {
     std::unordered_map<std::string, int> name2tid;
     bool name_map_built = false;
     std::string scratch;
+    uint64_t bam_header_bytes = 0; /* uncompressed bytes of a BAM file before its first record */
 };
 
 /* ---------- open / close ---------- */
@@ -637,6 +638,7 @@ extern "C" sam_hdr_t *sam_hdr_read(samFile *fp) {
         if (!rd.read_exact(h->text, l_text)) { sam_hdr_destroy(h); return nullptr; }
         h->text[l_text] = 0;
         h->l_text = strlen(h->text);  /* text may be NUL padded */
+        uint64_t consumed = 8 + (uint64_t)l_text + 4;
         if (!rd.read_exact(&n_ref, 4) || n_ref < 0) { sam_hdr_destroy(h); return nullptr; }
         for (int i = 0; i < n_ref; i++) {
             int32_t l_name, l_ref;
@@ -644,7 +646,9 @@ extern "C" sam_hdr_t *sam_hdr_read(samFile *fp) {
             std::string nm(l_name, 0);
             if (!rd.read_exact(&nm[0], l_name) || !rd.read_exact(&l_ref, 4)) { sam_hdr_destroy(h); return nullptr; }
             hdr_add_target(h, nm.c_str(), strlen(nm.c_str()), (uint32_t)l_ref);
+            consumed += 8 + (uint64_t)l_name;
         }
+        fp->impl->bam_header_bytes = consumed;
         return h;
     }
     std::string text, line;
@@ -845,6 +849,8 @@ extern "C" int ipx_bam_peek(samFile *fp, const uint8_t **rec, uint32_t *len) {
     *len = (uint32_t)block_len;
     return 1;
 }
+
+extern "C" uint64_t ipx_bam_header_bytes(samFile *fp) { return (fp && fp->impl) ? fp->impl->bam_header_bytes : 0; }
 
 extern "C" void ipx_bam_consume(samFile *fp) {
     Reader &rd = fp->impl->rd;

@@ -130,6 +130,8 @@ int bam_aux_del(bam1_t *b, uint8_t *s);
  * record, a CIGAR kept in the CG tag).  Nothing is consumed; the pointer is valid until the next read on fp.
  * ipx_bam_consume steps over the record the last ipx_bam_peek returned. */
 int ipx_bam_peek(samFile *fp, const uint8_t **rec, uint32_t *len);
+/* uncompressed bytes of a BAM file before its first record (after sam_hdr_read) */
+uint64_t ipx_bam_header_bytes(samFile *fp);
 void ipx_bam_consume(samFile *fp);
 
 #ifdef __cplusplus

@@ -137,7 +137,7 @@ struct StageTimer {
     uint64_t launches = 0;
 };
 
-static const size_t COUNTER_WORDS = 16 * 16; /* 16 cache lines of counters and flags */
+static const size_t COUNTER_WORDS = 16 * 16 + 1024; /* 16 cache lines of counters and flags, then the pools of junction ids */
 
 }  // namespace
 
@@ -186,6 +186,11 @@ struct ipx_handle {
     bool exported_unsettled = false;     /* an export went out before the last batch's fold was known to be complete */
     bool late_fold = false;              /* ... and it was not: events were folded after the export (ipx_exchange_settle) */
     uint64_t log_bound = 0; /* upper bound of the log entries written since the last clear (sizes the log ahead of a batch) */
+    /* host -> device copies of the last pushes: an event behind each, so that a caller that packs into two pinned
+     * buffers in turn knows when one may be written again (ipx_sync_uploads) */
+    static const int UPLOAD_RING = 4;
+    cudaEvent_t upload_done[UPLOAD_RING] = {};
+    uint64_t n_uploads = 0;
     /* deferred counting (multi-GPU with the canon filter): the events of every batch pushed since the last count */
     struct Deferred {
         void *events;
@@ -308,6 +313,7 @@ void set_counter_pointers(ipx_handle *h) {
     t.err_sv = h->d_counters + 64;
     t.overflow = (uint32_t *)(h->d_counters + 80);
     t.n_unfolded = h->d_counters + 128;
+    t.id_pools = h->d_counters + 256;
 }
 
 int alloc_counters(ipx_handle *h) {
@@ -326,6 +332,7 @@ int alloc_rows(ipx_handle *h, Tables &t, uint64_t max_j, bool dense) {
     CU(h, cudaMalloc(&t.jslot, max_j * sizeof(uint32_t)));
     CU(h, cudaMalloc(&t.stat, max_j * sizeof(JStat)));
     CU(h, cudaMalloc(&t.olog_cnt, max_j * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&t.obase, max_j * sizeof(uint32_t)));
     t.dense = nullptr;
     /* dense offset rows: 1 KB per junction */
     if (dense) CU(h, cudaMalloc(&t.dense, max_j * DENSE_W * sizeof(uint32_t)));
@@ -333,15 +340,15 @@ int alloc_rows(ipx_handle *h, Tables &t, uint64_t max_j, bool dense) {
 }
 
 void free_rows(Tables &t) {
-    cudaFree(t.jkey); cudaFree(t.jtid); cudaFree(t.jslot); cudaFree(t.stat); cudaFree(t.olog_cnt); cudaFree(t.dense);
-    t.jkey = nullptr; t.jtid = nullptr; t.jslot = nullptr; t.stat = nullptr; t.olog_cnt = nullptr; t.dense = nullptr;
+    cudaFree(t.jkey); cudaFree(t.jtid); cudaFree(t.jslot); cudaFree(t.stat); cudaFree(t.olog_cnt); cudaFree(t.obase); cudaFree(t.dense);
+    t.jkey = nullptr; t.jtid = nullptr; t.jslot = nullptr; t.stat = nullptr; t.olog_cnt = nullptr; t.obase = nullptr; t.dense = nullptr;
 }
 
 int alloc_tables(ipx_handle *h) {
     if (h->tables_ready) return IPX_OK;
     /* table_capacity = hash slots; at most half of them are used, so half as many junction rows.  Both grow on demand. */
     uint64_t want_cap = h->params.table_capacity ? h->params.table_capacity : (1ull << 22);
-    uint64_t cap = pow2_at_least(want_cap);
+    uint64_t cap = pow2_at_least(want_cap); /* (a power of two >= 1024: the junction rows come in whole blocks of ids) */
     uint64_t hcap = h->params.hist_capacity ? std::max<uint64_t>(h->params.hist_capacity, 1024) : (1ull << 26);
     if (cap > (1ull << 31)) return fail(h, IPX_ERR_ARG, "table_capacity too large");
     int rc = alloc_counters(h);
@@ -376,6 +383,7 @@ int grow_rows(ipx_handle *h, uint64_t in_use) {
     CU(h, cudaMemcpyAsync(t.jslot, old.jslot, in_use * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     CU(h, cudaMemcpyAsync(t.stat, old.stat, in_use * sizeof(JStat), cudaMemcpyDeviceToDevice, st));
     CU(h, cudaMemcpyAsync(t.olog_cnt, old.olog_cnt, in_use * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    CU(h, cudaMemcpyAsync(t.obase, old.obase, in_use * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     if (t.dense) CU(h, cudaMemcpyAsync(t.dense, old.dense, in_use * DENSE_W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     launch_init_rows(t, in_use, st);
     CU(h, cudaStreamSynchronize(st));
@@ -726,6 +734,8 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     finalize_release(h->fw);
     mailbox_release(h);
     cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
+    for (auto &e : h->upload_done)
+        if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -769,6 +779,15 @@ extern "C" int ipx_set_genome(ipx_handle *h, int32_t n_seqs, const char *const *
     return upload_target_maps(h);
 }
 
+namespace {
+void mark_upload(ipx_handle *h) {
+    cudaEvent_t &e = h->upload_done[h->n_uploads % ipx_handle::UPLOAD_RING];
+    if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventRecord(e, h->stream);
+    h->n_uploads++;
+}
+}  // namespace
+
 extern "C" int ipx_push_batch_device(ipx_handle *h, const ipx_batch *b) {
     if (!h || !b) return IPX_ERR_ARG;
     cudaSetDevice(h->device);
@@ -782,6 +801,11 @@ extern "C" int ipx_push_batch(ipx_handle *h, const ipx_batch *b) {
     if (b->n_cigar >> 32) return fail(h, IPX_ERR_ARG, "more than 2^32 CIGAR words in one batch");
     cudaSetDevice(h->device);
     const uint64_t n = b->n_records;
+    {
+        /* before this batch's copies are enqueued, so that the wait is for work that finished long ago */
+        int rcs = settle_batch(h);
+        if (rcs) return rcs;
+    }
     CU(h, h->s_tid.reserve(n * 4, h->stream));
     CU(h, h->s_pos.reserve(n * 4, h->stream));
     CU(h, h->s_flag.reserve(n * 2, h->stream));
@@ -797,6 +821,7 @@ extern "C" int ipx_push_batch(ipx_handle *h, const ipx_batch *b) {
     CU(h, cudaMemcpyAsync(h->s_xs.p, b->xs, n, cudaMemcpyHostToDevice, h->stream));
     CU(h, cudaMemcpyAsync(h->s_off.p, b->cigar_off, (n + 1) * 4, cudaMemcpyHostToDevice, h->stream));
     if (b->n_cigar) CU(h, cudaMemcpyAsync(h->s_cig.p, b->cigar, b->n_cigar * 4, cudaMemcpyHostToDevice, h->stream));
+    mark_upload(h);
     BatchView v{(const int32_t *)h->s_tid.p, (const int32_t *)h->s_pos.p, (const uint16_t *)h->s_flag.p,
                 (const uint8_t *)h->s_nh.p, (const uint8_t *)h->s_xs.p, (const uint32_t *)h->s_off.p,
                 (const uint32_t *)h->s_cig.p, n, b->seq_base};
@@ -856,6 +881,11 @@ extern "C" int ipx_push_batch_compact(ipx_handle *h, const ipx_batch_compact *b)
     cudaSetDevice(h->device);
     const uint64_t n = b->n_records, nr = b->n_tid_runs;
     cudaStream_t st = h->stream;
+    {
+        /* before this batch's copies are enqueued, so that the wait is for work that finished long ago */
+        int rcs = settle_batch(h);
+        if (rcs) return rcs;
+    }
     CU(h, h->s_tid.reserve(n * 4, st));
     CU(h, h->s_pos.reserve(n * 4, st));
     CU(h, h->s_flag.reserve(n * 2, st));
@@ -879,12 +909,36 @@ extern "C" int ipx_push_batch_compact(ipx_handle *h, const ipx_batch_compact *b)
     CU(h, cudaMemcpyAsync(h->s_nh.p, b->nh_class, n, cudaMemcpyHostToDevice, st));
     CU(h, cudaMemcpyAsync(h->s_xs.p, b->xs, n, cudaMemcpyHostToDevice, st));
     if (b->n_cigar) CU(h, cudaMemcpyAsync(h->s_cig.p, b->cigar, b->n_cigar * 4, cudaMemcpyHostToDevice, st));
+    mark_upload(h);
     CU(h, expand_compact((const uint16_t *)h->s_nops.p, n, (uint32_t *)h->s_off.p, d_run_tid, d_run_start, nr, (int32_t *)h->s_tid.p,
                          h->s_tmp.p, &tmp_bytes, st));
     BatchView v{(const int32_t *)h->s_tid.p, (const int32_t *)h->s_pos.p, (const uint16_t *)h->s_flag.p,
                 (const uint8_t *)h->s_nh.p, (const uint8_t *)h->s_xs.p, (const uint32_t *)h->s_off.p,
                 (const uint32_t *)h->s_cig.p, n, b->seq_base};
     return run_batch(h, v, b->n_cigar);
+}
+
+extern "C" void *ipx_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void ipx_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int ipx_sync_uploads(ipx_handle *h, uint32_t keep_in_flight) {
+    if (!h) return IPX_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (h->n_uploads <= keep_in_flight) return IPX_OK;
+    if (keep_in_flight >= (uint32_t)ipx_handle::UPLOAD_RING) return fail(h, IPX_ERR_ARG, "at most %d uploads are tracked", ipx_handle::UPLOAD_RING - 1);
+    const uint64_t last = h->n_uploads - 1 - keep_in_flight; /* this push and every earlier one must be done */
+    CU(h, cudaEventSynchronize(h->upload_done[last % ipx_handle::UPLOAD_RING]));
+    return IPX_OK;
 }
 
 extern "C" int ipx_finalize_device(ipx_handle *h) {

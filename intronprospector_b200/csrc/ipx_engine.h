@@ -121,7 +121,7 @@ struct FinalizeWork {
     uint64_t first_B = 1ull << 16, first_L = 1ull << 16, first_R = 1ull << 20; /* bounds of the very first finalize */
     unsigned long long *sort_key = nullptr, *tkey = nullptr;                     /* [B] */
     uint32_t *sort_sub = nullptr, *order = nullptr, *t_order = nullptr, *t_rank = nullptr; /* [B] */
-    uint32_t *seg_off = nullptr, *seg_fill = nullptr, *runs_j = nullptr, *nz_j = nullptr, *big_list = nullptr; /* [B] */
+    uint32_t *seg_off = nullptr, *seg_fill = nullptr, *runs_j = nullptr, *nz_j = nullptr, *below_j = nullptr, *big_list = nullptr; /* [B] */
     uint32_t *runs_r = nullptr;  /* [B + 1] */
     uint32_t *seg = nullptr;     /* [L] log entries grouped by junction, then the ordered runs' counts */
     uint32_t *big_scratch = nullptr;
@@ -140,11 +140,11 @@ struct FinalizeWork {
     /* what the captured graph depends on */
     struct Key {
         uint64_t B, L, R, C, max_j, olog_cap;
-        const void *tab_keys, *tab_rows, *tab_log, *name_rank, *gseq, *target_seq, *dense;
+        const void *tab_keys, *tab_rows, *tab_log, *tab_base, *name_rank, *gseq, *target_seq, *dense;
         int32_t n_targets, have_genome, skip_missing, filter_canon, wide, len_bits;
         bool operator==(const Key &o) const {
             return B == o.B && L == o.L && R == o.R && C == o.C && max_j == o.max_j && olog_cap == o.olog_cap &&
-                   tab_keys == o.tab_keys && tab_rows == o.tab_rows && tab_log == o.tab_log && name_rank == o.name_rank &&
+                   tab_keys == o.tab_keys && tab_rows == o.tab_rows && tab_log == o.tab_log && tab_base == o.tab_base && name_rank == o.name_rank &&
                    gseq == o.gseq && target_seq == o.target_seq && dense == o.dense && n_targets == o.n_targets &&
                    have_genome == o.have_genome && skip_missing == o.skip_missing && filter_canon == o.filter_canon &&
                    wide == o.wide && len_bits == o.len_bits;

@@ -34,7 +34,7 @@ __device__ __forceinline__ uint32_t hist_rows_of(uint32_t v) { return v ? (v - 1
 /* what a warp needs of one junction row: owner, key fields, its dense offset row (8 counters per lane) */
 struct RowView {
     int dest; /* -1: nothing to export (never created: nothing was counted into it) */
-    uint32_t i0, i1, mine, incl, nz;
+    uint32_t i0, i1, mine, incl, nz, base;
     int32_t tid;
     uint32_t v[8];
 };
@@ -46,6 +46,7 @@ __device__ __forceinline__ RowView read_row(const Tables &t, const uint32_t *nam
     const unsigned long long T = t.stat[j].T;
     const unsigned long long key = t.jkey[j];
     r.tid = t.jtid[j];
+    r.base = t.obase[j];
     uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
     if (t.dense) {
         const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + j * DENSE_W);
@@ -88,7 +89,7 @@ __device__ __forceinline__ void write_dense_rows(HistRow *hr, uint64_t o, uint32
         while (left) {
             const uint32_t piece = left > 0xFFFFu ? 0xFFFFu : left;
             HistRow h;
-            h.jrow = jrow; h.offset = (uint16_t)(lane * 8 + k); h.cnt = (uint16_t)piece;
+            h.jrow = jrow; h.offset = (uint16_t)(r.base + (uint32_t)(lane * 8 + k)); h.cnt = (uint16_t)piece;
             hr[o++] = h;
             left -= piece;
         }
@@ -163,8 +164,8 @@ void launch_export_scatter(const Tables &t, const uint32_t *name_rank, const Spl
 }
 
 /* fold one received junction row; returns the junction id or JID_NONE */
-__device__ __forceinline__ uint32_t import_junction_row(const Tables &t, const JunctionRow &r) {
-    const uint32_t j = junction_probe<true>(t, make_key(t.kl, r.tid, r.i0, r.i1), r.tid);
+__device__ __forceinline__ uint32_t import_junction_row(const Tables &t, IdPool *pool, const JunctionRow &r) {
+    const uint32_t j = junction_probe<true>(t, pool, make_key(t.kl, r.tid, r.i0, r.i1), r.tid);
     if (j == JID_NONE) return j;
     JStat *s = &t.stat[j];
     for (int c = 0; c < 3; ++c) {
@@ -178,10 +179,14 @@ __device__ __forceinline__ uint32_t import_junction_row(const Tables &t, const J
     return j;
 }
 
-__global__ void k_import_junction_rows(Tables t, const JunctionRow *jr, uint64_t n, uint32_t *jid_of) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    jid_of[i] = import_junction_row(t, jr[i]);
+__global__ void __launch_bounds__(256) k_import_junction_rows(Tables t, const JunctionRow *jr, uint64_t n, uint32_t *jid_of) {
+    __shared__ IdPool s_pool;
+    if (threadIdx.x == 0) id_pool_load(t, &s_pool);
+    __syncthreads();
+    const uint64_t n_threads = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += n_threads) jid_of[i] = import_junction_row(t, &s_pool, jr[i]);
+    __syncthreads();
+    if (threadIdx.x == 0) id_pool_store(t, &s_pool);
 }
 
 __global__ void __launch_bounds__(256) k_import_hist_rows(Tables t, const HistRow *hr, uint64_t n, const uint32_t *jid_of, uint64_t nj) {
@@ -196,15 +201,16 @@ __global__ void __launch_bounds__(256) k_import_hist_rows(Tables t, const HistRo
         cnt = r.cnt;
     }
     const bool ok = j != JID_NONE && cnt != 0u;
-    const bool in_row = t.dense != nullptr && off < DENSE_W;
-    if (ok && in_row) atomicAdd(&t.dense[(uint64_t)j * DENSE_W + off], cnt);
+    const uint32_t base = ok && t.dense ? dense_base(t, j, off) : 0u;
+    const bool in_row = ok && in_dense_row(t, base, off);
+    if (in_row) atomicAdd(&t.dense[(uint64_t)j * DENSE_W + (off - base)], cnt);
     log_append(t, log, ok && !in_row, olog_entry(j, off, cnt));
     log_flush(t, log);
 }
 
 void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, const HistRow *hr, uint64_t nh, uint32_t *jid_of,
                         cudaStream_t st) {
-    if (nj) k_import_junction_rows<<<blocks_for(nj, 256), 256, 0, st>>>(t, jr, nj, jid_of);
+    if (nj) k_import_junction_rows<<<blocks_for(nj, 256) < N_ID_POOLS ? blocks_for(nj, 256) : N_ID_POOLS, 256, 0, st>>>(t, jr, nj, jid_of);
     if (nh) k_import_hist_rows<<<blocks_for(nh, 256), 256, 0, st>>>(t, hr, nh, jid_of, nj);
 }
 
@@ -274,6 +280,7 @@ __global__ void __launch_bounds__(256) k_mail_rows(Tables t, const uint32_t *nam
                 p[2] = make_uint4(0u, 0u, 0u, 0u);
                 p[3] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
                 t.olog_cnt[j] = 0u;
+                t.obase[j] = BASE_UNSET;
             }
             if (fits) write_dense_rows(mail_hist_rows(m, box), hpos + (r.incl - r.mine), (uint32_t)jpos, r, lane);
             if (t.dense && r.nz) {
@@ -394,14 +401,24 @@ __global__ void k_mail_wait(Tables t, Mailboxes m, unsigned long long *verdict, 
 
 /* fold the junction rows of every source (blockIdx.y) out of this rank's own mailbox */
 __global__ void __launch_bounds__(256) k_mail_import_junctions(Tables t, Mailboxes m, const unsigned long long *verdict, uint32_t *jid_of) {
+    __shared__ IdPool s_pool;
     const int source = blockIdx.y;
     if (source == m.me || verdict[0] != 1ull) return;
+    /* (thread blocks of different sources share pools: every block of the grid gets its own) */
+    const uint32_t pool_index = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) {
+        s_pool.word = t.id_pools[pool_index % N_ID_POOLS];
+        s_pool.lock = 0u;
+    }
+    __syncthreads();
     char *box = mail_slot(m, m.me, source);
     const unsigned long long n_sent = *reinterpret_cast<const unsigned long long *>(box);
     const JunctionRow *jr = mail_junction_rows(box);
     uint32_t *ids = jid_of + (uint64_t)source * m.cap_j;
     const uint64_t n_threads = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sent; i += n_threads) ids[i] = import_junction_row(t, jr[i]);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sent; i += n_threads) ids[i] = import_junction_row(t, &s_pool, jr[i]);
+    __syncthreads();
+    if (threadIdx.x == 0) t.id_pools[pool_index % N_ID_POOLS] = *((volatile unsigned long long *)&s_pool.word);
 }
 
 __global__ void __launch_bounds__(256) k_mail_import_hist(Tables t, Mailboxes m, const unsigned long long *verdict, const uint32_t *jid_of) {
@@ -425,8 +442,9 @@ __global__ void __launch_bounds__(256) k_mail_import_hist(Tables t, Mailboxes m,
             cnt = r.cnt;
         }
         const bool ok = j != JID_NONE && cnt != 0u;
-        const bool in_row = t.dense != nullptr && off < DENSE_W;
-        if (ok && in_row) atomicAdd(&t.dense[(uint64_t)j * DENSE_W + off], cnt);
+        const uint32_t base = ok && t.dense ? dense_base(t, j, off) : 0u;
+        const bool in_row = ok && in_dense_row(t, base, off);
+        if (in_row) atomicAdd(&t.dense[(uint64_t)j * DENSE_W + (off - base)], cnt);
         log_append(t, log, ok && !in_row, olog_entry(j, off, cnt));
     }
     log_flush(t, log);
@@ -436,7 +454,8 @@ void launch_mail_import(const Tables &t, const Mailboxes &m, unsigned long long 
                         unsigned long long timeout_ns, cudaStream_t st) {
     k_mail_wait<<<1, 32, 0, st>>>(t, m, verdict, timeout_ns);
     if (m.world < 2) return;
-    const unsigned per_source = (unsigned)((sm_count * 4 + m.world - 2) / (m.world - 1));
+    unsigned per_source = (unsigned)((sm_count * 4 + m.world - 2) / (m.world - 1));
+    if (per_source * (unsigned)m.world > N_ID_POOLS) per_source = N_ID_POOLS / (unsigned)m.world; /* a pool of junction ids per block */
     k_mail_import_junctions<<<dim3(per_source ? per_source : 1, m.world), 256, 0, st>>>(t, m, verdict, jid_of);
     k_mail_import_hist<<<dim3(per_source ? 2 * per_source : 1, m.world), 256, 0, st>>>(t, m, verdict, jid_of);
 }
@@ -461,7 +480,7 @@ __global__ void k_import_thresholds(Tables t, const ThresholdRow *rows, uint64_t
     if (i >= n) return;
     const ThresholdRow r = rows[i];
     if (r.T == EMPTY64) return;
-    const uint32_t j = junction_probe<false>(t, make_key(t.kl, r.tid, r.i0, r.i1), r.tid);
+    const uint32_t j = junction_probe<false>(t, nullptr, make_key(t.kl, r.tid, r.i0, r.i1), r.tid);
     if (j != JID_NONE) atomicMin(&t.stat[j].T, r.T);
 }
 
@@ -480,8 +499,9 @@ __global__ void k_sample_keys(Tables t, uint64_t stride, uint64_t max_out, int32
     if (q == 0) *n_out = n < max_out ? n : max_out;
     if (q >= n || q >= max_out) return;
     const uint64_t j = q * stride;
-    tid[q] = t.jtid[j];
-    i0[q] = key_start(t.kl, t.jkey[j]);
+    const bool hole = t.jslot[j] == SLOT_NONE; /* an id no junction took */
+    tid[q] = hole ? -1 : t.jtid[j];
+    i0[q] = hole ? 0u : key_start(t.kl, t.jkey[j]);
 }
 
 void launch_sample_keys(const Tables &t, uint64_t stride, uint64_t max_out, int32_t *tid, uint32_t *i0, unsigned long long *n_out,

@@ -19,6 +19,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <utility>
+#include <vector>
+
 #include "ipx_engine.h"
 #include "ipx_motif.cuh"
 #include "ipx_scan.cuh"
@@ -85,7 +88,8 @@ __global__ void __launch_bounds__(256) k_fin_list(Tables t, const uint32_t *name
  * Keys equal to EMPTY64 are not part of the input.  (key, sub) pairs are unique. */
 static const int SS_MAX_BUCKETS = 4096;
 static const int SS_MAX_SAMPLE = 8192;
-static const int SS_SMEM_BUCKET = 4096; /* elements a bucket may have to be sorted in shared memory */
+static const int SS_BUCKET = 256;       /* keys per bucket the splitters aim at */
+static const int SS_SMEM_BUCKET = 1024; /* elements a bucket may have to be ranked in shared memory */
 
 struct SampleSort {
     unsigned long long *splitters; /* [SS_MAX_BUCKETS] */
@@ -131,10 +135,10 @@ __global__ void __launch_bounds__(1024) k_ss_sample(const unsigned long long *ke
                                                     SampleSort ss) {
     extern __shared__ unsigned long long s_sample[];
     const uint64_t n = *n_ptr < bound ? *n_ptr : bound;
-    uint32_t P = (uint32_t)((n + 511) / 512);
+    uint32_t P = (uint32_t)((n + SS_BUCKET - 1) / SS_BUCKET);
     if (P < 1u) P = 1u;
     if (P > (uint32_t)SS_MAX_BUCKETS) P = SS_MAX_BUCKETS;
-    uint64_t S = 4ull * P;
+    uint64_t S = 3ull * P;
     if (S > (uint64_t)SS_MAX_SAMPLE) S = SS_MAX_SAMPLE;
     if (S > n) S = n;
     uint32_t S2 = 1u;
@@ -157,15 +161,24 @@ __global__ void __launch_bounds__(256) k_ss_scatter(const unsigned long long *ke
     __syncthreads();
     const uint64_t n = *n_ptr < bound ? *n_ptr : bound;
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long key = keys[i];
-    if (key == EMPTY64) return;
-    uint32_t lo = 0u, hi = P - 1u; /* number of splitters <= key lies in [lo, hi] */
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (s_split[mid] <= key) lo = mid + 1u; else hi = mid;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long key = i < n ? keys[i] : EMPTY64;
+    uint32_t lo = 0xFFFFFFFFu - (uint32_t)lane; /* lanes with nothing to place group with nobody */
+    if (key != EMPTY64) {
+        uint32_t hi = P - 1u; /* number of splitters <= key lies in [lo, hi] */
+        lo = 0u;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_split[mid] <= key) lo = mid + 1u; else hi = mid;
+        }
     }
-    const uint32_t pos = atomicAdd(&ss.bucket_cnt[lo], 1u);
+    /* keys arrive nearly in order, so a warp's keys mostly share a bucket: one atomic per (warp, bucket) */
+    const unsigned grp = __match_any_sync(0xFFFFFFFFu, lo);
+    const int leader = __ffs(grp) - 1;
+    uint32_t pos = 0u;
+    if (key != EMPTY64 && lane == leader) pos = atomicAdd(&ss.bucket_cnt[lo], (uint32_t)__popc(grp));
+    pos = __shfl_sync(0xFFFFFFFFu, pos, leader) + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+    if (key == EMPTY64) return;
     if (pos < ss.C) {
         const uint64_t at = (uint64_t)lo * ss.C + pos;
         ss.bk[at] = key;
@@ -177,12 +190,14 @@ __global__ void __launch_bounds__(256) k_ss_scatter(const unsigned long long *ke
     }
 }
 
-/* one block per bucket: sort it, write the values at the bucket's place in the global order (and, when asked, the
- * position of every value).  A bucket that does not fit shared memory is ranked by counting (quadratic: only a
- * pathological input makes such buckets). */
-__global__ void __launch_bounds__(512) k_ss_local(SampleSort ss, uint32_t *out_vals, uint32_t *out_rank) {
-    extern __shared__ unsigned long long s_mem[];
-    __shared__ uint32_t s_part[16];
+/* One block per bucket: every key's rank among the bucket's keys by counting (the keys are unique), out of shared
+ * memory -- no barriers between steps, the inner loop reads one address per iteration (a broadcast).  The values go to
+ * the bucket's place in the global order (and, when asked, the position of every value).  A bucket that does not fit
+ * shared memory is counted out of global memory (only a pathological input makes such buckets). */
+__global__ void __launch_bounds__(256) k_ss_local(SampleSort ss, uint32_t *out_vals, uint32_t *out_rank) {
+    __shared__ unsigned long long s_k[SS_SMEM_BUCKET];
+    __shared__ uint32_t s_s[SS_SMEM_BUCKET];
+    __shared__ uint32_t s_part[8];
     const uint32_t P = ss.bucket_cnt[SS_MAX_BUCKETS];
     const uint32_t b = blockIdx.x;
     if (b >= P) return;
@@ -199,45 +214,75 @@ __global__ void __launch_bounds__(512) k_ss_local(SampleSort ss, uint32_t *out_v
     if (cnt == 0u) return;
     const unsigned long long *gk = ss.bk + (uint64_t)b * ss.C;
     const uint32_t *gs = ss.bs + (uint64_t)b * ss.C, *gv = ss.bv + (uint64_t)b * ss.C;
-    if (cnt <= (uint32_t)SS_SMEM_BUCKET) {
-        uint32_t n2 = 2u;
-        while (n2 < cnt) n2 <<= 1;
-        unsigned long long *k = s_mem;
-        uint32_t *s = reinterpret_cast<uint32_t *>(s_mem + SS_SMEM_BUCKET);
-        uint32_t *v = s + SS_SMEM_BUCKET;
-        for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
-            k[i] = i < cnt ? gk[i] : EMPTY64;
-            s[i] = i < cnt ? gs[i] : 0xFFFFFFFFu;
-            v[i] = i < cnt ? gv[i] : 0u;
-        }
-        block_bitonic<true>(k, s, v, n2);
+    const bool staged = cnt <= (uint32_t)SS_SMEM_BUCKET;
+    if (staged) {
         for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-            out_vals[base + i] = v[i];
-            if (out_rank) out_rank[v[i]] = base + i;
+            s_k[i] = gk[i];
+            s_s[i] = gs[i];
         }
-    } else {
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-            const unsigned long long ki = gk[i];
-            const uint32_t si = gs[i];
-            uint32_t rank = 0u;
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const unsigned long long ki = staged ? s_k[i] : gk[i];
+        const uint32_t si = staged ? s_s[i] : gs[i];
+        uint32_t rank = 0u;
+        if (staged) {
+#pragma unroll 4
+            for (uint32_t x = 0; x < cnt; ++x) rank += pair_less(s_k[x], s_s[x], ki, si) ? 1u : 0u;
+        } else {
             for (uint32_t x = 0; x < cnt; ++x) rank += pair_less(gk[x], gs[x], ki, si) ? 1u : 0u;
-            out_vals[base + rank] = gv[i];
-            if (out_rank) out_rank[gv[i]] = base + rank;
         }
+        const uint32_t v = gv[i];
+        out_vals[base + rank] = v;
+        if (out_rank) out_rank[v] = base + rank;
     }
 }
 
-static const size_t SS_LOCAL_SMEM = (size_t)SS_SMEM_BUCKET * (8 + 4 + 4);
+
+/* IPX_FIN_TRACE=1 (with IPX_NO_GRAPH=1): CUDA events between the steps, everything on one stream, times on stderr */
+struct FinTrace {
+    bool on;
+    cudaStream_t st;
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
+    const unsigned long long *counts = nullptr; /* pinned copy of d_count, valid after the last mark */
+    void mark(const char *what) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        marks.emplace_back(what, e);
+    }
+    void report() {
+        if (!on || marks.empty()) return;
+        cudaEventSynchronize(marks.back().second);
+        fprintf(stderr, "[ipx finalize]");
+        for (size_t i = 1; i < marks.size(); i++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            fprintf(stderr, " %s %.1f", marks[i].first, ms * 1000.f);
+        }
+        float total = 0.f;
+        cudaEventElapsedTime(&total, marks.front().second, marks.back().second);
+        fprintf(stderr, " | total %.1f us", total * 1000.f);
+        if (counts) fprintf(stderr, " | junctions %llu runs %llu ids %llu log %llu big %llu", counts[0], counts[1], counts[4], counts[5], counts[6]);
+        fprintf(stderr, "\n");
+        for (auto &m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+    }
+};
 
 static cudaError_t sample_sort(const unsigned long long *keys, const uint32_t *sub, const unsigned long long *n_ptr, uint64_t bound,
                                const SampleSort &ss, uint32_t *out_vals, uint32_t *out_rank, unsigned long long *d_count,
-                               cudaStream_t st) {
-    uint64_t p_bound = (bound + 511) / 512;
+                               cudaStream_t st, FinTrace *tr = nullptr) {
+    uint64_t p_bound = (bound + SS_BUCKET - 1) / SS_BUCKET;
     if (p_bound < 1) p_bound = 1;
     if (p_bound > (uint64_t)SS_MAX_BUCKETS) p_bound = SS_MAX_BUCKETS;
     k_ss_sample<<<1, 1024, SS_MAX_SAMPLE * sizeof(unsigned long long), st>>>(keys, n_ptr, bound, ss);
+    if (tr) tr->mark("sample");
     k_ss_scatter<<<(unsigned)((bound + 255) / 256), 256, 0, st>>>(keys, sub, n_ptr, bound, ss, d_count);
-    k_ss_local<<<(unsigned)p_bound, 512, SS_LOCAL_SMEM, st>>>(ss, out_vals, out_rank);
+    if (tr) tr->mark("scatter");
+    k_ss_local<<<(unsigned)p_bound, 256, 0, st>>>(ss, out_vals, out_rank);
+    if (tr) tr->mark("local");
     return cudaGetLastError();
 }
 
@@ -272,10 +317,11 @@ __device__ __forceinline__ uint32_t dense_nonzeros(const Tables &t, uint64_t j, 
 }
 
 /* warp per junction id: non-zero counters of its dense row; its log segment ordered by offset and run-length reduced
- * in place (the counts of the runs, ascending offset, replace the entries); runs_j = runs of both kinds.  Junctions
- * with more than FIN_SMALL log entries are left to k_fin_big. */
+ * in place (the counts of the runs, ascending offset, replace the entries); runs_j = runs of both kinds, below_j = log
+ * runs with offsets below the dense row's first (they come first in the output).  Junctions with more than FIN_SMALL
+ * log entries are left to k_fin_big. */
 __global__ void __launch_bounds__(256) k_fin_small(Tables t, uint64_t B, uint64_t L, unsigned long long *d_count, const uint32_t *seg_off,
-                                                   uint32_t *seg, uint32_t *runs_j, uint32_t *nz_j, uint32_t *big_list) {
+                                                   uint32_t *seg, uint32_t *runs_j, uint32_t *nz_j, uint32_t *below_j, uint32_t *big_list) {
     __shared__ uint32_t s_w[8][FIN_SMALL];
     __shared__ uint32_t s_c[8][FIN_SMALL];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -283,14 +329,14 @@ __global__ void __launch_bounds__(256) k_fin_small(Tables t, uint64_t B, uint64_
     const uint64_t nk = d_count[4] < B ? d_count[4] : B;
     if (j >= nk) return;
     if (t.stat[j].T == EMPTY64) {
-        if (lane == 0) { runs_j[j] = 0u; nz_j[j] = 0u; }
+        if (lane == 0) { runs_j[j] = 0u; nz_j[j] = 0u; below_j[j] = 0u; }
         return;
     }
     const uint32_t nz = dense_nonzeros(t, j, lane);
     const uint32_t n = t.olog_cnt[j];
     const uint64_t s0 = seg_off[j];
     if (n == 0u || s0 + n > L) { /* (beyond L: the bound was too small, the finalize runs again) */
-        if (lane == 0) { runs_j[j] = nz; nz_j[j] = nz; }
+        if (lane == 0) { runs_j[j] = nz; nz_j[j] = nz; below_j[j] = 0u; }
         return;
     }
     if (n > FIN_SMALL) {
@@ -300,6 +346,7 @@ __global__ void __launch_bounds__(256) k_fin_small(Tables t, uint64_t B, uint64_
         }
         return;
     }
+    const uint32_t base = t.dense ? t.obase[j] : 0u; /* (set: a junction with log entries has counted a read) */
     uint32_t *w = s_w[warp], *c = s_c[warp];
     uint32_t n2 = 2u;
     while (n2 < n) n2 <<= 1;
@@ -316,7 +363,7 @@ __global__ void __launch_bounds__(256) k_fin_small(Tables t, uint64_t B, uint64_
     }
     __syncwarp();
     /* runs of equal offsets (the high half of an entry), their counts summed */
-    uint32_t n_runs = 0u;
+    uint32_t n_runs = 0u, n_below = 0u;
     for (uint32_t i0 = 0; i0 < n; i0 += 32u) {
         const uint32_t i = i0 + lane;
         const bool valid = i < n;
@@ -328,71 +375,94 @@ __global__ void __launch_bounds__(256) k_fin_small(Tables t, uint64_t B, uint64_
         __syncwarp();
         if (valid) atomicAdd(&c[run], x & 0xFFFFu);
         n_runs += (uint32_t)__popc(hm);
+        n_below += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, head && (x >> 16) < base));
         __syncwarp();
     }
     for (uint32_t r = lane; r < n_runs; r += 32u) seg[s0 + r] = c[r];
-    if (lane == 0) { runs_j[j] = nz + n_runs; nz_j[j] = nz; }
+    if (lane == 0) { runs_j[j] = nz + n_runs; nz_j[j] = nz; below_j[j] = n_below; }
 }
 
-/* block per junction with many log entries: the entries' counts are summed per offset in a 65536-counter scratch of the
- * block (global memory, zero between uses) while a bitmap in shared memory remembers which offsets occur; the runs are
- * then read off the bitmap in ascending order */
-static const int FIN_BIG_BLOCKS = 148 * 2;
+/* Block per junction with many log entries: the entries' counts are summed per offset in a 65536-counter scratch of the
+ * block (global memory, zero between uses) while a two-level bitmap in shared memory remembers which offsets occur
+ * (64 summary words over 2048 words over 65536 offsets); the runs are then read off the bitmap in ascending order by
+ * the 64 threads that own a summary word each.  The cost follows the entries and the distinct offsets, not 65536. */
+static const int FIN_BIG_BLOCKS = 148 * 4;
 __global__ void __launch_bounds__(256) k_fin_big(Tables t, uint64_t L, const unsigned long long *d_count, const uint32_t *big_list,
                                                  const uint32_t *seg_off, uint32_t *seg, uint32_t *runs_j, const uint32_t *nz_j,
-                                                 uint32_t *scratch) {
+                                                 uint32_t *below_j, uint32_t *scratch) {
     __shared__ uint32_t s_bits[2048];
-    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_sum[64];
+    __shared__ uint32_t s_runs[64], s_below[64];
     uint32_t *cnt = scratch + (uint64_t)blockIdx.x * 65536u;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < 2048u; i += blockDim.x) s_bits[i] = 0u;
+    if (threadIdx.x < 64) s_sum[threadIdx.x] = 0u;
+    __syncthreads();
     const uint64_t n_big = d_count[6];
     for (uint64_t q = blockIdx.x; q < n_big; q += gridDim.x) {
         const uint32_t j = big_list[q];
         const uint32_t n = t.olog_cnt[j];
         const uint64_t s0 = seg_off[j];
-        for (uint32_t i = threadIdx.x; i < 2048u; i += blockDim.x) s_bits[i] = 0u;
-        __syncthreads();
+        const uint32_t base = t.dense ? t.obase[j] : 0u;
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
             const uint32_t x = seg[s0 + i];
             const uint32_t off = x >> 16;
-            atomicOr(&s_bits[off >> 5], 1u << (off & 31u));
+            const uint32_t bit = 1u << (off & 31u);
+            if (!(atomicOr(&s_bits[off >> 5], bit) & bit)) atomicOr(&s_sum[off >> 10], 1u << ((off >> 5) & 31u));
             atomicAdd(&cnt[off], x & 0xFFFFu);
         }
         __threadfence();
         __syncthreads();
-        /* thread i owns bitmap words [8 i, 8 i + 8) */
-        uint32_t mine = 0u;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) mine += (uint32_t)__popc(s_bits[threadIdx.x * 8 + k]);
-        uint32_t incl = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += y;
+        /* thread i < 64 owns summary word i = offsets [1024 i, 1024 i + 1024) */
+        uint32_t mine = 0u, mine_below = 0u;
+        if (threadIdx.x < 64) {
+            uint32_t words = s_sum[threadIdx.x];
+            while (words) {
+                const uint32_t wi = threadIdx.x * 32u + (uint32_t)__ffs(words) - 1u;
+                words &= words - 1u;
+                const uint32_t bits = s_bits[wi];
+                mine += (uint32_t)__popc(bits);
+                /* offsets of this word below the dense row's first */
+                const uint32_t lo = wi * 32u;
+                if (lo + 32u <= base) mine_below += (uint32_t)__popc(bits);
+                else if (lo < base) mine_below += (uint32_t)__popc(bits & ((1u << (base - lo)) - 1u));
+            }
+            s_runs[threadIdx.x] = mine;
+            s_below[threadIdx.x] = mine_below;
         }
-        if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        uint32_t pre = incl - mine, total = 0u;
-#pragma unroll
-        for (int w2 = 0; w2 < 8; ++w2) {
-            if (w2 < warp) pre += s_warp[w2];
-            total += s_warp[w2];
-        }
-        /* total <= n: the runs fit where the entries were */
-        for (int k = 0; k < 8; ++k) {
-            uint32_t bits = s_bits[threadIdx.x * 8 + k];
-            while (bits) {
-                const uint32_t bit = (uint32_t)__ffs(bits) - 1u;
-                bits &= bits - 1u;
-                const uint32_t off = ((uint32_t)threadIdx.x * 8u + (uint32_t)k) * 32u + bit;
-                seg[s0 + pre++] = __ldcg(&cnt[off]);
-                cnt[off] = 0u;
+        if (threadIdx.x < 64) {
+            uint32_t pre = 0u, total = 0u, below = 0u;
+            for (uint32_t k = 0; k < 64u; ++k) {
+                const uint32_t v = s_runs[k];
+                if (k < threadIdx.x) pre += v;
+                total += v;
+                below += s_below[k];
+            }
+            /* total <= n: the runs fit where the entries were (every entry has been read: the barrier above) */
+            uint32_t words = s_sum[threadIdx.x];
+            while (words) {
+                const uint32_t wi = threadIdx.x * 32u + (uint32_t)__ffs(words) - 1u;
+                words &= words - 1u;
+                uint32_t bits = s_bits[wi];
+                s_bits[wi] = 0u;
+                while (bits) {
+                    const uint32_t off = wi * 32u + (uint32_t)__ffs(bits) - 1u;
+                    bits &= bits - 1u;
+                    seg[s0 + pre++] = __ldcg(&cnt[off]);
+                    cnt[off] = 0u;
+                }
+            }
+            s_sum[threadIdx.x] = 0u;
+            if (threadIdx.x == 0) {
+                runs_j[j] = nz_j[j] + total;
+                below_j[j] = below;
             }
         }
-        if (threadIdx.x == 0) runs_j[j] = nz_j[j] + total;
         __syncthreads();
     }
     (void)L;
+    (void)lane;
 }
 
 /* ------------------------------------------------------------------ output rows */
@@ -456,11 +526,11 @@ struct RunsIn {
     __device__ __forceinline__ unsigned long long operator()(uint64_t i) const { return runs_r[i]; }
 };
 
-/* warp per junction, key order: its runs in ascending offset order -- dense row first (offsets < DENSE_W), then the
- * ordered runs of its log segment (offsets >= DENSE_W, or every offset when the table has no dense rows) */
+/* warp per junction, key order: its runs in ascending offset order -- the ordered runs of its log segment below the
+ * dense row's first offset, the dense row, the rest of the log runs */
 __global__ void __launch_bounds__(256) k_fin_write(Tables t, uint64_t B, uint64_t R, const uint32_t *order, unsigned long long *d_count,
-                                                   const unsigned long long *hist_off, const uint32_t *nz_j, const uint32_t *seg_off,
-                                                   const uint32_t *seg, uint32_t *hist_cnt) {
+                                                   const unsigned long long *hist_off, const uint32_t *nz_j, const uint32_t *below_j,
+                                                   const uint32_t *seg_off, const uint32_t *seg, uint32_t *hist_cnt) {
     const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const unsigned long long n_runs = hist_off[B]; /* rows beyond the junctions count zero runs */
@@ -472,7 +542,7 @@ __global__ void __launch_bounds__(256) k_fin_write(Tables t, uint64_t B, uint64_
     if (r >= d_count[0] || r >= B) return;
     const uint32_t j = order[r];
     const unsigned long long o0 = hist_off[r], o1 = hist_off[r + 1];
-    const uint32_t nz = nz_j[j];
+    const uint32_t nz = nz_j[j], below = below_j[j];
     if (t.dense && nz) {
         const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)j * DENSE_W);
         const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
@@ -486,7 +556,7 @@ __global__ void __launch_bounds__(256) k_fin_write(Tables t, uint64_t B, uint64_
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, pre, k);
             if (lane >= k) pre += y;
         }
-        uint64_t o = o0 + (pre - mine);
+        uint64_t o = o0 + below + (pre - mine);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             if (v[k] != 0) hist_cnt[o++] = v[k];
@@ -494,7 +564,7 @@ __global__ void __launch_bounds__(256) k_fin_write(Tables t, uint64_t B, uint64_
     }
     const unsigned long long n_log = (o1 - o0) - nz;
     const uint64_t s0 = seg_off[j];
-    for (unsigned long long q = lane; q < n_log; q += 32) hist_cnt[o0 + nz + q] = seg[s0 + q];
+    for (unsigned long long q = lane; q < n_log; q += 32) hist_cnt[o0 + q + (q < below ? 0u : nz)] = seg[s0 + q];
 }
 
 /* ------------------------------------------------------------------ host side */
@@ -526,7 +596,7 @@ void finalize_release(FinalizeWork &w) {
     if (w.exec) cudaGraphExecDestroy(w.exec);
     w.exec = nullptr;
     cudaFree(w.sort_key); cudaFree(w.sort_sub); cudaFree(w.tkey); cudaFree(w.order); cudaFree(w.t_order); cudaFree(w.t_rank);
-    cudaFree(w.seg_off); cudaFree(w.seg_fill); cudaFree(w.runs_j); cudaFree(w.nz_j); cudaFree(w.big_list); cudaFree(w.runs_r);
+    cudaFree(w.seg_off); cudaFree(w.seg_fill); cudaFree(w.runs_j); cudaFree(w.nz_j); cudaFree(w.below_j); cudaFree(w.big_list); cudaFree(w.runs_r);
     cudaFree(w.seg); cudaFree(w.big_scratch); cudaFree(w.scan_state); cudaFree(w.d_count);
     for (int k = 0; k < 2; ++k) {
         cudaFree(w.ss_splitters[k]); cudaFree(w.ss_bucket_cnt[k]); cudaFree(w.ss_bk[k]); cudaFree(w.ss_bs[k]); cudaFree(w.ss_bv[k]);
@@ -544,7 +614,7 @@ void finalize_release(FinalizeWork &w) {
 }
 
 static uint64_t bucket_bound(uint64_t B) {
-    uint64_t p = (B + 511) / 512;
+    uint64_t p = (B + SS_BUCKET - 1) / SS_BUCKET;
     if (p < 1) p = 1;
     return p > (uint64_t)SS_MAX_BUCKETS ? (uint64_t)SS_MAX_BUCKETS : p;
 }
@@ -566,7 +636,6 @@ static cudaError_t finalize_allocate(FinalizeWork &w, uint64_t B, uint64_t L, ui
         IPX_CU(cudaMalloc(&w.big_scratch, (size_t)FIN_BIG_BLOCKS * 65536 * sizeof(uint32_t)));
         IPX_CU(cudaMemset(w.big_scratch, 0, (size_t)FIN_BIG_BLOCKS * 65536 * sizeof(uint32_t)));
         IPX_CU(cudaFuncSetAttribute(k_ss_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SS_MAX_SAMPLE * sizeof(unsigned long long))));
-        IPX_CU(cudaFuncSetAttribute(k_ss_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_LOCAL_SMEM));
     }
     if (B != w.B || C != w.C) {
         const uint64_t cells = bucket_bound(B) * C;
@@ -578,7 +647,7 @@ static cudaError_t finalize_allocate(FinalizeWork &w, uint64_t B, uint64_t L, ui
     if (B != w.B) {
         IPX_CU(regrow(&w.sort_key, B)); IPX_CU(regrow(&w.sort_sub, B)); IPX_CU(regrow(&w.tkey, B)); IPX_CU(regrow(&w.order, B));
         IPX_CU(regrow(&w.t_order, B)); IPX_CU(regrow(&w.t_rank, B)); IPX_CU(regrow(&w.seg_off, B)); IPX_CU(regrow(&w.seg_fill, B));
-        IPX_CU(regrow(&w.runs_j, B)); IPX_CU(regrow(&w.nz_j, B)); IPX_CU(regrow(&w.big_list, B)); IPX_CU(regrow(&w.runs_r, B + 1));
+        IPX_CU(regrow(&w.runs_j, B)); IPX_CU(regrow(&w.nz_j, B)); IPX_CU(regrow(&w.below_j, B)); IPX_CU(regrow(&w.big_list, B)); IPX_CU(regrow(&w.runs_r, B + 1));
         IPX_CU(regrow(&w.scan_state, scan_state_words(B + 1)));
         DeviceTable &o = w.out;
         IPX_CU(regrow(&o.chrom, B)); IPX_CU(regrow(&o.i0, B)); IPX_CU(regrow(&o.i1, B)); IPX_CU(regrow(&o.a0, B));
@@ -598,46 +667,66 @@ static cudaError_t finalize_allocate(FinalizeWork &w, uint64_t B, uint64_t L, ui
 }
 
 /* the sequence itself, issued into `st` (under stream capture, or directly when capture is not possible) */
-static cudaError_t finalize_issue(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, FinalizeWork &w, cudaStream_t st) {
+static cudaError_t finalize_issue(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, FinalizeWork &w, cudaStream_t st,
+                                  bool trace = false) {
     const uint64_t B = w.B, L = w.L, R = w.R;
     DeviceTable &out = w.out;
+    FinTrace tr{trace, st, {}};
+    cudaStream_t s2 = trace ? st : w.s2, s3 = trace ? st : w.s3;
+    tr.mark("start");
     launch_resolve_T(t, g, st); /* creation thresholds for anything still unresolved */
     k_fin_begin<<<1, 1, 0, st>>>(t, w.d_count, B, L);
     k_fin_list<<<blocks_for(B, 256), 256, 0, st>>>(t, d_name_rank, B, w.d_count, w.sort_key, w.sort_sub, w.tkey, w.seg_off, w.seg_fill);
+    tr.mark("resolve+begin+list");
     /* three independent chains from here: key order (st), sjN ranking (s2), read-offset log (s3) */
-    IPX_CU(cudaEventRecord(w.ev_fork, st));
-    IPX_CU(cudaStreamWaitEvent(w.s2, w.ev_fork, 0));
-    IPX_CU(cudaStreamWaitEvent(w.s3, w.ev_fork, 0));
+    if (!trace) {
+        IPX_CU(cudaEventRecord(w.ev_fork, st));
+        IPX_CU(cudaStreamWaitEvent(w.s2, w.ev_fork, 0));
+        IPX_CU(cudaStreamWaitEvent(w.s3, w.ev_fork, 0));
+    }
     const unsigned long long *n_ptr = w.d_count + 4;
 
     /* st: key order -- chromosome-name rank, intron_start, intron_end */
     SampleSort ssa{w.ss_splitters[0], w.ss_bucket_cnt[0], w.ss_bk[0], w.ss_bs[0], w.ss_bv[0], w.C};
-    IPX_CU(sample_sort(w.sort_key, w.sort_sub, n_ptr, B, ssa, w.order, nullptr, w.d_count, st));
+    IPX_CU(sample_sort(w.sort_key, w.sort_sub, n_ptr, B, ssa, w.order, nullptr, w.d_count, st, &tr));
+    tr.mark("key-sort");
 
     /* s2: sjN = rank of the creating event in stream order */
     SampleSort ssb{w.ss_splitters[1], w.ss_bucket_cnt[1], w.ss_bk[1], w.ss_bs[1], w.ss_bv[1], w.C};
-    IPX_CU(sample_sort(w.tkey, nullptr, n_ptr, B, ssb, w.t_order, w.t_rank, w.d_count, w.s2));
-    IPX_CU(cudaEventRecord(w.ev_join2, w.s2));
+    IPX_CU(sample_sort(w.tkey, nullptr, n_ptr, B, ssb, w.t_order, w.t_rank, w.d_count, s2, &tr));
+    tr.mark("T-sort");
+    if (!trace) IPX_CU(cudaEventRecord(w.ev_join2, s2));
 
     /* s3: the log entries gathered per junction, ordered and run-length reduced */
-    k_fin_scatter<<<blocks_for(L, 256), 256, 0, w.s3>>>(t, B, L, w.d_count, w.seg_off, w.seg_fill, w.seg);
-    k_fin_small<<<blocks_for(B * 32, 256), 256, 0, w.s3>>>(t, B, L, w.d_count, w.seg_off, w.seg, w.runs_j, w.nz_j, w.big_list);
-    k_fin_big<<<FIN_BIG_BLOCKS, 256, 0, w.s3>>>(t, L, w.d_count, w.big_list, w.seg_off, w.seg, w.runs_j, w.nz_j, w.big_scratch);
-    IPX_CU(cudaEventRecord(w.ev_join3, w.s3));
-
-    /* join: rows in key order (motif, strand correction, sjN), then the histograms */
-    IPX_CU(cudaStreamWaitEvent(st, w.ev_join2, 0));
-    IPX_CU(cudaStreamWaitEvent(st, w.ev_join3, 0));
+    k_fin_scatter<<<blocks_for(L, 256), 256, 0, s3>>>(t, B, L, w.d_count, w.seg_off, w.seg_fill, w.seg);
+    tr.mark("log-scatter");
+    k_fin_small<<<blocks_for(B * 32, 256), 256, 0, s3>>>(t, B, L, w.d_count, w.seg_off, w.seg, w.runs_j, w.nz_j, w.below_j, w.big_list);
+    tr.mark("small");
+    k_fin_big<<<FIN_BIG_BLOCKS, 256, 0, s3>>>(t, L, w.d_count, w.big_list, w.seg_off, w.seg, w.runs_j, w.nz_j, w.below_j, w.big_scratch);
+    tr.mark("big");
+    if (!trace) {
+        IPX_CU(cudaEventRecord(w.ev_join3, s3));
+        /* join: rows in key order (motif, strand correction, sjN), then the histograms */
+        IPX_CU(cudaStreamWaitEvent(st, w.ev_join2, 0));
+        IPX_CU(cudaStreamWaitEvent(st, w.ev_join3, 0));
+    }
     k_fin_rows<<<blocks_for(B + 1, 256), 256, 0, st>>>(t, g, B, w.order, w.d_count, w.t_rank, w.runs_j, w.runs_r, out);
+    tr.mark("rows");
     IPX_CU(scan_exclusive(RunsIn{w.runs_r}, out.hist_off, B + 1, w.scan_state, st));
-    k_fin_write<<<blocks_for(B * 32, 256), 256, 0, st>>>(t, B, R, w.order, w.d_count, out.hist_off, w.nz_j, w.seg_off, w.seg, out.hist_cnt);
+    tr.mark("scan");
+    k_fin_write<<<blocks_for(B * 32, 256), 256, 0, st>>>(t, B, R, w.order, w.d_count, out.hist_off, w.nz_j, w.below_j, w.seg_off, w.seg,
+                                                        out.hist_cnt);
+    tr.mark("write");
     IPX_CU(cudaMemcpyAsync(w.h_count, w.d_count, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     w.launches_per_replay = 16;
+    tr.mark("counts");
+    tr.counts = w.h_count;
+    tr.report();
     return cudaGetLastError();
 }
 
 cudaError_t finalize_enqueue(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, FinalizeWork &w, cudaStream_t st) {
-    uint64_t B = w.B ? w.B : w.first_B, L = w.L ? w.L : w.first_L, R = w.R ? w.R : w.first_R, C = w.C ? w.C : 2048;
+    uint64_t B = w.B ? w.B : w.first_B, L = w.L ? w.L : w.first_L, R = w.R ? w.R : w.first_R, C = w.C ? w.C : 1024;
     if (w.wish_B > B) B = w.wish_B;
     if (w.wish_L > L) L = w.wish_L;
     if (w.wish_R > R) R = w.wish_R;
@@ -645,7 +734,7 @@ cudaError_t finalize_enqueue(const Tables &t, const GenomeView &g, const uint32_
     FinalizeWork::Key key{};
     key.B = B; key.L = L; key.R = R; key.C = C;
     key.tab_keys = t.keys; key.tab_rows = t.stat; key.tab_log = t.olog; key.max_j = t.max_j; key.olog_cap = t.olog_cap;
-    key.name_rank = d_name_rank; key.gseq = g.seq; key.target_seq = g.target_seq; key.dense = t.dense;
+    key.tab_base = t.obase; key.name_rank = d_name_rank; key.gseq = g.seq; key.target_seq = g.target_seq; key.dense = t.dense;
     key.n_targets = g.n_targets; key.have_genome = g.have_genome; key.skip_missing = g.skip_missing; key.filter_canon = g.filter_canon;
     key.wide = t.kl.wide; key.len_bits = t.kl.len_bits;
     if (!w.exec || !(key == w.key)) {
@@ -674,7 +763,8 @@ cudaError_t finalize_enqueue(const Tables &t, const GenomeView &g, const uint32_
         }
     }
     if (w.exec) return cudaGraphLaunch(w.exec, st);
-    return finalize_issue(t, g, d_name_rank, w, st);
+    static const bool trace = getenv("IPX_FIN_TRACE") != nullptr;
+    return finalize_issue(t, g, d_name_rank, w, st, trace);
 }
 
 bool finalize_check(FinalizeWork &w) {

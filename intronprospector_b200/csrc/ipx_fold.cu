@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(256) k_init_rows(Tables t, uint64_t first) {
         if (lane == 0) {
             reset_stat(&t.stat[j]);
             t.olog_cnt[j] = 0u;
+            t.jslot[j] = SLOT_NONE;
+            t.obase[j] = BASE_UNSET;
         }
         if (t.dense) {
             uint4 *row = reinterpret_cast<uint4 *>(t.dense + j * DENSE_W);
@@ -63,7 +65,10 @@ __global__ void __launch_bounds__(256) k_init_rows(Tables t, uint64_t first) {
     }
 }
 
+/* <<<1, N_ID_POOLS>>> */
 __global__ void k_reset_counters(Tables t) {
+    t.id_pools[threadIdx.x] = (unsigned long long)ID_BLOCK; /* nothing to hand out: the first taker fetches a block */
+    if (threadIdx.x != 0) return;
     *t.n_keys = 0ull;
     *t.n_olog = 0ull;
     *t.err_sv = EMPTY64;
@@ -79,12 +84,15 @@ __global__ void __launch_bounds__(256) k_clear_tables(Tables t) {
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t j = warp0; j < nk; j += n_warps) {
+        const uint32_t slot = t.jslot[j];
+        if (slot == SLOT_NONE) continue; /* an id no junction took: its row is in the reset state */
         if (lane == 0) {
-            const uint32_t slot = t.jslot[j];
             t.keys[slot] = EMPTY64;
             t.jid[slot] = JID_UNSET;
             reset_stat(&t.stat[j]);
             t.olog_cnt[j] = 0u;
+            t.jslot[j] = SLOT_NONE;
+            t.obase[j] = BASE_UNSET;
         }
         if (t.dense) {
             uint4 *row = reinterpret_cast<uint4 *>(t.dense + j * DENSE_W);
@@ -111,7 +119,7 @@ __global__ void k_sweep_full_slots(Tables t) {
 void launch_init_tables(const Tables &t, cudaStream_t st) {
     k_init_slots<<<148 * 8, 256, 0, st>>>(t.keys, t.jid, t.cap_mask + 1);
     k_init_rows<<<148 * 8, 256, 0, st>>>(t, 0);
-    k_reset_counters<<<1, 1, 0, st>>>(t);
+    k_reset_counters<<<1, N_ID_POOLS, 0, st>>>(t);
 }
 
 void launch_init_rows(const Tables &t, uint64_t first, cudaStream_t st) { k_init_rows<<<148 * 8, 256, 0, st>>>(t, first); }
@@ -119,12 +127,13 @@ void launch_init_rows(const Tables &t, uint64_t first, cudaStream_t st) { k_init
 void launch_clear_tables(const Tables &t, cudaStream_t st) {
     k_clear_tables<<<148 * 4, 256, 0, st>>>(t);
     k_sweep_full_slots<<<148, 256, 0, st>>>(t);
-    k_reset_counters<<<1, 1, 0, st>>>(t);
+    k_reset_counters<<<1, N_ID_POOLS, 0, st>>>(t);
 }
 
 /* Before the host grows anything: the counters that kept counting while a table was full go back to what exists,
  * and the flags of what is being repaired are lowered. */
 __global__ void k_settle_counters(Tables t) {
+    /* (every block of ids below max_j has been handed to a pool by the time one comes back short: the pools keep theirs) */
     *t.n_keys = junctions_in_use(t);
     *t.n_olog = log_entries_in_use(t);
     *t.n_unfolded = 0ull;
@@ -137,6 +146,7 @@ __global__ void k_rehash(Tables t) {
     const uint64_t nk = junctions_in_use(t);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nk; j += stride) {
+        if (t.jslot[j] == SLOT_NONE) continue; /* an id no junction took */
         const unsigned long long key = t.jkey[j];
         uint64_t h = junction_hash(key, t.jtid[j]) & t.cap_mask;
         for (;;) {
@@ -190,6 +200,7 @@ struct FoldCache {
     int32_t tid[FOLD_WAYS];
     uint32_t cnt[3][FOLD_WAYS];
     uint32_t a0[FOLD_WAYS], a1[FOLD_WAYS];
+    uint32_t base[FOLD_WAYS]; /* first offset of the junction's dense row */
     unsigned long long stage[LOG_STAGE];
 };
 
@@ -214,6 +225,9 @@ __device__ __forceinline__ void fold_write_back(const Tables &t, FoldCache &c, i
 template <int MODE>
 __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables t, Event *ev, TileInfo *tile_info, uint64_t n_tiles) {
     __shared__ FoldCache s_cache[FOLD_WARPS];
+    __shared__ IdPool s_pool;
+    if (threadIdx.x == 0) id_pool_load(t, &s_pool);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     FoldCache &c = s_cache[threadIdx.x >> 5];
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -244,7 +258,7 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
             const bool is_leader = valid && lane == leader;
             const int way = (int)((junction_hash(e.key, e.tid) >> 40) & (FOLD_WAYS - 1));
             /* ---- the group's junction: from the cache, else from the table ---- */
-            uint32_t jid = JID_NONE;
+            uint32_t jid = JID_NONE, dbase = 0u;
             unsigned long long T = EMPTY64;
             bool cached = false;
             const unsigned leaders = __ballot_sync(0xFFFFFFFFu, is_leader);
@@ -258,6 +272,7 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
                     if (ck == e.key && (!t.kl.wide || c.tid[way] == e.tid)) {
                         hit = cached = true;
                         jid = c.jid[way];
+                        dbase = c.base[way];
                         if (MODE == MODE_PASS2) T = c.first[0][way];
                     } else if (ck != EMPTY64) {
                         fold_write_back<MODE>(t, c, way);
@@ -265,12 +280,14 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
                     }
                 }
                 if (!hit) {
-                    jid = junction_probe<MODE != MODE_PASS2>(t, e.key, e.tid);
+                    jid = junction_probe<MODE != MODE_PASS2>(t, &s_pool, e.key, e.tid);
                     if (MODE == MODE_PASS2 && jid != JID_NONE) T = *((volatile unsigned long long *)&t.stat[jid].T);
+                    if (MODE != MODE_PASS1 && jid != JID_NONE) dbase = dense_base(t, jid, e.off_cat & 0xFFFFu);
                     if (owner && jid != JID_NONE) {
                         c.key[way] = e.key;
                         c.tid[way] = e.tid;
                         c.jid[way] = jid;
+                        c.base[way] = dbase;
                         c.cnt[0][way] = c.cnt[1][way] = c.cnt[2][way] = 0u;
                         c.a0[way] = 0xFFFFFFFFu;
                         c.a1[way] = 0u;
@@ -282,6 +299,7 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
             }
             __syncwarp();
             jid = __shfl_sync(0xFFFFFFFFu, jid, leader);
+            dbase = __shfl_sync(0xFFFFFFFFu, dbase, leader);
             cached = __shfl_sync(0xFFFFFFFFu, (int)cached, leader) != 0;
             const int gway = __shfl_sync(0xFFFFFFFFu, way, leader);
             const bool found = valid && jid != JID_NONE;
@@ -320,7 +338,7 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
                     }
                 }
                 const uint32_t off = e.off_cat & 0xFFFFu;
-                const bool in_row = t.dense != nullptr && off < DENSE_W;
+                const bool in_row = in_dense_row(t, dbase, off);
                 if (counted) {
                     if (cached) {
                         if (e.a0 < c.a0[gway]) atomicMin(&c.a0[gway], e.a0);
@@ -329,7 +347,7 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
                         stat_anchor(s, e.a0, e.a1);
                     }
                     /* Junction::count_read's push_back (junctions.hh:163-167), run-length form */
-                    if (in_row) atomicAdd(&t.dense[(uint64_t)jid * DENSE_W + off], 1u);
+                    if (in_row) atomicAdd(&t.dense[(uint64_t)jid * DENSE_W + (off - dbase)], 1u);
                 }
                 log_append(t, log, counted && !in_row, olog_entry(jid, off, 1u));
             }
@@ -350,6 +368,8 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
         if (c.key[w] != EMPTY64) fold_write_back<MODE>(t, c, w);
     if (MODE != MODE_PASS1) log_flush(t, log);
     if (lane == 0 && unfolded) atomicAdd(t.n_unfolded, unfolded);
+    __syncthreads();
+    if (threadIdx.x == 0) id_pool_store(t, &s_pool);
 }
 
 void launch_fold(int mode, const Tables &t, Event *ev, TileInfo *tile_info, uint64_t n_tiles, int sm_count, cudaStream_t st) {

@@ -40,6 +40,22 @@ static const uint32_t JID_NONE = 0xFFFFFFFDu;  /* probe result: absent (lookup) 
  * go to the read-offset log, as does everything when the rows are disabled. */
 static const uint32_t DENSE_W = 256;
 static const uint32_t LOG_STAGE = 128; /* log entries a warp stages in shared memory between reservations */
+/* Junction ids are handed out in blocks of ID_BLOCK to pools, one per thread block of an inserting kernel (kept in
+ * global memory between launches): taking an id is a shared-memory atomic, and the table's one counter sees a block
+ * per ID_BLOCK junctions instead of every insertion (a single address serves ~0.5 G atomics/s: at one per junction it
+ * was the bottleneck of a cold fold).  Ids of a pool's unfinished block are "holes": rows nobody ever wrote, which
+ * everything that walks the rows recognises by their reset state (T == EMPTY64, jslot == SLOT_NONE). */
+static const uint32_t ID_BLOCK = 64;
+static const uint32_t N_ID_POOLS = 1024; /* inserting kernels run at most this many thread blocks */
+static const uint32_t SLOT_NONE = 0xFFFFFFFFu;
+static const uint32_t BASE_UNSET = 0xFFFFFFFFu;
+/* The dense row of a junction counts the offsets [base, base + DENSE_W): base is fixed by the first read that is
+ * counted into the junction.  An offset below DENSE_W gives base 0 (first junctions of short reads: offset = length of
+ * the read's first aligned run); a larger one -- second junctions, whose offsets include the first intron -- centres
+ * the window on itself: the reads through one pair of junctions differ in their start by less than a read length, so
+ * their offsets form a cluster narrower than the window, and whichever of them comes first (thread blocks take tiles
+ * of the stream concurrently) the cluster fits around it. */
+static const uint32_t DENSE_LEAD = DENSE_W / 2;
 static const int SV_ORD_BITS = 20;
 static const int SV_SEQ_SHIFT = 28;
 
@@ -140,8 +156,10 @@ struct Tables {
     int32_t *jtid;
     uint32_t *jslot;          /* hash slot of the junction's key (for clear) */
     JStat *stat;
-    uint32_t *dense;          /* [max_j][DENSE_W] read counts for offsets < DENSE_W, or NULL when disabled */
+    uint32_t *dense;          /* [max_j][DENSE_W] read counts for offsets obase + [0, DENSE_W), or NULL when disabled */
+    uint32_t *obase;          /* [max_j] first offset of the junction's dense row, BASE_UNSET until a read is counted */
     uint32_t *olog_cnt;       /* entries of the read-offset log that name the junction */
+    unsigned long long *id_pools; /* [N_ID_POOLS] first id of the pool's block << 32 | ids taken from it */
     uint64_t max_j;
     unsigned long long *olog; /* [olog_cap] junction id << 32 | read offset << 16 | count */
     uint64_t olog_cap;
@@ -172,12 +190,46 @@ __device__ __forceinline__ uint64_t log_entries_in_use(const Tables &t) {
     return n < t.olog_cap ? n : t.olog_cap;
 }
 
+/* A thread block's pool of junction ids in shared memory (loaded from / stored back to t.id_pools by the kernel). */
+struct IdPool {
+    unsigned long long word; /* first id of the block << 32 | ids taken (>= ID_BLOCK: used up) */
+    uint32_t lock;
+};
+
+__device__ __forceinline__ void id_pool_load(const Tables &t, IdPool *p) {
+    p->word = t.id_pools[blockIdx.x % N_ID_POOLS];
+    p->lock = 0u;
+}
+__device__ __forceinline__ void id_pool_store(const Tables &t, const IdPool *p) {
+    t.id_pools[blockIdx.x % N_ID_POOLS] = *((volatile const unsigned long long *)&p->word);
+}
+
+/* the next junction id, or an id >= max_j when no row is left */
+__device__ __forceinline__ uint32_t id_pool_take(const Tables &t, IdPool *p) {
+    for (;;) {
+        const unsigned long long old = atomicAdd(&p->word, 1ull);
+        const uint32_t used = (uint32_t)old;
+        if (used < ID_BLOCK) return (uint32_t)(old >> 32) + used;
+        if (atomicCAS(&p->lock, 0u, 1u) == 0u) {
+            /* this thread refills the pool unless somebody did in the meantime */
+            bool full = false;
+            if ((uint32_t)(*((volatile unsigned long long *)&p->word)) >= ID_BLOCK) {
+                const unsigned long long nb = atomicAdd(t.n_keys, (unsigned long long)ID_BLOCK);
+                if (nb + ID_BLOCK <= t.max_j) atomicExch(&p->word, nb << 32); else full = true;
+            }
+            __threadfence_block();
+            atomicExch(&p->lock, 0u);
+            if (full) return (uint32_t)t.max_j; /* the rows are used up (max_j < 2^31) */
+        }
+    }
+}
+
 /* Find the junction id of (key, tid); INSERT: claim a slot and a junction row when absent.  Returns JID_NONE when the
  * key is absent (lookup) or when no slot / row is left (insert: the overflow flag is raised, the caller keeps the event).
  * The junction rows of ids never handed out hold the reset values (init / clear), so an inserter has nothing to
  * initialise but the identity. */
 template <bool INSERT>
-__device__ __forceinline__ uint32_t junction_probe(const Tables &t, unsigned long long key, int32_t tid) {
+__device__ __forceinline__ uint32_t junction_probe(const Tables &t, IdPool *pool, unsigned long long key, int32_t tid) {
     uint64_t h = junction_hash(key, tid) & t.cap_mask;
     for (uint32_t probe = 0; probe < MAX_PROBE; ++probe) {
         unsigned long long k = *((volatile unsigned long long *)&t.keys[h]);
@@ -185,7 +237,7 @@ __device__ __forceinline__ uint32_t junction_probe(const Tables &t, unsigned lon
             if (!INSERT) return JID_NONE;
             k = atomicCAS(&t.keys[h], EMPTY64, key);
             if (k == EMPTY64) {
-                const unsigned long long j = atomicAdd(t.n_keys, 1ull);
+                const uint32_t j = id_pool_take(t, pool);
                 if (j >= t.max_j) {
                     /* no row left: the slot stays claimed (it is re-used by the rehash that follows the growth) */
                     *((volatile uint32_t *)&t.jid[h]) = JID_FULL;
@@ -195,9 +247,12 @@ __device__ __forceinline__ uint32_t junction_probe(const Tables &t, unsigned lon
                 t.jkey[j] = key;
                 t.jtid[j] = tid;
                 t.jslot[j] = (uint32_t)h;
-                __threadfence(); /* the identity is visible before the id is */
-                *((volatile uint32_t *)&t.jid[h]) = (uint32_t)j;
-                return (uint32_t)j;
+                /* Whoever meets the id reads jtid in the wide layout only: there the identity must be visible before
+                 * the id is.  (jkey / jslot are read by later kernels; the record and the offset row are already in
+                 * their reset state.) */
+                if (t.kl.wide) __threadfence();
+                *((volatile uint32_t *)&t.jid[h]) = j;
+                return j;
             }
         }
         if (k == key) {
@@ -215,6 +270,21 @@ __device__ __forceinline__ uint32_t junction_probe(const Tables &t, unsigned lon
     }
     if (INSERT) atomicOr(t.overflow, OVF_TABLE);
     return JID_NONE;
+}
+
+/* first offset of junction j's dense row: set by whoever asks first (every asker proposes the window that suits the
+ * offset in its hand), the same for everybody afterwards */
+__device__ __forceinline__ uint32_t dense_base(const Tables &t, uint32_t j, uint32_t offset) {
+    uint32_t b = *((volatile uint32_t *)&t.obase[j]);
+    if (b == BASE_UNSET) {
+        const uint32_t mine = offset < DENSE_W ? 0u : offset - DENSE_LEAD;
+        b = atomicCAS(&t.obase[j], BASE_UNSET, mine);
+        if (b == BASE_UNSET) b = mine;
+    }
+    return b;
+}
+__device__ __forceinline__ bool in_dense_row(const Tables &t, uint32_t base, uint32_t offset) {
+    return t.dense != nullptr && offset >= base && offset - base < DENSE_W;
 }
 
 /* Per-warp writer of the read-offset log: entries are staged in shared memory (LOG_STAGE of them) and written out

@@ -692,7 +692,12 @@ extern "C" int ipx_synth_write_genome(const ipx_synth_data *d, const char *fasta
     if (!fai) { fclose(fa); return -1; }
     int64_t off = 0;
     const int W = 60;
-    for (size_t c = 0; c < d->contig_names.size(); c++) {
+    /* the contigs' text is made by a pool of threads (a few at a time: each holds its sequence twice), written in order */
+    const size_t n_contigs = d->contig_names.size();
+    size_t wave = std::thread::hardware_concurrency();
+    if (wave < 1) wave = 1;
+    if (wave > 8) wave = 8;
+    auto make_text = [&](size_t c, std::string &buf) {
         const int64_t len = (int64_t)d->contig_len[c];
         std::string s((size_t)len, 'A');
         for (int64_t p = 0; p < len; p++) s[p] = bg_base(d->spec.model_seed, (int)c, p);
@@ -728,18 +733,29 @@ extern "C" int ipx_synth_write_genome(const ipx_synth_data *d, const char *fasta
             const bool ns = rng.below(10) == 0;
             for (int64_t q = p; q < std::min(len, p + l); q++) s[q] = ns ? 'N' : (char)tolower(s[q]);
         }
-        int nl = fprintf(fa, ">%s\n", d->contig_names[c].c_str());
-        off += nl;
-        fprintf(fai, "%s\t%lld\t%lld\t%d\t%d\n", d->contig_names[c].c_str(), (long long)len, (long long)off, W, W + 1);
-        std::string buf;
+        buf.clear();
         buf.reserve((size_t)(len + len / W + 2));
         for (int64_t p = 0; p < len; p += W) {
             buf.append(s, (size_t)p, (size_t)std::min<int64_t>(W, len - p));
             buf.push_back('\n');
         }
-        fwrite(buf.data(), 1, buf.size(), fa);
-        off += (int64_t)buf.size();
+    };
+    bool ok = true;
+    for (size_t c0 = 0; c0 < n_contigs && ok; c0 += wave) {
+        const size_t c1 = std::min(n_contigs, c0 + wave);
+        std::vector<std::string> text(c1 - c0);
+        std::vector<std::thread> pool;
+        for (size_t c = c0; c < c1; c++) pool.emplace_back([&, c]() { make_text(c, text[c - c0]); });
+        for (auto &th : pool) th.join();
+        for (size_t c = c0; c < c1 && ok; c++) {
+            const int nl = fprintf(fa, ">%s\n", d->contig_names[c].c_str());
+            off += nl;
+            fprintf(fai, "%s\t%lld\t%lld\t%d\t%d\n", d->contig_names[c].c_str(), (long long)d->contig_len[c], (long long)off, W, W + 1);
+            ok = fwrite(text[c - c0].data(), 1, text[c - c0].size(), fa) == text[c - c0].size();
+            off += (int64_t)text[c - c0].size();
+        }
     }
+    if (!ok) { fclose(fai); fclose(fa); return -1; }
     fclose(fai);
     return fclose(fa) == 0 ? 0 : -1;
 }

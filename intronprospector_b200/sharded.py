@@ -59,6 +59,7 @@ def balanced_splitters_dist(eng, names, device, group=None, max_keys=1 << 14):
     import torch.distributed as dist
     world = dist.get_world_size(group)
     tid, i0 = eng.sample_keys(stride=1, max_keys=1 << 22)
+    tid, i0 = tid[tid >= 0], i0[tid >= 0]  # (ids no junction took come back as -1)
     if tid.size > max_keys:
         step = (tid.size + max_keys - 1) // max_keys
         tid, i0 = tid[::step], i0[::step]

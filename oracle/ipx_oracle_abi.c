@@ -89,3 +89,7 @@ int ipx_format_tsv_header(ipx_text *out) { return ipxo_format_tsv_header(out); }
 void ipx_text_free(ipx_text *t) { ipxo_text_free(t); }
 int ipx_get_timings(ipx_handle *h, ipx_timings *out) { (void)h; memset(out, 0, sizeof(*out)); return IPX_OK; }
 int ipx_reset_timings(ipx_handle *h) { (void)h; return IPX_OK; }
+/* pinned batches of the product's CLI: plain memory and nothing to wait for here */
+void *ipx_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void ipx_host_free(void *p) { free(p); }
+int ipx_sync_uploads(ipx_handle *h, uint32_t keep_in_flight) { (void)h; (void)keep_in_flight; return IPX_OK; }

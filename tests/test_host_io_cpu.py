@@ -197,3 +197,144 @@ def test_reference_inputs_as_bam_through_both_packers(built, tmp_path):
                 assert runs[tag] == runs["ref"], (name, extra, tag)
             checked += 1
     assert checked >= 16
+
+
+def _read_columns(path, pipeline, threads=3, max_records=2_000_000, max_cigar=8_000_000):
+    """every record of a BAM file as columns: through the BAM pipeline or record by record"""
+    import ctypes as C
+    import numpy as np
+    io = _native.load_io_library()
+    cols = {"tid": np.empty(max_records, np.int32), "pos": np.empty(max_records, np.int32), "flag": np.empty(max_records, np.uint16),
+            "nh_class": np.empty(max_records, np.uint8), "xs": np.empty(max_records, np.uint8),
+            "cigar_off": np.empty(max_records + 1, np.uint32), "cigar": np.empty(max_cigar, np.uint32)}
+    ptrs = [cols[k].ctypes.data for k in ("tid", "pos", "flag", "nh_class", "xs", "cigar_off", "cigar")]
+    nc = C.c_uint64()
+    if pipeline:
+        n = io.ipxio_pipeline_read(path.encode(), threads, max_records, max_cigar, *ptrs, C.byref(nc))
+    else:
+        r = C.c_void_p()
+        assert io.ipxio_open(path.encode(), C.byref(r)) == 0
+        n = io.ipxio_read_batch(r, max_records, max_cigar, *ptrs, C.byref(nc))
+        io.ipxio_close(r)
+    if n < 0:
+        return n, None
+    out = {k: cols[k][:n].copy() for k in ("tid", "pos", "flag", "nh_class", "xs")}
+    out["cigar_off"] = cols["cigar_off"][:n + 1].copy()
+    out["cigar"] = cols["cigar"][:nc.value].copy()
+    return n, out
+
+
+def _same_columns(a, b):
+    import numpy as np
+    for k in ("tid", "pos", "flag", "cigar_off", "cigar"):
+        assert np.array_equal(a[k], b[k]), k
+    # the pipeline looks at the tags of reads with an N operation only (nothing else on the path reads them)
+    off = a["cigar_off"].astype(np.int64)
+    has_n = np.zeros(len(a["tid"]), bool)
+    is_n = (a["cigar"] & 15) == 3
+    idx = np.flatnonzero(is_n)
+    has_n[np.searchsorted(off, idx, side="right") - 1] = True
+    for k in ("nh_class", "xs"):
+        assert np.array_equal(a[k][has_n], b[k][has_n]), k
+
+
+@pytest.mark.parametrize("kind", ["short", "long"])
+def test_bam_pipeline_packs_what_the_record_reader_reads(built, tmp_path, kind):
+    """The multi-threaded BAM pipeline (chunks of BGZF blocks inflated and packed in parallel, records that straddle
+    chunks gathered by the framer) against sam_read1 + the bam1_t packer: aligner-style records in BGZF blocks, and the
+    same stream uncompressed; 1, 3 and 8 threads."""
+    from intronprospector_b200.synth import LONG
+    syn = Synth(6_000 if kind == "long" else 150_000, kind=LONG if kind == "long" else SHORT_UNSTRANDED, genome_len=50_000_000,
+                n_genes=400, n_contigs=4)
+    full, raw = str(tmp_path / "full.bam"), str(tmp_path / "raw.bam")
+    syn.write_full_bam(full, threads=2, level=1)
+    syn.write_raw_bam(raw)
+    n_want = syn.n
+    syn.close()
+    for path in (full, raw):
+        n0, want = _read_columns(path, pipeline=False)
+        assert n0 == n_want
+        for threads in (1, 3, 8):
+            n1, got = _read_columns(path, pipeline=True, threads=threads)
+            assert n1 == n_want
+            _same_columns(want, got)
+
+
+def test_bam_pipeline_reports_damage_after_the_records_before_it(built, tmp_path):
+    """a file cut in the middle of a BGZF block, in the middle of a record, and one with a corrupted block: the
+    pipeline gives up where the record reader gives up"""
+    syn = Synth(120_000, kind=SHORT_UNSTRANDED, genome_len=50_000_000, n_genes=400, n_contigs=4)
+    full, raw = str(tmp_path / "full.bam"), str(tmp_path / "raw.bam")
+    syn.write_full_bam(full, threads=2, level=1)
+    syn.write_raw_bam(raw)
+    syn.close()
+    data, rawdata = open(full, "rb").read(), open(raw, "rb").read()
+    cut1, cut2, bad = str(tmp_path / "cut1.bam"), str(tmp_path / "cut2.bam"), str(tmp_path / "bad.bam")
+    open(cut1, "wb").write(data[:len(data) * 2 // 3])
+    open(cut2, "wb").write(rawdata[:len(rawdata) * 2 // 3 + 7])
+    spoiled = bytearray(data)
+    for i in range(len(data) // 2, len(data) // 2 + 64):
+        spoiled[i] ^= 0x5A
+    open(bad, "wb").write(bytes(spoiled))
+    for path in (cut1, cut2, bad):
+        n0, _ = _read_columns(path, pipeline=False)
+        n1, _ = _read_columns(path, pipeline=True)
+        assert n0 == -1 and n1 == -1, path
+
+
+def test_command_line_tool_through_the_pipeline_and_record_by_record(built, tmp_path):
+    """the tool's two ways of reading a BAM file give the same calls: sorted (per-target selection on runs of equal
+    target index), --unsorted, two files, a file whose targets come out of order (same error text, same partial output)"""
+    import os
+    import subprocess
+    syn = Synth(90_000, kind=SHORT_UNSTRANDED, genome_len=50_000_000, n_genes=400, n_contigs=5)
+    bam = str(tmp_path / "in.bam")
+    syn.write_full_bam(bam, threads=2, level=1)
+    cols = syn.columns()
+    # the same records with the third and fourth target swapped in the stream: "not coordinate sorted"
+    import numpy as np
+    tid = cols["tid"]
+    order = np.concatenate([np.flatnonzero(tid == t) for t in (0, 1, 3, 2, 4)])
+    syn.close()
+    shuffled = str(tmp_path / "shuffled.bam")
+    _write_raw_bam_from_columns(shuffled, ["chr%d" % (i + 1) for i in range(5)], cols, order)
+
+    def run(args, env):
+        out = {k: str(tmp_path / ("o." + k)) for k in ("tsv", "bed")}
+        e = dict(os.environ)
+        e.update(env)
+        proc = subprocess.run([helpers.ORACLE_EXTRACT, "--intron-calls=" + out["tsv"], "--junction-bed=" + out["bed"]] + args,
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+        return proc.returncode, proc.stderr, open(out["tsv"], "rb").read(), open(out["bed"], "rb").read()
+
+    for args in ([bam], ["--unsorted", bam], [bam, bam], [shuffled], ["-u", shuffled]):
+        fast = run(args, {})
+        slow = run(args, {"IPX_NO_PIPELINE": "1"})
+        ref = subprocess.run([helpers.REF_EXTRACT, "--intron-calls=" + str(tmp_path / "r.tsv"), "--junction-bed=" + str(tmp_path / "r.bed")] + args,
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert fast == slow, args
+        assert fast[0] == ref.returncode and fast[1] == ref.stderr, args
+        assert fast[2] == open(str(tmp_path / "r.tsv"), "rb").read() and fast[3] == open(str(tmp_path / "r.bed"), "rb").read(), args
+    assert run([shuffled], {})[0] != 0
+
+
+def _write_raw_bam_from_columns(path, names, cols, order):
+    """uncompressed BAM with the records of `cols` in the given order (test fixture)"""
+    import struct
+    out = bytearray(b"BAM\x01")
+    text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:100000000\n" % n for n in names)
+    out += struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(names))
+    for n in names:
+        out += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", 100000000)
+    off = cols["cigar_off"]
+    for r in order:
+        cig = cols["cigar"][int(off[r]):int(off[r + 1])]
+        aux = b""
+        if cols["nh_class"][r]:
+            aux += b"NHC" + bytes([1 if cols["nh_class"][r] == 1 else 3])
+        if cols["xs"][r]:
+            aux += b"XSA" + bytes([int(cols["xs"][r])])
+        body = struct.pack("<iiIIiiii", int(cols["tid"][r]), int(cols["pos"][r]), (4680 << 16) | (255 << 8) | 2,
+                           (int(cols["flag"][r]) << 16) | len(cig), 0, -1, -1, 0) + b"r\0" + cig.astype("<u4").tobytes() + aux
+        out += struct.pack("<i", len(body)) + body
+    open(path, "wb").write(bytes(out))
