@@ -389,7 +389,7 @@ def merge_workload(tmpdir, n_samples=64, n_universe=400_000):
     t0 = time.perf_counter()
     paths, _ = merge_synth.write_tables(tmpdir, n_samples, n_universe, n_contigs=25)
     gen_s = time.perf_counter() - t0
-    ref = Background(REF_MERGE, os.path.join(tmpdir, "ref_m"), paths)  # ~30 s on one core: collected at the very end
+    ref = Background(REF_MERGE, os.path.join(tmpdir, "merge_ref"), paths)  # ~30 s on one core: collected at the very end
     io = _native.load_io_library()
     arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
     calls = C.c_void_p()
@@ -417,7 +417,7 @@ def merge_workload(tmpdir, n_samples=64, n_universe=400_000):
     eng.close()
     fold_ms = tm["merge_ms"] / steps
     alg = 42.0 * n_rows + 48.0 * nj
-    t_cli, got, got_err = run_tool(GPU_MERGE, os.path.join(tmpdir, "gpu_m"), paths)
+    t_cli, got, got_err = run_tool(GPU_MERGE, os.path.join(tmpdir, "merge_gpu"), paths)
     line = {"workload": "intronProspectorMerge of %d per-sample tables (BASELINE configs[4]), one GPU" % n_samples, "tables": n_samples,
             "rows": n_rows, "junctions": int(nj), "generate_s": gen_s, "tsv_parse_s": parse_s, "call_ms_host_rows_in_table_out": call_ms,
             "value": n_rows / (call_ms / 1e3), "unit": "rows/s", "device_fold_ms": fold_ms, "tool_wall_s": t_cli,
@@ -437,7 +437,10 @@ def cli_end_to_end(tmpdir, n_rec):
     syn.close()
     gen_s = time.perf_counter() - t0
     size = os.path.getsize(bam)
-    t_ref, want, _ = run_tool(REF_BIN, os.path.join(tmpdir, "ref_cli"), [bam])
+    # the reference binary reads through this repo's htslib stand-in, whose BGZF reader would inflate on several threads:
+    # one thread, as htslib does unless asked otherwise (the reference never asks)
+    one_thread = dict(os.environ, IPX_DECODE_THREADS="1")
+    t_ref, want, _ = run_tool(REF_BIN, os.path.join(tmpdir, "ref_cli"), [bam], env=one_thread)
     t_gpu, got, _ = run_tool(GPU_BIN, os.path.join(tmpdir, "gpu_cli"), [bam])  # first run: includes CUDA context + table set-up
     t_gpu2, got2, _ = run_tool(GPU_BIN, os.path.join(tmpdir, "gpu_cli"), [bam])
     res = compare_outputs(got, want)
@@ -639,9 +642,12 @@ def main():
             part["cigar_off"] = host["cigar_off"][:sample + 1]
             part["cigar"] = host["cigar"][:cut]
             pc = _native.Engine.compact_columns({k: v.numpy() for k, v in part.items()})
-            eng.clear()
-            eng.push_compact(pc)
-            t = eng.flush()
+            eng.close()
+            eng = None
+            pe = _native.Engine(device=local)  # a fresh handle: sjN numbering continues across the flushes of one
+            pe.set_targets(names)
+            pe.push_compact(pc)
+            t = pe.flush()
             got = {"introns.tsv": t.tsv_header() + t.text_by_target(_native.FMT_INTRON_TSV, 1.0),
                    "juncs.bed": t.text_by_target(_native.FMT_JUNCTION_BED, 1.0),
                    "introns.bed": t.text_by_target(_native.FMT_INTRON_BED9, 1.0)}
@@ -649,11 +655,10 @@ def main():
             parity.update({"records": sample, "junctions": int(t.n), "how": "ipx_push_batch_compact + ipx_flush + ipx_format vs the files "
                            "the reference binary wrote for the same records (-c -j -n, -C 1.0)"})
             t.close()
+            pe.close()
             ok = ok and parity["identical"]
             log("parity on %d records: %s" % (sample, parity["identical"]))
             os.unlink(sample_bam)
-            eng.close()
-            eng = None
             del host
             # the merge's reference run takes ~30 s on one core: start it first, collect it last
             merge_line, merge_ref, merge_got, merge_err = merge_workload(tmpdir)

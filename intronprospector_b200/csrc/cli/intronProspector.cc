@@ -7,6 +7,7 @@
  * writing the formatted text.  It contains no junction arithmetic.
  */
 #include <getopt.h>
+#include <time.h>
 #include <algorithm>
 #include <map>
 #include <memory>
@@ -359,6 +360,24 @@ class Annotator {
     }
 };
 
+/* IPX_TRACE=1: wall-clock phases of the run on stderr */
+struct PhaseTrace {
+    bool on = getenv("IPX_TRACE") != NULL;
+    double t0 = now();
+    static double now() {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + ts.tv_nsec * 1e-9;
+    }
+    void mark(const char *what) {
+        if (!on) return;
+        const double t = now();
+        fprintf(stderr, "[ipx cli] %-32s %8.3f s\n", what, t - t0);
+        t0 = t;
+    }
+};
+static PhaseTrace g_trace;
+
 /* One batch of packed records in pinned host memory (ipx_batch_compact: 10 bytes per record + 4 per CIGAR word).
  * Two of them take turns: while the copy of one to the device is in flight, the other is being filled. */
 struct PinnedBatch {
@@ -607,8 +626,10 @@ class Driver {
     }
     ipx_table *flush() {
         push();
+        g_trace.mark("records read and pushed");
         ipx_table *t = nullptr;
         check_ipx(h_, ipx_flush(h_, &t));
+        g_trace.mark("table flushed");
         /* get_splice_sites' warning (junctions_extractor.cc:411-415) */
         for (uint64_t i = 0; i < t->n_missing_targets; i++)
             cerr << "Warning: genomic sequence not found for " << targets_[t->missing_targets[i]]
@@ -848,8 +869,10 @@ static void extract_whole_files(Driver &drv, const Options &opts, Outputs &out, 
 static void extract_junctions(const Options &opts) {
     ipx::LoadedGenome genome;
     if (opts.genome_fa.size() > 0) ipx::load_genome(opts.genome_fa, genome);
+    g_trace.mark("genome loaded");
     Annotator ann(opts);
     Driver drv(opts);
+    g_trace.mark("device + pinned batches ready");
     if (opts.genome_fa.size() > 0) drv.set_genome(genome);
     Outputs out(opts);
     if (opts.bam_files.size() > 1 || opts.unsorted) {
@@ -857,6 +880,7 @@ static void extract_junctions(const Options &opts) {
     } else {
         extract_by_target(drv, opts, out, ann);
     }
+    g_trace.mark("outputs written");
 }
 
 int main(int argc, char *argv[]) {

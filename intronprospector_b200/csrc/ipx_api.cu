@@ -332,16 +332,15 @@ int alloc_rows(ipx_handle *h, Tables &t, uint64_t max_j, bool dense) {
     CU(h, cudaMalloc(&t.jslot, max_j * sizeof(uint32_t)));
     CU(h, cudaMalloc(&t.stat, max_j * sizeof(JStat)));
     CU(h, cudaMalloc(&t.olog_cnt, max_j * sizeof(uint32_t)));
-    CU(h, cudaMalloc(&t.obase, max_j * sizeof(uint32_t)));
     t.dense = nullptr;
-    /* dense offset rows: 1 KB per junction */
-    if (dense) CU(h, cudaMalloc(&t.dense, max_j * DENSE_W * sizeof(uint32_t)));
+    /* dense offset rows: DENSE_ROWS x 1 KB per junction */
+    if (dense) CU(h, cudaMalloc(&t.dense, max_j * DENSE_ROWS * DENSE_W * sizeof(uint32_t)));
     return IPX_OK;
 }
 
 void free_rows(Tables &t) {
-    cudaFree(t.jkey); cudaFree(t.jtid); cudaFree(t.jslot); cudaFree(t.stat); cudaFree(t.olog_cnt); cudaFree(t.obase); cudaFree(t.dense);
-    t.jkey = nullptr; t.jtid = nullptr; t.jslot = nullptr; t.stat = nullptr; t.olog_cnt = nullptr; t.obase = nullptr; t.dense = nullptr;
+    cudaFree(t.jkey); cudaFree(t.jtid); cudaFree(t.jslot); cudaFree(t.stat); cudaFree(t.olog_cnt); cudaFree(t.dense);
+    t.jkey = nullptr; t.jtid = nullptr; t.jslot = nullptr; t.stat = nullptr; t.olog_cnt = nullptr; t.dense = nullptr;
 }
 
 int alloc_tables(ipx_handle *h) {
@@ -354,9 +353,9 @@ int alloc_tables(ipx_handle *h) {
     int rc = alloc_counters(h);
     if (rc) return rc;
     Tables &t = h->tab;
-    CU(h, cudaMalloc(&t.keys, cap * sizeof(unsigned long long)));
-    CU(h, cudaMalloc(&t.jid, cap * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&t.slots, cap * sizeof(Slot)));
     t.cap_mask = cap - 1;
+    t.extra_rows = 1;
     rc = alloc_rows(h, t, cap / 2, !getenv("IPX_NO_DENSE"));
     if (rc) return rc;
     CU(h, cudaMalloc(&t.olog, hcap * sizeof(unsigned long long)));
@@ -383,8 +382,7 @@ int grow_rows(ipx_handle *h, uint64_t in_use) {
     CU(h, cudaMemcpyAsync(t.jslot, old.jslot, in_use * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     CU(h, cudaMemcpyAsync(t.stat, old.stat, in_use * sizeof(JStat), cudaMemcpyDeviceToDevice, st));
     CU(h, cudaMemcpyAsync(t.olog_cnt, old.olog_cnt, in_use * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-    CU(h, cudaMemcpyAsync(t.obase, old.obase, in_use * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-    if (t.dense) CU(h, cudaMemcpyAsync(t.dense, old.dense, in_use * DENSE_W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    if (t.dense) CU(h, cudaMemcpyAsync(t.dense, old.dense, in_use * DENSE_ROWS * DENSE_W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     launch_init_rows(t, in_use, st);
     CU(h, cudaStreamSynchronize(st));
     free_rows(old);
@@ -396,17 +394,14 @@ int rebuild_slots(ipx_handle *h, bool twice) {
     Tables &t = h->tab;
     const uint64_t cap = (t.cap_mask + 1) * (twice ? 2 : 1);
     if (cap > (1ull << 32)) return fail(h, IPX_ERR_CAPACITY, "junction hash table beyond 2^32 slots");
-    if (twice) {
-        cudaFree(t.keys); cudaFree(t.jid);
-        t.keys = nullptr; t.jid = nullptr;
-        CU(h, cudaMalloc(&t.keys, cap * sizeof(unsigned long long)));
-        CU(h, cudaMalloc(&t.jid, cap * sizeof(uint32_t)));
-        t.cap_mask = cap - 1;
-    }
-    CU(h, cudaMemsetAsync(t.keys, 0xFF, cap * sizeof(unsigned long long), h->stream));
-    CU(h, cudaMemsetAsync(t.jid, 0xFF, cap * sizeof(uint32_t), h->stream));
-    launch_rehash(t, h->stream);
+    Slot *old = t.slots;
+    t.slots = nullptr;
+    CU(h, cudaMalloc(&t.slots, cap * sizeof(Slot)));
+    t.cap_mask = cap - 1;
+    launch_rehash(t, old, h->stream);
     CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));
+    cudaFree(old);
     return IPX_OK;
 }
 
@@ -610,6 +605,9 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
     const uint64_t n_tiles = tiles_of(b.n);
     rc = settle_batch(h); /* the previous batch's events are about to be overwritten */
     if (rc) return rc;
+    /* long reads scatter their offsets over thousands of values: extra dense rows would be given out to stragglers and
+     * then read by every finalize for nothing.  From the first such batch on, offsets >= DENSE_W go to the log. */
+    if (n_cigar > 8 * b.n) h->tab.extra_rows = 0;
     rc = ensure_log(h, ev_bound);
     if (rc) return rc;
     if (h->params.deferred_counting && two_pass(h)) {
@@ -724,7 +722,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     cudaStreamSynchronize(h->stream);
     drain(h->tm_extract); drain(h->tm_aggregate); drain(h->tm_motif); drain(h->tm_finalize); drain(h->tm_merge); drain(h->tm_export); drain(h->tm_import);
     drop_deferred(h);
-    cudaFree(h->tab.keys); cudaFree(h->tab.jid); cudaFree(h->tab.olog);
+    cudaFree(h->tab.slots); cudaFree(h->tab.olog);
     free_rows(h->tab);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     cudaFree(h->d_counters); cudaFree(h->d_name_rank); cudaFree(h->d_target_seq); cudaFree(h->d_export);
@@ -1149,6 +1147,7 @@ extern "C" int ipx_flush(ipx_handle *h, ipx_table **out) {
     /* clear(), junctions.hh:240-245 */
     h->finalized = false;
     launch_clear_tables(h->tab, st);
+    h->tab.extra_rows = 1;
     h->log_bound = 0;
     h->unsettled = false;
     h->exported_unsettled = false;
@@ -1169,6 +1168,7 @@ extern "C" int ipx_clear(ipx_handle *h) {
         CU(h, cudaGetLastError());
     }
     drop_deferred(h);
+    h->tab.extra_rows = 1;
     h->log_bound = 0;
     h->unsettled = false;
     h->import_pending = false;

@@ -92,7 +92,8 @@ void launch_init_rows(const Tables &t, uint64_t first, cudaStream_t st); /* junc
 /* only what is in use (and, when the overflow flag is up, the slots that were claimed while no junction row was left) */
 void launch_clear_tables(const Tables &t, cudaStream_t st);
 void launch_settle_counters(const Tables &t, cudaStream_t st); /* counters back to what exists, before growth */
-void launch_rehash(const Tables &t, cudaStream_t st);          /* every junction row into the (fresh) hash slots */
+/* every junction row into fresh hash slots (t.slots: allocated, any content); old_slots: where the rows' bases are */
+void launch_rehash(const Tables &t, const Slot *old_slots, cudaStream_t st);
 /* returns a CUDA error (attribute set-up of the pipelined kernel can fail), launches counted in *launches */
 cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractParams &p, const Tables &t, Event *out,
                            TileInfo *tile_info, unsigned long long *next_record, int sm_count, cudaStream_t st, int *launches);
@@ -121,7 +122,9 @@ struct FinalizeWork {
     uint64_t first_B = 1ull << 16, first_L = 1ull << 16, first_R = 1ull << 20; /* bounds of the very first finalize */
     unsigned long long *sort_key = nullptr, *tkey = nullptr;                     /* [B] */
     uint32_t *sort_sub = nullptr, *order = nullptr, *t_order = nullptr, *t_rank = nullptr; /* [B] */
-    uint32_t *seg_off = nullptr, *seg_fill = nullptr, *runs_j = nullptr, *nz_j = nullptr, *below_j = nullptr, *big_list = nullptr; /* [B] */
+    uint32_t *seg_off = nullptr, *seg_fill = nullptr, *runs_j = nullptr, *big_list = nullptr; /* [B] */
+    uint16_t *nz4 = nullptr;     /* [4 B] non-zero counters per dense row */
+    uint32_t *below3 = nullptr;  /* [3 B] log runs below each extra dense row */
     uint32_t *runs_r = nullptr;  /* [B + 1] */
     uint32_t *seg = nullptr;     /* [L] log entries grouped by junction, then the ordered runs' counts */
     uint32_t *big_scratch = nullptr;

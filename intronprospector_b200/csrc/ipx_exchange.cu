@@ -31,45 +31,49 @@ __device__ __forceinline__ int part_of(const Splitters &sp, uint32_t name_rank, 
 /* offset rows a counter needs: counts above 65535 are sent as several rows */
 __device__ __forceinline__ uint32_t hist_rows_of(uint32_t v) { return v ? (v - 1u) / 0xFFFFu + 1u : 0u; }
 
-/* what a warp needs of one junction row: owner, key fields, its dense offset row (8 counters per lane) */
+/* what a warp needs of one junction row: owner, key fields, the offset rows its dense counters turn into */
 struct RowView {
     int dest; /* -1: nothing to export (never created: nothing was counted into it) */
-    uint32_t i0, i1, mine, incl, nz, base;
+    uint32_t i0, i1, nz; /* nz: offset rows of all its dense rows together */
     int32_t tid;
-    uint32_t v[8];
+    uint32_t base[DENSE_ROWS - 1];
 };
+
+/* lane's 8 counters of dense row `row` of junction j */
+__device__ __forceinline__ void load_counters(const Tables &t, uint64_t j, uint32_t row, int lane, uint32_t v[8]) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(t.dense + (j * DENSE_ROWS + row) * DENSE_W);
+    const uint4 a = p[lane * 2], b = p[lane * 2 + 1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 __device__ __forceinline__ RowView read_row(const Tables &t, const uint32_t *name_rank, const Splitters &sp, uint64_t j, int lane) {
     RowView r;
     r.dest = -1;
-    r.mine = 0u;
-    /* everything that hangs on the junction id is requested at once: the warp's time is round trips, not bytes */
+    r.nz = 0u;
+    r.base[0] = r.base[1] = r.base[2] = BASE_UNSET;
     const unsigned long long T = t.stat[j].T;
     const unsigned long long key = t.jkey[j];
     r.tid = t.jtid[j];
-    r.base = t.obase[j];
-    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
-    if (t.dense) {
-        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + j * DENSE_W);
-        a = row[lane * 2];
-        b = row[lane * 2 + 1];
-    }
     r.i0 = key_start(t.kl, key);
     r.i1 = r.i0 + key_len(t.kl, key);
-    const bool live = T != EMPTY64;
-    if (live) r.dest = part_of(sp, name_rank[r.tid], r.i0);
-    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    if (T == EMPTY64) return r; /* (a hole or a disowned row: warp-uniform) */
+    r.dest = part_of(sp, name_rank[r.tid], r.i0);
+    if (t.dense) {
+        const Slot *s = &t.slots[t.jslot[j]];
+        r.base[0] = s->base[0]; r.base[1] = s->base[1]; r.base[2] = s->base[2];
+        uint32_t mine = 0u;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        r.v[k] = live ? r.v[k] : 0u;
-        r.mine += hist_rows_of(r.v[k]);
-    }
-    r.incl = r.mine;
+        for (uint32_t row = 0; row < DENSE_ROWS; ++row) {
+            if (row > 0u && r.base[row - 1] == BASE_UNSET) continue;
+            uint32_t v[8];
+            load_counters(t, j, row, lane, v);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, r.incl, d);
-        if (lane >= d) r.incl += y;
+            for (int k = 0; k < 8; ++k) mine += hist_rows_of(v[k]);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+        r.nz = mine;
     }
-    r.nz = __shfl_sync(0xFFFFFFFFu, r.incl, 31);
     return r;
 }
 
@@ -81,17 +85,45 @@ __device__ __forceinline__ JunctionRow make_junction_row(const JStat &s, const R
     return jr;
 }
 
-/* the lanes' non-zero dense counters as offset rows of junction row `jrow`, starting at hr[o] */
-__device__ __forceinline__ void write_dense_rows(HistRow *hr, uint64_t o, uint32_t jrow, const RowView &r, int lane) {
+/* the non-zero dense counters of junction j as offset rows of junction row `jrow`, starting at hr[o] (r.nz of them);
+ * ZERO: the counters are reset on the way (the junction is being disowned) */
+template <bool ZERO>
+__device__ __forceinline__ void write_dense_rows(const Tables &t, uint64_t j, HistRow *hr, uint64_t o, uint32_t jrow, const RowView &r,
+                                                 int lane, bool write) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        uint32_t left = r.v[k];
-        while (left) {
-            const uint32_t piece = left > 0xFFFFu ? 0xFFFFu : left;
-            HistRow h;
-            h.jrow = jrow; h.offset = (uint16_t)(r.base + (uint32_t)(lane * 8 + k)); h.cnt = (uint16_t)piece;
-            hr[o++] = h;
-            left -= piece;
+    for (uint32_t row = 0; row < DENSE_ROWS; ++row) {
+        if (row > 0u && r.base[row - 1] == BASE_UNSET) continue;
+        uint32_t v[8];
+        load_counters(t, j, row, lane, v);
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mine += hist_rows_of(v[k]);
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        const uint32_t first = row == 0u ? 0u : r.base[row - 1];
+        uint64_t at = o + (incl - mine);
+        if (write) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint32_t left = v[k];
+                while (left) {
+                    const uint32_t piece = left > 0xFFFFu ? 0xFFFFu : left;
+                    HistRow h;
+                    h.jrow = jrow; h.offset = (uint16_t)(first + (uint32_t)(lane * 8 + k)); h.cnt = (uint16_t)piece;
+                    hr[at++] = h;
+                    left -= piece;
+                }
+            }
+        }
+        o += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (ZERO) {
+            uint4 *p = reinterpret_cast<uint4 *>(t.dense + (j * DENSE_ROWS + row) * DENSE_W);
+            p[lane * 2] = make_uint4(0u, 0u, 0u, 0u);
+            p[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
         }
     }
 }
@@ -119,7 +151,7 @@ __global__ void __launch_bounds__(256) k_export_rows(Tables t, const uint32_t *n
         jr[jpos] = make_junction_row(t.stat[j], r);
         jrow_of[j] = ((uint32_t)r.dest << 24) | jrow; /* for the log entries of this junction */
     }
-    write_dense_rows(hr, hpos + (r.incl - r.mine), jrow, r, lane);
+    write_dense_rows<false>(t, j, hr, hpos, jrow, r, lane, true);
 }
 
 /* thread per entry of the read-offset log: one offset row each (equal pairs are summed by the importer) */
@@ -163,9 +195,20 @@ void launch_export_scatter(const Tables &t, const uint32_t *name_rank, const Spl
     if (n_olog) k_export_olog<true><<<blocks_for(n_olog, 256), 256, 0, st>>>(t, name_rank, sp, n_olog, cursors, jrow_of, hr);
 }
 
+/* which dense counter of junction j takes an offset that arrives from another rank (rows are given out as in K2) */
+__device__ __forceinline__ uint32_t place_offset(const Tables &t, uint32_t j, uint32_t off) {
+    if (t.dense == nullptr) return DENSE_NONE;
+    if (off < DENSE_W) return off;
+    const uint32_t slot = t.jslot[j];
+    const Slot *s = &t.slots[slot];
+    uint32_t base[DENSE_ROWS - 1] = {*((volatile const uint32_t *)&s->base[0]), *((volatile const uint32_t *)&s->base[1]),
+                                     *((volatile const uint32_t *)&s->base[2])};
+    return dense_place(t, slot, base, off);
+}
+
 /* fold one received junction row; returns the junction id or JID_NONE */
 __device__ __forceinline__ uint32_t import_junction_row(const Tables &t, IdPool *pool, const JunctionRow &r) {
-    const uint32_t j = junction_probe<true>(t, pool, make_key(t.kl, r.tid, r.i0, r.i1), r.tid);
+    const uint32_t j = junction_probe<true>(t, pool, make_key(t.kl, r.tid, r.i0, r.i1), r.tid).jid;
     if (j == JID_NONE) return j;
     JStat *s = &t.stat[j];
     for (int c = 0; c < 3; ++c) {
@@ -201,10 +244,9 @@ __global__ void __launch_bounds__(256) k_import_hist_rows(Tables t, const HistRo
         cnt = r.cnt;
     }
     const bool ok = j != JID_NONE && cnt != 0u;
-    const uint32_t base = ok && t.dense ? dense_base(t, j, off) : 0u;
-    const bool in_row = ok && in_dense_row(t, base, off);
-    if (in_row) atomicAdd(&t.dense[(uint64_t)j * DENSE_W + (off - base)], cnt);
-    log_append(t, log, ok && !in_row, olog_entry(j, off, cnt));
+    const uint32_t place = ok ? place_offset(t, j, off) : DENSE_NONE;
+    if (place != DENSE_NONE) atomicAdd(&t.dense[(uint64_t)j * (DENSE_ROWS * DENSE_W) + place], cnt);
+    log_append(t, log, ok && place == DENSE_NONE, olog_entry(j, off, cnt));
     log_flush(t, log);
 }
 
@@ -280,14 +322,10 @@ __global__ void __launch_bounds__(256) k_mail_rows(Tables t, const uint32_t *nam
                 p[2] = make_uint4(0u, 0u, 0u, 0u);
                 p[3] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
                 t.olog_cnt[j] = 0u;
-                t.obase[j] = BASE_UNSET;
             }
-            if (fits) write_dense_rows(mail_hist_rows(m, box), hpos + (r.incl - r.mine), (uint32_t)jpos, r, lane);
-            if (t.dense && r.nz) {
-                uint4 *row = reinterpret_cast<uint4 *>(t.dense + j * DENSE_W);
-                row[lane * 2] = make_uint4(0u, 0u, 0u, 0u);
-                row[lane * 2 + 1] = make_uint4(0u, 0u, 0u, 0u);
-            }
+            /* its offset rows go out and its counters back to zero (the rows stay given out: their bases are as good
+             * for the reads that may follow as any) */
+            if (t.dense) write_dense_rows<true>(t, j, mail_hist_rows(m, box), hpos, (uint32_t)jpos, r, lane, fits);
         }
         __syncthreads();
     }
@@ -442,10 +480,9 @@ __global__ void __launch_bounds__(256) k_mail_import_hist(Tables t, Mailboxes m,
             cnt = r.cnt;
         }
         const bool ok = j != JID_NONE && cnt != 0u;
-        const uint32_t base = ok && t.dense ? dense_base(t, j, off) : 0u;
-        const bool in_row = ok && in_dense_row(t, base, off);
-        if (in_row) atomicAdd(&t.dense[(uint64_t)j * DENSE_W + (off - base)], cnt);
-        log_append(t, log, ok && !in_row, olog_entry(j, off, cnt));
+        const uint32_t place = ok ? place_offset(t, j, off) : DENSE_NONE;
+        if (place != DENSE_NONE) atomicAdd(&t.dense[(uint64_t)j * (DENSE_ROWS * DENSE_W) + place], cnt);
+        log_append(t, log, ok && place == DENSE_NONE, olog_entry(j, off, cnt));
     }
     log_flush(t, log);
 }
@@ -480,7 +517,7 @@ __global__ void k_import_thresholds(Tables t, const ThresholdRow *rows, uint64_t
     if (i >= n) return;
     const ThresholdRow r = rows[i];
     if (r.T == EMPTY64) return;
-    const uint32_t j = junction_probe<false>(t, nullptr, make_key(t.kl, r.tid, r.i0, r.i1), r.tid);
+    const uint32_t j = junction_probe<false>(t, nullptr, make_key(t.kl, r.tid, r.i0, r.i1), r.tid).jid;
     if (j != JID_NONE) atomicMin(&t.stat[j].T, r.T);
 }
 

@@ -190,13 +190,13 @@ __global__ void __launch_bounds__(256) k_ss_scatter(const unsigned long long *ke
     }
 }
 
-/* One block per bucket: every key's rank among the bucket's keys by counting (the keys are unique), out of shared
- * memory -- no barriers between steps, the inner loop reads one address per iteration (a broadcast).  The values go to
- * the bucket's place in the global order (and, when asked, the position of every value).  A bucket that does not fit
- * shared memory is counted out of global memory (only a pathological input makes such buckets). */
+/* One block per bucket: a bitonic sort in shared memory (its cost grows with n log^2 n, so a bucket a few times the
+ * average does not hold the launch up the way a quadratic ranking would), then the values go to the bucket's place in
+ * the global order (and, when asked, the position of every value).  A bucket that does not fit shared memory is
+ * ranked by counting out of global memory (only a pathological input makes such buckets). */
 __global__ void __launch_bounds__(256) k_ss_local(SampleSort ss, uint32_t *out_vals, uint32_t *out_rank) {
     __shared__ unsigned long long s_k[SS_SMEM_BUCKET];
-    __shared__ uint32_t s_s[SS_SMEM_BUCKET];
+    __shared__ uint32_t s_s[SS_SMEM_BUCKET], s_v[SS_SMEM_BUCKET];
     __shared__ uint32_t s_part[8];
     const uint32_t P = ss.bucket_cnt[SS_MAX_BUCKETS];
     const uint32_t b = blockIdx.x;
@@ -214,30 +214,30 @@ __global__ void __launch_bounds__(256) k_ss_local(SampleSort ss, uint32_t *out_v
     if (cnt == 0u) return;
     const unsigned long long *gk = ss.bk + (uint64_t)b * ss.C;
     const uint32_t *gs = ss.bs + (uint64_t)b * ss.C, *gv = ss.bv + (uint64_t)b * ss.C;
-    const bool staged = cnt <= (uint32_t)SS_SMEM_BUCKET;
-    if (staged) {
+    if (cnt <= (uint32_t)SS_SMEM_BUCKET) {
+        uint32_t n2 = 2u;
+        while (n2 < cnt) n2 <<= 1;
+        for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) {
+            s_k[i] = i < cnt ? gk[i] : EMPTY64;
+            s_s[i] = i < cnt ? gs[i] : 0xFFFFFFFFu;
+            s_v[i] = i < cnt ? gv[i] : 0u;
+        }
+        block_bitonic<true>(s_k, s_s, s_v, n2);
         for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-            s_k[i] = gk[i];
-            s_s[i] = gs[i];
+            out_vals[base + i] = s_v[i];
+            if (out_rank) out_rank[s_v[i]] = base + i;
         }
-        __syncthreads();
-    }
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-        const unsigned long long ki = staged ? s_k[i] : gk[i];
-        const uint32_t si = staged ? s_s[i] : gs[i];
-        uint32_t rank = 0u;
-        if (staged) {
-#pragma unroll 4
-            for (uint32_t x = 0; x < cnt; ++x) rank += pair_less(s_k[x], s_s[x], ki, si) ? 1u : 0u;
-        } else {
+    } else {
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const unsigned long long ki = gk[i];
+            const uint32_t si = gs[i];
+            uint32_t rank = 0u;
             for (uint32_t x = 0; x < cnt; ++x) rank += pair_less(gk[x], gs[x], ki, si) ? 1u : 0u;
+            out_vals[base + rank] = gv[i];
+            if (out_rank) out_rank[gv[i]] = base + rank;
         }
-        const uint32_t v = gv[i];
-        out_vals[base + rank] = v;
-        if (out_rank) out_rank[v] = base + rank;
     }
 }
-
 
 /* IPX_FIN_TRACE=1 (with IPX_NO_GRAPH=1): CUDA events between the steps, everything on one stream, times on stderr */
 struct FinTrace {
@@ -304,49 +304,71 @@ __global__ void __launch_bounds__(256) k_fin_scatter(Tables t, uint64_t B, uint6
     if ((uint64_t)seg_off[j] + pos < L) seg[seg_off[j] + pos] = (uint32_t)e;
 }
 
-__device__ __forceinline__ uint32_t dense_nonzeros(const Tables &t, uint64_t j, int lane) {
-    uint32_t nz = 0u;
-    if (t.dense) {
-        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + j * DENSE_W);
-        const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
-        nz = (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0) + (b.x != 0) + (b.y != 0) + (b.z != 0) + (b.w != 0);
-    }
+/* the bases of junction j's dense rows 1 .. (BASE_UNSET: row not given out) */
+__device__ __forceinline__ void row_bases(const Tables &t, uint64_t j, uint32_t base[DENSE_ROWS - 1]) {
+    const Slot *s = &t.slots[t.jslot[j]];
+    base[0] = s->base[0];
+    base[1] = s->base[1];
+    base[2] = s->base[2];
+}
+
+/* non-zero counters of one dense row (all lanes get the sum) */
+__device__ __forceinline__ uint32_t dense_nonzeros(const Tables &t, uint64_t j, uint32_t row, int lane) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(t.dense + (j * DENSE_ROWS + row) * DENSE_W);
+    const uint4 a = p[lane * 2], b = p[lane * 2 + 1];
+    uint32_t nz = (a.x != 0) + (a.y != 0) + (a.z != 0) + (a.w != 0) + (b.x != 0) + (b.y != 0) + (b.z != 0) + (b.w != 0);
 #pragma unroll
     for (int k = 16; k > 0; k >>= 1) nz += __shfl_xor_sync(0xFFFFFFFFu, nz, k);
     return nz;
 }
 
-/* warp per junction id: non-zero counters of its dense row; its log segment ordered by offset and run-length reduced
- * in place (the counts of the runs, ascending offset, replace the entries); runs_j = runs of both kinds, below_j = log
- * runs with offsets below the dense row's first (they come first in the output).  Junctions with more than FIN_SMALL
- * log entries are left to k_fin_big. */
+/* nz4[4 j + r] = non-zero counters of junction j's row r; returns their sum */
+__device__ __forceinline__ uint32_t count_dense_rows(const Tables &t, uint64_t j, const uint32_t base[DENSE_ROWS - 1], int lane, uint16_t *nz4) {
+    uint32_t total = 0u;
+    if (!t.dense) {
+        if (lane < (int)DENSE_ROWS) nz4[4 * j + lane] = 0;
+        return 0u;
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < DENSE_ROWS; ++r) {
+        const uint32_t nz = (r == 0u || base[r - 1] != BASE_UNSET) ? dense_nonzeros(t, j, r, lane) : 0u;
+        if (lane == 0) nz4[4 * j + r] = (uint16_t)nz;
+        total += nz;
+    }
+    return total;
+}
+
+/* warp per junction id: non-zero counters of its dense rows; its log segment ordered by offset and run-length reduced
+ * in place (the counts of the runs, ascending offset, replace the entries); runs_j = runs of both kinds, below3[3 j + r]
+ * = log runs with offsets below the first offset of dense row r + 1 (they come before it in the output).  Junctions
+ * with more than FIN_SMALL log entries are left to k_fin_big. */
 __global__ void __launch_bounds__(256) k_fin_small(Tables t, uint64_t B, uint64_t L, unsigned long long *d_count, const uint32_t *seg_off,
-                                                   uint32_t *seg, uint32_t *runs_j, uint32_t *nz_j, uint32_t *below_j, uint32_t *big_list) {
+                                                   uint32_t *seg, uint32_t *runs_j, uint16_t *nz4, uint32_t *below3, uint32_t *big_list) {
     __shared__ uint32_t s_w[8][FIN_SMALL];
     __shared__ uint32_t s_c[8][FIN_SMALL];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nk = d_count[4] < B ? d_count[4] : B;
     if (j >= nk) return;
+    if (lane < 3) below3[3 * j + lane] = 0u;
     if (t.stat[j].T == EMPTY64) {
-        if (lane == 0) { runs_j[j] = 0u; nz_j[j] = 0u; below_j[j] = 0u; }
+        if (lane == 0) runs_j[j] = 0u;
+        if (lane < (int)DENSE_ROWS) nz4[4 * j + lane] = 0;
         return;
     }
-    const uint32_t nz = dense_nonzeros(t, j, lane);
+    uint32_t base[DENSE_ROWS - 1];
+    row_bases(t, j, base);
+    const uint32_t nz = count_dense_rows(t, j, base, lane, nz4);
     const uint32_t n = t.olog_cnt[j];
     const uint64_t s0 = seg_off[j];
     if (n == 0u || s0 + n > L) { /* (beyond L: the bound was too small, the finalize runs again) */
-        if (lane == 0) { runs_j[j] = nz; nz_j[j] = nz; below_j[j] = 0u; }
+        if (lane == 0) runs_j[j] = nz;
         return;
     }
     if (n > FIN_SMALL) {
-        if (lane == 0) {
-            nz_j[j] = nz;
-            big_list[atomicAdd(&d_count[6], 1ull)] = (uint32_t)j;
-        }
+        if (lane == 0) big_list[atomicAdd(&d_count[6], 1ull)] = (uint32_t)j;
         return;
     }
-    const uint32_t base = t.dense ? t.obase[j] : 0u; /* (set: a junction with log entries has counted a read) */
     uint32_t *w = s_w[warp], *c = s_c[warp];
     uint32_t n2 = 2u;
     while (n2 < n) n2 <<= 1;
@@ -363,7 +385,7 @@ __global__ void __launch_bounds__(256) k_fin_small(Tables t, uint64_t B, uint64_
     }
     __syncwarp();
     /* runs of equal offsets (the high half of an entry), their counts summed */
-    uint32_t n_runs = 0u, n_below = 0u;
+    uint32_t n_runs = 0u, below[DENSE_ROWS - 1] = {0u, 0u, 0u};
     for (uint32_t i0 = 0; i0 < n; i0 += 32u) {
         const uint32_t i = i0 + lane;
         const bool valid = i < n;
@@ -375,11 +397,16 @@ __global__ void __launch_bounds__(256) k_fin_small(Tables t, uint64_t B, uint64_
         __syncwarp();
         if (valid) atomicAdd(&c[run], x & 0xFFFFu);
         n_runs += (uint32_t)__popc(hm);
-        n_below += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, head && (x >> 16) < base));
+#pragma unroll
+        for (uint32_t r = 0; r < DENSE_ROWS - 1; ++r)
+            below[r] += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, head && base[r] != BASE_UNSET && (x >> 16) < base[r]));
         __syncwarp();
     }
     for (uint32_t r = lane; r < n_runs; r += 32u) seg[s0 + r] = c[r];
-    if (lane == 0) { runs_j[j] = nz + n_runs; nz_j[j] = nz; below_j[j] = n_below; }
+    if (lane == 0) {
+        runs_j[j] = nz + n_runs;
+        below3[3 * j + 0] = below[0]; below3[3 * j + 1] = below[1]; below3[3 * j + 2] = below[2];
+    }
 }
 
 /* Block per junction with many log entries: the entries' counts are summed per offset in a 65536-counter scratch of the
@@ -387,14 +414,18 @@ __global__ void __launch_bounds__(256) k_fin_small(Tables t, uint64_t B, uint64_
  * (64 summary words over 2048 words over 65536 offsets); the runs are then read off the bitmap in ascending order by
  * the 64 threads that own a summary word each.  The cost follows the entries and the distinct offsets, not 65536. */
 static const int FIN_BIG_BLOCKS = 148 * 4;
+__device__ __forceinline__ uint32_t bits_below(uint32_t bits, uint32_t lo, uint32_t base) {
+    /* set bits of a bitmap word that starts at offset lo whose offsets lie below base */
+    if (base == BASE_UNSET || lo >= base) return 0u;
+    return lo + 32u <= base ? (uint32_t)__popc(bits) : (uint32_t)__popc(bits & ((1u << (base - lo)) - 1u));
+}
 __global__ void __launch_bounds__(256) k_fin_big(Tables t, uint64_t L, const unsigned long long *d_count, const uint32_t *big_list,
-                                                 const uint32_t *seg_off, uint32_t *seg, uint32_t *runs_j, const uint32_t *nz_j,
-                                                 uint32_t *below_j, uint32_t *scratch) {
+                                                 const uint32_t *seg_off, uint32_t *seg, uint32_t *runs_j, const uint16_t *nz4,
+                                                 uint32_t *below3, uint32_t *scratch) {
     __shared__ uint32_t s_bits[2048];
     __shared__ uint32_t s_sum[64];
-    __shared__ uint32_t s_runs[64], s_below[64];
+    __shared__ uint32_t s_runs[64], s_below[DENSE_ROWS - 1][64];
     uint32_t *cnt = scratch + (uint64_t)blockIdx.x * 65536u;
-    const int lane = threadIdx.x & 31;
     for (uint32_t i = threadIdx.x; i < 2048u; i += blockDim.x) s_bits[i] = 0u;
     if (threadIdx.x < 64) s_sum[threadIdx.x] = 0u;
     __syncthreads();
@@ -403,7 +434,8 @@ __global__ void __launch_bounds__(256) k_fin_big(Tables t, uint64_t L, const uns
         const uint32_t j = big_list[q];
         const uint32_t n = t.olog_cnt[j];
         const uint64_t s0 = seg_off[j];
-        const uint32_t base = t.dense ? t.obase[j] : 0u;
+        uint32_t base[DENSE_ROWS - 1] = {BASE_UNSET, BASE_UNSET, BASE_UNSET};
+        if (t.dense) row_bases(t, j, base);
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
             const uint32_t x = seg[s0 + i];
             const uint32_t off = x >> 16;
@@ -414,30 +446,30 @@ __global__ void __launch_bounds__(256) k_fin_big(Tables t, uint64_t L, const uns
         __threadfence();
         __syncthreads();
         /* thread i < 64 owns summary word i = offsets [1024 i, 1024 i + 1024) */
-        uint32_t mine = 0u, mine_below = 0u;
         if (threadIdx.x < 64) {
+            uint32_t mine = 0u, mb[DENSE_ROWS - 1] = {0u, 0u, 0u};
             uint32_t words = s_sum[threadIdx.x];
             while (words) {
                 const uint32_t wi = threadIdx.x * 32u + (uint32_t)__ffs(words) - 1u;
                 words &= words - 1u;
                 const uint32_t bits = s_bits[wi];
                 mine += (uint32_t)__popc(bits);
-                /* offsets of this word below the dense row's first */
-                const uint32_t lo = wi * 32u;
-                if (lo + 32u <= base) mine_below += (uint32_t)__popc(bits);
-                else if (lo < base) mine_below += (uint32_t)__popc(bits & ((1u << (base - lo)) - 1u));
+#pragma unroll
+                for (uint32_t r = 0; r < DENSE_ROWS - 1; ++r) mb[r] += bits_below(bits, wi * 32u, base[r]);
             }
             s_runs[threadIdx.x] = mine;
-            s_below[threadIdx.x] = mine_below;
+#pragma unroll
+            for (uint32_t r = 0; r < DENSE_ROWS - 1; ++r) s_below[r][threadIdx.x] = mb[r];
         }
         __syncthreads();
         if (threadIdx.x < 64) {
-            uint32_t pre = 0u, total = 0u, below = 0u;
+            uint32_t pre = 0u, total = 0u, below[DENSE_ROWS - 1] = {0u, 0u, 0u};
             for (uint32_t k = 0; k < 64u; ++k) {
                 const uint32_t v = s_runs[k];
                 if (k < threadIdx.x) pre += v;
                 total += v;
-                below += s_below[k];
+#pragma unroll
+                for (uint32_t r = 0; r < DENSE_ROWS - 1; ++r) below[r] += s_below[r][k];
             }
             /* total <= n: the runs fit where the entries were (every entry has been read: the barrier above) */
             uint32_t words = s_sum[threadIdx.x];
@@ -455,14 +487,13 @@ __global__ void __launch_bounds__(256) k_fin_big(Tables t, uint64_t L, const uns
             }
             s_sum[threadIdx.x] = 0u;
             if (threadIdx.x == 0) {
-                runs_j[j] = nz_j[j] + total;
-                below_j[j] = below;
+                runs_j[j] = (uint32_t)nz4[4 * j] + nz4[4 * j + 1] + nz4[4 * j + 2] + nz4[4 * j + 3] + total;
+                below3[3 * j + 0] = below[0]; below3[3 * j + 1] = below[1]; below3[3 * j + 2] = below[2];
             }
         }
         __syncthreads();
     }
     (void)L;
-    (void)lane;
 }
 
 /* ------------------------------------------------------------------ output rows */
@@ -526,10 +557,10 @@ struct RunsIn {
     __device__ __forceinline__ unsigned long long operator()(uint64_t i) const { return runs_r[i]; }
 };
 
-/* warp per junction, key order: its runs in ascending offset order -- the ordered runs of its log segment below the
- * dense row's first offset, the dense row, the rest of the log runs */
+/* warp per junction, key order: its runs in ascending offset order -- row 0 (offsets below DENSE_W), then the other dense
+ * rows in the order of their first offsets, each preceded by the log runs that lie below it, then the rest of the log */
 __global__ void __launch_bounds__(256) k_fin_write(Tables t, uint64_t B, uint64_t R, const uint32_t *order, unsigned long long *d_count,
-                                                   const unsigned long long *hist_off, const uint32_t *nz_j, const uint32_t *below_j,
+                                                   const unsigned long long *hist_off, const uint16_t *nz4, const uint32_t *below3,
                                                    const uint32_t *seg_off, const uint32_t *seg, uint32_t *hist_cnt) {
     const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -542,29 +573,58 @@ __global__ void __launch_bounds__(256) k_fin_write(Tables t, uint64_t B, uint64_
     if (r >= d_count[0] || r >= B) return;
     const uint32_t j = order[r];
     const unsigned long long o0 = hist_off[r], o1 = hist_off[r + 1];
-    const uint32_t nz = nz_j[j], below = below_j[j];
-    if (t.dense && nz) {
-        const uint4 *row = reinterpret_cast<const uint4 *>(t.dense + (uint64_t)j * DENSE_W);
-        const uint4 a = row[lane * 2], b = row[lane * 2 + 1];
-        const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t mine = 0;
+    const uint64_t s0 = seg_off[j];
+    uint32_t base[DENSE_ROWS - 1] = {BASE_UNSET, BASE_UNSET, BASE_UNSET};
+    uint32_t nz[DENSE_ROWS] = {0u, 0u, 0u, 0u};
+    if (t.dense) {
+        row_bases(t, j, base);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) mine += (v[k] != 0);
-        uint32_t pre = mine;
+        for (uint32_t k = 0; k < DENSE_ROWS; ++k) nz[k] = nz4[4 * (uint64_t)j + k];
+    }
+    const uint32_t n_dense = nz[0] + nz[1] + nz[2] + nz[3];
+    const uint32_t n_log = (uint32_t)(o1 - o0) - n_dense;
+    /* the dense rows in output order: row 0, then rows 1 .. by ascending base (rows not given out last) */
+    uint32_t ord[DENSE_ROWS - 1] = {0u, 1u, 2u};
 #pragma unroll
-        for (int k = 1; k < 32; k <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, pre, k);
-            if (lane >= k) pre += y;
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2 - a; ++b)
+            if (base[ord[b]] > base[ord[b + 1]]) { const uint32_t x = ord[b]; ord[b] = ord[b + 1]; ord[b + 1] = x; }
+    uint64_t o = o0;
+    uint32_t q = 0u; /* log runs written so far */
+#pragma unroll
+    for (uint32_t k = 0; k < DENSE_ROWS; ++k) {
+        const uint32_t row = k == 0u ? 0u : ord[k - 1] + 1u;
+        if (k > 0u && base[row - 1u] == BASE_UNSET) break;
+        if (k > 0u) {
+            /* the log runs below this row's first offset */
+            const uint32_t upto = below3[3 * (uint64_t)j + (row - 1u)];
+            for (uint32_t x = q + lane; x < upto; x += 32u) hist_cnt[o + (x - q)] = seg[s0 + x];
+            o += upto - q;
+            q = upto;
         }
-        uint64_t o = o0 + below + (pre - mine);
+        if (nz[row]) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(t.dense + ((uint64_t)j * DENSE_ROWS + row) * DENSE_W);
+            const uint4 a = p[lane * 2], b = p[lane * 2 + 1];
+            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            uint32_t mine = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (v[k] != 0) hist_cnt[o++] = v[k];
+            for (int i = 0; i < 8; ++i) mine += (v[i] != 0);
+            uint32_t pre = mine;
+#pragma unroll
+            for (int i = 1; i < 32; i <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, pre, i);
+                if (lane >= i) pre += y;
+            }
+            uint64_t at = o + (pre - mine);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (v[i] != 0) hist_cnt[at++] = v[i];
+            }
+            o += nz[row];
         }
     }
-    const unsigned long long n_log = (o1 - o0) - nz;
-    const uint64_t s0 = seg_off[j];
-    for (unsigned long long q = lane; q < n_log; q += 32) hist_cnt[o0 + q + (q < below ? 0u : nz)] = seg[s0 + q];
+    for (uint32_t x = q + lane; x < n_log; x += 32u) hist_cnt[o + (x - q)] = seg[s0 + x];
 }
 
 /* ------------------------------------------------------------------ host side */
@@ -596,7 +656,7 @@ void finalize_release(FinalizeWork &w) {
     if (w.exec) cudaGraphExecDestroy(w.exec);
     w.exec = nullptr;
     cudaFree(w.sort_key); cudaFree(w.sort_sub); cudaFree(w.tkey); cudaFree(w.order); cudaFree(w.t_order); cudaFree(w.t_rank);
-    cudaFree(w.seg_off); cudaFree(w.seg_fill); cudaFree(w.runs_j); cudaFree(w.nz_j); cudaFree(w.below_j); cudaFree(w.big_list); cudaFree(w.runs_r);
+    cudaFree(w.seg_off); cudaFree(w.seg_fill); cudaFree(w.runs_j); cudaFree(w.nz4); cudaFree(w.below3); cudaFree(w.big_list); cudaFree(w.runs_r);
     cudaFree(w.seg); cudaFree(w.big_scratch); cudaFree(w.scan_state); cudaFree(w.d_count);
     for (int k = 0; k < 2; ++k) {
         cudaFree(w.ss_splitters[k]); cudaFree(w.ss_bucket_cnt[k]); cudaFree(w.ss_bk[k]); cudaFree(w.ss_bs[k]); cudaFree(w.ss_bv[k]);
@@ -647,7 +707,7 @@ static cudaError_t finalize_allocate(FinalizeWork &w, uint64_t B, uint64_t L, ui
     if (B != w.B) {
         IPX_CU(regrow(&w.sort_key, B)); IPX_CU(regrow(&w.sort_sub, B)); IPX_CU(regrow(&w.tkey, B)); IPX_CU(regrow(&w.order, B));
         IPX_CU(regrow(&w.t_order, B)); IPX_CU(regrow(&w.t_rank, B)); IPX_CU(regrow(&w.seg_off, B)); IPX_CU(regrow(&w.seg_fill, B));
-        IPX_CU(regrow(&w.runs_j, B)); IPX_CU(regrow(&w.nz_j, B)); IPX_CU(regrow(&w.below_j, B)); IPX_CU(regrow(&w.big_list, B)); IPX_CU(regrow(&w.runs_r, B + 1));
+        IPX_CU(regrow(&w.runs_j, B)); IPX_CU(regrow(&w.nz4, B * 4)); IPX_CU(regrow(&w.below3, B * 3)); IPX_CU(regrow(&w.big_list, B)); IPX_CU(regrow(&w.runs_r, B + 1));
         IPX_CU(regrow(&w.scan_state, scan_state_words(B + 1)));
         DeviceTable &o = w.out;
         IPX_CU(regrow(&o.chrom, B)); IPX_CU(regrow(&o.i0, B)); IPX_CU(regrow(&o.i1, B)); IPX_CU(regrow(&o.a0, B));
@@ -700,9 +760,9 @@ static cudaError_t finalize_issue(const Tables &t, const GenomeView &g, const ui
     /* s3: the log entries gathered per junction, ordered and run-length reduced */
     k_fin_scatter<<<blocks_for(L, 256), 256, 0, s3>>>(t, B, L, w.d_count, w.seg_off, w.seg_fill, w.seg);
     tr.mark("log-scatter");
-    k_fin_small<<<blocks_for(B * 32, 256), 256, 0, s3>>>(t, B, L, w.d_count, w.seg_off, w.seg, w.runs_j, w.nz_j, w.below_j, w.big_list);
+    k_fin_small<<<blocks_for(B * 32, 256), 256, 0, s3>>>(t, B, L, w.d_count, w.seg_off, w.seg, w.runs_j, w.nz4, w.below3, w.big_list);
     tr.mark("small");
-    k_fin_big<<<FIN_BIG_BLOCKS, 256, 0, s3>>>(t, L, w.d_count, w.big_list, w.seg_off, w.seg, w.runs_j, w.nz_j, w.below_j, w.big_scratch);
+    k_fin_big<<<FIN_BIG_BLOCKS, 256, 0, s3>>>(t, L, w.d_count, w.big_list, w.seg_off, w.seg, w.runs_j, w.nz4, w.below3, w.big_scratch);
     tr.mark("big");
     if (!trace) {
         IPX_CU(cudaEventRecord(w.ev_join3, s3));
@@ -714,7 +774,7 @@ static cudaError_t finalize_issue(const Tables &t, const GenomeView &g, const ui
     tr.mark("rows");
     IPX_CU(scan_exclusive(RunsIn{w.runs_r}, out.hist_off, B + 1, w.scan_state, st));
     tr.mark("scan");
-    k_fin_write<<<blocks_for(B * 32, 256), 256, 0, st>>>(t, B, R, w.order, w.d_count, out.hist_off, w.nz_j, w.below_j, w.seg_off, w.seg,
+    k_fin_write<<<blocks_for(B * 32, 256), 256, 0, st>>>(t, B, R, w.order, w.d_count, out.hist_off, w.nz4, w.below3, w.seg_off, w.seg,
                                                         out.hist_cnt);
     tr.mark("write");
     IPX_CU(cudaMemcpyAsync(w.h_count, w.d_count, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -733,8 +793,8 @@ cudaError_t finalize_enqueue(const Tables &t, const GenomeView &g, const uint32_
     if (w.wish_C > C) C = w.wish_C;
     FinalizeWork::Key key{};
     key.B = B; key.L = L; key.R = R; key.C = C;
-    key.tab_keys = t.keys; key.tab_rows = t.stat; key.tab_log = t.olog; key.max_j = t.max_j; key.olog_cap = t.olog_cap;
-    key.tab_base = t.obase; key.name_rank = d_name_rank; key.gseq = g.seq; key.target_seq = g.target_seq; key.dense = t.dense;
+    key.tab_keys = t.slots; key.tab_rows = t.stat; key.tab_log = t.olog; key.max_j = t.max_j; key.olog_cap = t.olog_cap;
+    key.tab_base = t.jslot; key.name_rank = d_name_rank; key.gseq = g.seq; key.target_seq = g.target_seq; key.dense = t.dense;
     key.n_targets = g.n_targets; key.have_genome = g.have_genome; key.skip_missing = g.skip_missing; key.filter_canon = g.filter_canon;
     key.wide = t.kl.wide; key.len_bits = t.kl.len_bits;
     if (!w.exec || !(key == w.key)) {

@@ -36,13 +36,30 @@ __device__ __forceinline__ void reset_stat(JStat *s) {
     p[3] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);                            /* cnt[2], a0 = none, a1 = 0 */
 }
 
+__device__ __forceinline__ void reset_slot(Slot *s) {
+    uint4 *p = reinterpret_cast<uint4 *>(s);
+    p[0] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, JID_UNSET, BASE_UNSET); /* key, jid, base[0] */
+    p[1] = make_uint4(BASE_UNSET, BASE_UNSET, 0u, 0u);                  /* base[1], base[2] */
+}
+
 /* hash slots [0, cap) */
-__global__ void k_init_slots(unsigned long long *keys, uint32_t *jid, uint64_t cap) {
+__global__ void k_init_slots(Slot *slots, uint64_t cap) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
-        keys[i] = EMPTY64;
-        jid[i] = JID_UNSET;
-    }
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) reset_slot(&slots[i]);
+}
+
+/* zero the dense rows of junction j that are in use: row 0, and the rows the slot's bases say were given out */
+__device__ __forceinline__ void zero_dense_rows(const Tables &t, uint64_t j, const uint32_t base[DENSE_ROWS - 1], int lane) {
+    if (!t.dense) return;
+    uint4 *row = reinterpret_cast<uint4 *>(t.dense + j * (DENSE_ROWS * DENSE_W));
+    row[lane] = make_uint4(0u, 0u, 0u, 0u);
+    row[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (uint32_t r = 0; r < DENSE_ROWS - 1; ++r)
+        if (base[r] != BASE_UNSET) {
+            row[(r + 1u) * 64u + lane] = make_uint4(0u, 0u, 0u, 0u);
+            row[(r + 1u) * 64u + lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+        }
 }
 
 /* junction rows [first, max_j): a warp per row (64-byte record, 1 KB offset row) */
@@ -55,12 +72,10 @@ __global__ void __launch_bounds__(256) k_init_rows(Tables t, uint64_t first) {
             reset_stat(&t.stat[j]);
             t.olog_cnt[j] = 0u;
             t.jslot[j] = SLOT_NONE;
-            t.obase[j] = BASE_UNSET;
         }
         if (t.dense) {
-            uint4 *row = reinterpret_cast<uint4 *>(t.dense + j * DENSE_W);
-            row[lane] = make_uint4(0u, 0u, 0u, 0u);
-            row[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+            uint4 *row = reinterpret_cast<uint4 *>(t.dense + j * (DENSE_ROWS * DENSE_W));
+            for (uint32_t q = lane; q < DENSE_ROWS * DENSE_W / 4; q += 32u) row[q] = make_uint4(0u, 0u, 0u, 0u);
         }
     }
 }
@@ -86,18 +101,15 @@ __global__ void __launch_bounds__(256) k_clear_tables(Tables t) {
     for (uint64_t j = warp0; j < nk; j += n_warps) {
         const uint32_t slot = t.jslot[j];
         if (slot == SLOT_NONE) continue; /* an id no junction took: its row is in the reset state */
+        Slot *s = &t.slots[slot];
+        const uint32_t base[DENSE_ROWS - 1] = {s->base[0], s->base[1], s->base[2]};
+        __syncwarp();
+        zero_dense_rows(t, j, base, lane);
         if (lane == 0) {
-            t.keys[slot] = EMPTY64;
-            t.jid[slot] = JID_UNSET;
+            reset_slot(s);
             reset_stat(&t.stat[j]);
             t.olog_cnt[j] = 0u;
             t.jslot[j] = SLOT_NONE;
-            t.obase[j] = BASE_UNSET;
-        }
-        if (t.dense) {
-            uint4 *row = reinterpret_cast<uint4 *>(t.dense + j * DENSE_W);
-            row[lane] = make_uint4(0u, 0u, 0u, 0u);
-            row[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
         }
     }
 }
@@ -108,16 +120,12 @@ __global__ void k_sweep_full_slots(Tables t) {
     if (!(*((volatile uint32_t *)t.overflow) & OVF_TABLE)) return;
     const uint64_t cap = t.cap_mask + 1;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
-        if (t.jid[i] == JID_FULL) {
-            t.keys[i] = EMPTY64;
-            t.jid[i] = JID_UNSET;
-        }
-    }
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride)
+        if (t.slots[i].jid == JID_FULL) reset_slot(&t.slots[i]);
 }
 
 void launch_init_tables(const Tables &t, cudaStream_t st) {
-    k_init_slots<<<148 * 8, 256, 0, st>>>(t.keys, t.jid, t.cap_mask + 1);
+    k_init_slots<<<148 * 8, 256, 0, st>>>(t.slots, t.cap_mask + 1);
     k_init_rows<<<148 * 8, 256, 0, st>>>(t, 0);
     k_reset_counters<<<1, N_ID_POOLS, 0, st>>>(t);
 }
@@ -140,26 +148,32 @@ __global__ void k_settle_counters(Tables t) {
     atomicAnd(t.overflow, ~(OVF_TABLE | OVF_LOG));
 }
 
-/* rehash into a fresh slot array (already initialised): every junction row claims a slot for its key again; the rows
- * themselves do not move */
-__global__ void k_rehash(Tables t) {
+/* rehash into a fresh slot array (already initialised): every junction row claims a slot for its key again and takes
+ * the bases of its dense rows along; the rows themselves do not move */
+__global__ void k_rehash(Tables t, const Slot *old_slots) {
     const uint64_t nk = junctions_in_use(t);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nk; j += stride) {
-        if (t.jslot[j] == SLOT_NONE) continue; /* an id no junction took */
+        const uint32_t was = t.jslot[j];
+        if (was == SLOT_NONE) continue; /* an id no junction took */
         const unsigned long long key = t.jkey[j];
         uint64_t h = junction_hash(key, t.jtid[j]) & t.cap_mask;
         for (;;) {
-            if (atomicCAS(&t.keys[h], EMPTY64, key) == EMPTY64) break;
+            if (atomicCAS(&t.slots[h].key, EMPTY64, key) == EMPTY64) break;
             h = (h + 1) & t.cap_mask;
         }
-        t.jid[h] = (uint32_t)j;
+        Slot *s = &t.slots[h];
+        s->jid = (uint32_t)j;
+        for (uint32_t r = 0; r < DENSE_ROWS - 1; ++r) s->base[r] = old_slots[was].base[r];
         t.jslot[j] = (uint32_t)h;
     }
 }
 
 void launch_settle_counters(const Tables &t, cudaStream_t st) { k_settle_counters<<<1, 1, 0, st>>>(t); }
-void launch_rehash(const Tables &t, cudaStream_t st) { k_rehash<<<148 * 4, 256, 0, st>>>(t); }
+void launch_rehash(const Tables &t, const Slot *old_slots, cudaStream_t st) {
+    k_init_slots<<<148 * 8, 256, 0, st>>>(t.slots, t.cap_mask + 1);
+    k_rehash<<<148 * 4, 256, 0, st>>>(t, old_slots);
+}
 
 /* ------------------------------------------------------------------ K2: keyed aggregation */
 __device__ __forceinline__ Event load_event(const Event *ev, uint64_t i, bool valid, int lane) {
@@ -200,7 +214,8 @@ struct FoldCache {
     int32_t tid[FOLD_WAYS];
     uint32_t cnt[3][FOLD_WAYS];
     uint32_t a0[FOLD_WAYS], a1[FOLD_WAYS];
-    uint32_t base[FOLD_WAYS]; /* first offset of the junction's dense row */
+    uint32_t slot[FOLD_WAYS];                   /* the junction's hash slot: the home of its row bases */
+    uint32_t base[DENSE_ROWS - 1][FOLD_WAYS];   /* first offsets of the junction's dense rows 1 .. (copy of the slot's) */
     unsigned long long stage[LOG_STAGE];
 };
 
@@ -258,7 +273,8 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
             const bool is_leader = valid && lane == leader;
             const int way = (int)((junction_hash(e.key, e.tid) >> 40) & (FOLD_WAYS - 1));
             /* ---- the group's junction: from the cache, else from the table ---- */
-            uint32_t jid = JID_NONE, dbase = 0u;
+            uint32_t jid = JID_NONE, gslot = 0u;
+            uint32_t rb[DENSE_ROWS - 1] = {BASE_UNSET, BASE_UNSET, BASE_UNSET}; /* bases of the junction's dense rows 1 .. */
             unsigned long long T = EMPTY64;
             bool cached = false;
             const unsigned leaders = __ballot_sync(0xFFFFFFFFu, is_leader);
@@ -272,7 +288,8 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
                     if (ck == e.key && (!t.kl.wide || c.tid[way] == e.tid)) {
                         hit = cached = true;
                         jid = c.jid[way];
-                        dbase = c.base[way];
+                        gslot = c.slot[way];
+                        rb[0] = c.base[0][way]; rb[1] = c.base[1][way]; rb[2] = c.base[2][way];
                         if (MODE == MODE_PASS2) T = c.first[0][way];
                     } else if (ck != EMPTY64) {
                         fold_write_back<MODE>(t, c, way);
@@ -280,14 +297,18 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
                     }
                 }
                 if (!hit) {
-                    jid = junction_probe<MODE != MODE_PASS2>(t, &s_pool, e.key, e.tid);
+                    /* one load of the junction's slot: its id and the bases of its dense rows */
+                    const Found f = junction_probe<MODE != MODE_PASS2>(t, &s_pool, e.key, e.tid);
+                    jid = f.jid;
+                    gslot = f.slot;
+                    rb[0] = f.base[0]; rb[1] = f.base[1]; rb[2] = f.base[2];
                     if (MODE == MODE_PASS2 && jid != JID_NONE) T = *((volatile unsigned long long *)&t.stat[jid].T);
-                    if (MODE != MODE_PASS1 && jid != JID_NONE) dbase = dense_base(t, jid, e.off_cat & 0xFFFFu);
                     if (owner && jid != JID_NONE) {
                         c.key[way] = e.key;
                         c.tid[way] = e.tid;
                         c.jid[way] = jid;
-                        c.base[way] = dbase;
+                        c.slot[way] = gslot;
+                        c.base[0][way] = rb[0]; c.base[1][way] = rb[1]; c.base[2][way] = rb[2];
                         c.cnt[0][way] = c.cnt[1][way] = c.cnt[2][way] = 0u;
                         c.a0[way] = 0xFFFFFFFFu;
                         c.a1[way] = 0u;
@@ -299,7 +320,6 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
             }
             __syncwarp();
             jid = __shfl_sync(0xFFFFFFFFu, jid, leader);
-            dbase = __shfl_sync(0xFFFFFFFFu, dbase, leader);
             cached = __shfl_sync(0xFFFFFFFFu, (int)cached, leader) != 0;
             const int gway = __shfl_sync(0xFFFFFFFFu, way, leader);
             const bool found = valid && jid != JID_NONE;
@@ -338,7 +358,26 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
                     }
                 }
                 const uint32_t off = e.off_cat & 0xFFFFu;
-                const bool in_row = in_dense_row(t, dbase, off);
+                /* row 0 takes the offsets below DENSE_W: nothing else to look at */
+                uint32_t place = (off < DENSE_W && t.dense != nullptr) ? off : DENSE_NONE;
+                const bool later = counted && off >= DENSE_W && t.dense != nullptr && t.extra_rows;
+                if (__any_sync(0xFFFFFFFFu, later)) {
+                    /* a later junction of its read: the junction's extra rows (their bases travel from the leader) */
+                    gslot = __shfl_sync(0xFFFFFFFFu, gslot, leader);
+                    rb[0] = __shfl_sync(0xFFFFFFFFu, rb[0], leader);
+                    rb[1] = __shfl_sync(0xFFFFFFFFu, rb[1], leader);
+                    rb[2] = __shfl_sync(0xFFFFFFFFu, rb[2], leader);
+                    if (later) {
+                        const uint32_t was[DENSE_ROWS - 1] = {rb[0], rb[1], rb[2]};
+                        place = dense_place(t, gslot, rb, off);
+                        if (cached) {
+                            /* rows given out just now: later chunks find them in the cache */
+#pragma unroll
+                            for (uint32_t r = 0; r < DENSE_ROWS - 1; ++r)
+                                if (rb[r] != was[r]) c.base[r][gway] = rb[r];
+                        }
+                    }
+                }
                 if (counted) {
                     if (cached) {
                         if (e.a0 < c.a0[gway]) atomicMin(&c.a0[gway], e.a0);
@@ -347,9 +386,9 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
                         stat_anchor(s, e.a0, e.a1);
                     }
                     /* Junction::count_read's push_back (junctions.hh:163-167), run-length form */
-                    if (in_row) atomicAdd(&t.dense[(uint64_t)jid * DENSE_W + (off - dbase)], 1u);
+                    if (place != DENSE_NONE) atomicAdd(&t.dense[(uint64_t)jid * (DENSE_ROWS * DENSE_W) + place], 1u);
                 }
-                log_append(t, log, counted && !in_row, olog_entry(jid, off, 1u));
+                log_append(t, log, counted && place == DENSE_NONE, olog_entry(jid, off, 1u));
             }
             /* events that could not be folded go back to the front of the region (behind what was read already) */
             const unsigned km = __ballot_sync(0xFFFFFFFFu, keep);

@@ -2,7 +2,8 @@
  * std::map<JunctionKey, Junction*> (junctions.hh:225-246) and Junction::read_offsets (junctions.hh:120).
  *
  * Layout in HBM (for real data a few tens of MB are live, i.e. mostly resident in the 126 MB L2):
- *   hash slots     keys[cap] (open addressing, linear probing) -> jid[cap], the junction id of the slot's key
+ *   hash slots     slots[cap] (open addressing, linear probing): 32 bytes = one sector: key, the junction id of the key
+ *                  and the first offsets of the junction's extra dense rows, so that one load answers a probe
  *   junction rows  indexed by junction id = order of first insertion, so everything a junction owns is COMPACT:
  *                  jkey / jtid / jslot (identity), JStat (64-byte record: per-strand-class first sequence numbers, the
  *                  creation threshold T, read counts by category, min anchor start, max anchor end), a dense row of
@@ -49,12 +50,13 @@ static const uint32_t ID_BLOCK = 64;
 static const uint32_t N_ID_POOLS = 1024; /* inserting kernels run at most this many thread blocks */
 static const uint32_t SLOT_NONE = 0xFFFFFFFFu;
 static const uint32_t BASE_UNSET = 0xFFFFFFFFu;
-/* The dense row of a junction counts the offsets [base, base + DENSE_W): base is fixed by the first read that is
- * counted into the junction.  An offset below DENSE_W gives base 0 (first junctions of short reads: offset = length of
- * the read's first aligned run); a larger one -- second junctions, whose offsets include the first intron -- centres
- * the window on itself: the reads through one pair of junctions differ in their start by less than a read length, so
- * their offsets form a cluster narrower than the window, and whichever of them comes first (thread blocks take tiles
- * of the stream concurrently) the cluster fits around it. */
+/* A junction owns DENSE_ROWS dense rows of DENSE_W counters.  Row 0 counts the offsets [0, DENSE_W): first junctions of
+ * short reads (offset = length of the read's first aligned run).  The offsets of a read's later junctions include the
+ * introns before them; the reads through one chain of junctions differ in their start by less than a read length, so
+ * those offsets form a cluster narrower than a row per chain.  Rows 1 .. DENSE_ROWS - 1 are given out to such clusters
+ * as they show up: the first offset no row takes yet centres the next free row on itself (slot.base[r - 1]), and from
+ * then on the row takes [base, base + DENSE_W) less what earlier rows take.  What no row takes goes to the log. */
+static const uint32_t DENSE_ROWS = 4;
 static const uint32_t DENSE_LEAD = DENSE_W / 2;
 static const int SV_ORD_BITS = 20;
 static const int SV_SEQ_SHIFT = 28;
@@ -147,17 +149,29 @@ IPX_HD uint64_t mix64(uint64_t x) {
 IPX_HD uint64_t junction_hash(uint64_t key, int32_t tid) { return mix64(key ^ ((uint64_t)(uint32_t)tid * 0x9E3779B97F4A7C15ull)); }
 
 /* device-side view of the tables, passed to kernels by value */
+/* one hash slot: a 32-byte sector */
+#if defined(__CUDACC__)
+struct __align__(32) Slot {
+#else
+struct alignas(32) Slot {
+#endif
+    unsigned long long key;         /* key64 or EMPTY64 */
+    uint32_t jid;                   /* junction id of the key (JID_UNSET while its inserter publishes it) */
+    uint32_t base[DENSE_ROWS - 1];  /* first offset of dense rows 1 .., BASE_UNSET = row not given out */
+    uint32_t pad[2];
+};
+
 struct Tables {
-    unsigned long long *keys; /* [cap] key64 or EMPTY64 */
-    uint32_t *jid;            /* [cap] junction id of the slot's key (JID_UNSET while its inserter publishes it) */
+    Slot *slots;              /* [cap] */
     uint64_t cap_mask;
     /* junction rows, [max_j] each, in order of first insertion */
     unsigned long long *jkey;
     int32_t *jtid;
     uint32_t *jslot;          /* hash slot of the junction's key (for clear) */
     JStat *stat;
-    uint32_t *dense;          /* [max_j][DENSE_W] read counts for offsets obase + [0, DENSE_W), or NULL when disabled */
-    uint32_t *obase;          /* [max_j] first offset of the junction's dense row, BASE_UNSET until a read is counted */
+    uint32_t *dense;          /* [max_j][DENSE_ROWS][DENSE_W] read counts per offset (see DENSE_ROWS), or NULL when disabled */
+    int32_t extra_rows;       /* rows 1 .. are given out (off for long reads, whose offsets scatter: everything >= DENSE_W
+                                 goes to the log then) */
     uint32_t *olog_cnt;       /* entries of the read-offset log that name the junction */
     unsigned long long *id_pools; /* [N_ID_POOLS] first id of the pool's block << 32 | ids taken from it */
     uint64_t max_j;
@@ -224,67 +238,107 @@ __device__ __forceinline__ uint32_t id_pool_take(const Tables &t, IdPool *p) {
     }
 }
 
-/* Find the junction id of (key, tid); INSERT: claim a slot and a junction row when absent.  Returns JID_NONE when the
- * key is absent (lookup) or when no slot / row is left (insert: the overflow flag is raised, the caller keeps the event).
+/* what a probe learns in its one load of the slot */
+struct Found {
+    uint32_t jid;  /* JID_NONE: absent (lookup) or no room (insert) */
+    uint32_t slot;
+    uint32_t base[DENSE_ROWS - 1];
+};
+
+__device__ __forceinline__ void load_slot(const Slot *s, unsigned long long &key, uint32_t &jid, uint32_t base[DENSE_ROWS - 1]) {
+    uint4 a, b;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(s));
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"((const char *)s + 16));
+    key = ((unsigned long long)a.y << 32) | a.x;
+    jid = a.z;
+    base[0] = a.w;
+    base[1] = b.x;
+    base[2] = b.y;
+}
+
+/* Find the junction of (key, tid); INSERT: claim a slot and a junction row when absent.  jid == JID_NONE when the key is
+ * absent (lookup) or when no slot / row is left (insert: the overflow flag is raised, the caller keeps the event).
  * The junction rows of ids never handed out hold the reset values (init / clear), so an inserter has nothing to
  * initialise but the identity. */
 template <bool INSERT>
-__device__ __forceinline__ uint32_t junction_probe(const Tables &t, IdPool *pool, unsigned long long key, int32_t tid) {
+__device__ __forceinline__ Found junction_probe(const Tables &t, IdPool *pool, unsigned long long key, int32_t tid) {
+    Found f;
+    f.jid = JID_NONE;
+    f.slot = 0u;
+    f.base[0] = f.base[1] = f.base[2] = BASE_UNSET;
     uint64_t h = junction_hash(key, tid) & t.cap_mask;
     for (uint32_t probe = 0; probe < MAX_PROBE; ++probe) {
-        unsigned long long k = *((volatile unsigned long long *)&t.keys[h]);
+        Slot *s = &t.slots[h];
+        unsigned long long k;
+        uint32_t j;
+        load_slot(s, k, j, f.base);
+        f.slot = (uint32_t)h;
         if (k == EMPTY64) {
-            if (!INSERT) return JID_NONE;
-            k = atomicCAS(&t.keys[h], EMPTY64, key);
+            if (!INSERT) return f;
+            k = atomicCAS(&s->key, EMPTY64, key);
             if (k == EMPTY64) {
-                const uint32_t j = id_pool_take(t, pool);
+                j = id_pool_take(t, pool);
                 if (j >= t.max_j) {
-                    /* no row left: the slot stays claimed (it is re-used by the rehash that follows the growth) */
-                    *((volatile uint32_t *)&t.jid[h]) = JID_FULL;
+                    /* no row left: the slot stays claimed (it is dropped by the rehash that follows the growth) */
+                    *((volatile uint32_t *)&s->jid) = JID_FULL;
                     atomicOr(t.overflow, OVF_TABLE);
-                    return JID_NONE;
+                    return f;
                 }
                 t.jkey[j] = key;
                 t.jtid[j] = tid;
                 t.jslot[j] = (uint32_t)h;
                 /* Whoever meets the id reads jtid in the wide layout only: there the identity must be visible before
-                 * the id is.  (jkey / jslot are read by later kernels; the record and the offset row are already in
-                 * their reset state.) */
+                 * the id is.  (jkey / jslot are read by later kernels; the record and the offset rows are already in
+                 * their reset state, and so are the slot's row bases.) */
                 if (t.kl.wide) __threadfence();
-                *((volatile uint32_t *)&t.jid[h]) = j;
-                return j;
+                *((volatile uint32_t *)&s->jid) = j;
+                f.jid = j;
+                f.base[0] = f.base[1] = f.base[2] = BASE_UNSET;
+                return f;
             }
+            j = JID_UNSET; /* somebody else claimed it in the meantime: look again below */
         }
         if (k == key) {
-            uint32_t j;
-            do {
-                j = *((volatile uint32_t *)&t.jid[h]);
-            } while (j == JID_UNSET);
+            while (j == JID_UNSET) load_slot(s, k, j, f.base);
             if (j == JID_FULL) {
-                if (INSERT && !t.kl.wide) return JID_NONE; /* the same key met the full table before (flag already raised) */
+                if (INSERT && !t.kl.wide) return f; /* the same key met the full table before (flag already raised) */
             } else if (!t.kl.wide || *((volatile int32_t *)&t.jtid[j]) == tid) {
-                return j;
+                f.jid = j;
+                return f;
             }
         }
         h = (h + 1) & t.cap_mask;
     }
     if (INSERT) atomicOr(t.overflow, OVF_TABLE);
-    return JID_NONE;
+    return f;
 }
 
-/* first offset of junction j's dense row: set by whoever asks first (every asker proposes the window that suits the
- * offset in its hand), the same for everybody afterwards */
-__device__ __forceinline__ uint32_t dense_base(const Tables &t, uint32_t j, uint32_t offset) {
-    uint32_t b = *((volatile uint32_t *)&t.obase[j]);
-    if (b == BASE_UNSET) {
-        const uint32_t mine = offset < DENSE_W ? 0u : offset - DENSE_LEAD;
-        b = atomicCAS(&t.obase[j], BASE_UNSET, mine);
-        if (b == BASE_UNSET) b = mine;
+/* Which dense counter takes `offset` for the junction in `slot`: row * DENSE_W + index, or DENSE_NONE (-> the log).
+ * base[] is the caller's copy of the slot's row bases; a row given out here is written back to it. */
+static const uint32_t DENSE_NONE = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t dense_place(const Tables &t, uint32_t slot, uint32_t base[DENSE_ROWS - 1], uint32_t offset) {
+    if (t.dense == nullptr) return DENSE_NONE;
+    if (offset < DENSE_W) return offset;
+    if (!t.extra_rows) return DENSE_NONE;
+#pragma unroll
+    for (uint32_t r = 0; r < DENSE_ROWS - 1; ++r) {
+        if (base[r] == BASE_UNSET) {
+            /* the next free row: centre it on this offset, unless somebody was faster */
+            const uint32_t mine = offset - DENSE_LEAD;
+            const uint32_t old = atomicCAS(&t.slots[slot].base[r], BASE_UNSET, mine);
+            base[r] = old == BASE_UNSET ? mine : old;
+        }
+        if (offset >= base[r] && offset - base[r] < DENSE_W) return (r + 1u) * DENSE_W + (offset - base[r]);
     }
-    return b;
+    return DENSE_NONE;
 }
-__device__ __forceinline__ bool in_dense_row(const Tables &t, uint32_t base, uint32_t offset) {
-    return t.dense != nullptr && offset >= base && offset - base < DENSE_W;
+/* the same test against bases that are known to be complete (no row is given out) */
+__device__ __forceinline__ uint32_t dense_find(const uint32_t base[DENSE_ROWS - 1], uint32_t offset) {
+    if (offset < DENSE_W) return offset;
+#pragma unroll
+    for (uint32_t r = 0; r < DENSE_ROWS - 1; ++r)
+        if (base[r] != BASE_UNSET && offset >= base[r] && offset - base[r] < DENSE_W) return (r + 1u) * DENSE_W + (offset - base[r]);
+    return DENSE_NONE;
 }
 
 /* Per-warp writer of the read-offset log: entries are staged in shared memory (LOG_STAGE of them) and written out
