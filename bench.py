@@ -623,74 +623,108 @@ def main():
 
     # ---- N = 1 extras: reference on the prefix, parity, the other configs, the tools end to end ----
     cpu_line = parity = other = cli = None
+    extras_errors = []
     ok = True
+
+    def attempt(what, fn):
+        """An extra that fails is reported in the line (and fails the run) instead of taking the headline with it."""
+        nonlocal ok
+        try:
+            return fn()
+        except Exception as e:  # noqa: BLE001 -- whatever went wrong is recorded
+            import traceback
+            traceback.print_exc()
+            extras_errors.append("%s: %s: %s" % (what, type(e).__name__, str(e)[-400:]))
+            ok = False
+            return None
+
     if extras:
         try:
             del devc, compact
             table.close()
             torch.cuda.empty_cache()
-            t_ref, want, _ = run_tool(REF_BIN, os.path.join(tmpdir, "ref_sample"), [sample_bam])
-            dec_s = time_decode(sample_bam)
-            cpu_line = {"value": sample / t_ref, "unit": UNIT, "cores": 1, "kind": "reference",
-                        "sample": "first %d records of the workload as uncompressed BAM in tmpfs; whole CLI run %.2f s of which "
-                                  "record decode alone %.2f s" % (sample, t_ref, dec_s),
-                        "host_cores_available": os.cpu_count()}
-            log("reference on %d records: %.2f s" % (sample, t_ref))
-            # the GPU path over the same records through the C ABI
-            cut = int(host["cigar_off"][sample])
-            part = {k: host[k][:sample] for k in ("tid", "pos", "flag", "nh_class", "xs")}
-            part["cigar_off"] = host["cigar_off"][:sample + 1]
-            part["cigar"] = host["cigar"][:cut]
-            pc = _native.Engine.compact_columns({k: v.numpy() for k, v in part.items()})
             eng.close()
             eng = None
-            pe = _native.Engine(device=local)  # a fresh handle: sjN numbering continues across the flushes of one
-            pe.set_targets(names)
-            pe.push_compact(pc)
-            t = pe.flush()
-            got = {"introns.tsv": t.tsv_header() + t.text_by_target(_native.FMT_INTRON_TSV, 1.0),
-                   "juncs.bed": t.text_by_target(_native.FMT_JUNCTION_BED, 1.0),
-                   "introns.bed": t.text_by_target(_native.FMT_INTRON_BED9, 1.0)}
-            parity = compare_outputs(got, want)
-            parity.update({"records": sample, "junctions": int(t.n), "how": "ipx_push_batch_compact + ipx_flush + ipx_format vs the files "
-                           "the reference binary wrote for the same records (-c -j -n, -C 1.0)"})
-            t.close()
-            pe.close()
-            ok = ok and parity["identical"]
-            log("parity on %d records: %s" % (sample, parity["identical"]))
-            os.unlink(sample_bam)
+
+            def reference_and_parity():
+                nonlocal cpu_line, parity, ok
+                t_ref, want, _ = run_tool(REF_BIN, os.path.join(tmpdir, "ref_sample"), [sample_bam])
+                dec_s = time_decode(sample_bam)
+                cpu_line = {"value": sample / t_ref, "unit": UNIT, "cores": 1, "kind": "reference",
+                            "sample": "first %d records of the workload as uncompressed BAM in tmpfs; whole CLI run %.2f s of which "
+                                      "record decode alone %.2f s" % (sample, t_ref, dec_s),
+                            "host_cores_available": os.cpu_count()}
+                log("reference on %d records: %.2f s" % (sample, t_ref))
+                # the GPU path over the same records through the C ABI
+                cut = int(host["cigar_off"][sample])
+                part = {k: host[k][:sample] for k in ("tid", "pos", "flag", "nh_class", "xs")}
+                part["cigar_off"] = host["cigar_off"][:sample + 1]
+                part["cigar"] = host["cigar"][:cut]
+                pc = _native.Engine.compact_columns({k: v.numpy() for k, v in part.items()})
+                pe = _native.Engine(device=local)  # a fresh handle: sjN numbering continues across the flushes of one
+                pe.set_targets(names)
+                pe.push_compact(pc)
+                t = pe.flush()
+                got = {"introns.tsv": t.tsv_header() + t.text_by_target(_native.FMT_INTRON_TSV, 1.0),
+                       "juncs.bed": t.text_by_target(_native.FMT_JUNCTION_BED, 1.0),
+                       "introns.bed": t.text_by_target(_native.FMT_INTRON_BED9, 1.0)}
+                parity = compare_outputs(got, want)
+                parity.update({"records": sample, "junctions": int(t.n), "how": "ipx_push_batch_compact + ipx_flush + ipx_format vs the "
+                               "files the reference binary wrote for the same records (-c -j -n, -C 1.0)"})
+                t.close()
+                pe.close()
+                ok = ok and parity["identical"]
+                log("parity on %d records: %s" % (sample, parity["identical"]))
+
+            attempt("reference + parity", reference_and_parity)
+            if os.path.exists(sample_bam):
+                os.unlink(sample_bam)
             del host
-            # the merge's reference run takes ~30 s on one core: start it first, collect it last
-            merge_line, merge_ref, merge_got, merge_err = merge_workload(tmpdir)
-            log("merge: %.1f ms per call" % merge_line["call_ms_host_rows_in_table_out"])
             other = []
-            other.append(extraction_workload(
-                "stranded RF + 3 Gb genome in HBM + canon filter, --min-anchor-length=12, 50 M records (BASELINE configs[2], half its "
-                "records)", 50_000_000, SHORT_STRANDED, tmpdir, torch, dev, peak, 10_000_000, with_genome=True,
+            # the merge's reference run takes ~30 s on one core: start it first, collect it last
+            merge = attempt("merge", lambda: merge_workload(tmpdir))
+            if merge:
+                log("merge: %.1f ms per call" % merge[0]["call_ms_host_rows_in_table_out"])
+
+            def add(what, fn):
+                w = attempt(what, fn)
+                if w:
+                    other.append(w)
+                    log("%s: %.3f ms per step" % (what, w["ms_per_step"]))
+
+            add("stranded", lambda: extraction_workload(
+                "stranded RF + 3 Gb genome in HBM + canon filter, --min-anchor-length=12, 50 M records (BASELINE configs[2], a quarter of "
+                "its records)", 50_000_000, SHORT_STRANDED, tmpdir, torch, dev, peak, 10_000_000, with_genome=True,
                 cli_sets=[("canon", ["--strandness=RF", "--min-anchor-length=12", "--genome-fasta=" + os.path.join(tmpdir, "g.fa")]),
                           ("all", ["--strandness=RF", "--min-anchor-length=12", "--sj-filter=all",
                                    "--genome-fasta=" + os.path.join(tmpdir, "g.fa")])],
                 strandness=_native.STRAND_RF, min_anchor_length=12, junction_filter=_native.FILTER_CANON))
-            log("stranded: %.3f ms per step" % other[-1]["ms_per_step"])
-            other.append(extraction_workload(
+            add("long reads", lambda: extraction_workload(
                 "long reads (~10 kb, ~800 CIGAR operations), 1 M reads, --allow-anchor-indels -C 0.0 (BASELINE configs[3], a fifth of "
                 "its reads)", 1_000_000, LONG, tmpdir, torch, dev, peak, 100_000,
                 cli_sets=[("indels", ["--allow-anchor-indels", "-C", "0.0"]), ("defaults", [])], max_anchor_indel_size=36))
-            log("long reads: %.3f ms per step" % other[-1]["ms_per_step"])
-            other.append(extraction_workload(
+            add("long reads, defaults", lambda: extraction_workload(
                 "the same long reads with default options (no anchor indels)", 1_000_000, LONG, tmpdir, torch, dev, peak, 0, cli_sets=[]))
-            cli = cli_end_to_end(tmpdir, args.cli_records)
-            ok = ok and cli["identical"]
-            log("tools end to end: reference %.1f s, GPU tool %.1f s" % (cli["reference_s"], cli["gpu_tool_s"]))
-            want_m = merge_ref.collect()
-            res = compare_outputs(merge_got, want_m)
-            res["stderr_identical"] = merge_err == merge_ref.stderr
-            res["identical"] = res["identical"] and res["stderr_identical"]
-            res.update({"reference_s": merge_ref.seconds, "how": "GPU intronProspectorMerge vs reference binary on the same 64 files: "
-                        "three output files and the strand-conflict lines on stderr"})
-            merge_line["parity"] = [res]
-            merge_line["cpu_baseline"] = {"value": merge_line["rows"] / merge_ref.seconds, "unit": "rows/s", "cores": 1, "kind": "reference"}
-            other.append(merge_line)
+            cli = attempt("tools end to end", lambda: cli_end_to_end(tmpdir, args.cli_records))
+            if cli:
+                ok = ok and cli["identical"]
+                log("tools end to end: reference %.1f s, GPU tool %.1f s" % (cli["reference_s"], cli["gpu_tool_s"]))
+            if merge:
+                merge_line, merge_ref, merge_got, merge_err = merge
+
+                def merge_parity():
+                    want_m = merge_ref.collect()
+                    res = compare_outputs(merge_got, want_m)
+                    res["stderr_identical"] = merge_err == merge_ref.stderr
+                    res["identical"] = res["identical"] and res["stderr_identical"]
+                    res.update({"reference_s": merge_ref.seconds, "how": "GPU intronProspectorMerge vs reference binary on the same 64 "
+                                "files: three output files and the strand-conflict lines on stderr"})
+                    merge_line["parity"] = [res]
+                    merge_line["cpu_baseline"] = {"value": merge_line["rows"] / merge_ref.seconds, "unit": "rows/s", "cores": 1,
+                                                  "kind": "reference"}
+
+                attempt("merge parity", merge_parity)
+                other.append(merge_line)
             for w in other:
                 for p in w.get("parity", []):
                     ok = ok and p["identical"]
@@ -750,6 +784,8 @@ def main():
             line["other_workloads"] = other
         if cli is not None:
             line["cli_e2e"] = cli
+        if extras_errors:
+            line["extras_errors"] = extras_errors
         emit(line)
     if eng is not None:
         eng.close()

@@ -1,7 +1,6 @@
 /* ipx_api.cu -- implementation of the C ABI in include/ipx.h on top of the CUDA engine.
  * CUDA-only: every compute entry point fails with IPX_ERR_CUDA when no device is usable.
  */
-#include <cub/cub.cuh> /* the merge fold still orders its keys with the library sort */
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -10,8 +9,10 @@
 #include <time.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -137,6 +138,21 @@ struct StageTimer {
     uint64_t launches = 0;
 };
 
+/* what ipx_merge_rows_fold keeps between calls: the intron table, its counters, the upload lanes */
+struct MergeWork {
+    Tables tab{};              /* slots, jkey / jtid / jslot, counters; the wide key layout */
+    MStat *stat = nullptr;     /* [max_j] */
+    uint8_t *slow_of_id = nullptr; /* [max_j] introns the host folds */
+    unsigned long long *counters = nullptr; /* n_keys, overflow, n_unfolded, n_slow, d_count[8] (16 words apart), id pools from 128 */
+    unsigned long long *h_state = nullptr;  /* pinned, 16 words */
+    struct Lane {
+        cudaStream_t st;
+        void *stage[2];
+        cudaEvent_t free_ev[2];
+    };
+    std::vector<Lane> lanes;
+};
+
 static const size_t COUNTER_WORDS = 16 * 16 + 1024; /* 16 cache lines of counters and flags, then the pools of junction ids */
 
 }  // namespace
@@ -224,8 +240,7 @@ struct ipx_handle {
     uint32_t ijunc_base = 0;
 
     /* merge */
-    MergeTables mt{};
-    uint64_t mt_cap = 0;
+    MergeWork mw;
 
     /* timings */
     StageTimer tm_extract, tm_aggregate, tm_motif, tm_finalize, tm_merge;
@@ -715,6 +730,7 @@ extern "C" int ipx_create(const ipx_params *params, ipx_handle **out) {
 }
 
 static void mailbox_release(ipx_handle *h);
+namespace { void merge_release(MergeWork &m); }
 
 extern "C" void ipx_destroy(ipx_handle *h) {
     if (!h) return;
@@ -731,7 +747,7 @@ extern "C" void ipx_destroy(ipx_handle *h) {
     h->s_off.release(); h->s_cig.release(); h->s_nops.release(); h->s_runs.release(); h->s_tmp.release(); h->ev_buf.release(); h->tile_cnt.release(); h->jrow_of.release(); h->jid_of.release();
     finalize_release(h->fw);
     mailbox_release(h);
-    cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
+    merge_release(h->mw);
     for (auto &e : h->upload_done)
         if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -1717,21 +1733,146 @@ extern "C" int ipx_count_deferred(ipx_handle *h) {
 /* ------------------------------------------------------------------ merge */
 namespace {
 
-struct MergeJ {
-    int32_t chrom;
-    uint32_t i0, i1, a0, a1;
-    char strand;
-    uint32_t site;
-    uint64_t cnt[3];
-    float conf;
-};
-
 std::string describe(const ipx_handle *h, const ipx_merge_rows *rows, int32_t chrom, uint32_t s, uint32_t e, char strand,
                      uint32_t site) {
     /* Junction::get_description (junctions.cc:72-74); mk_coords_str prints ints */
     char buf[512];
     snprintf(buf, sizeof(buf), "%s:%d-%d[%c/%s]", h->targets[chrom].c_str(), (int)s, (int)e, strand, rows->site_strings[site]);
     return buf;
+}
+
+/* bytes of one merge row over the link: chrom, start, end, anchors, sites, confidence (4 each), counts (12), strand (1) */
+const uint64_t MERGE_ROW_BYTES = 41;
+const uint64_t MERGE_CHUNK = 1ull << 20; /* rows per upload chunk */
+
+void merge_free_table(MergeWork &m) {
+    cudaFree(m.tab.slots); cudaFree(m.tab.jkey); cudaFree(m.tab.jtid); cudaFree(m.tab.jslot); cudaFree(m.stat); cudaFree(m.slow_of_id);
+    m.tab.slots = nullptr; m.tab.jkey = nullptr; m.tab.jtid = nullptr; m.tab.jslot = nullptr; m.stat = nullptr; m.slow_of_id = nullptr;
+    m.tab.max_j = 0;
+}
+
+void merge_release(MergeWork &m) {
+    merge_free_table(m);
+    cudaFree(m.counters);
+    m.counters = nullptr;
+    for (auto &l : m.lanes) {
+        if (l.stage[0]) cudaFreeHost(l.stage[0]);
+        if (l.stage[1]) cudaFreeHost(l.stage[1]);
+        if (l.free_ev[0]) cudaEventDestroy(l.free_ev[0]);
+        if (l.free_ev[1]) cudaEventDestroy(l.free_ev[1]);
+        if (l.st) cudaStreamDestroy(l.st);
+    }
+    m.lanes.clear();
+    if (m.h_state) cudaFreeHost(m.h_state);
+    m.h_state = nullptr;
+}
+
+/* the intron table of the merge fold: `max_j` intron rows, twice as many hash slots */
+int merge_alloc_table(ipx_handle *h, uint64_t max_j) {
+    MergeWork &m = h->mw;
+    if (!m.counters) {
+        CU(h, cudaMalloc(&m.counters, (128 + N_ID_POOLS) * sizeof(unsigned long long)));
+        CU(h, cudaMemsetAsync(m.counters, 0, (128 + N_ID_POOLS) * sizeof(unsigned long long), h->stream));
+        CU(h, cudaMallocHost(&m.h_state, 16 * sizeof(unsigned long long)));
+    }
+    if (m.tab.max_j >= max_j) return IPX_OK;
+    merge_free_table(m);
+    if (max_j >> 31) return fail(h, IPX_ERR_CAPACITY, "more than 2^31 introns");
+    Tables &t = m.tab;
+    CU(h, cudaMalloc(&t.slots, 2 * max_j * sizeof(Slot)));
+    CU(h, cudaMalloc(&t.jkey, max_j * sizeof(unsigned long long)));
+    CU(h, cudaMalloc(&t.jtid, max_j * sizeof(int32_t)));
+    CU(h, cudaMalloc(&t.jslot, max_j * sizeof(uint32_t)));
+    CU(h, cudaMalloc(&m.stat, max_j * sizeof(MStat)));
+    CU(h, cudaMalloc(&m.slow_of_id, max_j));
+    t.cap_mask = 2 * max_j - 1;
+    t.max_j = max_j;
+    t.n_keys = m.counters + 0;
+    t.overflow = (uint32_t *)(m.counters + 16);
+    t.id_pools = m.counters + 128;
+    t.kl = make_key_layout(31, 0);
+    t.kl.wide = 1; /* the chromosome is compared beside the (start, end) key */
+    return IPX_OK;
+}
+
+/* Host rows -> device columns.  The rows are ordinary (pageable) memory: worker threads copy chunk after chunk into
+ * pinned staging blocks and send them on streams of their own, so that staging, the link and the fold of the chunks
+ * that have arrived overlap.  chunk_ready[c] is recorded behind chunk c's copies. */
+struct MergeUpload {
+    std::vector<cudaEvent_t> chunk_ready;
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<char> issued; /* chunk c's copies are enqueued (its event may be waited for) */
+    cudaError_t err = cudaSuccess;
+    ~MergeUpload() {
+        for (auto &w : workers) w.join();
+        for (auto e : chunk_ready) cudaEventDestroy(e);
+    }
+};
+
+struct MergeColumns {
+    DeviceBuf chrom, i0, i1, a0, a1, strand, sites, counts, conf;
+    cudaError_t reserve(uint64_t n, cudaStream_t st) {
+        cudaError_t e;
+        for (DeviceBuf *b : {&chrom, &i0, &i1, &a0, &a1, &sites, &conf})
+            if ((e = b->reserve(n * 4, st)) != cudaSuccess) return e;
+        if ((e = strand.reserve(n, st)) != cudaSuccess) return e;
+        return counts.reserve(n * 12, st);
+    }
+    void release() {
+        for (DeviceBuf *b : {&chrom, &i0, &i1, &a0, &a1, &strand, &sites, &counts, &conf}) b->release();
+    }
+    MergeRowsView view(uint64_t first, uint64_t n) const {
+        return MergeRowsView{(const int32_t *)chrom.p + first, (const uint32_t *)i0.p + first, (const uint32_t *)i1.p + first,
+                             (const uint32_t *)a0.p + first, (const uint32_t *)a1.p + first, (const char *)strand.p + first,
+                             (const uint32_t *)sites.p + first, (const uint32_t *)counts.p + 3 * first, (const float *)conf.p + first, n, first};
+    }
+};
+
+int merge_lanes(ipx_handle *h, int want) {
+    MergeWork &m = h->mw;
+    while ((int)m.lanes.size() < want) {
+        MergeWork::Lane l{};
+        CU(h, cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CU(h, cudaMallocHost(&l.stage[k], MERGE_CHUNK * MERGE_ROW_BYTES));
+            CU(h, cudaEventCreateWithFlags(&l.free_ev[k], cudaEventDisableTiming));
+        }
+        m.lanes.push_back(l);
+    }
+    return IPX_OK;
+}
+
+void merge_upload_worker(ipx_handle *h, const ipx_merge_rows *rows, const MergeColumns *cols, MergeUpload *up, int lane, int n_lanes) {
+    cudaSetDevice(h->device);
+    MergeWork::Lane &l = h->mw.lanes[lane];
+    const uint64_t n = rows->n_rows, n_chunks = (n + MERGE_CHUNK - 1) / MERGE_CHUNK;
+    int turn = 0;
+    for (uint64_t c = (uint64_t)lane; c < n_chunks; c += (uint64_t)n_lanes, turn ^= 1) {
+        const uint64_t first = c * MERGE_CHUNK, len = std::min<uint64_t>(MERGE_CHUNK, n - first);
+        char *stage = (char *)l.stage[turn];
+        cudaError_t e = cudaEventSynchronize(l.free_ev[turn]); /* the copies that last read this block are done */
+        struct Col { const void *src; void *dst; uint64_t width; };
+        const Col col[9] = {{rows->chrom, cols->chrom.p, 4}, {rows->intron_start, cols->i0.p, 4}, {rows->intron_end, cols->i1.p, 4},
+                            {rows->anchor_start, cols->a0.p, 4}, {rows->anchor_end, cols->a1.p, 4}, {rows->sites, cols->sites.p, 4},
+                            {rows->confidence, cols->conf.p, 4}, {rows->counts, cols->counts.p, 12}, {rows->strand, cols->strand.p, 1}};
+        uint64_t at = 0;
+        for (const Col &k : col) {
+            memcpy(stage + at, (const char *)k.src + first * k.width, len * k.width);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync((char *)k.dst + first * k.width, stage + at, len * k.width, cudaMemcpyHostToDevice, l.st);
+            at += len * k.width;
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(l.free_ev[turn], l.st);
+        if (e == cudaSuccess) e = cudaEventRecord(up->chunk_ready[c], l.st);
+        {
+            std::lock_guard<std::mutex> g(up->mu);
+            if (e != cudaSuccess && up->err == cudaSuccess) up->err = e;
+            up->issued[c] = 1;
+        }
+        up->cv.notify_all();
+    }
 }
 
 }  // namespace
@@ -1743,126 +1884,179 @@ extern "C" int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ip
     cudaSetDevice(h->device);
     if (h->targets.empty()) return fail(h, IPX_ERR_STATE, "ipx_set_targets must be called first");
     cudaStream_t st = h->stream;
+    MergeWork &m = h->mw;
     const uint64_t n = rows->n_rows;
-    /* table sized for the worst case of all rows distinct, load <= 0.5 */
-    uint64_t cap = pow2_at_least(n * 2 + 1024);
-    if (h->mt_cap < cap) {
-        cudaFree(h->mt.keys); cudaFree(h->mt.chrom); cudaFree(h->mt.stat);
-        h->mt = MergeTables{};
-        CU(h, cudaMalloc(&h->mt.keys, cap * 8));
-        CU(h, cudaMalloc(&h->mt.chrom, cap * 4));
-        CU(h, cudaMalloc(&h->mt.stat, cap * sizeof(MStat)));
-        h->mt_cap = cap;
-    }
+    Trace tr;
+    /* The table is sized by introns, not rows: a guess from the row count (tables of the same genes share most of their
+     * introns), grown when the fold runs out of rows.  A table kept from an earlier call is used as it is. */
+    uint64_t want_j = 1ull << 16;
+    while (want_j < n / 16 && want_j < (1ull << 24)) want_j <<= 1;
+    if (const char *e = getenv("IPX_MERGE_ROWS")) want_j = pow2_at_least(strtoull(e, nullptr, 10));
+    int rc = merge_alloc_table(h, want_j);
+    if (rc) return rc;
+    unsigned long long *n_unfolded = m.counters + 32, *n_slow = m.counters + 48, *d_count = m.counters + 64;
+
+    MergeColumns cols;
+    CU(h, cols.reserve(n ? n : 1, st));
+    CU(h, cudaStreamSynchronize(st)); /* the columns exist before other streams write them */
+    const uint64_t n_chunks = (n + MERGE_CHUNK - 1) / MERGE_CHUNK;
     {
-        int rcc = alloc_counters(h);
-        if (rcc) return rcc;
+        /* the spans time the kernels alone: a chunk's span starts after the wait for its upload */
+        {
+            Span s(h, &h->tm_merge, 3);
+            launch_merge_init(m.tab, m.stat, n_unfolded, st);
+        }
+        if (n) {
+            int n_lanes = (int)std::min<uint64_t>(n_chunks, std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2)));
+            if (const char *e = getenv("IPX_MERGE_UPLOAD_THREADS")) n_lanes = std::max(1, std::min(atoi(e), 32));
+            rc = merge_lanes(h, n_lanes);
+            if (rc) return rc;
+            MergeUpload up;
+            up.chunk_ready.resize(n_chunks);
+            up.issued.assign(n_chunks, 0);
+            for (auto &e : up.chunk_ready) CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            for (int l = 0; l < n_lanes; l++) up.workers.emplace_back(merge_upload_worker, h, rows, &cols, &up, l, n_lanes);
+            for (uint64_t c = 0; c < n_chunks; c++) {
+                {
+                    std::unique_lock<std::mutex> g(up.mu);
+                    up.cv.wait(g, [&] { return up.issued[c] != 0; });
+                }
+                cudaStreamWaitEvent(st, up.chunk_ready[c], 0);
+                Span s(h, &h->tm_merge, 1);
+                launch_merge_fold(cols.view(c * MERGE_CHUNK, std::min<uint64_t>(MERGE_CHUNK, n - c * MERGE_CHUNK)), m.tab, m.stat, n_unfolded,
+                                  h->sm_count, st);
+            }
+            tr.mark("merge: folds enqueued");
+            for (auto &w : up.workers) w.join();
+            up.workers.clear();
+            tr.mark("merge: upload threads joined");
+            if (up.err != cudaSuccess) {
+                cols.release();
+                return fail(h, IPX_ERR_CUDA, "CUDA error %s while uploading merge rows", cudaGetErrorName(up.err));
+            }
+            cudaStreamSynchronize(st); /* before the chunk events are destroyed */
+        }
     }
-    h->mt.cap_mask = h->mt_cap - 1;
-    h->mt.n_keys = h->d_counters + 112;
-    h->mt.overflow = (uint32_t *)(h->d_counters + 120);
-    /* upload the row columns */
-    DeviceBuf b_chrom, b_i0, b_i1, b_a0, b_a1, b_strand, b_sites, b_counts, b_conf;
-    const uint64_t na = n ? n : 1;
-    CU(h, b_chrom.reserve(na * 4, h->stream)); CU(h, b_i0.reserve(na * 4, h->stream)); CU(h, b_i1.reserve(na * 4, h->stream)); CU(h, b_a0.reserve(na * 4, h->stream));
-    CU(h, b_a1.reserve(na * 4, h->stream)); CU(h, b_strand.reserve(na, h->stream)); CU(h, b_sites.reserve(na * 4, h->stream)); CU(h, b_counts.reserve(na * 12, h->stream));
-    CU(h, b_conf.reserve(na * 4, h->stream));
-    if (n) {
-        CU(h, cudaMemcpyAsync(b_chrom.p, rows->chrom, n * 4, cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(b_i0.p, rows->intron_start, n * 4, cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(b_i1.p, rows->intron_end, n * 4, cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(b_a0.p, rows->anchor_start, n * 4, cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(b_a1.p, rows->anchor_end, n * 4, cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(b_strand.p, rows->strand, n, cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(b_sites.p, rows->sites, n * 4, cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(b_counts.p, rows->counts, n * 12, cudaMemcpyHostToDevice, st));
-        CU(h, cudaMemcpyAsync(b_conf.p, rows->confidence, n * 4, cudaMemcpyHostToDevice, st));
+    tr.mark("merge: rows uploaded and folded");
+    /* did every row find room?  otherwise: twice the introns, fold everything again (the rows are on the device) */
+    unsigned long long *hs = m.h_state;
+    for (int round = 0;; round++) {
+        CU(h, cudaMemcpyAsync(&hs[0], m.tab.n_keys, 8, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaMemcpyAsync(&hs[1], n_unfolded, 8, cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        if (hs[1] == 0) break;
+        if (round > 20) { cols.release(); return fail(h, IPX_ERR_CAPACITY, "the intron table could not be grown far enough"); }
+        rc = merge_alloc_table(h, m.tab.max_j * 2);
+        if (rc) { cols.release(); return rc; }
+        Span s(h, &h->tm_merge, 4);
+        launch_merge_init(m.tab, m.stat, n_unfolded, st);
+        launch_merge_fold(cols.view(0, n), m.tab, m.stat, n_unfolded, h->sm_count, st);
     }
-    MergeRowsView rv{(const int32_t *)b_chrom.p, (const uint32_t *)b_i0.p, (const uint32_t *)b_i1.p, (const uint32_t *)b_a0.p,
-                     (const uint32_t *)b_a1.p, (const char *)b_strand.p, (const uint32_t *)b_sites.p,
-                     (const uint32_t *)b_counts.p, (const float *)b_conf.p, n, 0};
-    unsigned long long n_keys = 0;
-    {
-        Span s(h, &h->tm_merge, 2);
-        launch_merge_init(h->mt, st);
-        launch_merge_fold(rv, h->mt, h->sm_count, st);
+    const uint64_t B = std::max<uint64_t>(1, std::min<uint64_t>(hs[0], m.tab.max_j)); /* intron ids handed out, holes included */
+
+    /* key order (chromosome-name rank, start, end): the extraction path's sample sort */
+    DeviceBuf k_key, k_sub, order, ss_split, ss_cnt, ss_bk, ss_bs, ss_bv;
+    auto release_sort = [&]() { for (DeviceBuf *b : {&k_key, &k_sub, &order, &ss_split, &ss_cnt, &ss_bk, &ss_bs, &ss_bv}) b->release(); };
+    CU(h, k_key.reserve(B * 8, st)); CU(h, k_sub.reserve(B * 4, st)); CU(h, order.reserve(B * 4, st));
+    CU(h, ss_split.reserve(sample_sort_max_buckets() * 8, st)); CU(h, ss_cnt.reserve((sample_sort_max_buckets() + 1) * 4, st));
+    uint64_t J = 0;
+    for (uint64_t C = 1024;;) {
+        const uint64_t cells = sample_sort_buckets(B) * C;
+        CU(h, ss_bk.reserve(cells * 8, st)); CU(h, ss_bs.reserve(cells * 4, st)); CU(h, ss_bv.reserve(cells * 4, st));
+        SampleSort ss{(unsigned long long *)ss_split.p, (uint32_t *)ss_cnt.p, (unsigned long long *)ss_bk.p, (uint32_t *)ss_bs.p,
+                      (uint32_t *)ss_bv.p, C};
+        {
+            Span s(h, &h->tm_merge, 4);
+            CU(h, cudaMemsetAsync(d_count, 0, 8 * sizeof(unsigned long long), st));
+            launch_merge_keys(m.tab, h->d_name_rank, B, d_count, (unsigned long long *)k_key.p, (uint32_t *)k_sub.p, st);
+            CU(h, sample_sort_enqueue((const unsigned long long *)k_key.p, (const uint32_t *)k_sub.p, d_count + 4, B, ss, (uint32_t *)order.p,
+                                      nullptr, d_count, st));
+        }
+        CU(h, cudaMemcpyAsync(hs, d_count, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU(h, cudaStreamSynchronize(st));
+        if (!(hs[3] & 8ull)) { J = hs[0]; break; }
+        C = std::max<uint64_t>(2 * C, hs[7] + hs[7] / 4); /* a bucket was larger than its cells */
     }
-    CU(h, cudaGetLastError());
-    uint32_t overflow = 0;
-    CU(h, cudaMemcpyAsync(&n_keys, h->mt.n_keys, 8, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaMemcpyAsync(&overflow, h->mt.overflow, 4, cudaMemcpyDeviceToHost, st));
-    CU(h, cudaStreamSynchronize(st));
-    if (overflow) return fail(h, IPX_ERR_CAPACITY, "merge table overflow");
-    const uint64_t J = n_keys, Ja = J ? J : 1;
-    /* key order: (name rank, start, end) via two stable radix passes */
-    DeviceBuf k_hi, k_lo, k_hi2, k_lo2, v_a, v_b, cnt, tmp;
-    CU(h, k_hi.reserve(Ja * 8, h->stream)); CU(h, k_lo.reserve(Ja * 8, h->stream)); CU(h, k_hi2.reserve(Ja * 8, h->stream)); CU(h, k_lo2.reserve(Ja * 8, h->stream));
-    CU(h, v_a.reserve(Ja * 4, h->stream)); CU(h, v_b.reserve(Ja * 4, h->stream)); CU(h, cnt.reserve(8, h->stream));
-    CU(h, cudaMemsetAsync(cnt.p, 0, 8, st));
+    tr.mark("merge: key order");
+    const uint64_t Ja = J ? J : 1;
     HostTable *ht = new HostTable();
     memset(&ht->t, 0, sizeof(ht->t));
     std::vector<uint32_t> site;
     std::vector<uint8_t> slow;
     std::vector<unsigned long long> counts;
     {
-        Span s(h, &h->tm_merge, 6);
-        launch_merge_compact(h->mt, (unsigned long long *)cnt.p, (unsigned long long *)k_lo.p, (uint32_t *)v_a.p, st);
-        if (J) {
-            /* LSD order: stable sort by (start, end), then stable sort by chromosome-name rank */
-            size_t tb1 = 0, tb2 = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, tb1, (unsigned long long *)k_lo.p, (unsigned long long *)k_lo2.p,
-                                            (uint32_t *)v_a.p, (uint32_t *)v_b.p, (int)J, 0, 64, st);
-            cub::DeviceRadixSort::SortPairs(nullptr, tb2, (unsigned long long *)k_hi.p, (unsigned long long *)k_hi2.p,
-                                            (uint32_t *)v_b.p, (uint32_t *)v_a.p, (int)J, 0, 32, st);
-            CU(h, tmp.reserve(std::max(tb1, tb2), h->stream));
-            size_t tb = tmp.cap;
-            cub::DeviceRadixSort::SortPairs(tmp.p, tb, (unsigned long long *)k_lo.p, (unsigned long long *)k_lo2.p,
-                                            (uint32_t *)v_a.p, (uint32_t *)v_b.p, (int)J, 0, 64, st);
-            launch_merge_rank_keys(h->mt, h->d_name_rank, (const uint32_t *)v_b.p, J, (unsigned long long *)k_hi.p, st);
-            tb = tmp.cap;
-            cub::DeviceRadixSort::SortPairs(tmp.p, tb, (unsigned long long *)k_hi.p, (unsigned long long *)k_hi2.p,
-                                            (uint32_t *)v_b.p, (uint32_t *)v_a.p, (int)J, 0, 32, st);
-        }
         DeviceBuf o_chrom, o_i0, o_i1, o_a0, o_a1, o_site, o_counts, o_conf, o_strand, o_slow;
-        CU(h, o_chrom.reserve(Ja * 4, h->stream)); CU(h, o_i0.reserve(Ja * 4, h->stream)); CU(h, o_i1.reserve(Ja * 4, h->stream)); CU(h, o_a0.reserve(Ja * 4, h->stream));
-        CU(h, o_a1.reserve(Ja * 4, h->stream)); CU(h, o_site.reserve(Ja * 4, h->stream)); CU(h, o_counts.reserve(Ja * 24, h->stream)); CU(h, o_conf.reserve(Ja * 4, h->stream));
-        CU(h, o_strand.reserve(Ja, h->stream)); CU(h, o_slow.reserve(Ja, h->stream));
-        MergeOut mo{(int32_t *)o_chrom.p, (uint32_t *)o_i0.p, (uint32_t *)o_i1.p, (uint32_t *)o_a0.p, (uint32_t *)o_a1.p,
-                    (uint32_t *)o_site.p, (unsigned long long *)o_counts.p, (float *)o_conf.p, (char *)o_strand.p,
-                    (uint8_t *)o_slow.p};
-        launch_merge_gather(h->mt, (const uint32_t *)v_a.p, J, mo, st);
         cudaError_t e = cudaSuccess;
         auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+        chk(o_chrom.reserve(Ja * 4, st)); chk(o_i0.reserve(Ja * 4, st)); chk(o_i1.reserve(Ja * 4, st)); chk(o_a0.reserve(Ja * 4, st));
+        chk(o_a1.reserve(Ja * 4, st)); chk(o_site.reserve(Ja * 4, st)); chk(o_counts.reserve(Ja * 24, st)); chk(o_conf.reserve(Ja * 4, st));
+        chk(o_strand.reserve(Ja, st)); chk(o_slow.reserve(Ja, st));
+        if (e == cudaSuccess) {
+            Span s(h, &h->tm_merge, 1);
+            MergeOut mo{(int32_t *)o_chrom.p, (uint32_t *)o_i0.p, (uint32_t *)o_i1.p, (uint32_t *)o_a0.p, (uint32_t *)o_a1.p,
+                        (uint32_t *)o_site.p, (unsigned long long *)o_counts.p, (float *)o_conf.p, (char *)o_strand.p,
+                        (uint8_t *)o_slow.p};
+            chk(cudaMemsetAsync(m.slow_of_id, 0, m.tab.max_j, st));
+            launch_merge_gather(m.tab, m.stat, (const uint32_t *)order.p, J, mo, m.slow_of_id, st);
+        }
         chk(d2h(ht->chrom, o_chrom.p, J, st)); chk(d2h(ht->i0, o_i0.p, J, st)); chk(d2h(ht->i1, o_i1.p, J, st));
         chk(d2h(ht->a0, o_a0.p, J, st)); chk(d2h(ht->a1, o_a1.p, J, st)); chk(d2h(site, o_site.p, J, st));
         chk(d2h(counts, o_counts.p, J * 3, st)); chk(d2h(ht->conf, o_conf.p, J, st)); chk(d2h(ht->strand, o_strand.p, J, st));
         chk(d2h(slow, o_slow.p, J, st));
         chk(cudaStreamSynchronize(st));
         chk(cudaGetLastError());
-        o_chrom.release(); o_i0.release(); o_i1.release(); o_a0.release(); o_a1.release(); o_site.release();
-        o_counts.release(); o_conf.release(); o_strand.release(); o_slow.release();
+        for (DeviceBuf *b : {&o_chrom, &o_i0, &o_i1, &o_a0, &o_a1, &o_site, &o_counts, &o_conf, &o_strand, &o_slow}) b->release();
+        release_sort();
         if (e != cudaSuccess) {
             delete ht;
+            cols.release();
             return fail(h, IPX_ERR_CUDA, "CUDA error %s in merge: %s", cudaGetErrorName(e), cudaGetErrorString(e));
         }
     }
-    for (DeviceBuf *b : {&b_chrom, &b_i0, &b_i1, &b_a0, &b_a1, &b_strand, &b_sites, &b_counts, &b_conf, &k_hi, &k_lo, &k_hi2,
-                         &k_lo2, &v_a, &v_b, &cnt, &tmp})
-        b->release();
     ht->counts.assign(counts.begin(), counts.end());
+    tr.mark("merge: table to host");
 
-    /* introns whose fold depends on row order: redo them exactly as Junction::merge does (junctions.cc:76-105) */
+    /* Introns whose fold depends on row order: the device picks their rows out of the input, the host folds those in
+     * row order exactly as Junction::merge does (junctions.cc:76-105). */
     std::string log;
     std::unordered_map<uint64_t, std::vector<uint64_t>> slow_by_key; /* (start << 32 | end) -> table rows */
-    uint64_t n_slow = 0;
+    uint64_t n_slow_introns = 0;
     for (uint64_t i = 0; i < J; i++)
         if (slow[i]) {
             slow_by_key[((uint64_t)ht->i0[i] << 32) | ht->i1[i]].push_back(i);
-            n_slow++;
+            n_slow_introns++;
         }
-    if (n_slow) {
+    std::vector<unsigned long long> slow_rows;
+    if (n_slow_introns) {
+        DeviceBuf d_rows;
+        for (uint64_t cap = std::min<uint64_t>(n, 1ull << 16);;) {
+            cudaError_t e = d_rows.reserve(cap * 8, st);
+            if (e == cudaSuccess) e = cudaMemsetAsync(n_slow, 0, 8, st);
+            if (e == cudaSuccess) {
+                Span s(h, &h->tm_merge, 1);
+                launch_merge_slow_rows(cols.view(0, n), m.tab, m.slow_of_id, n_slow, cap, (unsigned long long *)d_rows.p, h->sm_count, st);
+                e = cudaMemcpyAsync(&hs[0], n_slow, 8, cudaMemcpyDeviceToHost, st);
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e == cudaSuccess && hs[0] <= cap) {
+                e = d2h(slow_rows, d_rows.p, hs[0], st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            }
+            if (e != cudaSuccess) {
+                d_rows.release(); cols.release();
+                delete ht;
+                return fail(h, IPX_ERR_CUDA, "CUDA error %s in merge: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+            }
+            if (hs[0] <= cap) break;
+            cap = hs[0];
+        }
+        d_rows.release();
+        std::sort(slow_rows.begin(), slow_rows.end());
+    }
+    cols.release();
+    if (n_slow_introns) {
         std::vector<char> started(J, 0);
-        for (uint64_t r = 0; r < n; r++) {
+        for (uint64_t r : slow_rows) {
             auto it = slow_by_key.find(((uint64_t)rows->intron_start[r] << 32) | rows->intron_end[r]);
             if (it == slow_by_key.end()) continue;
             uint64_t ti = ~0ull;
@@ -1908,6 +2102,7 @@ extern "C" int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ip
             }
         }
     }
+    tr.mark("merge: host fold of flagged introns");
     ht->sites.assign(J * 8, 0);
     for (uint64_t i = 0; i < J; i++) snprintf(ht->sites.data() + 8 * i, 8, "%s", rows->site_strings[site[i]]);
     ht->ijunc.assign(J, 0);
@@ -1919,6 +2114,7 @@ extern "C" int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ip
     std::vector<uint64_t> idx;
     sort_rows(&ht->t, names.data(), true, 0, J, idx);
     for (uint64_t k = 0; k < J; k++) ht->ijunc[idx[k]] = (uint32_t)k;
+    tr.mark("merge: presentation order");
     h->totals.merge_rows += n;
     h->totals.junctions += J;
     if (conflict_log) give_text(log, conflict_log);

@@ -164,6 +164,21 @@ cudaError_t finalize_enqueue(const Tables &t, const GenomeView &g, const uint32_
 bool finalize_check(FinalizeWork &w); /* true = results valid (w.out.n / n_hist set); false = bounds grown, run again */
 void finalize_release(FinalizeWork &w);
 
+/* Sample sort of (u64 key, u32 sub-key) pairs -> the values 0 .. n-1 in key order (ipx_finalize.cu).  Keys equal to
+ * EMPTY64 are left out; pairs must be unique.  `n_ptr`: the number of keys, on the device (at most `bound`). */
+struct SampleSort {
+    unsigned long long *splitters; /* [sample_sort_max_buckets()] */
+    uint32_t *bucket_cnt;          /* [sample_sort_max_buckets() + 1]: counts, then the number of buckets */
+    unsigned long long *bk;        /* [sample_sort_buckets(bound) * C] */
+    uint32_t *bs, *bv;             /* [sample_sort_buckets(bound) * C] */
+    uint64_t C;                    /* capacity of a bucket in bk / bs / bv */
+};
+uint64_t sample_sort_buckets(uint64_t bound);
+uint64_t sample_sort_max_buckets();
+/* d_count[3] |= 8 and d_count[7] = size when a bucket held more than C keys (grow C and run again) */
+cudaError_t sample_sort_enqueue(const unsigned long long *keys, const uint32_t *sub, const unsigned long long *n_ptr, uint64_t bound,
+                                const SampleSort &ss, uint32_t *out_vals, uint32_t *out_rank, unsigned long long *d_count, cudaStream_t st);
+
 /* stream-ordered allocation from the device's default pool (kept resident, see ipx_create): no implicit
  * device synchronisation and no driver round trip once the pool is warm */
 template <class T>

@@ -207,8 +207,8 @@ __device__ __forceinline__ uint32_t place_offset(const Tables &t, uint32_t j, ui
 }
 
 /* fold one received junction row; returns the junction id or JID_NONE */
-__device__ __forceinline__ uint32_t import_junction_row(const Tables &t, IdPool *pool, const JunctionRow &r) {
-    const uint32_t j = junction_probe<true>(t, pool, make_key(t.kl, r.tid, r.i0, r.i1), r.tid).jid;
+__device__ __forceinline__ uint32_t import_junction_row(const Tables &t, IdPool *pool, const JunctionRow &r, uint32_t &spare) {
+    const uint32_t j = junction_probe<true>(t, pool, make_key(t.kl, r.tid, r.i0, r.i1), r.tid, spare).jid;
     if (j == JID_NONE) return j;
     JStat *s = &t.stat[j];
     for (int c = 0; c < 3; ++c) {
@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(256) k_import_junction_rows(Tables t, const Ju
     if (threadIdx.x == 0) id_pool_load(t, &s_pool);
     __syncthreads();
     const uint64_t n_threads = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += n_threads) jid_of[i] = import_junction_row(t, &s_pool, jr[i]);
+    uint32_t spare = JID_NONE;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += n_threads) jid_of[i] = import_junction_row(t, &s_pool, jr[i], spare);
     __syncthreads();
     if (threadIdx.x == 0) id_pool_store(t, &s_pool);
 }
@@ -454,7 +455,8 @@ __global__ void __launch_bounds__(256) k_mail_import_junctions(Tables t, Mailbox
     const JunctionRow *jr = mail_junction_rows(box);
     uint32_t *ids = jid_of + (uint64_t)source * m.cap_j;
     const uint64_t n_threads = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sent; i += n_threads) ids[i] = import_junction_row(t, &s_pool, jr[i]);
+    uint32_t spare = JID_NONE;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sent; i += n_threads) ids[i] = import_junction_row(t, &s_pool, jr[i], spare);
     __syncthreads();
     if (threadIdx.x == 0) t.id_pools[pool_index % N_ID_POOLS] = *((volatile unsigned long long *)&s_pool.word);
 }
@@ -517,7 +519,7 @@ __global__ void k_import_thresholds(Tables t, const ThresholdRow *rows, uint64_t
     if (i >= n) return;
     const ThresholdRow r = rows[i];
     if (r.T == EMPTY64) return;
-    const uint32_t j = junction_probe<false>(t, nullptr, make_key(t.kl, r.tid, r.i0, r.i1), r.tid).jid;
+    const uint32_t j = junction_find(t, make_key(t.kl, r.tid, r.i0, r.i1), r.tid).jid;
     if (j != JID_NONE) atomicMin(&t.stat[j].T, r.T);
 }
 

@@ -91,13 +91,6 @@ static const int SS_MAX_SAMPLE = 8192;
 static const int SS_BUCKET = 256;       /* keys per bucket the splitters aim at */
 static const int SS_SMEM_BUCKET = 1024; /* elements a bucket may have to be ranked in shared memory */
 
-struct SampleSort {
-    unsigned long long *splitters; /* [SS_MAX_BUCKETS] */
-    uint32_t *bucket_cnt;          /* [SS_MAX_BUCKETS + 1]: counts, then the number of buckets */
-    unsigned long long *bk;        /* [P_bound * C] */
-    uint32_t *bs, *bv;             /* [P_bound * C] */
-    uint64_t C;                    /* capacity of a bucket in bk / bs / bv */
-};
 
 __device__ __forceinline__ bool pair_less(unsigned long long ka, uint32_t sa, unsigned long long kb, uint32_t sb) {
     return ka < kb || (ka == kb && sa < sb);
@@ -271,9 +264,22 @@ struct FinTrace {
     }
 };
 
+/* the sample kernel's shared memory is beyond the default limit: opt in, once per device (not under stream capture) */
+static cudaError_t sample_sort_configure() {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_ss_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SS_MAX_SAMPLE * sizeof(unsigned long long)));
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    return cudaSuccess;
+}
+
 static cudaError_t sample_sort(const unsigned long long *keys, const uint32_t *sub, const unsigned long long *n_ptr, uint64_t bound,
                                const SampleSort &ss, uint32_t *out_vals, uint32_t *out_rank, unsigned long long *d_count,
-                               cudaStream_t st, FinTrace *tr = nullptr) {
+                               cudaStream_t st, FinTrace *tr) {
     uint64_t p_bound = (bound + SS_BUCKET - 1) / SS_BUCKET;
     if (p_bound < 1) p_bound = 1;
     if (p_bound > (uint64_t)SS_MAX_BUCKETS) p_bound = SS_MAX_BUCKETS;
@@ -673,6 +679,20 @@ void finalize_release(FinalizeWork &w) {
     w = FinalizeWork();
 }
 
+/* the same sort for other callers (the merge fold): flags in d_count[3] (FLAG_C = 8: a bucket overflowed; d_count[7] = its size) */
+uint64_t sample_sort_buckets(uint64_t bound) {
+    uint64_t p = (bound + SS_BUCKET - 1) / SS_BUCKET;
+    if (p < 1) p = 1;
+    return p > (uint64_t)SS_MAX_BUCKETS ? (uint64_t)SS_MAX_BUCKETS : p;
+}
+uint64_t sample_sort_max_buckets() { return SS_MAX_BUCKETS; }
+cudaError_t sample_sort_enqueue(const unsigned long long *keys, const uint32_t *sub, const unsigned long long *n_ptr, uint64_t bound,
+                                const SampleSort &ss, uint32_t *out_vals, uint32_t *out_rank, unsigned long long *d_count, cudaStream_t st) {
+    cudaError_t e = sample_sort_configure();
+    if (e != cudaSuccess) return e;
+    return sample_sort(keys, sub, n_ptr, bound, ss, out_vals, out_rank, d_count, st, nullptr);
+}
+
 static uint64_t bucket_bound(uint64_t B) {
     uint64_t p = (B + SS_BUCKET - 1) / SS_BUCKET;
     if (p < 1) p = 1;
@@ -693,9 +713,9 @@ static cudaError_t finalize_allocate(FinalizeWork &w, uint64_t B, uint64_t L, ui
             IPX_CU(regrow(&w.ss_splitters[k], SS_MAX_BUCKETS));
             IPX_CU(regrow(&w.ss_bucket_cnt[k], SS_MAX_BUCKETS + 1));
         }
+        IPX_CU(sample_sort_configure());
         IPX_CU(cudaMalloc(&w.big_scratch, (size_t)FIN_BIG_BLOCKS * 65536 * sizeof(uint32_t)));
         IPX_CU(cudaMemset(w.big_scratch, 0, (size_t)FIN_BIG_BLOCKS * 65536 * sizeof(uint32_t)));
-        IPX_CU(cudaFuncSetAttribute(k_ss_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SS_MAX_SAMPLE * sizeof(unsigned long long))));
     }
     if (B != w.B || C != w.C) {
         const uint64_t cells = bucket_bound(B) * C;

@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
     c.key[lane + 32] = EMPTY64;
     __syncwarp();
     LogStage log{c.stage, 0u};
+    uint32_t spare = JID_NONE; /* see junction_probe */
     unsigned long long unfolded = 0ull;
     uint2 next = make_uint2(0u, 0u);
     if (warp0 < n_tiles) next = __ldg(reinterpret_cast<const uint2 *>(tile_info + warp0));
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
                 }
                 if (!hit) {
                     /* one load of the junction's slot: its id and the bases of its dense rows */
-                    const Found f = junction_probe<MODE != MODE_PASS2>(t, &s_pool, e.key, e.tid);
+                    const Found f = junction_probe<MODE != MODE_PASS2>(t, &s_pool, e.key, e.tid, spare);
                     jid = f.jid;
                     gslot = f.slot;
                     rb[0] = f.base[0]; rb[1] = f.base[1]; rb[2] = f.base[2];

@@ -7,27 +7,19 @@
 
 namespace ipx {
 
+/* what an intron accumulates, indexed by junction id (ipx_table.cuh) */
 #if defined(__CUDACC__)
 struct __align__(64) MStat {
 #else
 struct alignas(64) MStat {
 #endif
     unsigned long long cnt[3];
-    unsigned long long first_row; /* first row (file, row order) of this intron */
     uint32_t a0, a1;
-    uint32_t conf_bits;           /* max confidence as float bits (non-negative floats order like uints) */
-    uint32_t strand_min, strand_max; /* over strands other than '.'; max == 0 means none */
-    uint32_t site_min, site_max;  /* over splice-site string ids */
-    uint32_t odd;                 /* a row with negative / NaN confidence: fold on the host */
-};
-
-struct MergeTables {
-    unsigned long long *keys; /* [cap] intron_start << 32 | intron_end */
-    uint32_t *chrom;          /* [cap] chromosome index, 0xFFFFFFFF = unclaimed */
-    MStat *stat;              /* [cap] */
-    uint64_t cap_mask;
-    unsigned long long *n_keys;
-    uint32_t *overflow;
+    uint32_t conf_bits; /* max confidence as float bits (non-negative floats order like uints) */
+    uint32_t ev_lo;     /* min over rows of (splice-site string id << 8 | strand, '.' as 0xFF) */
+    uint32_t ev_hi;     /* max over rows of (splice-site string id << 8 | strand, '.' as 0) */
+    uint32_t odd;       /* a row with negative / -0.0 / NaN confidence: fold on the host */
+    uint32_t pad[4];
 };
 
 struct MergeRowsView {
@@ -50,14 +42,16 @@ struct MergeOut {
     uint8_t *slow;
 };
 
-void launch_merge_init(const MergeTables &t, cudaStream_t st);
-void launch_merge_fold(const MergeRowsView &r, const MergeTables &t, int sm_count, cudaStream_t st);
-void launch_merge_compact(const MergeTables &t, unsigned long long *d_count, unsigned long long *sort_lo, uint32_t *slot_out,
-                          cudaStream_t st);
-void launch_merge_rank_keys(const MergeTables &t, const uint32_t *name_rank, const uint32_t *slots, uint64_t n,
-                            unsigned long long *hi_out, cudaStream_t st);
-void launch_merge_gather(const MergeTables &t, const uint32_t *sorted_slot, uint64_t n, const MergeOut &out,
+/* `t`: slots, cap_mask, jkey, jtid, jslot, max_j, n_keys, id_pools, overflow, kl.wide = 1 (nothing else is used) */
+void launch_merge_init(const Tables &t, MStat *stat, unsigned long long *n_unfolded, cudaStream_t st);
+void launch_merge_fold(const MergeRowsView &r, const Tables &t, MStat *stat, unsigned long long *n_unfolded, int sm_count, cudaStream_t st);
+/* d_count[4] = ids in use (<= B), d_count[3] = 1 when B was too small */
+void launch_merge_keys(const Tables &t, const uint32_t *name_rank, uint64_t B, unsigned long long *d_count, unsigned long long *sort_key,
+                       uint32_t *sort_sub, cudaStream_t st);
+void launch_merge_gather(const Tables &t, const MStat *stat, const uint32_t *order, uint64_t n, const MergeOut &out, uint8_t *slow_of_id,
                          cudaStream_t st);
+void launch_merge_slow_rows(const MergeRowsView &r, const Tables &t, const uint8_t *slow_of_id, unsigned long long *n_slow, uint64_t cap,
+                            unsigned long long *slow_rows, int sm_count, cudaStream_t st);
 
 }  // namespace ipx
 #endif

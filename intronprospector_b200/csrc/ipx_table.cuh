@@ -32,7 +32,7 @@
 namespace ipx {
 
 static const uint64_t EMPTY64 = ~0ull;
-static const uint32_t JID_UNSET = 0xFFFFFFFFu; /* slot claimed, junction id not published yet */
+static const uint32_t JID_UNSET = 0xFFFFFFFFu; /* the id field of an empty slot */
 static const uint32_t JID_FULL = 0xFFFFFFFEu;  /* slot claimed when no junction row was left */
 static const uint32_t JID_NONE = 0xFFFFFFFDu;  /* probe result: absent (lookup) or no room (insert) */
 /* Read offsets (intron_start - read start) of short reads are < read length; counts for offsets below DENSE_W
@@ -256,12 +256,37 @@ __device__ __forceinline__ void load_slot(const Slot *s, unsigned long long &key
     base[2] = b.y;
 }
 
+/* 128-bit compare-and-swap on the first half of a slot -- (key, jid, base[0]) from the reset state to (key, jid,
+ * BASE_UNSET) -- so that a slot's key and its junction id become visible together: nobody ever waits for another
+ * thread to publish an id (threads that wait for each other's insertions across warps can wait in a circle).
+ * Returns what the half held before. */
+__device__ __forceinline__ bool slot_claim(Slot *s, unsigned long long key, uint32_t jid, uint32_t base0, unsigned long long &seen_key,
+                                           uint32_t &seen_jid, uint32_t &seen_base0) {
+    const unsigned long long c_lo = EMPTY64, c_hi = ((unsigned long long)BASE_UNSET << 32) | JID_UNSET;
+    const unsigned long long n_hi = ((unsigned long long)base0 << 32) | jid;
+    unsigned long long o_lo, o_hi;
+    asm volatile(
+        "{\n\t.reg .b128 c, n, o;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 n, {%4, %5};\n\t"
+        "atom.relaxed.gpu.global.cas.b128 o, [%6], c, n;\n\tmov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(o_lo), "=l"(o_hi)
+        : "l"(c_lo), "l"(c_hi), "l"(key), "l"(n_hi), "l"(s)
+        : "memory");
+    seen_key = o_lo;
+    seen_jid = (uint32_t)o_hi;
+    seen_base0 = (uint32_t)(o_hi >> 32);
+    return o_lo == c_lo && o_hi == c_hi;
+}
+
 /* Find the junction of (key, tid); INSERT: claim a slot and a junction row when absent.  jid == JID_NONE when the key is
  * absent (lookup) or when no slot / row is left (insert: the overflow flag is raised, the caller keeps the event).
  * The junction rows of ids never handed out hold the reset values (init / clear), so an inserter has nothing to
- * initialise but the identity. */
+ * initialise but the identity.
+ * `spare` (INSERT; one per thread, JID_NONE at first, kept across calls): a junction id the thread took for an insertion
+ * that another thread then won.  The id is taken BEFORE the slot is claimed and its identity (jkey, jtid) written and
+ * fenced, so the claim publishes a complete junction in one atomic operation; a spare left over at the end of a kernel
+ * is a hole like the unused ids of a pool's block. */
 template <bool INSERT>
-__device__ __forceinline__ Found junction_probe(const Tables &t, IdPool *pool, unsigned long long key, int32_t tid) {
+__device__ __forceinline__ Found junction_probe(const Tables &t, IdPool *pool, unsigned long long key, int32_t tid, uint32_t &spare) {
     Found f;
     f.jid = JID_NONE;
     f.slot = 0u;
@@ -275,33 +300,38 @@ __device__ __forceinline__ Found junction_probe(const Tables &t, IdPool *pool, u
         f.slot = (uint32_t)h;
         if (k == EMPTY64) {
             if (!INSERT) return f;
-            k = atomicCAS(&s->key, EMPTY64, key);
-            if (k == EMPTY64) {
-                j = id_pool_take(t, pool);
-                if (j >= t.max_j) {
-                    /* no row left: the slot stays claimed (it is dropped by the rehash that follows the growth) */
-                    *((volatile uint32_t *)&s->jid) = JID_FULL;
-                    atomicOr(t.overflow, OVF_TABLE);
+            if (spare == JID_NONE) {
+                spare = id_pool_take(t, pool);
+                if (spare >= t.max_j) spare = JID_NONE; /* no row left */
+            }
+            if (spare == JID_NONE) {
+                /* The key is marked as one that met the full table, so that nobody with an id to spare inserts it later
+                 * in the same launch: a key is in the table for all of its events of a pass or for none (the two-pass
+                 * fold relies on that).  The slot is dropped by the rehash that follows the growth. */
+                atomicOr(t.overflow, OVF_TABLE);
+                if (slot_claim(s, key, JID_FULL, (uint32_t)tid, k, j, f.base[0])) return f; /* (the target index in place of a row base) */
+            } else {
+                t.jkey[spare] = key;
+                t.jtid[spare] = tid;
+                __threadfence(); /* the identity is visible before the id is */
+                if (slot_claim(s, key, spare, BASE_UNSET, k, j, f.base[0])) {
+                    t.jslot[spare] = (uint32_t)h;
+                    f.jid = spare;
+                    spare = JID_NONE;
+                    f.base[0] = f.base[1] = f.base[2] = BASE_UNSET;
                     return f;
                 }
-                t.jkey[j] = key;
-                t.jtid[j] = tid;
-                t.jslot[j] = (uint32_t)h;
-                /* Whoever meets the id reads jtid in the wide layout only: there the identity must be visible before
-                 * the id is.  (jkey / jslot are read by later kernels; the record and the offset rows are already in
-                 * their reset state, and so are the slot's row bases.) */
-                if (t.kl.wide) __threadfence();
-                *((volatile uint32_t *)&s->jid) = j;
-                f.jid = j;
-                f.base[0] = f.base[1] = f.base[2] = BASE_UNSET;
-                return f;
             }
-            j = JID_UNSET; /* somebody else claimed it in the meantime: look again below */
+            /* somebody else claimed the slot in the meantime: k / j / base[0] are what it holds now; a junction that
+             * young has no further rows */
+            f.base[1] = f.base[2] = BASE_UNSET;
         }
         if (k == key) {
+            /* (key and id are written by one 128-bit operation; should a 16-byte load ever see them apart, the next
+             * one does not -- this waits for nobody) */
             while (j == JID_UNSET) load_slot(s, k, j, f.base);
             if (j == JID_FULL) {
-                if (INSERT && !t.kl.wide) return f; /* the same key met the full table before (flag already raised) */
+                if (INSERT && f.base[0] == (uint32_t)tid) return f; /* the same key met the full table before (flag already raised) */
             } else if (!t.kl.wide || *((volatile int32_t *)&t.jtid[j]) == tid) {
                 f.jid = j;
                 return f;
@@ -311,6 +341,11 @@ __device__ __forceinline__ Found junction_probe(const Tables &t, IdPool *pool, u
     }
     if (INSERT) atomicOr(t.overflow, OVF_TABLE);
     return f;
+}
+/* lookup only */
+__device__ __forceinline__ Found junction_find(const Tables &t, unsigned long long key, int32_t tid) {
+    uint32_t none = JID_NONE;
+    return junction_probe<false>(t, nullptr, key, tid, none);
 }
 
 /* Which dense counter takes `offset` for the junction in `slot`: row * DENSE_W + index, or DENSE_NONE (-> the log).
