@@ -509,7 +509,8 @@ __global__ void __launch_bounds__(256) k_fin_rows(Tables t, GenomeView g, uint64
                                                   const uint32_t *t_rank, const uint32_t *runs_j, uint32_t *runs_r, DeviceTable out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i > B) return;
-    if (i >= d_count[0] || i >= B) {
+    /* (a sort bucket that overflowed left keys out: `order` is incomplete, the host grows the buckets and replays) */
+    if (i >= d_count[0] || i >= B || (d_count[3] & FLAG_C)) {
         runs_r[i] = 0u;
         return;
     }
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(256) k_fin_write(Tables t, uint64_t B, uint64_
         if (n_runs > R) atomicOr(&d_count[3], FLAG_R);
     }
     if (n_runs > R) return; /* does not fit: the host grows R and replays */
-    if (r >= d_count[0] || r >= B) return;
+    if (r >= d_count[0] || r >= B || (d_count[3] & FLAG_C)) return;
     const uint32_t j = order[r];
     const unsigned long long o0 = hist_off[r], o1 = hist_off[r + 1];
     const uint64_t s0 = seg_off[j];
@@ -726,7 +727,10 @@ static cudaError_t finalize_allocate(FinalizeWork &w, uint64_t B, uint64_t L, ui
     }
     if (B != w.B) {
         IPX_CU(regrow(&w.sort_key, B)); IPX_CU(regrow(&w.sort_sub, B)); IPX_CU(regrow(&w.tkey, B)); IPX_CU(regrow(&w.order, B));
-        IPX_CU(regrow(&w.t_order, B)); IPX_CU(regrow(&w.t_rank, B)); IPX_CU(regrow(&w.seg_off, B)); IPX_CU(regrow(&w.seg_fill, B));
+        IPX_CU(regrow(&w.t_order, B)); IPX_CU(regrow(&w.t_rank, B));
+        /* what a sort leaves unwritten (see FLAG_C) must at least be junction ids */
+        IPX_CU(cudaMemset(w.order, 0, B * sizeof(uint32_t))); IPX_CU(cudaMemset(w.t_order, 0, B * sizeof(uint32_t)));
+        IPX_CU(cudaMemset(w.t_rank, 0, B * sizeof(uint32_t))); IPX_CU(regrow(&w.seg_off, B)); IPX_CU(regrow(&w.seg_fill, B));
         IPX_CU(regrow(&w.runs_j, B)); IPX_CU(regrow(&w.nz4, B * 4)); IPX_CU(regrow(&w.below3, B * 3)); IPX_CU(regrow(&w.big_list, B)); IPX_CU(regrow(&w.runs_r, B + 1));
         IPX_CU(regrow(&w.scan_state, scan_state_words(B + 1)));
         DeviceTable &o = w.out;
@@ -806,7 +810,7 @@ static cudaError_t finalize_issue(const Tables &t, const GenomeView &g, const ui
 }
 
 cudaError_t finalize_enqueue(const Tables &t, const GenomeView &g, const uint32_t *d_name_rank, FinalizeWork &w, cudaStream_t st) {
-    uint64_t B = w.B ? w.B : w.first_B, L = w.L ? w.L : w.first_L, R = w.R ? w.R : w.first_R, C = w.C ? w.C : 1024;
+    uint64_t B = w.B ? w.B : w.first_B, L = w.L ? w.L : w.first_L, R = w.R ? w.R : w.first_R, C = w.C ? w.C : 2048;
     if (w.wish_B > B) B = w.wish_B;
     if (w.wish_L > L) L = w.wish_L;
     if (w.wish_R > R) R = w.wish_R;

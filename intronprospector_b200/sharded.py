@@ -180,7 +180,16 @@ def exchange_mail_dist(eng, names, device, group=None, splitters=None):
     world = dist.get_world_size(group)
     split_tid, split_start = splitters if splitters is not None else key_splitters(names, world)
     eng.partial_export_mail(split_tid, split_start)
+    _debug_sync("export")
     eng.partial_import_mail()
+    _debug_sync("import")
+
+
+def _debug_sync(what):
+    """IPX_DEBUG_SYNC=export,import: wait for the device after that phase (fault hunting; never set in measurements)."""
+    import os
+    if what in os.environ.get("IPX_DEBUG_SYNC", "").split(","):
+        torch.cuda.synchronize()
 
 
 def settle_exchange_dist(eng, names, device, group=None, splitters=None):
