@@ -328,6 +328,7 @@ void set_counter_pointers(ipx_handle *h) {
     t.err_sv = h->d_counters + 64;
     t.overflow = (uint32_t *)(h->d_counters + 80);
     t.n_unfolded = h->d_counters + 128;
+    t.next_tile = h->d_counters + 144;
     t.id_pools = h->d_counters + 256;
 }
 
@@ -371,6 +372,8 @@ int alloc_tables(ipx_handle *h) {
     CU(h, cudaMalloc(&t.slots, cap * sizeof(Slot)));
     t.cap_mask = cap - 1;
     t.extra_rows = 1;
+    t.dense_lead = DENSE_LEAD;
+    if (const char *e = getenv("IPX_DENSE_LEAD")) t.dense_lead = std::min<uint32_t>((uint32_t)atoi(e), DENSE_W - 1);
     rc = alloc_rows(h, t, cap / 2, !getenv("IPX_NO_DENSE"));
     if (rc) return rc;
     CU(h, cudaMalloc(&t.olog, hcap * sizeof(unsigned long long)));
@@ -1450,7 +1453,9 @@ static void mailbox_release(ipx_handle *h) {
         h->mail.base[r] = nullptr;
     }
     if (h->mail_own) cudaFree(h->mail_own);
+    if (h->mail.outbox) cudaFree(h->mail.outbox);
     h->mail_own = nullptr;
+    h->mail.outbox = nullptr;
     h->mail_connected = false;
 }
 
@@ -1472,6 +1477,7 @@ extern "C" int ipx_mailbox_create(ipx_handle *h, int32_t world, int32_t rank, ui
     /* a plain cudaMalloc: memory from a stream-ordered pool cannot be shared through cudaIpcGetMemHandle */
     CU(h, cudaMalloc(&h->mail_own, 2 * (size_t)world * m.slot_bytes));
     CU(h, cudaMemset(h->mail_own, 0, 2 * (size_t)world * m.slot_bytes));
+    CU(h, cudaMalloc(&m.outbox, (size_t)world * m.slot_bytes));
     m.base[rank] = h->mail_own;
     return IPX_OK;
 }
@@ -1544,7 +1550,7 @@ extern "C" int ipx_partial_export_mail(ipx_handle *h, const int32_t *split_tid, 
     }
     {
         /* only what other ranks own moves; this rank's own share stays where it is */
-        Span s(h, &h->tm_export, 3);
+        Span s(h, &h->tm_export, 4);
         launch_mail_export(h->tab, h->d_name_rank, sp, h->mail, h->d_export, (uint32_t *)h->jrow_of.p, h->sm_count, st);
     }
     CU(h, cudaGetLastError());

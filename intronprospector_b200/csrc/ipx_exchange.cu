@@ -29,7 +29,7 @@ __device__ __forceinline__ int part_of(const Splitters &sp, uint32_t name_rank, 
 }
 
 /* offset rows a counter needs: counts above 65535 are sent as several rows */
-__device__ __forceinline__ uint32_t hist_rows_of(uint32_t v) { return v ? (v - 1u) / 0xFFFFu + 1u : 0u; }
+__device__ __forceinline__ uint32_t hist_rows_of(uint32_t v) { return v <= 0xFFFFu ? (v != 0u ? 1u : 0u) : (v - 1u) / 0xFFFFu + 1u; }
 
 /* what a warp needs of one junction row: owner, key fields, the offset rows its dense counters turn into */
 struct RowView {
@@ -62,9 +62,10 @@ __device__ __forceinline__ RowView read_row(const Tables &t, const uint32_t *nam
         const Slot *s = &t.slots[t.jslot[j]];
         r.base[0] = s->base[0]; r.base[1] = s->base[1]; r.base[2] = s->base[2];
         uint32_t mine = 0u;
-#pragma unroll
+        /* (not unrolled, here and below: the export kernel spent 72 % of its stall samples waiting for instructions) */
+#pragma unroll 1
         for (uint32_t row = 0; row < DENSE_ROWS; ++row) {
-            if (row > 0u && r.base[row - 1] == BASE_UNSET) continue;
+            if (row > 0u && (row == 1u ? r.base[0] : row == 2u ? r.base[1] : r.base[2]) == BASE_UNSET) continue;
             uint32_t v[8];
             load_counters(t, j, row, lane, v);
 #pragma unroll
@@ -90,9 +91,10 @@ __device__ __forceinline__ JunctionRow make_junction_row(const JStat &s, const R
 template <bool ZERO>
 __device__ __forceinline__ void write_dense_rows(const Tables &t, uint64_t j, HistRow *hr, uint64_t o, uint32_t jrow, const RowView &r,
                                                  int lane, bool write) {
-#pragma unroll
+#pragma unroll 1
     for (uint32_t row = 0; row < DENSE_ROWS; ++row) {
-        if (row > 0u && r.base[row - 1] == BASE_UNSET) continue;
+        const uint32_t row_base = row == 0u ? 0u : row == 1u ? r.base[0] : row == 2u ? r.base[1] : r.base[2];
+        if (row > 0u && row_base == BASE_UNSET) continue;
         uint32_t v[8];
         load_counters(t, j, row, lane, v);
         uint32_t mine = 0u;
@@ -104,7 +106,7 @@ __device__ __forceinline__ void write_dense_rows(const Tables &t, uint64_t j, Hi
             const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if (lane >= d) incl += y;
         }
-        const uint32_t first = row == 0u ? 0u : r.base[row - 1];
+        const uint32_t first = row_base;
         uint64_t at = o + (incl - mine);
         if (write) {
 #pragma unroll
@@ -261,6 +263,8 @@ void launch_import_rows(const Tables &t, const JunctionRow *jr, uint64_t nj, con
 __device__ __forceinline__ char *mail_slot(const Mailboxes &m, int owner, int source) {
     return m.base[owner] + (uint64_t)(m.parity * m.world + source) * m.slot_bytes;
 }
+/* where the rows for `owner` are put together before they cross the link in one coalesced copy (k_mail_send) */
+__device__ __forceinline__ char *outbox_slot(const Mailboxes &m, int owner) { return m.outbox + (uint64_t)owner * m.slot_bytes; }
 __device__ __forceinline__ JunctionRow *mail_junction_rows(char *slot) { return reinterpret_cast<JunctionRow *>(slot + MAIL_HEADER_BYTES); }
 __device__ __forceinline__ HistRow *mail_hist_rows(const Mailboxes &m, char *slot) {
     return reinterpret_cast<HistRow *>(slot + MAIL_HEADER_BYTES + m.hist_offset);
@@ -268,56 +272,82 @@ __device__ __forceinline__ HistRow *mail_hist_rows(const Mailboxes &m, char *slo
 
 static const uint32_t NOT_EXPORTED = 0xFFFFFFFFu;
 
-/* A warp per junction row, a block's eight warps in lock step: the block adds up what its eight rows need per owner
- * in shared memory, reserves it behind the owners' cursors with one atomic per owner that occurs (junction ids follow
- * the stream, so neighbours mostly share their owner), and the warps write their rows -- still in registers -- into the
- * owners' slots: NVLink stores.  An exported row is disowned here: its record and offset row go back to the reset
- * values, so that finalize passes over it and later events would start it afresh. */
+/* A warp takes MAIL_BATCH consecutive junction rows at a time.  First it looks at all of them (owner, offset rows its
+ * dense counters turn into), lane q keeping what it learnt about row q; then the lanes reserve room behind the owners'
+ * cursors together -- junction ids follow the stream, so the rows of a batch mostly share their owner: one pair of
+ * atomics per (batch, owner) -- and the rows go into the owner's slot of the local outbox (rows stored one by one
+ * straight into the peer's memory made the export three times slower on NVLink than it is locally: 8- and 72-byte
+ * stores; k_mail_send moves each outbox slot across the link as one coalesced copy).  Nothing is synchronised beyond
+ * the warp.  An exported row is disowned here: its record and offset rows go back to the reset values, so that finalize
+ * passes over it and later events would start it afresh. */
+static const int MAIL_BATCH = 8;
 __global__ void __launch_bounds__(256) k_mail_rows(Tables t, const uint32_t *name_rank, Splitters sp, Mailboxes m,
                                                    unsigned long long *counts, uint32_t *jrow_of) {
-    __shared__ unsigned long long s_j[MAX_PARTS], s_h[MAX_PARTS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t n_keys = junctions_in_use(t);
-    const uint64_t rounds = (n_keys + 8ull * gridDim.x - 1ull) / (8ull * gridDim.x);
-    for (uint64_t round = 0; round < rounds; ++round) {
-        const uint64_t j = (round * gridDim.x + blockIdx.x) * 8ull + (uint64_t)warp;
-        if (threadIdx.x < MAX_PARTS) s_j[threadIdx.x] = s_h[threadIdx.x] = 0ull;
-        __syncthreads();
-        RowView r;
-        r.dest = -1;
-        r.nz = 0u;
-        if (j < n_keys) r = read_row(t, name_rank, sp, j, lane);
-        const bool foreign = r.dest >= 0 && r.dest != m.me;
-        unsigned long long jpos = 0ull, hpos = 0ull;
-        if (foreign && lane == 0) {
-            jpos = atomicAdd(&s_j[r.dest], 1ull);
-            if (r.nz) hpos = atomicAdd(&s_h[r.dest], (unsigned long long)r.nz);
-        }
-        __syncthreads();
-        if (threadIdx.x < sp.n_parts) {
-            const int d = threadIdx.x;
-            const unsigned long long nj = s_j[d], nh = s_h[d];
-            s_j[d] = nj ? atomicAdd(&counts[d], nj) : 0ull;
-            s_h[d] = nh ? atomicAdd(&counts[sp.n_parts + d], nh) : 0ull;
-        }
-        __syncthreads();
-        if (j < n_keys && lane == 0 && !foreign) jrow_of[j] = NOT_EXPORTED;
-        if (foreign) {
-            if (lane == 0) {
-                jpos += s_j[r.dest];
-                hpos += s_h[r.dest];
+    const uint64_t n_batches = (n_keys + MAIL_BATCH - 1) / MAIL_BATCH;
+    for (uint64_t bt = warp0; bt < n_batches; bt += n_warps) {
+        const uint64_t j0 = bt * MAIL_BATCH;
+        RowView mine;
+        mine.dest = -1; mine.nz = 0u; mine.i0 = mine.i1 = 0u; mine.tid = 0;
+        mine.base[0] = mine.base[1] = mine.base[2] = BASE_UNSET;
+#pragma unroll 1
+        for (int q = 0; q < MAIL_BATCH; ++q) {
+            if (j0 + q < n_keys) {
+                const RowView r = read_row(t, name_rank, sp, j0 + q, lane);
+                if (lane == q) mine = r;
             }
-            jpos = __shfl_sync(0xFFFFFFFFu, jpos, 0);
-            hpos = __shfl_sync(0xFFFFFFFFu, hpos, 0);
+        }
+        const bool foreign = mine.dest >= 0 && mine.dest != m.me; /* (lanes >= MAIL_BATCH: false) */
+        /* room behind the owners' cursors: the lanes of one owner share a pair of atomics */
+        const int gkey = foreign ? mine.dest : -1 - lane;
+        const unsigned grp = __match_any_sync(0xFFFFFFFFu, gkey);
+        const int leader = __ffs(grp) - 1;
+        uint32_t hpre = 0u, htot = 0u;
+#pragma unroll
+        for (int q = 0; q < MAIL_BATCH; ++q) {
+            const int dq = __shfl_sync(0xFFFFFFFFu, gkey, q);
+            const uint32_t nq = __shfl_sync(0xFFFFFFFFu, mine.nz, q);
+            if (dq == gkey) {
+                htot += nq;
+                if (q < lane) hpre += nq;
+            }
+        }
+        unsigned long long jpos = 0ull, hpos = 0ull;
+        if (foreign && lane == leader) {
+            jpos = atomicAdd(&counts[mine.dest], (unsigned long long)__popc(grp));
+            if (htot) hpos = atomicAdd(&counts[sp.n_parts + mine.dest], (unsigned long long)htot);
+        }
+        jpos = __shfl_sync(0xFFFFFFFFu, jpos, leader) + (unsigned long long)__popc(grp & ((1u << lane) - 1u));
+        hpos = __shfl_sync(0xFFFFFFFFu, hpos, leader) + hpre;
+#pragma unroll 1
+        for (int q = 0; q < MAIL_BATCH; ++q) {
+            const uint64_t j = j0 + q;
+            if (j >= n_keys) break;
+            RowView r;
+            r.dest = __shfl_sync(0xFFFFFFFFu, mine.dest, q);
+            r.nz = __shfl_sync(0xFFFFFFFFu, mine.nz, q);
+            const bool fq = __shfl_sync(0xFFFFFFFFu, (int)foreign, q) != 0;
+            if (!fq) {
+                if (lane == 0) jrow_of[j] = NOT_EXPORTED;
+                continue;
+            }
+            r.i0 = __shfl_sync(0xFFFFFFFFu, mine.i0, q);
+            r.i1 = __shfl_sync(0xFFFFFFFFu, mine.i1, q);
+            r.tid = __shfl_sync(0xFFFFFFFFu, mine.tid, q);
+            r.base[0] = __shfl_sync(0xFFFFFFFFu, mine.base[0], q);
+            r.base[1] = __shfl_sync(0xFFFFFFFFu, mine.base[1], q);
+            r.base[2] = __shfl_sync(0xFFFFFFFFu, mine.base[2], q);
+            const unsigned long long jp = __shfl_sync(0xFFFFFFFFu, jpos, q), hp = __shfl_sync(0xFFFFFFFFu, hpos, q);
             /* a slot that is too small keeps counting: the owner sees counts beyond the capacity and reports it */
-            const bool fits = jpos < m.cap_j && hpos + r.nz <= m.cap_h;
-            char *box = mail_slot(m, r.dest, m.me);
+            const bool fits = jp < m.cap_j && hp + r.nz <= m.cap_h;
+            char *box = outbox_slot(m, r.dest);
             if (lane == 0) {
-                if (fits) mail_junction_rows(box)[jpos] = make_junction_row(t.stat[j], r);
-                jrow_of[j] = fits ? (((uint32_t)r.dest << 24) | (uint32_t)jpos) : (((uint32_t)r.dest << 24) | 0xFFFFFFu);
+                if (fits) mail_junction_rows(box)[jp] = make_junction_row(t.stat[j], r);
+                jrow_of[j] = fits ? (((uint32_t)r.dest << 24) | (uint32_t)jp) : (((uint32_t)r.dest << 24) | 0xFFFFFFu);
                 /* disown */
-                JStat *s = &t.stat[j];
-                uint4 *p = reinterpret_cast<uint4 *>(s);
+                uint4 *p = reinterpret_cast<uint4 *>(&t.stat[j]);
                 p[0] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
                 p[1] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
                 p[2] = make_uint4(0u, 0u, 0u, 0u);
@@ -326,9 +356,8 @@ __global__ void __launch_bounds__(256) k_mail_rows(Tables t, const uint32_t *nam
             }
             /* its offset rows go out and its counters back to zero (the rows stay given out: their bases are as good
              * for the reads that may follow as any) */
-            if (t.dense) write_dense_rows<true>(t, j, mail_hist_rows(m, box), hpos, (uint32_t)jpos, r, lane, fits);
+            if (t.dense) write_dense_rows<true>(t, j, mail_hist_rows(m, box), hp, (uint32_t)jp, r, lane, fits);
         }
-        __syncthreads();
     }
 }
 
@@ -364,9 +393,27 @@ __global__ void __launch_bounds__(256) k_mail_olog(Tables t, Splitters sp, Mailb
         if (dest >= 0 && at < m.cap_h && jrow != 0xFFFFFFu) {
             HistRow h;
             h.jrow = jrow; h.offset = (uint16_t)((e >> 16) & 0xFFFFull); h.cnt = (uint16_t)(e & 0xFFFFull);
-            mail_hist_rows(m, mail_slot(m, dest, m.me))[at] = h;
+            mail_hist_rows(m, outbox_slot(m, dest))[at] = h;
         }
     }
+}
+
+/* The outbox slots cross the link: blockIdx.y = destination, the blocks of a destination copy its junction rows and its
+ * offset rows (as many as the cursors say) with 16-byte loads and stores, consecutive lanes on consecutive addresses. */
+__global__ void __launch_bounds__(256) k_mail_send(Mailboxes m, const unsigned long long *counts) {
+    const int d = blockIdx.y;
+    if (d == m.me) return;
+    const unsigned long long nj = counts[d] < m.cap_j ? counts[d] : m.cap_j, nh = counts[m.world + d] < m.cap_h ? counts[m.world + d] : m.cap_h;
+    const char *src = outbox_slot(m, d);
+    char *dst = mail_slot(m, d, m.me);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t qj = (nj * sizeof(JunctionRow) + 15) / 16, qh = (nh * sizeof(HistRow) + 15) / 16; /* (slots are padded to 256 bytes) */
+    const uint4 *sj = reinterpret_cast<const uint4 *>(src + MAIL_HEADER_BYTES);
+    uint4 *dj = reinterpret_cast<uint4 *>(dst + MAIL_HEADER_BYTES);
+    for (uint64_t i = first; i < qj; i += stride) dj[i] = sj[i];
+    const uint4 *sh = reinterpret_cast<const uint4 *>(src + MAIL_HEADER_BYTES + m.hist_offset);
+    uint4 *dh = reinterpret_cast<uint4 *>(dst + MAIL_HEADER_BYTES + m.hist_offset);
+    for (uint64_t i = first; i < qh; i += stride) dh[i] = sh[i];
 }
 
 /* header of a slot: [0] junction rows, [1] offset rows, [2] epoch of the exchange they belong to */
@@ -384,6 +431,10 @@ void launch_mail_export(const Tables &t, const uint32_t *name_rank, const Splitt
                         uint32_t *jrow_of, int sm_count, cudaStream_t st) {
     k_mail_rows<<<sm_count * 8, 256, 0, st>>>(t, name_rank, sp, m, counts, jrow_of);
     k_mail_olog<<<sm_count * 8, 256, 0, st>>>(t, sp, m, counts, jrow_of);
+    if (m.world > 1) {
+        unsigned per_dest = (unsigned)((sm_count * 4 + m.world - 2) / (m.world - 1));
+        k_mail_send<<<dim3(per_dest ? per_dest : 1, m.world), 256, 0, st>>>(m, counts);
+    }
     k_mail_publish<<<1, MAX_PARTS, 0, st>>>(m, counts);
 }
 

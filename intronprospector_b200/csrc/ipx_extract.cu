@@ -471,11 +471,12 @@ __global__ void __launch_bounds__(256) k_seg_emit(BatchView b, ExtractParams p, 
  *                        tile i is classified (helping with its rounds if any are left), then takes chunks of tile i.
  *                        Classification of a tile therefore overlaps the walk of the tile before it, and a warp busy
  *                        with a long walk simply takes fewer units. */
-static const int EX_STAGES = 4;
+static const int EX_STAGES = 2;
+static const int EX_BLOCKS = 2; /* resident blocks per SM */
 static const int EX_WORKER_WARPS = 15;
 static const int EX_LOOKAHEAD = 1; /* workers classify up to this many tiles ahead of the one they walk */
 static const int EX_ROUNDS = EX_TILE / 128;
-static const int EX_CIG_CAP = 2048; /* staged CIGAR words per tile (average short-read tile: ~1500); words beyond are
+static const int EX_CIG_CAP = 2 * EX_TILE; /* staged CIGAR words per tile (short reads average 1.5 per record); words beyond are
                                        read from global memory */
 
 struct __align__(128) ExStage {
@@ -628,59 +629,71 @@ __device__ __forceinline__ void take_rounds(ExStage &S, int stage, uint64_t *cla
 }
 
 /* the short-CIGAR chunk: "aligned, N, aligned" is the only shape of two or three operations that emits a junction
- * (ReadJunctionExtractor, junctions_extractor.cc:208-254,278-282) */
+ * (ReadJunctionExtractor, junctions_extractor.cc:208-254,278-282).  Called by all 32 lanes of a chunk (`valid`: the lane
+ * has a record): the lanes that emit reserve their slots of the tile's region together, with one shared-memory atomic
+ * per chunk instead of one per event (32 lanes adding to one address are served one after the other). */
 __device__ __forceinline__ void walk_short(const BatchView &b, const ExtractParams &p, const Tables &t, ExStage &S, Event *region,
-                                           uint32_t rl, unsigned long long &events) {
-    const uint32_t c0 = S.off[rl], n_cigar = S.off[rl + 1] - c0;
-    const uint32_t w0 = cigar_word(S, b.cigar, c0), w1 = cigar_word(S, b.cigar, c0 + 1);
-    const uint32_t w2 = n_cigar == 3u ? cigar_word(S, b.cigar, c0 + 2) : 0u;
-    const uint32_t o0 = w0 & 15u, o1 = w1 & 15u, o2 = w2 & 15u;
-    const uint32_t known = 0x1BFu, aligned = 0x181u; /* MIDNSH=X ; M=X */
-    if (!((known >> o0) & (known >> o1) & (known >> o2) & 1u)) {
-        walk_record(b, p, t, S, region, rl, events); /* reports the unknown operation exactly */
-    } else if (n_cigar == 3u && o1 == OP_N && ((aligned >> o0) & (aligned >> o2) & 1u)) {
-        /* the one candidate: anchor_start = pos, intron = [pos + l0, + l1), anchor_end = intron_end + l2, mismatches =
-         * the X lengths, no indels.  Operation lengths are below 2^28 and pos is a BAM int32, so 32-bit arithmetic
-         * gives what the reference's 64-bit arithmetic gives wherever the result is usable (a start outside
-         * [0, 2^31) is reported). */
-        const uint32_t l0 = w0 >> 4, l1 = w1 >> 4, l2 = w2 >> 4;
-        const uint32_t flag = S.flag[rl], nh = S.nh[rl];
-        const uint32_t lbad = o0 == OP_X ? l0 : 0u, rbad = o2 == OP_X ? l2 : 0u;
-        /* junction_qc (junctions_extractor.cc:384-401) */
-        if (read_may_emit(p, flag, nh) && l1 >= p.min_intron_length && l1 <= p.max_intron_length &&
-            l0 - lbad >= p.min_anchor_length && l2 - rbad >= p.min_anchor_length) {
-            events++;
-            const uint32_t pos = (uint32_t)S.pos[rl];
-            const uint32_t i0 = pos + l0;
-            if (i0 > 0x7FFFFFFFu) {
-                atomicOr(t.overflow, OVF_START);
-            } else {
-                const char strand = read_strand(p.strandness, flag, S.xs[rl]);
-                const uint32_t tid = (uint32_t)S.tid[rl];
-                const unsigned long long key = ((unsigned long long)(tid & t.kl.tid_mask) << t.kl.tid_shift) |
-                                               ((unsigned long long)i0 << t.kl.start_shift) | l1;
-                const unsigned long long sv = make_sv(b.seq_base + (uint64_t)S.tile * EX_TILE + rl, 0u, strand);
-                const uint32_t off_cat = (l0 & 0xFFFFu) | (read_category(flag, nh) << 16) | ((uint32_t)strand_class(strand) << 18);
-                const uint32_t idx = atomicAdd(&S.region_fill, 1u);
-                uint4 *dst = reinterpret_cast<uint4 *>(region + idx);
-                __stcs(dst, make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)sv, (uint32_t)(sv >> 32)));
-                __stcs(dst + 1, make_uint4(pos, i0 + l1 + l2, off_cat, tid));
+                                           bool valid, uint32_t rl, int lane, unsigned long long &events) {
+    bool emit = false, general = false;
+    uint32_t pos = 0u, i0 = 0u, l0 = 0u, l1 = 0u, l2 = 0u, flag = 0u, nh = 0u;
+    if (valid) {
+        const uint32_t c0 = S.off[rl], n_cigar = S.off[rl + 1] - c0;
+        const uint32_t w0 = cigar_word(S, b.cigar, c0), w1 = cigar_word(S, b.cigar, c0 + 1);
+        const uint32_t w2 = n_cigar == 3u ? cigar_word(S, b.cigar, c0 + 2) : 0u;
+        const uint32_t o0 = w0 & 15u, o1 = w1 & 15u, o2 = w2 & 15u;
+        const uint32_t known = 0x1BFu, aligned = 0x181u; /* MIDNSH=X ; M=X */
+        if (!((known >> o0) & (known >> o1) & (known >> o2) & 1u)) {
+            general = true; /* the full automaton reports the unknown operation exactly */
+        } else if (n_cigar == 3u && o1 == OP_N && ((aligned >> o0) & (aligned >> o2) & 1u)) {
+            /* the one candidate: anchor_start = pos, intron = [pos + l0, + l1), anchor_end = intron_end + l2, mismatches =
+             * the X lengths, no indels.  Operation lengths are below 2^28 and pos is a BAM int32, so 32-bit arithmetic
+             * gives what the reference's 64-bit arithmetic gives wherever the result is usable (a start outside
+             * [0, 2^31) is reported). */
+            l0 = w0 >> 4; l1 = w1 >> 4; l2 = w2 >> 4;
+            flag = S.flag[rl]; nh = S.nh[rl];
+            const uint32_t lbad = o0 == OP_X ? l0 : 0u, rbad = o2 == OP_X ? l2 : 0u;
+            /* junction_qc (junctions_extractor.cc:384-401) */
+            if (read_may_emit(p, flag, nh) && l1 >= p.min_intron_length && l1 <= p.max_intron_length &&
+                l0 - lbad >= p.min_anchor_length && l2 - rbad >= p.min_anchor_length) {
+                events++;
+                pos = (uint32_t)S.pos[rl];
+                i0 = pos + l0;
+                if (i0 > 0x7FFFFFFFu) atomicOr(t.overflow, OVF_START); else emit = true;
             }
         }
     }
+    const unsigned em = __ballot_sync(0xFFFFFFFFu, emit);
+    if (em) {
+        const int leader = __ffs(em) - 1;
+        uint32_t idx = 0u;
+        if (lane == leader) idx = atomicAdd(&S.region_fill, (uint32_t)__popc(em));
+        idx = __shfl_sync(0xFFFFFFFFu, idx, leader) + (uint32_t)__popc(em & ((1u << lane) - 1u));
+        if (emit) {
+            const char strand = read_strand(p.strandness, flag, S.xs[rl]);
+            const uint32_t tid = (uint32_t)S.tid[rl];
+            const unsigned long long key = ((unsigned long long)(tid & t.kl.tid_mask) << t.kl.tid_shift) |
+                                           ((unsigned long long)i0 << t.kl.start_shift) | l1;
+            const unsigned long long sv = make_sv(b.seq_base + (uint64_t)S.tile * EX_TILE + rl, 0u, strand);
+            const uint32_t off_cat = (l0 & 0xFFFFu) | (read_category(flag, nh) << 16) | ((uint32_t)strand_class(strand) << 18);
+            uint4 *dst = reinterpret_cast<uint4 *>(region + idx);
+            __stcs(dst, make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)sv, (uint32_t)(sv >> 32)));
+            __stcs(dst + 1, make_uint4(pos, i0 + l1 + l2, off_cat, tid));
+        }
+    }
+    if (general) walk_record(b, p, t, S, region, rl, events);
 }
 
-template <int LOOKAHEAD, int WORKERS>
-__global__ void __launch_bounds__((WORKERS + 1) * 32, 2) k_extract_tma(BatchView b, uint32_t n_cigar_words, ExtractParams p, Tables t,
+template <int LOOKAHEAD, int WORKERS, int STAGES, int BLOCKS>
+__global__ void __launch_bounds__((WORKERS + 1) * 32, BLOCKS) k_extract_tma(BatchView b, uint32_t n_cigar_words, ExtractParams p, Tables t,
                                                                Event *out, TileInfo *tile_info, uint32_t n_full_tiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ExStage *stages = reinterpret_cast<ExStage *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + EX_STAGES * sizeof(ExStage)); /* TMA bytes have landed */
-    uint64_t *empty = full + EX_STAGES;                                                    /* every worker has left */
-    uint64_t *classified = empty + EX_STAGES;                                              /* all rounds are done */
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + STAGES * sizeof(ExStage)); /* TMA bytes have landed */
+    uint64_t *empty = full + STAGES;                                                    /* every worker has left */
+    uint64_t *classified = empty + STAGES;                                              /* all rounds are done */
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < EX_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1u);
             mbar_init(&empty[s], (uint32_t)WORKERS);
             mbar_init(&classified[s], (uint32_t)EX_ROUNDS);
@@ -702,12 +715,12 @@ __global__ void __launch_bounds__((WORKERS + 1) * 32, 2) k_extract_tma(BatchView
             nc0 = __ldg(&b.cigar_off[(uint64_t)first * EX_TILE]);
             nc1 = __ldg(&b.cigar_off[(uint64_t)first * EX_TILE + EX_TILE]);
         }
-        for (uint32_t it = 0; it < my_tiles + EX_STAGES; ++it) {
-            const int s = (int)(it % EX_STAGES);
+        for (uint32_t it = 0; it < my_tiles + STAGES; ++it) {
+            const int s = (int)(it % STAGES);
             ExStage &S = stages[s];
-            if (it >= (uint32_t)EX_STAGES) {
+            if (it >= (uint32_t)STAGES) {
                 /* the tile that occupied this stage has been left by every worker */
-                mbar_wait(&empty[s], ((it / EX_STAGES) & 1u) ^ 1u);
+                mbar_wait(&empty[s], ((it / STAGES) & 1u) ^ 1u);
                 tile_info[S.tile] = TileInfo{S.region_fill, S.off[0], 0u, 0u};
                 S.n_lists = S.next_round = S.rounds_done = S.next_short = S.next_long = S.region_fill = 0u;
             }
@@ -745,21 +758,21 @@ __global__ void __launch_bounds__((WORKERS + 1) * 32, 2) k_extract_tma(BatchView
     /* ---------------- workers ---------------- */
     unsigned long long live_words = 0ull, events = 0ull;
     for (uint32_t it = 0; it < my_tiles; ++it) {
-        const int s = (int)(it % EX_STAGES);
+        const int s = (int)(it % STAGES);
         ExStage &S = stages[s];
         /* (1) rounds of the tiles ahead whose data is already here, nearest first */
 #pragma unroll
         for (uint32_t d = 1; d <= (uint32_t)LOOKAHEAD; ++d) {
             if (it + d < my_tiles) {
-                const int s1 = (int)((it + d) % EX_STAGES);
-                if (mbar_test(&full[s1], ((it + d) / EX_STAGES) & 1u))
+                const int s1 = (int)((it + d) % STAGES);
+                if (mbar_test(&full[s1], ((it + d) / STAGES) & 1u))
                     take_rounds(stages[s1], s1, classified, lane, live_words);
             }
         }
         /* (2) this tile must be classified before it can be walked: help with what is left, then wait for the rest */
-        mbar_wait(&full[s], (it / EX_STAGES) & 1u);
+        mbar_wait(&full[s], (it / STAGES) & 1u);
         take_rounds(S, s, classified, lane, live_words);
-        mbar_wait(&classified[s], (it / EX_STAGES) & 1u);
+        mbar_wait(&classified[s], (it / STAGES) & 1u);
         /* (3) chunks of this tile: 32 listed records at a time, longest CIGARs first */
         const uint32_t n_lists = *((volatile uint32_t *)&S.n_lists);
         const uint32_t n_short = n_lists & 0xFFFFu, n_long = n_lists >> 16;
@@ -776,7 +789,7 @@ __global__ void __launch_bounds__((WORKERS + 1) * 32, 2) k_extract_tma(BatchView
             if (lane == 0) c = *((volatile uint32_t *)&S.next_short) >= n_short ? 0xFFFFFFFFu : atomicAdd(&S.next_short, 32u);
             c = __shfl_sync(0xFFFFFFFFu, c, 0);
             if (c >= n_short) break;
-            if (c + lane < n_short) walk_short(b, p, t, S, region, S.list[c + lane], events);
+            walk_short(b, p, t, S, region, c + lane < n_short, c + lane < n_short ? S.list[c + lane] : 0u, lane, events);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -802,16 +815,15 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
                            aligned16(b.nh) && aligned16(b.xs) && aligned16(b.cigar_off) && aligned16(b.cigar);
     uint64_t first_simple = 0;
     if (pipelined) {
+        /* measured on B200 (100 M short reads): 2048-record tiles with 15 workers, a 2-stage ring and
+         * 2 blocks per SM 0.644 ms; 11 / 13 workers 0.666 / 0.649; one block of 31 workers with 3 / 4 stages 0.756 / 0.686;
+         * 1024-record tiles: 15 workers x 4 stages x 2 blocks 0.716, 7 x 2 x 4 0.668, 5 x 2 x 4 0.727; look-ahead of
+         * 2 / 3 tiles and named barriers were slower still */
+        auto kernel = k_extract_tma<EX_LOOKAHEAD, EX_WORKER_WARPS, EX_STAGES, EX_BLOCKS>;
         const size_t smem = EX_STAGES * sizeof(ExStage) + 3 * EX_STAGES * sizeof(uint64_t);
-        /* measured on B200 (100 M short reads): look-ahead 1 / 2 / 3 tiles: 0.74 / 0.77 / 0.81 ms; 11 / 13 / 15 workers
-         * 0.74 - 0.78 ms; named barriers 1.05 ms */
-        auto kernel = k_extract_tma<EX_LOOKAHEAD, EX_WORKER_WARPS>;
-        {
-            /* per device (a process may drive several): cheap enough to repeat */
-            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
-        const uint64_t max_blocks = (uint64_t)sm_count * 2;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); /* per device: repeated */
+        if (e != cudaSuccess) return e;
+        const uint64_t max_blocks = (uint64_t)sm_count * EX_BLOCKS;
         const int blocks = (int)(n_full < max_blocks ? n_full : max_blocks);
         kernel<<<blocks, (EX_WORKER_WARPS + 1) * 32, smem, st>>>(b, (uint32_t)n_cigar, p, t, out, tile_info, (uint32_t)n_full);
         if (launches) (*launches)++;

@@ -89,7 +89,10 @@ __global__ void __launch_bounds__(256) k_fin_list(Tables t, const uint32_t *name
 static const int SS_MAX_BUCKETS = 4096;
 static const int SS_MAX_SAMPLE = 8192;
 static const int SS_BUCKET = 256;       /* keys per bucket the splitters aim at */
-static const int SS_SMEM_BUCKET = 1024; /* elements a bucket may have to be ranked in shared memory */
+/* Elements a bucket may have to be sorted in shared memory.  Junction ids are handed out to thread blocks in blocks of
+ * 64, so the keys arrive shuffled over tens of thousands of positions and the splitters behave like a random sample of 3
+ * per bucket: one sort in four saw a bucket of more than 4 times the average (1024), which then went the slow way. */
+static const int SS_SMEM_BUCKET = 2048;
 
 
 __device__ __forceinline__ bool pair_less(unsigned long long ka, uint32_t sa, unsigned long long kb, uint32_t sb) {

@@ -238,27 +238,38 @@ __device__ __forceinline__ void fold_write_back(const Tables &t, FoldCache &c, i
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables t, Event *ev, TileInfo *tile_info, uint64_t n_tiles) {
+__global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables t, Event *ev, TileInfo *tile_info, uint64_t n_tiles, uint32_t prefetch) {
     __shared__ FoldCache s_cache[FOLD_WARPS];
     __shared__ IdPool s_pool;
     if (threadIdx.x == 0) id_pool_load(t, &s_pool);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     FoldCache &c = s_cache[threadIdx.x >> 5];
-    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     c.key[lane] = EMPTY64;
     c.key[lane + 32] = EMPTY64;
     __syncwarp();
     LogStage log{c.stage, 0u};
     uint32_t spare = JID_NONE; /* see junction_probe */
     unsigned long long unfolded = 0ull;
+    /* Tiles are handed out one at a time from a counter, in stream order: a warp that drew short tiles takes more of
+     * them (with a fixed assignment a quarter of the warp time was spent waiting for the slowest warp at the end), and
+     * the tiles in flight stay neighbours, whose junctions share the lines of the table that are hot in L2.  The next
+     * tile is claimed, and its info requested, while the current one is folded. */
+    auto claim = [&]() {
+        unsigned long long v = 0ull;
+        if (lane == 0) v = atomicAdd(t.next_tile, 1ull);
+        return (uint64_t)__shfl_sync(0xFFFFFFFFu, v, 0);
+    };
+    uint64_t tile = claim(), tile_next = n_tiles;
     uint2 next = make_uint2(0u, 0u);
-    if (warp0 < n_tiles) next = __ldg(reinterpret_cast<const uint2 *>(tile_info + warp0));
-    for (uint64_t tile = warp0; tile < n_tiles; tile += n_warps) {
+    if (tile < n_tiles) {
+        next = __ldg(reinterpret_cast<const uint2 *>(tile_info + tile));
+        tile_next = claim();
+    }
+    for (; tile < n_tiles; tile = tile_next, tile_next = tile_next < n_tiles ? claim() : n_tiles) {
         const uint32_t cnt = next.x;
         const uint64_t base = tile_event_base(next.y);
-        if (tile + n_warps < n_tiles) next = __ldg(reinterpret_cast<const uint2 *>(tile_info + tile + n_warps));
+        if (tile_next < n_tiles) next = __ldg(reinterpret_cast<const uint2 *>(tile_info + tile_next));
         if (cnt == 0u) continue;
         uint32_t kept = 0u; /* events of this tile left unfolded (table full) */
         Event nxt = load_event(ev, base + lane, (uint32_t)lane < cnt, lane);
@@ -391,6 +402,9 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
                 }
                 log_append(t, log, counted && place == DENSE_NONE, olog_entry(jid, off, 1u));
             }
+            /* the home slots of the next chunk's keys on their way into L1 while this chunk's atomics drain */
+            if ((prefetch & 1u) && k0 + 32u + lane < cnt)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(&t.slots[junction_hash(nxt.key, nxt.tid) & t.cap_mask]));
             /* events that could not be folded go back to the front of the region (behind what was read already) */
             const unsigned km = __ballot_sync(0xFFFFFFFFu, keep);
             if (km) {
@@ -414,13 +428,16 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
 
 void launch_fold(int mode, const Tables &t, Event *ev, TileInfo *tile_info, uint64_t n_tiles, int sm_count, cudaStream_t st) {
     if (n_tiles == 0) return;
-    const uint64_t want = (n_tiles + FOLD_WARPS - 1) / FOLD_WARPS; /* one tile per warp at a time */
+    uint32_t prefetch = 0u;
+    if (const char *e = getenv("IPX_K2_PREFETCH")) prefetch = (uint32_t)atoi(e);
+    cudaMemsetAsync(t.next_tile, 0, sizeof(unsigned long long), st);
+    const uint64_t want = (n_tiles + FOLD_WARPS - 1) / FOLD_WARPS;
     const uint64_t max_blocks = (uint64_t)sm_count * IPX_K2_BLOCKS; /* what is resident at once */
     const int blocks = (int)(want < max_blocks ? want : max_blocks);
     switch (mode) {
-        case MODE_SINGLE: k_fold<MODE_SINGLE><<<blocks, FOLD_WARPS * 32, 0, st>>>(t, ev, tile_info, n_tiles); break;
-        case MODE_PASS1: k_fold<MODE_PASS1><<<blocks, FOLD_WARPS * 32, 0, st>>>(t, ev, tile_info, n_tiles); break;
-        default: k_fold<MODE_PASS2><<<blocks, FOLD_WARPS * 32, 0, st>>>(t, ev, tile_info, n_tiles); break;
+        case MODE_SINGLE: k_fold<MODE_SINGLE><<<blocks, FOLD_WARPS * 32, 0, st>>>(t, ev, tile_info, n_tiles, prefetch); break;
+        case MODE_PASS1: k_fold<MODE_PASS1><<<blocks, FOLD_WARPS * 32, 0, st>>>(t, ev, tile_info, n_tiles, prefetch); break;
+        default: k_fold<MODE_PASS2><<<blocks, FOLD_WARPS * 32, 0, st>>>(t, ev, tile_info, n_tiles, prefetch); break;
     }
 }
 

@@ -57,7 +57,7 @@ static const uint32_t BASE_UNSET = 0xFFFFFFFFu;
  * as they show up: the first offset no row takes yet centres the next free row on itself (slot.base[r - 1]), and from
  * then on the row takes [base, base + DENSE_W) less what earlier rows take.  What no row takes goes to the log. */
 static const uint32_t DENSE_ROWS = 4;
-static const uint32_t DENSE_LEAD = DENSE_W / 2;
+static const uint32_t DENSE_LEAD = DENSE_W / 2; /* default of Tables::dense_lead */
 static const int SV_ORD_BITS = 20;
 static const int SV_SEQ_SHIFT = 28;
 
@@ -170,6 +170,7 @@ struct Tables {
     uint32_t *jslot;          /* hash slot of the junction's key (for clear) */
     JStat *stat;
     uint32_t *dense;          /* [max_j][DENSE_ROWS][DENSE_W] read counts per offset (see DENSE_ROWS), or NULL when disabled */
+    uint32_t dense_lead;      /* a row given out to offset x takes [x - dense_lead, x - dense_lead + DENSE_W) */
     int32_t extra_rows;       /* rows 1 .. are given out (off for long reads, whose offsets scatter: everything >= DENSE_W
                                  goes to the log then) */
     uint32_t *olog_cnt;       /* entries of the read-offset log that name the junction */
@@ -183,6 +184,7 @@ struct Tables {
     unsigned long long *n_events;  /* events that passed junction_qc */
     unsigned long long *n_live;    /* CIGAR words of live records */
     unsigned long long *err_sv;    /* min over failing records of (record seq << 28 | code); EMPTY64 = none */
+    unsigned long long *next_tile;  /* K2: the next tile to hand out (reset by its launcher) */
     unsigned long long *n_unfolded; /* events K2 left in the event buffer because a table was full (see k_fold) */
     uint32_t *overflow;            /* bit set: 1 hash slots / junction rows full, 2 log full, 4 intron start beyond 2^31,
                                       8 mailbox slot too small, 16 a peer never published its export */
@@ -313,7 +315,9 @@ __device__ __forceinline__ Found junction_probe(const Tables &t, IdPool *pool, u
             } else {
                 t.jkey[spare] = key;
                 t.jtid[spare] = tid;
-                __threadfence(); /* the identity is visible before the id is */
+                /* Whoever meets the id during the same launch reads jtid, and only in the wide layout: there the identity
+                 * must be visible before the id is.  (A fence per insertion was a quarter of the fold's stall samples.) */
+                if (t.kl.wide) __threadfence();
                 if (slot_claim(s, key, spare, BASE_UNSET, k, j, f.base[0])) {
                     t.jslot[spare] = (uint32_t)h;
                     f.jid = spare;
@@ -359,7 +363,7 @@ __device__ __forceinline__ uint32_t dense_place(const Tables &t, uint32_t slot, 
     for (uint32_t r = 0; r < DENSE_ROWS - 1; ++r) {
         if (base[r] == BASE_UNSET) {
             /* the next free row: centre it on this offset, unless somebody was faster */
-            const uint32_t mine = offset - DENSE_LEAD;
+            const uint32_t mine = offset - t.dense_lead;
             const uint32_t old = atomicCAS(&t.slots[slot].base[r], BASE_UNSET, mine);
             base[r] = old == BASE_UNSET ? mine : old;
         }
