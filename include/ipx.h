@@ -245,6 +245,15 @@ int ipx_clear(ipx_handle *h);
  * junctions.cc:76-105), then sort_by_anchors + renumber_junctions (:201-205, :221-223).
  * Strand-conflict lines the reference prints to stderr are returned in `conflict_log`. */
 int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ipx_table **out, ipx_text *conflict_log);
+/* The same for one key range of a merge that is sharded over several devices (config 5: one handle per device, every
+ * handle gets the rows of a contiguous range of chromosomes -- a key lives in one range, so no exchange is needed).
+ * `row_ids[i]` is the position of row i in the whole input (file, row order; NULL: i).  What depends on that order
+ * across ranges comes back with row ids, so that the caller can restore it: `conflict_rows[k]` is the row the k-th line
+ * of `conflict_log` was raised at (malloc'ed: ipx_free), and on IPX_ERR_MERGE `*fail_row` is the row of the fatal
+ * disagreement (the reference stops at the first one in input order, after the conflict lines of the rows before it). */
+int ipx_merge_rows_fold_part(ipx_handle *h, const ipx_merge_rows *rows, const uint64_t *row_ids, ipx_table **out,
+                             ipx_text *conflict_log, uint64_t **conflict_rows, uint64_t *n_conflict_rows, uint64_t *fail_row);
+void ipx_free(void *p);
 
 /* Multi-GPU exchange (one process per GPU).  After ipx_finalize_device():
  *  ipx_partial_sizes   rows per destination rank for the given key splitters (n_parts - 1 of them,

@@ -3,7 +3,9 @@
  * B200 behind ipx_merge_rows_fold (include/ipx.h).  Host side only: options, TSV loading, text output.
  */
 #include <getopt.h>
+#include <algorithm>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include "calls_tsv.h"
@@ -96,6 +98,68 @@ static void parse_options(int argc, char *argv[], Options &o) {
         cmd_error("a least one input call TSV required on the command list or with the --intron_call_files (-i) option");
 }
 
+/* One key range of the merge on one device: the rows whose chromosomes fall into the range, in input order. */
+struct Part {
+    int device = 0;
+    vector<int32_t> chrom;
+    vector<uint32_t> i0, i1, a0, a1, sites, counts;
+    vector<char> strand;
+    vector<float> conf;
+    vector<uint64_t> row_ids;
+    ipx_merge_rows rows;
+    /* results */
+    ipx_table *table = nullptr;
+    int rc = IPX_OK;
+    string error, log;
+    vector<uint64_t> log_rows;
+    uint64_t fail_row = ~0ull;
+};
+
+/* Chromosome ranges with about the same number of rows each, contiguous in the order the outputs are sorted by
+ * (chromosome name): part_of[chromosome index]. */
+static vector<int> balanced_ranges(const ipx::CallsRows &rows, int n_parts) {
+    const size_t nc = rows.chrom_names.size();
+    vector<uint64_t> per_chrom(nc, 0);
+    for (int32_t c : rows.chrom) per_chrom[c]++;
+    vector<uint32_t> order(nc);
+    for (size_t i = 0; i < nc; i++) order[i] = (uint32_t)i;
+    sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return rows.chrom_names[a] < rows.chrom_names[b]; });
+    vector<int> part_of(nc, 0);
+    const uint64_t total = rows.chrom.size();
+    uint64_t seen = 0;
+    for (uint32_t c : order) {
+        /* the part in which the chromosome's middle row falls */
+        const uint64_t mid = seen + per_chrom[c] / 2;
+        part_of[c] = total ? (int)min<uint64_t>((uint64_t)n_parts - 1, mid * (uint64_t)n_parts / total) : 0;
+        seen += per_chrom[c];
+    }
+    return part_of;
+}
+
+static void fold_part(Part *p, const vector<const char *> *names) {
+    ipx_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.device = p->device;
+    ipx_handle *h = nullptr;
+    if (ipx_create(&prm, &h) != IPX_OK) {
+        p->rc = IPX_ERR_CUDA;
+        p->error = "no usable CUDA device: the merge fold needs an NVIDIA B200 (sm_100a) GPU";
+        return;
+    }
+    p->rc = ipx_set_targets(h, (int32_t)names->size(), names->data());
+    if (p->rc == IPX_OK) {
+        ipx_text log;
+        uint64_t *log_rows = nullptr, n_log_rows = 0;
+        p->rc = ipx_merge_rows_fold_part(h, &p->rows, p->row_ids.data(), &p->table, &log, &log_rows, &n_log_rows, &p->fail_row);
+        if (log.data) p->log.assign(log.data, log.len);
+        ipx_text_free(&log);
+        if (log_rows) p->log_rows.assign(log_rows, log_rows + n_log_rows);
+        ipx_free(log_rows);
+    }
+    if (p->rc != IPX_OK) p->error = ipx_last_error(h);
+    ipx_destroy(h);
+}
+
 /* intron_prospector_merge (intronProspectorMerge.cc:207-238) */
 static void merge(const Options &opts) {
     ipx::CallsRows rows;
@@ -105,28 +169,110 @@ static void merge(const Options &opts) {
     } catch (const std::exception &e) {
         parse_error = e.what(); /* rows read before the bad one are still folded: their stderr lines come first */
     }
-    rows.bind();
-    ipx_params p;
-    memset(&p, 0, sizeof(p));
-    if (const char *d = getenv("IPX_DEVICE")) p.device = atoi(d);
-    ipx_handle *h = nullptr;
-    if (ipx_create(&p, &h) != IPX_OK) throw runtime_error("no usable CUDA device: the merge fold needs an NVIDIA B200 (sm_100a) GPU");
-    struct Guard {
-        ipx_handle *h;
-        ~Guard() { ipx_destroy(h); }
-    } guard{h};
     if (rows.chrom_names.empty()) rows.chrom_names.push_back("");
     rows.bind();
-    check_ipx(h, ipx_set_targets(h, (int32_t)rows.chrom_ptrs.size(), rows.chrom_ptrs.data()));
-    ipx_table *t = nullptr;
-    ipx_text log;
-    int rc = ipx_merge_rows_fold(h, &rows.rows, &t, &log);
-    if (log.data) cerr << string(log.data, log.len);
-    ipx_text_free(&log);
-    if (rc != IPX_OK) throw runtime_error(ipx_last_error(h));
-    if (!parse_error.empty()) {
-        ipx_table_free(t);
-        throw runtime_error(parse_error);
+    /* Key ranges over the devices of this host (BASELINE config 5): every device folds the rows of a contiguous range of
+     * chromosomes.  A key lives in one range, so the partial tables are simply concatenated in key order.
+     * IPX_MERGE_DEVICES=n caps the number of devices (default: all that are visible, one when the input is small);
+     * IPX_MERGE_PARTS=n asks for n ranges whatever the number of devices (range k runs on device k mod devices: tests);
+     * IPX_DEVICE picks the device of a single-device run. */
+    const int n_dev = max(1, ipx_device_count()); /* (without a device ipx_create fails below: there is no other path) */
+    int n_parts = rows.chrom.size() >= (1u << 20) ? n_dev : 1;
+    if (const char *e = getenv("IPX_MERGE_DEVICES")) n_parts = max(1, min(atoi(e), n_dev));
+    if (const char *e = getenv("IPX_MERGE_PARTS")) n_parts = max(1, min(atoi(e), 64));
+    n_parts = (int)min<size_t>((size_t)n_parts, rows.chrom_names.size());
+    vector<unique_ptr<Part>> parts;
+    if (n_parts <= 1) {
+        parts.emplace_back(new Part());
+        Part &p = *parts[0];
+        if (const char *d = getenv("IPX_DEVICE")) p.device = atoi(d);
+        p.rows = rows.rows;
+        p.row_ids.resize(rows.chrom.size());
+        for (size_t i = 0; i < p.row_ids.size(); i++) p.row_ids[i] = i;
+        fold_part(&p, &rows.chrom_ptrs);
+    } else {
+        const vector<int> part_of = balanced_ranges(rows, n_parts);
+        for (int k = 0; k < n_parts; k++) {
+            parts.emplace_back(new Part());
+            parts[k]->device = k % n_dev;
+        }
+        /* the rows of every part, gathered by a thread per part, which then folds them on its device */
+        vector<thread> threads;
+        for (int k = 0; k < n_parts; k++)
+            threads.emplace_back([&, k]() {
+                Part &p = *parts[k];
+                const size_t n = rows.chrom.size();
+                size_t mine = 0;
+                for (size_t i = 0; i < n; i++) mine += part_of[rows.chrom[i]] == k;
+                p.chrom.reserve(mine); p.i0.reserve(mine); p.i1.reserve(mine); p.a0.reserve(mine); p.a1.reserve(mine);
+                p.sites.reserve(mine); p.counts.reserve(3 * mine); p.strand.reserve(mine); p.conf.reserve(mine); p.row_ids.reserve(mine);
+                for (size_t i = 0; i < n; i++) {
+                    if (part_of[rows.chrom[i]] != k) continue;
+                    p.chrom.push_back(rows.chrom[i]); p.i0.push_back(rows.i0[i]); p.i1.push_back(rows.i1[i]);
+                    p.a0.push_back(rows.a0[i]); p.a1.push_back(rows.a1[i]); p.sites.push_back(rows.sites[i]);
+                    p.counts.push_back(rows.counts[3 * i]); p.counts.push_back(rows.counts[3 * i + 1]); p.counts.push_back(rows.counts[3 * i + 2]);
+                    p.strand.push_back(rows.strand[i]); p.conf.push_back(rows.conf[i]); p.row_ids.push_back(i);
+                }
+                p.rows = rows.rows; /* the dictionaries */
+                p.rows.n_rows = p.chrom.size();
+                p.rows.chrom = p.chrom.data(); p.rows.intron_start = p.i0.data(); p.rows.intron_end = p.i1.data();
+                p.rows.anchor_start = p.a0.data(); p.rows.anchor_end = p.a1.data(); p.rows.strand = p.strand.data();
+                p.rows.sites = p.sites.data(); p.rows.counts = p.counts.data(); p.rows.confidence = p.conf.data();
+                fold_part(&p, &rows.chrom_ptrs);
+            });
+        for (auto &t : threads) t.join();
+    }
+    struct Tables {
+        vector<unique_ptr<Part>> &parts;
+        ~Tables() {
+            for (auto &p : parts) ipx_table_free(p->table);
+        }
+    } guard{parts};
+    /* what the reference does in input order: strand-conflict lines on stderr as their rows come by, the fatal
+     * disagreement at the first row that has one */
+    uint64_t fail_row = ~0ull;
+    string fail_text;
+    for (auto &p : parts) {
+        if (p->rc != IPX_OK && p->rc != IPX_ERR_MERGE) throw runtime_error(p->error);
+        if (p->rc == IPX_ERR_MERGE && p->fail_row < fail_row) {
+            fail_row = p->fail_row;
+            fail_text = p->error;
+        }
+    }
+    vector<pair<uint64_t, string>> lines;
+    for (auto &p : parts) {
+        size_t pos = 0, k = 0;
+        while (pos < p->log.size()) {
+            size_t nl = p->log.find('\n', pos);
+            if (nl == string::npos) nl = p->log.size() - 1;
+            const uint64_t row = k < p->log_rows.size() ? p->log_rows[k] : 0;
+            if (row < fail_row) lines.emplace_back(row, p->log.substr(pos, nl + 1 - pos));
+            pos = nl + 1;
+            k++;
+        }
+    }
+    stable_sort(lines.begin(), lines.end(), [](const pair<uint64_t, string> &a, const pair<uint64_t, string> &b) { return a.first < b.first; });
+    for (auto &l : lines) cerr << l.second;
+    if (fail_row != ~0ull) throw runtime_error(fail_text);
+    if (!parse_error.empty()) throw runtime_error(parse_error);
+    /* the ranges are contiguous in the order of the outputs: sjN = position in anchor order over all of them */
+    vector<Part *> in_order;
+    for (auto &p : parts) in_order.push_back(p.get());
+    if (n_parts > 1) {
+        /* by the name of a part's first chromosome (parts without rows are empty tables) */
+        vector<pair<string, Part *>> keyed;
+        for (Part *p : in_order)
+            if (p->table && p->table->n_junctions) keyed.emplace_back(rows.chrom_names[p->table->chrom[0]], p);
+        sort(keyed.begin(), keyed.end(), [](const pair<string, Part *> &a, const pair<string, Part *> &b) { return a.first < b.first; });
+        in_order.clear();
+        for (auto &k : keyed) in_order.push_back(k.second);
+        uint32_t base = 0;
+        for (Part *p : in_order) {
+            vector<uint32_t> ij(p->table->ijunc, p->table->ijunc + p->table->n_junctions);
+            for (auto &x : ij) x += base;
+            ipx_table_set_ijunc(p->table, ij.data());
+            base += (uint32_t)p->table->n_junctions;
+        }
     }
     auto emit = [&](const string &fn, int fmt, bool header) {
         if (fn == "") return;
@@ -137,15 +283,18 @@ static void merge(const Options &opts) {
             out.write(txt);
             ipx_text_free(&txt);
         }
-        if (ipx_format(t, rows.chrom_ptrs.data(), fmt, 0.0f, 0, t->n_junctions, &txt) != IPX_OK) throw runtime_error("formatting failed");
-        out.write(txt);
-        ipx_text_free(&txt);
+        for (Part *p : in_order) {
+            if (!p->table) continue;
+            if (ipx_format(p->table, rows.chrom_ptrs.data(), fmt, 0.0f, 0, p->table->n_junctions, &txt) != IPX_OK)
+                throw runtime_error("formatting failed");
+            out.write(txt);
+            ipx_text_free(&txt);
+        }
     };
     emit(opts.junction_bed, IPX_FMT_JUNCTION_BED, false);
     emit(opts.intron_bed, IPX_FMT_INTRON_BED9, false);
     emit(opts.intron_bed6, IPX_FMT_INTRON_BED6, false);
     emit(opts.intron_call_tsv, IPX_FMT_INTRON_TSV, true);
-    ipx_table_free(t);
 }
 
 int main(int argc, char *argv[]) {

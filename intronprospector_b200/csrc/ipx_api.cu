@@ -1883,8 +1883,26 @@ void merge_upload_worker(ipx_handle *h, const ipx_merge_rows *rows, const MergeC
 
 }  // namespace
 
+extern "C" void ipx_free(void *p) { free(p); }
+
 extern "C" int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ipx_table **out, ipx_text *conflict_log) {
+    return ipx_merge_rows_fold_part(h, rows, nullptr, out, conflict_log, nullptr, nullptr, nullptr);
+}
+
+extern "C" int ipx_merge_rows_fold_part(ipx_handle *h, const ipx_merge_rows *rows, const uint64_t *row_ids, ipx_table **out,
+                                        ipx_text *conflict_log, uint64_t **conflict_rows, uint64_t *n_conflict_rows, uint64_t *fail_row) {
     if (!h || !rows || !out) return IPX_ERR_ARG;
+    if (conflict_rows) *conflict_rows = nullptr;
+    if (n_conflict_rows) *n_conflict_rows = 0;
+    if (fail_row) *fail_row = ~0ull;
+    std::vector<uint64_t> log_rows;
+    auto give_log_rows = [&]() {
+        if (!conflict_rows || !n_conflict_rows || log_rows.empty()) return;
+        *conflict_rows = (uint64_t *)malloc(log_rows.size() * sizeof(uint64_t));
+        if (!*conflict_rows) return;
+        memcpy(*conflict_rows, log_rows.data(), log_rows.size() * sizeof(uint64_t));
+        *n_conflict_rows = log_rows.size();
+    };
     *out = nullptr;
     if (conflict_log) { conflict_log->data = nullptr; conflict_log->len = 0; }
     cudaSetDevice(h->device);
@@ -2089,12 +2107,15 @@ extern "C" int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ip
                 log += "intron records have different strand:" +
                        describe(h, rows, rows->chrom[r], rows->intron_start[r], rows->intron_end[r], rstrand, rsite) + " with " +
                        describe(h, rows, ht->chrom[ti], ht->i0[ti], ht->i1[ti], ht->strand[ti], site[ti]) + "\n";
+                log_rows.push_back(row_ids ? row_ids[r] : r);
                 continue;
             } else if (strcmp(rows->site_strings[rsite], rows->site_strings[site[ti]]) != 0) {
                 std::string msg = "intron records have different splice sites:" +
                                   describe(h, rows, rows->chrom[r], rows->intron_start[r], rows->intron_end[r], rstrand, rsite) +
                                   " with " + describe(h, rows, ht->chrom[ti], ht->i0[ti], ht->i1[ti], ht->strand[ti], site[ti]);
                 if (conflict_log) give_text(log, conflict_log);
+                give_log_rows();
+                if (fail_row) *fail_row = row_ids ? row_ids[r] : r;
                 delete ht;
                 return fail(h, IPX_ERR_MERGE, "%s", msg.c_str());
             }
@@ -2124,6 +2145,7 @@ extern "C" int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ip
     h->totals.merge_rows += n;
     h->totals.junctions += J;
     if (conflict_log) give_text(log, conflict_log);
+    give_log_rows();
     *out = &ht->t;
     return IPX_OK;
 }

@@ -81,6 +81,31 @@ int ipx_merge_rows_fold(ipx_handle *h, const ipx_merge_rows *rows, ipx_table **o
     return rc;
 }
 
+/* one key range of a sharded merge: the oracle only ever folds everything at once (ipx_device_count() is 0 here), so the
+ * lines of its log are already in input order -- they are numbered as they come */
+int ipx_merge_rows_fold_part(ipx_handle *h, const ipx_merge_rows *rows, const uint64_t *row_ids, ipx_table **out,
+                             ipx_text *conflict_log, uint64_t **conflict_rows, uint64_t *n_conflict_rows, uint64_t *fail_row) {
+    (void)row_ids;
+    ipx_text log = {NULL, 0};
+    int rc = ipx_merge_rows_fold(h, rows, out, &log);
+    uint64_t n_lines = 0;
+    for (size_t i = 0; i < log.len; i++) n_lines += log.data[i] == '\n';
+    if (conflict_rows && n_conflict_rows) {
+        *conflict_rows = (uint64_t *)malloc((n_lines ? n_lines : 1) * sizeof(uint64_t));
+        for (uint64_t i = 0; i < n_lines; i++) (*conflict_rows)[i] = i;
+        *n_conflict_rows = n_lines;
+    }
+    if (fail_row) *fail_row = rc == IPX_ERR_MERGE ? n_lines : ~0ull;
+    if (conflict_log) *conflict_log = log; else ipxo_text_free(&log);
+    return rc;
+}
+void ipx_free(void *p) { free(p); }
+int ipx_table_set_ijunc(ipx_table *t, const uint32_t *ijunc) {
+    if (!t || (t->n_junctions && !ijunc)) return IPX_ERR_ARG;
+    memcpy((uint32_t *)t->ijunc, ijunc, t->n_junctions * sizeof(uint32_t)); /* (the oracle's tables own their columns) */
+    return IPX_OK;
+}
+
 int ipx_format(const ipx_table *t, const char *const *names, int format, float min_confidence, uint64_t begin, uint64_t end,
                ipx_text *out) {
     return ipxo_format(t, names, format, min_confidence, begin, end, out);

@@ -34,6 +34,21 @@ def test_merge_cli_matches_reference(built, tmp_path, extra):
         assert ref[k] is not None and ref[k] == gpu[k], "%s differs" % k
 
 
+@pytest.mark.parametrize("n_parts", [2, 5])
+def test_merge_cli_sharded_matches_reference(built, tmp_path, n_parts, monkeypatch):
+    """BASELINE config 5 through the tool: the fold sharded over key ranges (one handle and one thread per range; on a
+    multi-GPU host one device per range) against the reference binary -- files, and the strand-conflict lines on
+    stderr in input order although they are raised on different ranges."""
+    paths, _ = merge_synth.write_tables(str(tmp_path), n_samples=12, n_universe=30_000, conflicts=40)
+    rc_r, err_r, ref = run_merge(helpers.REF_MERGE, str(tmp_path), "ref", paths)
+    monkeypatch.setenv("IPX_MERGE_PARTS", str(n_parts))
+    rc_g, err_g, gpu = run_merge(helpers.GPU_MERGE, str(tmp_path), "gpu", paths)
+    assert rc_r == 0 and rc_g == 0, (err_r, err_g)
+    assert err_r == err_g and err_r.count(b"different strand") > 40
+    for k in ref:
+        assert ref[k] is not None and ref[k] == gpu[k], "%s differs" % k
+
+
 def test_merge_sharded_by_key_range(built, tmp_path):
     """Rows partitioned by chromosome range (no exchange needed: a key lives on one rank), one fold per rank; sjN is
     the index in anchor order, so a rank's numbers are its local ones plus the junction count of the ranks before."""
