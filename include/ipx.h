@@ -255,6 +255,36 @@ int ipx_merge_rows_fold_part(ipx_handle *h, const ipx_merge_rows *rows, const ui
                              ipx_text *conflict_log, uint64_t **conflict_rows, uint64_t *n_conflict_rows, uint64_t *fail_row);
 void ipx_free(void *p);
 
+/* Intron-call TSV rows tokenised on the device (Tsv::next_row + read_junction,
+ * tsv.hh:27-74, intronProspectorMerge.cc:164-177).  `bytes` = one uncompressed file WITHOUT its header line (any host
+ * memory; ipx_host_alloc'ed memory crosses the link faster), `columns` = where the header put the columns read_junction
+ * asks for.  One ipx_tsv_rows entry per line, in file order.  The device parses the plain form only (unsigned decimal
+ * integers that fit 32 bits, decimal fractions without sign or exponent and at most 8 fractional digits, the right number
+ * of columns); every other row has flags[i] != 0 and none of its values set: the caller parses the line
+ * bytes[line_off[i] .. + line_len[i]) with the reference's rules, which also produces the reference's error for it.
+ * IPX_ERR_ARG: an input this entry point does not take (4 GB or more, a column missing). */
+typedef struct ipx_tsv_columns {
+    int32_t n_columns; /* of the header: rows with another number of columns are flagged */
+    int32_t chrom, intron_start, intron_end, strand, uniq_mapped_count, multi_mapped_count, unsure_mapped_count, max_left_overhang,
+        max_right_overhang, confidence, splice_sites;
+} ipx_tsv_columns;
+typedef struct ipx_tsv_rows {
+    uint64_t n_rows;
+    const uint32_t *intron_start, *intron_end;
+    const uint32_t *anchor_start, *anchor_end; /* start - max_left_overhang, end + max_right_overhang (uint32 arithmetic) */
+    const uint32_t *counts;                    /* [n][3] uniq, multi, unsure */
+    const float *confidence;
+    const char *strand;                        /* first character of the column, 0 when it is empty */
+    const uint64_t *sites8;                    /* the splice_sites string, byte k in bits 8k .. 8k+7 */
+    const uint8_t *sites_len;                  /* <= 8 (longer strings are flagged) */
+    const uint32_t *chrom_off;                 /* the chrom string is bytes[chrom_off .. + chrom_len) */
+    const uint16_t *chrom_len;
+    const uint32_t *line_off, *line_len;       /* the line without its newline */
+    const uint8_t *flags;
+} ipx_tsv_rows;
+int ipx_tsv_tokenize(int32_t device, const char *bytes, uint64_t n_bytes, const ipx_tsv_columns *columns, ipx_tsv_rows **out);
+void ipx_tsv_rows_free(ipx_tsv_rows *rows);
+
 /* Multi-GPU exchange (one process per GPU).  After ipx_finalize_device():
  *  ipx_partial_sizes   rows per destination rank for the given key splitters (n_parts - 1 of them,
  *                      each = first key owned by the next rank: target index, intron_start)

@@ -153,7 +153,7 @@ ABI_SYMBOLS = [
     "ipx_thresholds_import", "ipx_count_deferred", "ipx_table_set_ijunc", "ipx_push_batch_compact",
     "ipx_mailbox_create", "ipx_mailbox_ipc_handle", "ipx_mailbox_ptr", "ipx_mailbox_connect", "ipx_partial_export_mail",
     "ipx_partial_import_mail", "ipx_exchange_settle", "ipx_sample_keys", "ipx_host_alloc", "ipx_host_free", "ipx_sync_uploads",
-    "ipx_merge_rows_fold_part", "ipx_free",
+    "ipx_merge_rows_fold_part", "ipx_free", "ipx_tsv_tokenize", "ipx_tsv_rows_free",
 ]
 IO_SYMBOLS = [
     "ipxio_last_error", "ipxio_open", "ipxio_close", "ipxio_n_targets", "ipxio_target_name", "ipxio_read_batch",

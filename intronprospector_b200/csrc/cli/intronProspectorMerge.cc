@@ -160,12 +160,24 @@ static void fold_part(Part *p, const vector<const char *> *names) {
     ipx_destroy(h);
 }
 
+/* the rows are tokenised on the device (ipx_tsv_tokenize); IPX_TSV_HOST=1 keeps the host parser (tests compare the two) */
+static int tokenizer_device = 0;
+static int tokenize_on_device(const char *bytes, uint64_t n, const ipx_tsv_columns *cols, ipx_tsv_rows **out) {
+    return ipx_tsv_tokenize(tokenizer_device, bytes, n, cols, out);
+}
+
 /* intron_prospector_merge (intronProspectorMerge.cc:207-238) */
 static void merge(const Options &opts) {
     ipx::CallsRows rows;
     string parse_error;
     try {
-        ipx::load_calls_tsvs(opts.input_calls_tsvs, opts.junction_filter, rows);
+        if (getenv("IPX_TSV_HOST")) {
+            ipx::load_calls_tsvs(opts.input_calls_tsvs, opts.junction_filter, rows);
+        } else {
+            if (const char *d = getenv("IPX_DEVICE")) tokenizer_device = atoi(d);
+            const ipx::TsvTokenizer tok{malloc, free, tokenize_on_device, ipx_tsv_rows_free};
+            ipx::load_calls_tsvs(opts.input_calls_tsvs, opts.junction_filter, rows, tok);
+        }
     } catch (const std::exception &e) {
         parse_error = e.what(); /* rows read before the bad one are still folded: their stderr lines come first */
     }

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
+#include <algorithm>
 #include <atomic>
 #include <memory>
 #include <stdexcept>
@@ -112,77 +113,214 @@ bool canonical(const std::string &s) {
 
 }  // namespace
 
+/* what the header says about the columns read_junction asks for (-1: absent, which only matters once a row is read) */
+struct Header {
+    int ncol = 0;
+    int c_chrom = -1, c_start = -1, c_end = -1, c_strand = -1, c_uniq = -1, c_multi = -1, c_unsure = -1, c_left = -1, c_right = -1,
+        c_conf = -1, c_sites = -1;
+    bool complete() const {
+        return c_chrom >= 0 && c_start >= 0 && c_end >= 0 && c_strand >= 0 && c_uniq >= 0 && c_multi >= 0 && c_unsure >= 0 && c_left >= 0 &&
+               c_right >= 0 && c_conf >= 0 && c_sites >= 0;
+    }
+};
+
+static Header read_header(const std::string &line) {
+    std::vector<std::string> words;
+    split_tabs(line, words);
+    Header h;
+    h.ncol = (int)words.size();
+    std::unordered_map<std::string, int> col;
+    for (int i = 0; i < h.ncol; i++) col[words[i]] = i; /* later duplicates win, as with map::operator[] */
+    auto need = [&](const char *name) -> int {
+        auto it = col.find(name);
+        return it == col.end() ? -1 : it->second;
+    };
+    h.c_chrom = need("chrom"); h.c_start = need("intron_start"); h.c_end = need("intron_end"); h.c_strand = need("strand");
+    h.c_uniq = need("uniq_mapped_count"); h.c_multi = need("multi_mapped_count"); h.c_unsure = need("unsure_mapped_count");
+    h.c_left = need("max_left_overhang"); h.c_right = need("max_right_overhang"); h.c_conf = need("confidence");
+    h.c_sites = need("splice_sites");
+    return h;
+}
+
+static int32_t chrom_id(CallsRows &out, const std::string &chrom) {
+    auto ci = out.chrom_index.find(chrom);
+    if (ci == out.chrom_index.end()) {
+        ci = out.chrom_index.emplace(chrom, (int32_t)out.chrom_names.size()).first;
+        out.chrom_names.push_back(chrom);
+    }
+    return ci->second;
+}
+
+static uint32_t site_id(CallsRows &out, const std::string &sites) {
+    auto si = out.site_index.find(sites);
+    if (si == out.site_index.end()) {
+        si = out.site_index.emplace(sites, (uint32_t)out.site_strings.size()).first;
+        out.site_strings.push_back(sites);
+    }
+    return si->second;
+}
+
+/* one row: Tsv::next_row's column check, junction_filter_check, read_junction -- in the reference's order, with its errors */
+static void add_line(const std::string &line, const Header &h, const std::string &path, int junction_filter, std::vector<std::string> &words,
+                     CallsRows &out) {
+    auto get = [&](int c, const char *name) -> const std::string & {
+        if (c < 0) throw std::runtime_error(std::string("column '") + name + "' not found: " + path);
+        return words[c];
+    };
+    split_tabs(line, words);
+    if ((int)words.size() != h.ncol) {
+        const std::string n = std::to_string(h.ncol);
+        throw std::runtime_error("expected " + n + " columns, got " + n + ":" + path); /* sic, tsv.hh:71 */
+    }
+    const std::string &sites = get(h.c_sites, "splice_sites");
+    /* junction_filter_check (splice_juncs.cc:52-61) */
+    if (!sites.empty() && junction_filter == IPX_FILTER_CANON && !canonical(sites)) return;
+    const uint32_t start = to_uint(get(h.c_start, "intron_start"));
+    const uint32_t end = to_uint(get(h.c_end, "intron_end"));
+    const std::string &chrom = get(h.c_chrom, "chrom");
+    const uint32_t a0 = start - to_uint(get(h.c_left, "max_left_overhang"));
+    const uint32_t a1 = end + to_uint(get(h.c_right, "max_right_overhang"));
+    const std::string &strand = get(h.c_strand, "strand");
+    const uint32_t uniq = to_uint(get(h.c_uniq, "uniq_mapped_count"));
+    const uint32_t multi = to_uint(get(h.c_multi, "multi_mapped_count"));
+    const uint32_t unsure = to_uint(get(h.c_unsure, "unsure_mapped_count"));
+    const float conf = to_float(get(h.c_conf, "confidence"));
+    out.chrom.push_back(chrom_id(out, chrom));
+    out.i0.push_back(start);
+    out.i1.push_back(end);
+    out.a0.push_back(a0);
+    out.a1.push_back(a1);
+    out.strand.push_back(strand.empty() ? '\0' : strand[0]);
+    out.sites.push_back(site_id(out, sites));
+    out.counts.push_back(uniq);
+    out.counts.push_back(multi);
+    out.counts.push_back(unsure);
+    out.conf.push_back(conf);
+}
+
+static std::string open_error(const std::string &path) {
+    return std::string("Failed to open ") + (path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0 ? "gzip file: " : "file: ") + path;
+}
+
 void load_calls_tsv(const std::string &path, int junction_filter, CallsRows &out) {
     gzFile gz = gzopen(path.c_str(), "rb");
-    if (!gz) throw std::runtime_error(std::string("Failed to open ") + (path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0 ? "gzip file: " : "file: ") + path);
+    if (!gz) throw std::runtime_error(open_error(path));
     gzbuffer(gz, 1 << 20);
     LineReader rd(gz);
     std::string line;
     std::vector<std::string> words;
     try {
         if (!rd.getline(line)) throw std::runtime_error("empty TSV file: " + path);
-        split_tabs(line, words);
-        const int ncol = (int)words.size();
-        std::unordered_map<std::string, int> col;
-        for (int i = 0; i < ncol; i++) col[words[i]] = i; /* later duplicates win, as with map::operator[] */
-        auto need = [&](const char *name) -> int {
-            auto it = col.find(name);
-            return it == col.end() ? -1 : it->second;
-        };
-        const int c_chrom = need("chrom"), c_start = need("intron_start"), c_end = need("intron_end"), c_strand = need("strand"),
-                  c_uniq = need("uniq_mapped_count"), c_multi = need("multi_mapped_count"), c_unsure = need("unsure_mapped_count"),
-                  c_left = need("max_left_overhang"), c_right = need("max_right_overhang"), c_conf = need("confidence"),
-                  c_sites = need("splice_sites");
-        auto get = [&](int c, const char *name) -> const std::string & {
-            if (c < 0) throw std::runtime_error(std::string("column '") + name + "' not found: " + path);
-            return words[c];
-        };
-        while (rd.getline(line)) {
-            split_tabs(line, words);
-            if ((int)words.size() != ncol) {
-                const std::string n = std::to_string(ncol);
-                throw std::runtime_error("expected " + n + " columns, got " + n + ":" + path); /* sic, tsv.hh:71 */
-            }
-            const std::string &sites = get(c_sites, "splice_sites");
-            /* junction_filter_check (splice_juncs.cc:52-61) */
-            if (!sites.empty() && junction_filter == IPX_FILTER_CANON && !canonical(sites)) continue;
-            const uint32_t start = to_uint(get(c_start, "intron_start"));
-            const uint32_t end = to_uint(get(c_end, "intron_end"));
-            const std::string &chrom = get(c_chrom, "chrom");
-            const uint32_t a0 = start - to_uint(get(c_left, "max_left_overhang"));
-            const uint32_t a1 = end + to_uint(get(c_right, "max_right_overhang"));
-            const std::string &strand = get(c_strand, "strand");
-            const uint32_t uniq = to_uint(get(c_uniq, "uniq_mapped_count"));
-            const uint32_t multi = to_uint(get(c_multi, "multi_mapped_count"));
-            const uint32_t unsure = to_uint(get(c_unsure, "unsure_mapped_count"));
-            const float conf = to_float(get(c_conf, "confidence"));
-            auto ci = out.chrom_index.find(chrom);
-            if (ci == out.chrom_index.end()) {
-                ci = out.chrom_index.emplace(chrom, (int32_t)out.chrom_names.size()).first;
-                out.chrom_names.push_back(chrom);
-            }
-            auto si = out.site_index.find(sites);
-            if (si == out.site_index.end()) {
-                si = out.site_index.emplace(sites, (uint32_t)out.site_strings.size()).first;
-                out.site_strings.push_back(sites);
-            }
-            out.chrom.push_back(ci->second);
-            out.i0.push_back(start);
-            out.i1.push_back(end);
-            out.a0.push_back(a0);
-            out.a1.push_back(a1);
-            out.strand.push_back(strand.empty() ? '\0' : strand[0]);
-            out.sites.push_back(si->second);
-            out.counts.push_back(uniq);
-            out.counts.push_back(multi);
-            out.counts.push_back(unsure);
-            out.conf.push_back(conf);
-        }
+        const Header h = read_header(line);
+        while (rd.getline(line)) add_line(line, h, path, junction_filter, words, out);
     } catch (...) {
         gzclose(gz);
         throw;
     }
     gzclose(gz);
+}
+
+/* The rows of one file through the device tokeniser.  false: not an input for the device (nothing was added to `out`). */
+static bool load_calls_tsv_tokenized(const std::string &path, int junction_filter, CallsRows &out, const TsvTokenizer &tok) {
+    gzFile gz = gzopen(path.c_str(), "rb");
+    if (!gz) throw std::runtime_error(open_error(path));
+    gzbuffer(gz, 1 << 20);
+    /* the whole file, inflated, in memory the tokeniser likes */
+    size_t cap = 32u << 20, n = 0;
+    char *bytes = (char *)tok.alloc(cap);
+    struct Guard {
+        const TsvTokenizer &tok;
+        gzFile gz;
+        char *&bytes;
+        ipx_tsv_rows *rows = nullptr;
+        ~Guard() {
+            if (gz) gzclose(gz);
+            if (rows) tok.rows_free(rows);
+            if (bytes) tok.release(bytes);
+        }
+    } guard{tok, gz, bytes};
+    if (!bytes) return false;
+    for (;;) {
+        if (n == cap) {
+            if (cap >= (1ull << 32)) return false; /* beyond what the device entry point takes */
+            char *grown = (char *)tok.alloc(cap * 2);
+            if (!grown) return false;
+            memcpy(grown, bytes, n);
+            tok.release(bytes);
+            bytes = grown;
+            cap *= 2;
+        }
+        const int got = gzread(gz, bytes + n, (unsigned)std::min<size_t>(cap - n, 1u << 30));
+        if (got <= 0) break;
+        n += (size_t)got;
+    }
+    if (n == 0) throw std::runtime_error("empty TSV file: " + path);
+    const char *nl = (const char *)memchr(bytes, '\n', n);
+    const size_t header_len = nl ? (size_t)(nl - bytes) : n, body = nl ? header_len + 1 : n;
+    const Header h = read_header(std::string(bytes, header_len));
+    if (!h.complete()) return false; /* the reference's "column not found" comes from the host parser, at the first row */
+    ipx_tsv_columns cols;
+    cols.n_columns = h.ncol;
+    cols.chrom = h.c_chrom; cols.intron_start = h.c_start; cols.intron_end = h.c_end; cols.strand = h.c_strand;
+    cols.uniq_mapped_count = h.c_uniq; cols.multi_mapped_count = h.c_multi; cols.unsure_mapped_count = h.c_unsure;
+    cols.max_left_overhang = h.c_left; cols.max_right_overhang = h.c_right; cols.confidence = h.c_conf; cols.splice_sites = h.c_sites;
+    const char *text = bytes + body;
+    const int rc = tok.tokenize(text, n - body, &cols, &guard.rows);
+    if (rc == IPX_ERR_ARG) return false;
+    if (rc != IPX_OK || !guard.rows) throw std::runtime_error("the device could not tokenise " + path);
+    const ipx_tsv_rows &r = *guard.rows;
+    const size_t n0 = out.chrom.size();
+    out.chrom.reserve(n0 + r.n_rows); out.i0.reserve(n0 + r.n_rows); out.i1.reserve(n0 + r.n_rows); out.a0.reserve(n0 + r.n_rows);
+    out.a1.reserve(n0 + r.n_rows); out.strand.reserve(n0 + r.n_rows); out.sites.reserve(n0 + r.n_rows);
+    out.counts.reserve(3 * (n0 + r.n_rows)); out.conf.reserve(n0 + r.n_rows);
+    std::vector<std::string> words;
+    std::string line;
+    /* consecutive rows mostly share their chromosome and their splice sites: remember the last of each */
+    const char *last_chrom = nullptr;
+    uint32_t last_chrom_len = 0;
+    int32_t last_chrom_id = -1;
+    uint64_t last_s8 = 0;
+    uint32_t last_s_len = 0xFFFFFFFFu, last_site_id = 0;
+    bool last_site_kept = true;
+    for (uint64_t i = 0; i < r.n_rows; i++) {
+        if (r.flags[i]) {
+            line.assign(text + r.line_off[i], r.line_len[i]);
+            add_line(line, h, path, junction_filter, words, out); /* (throws what the reference throws for this row) */
+            continue;
+        }
+        const uint64_t s8 = r.sites8[i];
+        const uint32_t s_len = r.sites_len[i];
+        if (s8 != last_s8 || s_len != last_s_len) {
+            char sb[9];
+            for (uint32_t k = 0; k < 8; k++) sb[k] = (char)((s8 >> (8 * k)) & 0xFF);
+            const std::string sites(sb, s_len);
+            last_site_kept = sites.empty() || junction_filter != IPX_FILTER_CANON || canonical(sites);
+            /* (a string the filter drops gets no number, as in the host parser) */
+            last_site_id = last_site_kept ? site_id(out, sites) : 0u;
+            last_s8 = s8;
+            last_s_len = s_len;
+        }
+        if (!last_site_kept) continue;
+        const char *cp = text + r.chrom_off[i];
+        const uint32_t cl = r.chrom_len[i];
+        if (last_chrom == nullptr || cl != last_chrom_len || memcmp(cp, last_chrom, cl) != 0) {
+            last_chrom_id = chrom_id(out, std::string(cp, cl));
+            last_chrom = cp;
+            last_chrom_len = cl;
+        }
+        out.chrom.push_back(last_chrom_id);
+        out.i0.push_back(r.intron_start[i]);
+        out.i1.push_back(r.intron_end[i]);
+        out.a0.push_back(r.anchor_start[i]);
+        out.a1.push_back(r.anchor_end[i]);
+        out.strand.push_back(r.strand[i]);
+        out.sites.push_back(last_site_id);
+        out.counts.push_back(r.counts[3 * i]);
+        out.counts.push_back(r.counts[3 * i + 1]);
+        out.counts.push_back(r.counts[3 * i + 2]);
+        out.conf.push_back(r.confidence[i]);
+    }
+    return true;
 }
 
 namespace {
@@ -226,13 +364,26 @@ void append_part(const CallsRows &part, CallsRows &out) {
 
 }  // namespace
 
+static void load_calls_tsvs_impl(const std::vector<std::string> &paths, int junction_filter, CallsRows &out, const TsvTokenizer *tok);
+
 void load_calls_tsvs(const std::vector<std::string> &paths, int junction_filter, CallsRows &out) {
+    load_calls_tsvs_impl(paths, junction_filter, out, nullptr);
+}
+void load_calls_tsvs(const std::vector<std::string> &paths, int junction_filter, CallsRows &out, const TsvTokenizer &tok) {
+    load_calls_tsvs_impl(paths, junction_filter, out, &tok);
+}
+
+static void load_calls_tsvs_impl(const std::vector<std::string> &paths, int junction_filter, CallsRows &out, const TsvTokenizer *tok) {
+    auto load_one = [&](const std::string &path, CallsRows &rows) {
+        if (tok && load_calls_tsv_tokenized(path, junction_filter, rows, *tok)) return;
+        load_calls_tsv(path, junction_filter, rows);
+    };
     unsigned threads = std::thread::hardware_concurrency();
     if (threads > 16u) threads = 16u;
     if (const char *e = getenv("IPX_PARSE_THREADS")) threads = (unsigned)atoi(e);
     if (threads > paths.size()) threads = (unsigned)paths.size();
     if (threads <= 1u) {
-        for (const std::string &f : paths) load_calls_tsv(f, junction_filter, out);
+        for (const std::string &f : paths) load_one(f, out);
         return;
     }
     struct Part {
@@ -248,7 +399,7 @@ void load_calls_tsvs(const std::vector<std::string> &paths, int junction_filter,
             const size_t i = next.fetch_add(1);
             if (i >= paths.size() || i > first_bad.load()) break; /* nothing after the first bad file is used */
             try {
-                load_calls_tsv(paths[i], junction_filter, parts[i]->rows);
+                load_one(paths[i], parts[i]->rows);
             } catch (const std::exception &e) {
                 parts[i]->error = e.what();
                 parts[i]->failed = true;

@@ -33,5 +33,18 @@ void load_calls_tsv(const std::string &path, int junction_filter, CallsRows &out
  * its error is thrown. */
 void load_calls_tsvs(const std::vector<std::string> &paths, int junction_filter, CallsRows &out);
 
+/* The same with the rows tokenised on the device (ipx_tsv_tokenize of include/ipx.h, handed in as functions so that this
+ * file needs no CUDA): a file is read (and inflated) whole, its header is looked at here, the rows come back as columns;
+ * what the device flags as not being in the plain form is parsed here, line by line, with the rules above -- so rows,
+ * dictionaries and errors are those of load_calls_tsvs.  tokenize() returning IPX_ERR_ARG means "not an input for the
+ * device" (the file is then parsed here); any other failure is an error. */
+struct TsvTokenizer {
+    void *(*alloc)(size_t);  /* memory for a file's bytes (pinned memory crosses the link faster) */
+    void (*release)(void *);
+    int (*tokenize)(const char *bytes, uint64_t n_bytes, const ipx_tsv_columns *columns, ipx_tsv_rows **out);
+    void (*rows_free)(ipx_tsv_rows *);
+};
+void load_calls_tsvs(const std::vector<std::string> &paths, int junction_filter, CallsRows &out, const TsvTokenizer &tok);
+
 }  // namespace ipx
 #endif

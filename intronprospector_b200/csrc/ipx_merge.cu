@@ -56,10 +56,11 @@ __global__ void k_merge_init_slots(Slot *slots, uint64_t cap) {
     }
 }
 
-/* strand and splice-site evidence of a row as one word each way: site << 8 | strand, with '.' counting as the largest
- * strand for the minimum and the smallest for the maximum, so that it never decides either */
-__device__ __forceinline__ uint32_t ev_for_min(uint32_t site, uint32_t strand) { return (site << 8) | (strand == (uint32_t)'.' ? 0xFFu : strand); }
-__device__ __forceinline__ uint32_t ev_for_max(uint32_t site, uint32_t strand) { return (site << 8) | (strand == (uint32_t)'.' ? 0u : strand); }
+/* strand and splice-site evidence of a row as one word each way: site << 9 | strand code.  The code of a strand character
+ * is the character + 1 (any byte, 0 included: an empty strand column); '.' counts as the largest code for the minimum and
+ * as 0 for the maximum, so that it never decides either */
+__device__ __forceinline__ uint32_t ev_for_min(uint32_t site, uint32_t strand) { return (site << 9) | (strand == (uint32_t)'.' ? 0x1FFu : strand + 1u); }
+__device__ __forceinline__ uint32_t ev_for_max(uint32_t site, uint32_t strand) { return (site << 9) | (strand == (uint32_t)'.' ? 0u : strand + 1u); }
 
 /* Thread per row: one probe (a load of the intron's slot, out of L2 once the table is warm), then fire-and-forget atomics
  * into its 64-byte record.  Rows of one warp that name the same intron (the last rows of one file and the first of the
@@ -155,11 +156,11 @@ __global__ void k_merge_gather(Tables t, const MStat *stat, const uint32_t *orde
     out.counts[3 * i + 1] = s.cnt[1];
     out.counts[3 * i + 2] = s.cnt[2];
     out.conf[i] = __uint_as_float(s.conf_bits);
-    const bool one_site = (s.ev_lo >> 8) == (s.ev_hi >> 8);
-    const uint32_t st_min = s.ev_lo & 0xFFu, st_max = s.ev_hi & 0xFFu; /* 0xFF / 0 when every row has '.' */
+    const bool one_site = (s.ev_lo >> 9) == (s.ev_hi >> 9);
+    const uint32_t st_min = s.ev_lo & 0x1FFu, st_max = s.ev_hi & 0x1FFu; /* 0x1FF / 0 when every row has '.' */
     const bool one_strand = st_max == 0u || st_min == st_max;
-    out.strand[i] = st_max == 0u ? '.' : (char)st_min;
-    out.site[i] = s.ev_lo >> 8;
+    out.strand[i] = st_max == 0u ? '.' : (char)(st_min - 1u);
+    out.site[i] = s.ev_lo >> 9;
     const uint8_t slow = (one_strand && one_site && !s.odd) ? 0 : 1;
     out.slow[i] = slow;
     slow_of_id[j] = slow;

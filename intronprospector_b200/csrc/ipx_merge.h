@@ -16,8 +16,8 @@ struct alignas(64) MStat {
     unsigned long long cnt[3];
     uint32_t a0, a1;
     uint32_t conf_bits; /* max confidence as float bits (non-negative floats order like uints) */
-    uint32_t ev_lo;     /* min over rows of (splice-site string id << 8 | strand, '.' as 0xFF) */
-    uint32_t ev_hi;     /* max over rows of (splice-site string id << 8 | strand, '.' as 0) */
+    uint32_t ev_lo;     /* min over rows of (splice-site string id << 9 | strand code, '.' as 0x1FF): see ev_for_min */
+    uint32_t ev_hi;     /* max over rows of (splice-site string id << 9 | strand code, '.' as 0) */
     uint32_t odd;       /* a row with negative / -0.0 / NaN confidence: fold on the host */
     uint32_t pad[4];
 };

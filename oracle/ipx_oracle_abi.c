@@ -100,6 +100,13 @@ int ipx_merge_rows_fold_part(ipx_handle *h, const ipx_merge_rows *rows, const ui
     return rc;
 }
 void ipx_free(void *p) { free(p); }
+/* the device tokeniser: not an input this build takes -- the tools then read the rows with the host parser */
+int ipx_tsv_tokenize(int32_t device, const char *bytes, uint64_t n_bytes, const ipx_tsv_columns *columns, ipx_tsv_rows **out) {
+    (void)device; (void)bytes; (void)n_bytes; (void)columns;
+    if (out) *out = NULL;
+    return IPX_ERR_ARG;
+}
+void ipx_tsv_rows_free(ipx_tsv_rows *rows) { (void)rows; }
 int ipx_table_set_ijunc(ipx_table *t, const uint32_t *ijunc) {
     if (!t || (t->n_junctions && !ijunc)) return IPX_ERR_ARG;
     memcpy((uint32_t *)t->ijunc, ijunc, t->n_junctions * sizeof(uint32_t)); /* (the oracle's tables own their columns) */
