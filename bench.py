@@ -418,9 +418,14 @@ def merge_workload(tmpdir, n_samples=64, n_universe=400_000):
     fold_ms = tm["merge_ms"] / steps
     alg = 42.0 * n_rows + 48.0 * nj
     t_cli, got, got_err = run_tool(GPU_MERGE, os.path.join(tmpdir, "merge_gpu"), paths)
+    # the same with the rows parsed by the host's thread pool instead of the device tokeniser
+    t_cli_host, got_h, got_err_h = run_tool(GPU_MERGE, os.path.join(tmpdir, "merge_gpu_h"), paths, env=dict(os.environ, IPX_TSV_HOST="1"))
+    if got_h != got or got_err_h != got_err:
+        raise RuntimeError("the device tokeniser and the host parser disagree")
     line = {"workload": "intronProspectorMerge of %d per-sample tables (BASELINE configs[4]), one GPU" % n_samples, "tables": n_samples,
             "rows": n_rows, "junctions": int(nj), "generate_s": gen_s, "tsv_parse_s": parse_s, "call_ms_host_rows_in_table_out": call_ms,
             "value": n_rows / (call_ms / 1e3), "unit": "rows/s", "device_fold_ms": fold_ms, "tool_wall_s": t_cli,
+            "tool_wall_host_tsv_parser_s": t_cli_host, "devices_visible_to_the_tool": _native.load_library().ipx_device_count(),
             "roofline": {"bound": "hbm", "kernel": "k_merge_fold (K4)", "kernel_ms": fold_ms, "algorithmic_bytes_per_launch": alg,
                          "achieved": alg / (fold_ms / 1e3) / 1e9 if fold_ms > 0 else 0.0, "unit": "GB/s"}}
     return line, ref, got, got_err

@@ -995,6 +995,10 @@ static int sam_parse_line(ipx_hts_impl *im, sam_hdr_t *h, const std::string &lin
     };
     c->tid = lookup(fld[2], fln[2]);
     c->pos = strtoll(fld[3], nullptr, 10) - 1;
+    /* htslib's sam_parse1: a mapped query cannot have a zero coordinate -- it is treated as unmapped; a record without a
+     * (known) reference is flagged unmapped */
+    if (c->pos < 0 && c->tid >= 0) c->tid = -1;
+    if (c->tid < 0) c->flag |= BAM_FUNMAP;
     c->qual = (uint8_t)strtoul(fld[4], nullptr, 10);
     /* cigar */
     c->n_cigar = 0;
@@ -1017,6 +1021,7 @@ static int sam_parse_line(ipx_hts_impl *im, sam_hdr_t *h, const std::string &lin
     if (fln[6] == 1 && fld[6][0] == '=') c->mtid = c->tid;
     else c->mtid = lookup(fld[6], fln[6]);
     c->mpos = strtoll(fld[7], nullptr, 10) - 1;
+    if (c->mpos < 0 && c->mtid >= 0) c->mtid = -1; /* (the same for the mate) */
     c->isize = strtoll(fld[8], nullptr, 10);
     /* seq / qual */
     if (fln[9] == 1 && fld[9][0] == '*') {

@@ -620,7 +620,8 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
     if (b.n >> 36) return fail(h, IPX_ERR_ARG, "batch too large");
     /* event buffer for the worst case: every emitted candidate consumes one N op and a following aligned op */
     const uint64_t ev_bound = n_cigar / 2 + 1;
-    const uint64_t n_tiles = tiles_of(b.n);
+    uint64_t n_tiles = tiles_of(b.n); /* (launch_extract says how many tiles it cut the batch into) */
+    const uint64_t tiles_bound = max_tiles_of(b.n);
     rc = settle_batch(h); /* the previous batch's events are about to be overwritten */
     if (rc) return rc;
     /* long reads scatter their offsets over thousands of values: extra dense rows would be given out to stragglers and
@@ -632,14 +633,15 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
         /* K1 and the first-seen pass only; the events stay on the device until ipx_count_deferred */
         ipx_handle::Deferred d{nullptr, nullptr, n_tiles};
         CU(h, cudaMallocAsync(&d.events, ev_bound * sizeof(Event), h->stream));
-        CU(h, cudaMallocAsync(&d.tile_info, (n_tiles + 1) * sizeof(TileInfo), h->stream));
+        CU(h, cudaMallocAsync(&d.tile_info, (tiles_bound + 1) * sizeof(TileInfo), h->stream));
         h->deferred.push_back(d);
         {
             Span s(h, &h->tm_extract, 0);
             int launched = 0;
             CU(h, launch_extract(b, n_cigar, h->xp, h->tab, (Event *)d.events, (TileInfo *)d.tile_info, h->d_counters + 96,
-                                 h->sm_count, h->stream, &launched));
+                                 h->sm_count, h->stream, &launched, &n_tiles));
             h->tm_extract.launches += (uint64_t)launched;
+            h->deferred.back().n_tiles = n_tiles;
         }
         {
             Span s(h, &h->tm_aggregate, 1);
@@ -652,12 +654,12 @@ int run_batch(ipx_handle *h, const BatchView &b, uint64_t n_cigar) {
         return IPX_OK;
     }
     CU(h, h->ev_buf.reserve(ev_bound * sizeof(Event), h->stream));
-    CU(h, h->tile_cnt.reserve((n_tiles + 1) * sizeof(TileInfo), h->stream));
+    CU(h, h->tile_cnt.reserve((tiles_bound + 1) * sizeof(TileInfo), h->stream));
     {
         Span s(h, &h->tm_extract, 0);
         int launched = 0;
         CU(h, launch_extract(b, n_cigar, h->xp, h->tab, (Event *)h->ev_buf.p, (TileInfo *)h->tile_cnt.p, h->d_counters + 96,
-                             h->sm_count, h->stream, &launched));
+                             h->sm_count, h->stream, &launched, &n_tiles));
         h->tm_extract.launches += (uint64_t)launched;
     }
     fold_events(h, (Event *)h->ev_buf.p, (TileInfo *)h->tile_cnt.p, n_tiles);

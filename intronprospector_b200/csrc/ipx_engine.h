@@ -90,6 +90,10 @@ struct __align__(16) TileInfo {
 /* first event index of a tile's region in the event buffer */
 __host__ __device__ inline uint64_t tile_event_base(uint32_t first_cigar_word) { return ((uint64_t)first_cigar_word + 1ull) >> 1; }
 inline uint64_t tiles_of(uint64_t n_records) { return (n_records + EX_TILE - 1) / EX_TILE; }
+/* The long-read kernels cut the batch into tiles of LONG_TILE records instead: a tile is also K2's unit of work, and a
+ * million long reads in tiles of 2048 are 488 tiles for 4736 warps (K2 took 2.1 ms instead of 0.7). */
+static const int LONG_TILE = 256;
+inline uint64_t max_tiles_of(uint64_t n_records) { return (n_records + LONG_TILE - 1) / LONG_TILE; }
 
 /* kernels' launchers; all asynchronous on `st` */
 void launch_init_tables(const Tables &t, cudaStream_t st);  /* whole tables, once after allocation */
@@ -99,9 +103,11 @@ void launch_clear_tables(const Tables &t, cudaStream_t st);
 void launch_settle_counters(const Tables &t, cudaStream_t st); /* counters back to what exists, before growth */
 /* every junction row into fresh hash slots (t.slots: allocated, any content); old_slots: where the rows' bases are */
 void launch_rehash(const Tables &t, const Slot *old_slots, cudaStream_t st);
-/* returns a CUDA error (attribute set-up of the pipelined kernel can fail), launches counted in *launches */
+/* returns a CUDA error (attribute set-up of the pipelined kernel can fail), launches counted in *launches; *n_tiles = the
+ * tiles the batch was cut into (tile_info has room for max_tiles_of(b.n) + 1) */
 cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractParams &p, const Tables &t, Event *out,
-                           TileInfo *tile_info, unsigned long long *next_record, int sm_count, cudaStream_t st, int *launches);
+                           TileInfo *tile_info, unsigned long long *next_record, int sm_count, cudaStream_t st, int *launches,
+                           uint64_t *n_tiles);
 /* K2 consumes the events: afterwards tile_info[].count is what it could not fold (0 unless a table was full) */
 void launch_fold(int mode, const Tables &t, Event *ev, TileInfo *tile_info, uint64_t n_tiles, int sm_count, cudaStream_t st);
 void launch_resolve_T(const Tables &t, const GenomeView &g, cudaStream_t st);

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) k_long_keys(const uint32_t *cigar_off, ui
     const uint32_t c0 = __ldg(&cigar_off[i]);
     n_ops[i] = __ldg(&cigar_off[i + 1]) - c0;
     index[i] = (uint32_t)i;
-    if (i % EX_TILE == 0) tile_info[i / EX_TILE] = TileInfo{0u, c0, 0u, 0u};
+    if (i % LONG_TILE == 0) tile_info[i / LONG_TILE] = TileInfo{0u, c0, 0u, 0u};
 }
 
 /* K1 sink of the long-read kernel: the walk keeps only the record index; what an event needs of the record (strand,
@@ -220,8 +220,8 @@ struct LazySink {
     uint64_t r;
     uint32_t n_events;
     __device__ __forceinline__ EventSink open() const {
-        const uint64_t tile = r / EX_TILE;
-        Event *region = out + tile_event_base(__ldg(&b.cigar_off[tile * EX_TILE]));
+        const uint64_t tile = r / LONG_TILE;
+        Event *region = out + tile_event_base(__ldg(&b.cigar_off[tile * LONG_TILE]));
         /* the tile's event count in tile_info doubles as the fill pointer of its region */
         return make_sink(t, p, region, &tile_info[tile].count, __ldg(&b.tid[r]), __ldg(&b.pos[r]), b.seq_base + r, __ldg(&b.flag[r]),
                          __ldg(&b.nh[r]), __ldg(&b.xs[r]));
@@ -805,8 +805,10 @@ __global__ void __launch_bounds__((WORKERS + 1) * 32, BLOCKS) k_extract_tma(Batc
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
 cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractParams &p, const Tables &t, Event *out,
-                           TileInfo *tile_info, unsigned long long *next_record, int sm_count, cudaStream_t st, int *launches) {
+                           TileInfo *tile_info, unsigned long long *next_record, int sm_count, cudaStream_t st, int *launches,
+                           uint64_t *n_tiles_out) {
     if (launches) *launches = 0;
+    if (n_tiles_out) *n_tiles_out = tiles_of(b.n);
     if (b.n == 0) return cudaSuccess;
     const uint64_t n_tiles = tiles_of(b.n), n_full = b.n / EX_TILE;
     /* the pipelined kernel takes whole tiles of batches whose columns can be bulk-copied and whose reads are short
@@ -840,6 +842,7 @@ cudaError_t launch_extract(const BatchView &b, uint64_t n_cigar, const ExtractPa
         const char *seg_env = getenv("IPX_K1_SEG_MIN");
         const uint32_t seg_min_ops = seg_env ? (uint32_t)atoi(seg_env) : 16384u;
         const bool segmented = seg_min_ops != 0u;
+        if (n_tiles_out) *n_tiles_out = max_tiles_of(b.n); /* tiles of LONG_TILE records */
         const int n = (int)b.n;
         size_t sort_bytes = 0, scan_bytes = 0;
         cudaError_t e = cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
