@@ -3,7 +3,10 @@
  * B200 behind ipx_merge_rows_fold (include/ipx.h).  Host side only: options, TSV loading, text output.
  */
 #include <getopt.h>
+#include <stdio.h>
+#include <time.h>
 #include <algorithm>
+#include <atomic>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -34,6 +37,23 @@ static void usage() {
     cerr << usage_msg;
     exit(0);
 }
+
+/* IPX_TRACE=1: wall-clock marks of the tool's phases on stderr */
+struct PhaseTrace {
+    bool on = getenv("IPX_TRACE") != NULL;
+    double t0 = now();
+    static double now() {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    void mark(const char *what) {
+        if (!on) return;
+        const double t = now();
+        fprintf(stderr, "[merge] %-32s %9.1f ms\n", what, t - t0);
+        t0 = t;
+    }
+};
 
 struct Options {
     vector<string> input_calls_tsvs;
@@ -137,6 +157,7 @@ static vector<int> balanced_ranges(const ipx::CallsRows &rows, int n_parts) {
 }
 
 static void fold_part(Part *p, const vector<const char *> *names) {
+    PhaseTrace tr;
     ipx_params prm;
     memset(&prm, 0, sizeof(prm));
     prm.device = p->device;
@@ -146,7 +167,9 @@ static void fold_part(Part *p, const vector<const char *> *names) {
         p->error = "no usable CUDA device: the merge fold needs an NVIDIA B200 (sm_100a) GPU";
         return;
     }
+    tr.mark("  handle");
     p->rc = ipx_set_targets(h, (int32_t)names->size(), names->data());
+    tr.mark("  targets");
     if (p->rc == IPX_OK) {
         ipx_text log;
         uint64_t *log_rows = nullptr, n_log_rows = 0;
@@ -157,25 +180,53 @@ static void fold_part(Part *p, const vector<const char *> *names) {
         ipx_free(log_rows);
     }
     if (p->rc != IPX_OK) p->error = ipx_last_error(h);
+    tr.mark("  fold call");
     ipx_destroy(h);
+    tr.mark("  handle released");
 }
 
-/* the rows are tokenised on the device (ipx_tsv_tokenize); IPX_TSV_HOST=1 keeps the host parser (tests compare the two) */
+/* The rows are tokenised on the device (ipx_tsv_tokenize); IPX_TSV_HOST=1 keeps the host parser (tests compare the two).
+ * Bringing the device up takes a second or so of a tool's run: a thread does it from the start, and the files that come
+ * by before it is done are parsed by the host's threads (the rows are the same either way). */
 static int tokenizer_device = 0;
+static std::atomic<bool> device_up{false};
+static std::atomic<int> files_on_device{0};
 static int tokenize_on_device(const char *bytes, uint64_t n, const ipx_tsv_columns *cols, ipx_tsv_rows **out) {
+    files_on_device++;
     return ipx_tsv_tokenize(tokenizer_device, bytes, n, cols, out);
+}
+static bool device_is_up() { return device_up.load(); }
+static void bring_device_up() {
+    PhaseTrace tr;
+    ipx_tsv_columns c;
+    memset(&c, 0, sizeof(c));
+    c.n_columns = 1;
+    ipx_tsv_rows *r = nullptr;
+    if (ipx_tsv_tokenize(tokenizer_device, "", 0, &c, &r) == IPX_OK) device_up.store(true);
+    ipx_tsv_rows_free(r);
+    tr.mark("(device up)");
 }
 
 /* intron_prospector_merge (intronProspectorMerge.cc:207-238) */
 static void merge(const Options &opts) {
+    PhaseTrace tr;
     ipx::CallsRows rows;
     string parse_error;
+    if (const char *d = getenv("IPX_DEVICE")) tokenizer_device = atoi(d);
+    thread warm_up(bring_device_up);
+    struct Join {
+        thread &t;
+        ~Join() {
+            if (t.joinable()) t.join();
+        }
+    } join_warm_up{warm_up};
     try {
         if (getenv("IPX_TSV_HOST")) {
             ipx::load_calls_tsvs(opts.input_calls_tsvs, opts.junction_filter, rows);
         } else {
-            if (const char *d = getenv("IPX_DEVICE")) tokenizer_device = atoi(d);
-            const ipx::TsvTokenizer tok{malloc, free, tokenize_on_device, ipx_tsv_rows_free};
+            /* IPX_TSV_DEVICE=1: wait for the device first, so that every file goes through it (tests) */
+            if (getenv("IPX_TSV_DEVICE")) warm_up.join();
+            const ipx::TsvTokenizer tok{malloc, free, tokenize_on_device, ipx_tsv_rows_free, device_is_up};
             ipx::load_calls_tsvs(opts.input_calls_tsvs, opts.junction_filter, rows, tok);
         }
     } catch (const std::exception &e) {
@@ -183,6 +234,8 @@ static void merge(const Options &opts) {
     }
     if (rows.chrom_names.empty()) rows.chrom_names.push_back("");
     rows.bind();
+    if (tr.on) fprintf(stderr, "[merge] files tokenised on the device: %d of %zu\n", files_on_device.load(), opts.input_calls_tsvs.size());
+    tr.mark("rows read");
     /* Key ranges over the devices of this host (BASELINE config 5): every device folds the rows of a contiguous range of
      * chromosomes.  A key lives in one range, so the partial tables are simply concatenated in key order.
      * IPX_MERGE_DEVICES=n caps the number of devices (default: all that are visible, one when the input is small);
@@ -234,6 +287,7 @@ static void merge(const Options &opts) {
             });
         for (auto &t : threads) t.join();
     }
+    tr.mark("fold");
     struct Tables {
         vector<unique_ptr<Part>> &parts;
         ~Tables() {
@@ -286,27 +340,62 @@ static void merge(const Options &opts) {
             base += (uint32_t)p->table->n_junctions;
         }
     }
-    auto emit = [&](const string &fn, int fmt, bool header) {
-        if (fn == "") return;
-        OutFile out(fn);
+    /* The output files are independent of each other: they are opened in the reference's order (so that a file that
+     * cannot be opened stops the run where it stops the reference's: the files before it written, none after it), then
+     * formatted and written by a thread each. */
+    struct Job {
+        const string *fn;
+        int fmt;
+        bool header;
+        unique_ptr<OutFile> out;
+        string error;
+    } jobs[4] = {{&opts.junction_bed, IPX_FMT_JUNCTION_BED, false, nullptr, ""}, {&opts.intron_bed, IPX_FMT_INTRON_BED9, false, nullptr, ""},
+                 {&opts.intron_bed6, IPX_FMT_INTRON_BED6, false, nullptr, ""}, {&opts.intron_call_tsv, IPX_FMT_INTRON_TSV, true, nullptr, ""}};
+    string open_error;
+    int n_jobs = 0;
+    for (Job &j : jobs) {
+        if (*j.fn != "") {
+            try {
+                j.out.reset(new OutFile(*j.fn));
+            } catch (const std::exception &e) {
+                open_error = e.what();
+                break;
+            }
+        }
+        n_jobs++;
+    }
+    auto emit = [&](Job &j) {
+        if (!j.out) return;
         ipx_text txt;
-        if (header) {
+        if (j.header) {
             ipx_format_tsv_header(&txt);
-            out.write(txt);
+            j.out->write(txt);
             ipx_text_free(&txt);
         }
         for (Part *p : in_order) {
             if (!p->table) continue;
-            if (ipx_format(p->table, rows.chrom_ptrs.data(), fmt, 0.0f, 0, p->table->n_junctions, &txt) != IPX_OK)
+            if (ipx_format(p->table, rows.chrom_ptrs.data(), j.fmt, 0.0f, 0, p->table->n_junctions, &txt) != IPX_OK)
                 throw runtime_error("formatting failed");
-            out.write(txt);
+            j.out->write(txt);
             ipx_text_free(&txt);
         }
+        j.out.reset();
     };
-    emit(opts.junction_bed, IPX_FMT_JUNCTION_BED, false);
-    emit(opts.intron_bed, IPX_FMT_INTRON_BED9, false);
-    emit(opts.intron_bed6, IPX_FMT_INTRON_BED6, false);
-    emit(opts.intron_call_tsv, IPX_FMT_INTRON_TSV, true);
+    vector<thread> writers;
+    for (int k = 0; k < n_jobs; k++)
+        writers.emplace_back([&emit, &jobs, k]() {
+            try {
+                emit(jobs[k]);
+            } catch (const std::exception &e) {
+                jobs[k].error = e.what();
+                if (jobs[k].error.empty()) jobs[k].error = "output failed";
+            }
+        });
+    for (auto &w : writers) w.join();
+    for (int k = 0; k < n_jobs; k++)
+        if (!jobs[k].error.empty()) throw runtime_error(jobs[k].error);
+    if (!open_error.empty()) throw runtime_error(open_error);
+    tr.mark("outputs written");
 }
 
 int main(int argc, char *argv[]) {

@@ -375,7 +375,7 @@ void load_calls_tsvs(const std::vector<std::string> &paths, int junction_filter,
 
 static void load_calls_tsvs_impl(const std::vector<std::string> &paths, int junction_filter, CallsRows &out, const TsvTokenizer *tok) {
     auto load_one = [&](const std::string &path, CallsRows &rows) {
-        if (tok && load_calls_tsv_tokenized(path, junction_filter, rows, *tok)) return;
+        if (tok && (!tok->ready || tok->ready()) && load_calls_tsv_tokenized(path, junction_filter, rows, *tok)) return;
         load_calls_tsv(path, junction_filter, rows);
     };
     unsigned threads = std::thread::hardware_concurrency();

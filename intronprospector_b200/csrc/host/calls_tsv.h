@@ -43,6 +43,7 @@ struct TsvTokenizer {
     void (*release)(void *);
     int (*tokenize)(const char *bytes, uint64_t n_bytes, const ipx_tsv_columns *columns, ipx_tsv_rows **out);
     void (*rows_free)(ipx_tsv_rows *);
+    bool (*ready)(); /* optional: false while the device is not up yet -- files that come by meanwhile are parsed here */
 };
 void load_calls_tsvs(const std::vector<std::string> &paths, int junction_filter, CallsRows &out, const TsvTokenizer &tok);
 

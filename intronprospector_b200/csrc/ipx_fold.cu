@@ -238,7 +238,7 @@ __device__ __forceinline__ void fold_write_back(const Tables &t, FoldCache &c, i
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables t, Event *ev, TileInfo *tile_info, uint64_t n_tiles, uint32_t prefetch) {
+__global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables t, Event *ev, TileInfo *tile_info, uint64_t n_tiles) {
     __shared__ FoldCache s_cache[FOLD_WARPS];
     __shared__ IdPool s_pool;
     if (threadIdx.x == 0) id_pool_load(t, &s_pool);
@@ -402,9 +402,6 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
                 }
                 log_append(t, log, counted && place == DENSE_NONE, olog_entry(jid, off, 1u));
             }
-            /* the home slots of the next chunk's keys on their way into L1 while this chunk's atomics drain */
-            if ((prefetch & 1u) && k0 + 32u + lane < cnt)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(&t.slots[junction_hash(nxt.key, nxt.tid) & t.cap_mask]));
             /* events that could not be folded go back to the front of the region (behind what was read already) */
             const unsigned km = __ballot_sync(0xFFFFFFFFu, keep);
             if (km) {
@@ -428,16 +425,14 @@ __global__ void __launch_bounds__(FOLD_WARPS * 32, IPX_K2_BLOCKS) k_fold(Tables 
 
 void launch_fold(int mode, const Tables &t, Event *ev, TileInfo *tile_info, uint64_t n_tiles, int sm_count, cudaStream_t st) {
     if (n_tiles == 0) return;
-    uint32_t prefetch = 0u;
-    if (const char *e = getenv("IPX_K2_PREFETCH")) prefetch = (uint32_t)atoi(e);
     cudaMemsetAsync(t.next_tile, 0, sizeof(unsigned long long), st);
     const uint64_t want = (n_tiles + FOLD_WARPS - 1) / FOLD_WARPS;
     const uint64_t max_blocks = (uint64_t)sm_count * IPX_K2_BLOCKS; /* what is resident at once */
     const int blocks = (int)(want < max_blocks ? want : max_blocks);
     switch (mode) {
-        case MODE_SINGLE: k_fold<MODE_SINGLE><<<blocks, FOLD_WARPS * 32, 0, st>>>(t, ev, tile_info, n_tiles, prefetch); break;
-        case MODE_PASS1: k_fold<MODE_PASS1><<<blocks, FOLD_WARPS * 32, 0, st>>>(t, ev, tile_info, n_tiles, prefetch); break;
-        default: k_fold<MODE_PASS2><<<blocks, FOLD_WARPS * 32, 0, st>>>(t, ev, tile_info, n_tiles, prefetch); break;
+        case MODE_SINGLE: k_fold<MODE_SINGLE><<<blocks, FOLD_WARPS * 32, 0, st>>>(t, ev, tile_info, n_tiles); break;
+        case MODE_PASS1: k_fold<MODE_PASS1><<<blocks, FOLD_WARPS * 32, 0, st>>>(t, ev, tile_info, n_tiles); break;
+        default: k_fold<MODE_PASS2><<<blocks, FOLD_WARPS * 32, 0, st>>>(t, ev, tile_info, n_tiles); break;
     }
 }
 

@@ -278,11 +278,56 @@ size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace
 
+namespace {
+/* what a thread needs to tokenise a file, kept from file to file: a tool runs dozens of files through a pool of threads,
+ * and creating streams and (un)mapping device memory per file cost more than the tokenising */
+struct TokCtx {
+    int device = -1;
+    cudaStream_t st = nullptr;
+    char *d_bytes = nullptr, *d_out = nullptr;
+    uint32_t *d_tiles = nullptr, *d_nl = nullptr;
+    unsigned long long *d_total = nullptr;
+    size_t bytes_cap = 0, out_cap = 0, tiles_cap = 0, nl_cap = 0;
+    void release() {
+        if (device < 0) return;
+        cudaSetDevice(device);
+        cudaFree(d_bytes); cudaFree(d_out); cudaFree(d_tiles); cudaFree(d_nl); cudaFree(d_total);
+        if (st) cudaStreamDestroy(st);
+        cudaGetLastError(); /* (at process exit the runtime may be gone already) */
+        *this = TokCtx();
+    }
+    ~TokCtx() { release(); }
+    template <class T>
+    static bool room(T **p, size_t *cap, size_t want) {
+        if (*cap >= want) return true;
+        cudaFree(*p);
+        *p = nullptr;
+        *cap = 0;
+        const size_t take = want + want / 4 + 4096;
+        if (cudaMalloc((void **)p, take) != cudaSuccess) return false;
+        *cap = take;
+        return true;
+    }
+    bool open(int dev) {
+        if (device == dev) return true;
+        release();
+        if (cudaSetDevice(dev) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMalloc((void **)&d_total, 16) != cudaSuccess) {
+            cudaGetLastError();
+            st = nullptr;
+            return false;
+        }
+        device = dev;
+        return true;
+    }
+};
+thread_local TokCtx t_ctx;
+}  // namespace
+
 extern "C" int ipx_tsv_tokenize(int32_t device, const char *bytes, uint64_t n_bytes, const ipx_tsv_columns *columns, ipx_tsv_rows **out) {
     if (!bytes || !columns || !out) return IPX_ERR_ARG;
     *out = nullptr;
     if (n_bytes >= (1ull << 32) || columns->n_columns < 1) return IPX_ERR_ARG; /* (positions are 32 bits: larger files are the host's) */
-    if (cudaSetDevice(device) != cudaSuccess) return IPX_ERR_CUDA;
     TsvCols cols;
     cols.n_columns = columns->n_columns;
     const int32_t want[N_FIELDS] = {columns->chrom, columns->intron_start, columns->intron_end, columns->strand, columns->uniq_mapped_count,
@@ -292,43 +337,32 @@ extern "C" int ipx_tsv_tokenize(int32_t device, const char *bytes, uint64_t n_by
         if (want[f] < 0 || want[f] >= columns->n_columns) return IPX_ERR_ARG;
         cols.col[f] = want[f];
     }
+    TokCtx &c = t_ctx;
+    if (!c.open(device)) return IPX_ERR_CUDA;
+    cudaSetDevice(device);
     Owned *own = (Owned *)calloc(1, sizeof(Owned));
     if (!own) return IPX_ERR_ARG;
     if (n_bytes == 0) {
         *out = &own->rows;
         return IPX_OK;
     }
-    cudaStream_t st = nullptr;
-    char *d_bytes = nullptr, *d_out = nullptr;
-    uint32_t *d_tiles = nullptr, *d_nl = nullptr;
-    unsigned long long *d_total = nullptr;
-    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    cudaStream_t st = c.st;
     auto fail = [&](int code) {
-        if (st) {
-            cudaStreamSynchronize(st);
-            cudaFreeAsync(d_bytes, st); cudaFreeAsync(d_out, st); cudaFreeAsync(d_tiles, st); cudaFreeAsync(d_nl, st); cudaFreeAsync(d_total, st);
-            cudaStreamSynchronize(st);
-            cudaStreamDestroy(st);
-        }
+        cudaStreamSynchronize(st);
         if (own->block) g_blocks.give(own->block, own->block_cap);
         free(own);
         cudaGetLastError();
         return code;
     };
-    if (e != cudaSuccess) { st = nullptr; return fail(IPX_ERR_CUDA); }
     const uint32_t n_tiles = (uint32_t)((n_bytes + TSV_TILE - 1) / TSV_TILE);
-    if (cudaMallocAsync((void **)&d_bytes, n_bytes + 16, st) != cudaSuccess || cudaMallocAsync((void **)&d_tiles, (size_t)n_tiles * 4, st) != cudaSuccess ||
-        cudaMallocAsync((void **)&d_total, 16, st) != cudaSuccess)
-        return fail(IPX_ERR_CUDA);
-    if (cudaMemcpyAsync(d_bytes, bytes, n_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(IPX_ERR_CUDA);
-    k_tsv_count<<<n_tiles, TSV_BLOCK, 0, st>>>(d_bytes, n_bytes, d_tiles);
-    k_tsv_block_scan<<<1, 1024, 0, st>>>(d_tiles, n_tiles, d_bytes, n_bytes, d_total);
+    if (!TokCtx::room(&c.d_bytes, &c.bytes_cap, n_bytes + 16) || !TokCtx::room(&c.d_tiles, &c.tiles_cap, (size_t)n_tiles * 4)) return fail(IPX_ERR_CUDA);
+    if (cudaMemcpyAsync(c.d_bytes, bytes, n_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(IPX_ERR_CUDA);
+    k_tsv_count<<<n_tiles, TSV_BLOCK, 0, st>>>(c.d_bytes, n_bytes, c.d_tiles);
+    k_tsv_block_scan<<<1, 1024, 0, st>>>(c.d_tiles, n_tiles, c.d_bytes, n_bytes, c.d_total);
     unsigned long long total[2] = {0, 0};
-    if (cudaMemcpyAsync(total, d_total, 16, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+    if (cudaMemcpyAsync(total, c.d_total, 16, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
         return fail(IPX_ERR_CUDA);
     const uint64_t n_nl = total[0], n = total[1];
-    if (cudaMallocAsync((void **)&d_nl, (size_t)(n_nl ? n_nl : 1) * 4, st) != cudaSuccess) return fail(IPX_ERR_CUDA);
-    k_tsv_newlines<<<n_tiles, TSV_BLOCK, 0, st>>>(d_bytes, n_bytes, d_tiles, d_nl);
     /* every column in one device block and one pinned block: one copy back */
     size_t at = 0;
     struct Piece { size_t off, width; } pc[14];
@@ -339,20 +373,19 @@ extern "C" int ipx_tsv_tokenize(int32_t device, const char *bytes, uint64_t n_by
         at += up256((size_t)(n ? n : 1) * widths[k]);
     }
     const size_t out_bytes = at;
-    if (cudaMallocAsync((void **)&d_out, out_bytes, st) != cudaSuccess) return fail(IPX_ERR_CUDA);
+    if (!TokCtx::room(&c.d_nl, &c.nl_cap, (size_t)(n_nl ? n_nl : 1) * 4) || !TokCtx::room(&c.d_out, &c.out_cap, out_bytes)) return fail(IPX_ERR_CUDA);
+    k_tsv_newlines<<<n_tiles, TSV_BLOCK, 0, st>>>(c.d_bytes, n_bytes, c.d_tiles, c.d_nl);
     own->block = g_blocks.take(out_bytes, &own->block_cap);
     if (!own->block) return fail(IPX_ERR_CUDA);
+    char *d_out = c.d_out;
     auto dev = [&](int k) { return d_out + pc[k].off; };
     TsvOut o{(uint32_t *)dev(0), (uint32_t *)dev(1), (uint32_t *)dev(2), (uint32_t *)dev(3), (uint32_t *)dev(4), (float *)dev(5), dev(6),
              (unsigned long long *)dev(7), (uint8_t *)dev(8), (uint32_t *)dev(9), (uint16_t *)dev(10), (uint32_t *)dev(11), (uint32_t *)dev(12),
              (uint8_t *)dev(13)};
-    if (n) k_tsv_parse<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_bytes, n_bytes, d_nl, d_total, cols, o);
+    if (n) k_tsv_parse<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.d_bytes, n_bytes, c.d_nl, c.d_total, cols, o);
     if (cudaGetLastError() != cudaSuccess) return fail(IPX_ERR_CUDA);
     if (cudaMemcpyAsync(own->block, d_out, out_bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
         return fail(IPX_ERR_CUDA);
-    cudaFreeAsync(d_bytes, st); cudaFreeAsync(d_out, st); cudaFreeAsync(d_tiles, st); cudaFreeAsync(d_nl, st); cudaFreeAsync(d_total, st);
-    cudaStreamSynchronize(st);
-    cudaStreamDestroy(st);
     char *hb = (char *)own->block;
     ipx_tsv_rows &r = own->rows;
     r.n_rows = n;

@@ -74,6 +74,7 @@ def test_tokenizer_rows_the_device_leaves_to_the_host(built, tmp_path, extra, mo
         swapped += "\t".join(f[k] for k in order) + "\tx\n"
     _write(tmp_path / "c.tsv", swapped)
     paths = [str(tmp_path / n) for n in ("a.tsv", "b.tsv.gz", "c.tsv")]
+    monkeypatch.setenv("IPX_TSV_DEVICE", "1")  # every file through the device (the tool starts on the host's parser while the device comes up)
     rc_r, err_r, ref = run_merge(helpers.REF_MERGE, str(tmp_path), "ref", paths, extra)
     rc_g, err_g, gpu = run_merge(helpers.GPU_MERGE, str(tmp_path), "gpu", paths, extra)
     monkeypatch.setenv("IPX_TSV_HOST", "1")
@@ -94,7 +95,7 @@ BAD = {
 
 
 @pytest.mark.parametrize("kind", sorted(BAD))
-def test_tokenizer_bad_rows_fail_like_the_reference(built, tmp_path, kind):
+def test_tokenizer_bad_rows_fail_like_the_reference(built, tmp_path, kind, monkeypatch):
     """A malformed row in the second of three files: the same exit code and the same stderr (the conflict lines of the
     rows before it, then the reference's error text), and no output beyond what the reference leaves."""
     good = TSV_HEADER + ROWS_PLAIN * 50
@@ -103,6 +104,7 @@ def test_tokenizer_bad_rows_fail_like_the_reference(built, tmp_path, kind):
     _write(tmp_path / "b.tsv", good + BAD[kind] + ROWS_PLAIN)
     _write(tmp_path / "c.tsv", good)
     paths = [str(tmp_path / n) for n in ("a.tsv", "b.tsv", "c.tsv")]
+    monkeypatch.setenv("IPX_TSV_DEVICE", "1")
     rc_r, err_r, ref = run_merge(helpers.REF_MERGE, str(tmp_path), "ref", paths)
     rc_g, err_g, gpu = run_merge(helpers.GPU_MERGE, str(tmp_path), "gpu", paths)
     assert (rc_g, err_g) == (rc_r, err_r)
@@ -114,6 +116,7 @@ def test_tokenizer_bad_rows_fail_like_the_reference(built, tmp_path, kind):
 def test_tokenizer_large_tables_match_the_host_parser(built, tmp_path, monkeypatch):
     """Many rows per file (several tiles of the newline scan, every thread block shape) against the host parser."""
     paths, _ = merge_synth.write_tables(str(tmp_path), n_samples=6, n_universe=120_000, conflicts=20)
+    monkeypatch.setenv("IPX_TSV_DEVICE", "1")
     rc_g, err_g, gpu = run_merge(helpers.GPU_MERGE, str(tmp_path), "gpu", paths)
     monkeypatch.setenv("IPX_TSV_HOST", "1")
     rc_h, err_h, host = run_merge(helpers.GPU_MERGE, str(tmp_path), "host", paths)
