@@ -391,20 +391,25 @@ struct PinnedBatch {
     vector<uint32_t> ops32; /* the operation counts once more, 32 bits wide: only used when one exceeds 65535 */
     bool compact_ok = true;
     uint64_t seq_base = 0;
+    bool pinned = true; /* false: ordinary memory (the batch that fills while the device is still coming up) */
+    void *take(size_t bytes) const { return pinned ? ipx_host_alloc(bytes) : malloc(bytes ? bytes : 1); }
+    void give(void *p) const {
+        if (pinned) ipx_host_free(p); else free(p);
+    }
     void allocate(size_t records, size_t cigar_words) {
         cap_rec = records;
         cap_cig = cigar_words;
-        pos = (int32_t *)ipx_host_alloc(records * 4);
-        flag = (uint16_t *)ipx_host_alloc(records * 2);
-        n_ops = (uint16_t *)ipx_host_alloc(records * 2);
-        nh = (uint8_t *)ipx_host_alloc(records);
-        xs = (uint8_t *)ipx_host_alloc(records);
-        cigar = (uint32_t *)ipx_host_alloc(cigar_words * 4);
+        pos = (int32_t *)take(records * 4);
+        flag = (uint16_t *)take(records * 2);
+        n_ops = (uint16_t *)take(records * 2);
+        nh = (uint8_t *)take(records);
+        xs = (uint8_t *)take(records);
+        cigar = (uint32_t *)take(cigar_words * 4);
         if (!pos || !flag || !n_ops || !nh || !xs || !cigar) throw runtime_error("cannot allocate pinned host memory for the record batches");
     }
     void release() {
-        ipx_host_free(pos); ipx_host_free(flag); ipx_host_free(n_ops); ipx_host_free(nh); ipx_host_free(xs); ipx_host_free(cigar);
-        pos = nullptr;
+        give(pos); give(flag); give(n_ops); give(nh); give(xs); give(cigar);
+        pos = nullptr; flag = n_ops = nullptr; nh = xs = nullptr; cigar = nullptr;
     }
     void clear(uint64_t next_seq_base) {
         n = n_cig = 0;
@@ -437,8 +442,14 @@ class Driver {
     vector<string> targets_;            /* targets_, appended per file (save_targets, junctions_extractor.cc:564-568) */
     vector<int32_t> canon_tid_;         /* first index carrying the same name: the reference keys junctions by name */
     map<string, int32_t> name_first_;
-    PinnedBatch batches_[2];
-    int cur_ = 0;
+    /* Bringing the device up (CUDA start-up, the handle, pinning the two batches) takes most of a second: a thread does
+     * it while the first records are already being read and packed into batches_[2], an ordinary-memory batch.  Whatever
+     * needs the handle waits for that thread (dev()). */
+    PinnedBatch batches_[3];
+    int cur_ = 2;
+    thread init_;
+    bool ready_ = false, targets_dirty_ = false;
+    string init_error_;
     uint64_t next_seq_ = 0;
     uint64_t last_seq_ = 0; /* stream index and engine target of the record process() saw last */
     int32_t last_tid_ = -1;
@@ -456,6 +467,21 @@ class Driver {
         next_seq_ += n_records;
     }
 
+    void dev() {
+        if (ready_) return;
+        if (init_.joinable()) init_.join();
+        ready_ = true;
+        if (!init_error_.empty()) throw runtime_error(init_error_);
+        g_trace.mark("(waited for the device)");
+    }
+    void sync_targets() {
+        if (!targets_dirty_) return;
+        targets_dirty_ = false;
+        vector<const char *> ptrs(targets_.size());
+        for (size_t i = 0; i < targets_.size(); i++) ptrs[i] = targets_[i].c_str();
+        check_ipx(h_, ipx_set_targets(h_, (int32_t)ptrs.size(), ptrs.data()));
+    }
+
     public:
     explicit Driver(const Options &o) : opts_(o) {
         ipx_params p;
@@ -470,19 +496,31 @@ class Driver {
         p.skip_missing_targets = o.skip_missing_targets ? 1 : 0;
         p.device = 0;
         if (const char *d = getenv("IPX_DEVICE")) p.device = atoi(d);
-        int rc = ipx_create(&p, &h_);
-        if (rc != IPX_OK) throw runtime_error("no usable CUDA device: junction extraction needs an NVIDIA B200 (sm_100a) GPU");
-        for (auto &b : batches_) {
-            b.allocate(BATCH_RECORDS, BATCH_CIGAR);
-            b.clear(0);
-        }
+        batches_[2].pinned = false;
+        batches_[2].allocate(BATCH_RECORDS, BATCH_CIGAR);
+        batches_[2].clear(0);
+        init_ = thread([this, p]() {
+            try {
+                if (ipx_create(&p, &h_) != IPX_OK)
+                    throw runtime_error("no usable CUDA device: junction extraction needs an NVIDIA B200 (sm_100a) GPU");
+                for (int k = 0; k < 2; k++) {
+                    batches_[k].allocate(BATCH_RECORDS, BATCH_CIGAR);
+                    batches_[k].clear(0);
+                }
+            } catch (const std::exception &e) {
+                init_error_ = e.what();
+            }
+        });
     }
     ~Driver() {
+        if (init_.joinable()) init_.join();
         ipx_destroy(h_);
-        for (auto &b : batches_) b.release();
+        for (auto &b : batches_)
+            if (b.pos) b.release();
     }
 
     void set_genome(const ipx::LoadedGenome &g) {
+        dev();
         check_ipx(h_, ipx_set_genome(h_, (int32_t)g.names.size(), g.name_ptrs.data(), g.lengths.data(), g.seq_ptrs.data()));
     }
 
@@ -501,9 +539,7 @@ class Driver {
             }
             targets_.push_back(nm);
         }
-        vector<const char *> ptrs(targets_.size());
-        for (size_t i = 0; i < targets_.size(); i++) ptrs[i] = targets_[i].c_str();
-        check_ipx(h_, ipx_set_targets(h_, (int32_t)ptrs.size(), ptrs.data()));
+        targets_dirty_ = true; /* handed to the engine with the next batch (the device may still be coming up) */
     }
     size_t n_targets() const { return targets_.size(); }
     uint64_t last_seq() const { return last_seq_; }
@@ -588,6 +624,8 @@ class Driver {
      * next_cigar: CIGAR words of the record that comes next (a record with more words than a batch holds gets a batch
      * of its own size) */
     void push(size_t next_cigar = 0) {
+        dev();
+        sync_targets();
         PinnedBatch &b = batch();
         if (b.n != 0) {
             if (b.compact_ok) {
@@ -613,9 +651,19 @@ class Driver {
                 check_ipx(h_, ipx_push_batch(h_, &v));
                 check_ipx(h_, ipx_sync_uploads(h_, 0)); /* off / tid go out of scope */
             }
-            cur_ ^= 1;
-            /* the other buffer was handed over two pushes ago: its copy must have run before it is written again */
-            check_ipx(h_, ipx_sync_uploads(h_, 1));
+            if (cur_ == 2) {
+                /* the batch that filled while the device came up: ordinary memory, not used again */
+                check_ipx(h_, ipx_sync_uploads(h_, 0));
+                b.release();
+                cur_ = 0;
+            } else {
+                cur_ ^= 1;
+                /* the other buffer was handed over two pushes ago: its copy must have run before it is written again */
+                check_ipx(h_, ipx_sync_uploads(h_, 1));
+            }
+        } else if (cur_ == 2) {
+            b.release();
+            cur_ = 0;
         }
         PinnedBatch &nb = batch();
         nb.clear(next_seq_);
@@ -644,7 +692,11 @@ class Driver {
         }
         return tid;
     }
-    ipx_handle *handle() { return h_; }
+    ipx_handle *handle() {
+        dev();
+        sync_targets();
+        return h_;
+    }
 };
 
 /* The BAM pipeline (host/bam_pipeline.h) takes a regular BAM file whenever nobody needs the records themselves (no
@@ -867,12 +919,11 @@ static void extract_whole_files(Driver &drv, const Options &opts, Outputs &out, 
 }
 
 static void extract_junctions(const Options &opts) {
+    Driver drv(opts); /* (the device comes up while the genome is read) */
     ipx::LoadedGenome genome;
     if (opts.genome_fa.size() > 0) ipx::load_genome(opts.genome_fa, genome);
     g_trace.mark("genome loaded");
     Annotator ann(opts);
-    Driver drv(opts);
-    g_trace.mark("device + pinned batches ready");
     if (opts.genome_fa.size() > 0) drv.set_genome(genome);
     Outputs out(opts);
     if (opts.bam_files.size() > 1 || opts.unsorted) {
