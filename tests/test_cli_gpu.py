@@ -53,3 +53,17 @@ def test_cuda_cli_matches_reference_binary(name, kind, n, args, genome, built, t
     assert rc_r == 0, err_r
     assert rc_g == 0, err_g
     helpers.assert_same_outputs(ref, gpu, name)
+
+
+def test_cuda_cli_on_spec_built_bam(built, tmp_path):
+    """The BAM assembled from the specification in tests/test_bam_spec_cpu.py (BGZF members of odd sizes, B arrays, a
+    CG:B:I long CIGAR) through the CUDA tool -- pipeline and record reader -- against the reference on the SAM text."""
+    import test_bam_spec_cpu as spec
+    paths = spec.write_inputs(tmp_path)
+    extra = ["--allow-anchor-indels", "-C", "0.0"]
+    rc_r, err_r, ref = helpers.run_extract(helpers.REF_EXTRACT, str(tmp_path), "ref", [paths["hand.sam"]], extra)
+    assert rc_r == 0, err_r
+    for tag in ("many.bam", "one.bam", "raw.bam", "hand.sam"):
+        rc_g, err_g, gpu = helpers.run_extract(helpers.GPU_EXTRACT, str(tmp_path), "gpu_" + tag.replace(".", "_"), [paths[tag]], extra)
+        assert rc_g == 0, err_g
+        helpers.assert_same_outputs(ref, gpu, tag)
