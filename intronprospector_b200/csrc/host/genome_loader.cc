@@ -38,6 +38,15 @@ void load_genome(const std::string &fasta, LoadedGenome &out) {
     if (const char *e = getenv("IPX_GENOME_THREADS")) threads = (unsigned)atoi(e);
     if (threads <= 1u) {
         for (int i = 0; i < n; i++) fetch(fai, i);
+    } else if (ipx_fai_in_memory(fai)) {
+        /* a bgzip-compressed FASTA was inflated whole by fai_load3: the threads share the one handle */
+        std::atomic<int> next(0);
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < threads; t++)
+            pool.emplace_back([&]() {
+                for (int i; (i = next.fetch_add(1)) < n;) fetch(fai, i);
+            });
+        for (auto &t : pool) t.join();
     } else {
         std::atomic<int> next(0);
         std::vector<std::thread> pool;

@@ -1315,7 +1315,45 @@ struct faidx_t {
     FILE *fp = nullptr;
     std::vector<fai_entry> seqs;
     std::unordered_map<std::string, int> by_name;
+    /* a bgzip-compressed FASTA (fn.gz + fn.gz.fai + fn.gz.gzi, the form the reference's documentation uses): inflated
+     * whole -- the .fai offsets count uncompressed bytes, and the one caller here reads every sequence anyway */
+    std::vector<unsigned char> mem;
+    bool in_memory = false;
 };
+
+/* every member of a gzip / BGZF file, inflated into `out`; false when the data is damaged */
+static bool inflate_members(FILE *in, std::vector<unsigned char> &out) {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, 15 + 32) != Z_OK) return false;
+    std::vector<unsigned char> ibuf(1 << 20), obuf(4 << 20);
+    bool ok = true, member_open = false;
+    for (;;) {
+        const size_t n = fread(ibuf.data(), 1, ibuf.size(), in);
+        if (n == 0) break;
+        zs.next_in = ibuf.data();
+        zs.avail_in = (uInt)n;
+        while (zs.avail_in > 0) {
+            zs.next_out = obuf.data();
+            zs.avail_out = (uInt)obuf.size();
+            member_open = true;
+            const int rc = inflate(&zs, Z_NO_FLUSH);
+            out.insert(out.end(), obuf.data(), obuf.data() + (obuf.size() - zs.avail_out));
+            if (rc == Z_STREAM_END) {
+                member_open = false;
+                if (inflateReset(&zs) != Z_OK) { ok = false; break; }
+            } else if (rc != Z_OK && rc != Z_BUF_ERROR) {
+                ok = false;
+                break;
+            } else if (rc == Z_BUF_ERROR && zs.avail_out != 0) {
+                break; /* needs more input */
+            }
+        }
+        if (!ok) break;
+    }
+    inflateEnd(&zs);
+    return ok && !member_open;
+}
 
 extern "C" int fai_build(const char *fn) {
     FILE *in = fopen(fn, "rb");
@@ -1404,8 +1442,36 @@ extern "C" faidx_t *fai_load3(const char *fn, const char *fnfai, const char *fng
         delete fai;
         return nullptr;
     }
+    unsigned char magic[18] = {0};
+    const size_t got = fread(magic, 1, sizeof(magic), fai->fp);
+    rewind(fai->fp);
+    if (got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+        /* htslib takes compressed FASTA only in BGZF form, and only with its .gzi index beside it */
+        const bool is_bgzf = got >= 18 && (magic[3] & 4) && magic[12] == 'B' && magic[13] == 'C';
+        if (!is_bgzf) {
+            fprintf(stderr, "[E::fai_load3_core] Cannot index files compressed with gzip, please use bgzip\n");
+            fai_destroy(fai);
+            return nullptr;
+        }
+        const std::string gzi = fngzi ? std::string(fngzi) : std::string(fn) + ".gzi";
+        FILE *fg = fopen(gzi.c_str(), "rb");
+        if (!fg) {
+            fprintf(stderr, "[E::fai_load3_core] Failed to open BGZF index %s: %s\n", gzi.c_str(), strerror(errno));
+            fai_destroy(fai);
+            return nullptr;
+        }
+        fclose(fg);
+        if (!inflate_members(fai->fp, fai->mem)) {
+            fprintf(stderr, "[E::fai_load3_core] Failed to inflate %s\n", fn);
+            fai_destroy(fai);
+            return nullptr;
+        }
+        fai->in_memory = true;
+    }
     return fai;
 }
+
+extern "C" int ipx_fai_in_memory(const faidx_t *fai) { return fai && fai->in_memory ? 1 : 0; }
 
 extern "C" faidx_t *fai_load(const char *fn) {
     return fai_load3(fn, nullptr, nullptr, FAI_CREATE);
@@ -1453,6 +1519,16 @@ extern "C" char *faidx_fetch_seq(const faidx_t *fai, const char *c_name, int p_b
     int64_t got = 0;
     if (want > 0 && e.line_blen > 0) {
         int64_t off = e.offset + beg / e.line_blen * e.line_len + beg % e.line_blen;
+        if (fai->in_memory) {
+            for (size_t i = (size_t)std::max<int64_t>(off, 0); i < fai->mem.size() && got < want; i++) {
+                const unsigned char ch = fai->mem[i];
+                s[got] = (char)ch;
+                got += isgraph(ch) ? 1 : 0;
+            }
+            s[got] = 0;
+            *len = (int)got;
+            return s;
+        }
         if (fseeko(fai->fp, off, SEEK_SET) != 0) { free(s); *len = -1; return nullptr; }
         /* the bases are what is left of the bytes from `off` on once non-printing characters (line ends) are dropped;
          * read in blocks -- a getc per base costs tens of nanoseconds, a whole genome minutes */

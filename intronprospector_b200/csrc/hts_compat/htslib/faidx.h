@@ -22,6 +22,9 @@ int faidx_nseq(const faidx_t *fai);
 const char *faidx_iseq(const faidx_t *fai, int i);
 int faidx_seq_len(const faidx_t *fai, const char *seq);
 char *faidx_fetch_seq(const faidx_t *fai, const char *c_name, int p_beg_i, int p_end_i, int *len);
+/* not htslib: 1 when the handle holds a bgzip-compressed FASTA inflated in memory (fetches need no file position then,
+ * so threads may share the handle) */
+int ipx_fai_in_memory(const faidx_t *fai);
 #ifdef __cplusplus
 }
 #endif

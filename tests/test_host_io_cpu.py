@@ -338,3 +338,57 @@ def _write_raw_bam_from_columns(path, names, cols, order):
                            (int(cols["flag"][r]) << 16) | len(cig), 0, -1, -1, 0) + b"r\0" + cig.astype("<u4").tobytes() + aux
         out += struct.pack("<i", len(body)) + body
     open(path, "wb").write(bytes(out))
+
+
+def _bgzip(src, dst, block=65280):
+    """bgzip + its .gzi index, from the BGZF description in SAMv1 4.1 (members of at most 64 KB, BC extra field, EOF marker)."""
+    import struct
+    import test_bam_spec_cpu as spec
+    data = open(src, "rb").read()
+    out, index, coff = b"", [], 0
+    for uoff in range(0, len(data), block):
+        if uoff:
+            index.append((coff, uoff))
+        member = spec.bgzf_block(data[uoff:uoff + block])
+        out += member
+        coff += len(member)
+    open(dst, "wb").write(out + spec.bgzf_block(b""))
+    open(dst + ".gzi", "wb").write(struct.pack("<Q", len(index)) + b"".join(struct.pack("<QQ", c, u) for c, u in index))
+
+
+def test_bgzip_compressed_genome(built, tmp_path, monkeypatch):
+    """docs/intronProspector.md:151 of the reference recommends a bgzip'ed genome (fa.gz + .fai + .gzi): the loader reads
+    the same sequences from it, the tools make the same calls, and what htslib refuses (plain gzip, no .gzi) is refused."""
+    import gzip
+    import os
+    import shutil
+    import subprocess
+    syn = Synth(200_000, kind=SHORT_UNSTRANDED, genome_len=20_000_000, n_genes=300, n_contigs=7, seed=4)
+    fa = str(tmp_path / "g.fa")
+    syn.write_genome(fa)
+    bam = str(tmp_path / "in.bam")
+    syn.write_raw_bam(bam)
+    syn.close()
+    gz = fa + ".gz"
+    _bgzip(fa, gz)
+    shutil.copy(fa + ".fai", gz + ".fai")
+    plain = _load(fa, 4, monkeypatch)
+    for threads in (1, 5):
+        assert _load(gz, threads, monkeypatch) == plain
+    for binary in (helpers.REF_EXTRACT, helpers.ORACLE_EXTRACT):
+        rc_a, err_a, a = helpers.run_extract(binary, str(tmp_path), "plain", [bam], ["-C", "0.0", "--genome-fasta=" + fa])
+        rc_b, err_b, b = helpers.run_extract(binary, str(tmp_path), "bgz", [bam], ["-C", "0.0", "--genome-fasta=" + gz])
+        assert rc_a == 0 and rc_b == 0, (err_a, err_b)
+        helpers.assert_same_outputs(a, b, os.path.basename(binary))
+        assert a["introns.tsv"].count(b"GT/AG") > 100
+    # no .gzi beside it; a gzip file that is not BGZF
+    os.rename(gz + ".gzi", gz + ".gzi.away")
+    rc, err, _ = helpers.run_extract(helpers.ORACLE_EXTRACT, str(tmp_path), "nogzi", [bam], ["--genome-fasta=" + gz])
+    assert rc != 0 and "can't open genome FASTA file or associated index" in err
+    os.rename(gz + ".gzi.away", gz + ".gzi")
+    with open(fa, "rb") as f, gzip.open(str(tmp_path / "p.fa.gz"), "wb") as g:
+        g.write(f.read())
+    shutil.copy(fa + ".fai", str(tmp_path / "p.fa.gz.fai"))
+    open(str(tmp_path / "p.fa.gz.gzi"), "wb").write(b"\0" * 8)
+    rc, err, _ = helpers.run_extract(helpers.ORACLE_EXTRACT, str(tmp_path), "gzip", [bam], ["--genome-fasta=" + str(tmp_path / "p.fa.gz")])
+    assert rc != 0 and "please use bgzip" in err
