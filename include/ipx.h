@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define IPX_ABI_VERSION 1
+#define IPX_ABI_VERSION 2
 
 #define IPX_OK 0
 #define IPX_ERR_ARG (-1)       /* bad argument */
@@ -145,6 +145,10 @@ typedef struct ipx_table {
     const uint64_t *creation_seq;  /* [n] stream position of the read that created the junction (record index << 20 |
                                       ordinal of the junction within the read): sjN numbering is the rank of this value,
                                       which lets per-GPU tables be renumbered globally.  NULL from ipx_merge_rows_fold. */
+    /* Merge only (NULL from extraction, whose motifs are five characters): the splice_sites strings of the input at
+     * their full length -- row i has site_strings[site_ids[i]]; splice_sites[i] holds its first seven characters. */
+    const char *const *site_strings;
+    const uint32_t *site_ids;      /* [n] */
 } ipx_table;
 
 /* Device-time breakdown (milliseconds, CUDA events on the library's stream) and unit counts

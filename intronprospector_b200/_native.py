@@ -95,6 +95,8 @@ class TableStruct(C.Structure):
         ("missing_targets", C.POINTER(C.c_int32)),
         ("n_missing_targets", C.c_uint64),
         ("creation_seq", C.POINTER(C.c_uint64)),
+        ("site_strings", C.POINTER(C.c_char_p)),
+        ("site_ids", C.POINTER(C.c_uint32)),
     ]
 
 

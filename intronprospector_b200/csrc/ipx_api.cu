@@ -83,6 +83,9 @@ struct HostTable {
     std::vector<uint64_t> counts, hist_off;
     std::vector<float> conf;
     std::vector<uint64_t> creation;
+    std::vector<std::string> site_text; /* merge: the input's splice_sites strings at full length */
+    std::vector<const char *> site_ptrs;
+    std::vector<uint32_t> site_ids;
     void bind() {
         if (block) { /* the columns live in the block: only what stays in vectors is rebound */
             t.missing_targets = missing.data();
@@ -107,6 +110,12 @@ struct HostTable {
         t.missing_targets = missing.data();
         t.n_missing_targets = missing.size();
         t.creation_seq = creation.empty() ? nullptr : creation.data();
+        if (!site_text.empty()) {
+            site_ptrs.resize(site_text.size());
+            for (size_t i = 0; i < site_text.size(); i++) site_ptrs[i] = site_text[i].c_str();
+            t.site_strings = site_ptrs.data();
+            t.site_ids = site_ids.data();
+        }
     }
 };
 
@@ -2135,6 +2144,9 @@ extern "C" int ipx_merge_rows_fold_part(ipx_handle *h, const ipx_merge_rows *row
     tr.mark("merge: host fold of flagged introns");
     ht->sites.assign(J * 8, 0);
     for (uint64_t i = 0; i < J; i++) snprintf(ht->sites.data() + 8 * i, 8, "%s", rows->site_strings[site[i]]);
+    ht->site_text.reserve(rows->n_site_strings);
+    for (uint32_t k = 0; k < rows->n_site_strings; k++) ht->site_text.emplace_back(rows->site_strings[k]);
+    ht->site_ids.assign(site.begin(), site.end());
     ht->ijunc.assign(J, 0);
     ht->hist_off.assign(J + 1, 0);
     ht->bind();

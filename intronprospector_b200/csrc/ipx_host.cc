@@ -123,7 +123,7 @@ int format_rows(const ipx_table *t, const char *const *names, int format, float 
     for (uint64_t i : idx) {
         if (!(t->confidence[i] >= min_confidence)) continue;
         const char *chrom = names[t->chrom[i]];
-        const char *sites = t->splice_sites + 8 * i;
+        const char *sites = (t->site_strings && t->site_ids) ? t->site_strings[t->site_ids[i]] : t->splice_sites + 8 * i;
         const uint64_t total = t->read_counts[3 * i] + t->read_counts[3 * i + 1] + t->read_counts[3 * i + 2];
         const uint64_t score = total <= 1000 ? total : 1000; /* read_count_to_bed_score (junctions.cc:162-164) */
         const uint32_t a0 = t->anchor_start[i], a1 = t->anchor_end[i], i0 = t->intron_start[i], i1 = t->intron_end[i];

@@ -52,7 +52,7 @@ ROWS_ODD = ("chr1\t100\t900\t+\t5\t1\t0\t30\t40\t1e-05\tGT/AG\tsj0\n"
             "chr1\t100\t900\t+\t+5\t1\t0\t30\t40\t1.5\tGT/AG\tsj0\n"
             "chr1\t 100\t900\t+\t5\t1\t0\t30\t40\t1.5\tGT/AG\tsj0\n"
             "chr1\t100\t900\t+\t4294967297\t1\t0\t30\t40\t1.5\tGT/AG\tsj0\n"
-            "chr3\t100\t900\t\t5\t1\t0\t30\t40\t16777217\tGTA/AGA\tsj0\n"
+            "chr3\t100\t900\t\t5\t1\t0\t30\t40\t16777217\tGTAGGTAGGT/AGAG\tsj0\n"
             "chr3\t100\t950\t.\t5\t1\t0\t200\t40\t.5\t\tsj0\n"
             "chr3\t100\t960\t+\t5\t1\t0\t2\t40\t5.\tgt/ag\tsj0\n"
             "chr3\t100\t970\t+\t0\t0\t9\t2\t40\t0.30000001192092896\tGT/AG\tsj0\n"
