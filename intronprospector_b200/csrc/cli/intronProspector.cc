@@ -543,6 +543,7 @@ class Driver {
     }
     size_t n_targets() const { return targets_.size(); }
     uint64_t last_seq() const { return last_seq_; }
+    uint64_t records_seen() const { return next_seq_; }
     int32_t last_tid() const { return last_tid_; }
     const vector<string> &targets() const { return targets_; }
 
@@ -806,6 +807,7 @@ static void extract_by_target(Driver &drv, const Options &opts, Outputs &out, An
         cur_tid = in.rec->core.tid;
         return true;
     };
+    uint64_t flushed_records = 0; /* records the engine had seen at the last per-target flush */
     for (int target = 0; !fast && target < n_targets && fatal.empty(); target++) {
         for (;;) {
             if (!pending) {
@@ -833,6 +835,21 @@ static void extract_by_target(Driver &drv, const Options &opts, Outputs &out, An
             drv.process(aln);
             if (ann.active()) ann.keep(aln, drv.last_seq(), drv.last_tid(), true, true); /* written after the flush */
             else in.pass(aln);
+        }
+        if (ann.active() && fatal.empty() && drv.records_seen() != flushed_records) {
+            flushed_records = drv.records_seen();
+            /* With the per-read side outputs the records are kept until their junctions are known: flush target by target,
+             * as the reference does (intronProspector.cc:365-369), so that no more than one target's records are held.
+             * Junction keys never cross targets and sjN keeps counting across flushes. */
+            ipx_table *tt = drv.flush();
+            ann.finish(tt, drv.targets(), in.out != NULL ? &in : NULL);
+            if (tt->status != IPX_OK) {
+                fatal = tt->error_text;
+                stop_target = target;
+            } else if (tt->n_junctions) {
+                output_junctions(tt, drv.targets(), 0, tt->n_junctions, opts.min_confidence_score, out);
+            }
+            ipx_table_free(tt);
         }
         previous_target = target;
     }
