@@ -205,7 +205,10 @@ __device__ __forceinline__ void store_event(Event *ev, uint64_t i, const Event &
 #define IPX_K2_BLOCKS 4 /* resident blocks per SM */
 #endif
 static const int FOLD_WARPS = 8;
-static const int FOLD_WAYS = 64;
+#ifndef IPX_FOLD_WAYS
+#define IPX_FOLD_WAYS 64
+#endif
+static const int FOLD_WAYS = IPX_FOLD_WAYS;
 
 struct FoldCache {
     unsigned long long key[FOLD_WAYS];
