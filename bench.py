@@ -699,14 +699,14 @@ def main():
 
             add("stranded", lambda: extraction_workload(
                 "stranded RF + 3 Gb genome in HBM + canon filter, --min-anchor-length=12, 50 M records (BASELINE configs[2], a quarter of "
-                "its records)", 50_000_000, SHORT_STRANDED, tmpdir, torch, dev, peak, 10_000_000, with_genome=True,
+                "its records)", 50_000_000, SHORT_STRANDED, tmpdir, torch, dev, peak, 20_000_000, with_genome=True,
                 cli_sets=[("canon", ["--strandness=RF", "--min-anchor-length=12", "--genome-fasta=" + os.path.join(tmpdir, "g.fa")]),
                           ("all", ["--strandness=RF", "--min-anchor-length=12", "--sj-filter=all",
                                    "--genome-fasta=" + os.path.join(tmpdir, "g.fa")])],
                 strandness=_native.STRAND_RF, min_anchor_length=12, junction_filter=_native.FILTER_CANON))
             add("long reads", lambda: extraction_workload(
                 "long reads (~10 kb, ~800 CIGAR operations), 1 M reads, --allow-anchor-indels -C 0.0 (BASELINE configs[3], a fifth of "
-                "its reads)", 1_000_000, LONG, tmpdir, torch, dev, peak, 100_000,
+                "its reads)", 1_000_000, LONG, tmpdir, torch, dev, peak, 300_000,
                 cli_sets=[("indels", ["--allow-anchor-indels", "-C", "0.0"]), ("defaults", [])], max_anchor_indel_size=36))
             add("long reads, defaults", lambda: extraction_workload(
                 "the same long reads with default options (no anchor indels)", 1_000_000, LONG, tmpdir, torch, dev, peak, 0, cli_sets=[]))

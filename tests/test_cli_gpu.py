@@ -28,6 +28,8 @@ def test_cuda_cli_reproduces_golden(case, built, fixture_dir):
 
 SYN = [
     ("short", SHORT_UNSTRANDED, 1_000_000, [], False),
+    ("short_20m", SHORT_UNSTRANDED, 20_000_000, [], False),  # bench-scale widths: several pinned batches, millions of events
+
     ("short_conf0_multi", SHORT_UNSTRANDED, 300_000, ["-C", "0.0", "--exclude=multi", "-a", "12"], False),
     ("stranded_canon", SHORT_STRANDED, 500_000, ["--strandness=RF", "--min-anchor-length=12"], True),
     ("stranded_all", SHORT_STRANDED, 300_000, ["--strandness=RF", "--sj-filter=all", "-C", "0.0"], True),
