@@ -180,19 +180,28 @@ def run_tool(binary, prefix, inputs, extra=(), env=None):
 
 
 class Background:
-    """A reference run started early and collected late (the reference is single-threaded; the box has cores to spare)."""
+    """A reference run started early and collected late (the reference is single-threaded; the box has cores to spare).
+    A thread waits for the process, so that `seconds` is the run's own wall clock, not the time until it was collected."""
 
     def __init__(self, binary, prefix, inputs, extra=()):
         self.prefix = prefix
         self.t0 = time.perf_counter()
         self.proc = subprocess.Popen(tool_command(binary, prefix, inputs, extra), stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        self._err = b""
+        self._end = None
+        self._waiter = threading.Thread(target=self._wait, daemon=True)
+        self._waiter.start()
+
+    def _wait(self):
+        _, self._err = self.proc.communicate()
+        self._end = time.perf_counter()
 
     def collect(self):
-        _, err = self.proc.communicate()
-        self.seconds = time.perf_counter() - self.t0
+        self._waiter.join()
+        self.seconds = self._end - self.t0
         if self.proc.returncode != 0:
-            raise RuntimeError("reference failed: " + err.decode(errors="replace")[-500:])
-        self.stderr = err.decode(errors="replace")
+            raise RuntimeError("reference failed: " + self._err.decode(errors="replace")[-500:])
+        self.stderr = self._err.decode(errors="replace")
         return {k: open(p, "rb").read() for k, p in outputs_of(self.prefix).items()}
 
 
