@@ -238,11 +238,14 @@ static void merge(const Options &opts) {
     tr.mark("rows read");
     /* Key ranges over the devices of this host (BASELINE config 5): every device folds the rows of a contiguous range of
      * chromosomes.  A key lives in one range, so the partial tables are simply concatenated in key order.
-     * IPX_MERGE_DEVICES=n caps the number of devices (default: all that are visible, one when the input is small);
+     * IPX_MERGE_DEVICES=n sets the number of devices (default: one per 32 M rows, at most all that are visible);
      * IPX_MERGE_PARTS=n asks for n ranges whatever the number of devices (range k runs on device k mod devices: tests);
      * IPX_DEVICE picks the device of a single-device run. */
     const int n_dev = max(1, ipx_device_count()); /* (without a device ipx_create fails below: there is no other path) */
-    int n_parts = rows.chrom.size() >= (1u << 20) ? n_dev : 1;
+    /* one device per 32 M rows: bringing a second device up costs a second or two (2.1 s each for two B200s side by side),
+     * the fold of 15 M rows 50 ms */
+    int n_parts = (int)min<uint64_t>((uint64_t)n_dev, (rows.chrom.size() + (32u << 20) - 1) / (32u << 20));
+    if (n_parts < 1) n_parts = 1;
     if (const char *e = getenv("IPX_MERGE_DEVICES")) n_parts = max(1, min(atoi(e), n_dev));
     if (const char *e = getenv("IPX_MERGE_PARTS")) n_parts = max(1, min(atoi(e), 64));
     n_parts = (int)min<size_t>((size_t)n_parts, rows.chrom_names.size());
