@@ -1,8 +1,9 @@
 /* ipx_exchange.cu -- multi-GPU exchange of partial junction tables by key range (sm_100a).
  *
  *  k_mail_*          the exchange over peer memory (NVLink / NVSwitch): every rank owns a mailbox with one slot per
- *                    source rank; the exporting kernels store the rows of the junctions another rank owns straight
- *                    into that rank's slot and disown them locally -- the rank's own share never moves.  A last small
+ *                    source rank; the exporting kernels put the rows of the junctions another rank owns together in a
+ *                    local outbox and disown them -- the rank's own share never moves -- k_mail_send copies every
+ *                    outbox slot into its owner's mailbox (coalesced 16-byte stores over NVLink), and a last small
  *                    kernel publishes the row counts and the exchange's epoch into the slot headers; the importing
  *                    side starts with a one-warp kernel that waits for the epoch of every source (a device-side
  *                    barrier: no collective, no host round trip) and then folds all sources' slots in two launches.

@@ -1,15 +1,17 @@
 /* ipx_extract.cu -- K1, the extraction kernels (sm_100a), and the expansion of compact batches.
  *
  *  k_extract_tma     the hot kernel: persistent blocks (two per SM: a producer warp + 15 worker warps) stream
- *                    tiles of EX_TILE consecutive records through a 4-stage shared-memory ring filled by TMA bulk
+ *                    tiles of EX_TILE (2048) consecutive records through a 2-stage shared-memory ring filled by TMA bulk
  *                    copies (cp.async.bulk + mbarrier), so every record column and CIGAR word is read from HBM
  *                    exactly once, coalesced, with the latency hidden behind the previous tiles' work.  The workers
  *                    (a) classify the tile's records and compact the live ones (process_alignment's skip test) into
  *                    two lists -- CIGARs of at most three operations, which can only be "aligned, N, aligned", and
  *                    longer ones -- then (b) walk the listed records with full warps (ipx_walk.cuh) and write each
- *                    junction event straight into the tile's private region of the event buffer.
+ *                    junction event straight into the tile's private region of the event buffer (the emitting lanes
+ *                    of a chunk reserve their slots with one shared-memory atomic).
  *  k_extract_sorted  K1 for long reads: records taken longest first, lean 32-bit automaton, 32-byte CIGAR groups;
- *                    k_seg_* walk outliers (tens of thousands of operations) segment by segment.
+ *                    k_seg_* walk outliers (tens of thousands of operations) segment by segment.  Long-read batches
+ *                    are cut into tiles of LONG_TILE (256) records: a tile is K2's unit of work.
  *  k_extract_simple  K1 for what is left: the last partial tile, columns that are not 16-byte aligned.
  *
  * Reference semantics: SURVEY.md section 8(a) A1-A5 (junctions_extractor.cc:49-95,124-319,322-401,533-549).
