@@ -737,16 +737,6 @@ static void output_junctions(const ipx_table *t, const vector<string> &targets, 
     emit(out.intron_call, IPX_FMT_INTRON_TSV);
 }
 
-/* rows of one target are contiguous in the key-ordered table */
-static void target_rows(const ipx_table *t, int32_t tid, uint64_t *begin, uint64_t *end) {
-    uint64_t b = 0;
-    while (b < t->n_junctions && t->chrom[b] != tid) b++;
-    uint64_t e = b;
-    while (e < t->n_junctions && t->chrom[e] == tid) e++;
-    *begin = b;
-    *end = e;
-}
-
 /* extract_junctions_by_target (intronProspector.cc:356-371) with identify_junctions_for_target /
  * process_target_alignment (junctions_extractor.cc:637-664) */
 static void extract_by_target(Driver &drv, const Options &opts, Outputs &out, Annotator &ann) {
@@ -884,7 +874,6 @@ static void extract_by_target(Driver &drv, const Options &opts, Outputs &out, An
         if (pending) in.pass(in.rec);
         while (!eof && in.read()) in.pass(in.rec);
     }
-    (void)target_rows;
 }
 
 /* extract_junctions_unsorted / extract_junctions_multiple (intronProspector.cc:375-401) */
