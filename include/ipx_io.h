@@ -54,6 +54,13 @@ int ipxio_faidx_build(const char *fasta);
  * (IPX_FILTER_*), produce merge rows and the chromosome name list.  On a malformed file the rows parsed so far
  * are kept, the function returns IPX_ERR_ARG and ipxio_last_error() holds the reference's message. */
 int ipxio_calls_load(const char *const *paths, int32_t n_paths, int32_t junction_filter, ipxio_calls **out);
+/* The same with the rows of every file tokenised by `tokenize` -- ipx_tsv_tokenize of ipx.h bound to a device, or any
+ * stand-in with its contract -- and only the rows it flags parsed here (this library itself needs no CUDA).  `rows_free`
+ * releases what `tokenize` returned.  Rows, dictionaries and errors are those of ipxio_calls_load. */
+typedef int (*ipxio_tokenize_fn)(const char *bytes, uint64_t n_bytes, const ipx_tsv_columns *columns, ipx_tsv_rows **out);
+typedef void (*ipxio_rows_free_fn)(ipx_tsv_rows *rows);
+int ipxio_calls_load_tokenized(const char *const *paths, int32_t n_paths, int32_t junction_filter, ipxio_tokenize_fn tokenize,
+                               ipxio_rows_free_fn rows_free, ipxio_calls **out);
 void ipxio_calls_free(ipxio_calls *c);
 const ipx_merge_rows *ipxio_calls_rows(const ipxio_calls *c);
 int32_t ipxio_calls_n_chroms(const ipxio_calls *c);

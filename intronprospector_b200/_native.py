@@ -160,7 +160,7 @@ ABI_SYMBOLS = [
 IO_SYMBOLS = [
     "ipxio_last_error", "ipxio_open", "ipxio_close", "ipxio_n_targets", "ipxio_target_name", "ipxio_read_batch",
     "ipxio_genome_load", "ipxio_genome_free", "ipxio_genome_n_seqs", "ipxio_genome_names", "ipxio_genome_lengths",
-    "ipxio_genome_seqs", "ipxio_faidx_build", "ipxio_calls_load", "ipxio_calls_free", "ipxio_calls_rows",
+    "ipxio_genome_seqs", "ipxio_faidx_build", "ipxio_calls_load", "ipxio_calls_load_tokenized", "ipxio_calls_free", "ipxio_calls_rows",
     "ipxio_calls_n_chroms", "ipxio_calls_chroms", "ipxio_pipeline_read",
 ]
 

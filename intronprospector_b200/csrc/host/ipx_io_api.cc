@@ -195,6 +195,25 @@ extern "C" int ipxio_calls_load(const char *const *paths, int32_t n_paths, int32
     return rc;
 }
 
+extern "C" int ipxio_calls_load_tokenized(const char *const *paths, int32_t n_paths, int32_t junction_filter, ipxio_tokenize_fn tokenize,
+                                          ipxio_rows_free_fn rows_free, ipxio_calls **out) {
+    if (!tokenize || !rows_free) return IPX_ERR_ARG;
+    ipxio_calls *c = new ipxio_calls();
+    *out = c;
+    int rc = IPX_OK;
+    try {
+        std::vector<std::string> files;
+        for (int32_t i = 0; i < n_paths; i++) files.push_back(paths[i]);
+        const ipx::TsvTokenizer tok{malloc, free, tokenize, rows_free, nullptr};
+        ipx::load_calls_tsvs(files, junction_filter, c->rows, tok);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        rc = IPX_ERR_ARG;
+    }
+    c->rows.bind();
+    return rc;
+}
+
 extern "C" void ipxio_calls_free(ipxio_calls *c) { delete c; }
 extern "C" const ipx_merge_rows *ipxio_calls_rows(const ipxio_calls *c) { return &c->rows.rows; }
 extern "C" int32_t ipxio_calls_n_chroms(const ipxio_calls *c) { return (int32_t)c->rows.chrom_names.size(); }
