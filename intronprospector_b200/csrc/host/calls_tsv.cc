@@ -323,47 +323,6 @@ static bool load_calls_tsv_tokenized(const std::string &path, int junction_filte
     return true;
 }
 
-namespace {
-
-/* append the rows of one file, parsed into dictionaries of its own, translating them into the common dictionaries:
- * names new to `out` get their numbers in the order the file first used them, as if it had been parsed into `out` */
-void append_part(const CallsRows &part, CallsRows &out) {
-    std::vector<int32_t> chrom_map(part.chrom_names.size());
-    for (size_t i = 0; i < part.chrom_names.size(); i++) {
-        auto it = out.chrom_index.find(part.chrom_names[i]);
-        if (it == out.chrom_index.end()) {
-            it = out.chrom_index.emplace(part.chrom_names[i], (int32_t)out.chrom_names.size()).first;
-            out.chrom_names.push_back(part.chrom_names[i]);
-        }
-        chrom_map[i] = it->second;
-    }
-    std::vector<uint32_t> site_map(part.site_strings.size());
-    for (size_t i = 0; i < part.site_strings.size(); i++) {
-        auto it = out.site_index.find(part.site_strings[i]);
-        if (it == out.site_index.end()) {
-            it = out.site_index.emplace(part.site_strings[i], (uint32_t)out.site_strings.size()).first;
-            out.site_strings.push_back(part.site_strings[i]);
-        }
-        site_map[i] = it->second;
-    }
-    const size_t n0 = out.chrom.size(), n = part.chrom.size();
-    out.chrom.resize(n0 + n);
-    out.sites.resize(n0 + n);
-    for (size_t i = 0; i < n; i++) {
-        out.chrom[n0 + i] = chrom_map[part.chrom[i]];
-        out.sites[n0 + i] = site_map[part.sites[i]];
-    }
-    out.i0.insert(out.i0.end(), part.i0.begin(), part.i0.end());
-    out.i1.insert(out.i1.end(), part.i1.begin(), part.i1.end());
-    out.a0.insert(out.a0.end(), part.a0.begin(), part.a0.end());
-    out.a1.insert(out.a1.end(), part.a1.begin(), part.a1.end());
-    out.strand.insert(out.strand.end(), part.strand.begin(), part.strand.end());
-    out.counts.insert(out.counts.end(), part.counts.begin(), part.counts.end());
-    out.conf.insert(out.conf.end(), part.conf.begin(), part.conf.end());
-}
-
-}  // namespace
-
 static void load_calls_tsvs_impl(const std::vector<std::string> &paths, int junction_filter, CallsRows &out, const TsvTokenizer *tok);
 
 void load_calls_tsvs(const std::vector<std::string> &paths, int junction_filter, CallsRows &out) {
@@ -412,11 +371,55 @@ static void load_calls_tsvs_impl(const std::vector<std::string> &paths, int junc
     std::vector<std::thread> pool;
     for (unsigned t = 0; t < threads; t++) pool.emplace_back(work);
     for (auto &t : pool) t.join();
-    for (size_t i = 0; i < paths.size(); i++) {
-        append_part(parts[i]->rows, out);
-        if (parts[i]->failed) throw std::runtime_error(parts[i]->error);
-        parts[i].reset(); /* give the file's rows back before the next one is appended */
+    /* The files' rows into the common columns: the dictionaries are merged file by file (names new to `out` get their
+     * numbers in the order the files first used them, as if everything had been parsed into `out`), which also gives
+     * every file its place in the columns; the rows are then copied, and renumbered, by the pool.  Everything up to and
+     * including the first bad file is used. */
+    size_t n_use = paths.size();
+    for (size_t i = 0; i < paths.size(); i++)
+        if (parts[i]->failed) {
+            n_use = i + 1;
+            break;
+        }
+    std::vector<std::vector<int32_t>> chrom_map(n_use);
+    std::vector<std::vector<uint32_t>> site_map(n_use);
+    std::vector<size_t> at(n_use + 1, out.chrom.size());
+    for (size_t i = 0; i < n_use; i++) {
+        const CallsRows &part = parts[i]->rows;
+        chrom_map[i].resize(part.chrom_names.size());
+        for (size_t k = 0; k < part.chrom_names.size(); k++) chrom_map[i][k] = chrom_id(out, part.chrom_names[k]);
+        site_map[i].resize(part.site_strings.size());
+        for (size_t k = 0; k < part.site_strings.size(); k++) site_map[i][k] = site_id(out, part.site_strings[k]);
+        at[i + 1] = at[i] + part.chrom.size();
     }
+    const size_t total = at[n_use];
+    out.chrom.resize(total); out.sites.resize(total); out.i0.resize(total); out.i1.resize(total); out.a0.resize(total);
+    out.a1.resize(total); out.strand.resize(total); out.conf.resize(total); out.counts.resize(3 * total);
+    std::atomic<size_t> next_copy(0);
+    auto copy = [&]() {
+        for (size_t i; (i = next_copy.fetch_add(1)) < n_use;) {
+            const CallsRows &part = parts[i]->rows;
+            const size_t n0 = at[i], n = part.chrom.size();
+            for (size_t r = 0; r < n; r++) {
+                out.chrom[n0 + r] = chrom_map[i][part.chrom[r]];
+                out.sites[n0 + r] = site_map[i][part.sites[r]];
+            }
+            std::copy(part.i0.begin(), part.i0.end(), out.i0.begin() + n0);
+            std::copy(part.i1.begin(), part.i1.end(), out.i1.begin() + n0);
+            std::copy(part.a0.begin(), part.a0.end(), out.a0.begin() + n0);
+            std::copy(part.a1.begin(), part.a1.end(), out.a1.begin() + n0);
+            std::copy(part.strand.begin(), part.strand.end(), out.strand.begin() + n0);
+            std::copy(part.conf.begin(), part.conf.end(), out.conf.begin() + n0);
+            std::copy(part.counts.begin(), part.counts.end(), out.counts.begin() + 3 * n0);
+            parts[i].reset(); /* give the file's rows back */
+        }
+    };
+    std::string error = n_use && parts[n_use - 1]->failed ? parts[n_use - 1]->error : std::string();
+    const bool failed = n_use && parts[n_use - 1]->failed;
+    pool.clear();
+    for (unsigned t = 0; t < threads && t < n_use; t++) pool.emplace_back(copy);
+    for (auto &t : pool) t.join();
+    if (failed) throw std::runtime_error(error);
 }
 
 }  // namespace ipx
